@@ -1,0 +1,561 @@
+// bvg_bvar_sweep.cuh -- one chain of the constant-parameter BVAR Gibbs sampler, all sweeps on-chip.
+//
+// Restates the sweep of the reference's monolithic loop (src/bvaralg.cpp:292-560) for pure VAR regressors
+// (z = kron(x_t', I_k), R/gen_var.R:281), exploiting the structure the reference materialises densely:
+//   z' D z = (X X') (x) Sigma^-1               (const Sigma)     bvaralg.cpp:305   [post_normal.cpp:86 identity]
+//          = interleave_i( sum_t e^{-h_ti} x_t x_t' )   (SV, diagonal Sigma_t)     bvaralg.cpp:494,305
+//   z' D y = vec(Sigma^-1 Y X')                                    bvaralg.cpp:306
+//   a = P^-1 b + chol(P)^-1 eps  ==  L^-T (L^-1 b + eps),  P = L L'                bvaralg.cpp:306-307
+//   u u'  = SSE_ols + (A - A_ols) XX' (A - A_ols)'   (exact; "moment" residual mode)   bvaralg.cpp:364,511
+// Sweep order is the reference's: coefficients (with last sweep's Sigma^-1) -> SSVS | BVS -> residuals ->
+// SV | gamma | Wishart -> store.
+#pragma once
+#include "bvg_linalg.cuh"
+
+namespace bvg {
+
+enum SigmaType : int { SIG_WISHART = 0, SIG_GAMMA = 1, SIG_SV = 2 };
+enum VarSel : int { VS_NONE = 0, VS_SSVS = 1, VS_BVS = 2 };
+enum ResidMode : int { RES_DIRECT = 1, RES_MOMENT = 2 };
+
+// Model constants, shared by all chains of one model.  All pointers are device (or host, in tests/emu) memory.
+struct BvarModel {
+  int k, T, M, n;
+  int sigma_type, varsel, resid_mode;
+  int n_mix;                       // 7 (KSC-1998) or 10 (OCSN-2007)
+  const double* Y;                 // k x T  col-major: y_it at i + k t            (bvaralg.cpp:10)
+  const double* X;                 // M x T  col-major: x_jt at j + M t            (Z' of gen_var)
+  const double* XX;                // M x M  X X'
+  const double* YX;                // k x M  Y X'   col-major (i + k j)
+  const double* Aols;              // k x M  OLS coefficients (moment mode)
+  const double* SSE;               // k x k  OLS residual cross product (moment mode)
+  const double* mu;                // n      prior mean
+  const double* vi_off;            // n x n packed lower, off-diagonal part of V^-1 (diag slots zero) or nullptr
+  const double* vmu_off;           // n      vi_off * mu (or nullptr)
+  const double* vdiag0;            // n      initial diagonal of V^-1
+  // SSVS / BVS
+  const double* tau0; const double* tau1; const double* inprior;     // n each
+  const unsigned char* include;    // n  (1 = position takes part in the selection)
+  // error variance prior
+  double wish_df_post;             // df + T                                         (bvaralg.cpp:234)
+  const double* S0;                // k x k                                          (bvaralg.cpp:235)
+  const double* g_shape_post;      // k   shape + T/2  (gamma and SV)                (bvaralg.cpp:223,239)
+  const double* g_rate;            // k
+  const double* sv_mu;             // k   prior mean of h_init
+  const double* sv_vi;             // k x k prior precision of h_init (col-major)
+  const double* sv_const;          // k   offset constant c                          (bvaralg.cpp:229)
+  const double* mix_p; const double* mix_mu; const double* mix_s2;   // n_mix each
+  const double* omega_off;         // k x k off-diagonal part of the initial Sigma^-1 (gamma prior), zero diagonal
+};
+
+// Per-chain persistent state in global memory (between kernel launches), doubles:
+//   [0, k*k)            Sigma^-1 (col-major)           (const Sigma)          | unused for SV
+//   then n              vdiag   (diagonal of V^-1, changed by SSVS)
+//   then n              lambda  (0/1)
+//   SV only: then T*k   h (col-major T x k: h_ti at t + T i), then k sigma_h, then k h_init
+BVG_HD int bvar_state_len(int k, int T, int n, int sigma_type) {
+  return k * k + 2 * n + (sigma_type == SIG_SV ? T * k + 2 * k : 0);
+}
+
+// Shared-memory doubles needed per chain.
+BVG_HD int bvar_smem_len(int k, int T, int M, int n, int sigma_type, int resid_mode) {
+  int len = tri(n) + 5 * n           // L, w, a, dinv, vdiag, lam
+            + 6 * k * k + 2 * k      // sig, S, 4 k x k work, kd, kv
+            + 2 * k * M;             // Dm, Wm
+  if (resid_mode == RES_DIRECT || sigma_type == SIG_SV) len += k * T;                 // U
+  if (sigma_type == SIG_SV) len += 3 * k * T + k * tri(M) + 2 * k;                    // h, ew, sv work, GW, sigma_h, h_init
+  return len;
+}
+
+struct BvarOut {
+  double* coef;     // [chain][iter][n]
+  double* sigma;    // [chain][iter][k*k]  or  [chain][iter][T][k*k] (SV)
+  double* lambda;   // [chain][iter][n] or nullptr
+  double* sigma_h;  // [chain][iter][k]  (SV) or nullptr
+  int* status;      // [chain]
+  long long iters;  // retained iterations (stride computation)
+};
+
+// ---- small k x k helpers (full col-major storage, group-parallel) -----------------------------------------
+// lower Cholesky of a full symmetric k x k matrix A into packed Lp (+dinv), then true diagonal written.
+template <class Grp>
+BVG_HD void small_chol(const Grp& g, const double* A, double* Lp, double* dinv, int k, int& fail) {
+  for (int e = g.tid(); e < tri(k); e += g.size()) {
+    int i = 0; while (tri(i + 1) <= e) ++i;
+    const int j = e - tri(i);
+    Lp[e] = A[i + k * j];
+  }
+  g.sync();
+  chol_crout(g, Lp, dinv, (double*)nullptr, k, fail);
+}
+
+// The inverse-Wishart block (bvaralg.cpp:511-514,528): given S = S0 + u u' (full, col-major) draw
+//   Sigma^-1 = (A D)' (A D),  D = chol(S^-1) upper,  A = Bartlett factor  (arma::wishrnd convention)
+// and return Sigma = (Sigma^-1)^-1 when `want_sigma`.  Work arrays: W1..W4 (k*k each), kd (k).
+template <class Grp>
+BVG_HD void wishart_block(const Grp& g, const ChainRng& rng, int sweep, int k, double df_post, const double* S,
+                          double* sig, double* sigma_out, bool want_sigma, double* W1, double* W2, double* W3,
+                          double* W4, double* kd, int& fail) {
+  const int G = g.size(), tid = g.tid();
+  // 1. S = Ls Ls'   (W1 packed, kd)
+  small_chol(g, S, W1, kd, k, fail);
+  // 2. Minv = Ls^-1 (W2 packed);  Sbar = S^-1 = Minv' Minv (W3 packed lower)
+  tri_inverse(g, W1, kd, W2, k);
+  mtm_lower(g, W2, W3, k);
+  // 3. Sbar = Ld Ld'  (in place in W3, kd);  D = Ld' upper
+  chol_crout(g, W3, kd, (double*)nullptr, k, fail);
+  fix_diag(g, W3, kd, k);
+  // 4. Bartlett factor A (upper, full col-major in W4): A_ii = sqrt(chi2(df - i)), strict upper N(0,1) filled
+  //    column by column (column i holds i normals)
+  for (int e = tid; e < k * k; e += G) {
+    const int r = e % k, c = e / k;
+    double v = 0.0;
+    if (r == c) v = sqrt(rng.chi2(VB_WISH_C, sweep, r, df_post - (double)r));
+    else if (r < c) v = rng.normal(VB_WISH_N, sweep, tri(c - 1) + r);
+    W4[e] = v;
+  }
+  g.sync();
+  // 5. B = A D (upper, full col-major in W1): B_rc = sum_{m=r..c} A_rm D_mc, D_mc = Ld_cm
+  for (int e = tid; e < k * k; e += G) {
+    const int r = e % k, c = e / k;
+    double s = 0.0;
+    if (r <= c) for (int m = r; m <= c; ++m) s = fma(W4[r + k * m], W3[tri(c) + m], s);
+    W1[e] = s;
+  }
+  g.sync();
+  // 6. Sigma^-1 = B' B
+  for (int e = tid; e < k * k; e += G) {
+    const int i = e % k, j = e / k;
+    const int mm = i < j ? i : j;
+    double s = 0.0;
+    for (int m = 0; m <= mm; ++m) s = fma(W1[m + k * i], W1[m + k * j], s);
+    sig[e] = s;
+  }
+  g.sync();
+  if (want_sigma) {
+    // Sigma = B^-1 B^-T.  Binv (upper) by columns: column c of B^-1 solves B x = e_c (back substitution).
+    for (int c = tid; c < k; c += G) {
+      for (int r = k - 1; r >= 0; --r) {
+        double s = (r == c) ? 1.0 : 0.0;
+        for (int m = r + 1; m <= c; ++m) s = fma(-W1[r + k * m], W2[m + k * c], s);
+        W2[r + k * c] = (r <= c) ? s / W1[r + k * r] : 0.0;
+      }
+    }
+    g.sync();
+    for (int e = tid; e < k * k; e += G) {
+      const int i = e % k, j = e / k;
+      const int m0 = i > j ? i : j;
+      double s = 0.0;
+      for (int m = m0; m < k; ++m) s = fma(W2[i + k * m], W2[j + k * m], s);
+      sigma_out[e] = s;
+    }
+    g.sync();
+  }
+}
+
+// general symmetric positive definite k x k inverse (full col-major), used for storing Sigma under the gamma prior
+template <class Grp>
+BVG_HD void small_spd_inverse(const Grp& g, const double* A, double* out, double* W1, double* W2, double* W3,
+                              double* kd, int k, int& fail) {
+  small_chol(g, A, W1, kd, k, fail);
+  tri_inverse(g, W1, kd, W2, k);
+  mtm_lower(g, W2, W3, k);
+  for (int e = g.tid(); e < k * k; e += g.size()) {
+    const int i = e % k, j = e / k;
+    out[e] = (i >= j) ? W3[tri(i) + j] : W3[tri(j) + i];
+  }
+  g.sync();
+}
+
+// ---- the KSC-1998 / OCSN-2007 step for all k series of one chain (stochvol_ksc1998.cpp:89-105) -----------------
+// U (k x T col-major residuals) is overwritten by y* = log(u^2 + c).  h: T x k col-major (t + T i).
+// Work: pr (k*T), rh (k*T).  The indicator step is time-parallel; the tridiagonal factor/solve is one thread
+// per series.
+template <class Grp>
+BVG_HD void sv_step(const Grp& g, const ChainRng& rng, int sweep, const BvarModel& m, double* U, double* h,
+                    const double* sigma_h, const double* h_init, double* pr, double* rh) {
+  const int G = g.size(), tid = g.tid(), k = m.k, T = m.T, J = m.n_mix;
+  for (int e = tid; e < k * T; e += G) {
+    const int i = e % k, t = e / k;
+    const double u = U[e];
+    const double ys = log(u * u + m.sv_const[i]);                                  // :91
+    const double ht = h[t + T * i];
+    double q[10];
+    double qs = 0.0;
+    for (int j = 0; j < J; ++j) {
+      const double sd = sqrt(m.mix_s2[j]);
+      const double z = (ys - (ht + m.mix_mu[j])) / sd;
+      q[j] = m.mix_p[j] * (exp(-0.5 * (z * z)) / (sd * 2.5066282746310002));     // :94 (arma::normpdf)
+      qs += q[j];
+    }
+    const double uu = rng.uniform(VB_SV_U, sweep, i * T + t);
+    double cum = 0.0;
+    int cnt = 0;
+    for (int j = 0; j < J; ++j) {
+      cum += q[j] / qs;                                                            // :95-96
+      cnt += (uu < cum) ? 1 : 0;
+    }
+    int s = J - cnt;
+    if (s > J - 1) s = J - 1;                                                      // reference: out of bounds
+    const double p = 1.0 / m.mix_s2[s];                                            // :101
+    pr[i * T + t] = p;
+    rh[i * T + t] = p * (ys - m.mix_mu[s]);                                        // :103 sigs * (y - mu_s)
+  }
+  g.sync();
+  for (int i = tid; i < k; i += G) {
+    const double si = 1.0 / sigma_h[i];                                            // hh / sigma(i), :99
+    double* p = pr + i * T;
+    double* r = rh + i * T;
+    // lower bidiagonal Cholesky of tridiag(diag = {2,...,2,1} si + p_t, off = -si); forward solve fused
+    double mprev = 0.0, wprev = 0.0;
+    for (int t = 0; t < T; ++t) {
+      const double dg = ((t < T - 1) ? 2.0 : 1.0) * si + p[t];
+      const double l = sqrt(dg - mprev * mprev);
+      double b = r[t];
+      if (t == 0) b += si * h_init[i];                                             // hh * 1 * h_init = e_1 h_init
+      const double w = (b - mprev * wprev) / l;
+      p[t] = l;                         // keep l_t
+      r[t] = w + rng.normal(VB_SV_N, sweep, i * T + t);                           // w + eps
+      mprev = -si / l;                  // m_t = L_{t+1,t}
+      wprev = w;
+    }
+    // back substitution L' h = w + eps
+    double hn = 0.0;
+    for (int t = T - 1; t >= 0; --t) {
+      const double l = p[t];
+      const double mt = -si / l;
+      const double v = (t == T - 1) ? r[t] / l : (r[t] - mt * hn) / l;
+      h[t + T * i] = v;
+      hn = v;
+    }
+  }
+  g.sync();
+}
+
+// ---- the chain ---------------------------------------------------------------------------------------------
+template <class Grp>
+BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, double* state, double* sm,
+                       const BvarOut& out, long long chain_local, int sweep_begin, int sweep_end, int burnin) {
+  const int G = g.size(), tid = g.tid();
+  const int k = m.k, T = m.T, M = m.M, n = m.n, kk = k * k;
+  const bool sv = m.sigma_type == SIG_SV;
+  const bool direct = (m.resid_mode == RES_DIRECT) || sv;
+  // carve shared memory
+  double* L = sm;           sm += tri(n);
+  double* w = sm;           sm += n;
+  double* a = sm;           sm += n;
+  double* dinv = sm;        sm += n;
+  double* vdiag = sm;       sm += n;
+  double* lam = sm;         sm += n;
+  double* sig = sm;         sm += kk;
+  double* S = sm;           sm += kk;
+  double* W1 = sm;          sm += kk;
+  double* W2 = sm;          sm += kk;
+  double* W3 = sm;          sm += kk;
+  double* W4 = sm;          sm += kk;
+  double* kd = sm;          sm += k;
+  double* kv = sm;          sm += k;
+  double* Dm = sm;          sm += k * M;
+  double* Wm = sm;          sm += k * M;
+  double* U = nullptr; double* h = nullptr; double* ew = nullptr; double* svw = nullptr; double* GW = nullptr;
+  double* sigma_h = nullptr; double* h_init = nullptr;
+  if (direct) { U = sm; sm += k * T; }
+  if (sv) {
+    h = sm; sm += k * T;  ew = sm; sm += k * T;  svw = sm; sm += k * T;  GW = sm; sm += k * tri(M);
+    sigma_h = sm; sm += k;  h_init = sm; sm += k;
+  }
+  int fail = 0;
+
+  // load state
+  double* st_sig = state;
+  double* st_vd = state + kk;
+  double* st_lam = st_vd + n;
+  double* st_h = st_lam + n;
+  for (int e = tid; e < kk; e += G) sig[e] = st_sig[e];
+  for (int e = tid; e < n; e += G) { vdiag[e] = st_vd[e]; lam[e] = st_lam[e]; }
+  if (sv) {
+    for (int e = tid; e < T * k; e += G) h[e] = st_h[e];
+    for (int e = tid; e < k; e += G) { sigma_h[e] = st_h[T * k + e]; h_init[e] = st_h[T * k + k + e]; }
+  }
+  g.sync();
+
+  for (int sweep = sweep_begin; sweep < sweep_end; ++sweep) {
+    const bool keep = sweep >= burnin;
+    const long long pos = (long long)sweep - burnin;
+
+    if (n > 0) {
+      // ---- precision P = V^-1 + Lambda (z'Dz) Lambda and rhs b = V^-1 mu + Lambda z'Dy  (bvaralg.cpp:303-306)
+      if (sv) {
+        // :494, ew[t + T i]; the very first sweep uses h.row(0) for every period (bvaralg.cpp:230-231,246)
+        for (int e = tid; e < k * T; e += G) ew[e] = 1.0 / exp(sweep == 0 ? h[T * (e / T)] : h[e]);
+        g.sync();
+        for (int e = tid; e < k * tri(M); e += G) {
+          const int i = e / tri(M), f = e % tri(M);
+          int j = 0; while (tri(j + 1) <= f) ++j;
+          const int j2 = f - tri(j);
+          double s = 0.0;
+          for (int t = 0; t < T; ++t) s = fma(m.X[j + M * t] * m.X[j2 + M * t], ew[t + T * i], s);
+          GW[e] = s;
+        }
+        for (int r = tid; r < n; r += G) {
+          const int j = r / k, i = r % k;
+          double s = 0.0;
+          for (int t = 0; t < T; ++t) s = fma(m.X[j + M * t] * ew[t + T * i], m.Y[i + k * t], s);
+          w[r] = s;
+        }
+        g.sync();
+      } else {
+        for (int r = tid; r < n; r += G) {
+          const int j = r / k, i = r % k;
+          double s = 0.0;
+          for (int i2 = 0; i2 < k; ++i2) s = fma(sig[i + k * i2], m.YX[i2 + k * j], s);   // (Sigma^-1 Y X')_ij
+          w[r] = s;
+        }
+      }
+      const bool bvs = m.varsel == VS_BVS;
+      for (int r = tid; r < n; r += G) {
+        const int j = r / k, i = r % k;
+        double* Lr = L + tri(r);
+        const double lr = bvs ? lam[r] : 1.0;
+        int j2 = 0, i2 = 0;
+        for (int c = 0; c <= r; ++c) {
+          double gv;
+          if (sv) gv = (i == i2) ? GW[i * tri(M) + tri(j) + j2] : 0.0;
+          else gv = m.XX[j + M * j2] * sig[i + k * i2];
+          if (bvs) gv *= lr * lam[c];
+          if (m.vi_off != nullptr) gv += m.vi_off[tri(r) + c];
+          if (c == r) gv += vdiag[r];
+          Lr[c] = gv;
+          if (++i2 == k) { i2 = 0; ++j2; }
+        }
+        double b = w[r] * lr + vdiag[r] * m.mu[r];
+        if (m.vmu_off != nullptr) b += m.vmu_off[r];
+        w[r] = b;
+      }
+      g.sync();
+      // ---- a = L^-T (L^-1 b + eps)                                                  (bvaralg.cpp:306-307)
+      chol_crout(g, L, dinv, w, n, fail);
+      for (int r = tid; r < n; r += G) w[r] += rng.normal(VB_COEF_N, sweep, r);
+      g.sync();
+      back_solve_lt(g, L, dinv, w, a, n);
+
+      // ---- SSVS (bvaralg.cpp:314-331)
+      if (m.varsel == VS_SSVS) {
+        for (int r = tid; r < n; r += G) {
+          if (!m.include[r]) continue;
+          const double t0 = m.tau0[r], t1 = m.tau1[r], pi = m.inprior[r];
+          const double t0sq = t0 * t0, t1sq = t1 * t1, ar = a[r];
+          const double u0 = 1.0 / t0 * exp(-((ar * ar) / (2.0 * t0sq))) * (1.0 - pi);     // :316
+          const double u1 = 1.0 / t1 * exp(-((ar * ar) / (2.0 * t1sq))) * pi;             // :317
+          const double p = u1 / (u0 + u1);
+          const double ld = bernoulli_rbinom(p, rng.uniform(VB_SSVS_U, sweep, r));
+          lam[r] = ld;
+          vdiag[r] = (ld == 0.0) ? 1.0 / t0sq : 1.0 / t1sq;                               // :324-328
+        }
+        g.sync();
+      }
+    }
+
+    // ---- residuals and BVS -------------------------------------------------------------------------------
+    // Dm = A_AG - A_ols  (moment mode)  /  U = Y - A_AG X  (direct mode), with A_AG = Lambda a (stale, :335)
+    const bool bvs = (m.varsel == VS_BVS) && n > 0;
+    if (direct) {
+      for (int e = tid; e < k * T; e += G) {
+        const int i = e % k, t = e / k;
+        double s = m.Y[e];
+        for (int j = 0; j < M; ++j) {
+          const double av = bvs ? lam[j * k + i] * a[j * k + i] : a[j * k + i];
+          s = fma(-av, m.X[j + M * t], s);
+        }
+        U[e] = s;
+      }
+      g.sync();
+    } else {
+      for (int r = tid; r < n; r += G) Dm[r] = (bvs ? lam[r] * a[r] : a[r]) - m.Aols[r];  // r = i + k j
+      g.sync();
+      for (int r = tid; r < n; r += G) {
+        const int j = r / k, i = r % k;
+        double s = 0.0;
+        for (int j2 = 0; j2 < M; ++j2) s = fma(Dm[i + k * j2], m.XX[j2 + M * j], s);
+        Wm[r] = s;                                                                        // (D XX')_ij
+      }
+      g.sync();
+    }
+    if (bvs) {
+      // Korobilis (2013) indicator update, coefficient-parallel rank-1 form:
+      //   r_theta = r_base + z_j delta,  delta0 = lambda_j a_j, delta1 = (lambda_j - 1) a_j,  r_base = y - z a_AG
+      //   q(delta) = q_base + 2 delta c_j + delta^2 g_j,   c_j = z_j' D r_base,  g_j = z_j' D z_j
+      //   l1 - l0 = -(q1 - q0)/2 + (lp1 - lp0)                                          (bvaralg.cpp:342-350)
+      for (int r = tid; r < n; r += G) {
+        double newlam = lam[r];
+        if (m.include[r]) {
+          const int j = r / k, i = r % k;
+          const double lp0 = log(1.0 - m.inprior[r]), lp1 = log(m.inprior[r]);            // :124-125
+          const double g1 = log(rng.uniform(VB_BVS_U1, sweep, r));                        // :338
+          const bool gate = (lam[r] == 1.0) ? (g1 < lp1) : (g1 < lp0);                    // :339-341
+          if (gate) {
+            double cj = 0.0, gj = 0.0;
+            if (direct) {
+              if (sv) {
+                for (int t = 0; t < T; ++t) {
+                  const double xw = m.X[j + M * t] * ew[t + T * i];
+                  cj = fma(xw, U[i + k * t], cj);
+                  gj = fma(xw, m.X[j + M * t], gj);
+                }
+              } else {
+                for (int t = 0; t < T; ++t) {
+                  double v = 0.0;
+                  for (int i2 = 0; i2 < k; ++i2) v = fma(sig[i + k * i2], U[i2 + k * t], v);
+                  cj = fma(m.X[j + M * t], v, cj);
+                }
+                gj = m.XX[j + M * j] * sig[i + k * i];
+              }
+            } else {
+              // c_j = [Sigma^-1 (Y - A_AG X) X']_ij = -[Sigma^-1 D XX']_ij
+              for (int i2 = 0; i2 < k; ++i2) cj = fma(-sig[i + k * i2], Wm[i2 + k * j], cj);
+              gj = m.XX[j + M * j] * sig[i + k * i];
+            }
+            const double ar = a[r];
+            const double d0 = lam[r] * ar, d1 = (lam[r] - 1.0) * ar;
+            const double dq = 2.0 * (d1 - d0) * cj + (d1 * d1 - d0 * d0) * gj;           // q1 - q0
+            const double bayes = -0.5 * dq + (lp1 - lp0);
+            const double g2 = log(rng.uniform(VB_BVS_U2, sweep, r));                      // :351
+            newlam = (bayes >= g2) ? 1.0 : 0.0;                                           // :352-356
+          }
+        }
+        w[r] = newlam;      // w is free here; commit after everyone has read lam
+      }
+      g.sync();
+      // a = Lambda a (:359); residuals must be refreshed for the new Lambda (:364)
+      for (int r = tid; r < n; r += G) { lam[r] = w[r]; a[r] *= w[r]; }
+      g.sync();
+      if (direct) {
+        for (int e = tid; e < k * T; e += G) {
+          const int i = e % k, t = e / k;
+          double s = m.Y[e];
+          for (int j = 0; j < M; ++j) s = fma(-a[j * k + i], m.X[j + M * t], s);
+          U[e] = s;
+        }
+        g.sync();
+      } else {
+        for (int r = tid; r < n; r += G) Dm[r] = a[r] - m.Aols[r];
+        g.sync();
+        for (int r = tid; r < n; r += G) {
+          const int j = r / k, i = r % k;
+          double s = 0.0;
+          for (int j2 = 0; j2 < M; ++j2) s = fma(Dm[i + k * j2], m.XX[j2 + M * j], s);
+          Wm[r] = s;
+        }
+        g.sync();
+      }
+    }
+
+    // ---- error variances ---------------------------------------------------------------------------------
+    double* out_sig = nullptr;
+    if (keep) out_sig = out.sigma + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)(sv ? kk * T : kk);
+    if (sv) {
+      sv_step(g, rng, sweep, m, U, h, sigma_h, h_init, ew, svw);                          // :462
+      // sigma_h (:465-471)
+      for (int i = tid; i < k; i += G) {
+        double ss = 0.0, prev = h_init[i];
+        for (int t = 0; t < T; ++t) { const double d = h[t + T * i] - prev; ss = fma(d, d, ss); prev = h[t + T * i]; }
+        const double scale = 1.0 / (m.g_rate[i] + ss * 0.5);
+        kv[i] = 1.0 / (scale * rng.gamma(VB_SIGH_G, sweep, i, m.g_shape_post[i]));
+      }
+      g.sync();
+      for (int i = tid; i < k; i += G) sigma_h[i] = kv[i];
+      // h_init (:474-477): (V0^-1 + diag(1/sigma_h)) k x k
+      for (int e = tid; e < kk; e += G) {
+        const int i = e % k, j = e / k;
+        S[e] = m.sv_vi[e] + ((i == j) ? 1.0 / kv[i] : 0.0);
+      }
+      for (int i = tid; i < k; i += G) {
+        double s = (1.0 / kv[i]) * h[0 + T * i];
+        for (int j = 0; j < k; ++j) s = fma(m.sv_vi[i + k * j], m.sv_mu[j], s);
+        W4[i] = s;
+      }
+      g.sync();
+      for (int e = tid; e < tri(k); e += G) {
+        int i = 0; while (tri(i + 1) <= e) ++i;
+        W1[e] = S[i + k * (e - tri(i))];
+      }
+      g.sync();
+      chol_crout(g, W1, kd, W4, k, fail);
+      for (int i = tid; i < k; i += G) W4[i] += rng.normal(VB_HINIT_N, sweep, i);
+      g.sync();
+      back_solve_lt(g, W1, kd, W4, h_init, k);
+      if (keep) {
+        // Sigma_t = diag(exp(h_t)) (solve of the diagonal block, :523-525); sigma_h (:526)
+        for (int e = tid; e < kk * T; e += G) {
+          const int t = e / kk, f = e % kk, i = f % k, j = f / k;
+          out_sig[e] = (i == j) ? 1.0 / (1.0 / exp(h[t + T * i])) : 0.0;
+        }
+        double* osh = out.sigma_h + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)k;
+        for (int i = tid; i < k; i += G) osh[i] = kv[i];
+      }
+      g.sync();
+    } else {
+      // S = S0 + u u'  /  sse diagonal
+      for (int e = tid; e < kk; e += G) {
+        const int i = e % k, j = e / k;
+        double s = 0.0;
+        if (direct) {
+          for (int t = 0; t < T; ++t) s = fma(U[i + k * t], U[j + k * t], s);
+        } else {
+          s = m.SSE[e];
+          for (int j2 = 0; j2 < M; ++j2) s = fma(Wm[i + k * j2], Dm[j + k * j2], s);
+        }
+        S[e] = s;
+      }
+      g.sync();
+      if (m.sigma_type == SIG_GAMMA) {
+        for (int i = tid; i < k; i += G) {
+          const double gs = rng.gamma(VB_OMEGA_G, sweep, i, m.g_shape_post[i]);
+          kv[i] = gs * (1.0 / (m.g_rate[i] + S[i + k * i] * 0.5));                        // :484
+        }
+        g.sync();
+        for (int e = tid; e < kk; e += G) {
+          const int i = e % k, j = e / k;
+          sig[e] = (i == j) ? kv[i] : m.omega_off[e];                                     // :507
+        }
+        g.sync();
+        if (keep) {
+          small_spd_inverse(g, sig, W4, W1, W2, W3, kd, k, fail);                         // :528
+          for (int e = tid; e < kk; e += G) out_sig[e] = W4[e];
+        }
+      } else {
+        for (int e = tid; e < kk; e += G) S[e] += m.S0[e];
+        g.sync();
+        // symmetrise exactly (moment mode computes both triangles independently)
+        for (int e = tid; e < kk; e += G) { const int i = e % k, j = e / k; if (i < j) S[e] = S[j + k * i]; }
+        g.sync();
+        wishart_block(g, rng, sweep, k, m.wish_df_post, S, sig, W4, keep, W1, W2, W3, W4 /*A then Sigma*/, kd, fail);
+        if (keep) for (int e = tid; e < kk; e += G) out_sig[e] = W4[e];
+      }
+      g.sync();
+    }
+
+    // ---- store (bvaralg.cpp:518-559)
+    if (keep && n > 0) {
+      double* oc = out.coef + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n;
+      for (int r = tid; r < n; r += G) oc[r] = a[r];
+      if (out.lambda != nullptr) {
+        double* ol = out.lambda + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n;
+        for (int r = tid; r < n; r += G) ol[r] = lam[r];
+      }
+    }
+    g.sync();
+  }
+
+  // save state
+  for (int e = tid; e < kk; e += G) st_sig[e] = sig[e];
+  for (int e = tid; e < n; e += G) { st_vd[e] = vdiag[e]; st_lam[e] = lam[e]; }
+  if (sv) {
+    for (int e = tid; e < T * k; e += G) st_h[e] = h[e];
+    for (int e = tid; e < k; e += G) { st_h[T * k + e] = sigma_h[e]; st_h[T * k + k + e] = h_init[e]; }
+  }
+  if (fail && tid == 0) out.status[chain_local] = 1;
+  g.sync();
+}
+
+}  // namespace bvg

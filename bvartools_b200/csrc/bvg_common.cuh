@@ -1,0 +1,159 @@
+// bvg_common.cuh -- shared definitions: host/device macros, Philox4x32-10, variate transforms, site addressing.
+//
+// All kernel logic in this directory is written as group-generic __host__ __device__ templates (see
+// bvg_group.cuh).  The product path instantiates them inside CUDA kernels for sm_100a; tests/emu compiles the
+// very same headers with g++ (single-thread group) purely to check the arithmetic against the oracle on
+// machines without a GPU.  There is no CPU execution path in the product library.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define BVG_HD __host__ __device__ __forceinline__
+#define BVG_D __device__ __forceinline__
+#else
+#define BVG_HD inline
+#define BVG_D inline
+#endif
+
+namespace bvg {
+
+// ---- variate blocks (site addressing, SURVEY.md Appendix B / oracle/variates.py) --------------------------
+enum VarBlock : int {
+  VB_COEF_N = 0,   // N(0,1) x n           coefficient draw                 bvaralg.cpp:307
+  VB_SSVS_U = 1,   // U(0,1) x n           SSVS Bernoulli                   bvaralg.cpp:322
+  VB_BVS_U1 = 2,   // U(0,1) x n           BVS prior gate                   bvaralg.cpp:338
+  VB_BVS_U2 = 3,   // U(0,1) x n           BVS acceptance                   bvaralg.cpp:351
+  VB_SV_U = 4,     // U(0,1) x k*T         mixture indicators               stochvol_ksc1998.cpp:96
+  VB_SV_N = 5,     // N(0,1) x k*T         log-volatility path              stochvol_ksc1998.cpp:104
+  VB_SIGH_G = 6,   // Gamma(shape,1) x k   sigma_h                          bvaralg.cpp:470
+  VB_HINIT_N = 7,  // N(0,1) x k           h_init                           bvaralg.cpp:477
+  VB_OMEGA_G = 8,  // Gamma(shape,1) x k   inverse-gamma error variances    bvaralg.cpp:484
+  VB_WISH_C = 9,   // chi2(df-i) x k       Bartlett diagonal                bvaralg.cpp:511
+  VB_WISH_N = 10,  // N(0,1) x k(k-1)/2    Bartlett strict upper triangle
+  VB_STATE_N = 11, // N(0,1) x n*T         TVP state path                   bvartvpalg.cpp:297
+  VB_SIGV_G = 12,  // Gamma(shape,1) x n   TVP state precisions             bvartvpalg.cpp:476
+  VB_AINIT_N = 13, // N(0,1) x n           TVP initial state                bvartvpalg.cpp:482
+  VB_COUNT = 14
+};
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter-based: no state, any site can be drawn by any thread ------
+struct Philox4 { uint32_t x, y, z, w; };
+
+BVG_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+BVG_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+  return o;
+}
+
+// 53-bit uniform strictly inside (0,1)
+BVG_HD double u53(uint32_t hi, uint32_t lo) {
+  const uint64_t v = ((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6);
+  return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+BVG_HD double bvg_cospi(double x) {
+#if defined(__CUDA_ARCH__)
+  return cospi(x);
+#else
+  return cos(3.14159265358979323846 * x);
+#endif
+}
+
+// ---- random source of one chain ----------------------------------------------------------------------------
+// Injected variates (tier-1 parity tests): device arrays [chain][sweep][count] or nullptr per block.  Lives in
+// kernel parameter (constant) space; the chain only keeps a pointer to it so that the Philox path carries no
+// per-block pointers in registers.
+struct RngParams {
+  uint64_t seed;
+  uint64_t chain_offset;
+  const double* inj[VB_COUNT];
+  int inj_stride[VB_COUNT];               // count per sweep
+  long long inj_chain_stride[VB_COUNT];   // sweeps * count
+};
+
+// Site = (block, sweep, index[, attempt]).  Key = seed, counter = (index | attempt<<24, sweep, chain_lo,
+// chain_hi ^ block<<24): results are independent of thread mapping, launch chunking and GPU count.
+struct ChainRng {
+  uint64_t seed;
+  uint64_t chain;                 // GLOBAL chain id
+  const RngParams* rp;            // injected variates (or all-null)
+  long long chain_local;
+
+  BVG_HD ChainRng(const RngParams* p, long long local)
+      : seed(p->seed), chain(p->chain_offset + (uint64_t)local), rp(p), chain_local(local) {}
+
+  BVG_HD Philox4 raw(int block, int sweep, int idx, int attempt) const {
+    return philox4x32_10((uint32_t)idx | ((uint32_t)attempt << 24), (uint32_t)sweep, (uint32_t)chain,
+                         (uint32_t)(chain >> 32) ^ ((uint32_t)block << 24), (uint32_t)seed, (uint32_t)(seed >> 32));
+  }
+  BVG_HD bool injected(int block) const { return rp->inj[block] != nullptr; }
+  BVG_HD double inj_at(int block, int sweep, int idx) const {
+    return rp->inj[block][(size_t)chain_local * (size_t)rp->inj_chain_stride[block] +
+                          (size_t)sweep * (size_t)rp->inj_stride[block] + (size_t)idx];
+  }
+  BVG_HD double uniform(int block, int sweep, int idx, int attempt = 0) const {
+    if (rp->inj[block]) return inj_at(block, sweep, idx);
+    const Philox4 p = raw(block, sweep, idx, attempt);
+    return u53(p.x, p.y);
+  }
+  // one site -> one normal (Box-Muller cosine branch; the sine is not used so that sites stay independent)
+  BVG_HD double normal(int block, int sweep, int idx, int attempt = 0) const {
+    if (rp->inj[block]) return inj_at(block, sweep, idx);
+    const Philox4 p = raw(block, sweep, idx, attempt);
+    const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
+    return sqrt(-2.0 * log(u1)) * bvg_cospi(2.0 * u2);
+  }
+  // Gamma(shape, 1), Marsaglia-Tsang 2000 (shape < 1 boosted); attempts are separate sites
+  BVG_HD double gamma(int block, int sweep, int idx, double shape) const {
+    if (rp->inj[block]) return inj_at(block, sweep, idx);
+    double boost = 1.0, a = shape;
+    if (a < 1.0) {
+      const Philox4 p = raw(block, sweep, idx, 255);
+      boost = pow(u53(p.x, p.y), 1.0 / a);
+      a += 1.0;
+    }
+    const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (int attempt = 0; attempt < 100; ++attempt) {
+      const Philox4 p = raw(block, sweep, idx, attempt);
+      const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
+      const double x = sqrt(-2.0 * log(u1)) * bvg_cospi(2.0 * u2);
+      double v = 1.0 + c * x;
+      if (v <= 0.0) continue;
+      v = v * v * v;
+      const Philox4 q = raw(block, sweep, idx, attempt + 100);
+      const double u = u53(q.x, q.y);
+      if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v;
+    }
+    return boost * d;   // unreachable in practice (acceptance > 95 %)
+  }
+  BVG_HD double chi2(int block, int sweep, int idx, double df) const {
+    if (rp->inj[block]) return inj_at(block, sweep, idx);
+    return 2.0 * gamma(block, sweep, idx, 0.5 * df);
+  }
+};
+
+BVG_HD int tri(int i) { return (i * (i + 1)) >> 1; }   // offset of row i in packed lower row-major storage
+
+// R's rbinom(1, 1, p) driven by one uniform (convention: oracle/variates.py)
+BVG_HD double bernoulli_rbinom(double p, double u) { return (p > 0.5) ? ((u < p) ? 1.0 : 0.0) : ((u >= 1.0 - p) ? 1.0 : 0.0); }
+
+}  // namespace bvg

@@ -1,0 +1,170 @@
+// bvg_kern_util.cu -- launch planning, posterior-moment reduction, FP64 peak probe.
+#include "bvg_kernels.cuh"
+
+namespace bvg {
+
+static int pick_tile(int n_work) {
+  if (n_work >= 16) return 32;
+  if (n_work >= 8) return 16;
+  if (n_work >= 4) return 8;
+  return 4;
+}
+
+static cudaError_t finish_plan(LaunchPlan* plan, int per_chain_doubles, long long n_chains, int tpc) {
+  if (tpc <= 32) {
+    if (tpc != 4 && tpc != 8 && tpc != 16 && tpc != 32) return cudaErrorInvalidValue;
+    plan->threads_per_chain = tpc;
+    plan->smem_per_chain = per_chain_doubles;
+    plan->block_threads = 128;
+    plan->chains_per_block = 128 / tpc;
+    while (plan->chains_per_block > 1 && (size_t)plan->chains_per_block * per_chain_doubles * 8 > 200 * 1024) {
+      plan->chains_per_block >>= 1;
+      plan->block_threads >>= 1;
+    }
+    plan->smem_bytes = (size_t)plan->chains_per_block * per_chain_doubles * 8;
+  } else {
+    if (tpc % 32 != 0 || tpc > 1024) return cudaErrorInvalidValue;
+    plan->threads_per_chain = tpc;
+    plan->smem_per_chain = per_chain_doubles;
+    plan->block_threads = tpc;
+    plan->chains_per_block = 1;
+    plan->smem_bytes = ((size_t)per_chain_doubles + BVG_BLOCK_SCRATCH) * 8;
+  }
+  if (plan->smem_bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
+  plan->grid = (int)((n_chains + plan->chains_per_block - 1) / plan->chains_per_block);
+  return cudaSuccess;
+}
+
+cudaError_t plan_bvar(const BvarModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan) {
+  const int per = bvar_smem_len(m.k, m.T, m.M, m.n, m.sigma_type, m.resid_mode);
+  int tpc = requested_tpc;
+  if (tpc <= 0) {
+    if ((size_t)per * 8 > 24 * 1024 || m.n > 64) tpc = (m.n > 96) ? 256 : 128;   // one CTA per chain
+    else tpc = pick_tile(m.n > m.k ? m.n : m.k);
+  }
+  return finish_plan(plan, per, n_chains, tpc);
+}
+
+cudaError_t plan_tvp(const TvpModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan) {
+  const int per = tvp_smem_len(m.b.k, m.b.T, m.b.n, m.b.sigma_type);
+  int tpc = requested_tpc;
+  if (tpc <= 0) {
+    if ((size_t)per * 8 > 48 * 1024 || m.b.n > 64) tpc = (m.b.n > 96) ? 256 : 128;
+    else tpc = pick_tile(m.b.n);
+  }
+  return finish_plan(plan, per, n_chains, tpc);
+}
+
+cudaError_t launch_bvar(const LaunchPlan& plan, const BvarModel& m, const RngParams& rp, double* state,
+                        int state_len, const BvarOut& out, long long n_chains, int s0, int s1, int burnin,
+                        cudaStream_t stream) {
+  switch (plan.threads_per_chain) {
+    case 4: return launch_bvar_g4(plan, m, rp, state, state_len, out, n_chains, s0, s1, burnin, stream);
+    case 8: return launch_bvar_g8(plan, m, rp, state, state_len, out, n_chains, s0, s1, burnin, stream);
+    case 16: return launch_bvar_g16(plan, m, rp, state, state_len, out, n_chains, s0, s1, burnin, stream);
+    case 32: return launch_bvar_g32(plan, m, rp, state, state_len, out, n_chains, s0, s1, burnin, stream);
+    default: return launch_bvar_g0(plan, m, rp, state, state_len, out, n_chains, s0, s1, burnin, stream);
+  }
+}
+
+cudaError_t launch_tvp(const LaunchPlan& plan, const TvpModel& m, const RngParams& rp, double* state,
+                       int state_len, double* scratch, long long spc, const TvpOut& out, long long n_chains,
+                       int s0, int s1, int burnin, cudaStream_t stream) {
+  switch (plan.threads_per_chain) {
+    case 4: return launch_tvp_g4(plan, m, rp, state, state_len, scratch, spc, out, n_chains, s0, s1, burnin, stream);
+    case 8: return launch_tvp_g8(plan, m, rp, state, state_len, scratch, spc, out, n_chains, s0, s1, burnin, stream);
+    case 16: return launch_tvp_g16(plan, m, rp, state, state_len, scratch, spc, out, n_chains, s0, s1, burnin, stream);
+    case 32: return launch_tvp_g32(plan, m, rp, state, state_len, scratch, spc, out, n_chains, s0, s1, burnin, stream);
+    default: return launch_tvp_g0(plan, m, rp, state, state_len, scratch, spc, out, n_chains, s0, s1, burnin, stream);
+  }
+}
+
+// ---------------- posterior moments: sums[r] = sum over (chain, iter) of x, sumsq likewise ----------------
+// draws is [chains*iters][rows]; HBM-bound streaming reduction (8 B read per element), grid = 8 CTAs per SM.
+__global__ void __launch_bounds__(256) moments_kernel(const double* __restrict__ draws, long long n_draws,
+                                                      long long rows, double* sums, double* sumsq) {
+  const long long total = n_draws * rows;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // per-thread stride is a multiple of rows, so a thread always sees the same row and loads stay coalesced
+  const long long step = (stride / rows) * rows;
+  if (step == 0) {   // more rows than threads: one row at a time per thread
+    for (long long rr = idx; rr < rows; rr += stride) {
+      double s = 0.0, s2 = 0.0;
+      for (long long d = 0; d < n_draws; ++d) { const double v = draws[d * rows + rr]; s += v; s2 = fma(v, v, s2); }
+      sums[rr] = s;
+      sumsq[rr] = s2;
+    }
+    return;
+  }
+  if (idx >= step) return;
+  const long long r = idx % rows;
+  double s = 0.0, s2 = 0.0;
+  for (; idx < total; idx += step) {
+    const double v = draws[idx];
+    s += v;
+    s2 = fma(v, v, s2);
+  }
+  atomicAdd(&sums[r], s);
+  atomicAdd(&sumsq[r], s2);
+}
+
+cudaError_t launch_moments(const double* draws, long long chains, long long iters, long long rows, double* sums,
+                           double* sumsq, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)rows * 8, stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(sumsq, 0, (size_t)rows * 8, stream);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  moments_kernel<<<sms * 8, 256, 0, stream>>>(draws, chains * iters, rows, sums, sumsq);
+  return cudaGetLastError();
+}
+
+// ---------------- FP64 FMA peak probe (roofline denominator; MEASURED_PEAKS.json has no FP64 entry) --------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
+         a6 = a0 + 6.0, a7 = a0 + 7.0;
+  const double b = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456) sink[0] = s;
+}
+
+cudaError_t launch_fp64_peak(double* tflops, cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  double* sink = nullptr;
+  cudaError_t e = cudaMalloc(&sink, 8);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 1 << 16, blocks = sms * 8, threads = 256;
+  fp64_peak_kernel<<<blocks, threads, 0, stream>>>(sink, 1024);   // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, stream);
+    fp64_peak_kernel<<<blocks, threads, 0, stream>>>(sink, iters);
+    cudaEventRecord(e1, stream);
+    e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *tflops = best;
+  return e;
+}
+
+}  // namespace bvg

@@ -1,0 +1,52 @@
+// bvg_kernels.cuh -- launcher interface between the host API (bvg_api.cu) and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include "bvg_bvar_sweep.cuh"
+#include "bvg_tvp_sweep.cuh"
+
+namespace bvg {
+
+struct LaunchPlan {
+  int threads_per_chain;   // 4..32 (tile of a warp) or a multiple of 32 (CTA per chain)
+  int block_threads;
+  int chains_per_block;
+  size_t smem_bytes;       // dynamic shared memory per block
+  int smem_per_chain;      // doubles
+  int grid;
+};
+
+#define BVG_BLOCK_SCRATCH 40   // doubles reserved in front of the chain's shared memory for BlockGroup
+
+cudaError_t plan_bvar(const BvarModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan);
+cudaError_t launch_bvar(const LaunchPlan& plan, const BvarModel& m, const RngParams& rp, double* state,
+                        int state_len, const BvarOut& out, long long n_chains, int sweep_begin, int sweep_end,
+                        int burnin, cudaStream_t stream);
+
+cudaError_t plan_tvp(const TvpModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan);
+cudaError_t launch_tvp(const LaunchPlan& plan, const TvpModel& m, const RngParams& rp, double* state,
+                       int state_len, double* scratch, long long scratch_per_chain, const TvpOut& out,
+                       long long n_chains, int sweep_begin, int sweep_end, int burnin, cudaStream_t stream);
+
+cudaError_t launch_moments(const double* draws, long long chains, long long iters, long long rows, double* sums,
+                           double* sumsq, cudaStream_t stream);
+cudaError_t launch_fp64_peak(double* tflops, cudaStream_t stream);
+
+// per-instantiation launchers (one translation unit each, see Makefile): G = 4, 8, 16, 32 lanes per chain, 0 = CTA
+#define BVG_DECL_TILE(G)                                                                                          \
+  cudaError_t launch_bvar_g##G(const LaunchPlan&, const BvarModel&, const RngParams&, double*, int, const BvarOut&, \
+                               long long, int, int, int, cudaStream_t);                                            \
+  cudaError_t launch_tvp_g##G(const LaunchPlan&, const TvpModel&, const RngParams&, double*, int, double*,         \
+                              long long, const TvpOut&, long long, int, int, int, cudaStream_t);
+BVG_DECL_TILE(0)
+BVG_DECL_TILE(4)
+BVG_DECL_TILE(8)
+BVG_DECL_TILE(16)
+BVG_DECL_TILE(32)
+
+template <typename K>
+static inline cudaError_t set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return cudaSuccess;
+}
+
+}  // namespace bvg

@@ -1,0 +1,139 @@
+// bvg_linalg.cuh -- group-parallel FP64 dense kernels on shared-memory operands.
+//
+// Storage: symmetric / triangular matrices are packed lower, row-major: element (i,j), j <= i, at tri(i)+j.
+// Row ownership is cyclic and fixed: row i belongs to thread i % G, so a thread re-reads only what it wrote
+// between barriers, and the only cross-thread traffic per column is row j (the pivot row).
+#pragma once
+#include "bvg_group.cuh"
+
+namespace bvg {
+
+// Cholesky-Crout, P = L L', with the right-hand side carried as an extra row (augmented system), so that the
+// forward substitution w = L^-1 b costs no extra barriers.
+//   in : L   packed lower with P;  b (n) or nullptr
+//   out: strict lower part of L = factor, dinv[j] = 1 / L_jj  (the diagonal slots of L are left holding the
+//        pivots d_j = L_jj^2 and must not be used);  b <- L^-1 b
+//   fail is set when a pivot is not positive (or NaN).
+// Reference call sites: arma::chol + arma::solve in bvaralg.cpp:306-307, bvartvpalg.cpp:296-297, :429, :482.
+template <class Grp>
+BVG_HD void chol_crout(const Grp& g, double* L, double* dinv, double* b, int n, int& fail) {
+  const int G = g.size(), tid = g.tid();
+  const int bowner = n % G;
+  for (int j = 0; j < n; ++j) {
+    const double* Lj = L + tri(j);
+    int i0 = j - (j % G) + tid;       // first row >= j owned by this thread
+    if (i0 < j) i0 += G;
+    for (int i = i0; i < n; i += G) {
+      double* Li = L + tri(i);
+      double s0 = Li[j], s1 = 0.0;
+      int c = 0;
+      for (; c + 1 < j; c += 2) {
+        s0 = fma(-Li[c], Lj[c], s0);
+        s1 = fma(-Li[c + 1], Lj[c + 1], s1);
+      }
+      if (c < j) s0 = fma(-Li[c], Lj[c], s0);
+      Li[j] = s0 + s1;
+    }
+    if (b != nullptr && tid == bowner) {
+      double s0 = b[j], s1 = 0.0;
+      int c = 0;
+      for (; c + 1 < j; c += 2) {
+        s0 = fma(-b[c], Lj[c], s0);
+        s1 = fma(-b[c + 1], Lj[c + 1], s1);
+      }
+      if (c < j) s0 = fma(-b[c], Lj[c], s0);
+      b[j] = s0 + s1;
+    }
+    g.sync();
+    const double d = Lj[j];
+    if (!(d > 0.0)) fail = 1;
+    const double rs = 1.0 / sqrt(d);
+    for (int i = (i0 == j ? i0 + G : i0); i < n; i += G) L[tri(i) + j] *= rs;
+    if (b != nullptr && tid == bowner) b[j] *= rs;
+    if (tid == 0) dinv[j] = rs;
+    g.sync();
+  }
+}
+
+// a = L^-T w  (back substitution with the transposed factor); w is destroyed.  a may alias nothing in w.
+template <class Grp>
+BVG_HD void back_solve_lt(const Grp& g, const double* L, const double* dinv, double* w, double* a, int n) {
+  const int G = g.size(), tid = g.tid();
+  for (int i = n - 1; i >= 0; --i) {
+    const double ai = w[i] * dinv[i];
+    const double* Li = L + tri(i);
+    for (int r = tid; r < i; r += G) w[r] = fma(-Li[r], ai, w[r]);
+    if (tid == 0) a[i] = ai;
+    g.sync();
+  }
+}
+
+// w = L^-1 b in place (forward substitution), for factors whose rhs was not carried through chol_crout.
+template <class Grp>
+BVG_HD void fwd_solve_l(const Grp& g, const double* L, const double* dinv, double* b, int n) {
+  const int G = g.size(), tid = g.tid();
+  for (int j = 0; j < n; ++j) {
+    const double wj = b[j] * dinv[j];
+    g.sync();                                  // everyone has read b[j] before the owner overwrites it
+    if (tid == 0) b[j] = wj;
+    for (int i = j + 1 + tid; i < n; i += G) b[i] = fma(-L[tri(i) + j], wj, b[i]);
+    g.sync();
+  }
+}
+
+// M = L^-1 (lower triangular inverse, packed), column per thread.  L's diagonal comes from dinv.
+template <class Grp>
+BVG_HD void tri_inverse(const Grp& g, const double* L, const double* dinv, double* Minv, int n) {
+  const int G = g.size(), tid = g.tid();
+  for (int c = tid; c < n; c += G) {
+    Minv[tri(c) + c] = dinv[c];
+    for (int i = c + 1; i < n; ++i) {
+      const double* Li = L + tri(i);
+      double s = 0.0;
+      for (int m = c; m < i; ++m) s = fma(Li[m], Minv[tri(m) + c], s);
+      Minv[tri(i) + c] = -s * dinv[i];
+    }
+  }
+  g.sync();
+}
+
+// C (packed lower) = M' M for lower-triangular packed M:  C_ij = sum_{m >= i} M_mi M_mj  (i >= j)
+template <class Grp>
+BVG_HD void mtm_lower(const Grp& g, const double* Minv, double* C, int n) {
+  const int G = g.size(), tid = g.tid();
+  const int ne = tri(n);
+  int i = 0;
+  for (int e = tid; e < ne; e += G) {
+    while (tri(i + 1) <= e) ++i;
+    const int j = e - tri(i);
+    double s = 0.0;
+    for (int m = i; m < n; ++m) s = fma(Minv[tri(m) + i], Minv[tri(m) + j], s);
+    C[e] = s;
+  }
+  g.sync();
+}
+
+// C (packed lower) = M M' for lower-triangular packed M:  C_ij = sum_{m <= j} M_im M_jm  (i >= j)
+template <class Grp>
+BVG_HD void mmt_lower(const Grp& g, const double* Mlow, double* C, int n) {
+  const int G = g.size(), tid = g.tid();
+  const int ne = tri(n);
+  int i = 0;
+  for (int e = tid; e < ne; e += G) {
+    while (tri(i + 1) <= e) ++i;
+    const int j = e - tri(i);
+    double s = 0.0;
+    for (int m = 0; m <= j; ++m) s = fma(Mlow[tri(i) + m], Mlow[tri(j) + m], s);
+    C[e] = s;
+  }
+  g.sync();
+}
+
+// write the true diagonal (1/dinv) into the packed factor so it can be used as a plain triangular matrix
+template <class Grp>
+BVG_HD void fix_diag(const Grp& g, double* L, const double* dinv, int n) {
+  for (int i = g.tid(); i < n; i += g.size()) L[tri(i) + i] = 1.0 / dinv[i];
+  g.sync();
+}
+
+}  // namespace bvg

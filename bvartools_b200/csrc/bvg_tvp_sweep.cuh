@@ -1,0 +1,370 @@
+// bvg_tvp_sweep.cuh -- one chain of the TVP-BVAR Gibbs sampler (src/bvartvpalg.cpp:282-553).
+//
+// The reference assembles the (nT) x (nT) precision  P = H'(I_T (x) Sv^-1)H + zz' Su^-1 zz  (bvartvpalg.cpp:293-295),
+// converts it to a DENSE matrix and runs LU solve + Cholesky on it (:296-297).  P is block tridiagonal with
+// n x n blocks:  diag  B_t = c_t Q + Z_t' S_t^-1 Z_t  (c_t = 2, last 1; Q = diag(Sv^-1)),  off-diagonal -Q.
+// Its (unique) Cholesky factor is block bidiagonal, so the reference's  a = P^-1 rhs + chol(P)^-1 eps  is
+// reproduced exactly by a block forward recursion (per t: one n x n Cholesky, one triangular inverse M_t = L_tt^-1,
+// one M'M product) and a backward recursion made only of triangular mat-vecs:
+//     D_t   = B_t - Q M_{t-1}' M_{t-1} Q                      L_tt L_tt' = D_t
+//     w_t   = L_tt^-1 (rhs_t + Q M_{t-1}' w_{t-1})
+//     a_t   = M_t' ( w_t + eps_t + M_t Q a_{t+1} )
+// M_t (packed lower) is streamed through HBM: T tri(n) doubles written forward, read backward.
+#pragma once
+#include "bvg_bvar_sweep.cuh"
+
+namespace bvg {
+
+struct TvpModel {
+  BvarModel b;                   // data, error-variance prior, BVS prior; mu/vdiag0/vi_off = prior of the initial state
+  const double* v_shape_post;    // n  shape + T/2                                   (bvartvpalg.cpp:104)
+  const double* v_rate;          // n                                                (bvartvpalg.cpp:105)
+};
+
+struct TvpOut {
+  double* coef;      // [chain][iter][T][n]
+  double* sigma;     // [chain][iter][k*k] or [chain][iter][T][k*k]
+  double* lambda;    // [chain][iter][n] or nullptr
+  double* sigma_h;   // [chain][iter][k] or nullptr
+  double* sigma_v;   // [chain][iter][n]
+  int* status;
+  long long iters;
+};
+
+// state: [0,kk) Sigma_u^-1 | n q = diag(Sigma_v^-1) | n a_init | n lambda | SV: T*k h, k sigma_h, k h_init
+BVG_HD int tvp_state_len(int k, int T, int n, int sigma_type) {
+  return k * k + 3 * n + (sigma_type == SIG_SV ? T * k + 2 * k : 0);
+}
+// global scratch per chain: T*tri(n) (M_t) + T*n (w_t + eps_t) + T*n (a path)
+BVG_HD long long tvp_scratch_len(int T, int n) { return (long long)T * (tri(n) + 2 * n); }
+
+BVG_HD int tvp_smem_len(int k, int T, int n, int sigma_type) {
+  int len = 3 * tri(n) + 9 * n + 6 * k * k + 2 * k + k * T;
+  if (sigma_type == SIG_SV) len += 3 * k * T + 2 * k;
+  return len;
+}
+
+template <class Grp>
+BVG_HD void tvp_residuals(const Grp& g, const BvarModel& m, const double* apath, const double* lam, bool mask,
+                          double* U) {
+  const int k = m.k, T = m.T, M = m.M, n = m.n;
+  for (int e = g.tid(); e < k * T; e += g.size()) {
+    const int i = e % k, t = e / k;
+    const double* at = apath + (size_t)t * n;
+    double s = m.Y[e];
+    for (int j = 0; j < M; ++j) {
+      const double av = mask ? lam[j * k + i] * at[j * k + i] : at[j * k + i];
+      s = fma(-av, m.X[j + M * t], s);
+    }
+    U[e] = s;
+  }
+  g.sync();
+}
+
+template <class Grp>
+BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, double* state, double* scratch,
+                      double* sm, const TvpOut& out, long long chain_local, int sweep_begin, int sweep_end,
+                      int burnin) {
+  const BvarModel& m = tm.b;
+  const int G = g.size(), tid = g.tid();
+  const int k = m.k, T = m.T, M = m.M, n = m.n, kk = k * k, tn = tri(n);
+  const bool sv = m.sigma_type == SIG_SV;
+  const bool bvs = m.varsel == VS_BVS;
+  double* Dt = sm;      sm += tn;
+  double* Mi = sm;      sm += tn;
+  double* Cq = sm;      sm += tn;
+  double* wv = sm;      sm += n;      // rhs_t -> w_t
+  double* cvec = sm;    sm += n;      // Q M_t' w_t (carry into t+1)
+  double* dinv = sm;    sm += n;
+  double* q = sm;       sm += n;
+  double* a_init = sm;  sm += n;
+  double* lam = sm;     sm += n;
+  double* anext = sm;   sm += n;
+  double* tmp = sm;     sm += n;
+  double* tmp2 = sm;    sm += n;
+  double* sig = sm;     sm += kk;
+  double* S = sm;       sm += kk;
+  double* W1 = sm;      sm += kk;
+  double* W2 = sm;      sm += kk;
+  double* W3 = sm;      sm += kk;
+  double* W4 = sm;      sm += kk;
+  double* kd = sm;      sm += k;
+  double* kv = sm;      sm += k;
+  double* U = sm;       sm += k * T;
+  double* h = nullptr; double* ew = nullptr; double* svw = nullptr; double* sigma_h = nullptr; double* h_init = nullptr;
+  if (sv) { h = sm; sm += k * T; ew = sm; sm += k * T; svw = sm; sm += k * T; sigma_h = sm; sm += k; h_init = sm; sm += k; }
+  double* Mpath = scratch;                         // [T][tn]
+  double* wpath = scratch + (size_t)T * tn;        // [T][n]
+  double* apath = wpath + (size_t)T * n;           // [T][n]
+  int fail = 0;
+
+  double* st_q = state + kk;
+  double* st_ai = st_q + n;
+  double* st_lam = st_ai + n;
+  double* st_h = st_lam + n;
+  for (int e = tid; e < kk; e += G) sig[e] = state[e];
+  for (int e = tid; e < n; e += G) { q[e] = st_q[e]; a_init[e] = st_ai[e]; lam[e] = st_lam[e]; }
+  if (sv) {
+    for (int e = tid; e < T * k; e += G) h[e] = st_h[e];
+    for (int e = tid; e < k; e += G) { sigma_h[e] = st_h[T * k + e]; h_init[e] = st_h[T * k + k + e]; }
+  }
+  g.sync();
+
+  for (int sweep = sweep_begin; sweep < sweep_end; ++sweep) {
+    const bool keep = sweep >= burnin;
+    const long long pos = (long long)sweep - burnin;
+    if (sv) {
+      // bvartvpalg.cpp:446; the very first sweep uses h.row(0) for every period (:224-225,230)
+      for (int e = tid; e < k * T; e += G) ew[e] = 1.0 / exp(sweep == 0 ? h[T * (e / T)] : h[e]);
+      g.sync();
+    }
+    // ================= forward recursion =================
+    for (int t = 0; t < T; ++t) {
+      const double* xt = m.X + (size_t)M * t;
+      const double* yt = m.Y + (size_t)k * t;
+      // kv = Sigma_t^-1 y_t
+      for (int i = tid; i < k; i += G) {
+        double s;
+        if (sv) s = ew[t + T * i] * yt[i];
+        else { s = 0.0; for (int i2 = 0; i2 < k; ++i2) s = fma(sig[i + k * i2], yt[i2], s); }
+        kv[i] = s;
+      }
+      g.sync();
+      const double ct = (t < T - 1) ? 2.0 : 1.0;
+      for (int r = tid; r < n; r += G) {
+        const int j = r / k, i = r % k;
+        double* Dr = Dt + tri(r);
+        const double lr = bvs ? lam[r] : 1.0;
+        const double xr = xt[j] * lr;
+        int j2 = 0, i2 = 0;
+        for (int c = 0; c <= r; ++c) {
+          double sv_ii;
+          if (sv) sv_ii = (i == i2) ? ew[t + T * i] : 0.0;
+          else sv_ii = sig[i + k * i2];
+          double gv = xr * (xt[j2] * (bvs ? lam[c] : 1.0)) * sv_ii;
+          if (c == r) gv += ct * q[r];
+          if (t > 0) gv -= Cq[tri(r) + c];
+          Dr[c] = gv;
+          if (++i2 == k) { i2 = 0; ++j2; }
+        }
+        double b = xr * kv[i];
+        if (t == 0) b += q[r] * a_init[r];                                              // :296 first block
+        else b += cvec[r];
+        wv[r] = b;
+      }
+      g.sync();
+      chol_crout(g, Dt, dinv, wv, n, fail);
+      tri_inverse(g, Dt, dinv, Mi, n);
+      // stream M_t and w_t + eps_t to HBM
+      double* Mg = Mpath + (size_t)t * tn;
+      for (int e = tid; e < tn; e += G) Mg[e] = Mi[e];
+      for (int r = tid; r < n; r += G) wpath[(size_t)t * n + r] = wv[r] + rng.normal(VB_STATE_N, sweep, t * n + r);
+      if (t < T - 1) {
+        // carry: Cq = Q M'M Q,  cvec = Q M' w
+        mtm_lower(g, Mi, Cq, n);
+        int i = 0;
+        for (int e = tid; e < tn; e += G) {
+          while (tri(i + 1) <= e) ++i;
+          Cq[e] *= q[i] * q[e - tri(i)];
+        }
+        for (int r = tid; r < n; r += G) {
+          double s = 0.0;
+          for (int mm = r; mm < n; ++mm) s = fma(Mi[tri(mm) + r], wv[mm], s);
+          cvec[r] = q[r] * s;
+        }
+      }
+      g.sync();
+    }
+    // ================= backward recursion =================
+    for (int t = T - 1; t >= 0; --t) {
+      const double* Mg = Mpath + (size_t)t * tn;
+      for (int e = tid; e < tn; e += G) Mi[e] = Mg[e];
+      for (int r = tid; r < n; r += G) tmp[r] = wpath[(size_t)t * n + r];
+      g.sync();
+      if (t < T - 1) {
+        for (int r = tid; r < n; r += G) {
+          double s = 0.0;
+          const double* Mr = Mi + tri(r);
+          for (int c = 0; c <= r; ++c) s = fma(Mr[c], q[c] * anext[c], s);
+          tmp2[r] = tmp[r] + s;
+        }
+      } else {
+        for (int r = tid; r < n; r += G) tmp2[r] = tmp[r];
+      }
+      g.sync();
+      for (int r = tid; r < n; r += G) {
+        double s = 0.0;
+        for (int mm = r; mm < n; ++mm) s = fma(Mi[tri(mm) + r], tmp2[mm], s);
+        apath[(size_t)t * n + r] = s;
+        tmp[r] = s;
+      }
+      g.sync();
+      for (int r = tid; r < n; r += G) anext[r] = tmp[r];
+      g.sync();
+    }
+
+    // ================= BVS (bvartvpalg.cpp:300-330) and residuals (:332-336) =================
+    tvp_residuals(g, m, apath, lam, bvs, U);
+    if (bvs) {
+      for (int r = tid; r < n; r += G) {
+        double newlam = lam[r];
+        if (m.include[r]) {
+          const int j = r / k, i = r % k;
+          const double lp0 = log(1.0 - m.inprior[r]), lp1 = log(m.inprior[r]);
+          const double g1 = log(rng.uniform(VB_BVS_U1, sweep, r));
+          const bool gate = (lam[r] == 1.0) ? (g1 < lp1) : (g1 < lp0);
+          if (gate) {
+            double dq = 0.0;
+            for (int t = 0; t < T; ++t) {
+              const double x = m.X[j + M * t];
+              double v, sii;
+              if (sv) { sii = ew[t + T * i]; v = sii * U[i + k * t]; }
+              else {
+                sii = sig[i + k * i];
+                v = 0.0;
+                for (int i2 = 0; i2 < k; ++i2) v = fma(sig[i + k * i2], U[i2 + k * t], v);
+              }
+              const double ar = apath[(size_t)t * n + r];
+              const double d0 = lam[r] * ar, d1 = (lam[r] - 1.0) * ar;
+              dq += 2.0 * (d1 - d0) * (x * v) + (d1 * d1 - d0 * d0) * (x * x * sii);
+            }
+            const double bayes = -0.5 * dq + (lp1 - lp0);
+            const double g2 = log(rng.uniform(VB_BVS_U2, sweep, r));
+            newlam = (bayes >= g2) ? 1.0 : 0.0;
+          }
+        }
+        tmp[r] = newlam;
+      }
+      g.sync();
+      for (int r = tid; r < n; r += G) lam[r] = tmp[r];
+      g.sync();
+      for (int e = tid; e < n * T; e += G) apath[e] *= lam[e % n];                     // :328
+      g.sync();
+      tvp_residuals(g, m, apath, lam, false, U);
+    }
+
+    // ================= error variances =================
+    double* out_sig = nullptr;
+    if (keep) out_sig = out.sigma + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)(sv ? kk * T : kk);
+    if (sv) {
+      sv_step(g, rng, sweep, m, U, h, sigma_h, h_init, ew, svw);                       // :414
+      for (int i = tid; i < k; i += G) {
+        double ss = 0.0, prev = h_init[i];
+        for (int t = 0; t < T; ++t) { const double d = h[t + T * i] - prev; ss = fma(d, d, ss); prev = h[t + T * i]; }
+        const double scale = 1.0 / (m.g_rate[i] + ss * 0.5);
+        kv[i] = 1.0 / (scale * rng.gamma(VB_SIGH_G, sweep, i, m.g_shape_post[i]));     // :422
+      }
+      g.sync();
+      for (int i = tid; i < k; i += G) sigma_h[i] = kv[i];
+      for (int e = tid; e < kk; e += G) {
+        const int i = e % k, j = e / k;
+        S[e] = m.sv_vi[e] + ((i == j) ? 1.0 / kv[i] : 0.0);
+      }
+      for (int i = tid; i < k; i += G) {
+        double s = (1.0 / kv[i]) * h[0 + T * i];
+        for (int j = 0; j < k; ++j) s = fma(m.sv_vi[i + k * j], m.sv_mu[j], s);
+        W4[i] = s;
+      }
+      g.sync();
+      for (int e = tid; e < tri(k); e += G) {
+        int i = 0; while (tri(i + 1) <= e) ++i;
+        W1[e] = S[i + k * (e - tri(i))];
+      }
+      g.sync();
+      chol_crout(g, W1, kd, W4, k, fail);
+      for (int i = tid; i < k; i += G) W4[i] += rng.normal(VB_HINIT_N, sweep, i);
+      g.sync();
+      back_solve_lt(g, W1, kd, W4, h_init, k);                                         // :429
+      if (keep) {
+        for (int e = tid; e < kk * T; e += G) {
+          const int t = e / kk, f = e % kk, i = f % k, j = f / k;
+          out_sig[e] = (i == j) ? 1.0 / (1.0 / exp(h[t + T * i])) : 0.0;               // :507-509
+        }
+        double* osh = out.sigma_h + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)k;
+        for (int i = tid; i < k; i += G) osh[i] = kv[i];
+      }
+      g.sync();
+    } else {
+      for (int e = tid; e < kk; e += G) {
+        const int i = e % k, j = e / k;
+        double s = 0.0;
+        for (int t = 0; t < T; ++t) s = fma(U[i + k * t], U[j + k * t], s);
+        S[e] = s;
+      }
+      g.sync();
+      if (m.sigma_type == SIG_GAMMA) {
+        for (int i = tid; i < k; i += G) {
+          const double gs = rng.gamma(VB_OMEGA_G, sweep, i, m.g_shape_post[i]);
+          kv[i] = gs * (1.0 / (m.g_rate[i] + S[i + k * i] * 0.5));                     // :436
+        }
+        g.sync();
+        for (int e = tid; e < kk; e += G) {
+          const int i = e % k, j = e / k;
+          sig[e] = (i == j) ? kv[i] : m.omega_off[e];
+        }
+        g.sync();
+        if (keep) {
+          small_spd_inverse(g, sig, W4, W1, W2, W3, kd, k, fail);
+          for (int e = tid; e < kk; e += G) out_sig[e] = W4[e];
+        }
+      } else {
+        for (int e = tid; e < kk; e += G) S[e] += m.S0[e];
+        g.sync();
+        wishart_block(g, rng, sweep, k, m.wish_df_post, S, sig, W4, keep, W1, W2, W3, W4, kd, fail);   // :461
+        if (keep) for (int e = tid; e < kk; e += G) out_sig[e] = W4[e];
+      }
+      g.sync();
+    }
+
+    // ================= state variances (:469-477) and initial state (:480-482) =================
+    for (int r = tid; r < n; r += G) {
+      double ss = 0.0, prev = a_init[r];
+      for (int t = 0; t < T; ++t) { const double v = apath[(size_t)t * n + r]; const double d = v - prev; ss = fma(d, d, ss); prev = v; }
+      const double scale = 1.0 / (tm.v_rate[r] + ss * 0.5);
+      tmp[r] = rng.gamma(VB_SIGV_G, sweep, r, tm.v_shape_post[r]) * scale;             // :476
+    }
+    g.sync();
+    for (int r = tid; r < n; r += G) q[r] = tmp[r];
+    g.sync();
+    for (int r = tid; r < n; r += G) {
+      double* Dr = Dt + tri(r);
+      for (int c = 0; c <= r; ++c) {
+        double v = (m.vi_off != nullptr) ? m.vi_off[tri(r) + c] : 0.0;
+        if (c == r) v += m.vdiag0[r] + q[r];
+        Dr[c] = v;
+      }
+      double b = m.vdiag0[r] * m.mu[r] + q[r] * apath[r];
+      if (m.vmu_off != nullptr) b += m.vmu_off[r];
+      wv[r] = b;
+    }
+    g.sync();
+    chol_crout(g, Dt, dinv, wv, n, fail);
+    for (int r = tid; r < n; r += G) wv[r] += rng.normal(VB_AINIT_N, sweep, r);
+    g.sync();
+    back_solve_lt(g, Dt, dinv, wv, a_init, n);
+
+    // ================= store (:502-551) =================
+    if (keep) {
+      double* oc = out.coef + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n * (size_t)T;
+      for (int e = tid; e < n * T; e += G) oc[e] = apath[e];
+      double* ov = out.sigma_v + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n;
+      for (int r = tid; r < n; r += G) ov[r] = 1.0 / q[r];                             // :525
+      if (out.lambda != nullptr) {
+        double* ol = out.lambda + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n;
+        for (int r = tid; r < n; r += G) ol[r] = lam[r];
+      }
+    }
+    g.sync();
+  }
+
+  for (int e = tid; e < kk; e += G) state[e] = sig[e];
+  for (int e = tid; e < n; e += G) { st_q[e] = q[e]; st_ai[e] = a_init[e]; st_lam[e] = lam[e]; }
+  if (sv) {
+    for (int e = tid; e < T * k; e += G) st_h[e] = h[e];
+    for (int e = tid; e < k; e += G) { st_h[T * k + e] = sigma_h[e]; st_h[T * k + k + e] = h_init[e]; }
+  }
+  if (fail && tid == 0) out.status[chain_local] = 1;
+  g.sync();
+}
+
+}  // namespace bvg

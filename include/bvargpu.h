@@ -1,0 +1,209 @@
+/* bvargpu.h -- C ABI of libbvargpu.so, the B200-native Gibbs-sampler hot path behind bvartools'
+ * draw_posterior() / bvarpost().
+ *
+ * Every entry point replaces one FFI entry of the reference (file:line into franzmohr/bvartools):
+ *
+ *   bvg_bvaralg          <-  RcppExport SEXP _bvartools_bvaralg(SEXP)      src/RcppExports.cpp:19-27   (R: .bvaralg,    R/RcppExports.R:4-6)
+ *   bvg_bvartvpalg       <-  RcppExport SEXP _bvartools_bvartvpalg(SEXP)   src/RcppExports.cpp:30-38   (R: .bvartvpalg, R/RcppExports.R:8-10)
+ *   bvg_post_normal      <-  _bvartools_post_normal       (5 args)          src/RcppExports.cpp:318-332
+ *   bvg_post_normal_sur  <-  _bvartools_post_normal_sur   (6 args)          src/RcppExports.cpp:333-348
+ *   bvg_ssvs             <-  _bvartools_ssvs              (5 args)          src/RcppExports.cpp:477-490
+ *   bvg_bvs              <-  _bvartools_bvs               (7 args)          src/RcppExports.cpp:62-77
+ *   bvg_stochvol         <-  _bvartools_stochvol_ksc1998 / _ocsn2007 / _stoch_vol (5 args)   src/RcppExports.cpp:349-463
+ *   bvg_kalman_dk        <-  _bvartools_kalman_dk         (7 args)          src/RcppExports.cpp:196-234
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary: every function returns 0 on success, < 0 for an invalid
+ *     argument / unsupported model, > 0 for a CUDA error (the cudaError_t value); bvg_last_error() returns the
+ *     message of the last failure on the calling thread (the glue maps it to Rcpp::stop()).
+ *   - all matrices are FP64, column-major (Armadillo / R layout); the caller owns every buffer it passes and
+ *     allocates the outputs; device memory is owned by the library.
+ *   - many independent chains per call ("batch"); random variates are Philox4x32-10 keyed by
+ *     (seed, GLOBAL chain id, sweep, site), so results do not depend on thread mapping, launch chunking or on
+ *     how chains are sharded over GPUs / ranks (chain_offset).
+ *   - no CPU fallback: without a CUDA device every compute entry point fails with a message.
+ */
+#ifndef BVARGPU_H
+#define BVARGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BVG_ABI_VERSION 1
+
+/* error-variance prior (priors$sigma, R/add_priors.bvarmodel.R:521-569) */
+#define BVG_SIGMA_WISHART 0
+#define BVG_SIGMA_GAMMA 1
+#define BVG_SIGMA_SV 2
+/* variable selection (priors$coefficients$ssvs / $bvs) */
+#define BVG_VARSEL_NONE 0
+#define BVG_VARSEL_SSVS 1
+#define BVG_VARSEL_BVS 2
+/* residual evaluation: 0 = library decides */
+#define BVG_RESID_AUTO 0
+#define BVG_RESID_DIRECT 1 /* u_t = y_t - A x_t, O(T) per sweep                    (bvaralg.cpp:364)      */
+#define BVG_RESID_MOMENT 2 /* u u' = SSE_ols + (A-A_ols) XX' (A-A_ols)', T-free     (needs X of full rank) */
+/* mixture table of the SV step */
+#define BVG_MIX_KSC1998 7   /* src/stochvol_ksc1998.cpp:74-78 */
+#define BVG_MIX_OCSN2007 10 /* src/stochvol_ocsn2007.cpp:74-84 */
+
+/* Injected random variates (tier-1 parity tests).  NULL = generate with Philox on the device.  Each array is
+ * [chain][sweep][count] with the counts of oracle/variates.py; sweeps = iterations + burnin. */
+typedef struct bvg_inject {
+  const double* coef_normal;    /* n            */
+  const double* ssvs_u;         /* n            */
+  const double* bvs_u1;         /* n            */
+  const double* bvs_u2;         /* n            */
+  const double* sv_u;           /* k*T  ([series][t]) */
+  const double* sv_normal;      /* k*T          */
+  const double* sigma_h_gamma;  /* k            */
+  const double* h_init_normal;  /* k            */
+  const double* omega_gamma;    /* k            */
+  const double* wishart_chi2;   /* k            */
+  const double* wishart_normal; /* k(k-1)/2     */
+  const double* state_normal;   /* n*T          */
+  const double* sigma_v_gamma;  /* n            */
+  const double* a_init_normal;  /* n            */
+} bvg_inject;
+
+/* The flat POD the Rcpp glue fills from the `bvarmodel` list (what src/bvaralg.cpp:9-249 and
+ * src/bvartvpalg.cpp:11-279 unpack by name).  Pure VAR regressors: SUR = kron(Z, I_k) (R/gen_var.R:281). */
+typedef struct bvg_spec {
+  int32_t abi_version; /* BVG_ABI_VERSION */
+  int32_t device;      /* CUDA device ordinal, -1 = current */
+  /* dimensions */
+  int32_t k; /* endogenous variables                                       */
+  int32_t T; /* observations                                               */
+  int32_t M; /* regressors per equation (k p + exogenous + deterministic)  */
+  int32_t tvp;
+  int32_t iterations, burnin;
+  /* batch */
+  int64_t n_chains;     /* chains computed by this call                    */
+  int64_t chain_offset; /* global id of the first one (RNG key)            */
+  uint64_t seed;
+  /* data: data$Y (T x k) and data$Z (T x M) as the samplers use them, transposed */
+  const double* Y; /* k x T  (y = t(Y), bvaralg.cpp:10)               */
+  const double* X; /* M x T  (x = t(Z)); may be NULL when M == 0      */
+  /* priors$coefficients */
+  const double* mu;      /* n = k M                                        */
+  const double* Vi;      /* V^-1: n (diagonal) or n x n, see vi_dense     */
+  int32_t vi_dense;
+  int32_t varsel;        /* BVG_VARSEL_*                                   */
+  const double* tau0;    /* n, SSVS                                        */
+  const double* tau1;    /* n, SSVS                                        */
+  const double* inprior; /* n, SSVS / BVS prior inclusion probability      */
+  const int32_t* include; /* 0-based positions taking part (R's include - 1) */
+  int32_t n_include;
+  /* priors$sigma + initial$sigma */
+  int32_t sigma_type;        /* BVG_SIGMA_*                                */
+  double wishart_df;         /* prior df (posterior df = df + T)           */
+  const double* wishart_scale; /* k x k                                    */
+  const double* sigma_shape; /* k   gamma / SV prior shape                 */
+  const double* sigma_rate;  /* k                                          */
+  const double* sv_mu;       /* k                                          */
+  const double* sv_vi;       /* k x k                                      */
+  const double* sv_sigma_h;  /* k   initial$sigma$sigma_h                  */
+  const double* sv_constant; /* k   initial$sigma$constant                 */
+  const double* sv_h;        /* T x k initial$sigma$h                      */
+  int32_t sv_mixture;        /* BVG_MIX_*                                  */
+  const double* sigma_i;     /* k x k initial$sigma$sigma_i (non-SV)       */
+  /* TVP (priors$coefficients$shape/rate, initial$coefficients$draw) */
+  const double* tvp_shape; /* n */
+  const double* tvp_rate;  /* n */
+  const double* a_init;    /* n */
+  /* tuning / testing */
+  int32_t resid_mode;       /* BVG_RESID_*                                 */
+  int32_t threads_per_chain; /* 0 = auto; 1,2,4,8,16,32 (sub-warp tiles) or a multiple of 32 (CTA per chain) */
+  int32_t sweeps_per_launch; /* 0 = auto: kernel launches are chunked so that D2H copies overlap compute */
+  const bvg_inject* inject;  /* NULL = Philox                              */
+} bvg_spec;
+
+/* Output buffers (caller-allocated; host for bvg_bvaralg / bvg_sampler_fetch).  Per chain a column-major
+ * rows x iterations matrix -- exactly the reference's draws_* matrices (bvaralg.cpp:265-275,
+ * bvartvpalg.cpp:249-265); the glue slices rows into a / b / c.  NULL = not wanted. */
+typedef struct bvg_out {
+  double* coef;    /* [chain][iter][n]     (TVP: [chain][iter][T][n], time-major like vectorise(a_mat)) */
+  double* sigma;   /* [chain][iter][k*k]   (SV: [chain][iter][T][k*k])                                   */
+  double* lambda;  /* [chain][iter][n]     inclusion indicators (SSVS / BVS)                             */
+  double* sigma_h; /* [chain][iter][k]     SV: sigma_h (the reference stores diag(sigma_h) as k*k)       */
+  double* sigma_v; /* [chain][iter][n]     TVP: state variances 1/diag(Sigma_v^-1)                       */
+  int32_t* status; /* [chain]              0 ok, 1 = a Cholesky pivot was not positive (chain continues) */
+} bvg_out;
+
+typedef struct bvg_sampler bvg_sampler; /* opaque: validated spec + device buffers */
+
+/* library */
+const char* bvg_version(void);
+const char* bvg_last_error(void);
+int bvg_device_count(void);
+void* bvg_host_alloc(size_t bytes); /* pinned host memory for outputs (NULL on failure) */
+void bvg_host_free(void* p);
+
+/* sizes of the output rows per retained draw, so the caller can allocate */
+int bvg_out_rows(const bvg_spec* spec, int64_t* coef_rows, int64_t* sigma_rows, int64_t* lambda_rows,
+                 int64_t* sigma_h_rows, int64_t* sigma_v_rows);
+
+/* one-shot drop-ins for .bvaralg / .bvartvpalg: host in, host out */
+int bvg_bvaralg(const bvg_spec* spec, const bvg_out* out);
+int bvg_bvartvpalg(const bvg_spec* spec, const bvg_out* out);
+
+/* handle API: inputs uploaded once, draws stay resident in HBM until fetched */
+int bvg_sampler_create(const bvg_spec* spec, bvg_sampler** sampler);
+int bvg_sampler_reset(bvg_sampler* s);                    /* back to the initial state (re-run the same job) */
+int bvg_sampler_run(bvg_sampler* s, void* cuda_stream);   /* all sweeps, asynchronous on the given stream    */
+int bvg_sampler_run_to_host(bvg_sampler* s, const bvg_out* host_out, void* cuda_stream); /* chunked, D2H overlapped; returns after completion */
+int bvg_sampler_fetch(bvg_sampler* s, const bvg_out* host_out); /* synchronous D2H of everything            */
+int bvg_sampler_device_out(bvg_sampler* s, bvg_out* dev_out);   /* device pointers of the draw buffers       */
+int bvg_sampler_sync(bvg_sampler* s);
+double bvg_sampler_last_kernel_ms(bvg_sampler* s);        /* CUDA-event time of the sweep kernels of the last run */
+int64_t bvg_sampler_launch_count(bvg_sampler* s);         /* kernels launched by the last run                 */
+void bvg_sampler_destroy(bvg_sampler* s);
+
+/* set a callback polled between kernel batches (Rcpp::checkUserInterrupt analogue, bvaralg.cpp:294-296);
+ * a non-zero return aborts the run with error code -100 */
+void bvg_set_interrupt_poll(int (*poll)(void));
+
+/* on-device posterior moments of a draw buffer [chains][iters][rows]: sums[r] = sum x, sumsq[r] = sum x^2
+ * (inputs to an NCCL all-reduce over ranks); device pointers */
+int bvg_moments(const double* dev_draws, int64_t chains, int64_t iters, int64_t rows, double* dev_sums,
+                double* dev_sumsq, void* cuda_stream);
+
+/* measured FP64 FMA throughput of the device (TFLOP/s) -- roofline denominator for the sweep kernels */
+int bvg_fp64_peak(double* tflops_fma, void* cuda_stream);
+
+/* ---- batched stand-alone building blocks (B independent problems per call; host pointers) ---------------- */
+/* post_normal (src/post_normal.cpp:61-93): out[b] = a_post + sqrtm(V_post) eps.  method 0 = symmetric
+ * eigen square root (reference mapping), 1 = Cholesky L^-T (bvaralg mapping). eps NULL = Philox(seed). */
+int bvg_post_normal(int64_t B, int k, int T, int M, const double* y, const double* x, const double* sigma_i,
+                    const double* a_prior, const double* v_i_prior, const double* eps, uint64_t seed,
+                    int method, double* out);
+/* post_normal_sur (src/post_normal_sur.cpp:60-113): z kT x n shared, sigma_i [B][k x k] or [B][kT x k] */
+int bvg_post_normal_sur(int64_t B, int k, int T, int n, const double* y, const double* z, const double* sigma_i,
+                        int sigma_tv, const double* a_prior, const double* v_i_prior, const double* eps,
+                        uint64_t seed, int method, double* out);
+/* ssvs (src/svss.cpp:76-111): a [B][n]; lambda_out [B][n], vdiag_out [B][n] (diagonal of v_i) */
+int bvg_ssvs(int64_t B, int n, const double* a, const double* tau0, const double* tau1, const double* prob_prior,
+             const int32_t* include, int n_include, const double* u, uint64_t seed, double* lambda_out,
+             double* vdiag_out);
+/* bvs (src/bvs.cpp:73-159): constant parameters; lambda [B][n] (diagonal), sigma_i [B][k x k] */
+int bvg_bvs(int64_t B, int k, int T, int M, const double* y, const double* x, const double* a,
+            const double* lambda, const double* sigma_i, const double* prob_prior, const int32_t* include,
+            int n_include, const double* u1, const double* u2, uint64_t seed, double* lambda_out);
+/* stochvol_ksc1998 / stochvol_ocsn2007 / stoch_vol (src/stochvol_*.cpp:60-114): y,h [B][T x k] */
+int bvg_stochvol(int64_t B, int T, int k, const double* y, const double* h, const double* sigma,
+                 const double* h_init, const double* constant, int mixture, const double* u, const double* eps,
+                 uint64_t seed, double* h_out, int32_t* s_out);
+/* kalman_dk (src/kalman_dk.cpp:91-184): y k x T and z kT x n shared; per problem sigma_u (k x k),
+ * sigma_v (n x n), B (n x n), a_init (n), P_init (n x n); out [B][n x (T+1)] */
+int bvg_kalman_dk(int64_t B, int k, int T, int n, const double* y, const double* z, const double* sigma_u,
+                  const double* sigma_v, const double* Bmat, const double* a_init, const double* P_init,
+                  const double* eps, uint64_t seed, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BVARGPU_H */
