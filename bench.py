@@ -1,0 +1,348 @@
+#!/usr/bin/env python3
+"""bench.py -- retained Gibbs draws/sec (chains x iterations, whole box) of the B200 sampler, next to the
+reference-faithful CPU restatement timed on the same box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2a|c3|c4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the hot path over one batch: `chains` independent chains x (iterations + burnin) sweeps of the
+named model (default: BASELINE.json configs[1], e1 VAR(2) normal-Wishart, 4096 chains, 5000 / 1000).  Chains are
+sharded over ranks by global chain id with no data-path collective (weak scaling: `chains` PER GPU); the only
+collective is the NCCL all-reduce of on-device posterior moments at the end of each step.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "retained_gibbs_draws_per_sec"
+UNIT = "draws/s"
+
+
+def build_workload(name, iterations=None, burnin=None):
+    import helpers
+    if name == "c2a":
+        it, bi = iterations or 5000, 1000 if burnin is None else burnin
+        obj = helpers.model_c1(iterations=it, burnin=bi)
+        label = "c2-A: e1 VAR(2)+const, independent normal-Wishart (v_i=0, df=1, scale=1e-4), %d iter / %d burn-in" % (it, bi)
+    elif name == "c3":
+        it, bi = iterations or 5000, 1000 if burnin is None else burnin
+        obj = helpers.model_c3(iterations=it, burnin=bi)
+        label = "c3: synthetic VAR(4) K=6 T=191 SSVS (semiautomatic 0.01/10), %d iter / %d burn-in" % (it, bi)
+    elif name == "c4":
+        it, bi = iterations or 500, 500 if burnin is None else burnin
+        obj = helpers.model_sv(K=3, p=2, nobs=202, iterations=it, burnin=bi, tvp=True)
+        label = "c4: synthetic TVP-VAR(2) K=3 T=200 + KSC-1998 SV, %d iter / %d burn-in" % (it, bi)
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return obj, label
+
+
+def flops_per_sweep(obj, resid_moment):
+    """Algorithmic FP64 flops of one sweep of one chain as EXECUTED ('Roofline accounting').
+    Constant-parameter path: precision build + rhs + Cholesky + two triangular solves + residual cross product
+    + k x k Wishart block.  `resid_moment`: u u' from cross moments (what the kernel does when T > M)."""
+    T, k = obj["data"]["Y"].shape
+    M = obj["data"]["Z"].shape[1]
+    n = k * M
+    if obj["model"].get("tvp"):
+        # per period: Cholesky n^3/3, triangular inverse n^3/3, M'M n^3/3, block build + mat-vecs ~ 6 n^2;
+        # plus residuals, J pdf evaluations per (series, t) and the tridiagonal solves of the SV step
+        return T * (n ** 3 + 6 * n * n) + 2 * k * M * T + T * k * 7 * 30 + 12 * T * k
+    base = n * (n + 1) / 2 + 2 * k * k * M + n + n ** 3 / 3 + 2 * n * n + 5 * k ** 3
+    if resid_moment:
+        return base + 2 * k * M * M + 2 * k * k * M
+    return base + 2 * k * M * T + k * (k + 1) * T
+
+
+def survey_flops_per_sweep(obj):
+    """SURVEY.md section 8d figure (direct residuals): 8424 flop for c1."""
+    T, k = obj["data"]["Y"].shape
+    M = obj["data"]["Z"].shape[1]
+    n = k * M
+    return n * (n + 1) / 2 + 2 * k * k * M + n + n ** 3 / 3 + 2 * n * n + 2 * k * M * T + k * (k + 1) * T + 5 * k ** 3
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.rows, self.stop_flag = device, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.device)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+        sm = [num(r[1]) for r in self.rows if len(r) > 8 and num(r[1]) is not None]
+        mx = [num(r[2]) for r in self.rows if len(r) > 8 and num(r[2]) is not None]
+        pw = [num(r[3]) for r in self.rows if len(r) > 8 and num(r[3]) is not None]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _numpy_oracle_chain(args):
+    obj, seed = args
+    from oracle import samplers
+    from oracle.variates import VariateSource
+    fn = samplers.bvartvpalg if obj["model"].get("tvp") else samplers.bvaralg
+    fn(obj, VariateSource(rng=np.random.default_rng(seed)), literal=True)
+    return 0
+
+
+def cpu_reference_run(obj, label, steps, warmup, sample_sweeps, as_line, n_gpus=1):
+    """The reference's own algorithm (dense restatement: oracle/bvar_dense_ref.c, or the NumPy oracle for SV / TVP /
+    BVS) on all host cores: one chain per core like parallel::mclapply(mc.cores = ncores)."""
+    cores = os.cpu_count() or 1
+    is_c = not (obj["model"].get("tvp") or obj["model"].get("sv") or "bvs" in obj["priors"].get("coefficients", {}))
+    times = []
+    if is_c:
+        from oracle.dense_ref import bvar_dense
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            bvar_dense(obj, n_chains=cores, seed=1 + i, n_threads=cores, dense_gemm=True, iterations=sample_sweeps,
+                       burnin=0)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+        kind_note = "oracle/bvar_dense_ref.c (dense kron(I_T,Sigma^-1) + GEMM + LU solve + chol, plain loops as reference BLAS)"
+    else:
+        import copy
+        from concurrent.futures import ProcessPoolExecutor
+        small = copy.deepcopy(obj)
+        small["model"]["iterations"], small["model"]["burnin"] = sample_sweeps, 0
+        with ProcessPoolExecutor(max_workers=cores) as ex:
+            for i in range(warmup + steps):
+                t0 = time.perf_counter()
+                list(ex.map(_numpy_oracle_chain, [(small, 100 * i + c) for c in range(cores)]))
+                dt = time.perf_counter() - t0
+                if i >= warmup:
+                    times.append(dt)
+        kind_note = "oracle/samplers.py literal dense path (NumPy/SciPy LAPACK), one chain per process"
+    t = float(np.mean(times))
+    value = cores * sample_sweeps / t
+    base = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{cores} chains x {sample_sweeps} sweeps per step; {kind_note}"}
+    if not as_line:
+        return base
+    return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "e1 data set (shipped fixture) / synthetic", "impl": "reference", "config": {"workload": label},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2a")
+    ap.add_argument("--chains", type=int, default=0, help="chains PER GPU (default: 4096 for c2a, 1024 otherwise)")
+    ap.add_argument("--iterations", type=int, default=0)
+    ap.add_argument("--burnin", type=int, default=-1)
+    ap.add_argument("--threads-per-chain", type=int, default=0)
+    ap.add_argument("--cpu-sweeps", type=int, default=0, help="sweeps per chain of the CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    obj, label = build_workload(args.workload, args.iterations or None, None if args.burnin < 0 else args.burnin)
+    cpu_sweeps = args.cpu_sweeps or {"c2a": 1500, "c3": 8, "c4": 2}.get(args.workload, 50)
+
+    if args.impl == "reference":
+        if rank == 0:
+            line = cpu_reference_run(obj, label, args.steps, min(args.warmup, 1), cpu_sweeps, True, n_gpus=args.gpus)
+            print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from bvartools_b200 import ChainSampler, _abi, pinned_empty
+    from bvartools_b200._lib import check, lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = lib()
+    chains = args.chains or (4096 if args.workload == "c2a" else 1024)
+    it, bi = obj["model"]["iterations"], obj["model"]["burnin"]
+    seed = 20240113
+    stream = torch.cuda.current_stream()
+
+    sampler = ChainSampler(obj, n_chains=chains, seed=seed, chain_offset=rank * chains, device=local_rank,
+                           threads_per_chain=args.threads_per_chain)
+    rows = sampler.spec.out_rows()
+    dout = sampler.device_out()
+    n_out = rows["coef"]
+    sums = torch.zeros(n_out, dtype=torch.float64, device=dev)
+    sumsq = torch.zeros(n_out, dtype=torch.float64, device=dev)
+
+    def step():
+        sampler.reset()
+        sampler.run(stream.cuda_stream)
+        check(L.bvg_moments(C.cast(dout.coef, C.c_void_p), chains, it, n_out, C.c_void_p(sums.data_ptr()),
+                            C.c_void_p(sumsq.data_ptr()), C.c_void_p(stream.cuda_stream)))
+        if world > 1:
+            dist.all_reduce(sums)
+            dist.all_reduce(sumsq)
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    fence()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sweep_ms = []
+    fence()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    fence()
+    elapsed_ms = e0.elapsed_time(e1)
+    # duration of the sweep kernels of the last step, from the library's CUDA events on the launching stream
+    last_sweep_ms = sampler.last_kernel_ms
+    launches_per_step = int(sampler.launch_count) + 1          # + the moments kernel
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    if rank == 0:
+        clocks.stop_flag.set()
+        clocks.join(timeout=3)
+    ms_per_step = elapsed_ms / args.steps
+    total_draws = world * chains * it
+    value = total_draws / (ms_per_step * 1e-3)
+    post_mean = (sums / (world * chains * it)).cpu().numpy()
+    tpc_used = sampler.spec.c.threads_per_chain
+
+    # ---- end to end through the public API: host inputs -> H2D -> sweeps -> D2H into pinned host memory
+    e2e = None
+    if not args.no_e2e:
+        host = _abi.OutBuffers(sampler.spec, alloc=pinned_empty)
+        d2h = sum(a.nbytes for a in host.arrays.values()) + host.status.nbytes
+        sampler.close()
+        e2e_times, h2d, checksum = [], 0, 0.0
+        n_warm = 2
+        for i in range(n_warm + args.steps):
+            fence()
+            t0 = time.perf_counter()
+            s = ChainSampler(obj, n_chains=chains, seed=seed, chain_offset=rank * chains, device=local_rank,
+                             threads_per_chain=args.threads_per_chain)          # validates + uploads the inputs
+            s.run_to_host(host, stream.cuda_stream)                             # sweeps, D2H overlapped
+            checksum = float(host.arrays["coef"][0, -1, 0])                     # host read of the result
+            fence()
+            dt = time.perf_counter() - t0
+            h2d = sum(v.nbytes for v in s.spec.keep.values())
+            s.close()
+            if i >= n_warm:
+                e2e_times.append(dt)
+        te = torch.tensor([float(np.mean(e2e_times))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_draws / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
+               "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": float(te.item()) * 1e3,
+               "api": "ChainSampler(model).run_to_host(pinned out) = bvg_sampler_create + bvg_sampler_run_to_host",
+               "checksum": checksum}
+    else:
+        sampler.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (the sweep kernel): executed algorithmic FP64 flops / launch time
+    moment = not (obj["model"].get("tvp") or obj["model"].get("sv")) and \
+        obj["data"]["Y"].shape[0] > obj["data"]["Z"].shape[1]
+    fl_sweep = flops_per_sweep(obj, moment)
+    peak = C.c_double(0.0)
+    check(L.bvg_fp64_peak(C.byref(peak), None))
+    sweep_kernel_s = last_sweep_ms * 1e-3
+    achieved = fl_sweep * chains * (it + bi) / sweep_kernel_s / 1e12
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    out_bytes = 8.0 * chains * it * sum(rows.values())
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
+                "frac": achieved / peak.value if peak.value > 0 else None, "traffic": None,
+                "kernel": "tvp sweep kernel" if obj["model"].get("tvp") else "bvar sweep kernel",
+                "peak_source": "FP64 FMA probe kernel run live by bench.py (bvg_fp64_peak); MEASURED_PEAKS.json "
+                               "has no FP64 entry",
+                "flops_per_sweep_executed": fl_sweep, "flops_per_sweep_survey": survey_flops_per_sweep(obj),
+                "sweep_kernel_ms_per_step": last_sweep_ms, "sweep_share_of_step": last_sweep_ms / ms_per_step,
+                "hbm_write_GBps": out_bytes / sweep_kernel_s / 1e9, "hbm_peak_GBps": peaks.get("hbm_gbs")}
+    cpu = None
+    if not args.no_cpu:
+        cpu = cpu_reference_run(obj, label, 1, 0, cpu_sweeps, False)
+    par = "1 GPU" if world == 1 else (f"chains sharded over {world} GPUs by global chain id, no data-path "
+                                      "collective; NCCL all-reduce of posterior moments per step")
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64",
+            "data": "e1 data set (shipped fixture)" if args.workload == "c2a" else "synthetic",
+            "config": {"workload": label, "chains_per_gpu": chains, "chains_total": chains * world,
+                       "parallelism": par,
+                       "l2": f"retained draws {out_bytes / 1e9:.2f} GB per step per GPU >> 126 MB L2 (no flush needed)",
+                       "threads_per_chain": tpc_used or "auto"},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu,
+            "posterior_mean_first3": [float(v) for v in post_mean[:3]]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,422 @@
+// bvg_api.cu -- C ABI of libbvargpu.so (include/bvargpu.h): validation, device residency, launch sequencing.
+//
+// Host side of the drop-in boundary.  Replaces the body of the reference's exported samplers
+// (_bvartools_bvaralg / _bvartools_bvartvpalg, src/RcppExports.cpp:19-38): inputs are uploaded once, all
+// iterations + burnin sweeps run on the GPU without host round trips (chunked only so that device->host
+// copies of retained draws overlap the next chunk and the interrupt callback can be polled, the analogue of
+// Rcpp::checkUserInterrupt every 20 draws, bvaralg.cpp:294-296), and the draws_* matrices come back in the
+// reference's layout.  There is no CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "bvg_kernels.cuh"
+#include "bvg_prepare.hpp"
+
+using namespace bvg;
+
+static thread_local std::string g_last_error;
+static int (*g_poll)(void) = nullptr;
+
+static int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return (int)e > 0 ? (int)e : 999;
+}
+#define CK(call)                                              \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call);     \
+  } while (0)
+
+struct bvg_sampler {
+  Prepared P;
+  int device = 0;
+  long long n_chains = 0;
+  long long chain_offset = 0;
+  uint64_t seed = 0;
+  int sweeps = 0;
+  int chunk = 0;
+  int requested_tpc = 0;
+  // device memory
+  double* d_blob = nullptr;
+  unsigned char* d_include = nullptr;
+  double* d_state = nullptr;
+  double* d_state0 = nullptr;   // one chain's initial state
+  double* d_scratch = nullptr;  // TVP
+  long long scratch_per_chain = 0;
+  double* d_inj[VB_COUNT] = {nullptr};
+  // outputs (device)
+  double* d_coef = nullptr; double* d_sigma = nullptr; double* d_lambda = nullptr; double* d_sigma_h = nullptr;
+  double* d_sigma_v = nullptr; int* d_status = nullptr;
+  long long rows_coef = 0, rows_sigma = 0, rows_lambda = 0, rows_sigma_h = 0, rows_sigma_v = 0;
+  // launch
+  BvarModel bm; TvpModel tm; RngParams rp; LaunchPlan plan;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> chunk_ev;
+  bool timed = false;
+  long long launches = 0;
+};
+
+static void rows_of(const Prepared& P, long long* coef, long long* sigma, long long* lambda, long long* sh,
+                    long long* sv) {
+  const long long k = P.k, T = P.T, n = P.n;
+  const bool svm = P.sigma_type == BVG_SIGMA_SV;
+  *coef = P.tvp ? n * T : n;
+  *sigma = svm ? k * k * T : k * k;
+  *lambda = (P.varsel != BVG_VARSEL_NONE) ? n : 0;
+  *sh = svm ? k : 0;
+  *sv = P.tvp ? n : 0;
+}
+
+extern "C" {
+
+const char* bvg_version(void) { return "bvargpu 0.1.0 (sm_100a, abi 1)"; }
+const char* bvg_last_error(void) { return g_last_error.c_str(); }
+
+int bvg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void* bvg_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void bvg_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+void bvg_set_interrupt_poll(int (*poll)(void)) { g_poll = poll; }
+
+int bvg_out_rows(const bvg_spec* spec, int64_t* coef_rows, int64_t* sigma_rows, int64_t* lambda_rows,
+                 int64_t* sigma_h_rows, int64_t* sigma_v_rows) {
+  if (!spec) return fail(-1, "spec is NULL");
+  Prepared P;
+  P.k = spec->k; P.T = spec->T; P.M = spec->M; P.n = spec->k * spec->M; P.tvp = spec->tvp ? 1 : 0;
+  P.sigma_type = spec->sigma_type; P.varsel = spec->varsel;
+  long long a, b, c, d, e;
+  rows_of(P, &a, &b, &c, &d, &e);
+  if (coef_rows) *coef_rows = a;
+  if (sigma_rows) *sigma_rows = b;
+  if (lambda_rows) *lambda_rows = c;
+  if (sigma_h_rows) *sigma_h_rows = d;
+  if (sigma_v_rows) *sigma_v_rows = e;
+  return 0;
+}
+
+void bvg_sampler_destroy(bvg_sampler* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaFree(s->d_blob); cudaFree(s->d_include); cudaFree(s->d_state); cudaFree(s->d_state0); cudaFree(s->d_scratch);
+  for (int b = 0; b < VB_COUNT; ++b) cudaFree(s->d_inj[b]);
+  cudaFree(s->d_coef); cudaFree(s->d_sigma); cudaFree(s->d_lambda); cudaFree(s->d_sigma_h); cudaFree(s->d_sigma_v);
+  cudaFree(s->d_status);
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  for (cudaEvent_t e : s->chunk_ev) cudaEventDestroy(e);
+  delete s;
+}
+
+static int alloc_out(double** p, long long chains, long long iters, long long rows) {
+  if (rows == 0) { *p = nullptr; return 0; }
+  CK(cudaMalloc(p, (size_t)chains * (size_t)iters * (size_t)rows * sizeof(double)));
+  return 0;
+}
+
+int bvg_sampler_reset(bvg_sampler* s) {
+  if (!s) return fail(-1, "sampler is NULL");
+  CK(cudaSetDevice(s->device));
+  // replicate the single initial state to every chain (device-side strided copy via 2D memcpy with pitch 0 is not
+  // allowed, so broadcast with a tiny kernel-free loop of async copies in doubling steps)
+  const size_t len = (size_t)s->P.state_len * sizeof(double);
+  CK(cudaMemcpy(s->d_state, s->d_state0, len, cudaMemcpyDeviceToDevice));
+  long long have = 1;
+  while (have < s->n_chains) {
+    const long long cnt = (have < s->n_chains - have) ? have : s->n_chains - have;
+    CK(cudaMemcpy((char*)s->d_state + (size_t)have * len, s->d_state, (size_t)cnt * len, cudaMemcpyDeviceToDevice));
+    have += cnt;
+  }
+  CK(cudaMemset(s->d_status, 0, (size_t)s->n_chains * sizeof(int)));
+  return 0;
+}
+
+int bvg_sampler_create(const bvg_spec* spec, bvg_sampler** out) {
+  if (!out) return fail(-1, "sampler output pointer is NULL");
+  *out = nullptr;
+  bvg_sampler* s = new bvg_sampler();
+  int rc = prepare(spec, s->P);
+  if (rc != 0) { std::string m = s->P.error; delete s; return fail(rc, m); }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    delete s;
+    return fail(-50, "no CUDA device available: libbvargpu has no CPU fallback");
+  }
+  if (spec->device >= 0) {
+    if (spec->device >= ndev) { delete s; return fail(-51, "device ordinal out of range"); }
+    s->device = spec->device;
+  } else {
+    cudaGetDevice(&s->device);
+  }
+#define CKS(call)                                                                     \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) { int r__ = cuda_fail(e__, #call); bvg_sampler_destroy(s); return r__; } \
+  } while (0)
+  CKS(cudaSetDevice(s->device));
+  const Prepared& P = s->P;
+  s->n_chains = spec->n_chains;
+  s->chain_offset = spec->chain_offset;
+  s->seed = spec->seed;
+  s->sweeps = P.iterations + P.burnin;
+  s->requested_tpc = spec->threads_per_chain;
+  s->chunk = spec->sweeps_per_launch > 0 ? spec->sweeps_per_launch : 0;
+  rows_of(P, &s->rows_coef, &s->rows_sigma, &s->rows_lambda, &s->rows_sigma_h, &s->rows_sigma_v);
+
+  CKS(cudaMalloc(&s->d_blob, P.blob.size() * sizeof(double)));
+  CKS(cudaMemcpy(s->d_blob, P.blob.data(), P.blob.size() * sizeof(double), cudaMemcpyHostToDevice));
+  if (!P.include.empty()) {
+    CKS(cudaMalloc(&s->d_include, P.include.size()));
+    CKS(cudaMemcpy(s->d_include, P.include.data(), P.include.size(), cudaMemcpyHostToDevice));
+  }
+  CKS(cudaMalloc(&s->d_state0, (size_t)P.state_len * sizeof(double)));
+  CKS(cudaMemcpy(s->d_state0, P.state0.data(), (size_t)P.state_len * sizeof(double), cudaMemcpyHostToDevice));
+  CKS(cudaMalloc(&s->d_state, (size_t)s->n_chains * P.state_len * sizeof(double)));
+  CKS(cudaMalloc(&s->d_status, (size_t)s->n_chains * sizeof(int)));
+  if (P.tvp) {
+    s->scratch_per_chain = tvp_scratch_len(P.T, P.n);
+    CKS(cudaMalloc(&s->d_scratch, (size_t)s->n_chains * (size_t)s->scratch_per_chain * sizeof(double)));
+    bind_tvp(P, s->d_blob, s->d_include, &s->tm);
+  } else {
+    bind_bvar(P, s->d_blob, s->d_include, &s->bm);
+  }
+  // injected variates
+  memset(&s->rp, 0, sizeof(s->rp));
+  s->rp.seed = s->seed;
+  s->rp.chain_offset = (uint64_t)s->chain_offset;
+  if (spec->inject) {
+    const int k = P.k, T = P.T, n = P.n;
+    const double* ptr[VB_COUNT] = {spec->inject->coef_normal, spec->inject->ssvs_u, spec->inject->bvs_u1,
+                                   spec->inject->bvs_u2, spec->inject->sv_u, spec->inject->sv_normal,
+                                   spec->inject->sigma_h_gamma, spec->inject->h_init_normal,
+                                   spec->inject->omega_gamma, spec->inject->wishart_chi2,
+                                   spec->inject->wishart_normal, spec->inject->state_normal,
+                                   spec->inject->sigma_v_gamma, spec->inject->a_init_normal};
+    const int cnt[VB_COUNT] = {n, n, n, n, k * T, k * T, k, k, k, k, k * (k - 1) / 2, n * T, n, n};
+    for (int b = 0; b < VB_COUNT; ++b) {
+      if (!ptr[b] || cnt[b] == 0) continue;
+      const size_t bytes = (size_t)s->n_chains * s->sweeps * cnt[b] * sizeof(double);
+      CKS(cudaMalloc(&s->d_inj[b], bytes));
+      CKS(cudaMemcpy(s->d_inj[b], ptr[b], bytes, cudaMemcpyHostToDevice));
+      s->rp.inj[b] = s->d_inj[b];
+      s->rp.inj_stride[b] = cnt[b];
+      s->rp.inj_chain_stride[b] = (long long)s->sweeps * cnt[b];
+    }
+  }
+  // outputs
+  if (alloc_out(&s->d_coef, s->n_chains, P.iterations, s->rows_coef) ||
+      alloc_out(&s->d_sigma, s->n_chains, P.iterations, s->rows_sigma) ||
+      alloc_out(&s->d_lambda, s->n_chains, P.iterations, s->rows_lambda) ||
+      alloc_out(&s->d_sigma_h, s->n_chains, P.iterations, s->rows_sigma_h) ||
+      alloc_out(&s->d_sigma_v, s->n_chains, P.iterations, s->rows_sigma_v)) {
+    std::string m = g_last_error;
+    bvg_sampler_destroy(s);
+    return fail(2, m);
+  }
+  cudaError_t pe = P.tvp ? plan_tvp(s->tm, s->n_chains, s->requested_tpc, &s->plan)
+                         : plan_bvar(s->bm, s->n_chains, s->requested_tpc, &s->plan);
+  if (pe != cudaSuccess) {
+    bvg_sampler_destroy(s);
+    return fail(-52, "model does not fit the shared-memory kernels (n too large for this path) or invalid threads_per_chain");
+  }
+  CKS(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  CKS(cudaEventCreate(&s->ev0));
+  CKS(cudaEventCreate(&s->ev1));
+  rc = bvg_sampler_reset(s);
+  if (rc != 0) { bvg_sampler_destroy(s); return rc; }
+#undef CKS
+  *out = s;
+  return 0;
+}
+
+static int launch_chunk(bvg_sampler* s, int s0, int s1, cudaStream_t stream) {
+  const Prepared& P = s->P;
+  cudaError_t e;
+  if (P.tvp) {
+    TvpOut o;
+    o.coef = s->d_coef; o.sigma = s->d_sigma; o.lambda = s->d_lambda; o.sigma_h = s->d_sigma_h;
+    o.sigma_v = s->d_sigma_v; o.status = s->d_status; o.iters = P.iterations;
+    e = launch_tvp(s->plan, s->tm, s->rp, s->d_state, P.state_len, s->d_scratch, s->scratch_per_chain, o,
+                   s->n_chains, s0, s1, P.burnin, stream);
+  } else {
+    BvarOut o;
+    o.coef = s->d_coef; o.sigma = s->d_sigma; o.lambda = s->d_lambda; o.sigma_h = s->d_sigma_h;
+    o.status = s->d_status; o.iters = P.iterations;
+    e = launch_bvar(s->plan, s->bm, s->rp, s->d_state, P.state_len, o, s->n_chains, s0, s1, P.burnin, stream);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+  s->launches += 1;
+  return 0;
+}
+
+static int default_chunk(const bvg_sampler* s) {
+  if (s->chunk > 0) return s->chunk;
+  int c = (s->sweeps + 11) / 12;
+  if (c < 20) c = 20;
+  return c;
+}
+
+int bvg_sampler_run(bvg_sampler* s, void* cuda_stream) {
+  if (!s) return fail(-1, "sampler is NULL");
+  CK(cudaSetDevice(s->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int chunk = default_chunk(s);
+  s->launches = 0;
+  CK(cudaEventRecord(s->ev0, st));
+  for (int s0 = 0; s0 < s->sweeps; s0 += chunk) {
+    const int s1 = (s0 + chunk < s->sweeps) ? s0 + chunk : s->sweeps;
+    int rc = launch_chunk(s, s0, s1, st);
+    if (rc) return rc;
+    if (g_poll) {   // the callback is only meaningful between finished batches
+      CK(cudaStreamSynchronize(st));
+      if (g_poll()) return fail(-100, "interrupted");
+    }
+  }
+  CK(cudaEventRecord(s->ev1, st));
+  s->timed = true;
+  return 0;
+}
+
+static int copy_rows(double* host, const double* dev, long long chains, long long iters, long long rows,
+                     long long it0, long long it1, cudaStream_t st) {
+  if (!host || !dev || rows == 0 || it1 <= it0) return 0;
+  const size_t pitch = (size_t)iters * rows * sizeof(double);
+  const size_t width = (size_t)(it1 - it0) * rows * sizeof(double);
+  const size_t off = (size_t)it0 * rows;
+  CK(cudaMemcpy2DAsync(host + off, pitch, dev + off, pitch, width, (size_t)chains, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+int bvg_sampler_run_to_host(bvg_sampler* s, const bvg_out* h, void* cuda_stream) {
+  if (!s || !h) return fail(-1, "sampler / output is NULL");
+  CK(cudaSetDevice(s->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const Prepared& P = s->P;
+  const int chunk = default_chunk(s);
+  const int nchunks = (s->sweeps + chunk - 1) / chunk;
+  while ((int)s->chunk_ev.size() < nchunks) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    s->chunk_ev.push_back(e);
+  }
+  s->launches = 0;
+  CK(cudaEventRecord(s->ev0, st));
+  int ci = 0;
+  for (int s0 = 0; s0 < s->sweeps; s0 += chunk, ++ci) {
+    const int s1 = (s0 + chunk < s->sweeps) ? s0 + chunk : s->sweeps;
+    int rc = launch_chunk(s, s0, s1, st);
+    if (rc) return rc;
+    CK(cudaEventRecord(s->chunk_ev[ci], st));
+    const long long it0 = (s0 > P.burnin ? s0 : P.burnin) - P.burnin;
+    const long long it1 = (long long)s1 - P.burnin;
+    if (it1 > it0) {
+      CK(cudaStreamWaitEvent(s->copy_stream, s->chunk_ev[ci], 0));
+      if ((rc = copy_rows(h->coef, s->d_coef, s->n_chains, P.iterations, s->rows_coef, it0, it1, s->copy_stream))) return rc;
+      if ((rc = copy_rows(h->sigma, s->d_sigma, s->n_chains, P.iterations, s->rows_sigma, it0, it1, s->copy_stream))) return rc;
+      if ((rc = copy_rows(h->lambda, s->d_lambda, s->n_chains, P.iterations, s->rows_lambda, it0, it1, s->copy_stream))) return rc;
+      if ((rc = copy_rows(h->sigma_h, s->d_sigma_h, s->n_chains, P.iterations, s->rows_sigma_h, it0, it1, s->copy_stream))) return rc;
+      if ((rc = copy_rows(h->sigma_v, s->d_sigma_v, s->n_chains, P.iterations, s->rows_sigma_v, it0, it1, s->copy_stream))) return rc;
+    }
+    if (g_poll) {
+      CK(cudaStreamSynchronize(st));
+      if (g_poll()) { cudaDeviceSynchronize(); return fail(-100, "interrupted"); }
+    }
+  }
+  CK(cudaEventRecord(s->ev1, st));
+  s->timed = true;
+  CK(cudaStreamSynchronize(st));
+  if (h->status) CK(cudaMemcpyAsync(h->status, s->d_status, (size_t)s->n_chains * sizeof(int), cudaMemcpyDeviceToHost, s->copy_stream));
+  CK(cudaStreamSynchronize(s->copy_stream));
+  return 0;
+}
+
+int bvg_sampler_sync(bvg_sampler* s) {
+  if (!s) return fail(-1, "sampler is NULL");
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int bvg_sampler_fetch(bvg_sampler* s, const bvg_out* h) {
+  if (!s || !h) return fail(-1, "sampler / output is NULL");
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  const size_t per = (size_t)s->n_chains * s->P.iterations * sizeof(double);
+  if (h->coef && s->d_coef) CK(cudaMemcpy(h->coef, s->d_coef, per * s->rows_coef, cudaMemcpyDeviceToHost));
+  if (h->sigma && s->d_sigma) CK(cudaMemcpy(h->sigma, s->d_sigma, per * s->rows_sigma, cudaMemcpyDeviceToHost));
+  if (h->lambda && s->d_lambda) CK(cudaMemcpy(h->lambda, s->d_lambda, per * s->rows_lambda, cudaMemcpyDeviceToHost));
+  if (h->sigma_h && s->d_sigma_h) CK(cudaMemcpy(h->sigma_h, s->d_sigma_h, per * s->rows_sigma_h, cudaMemcpyDeviceToHost));
+  if (h->sigma_v && s->d_sigma_v) CK(cudaMemcpy(h->sigma_v, s->d_sigma_v, per * s->rows_sigma_v, cudaMemcpyDeviceToHost));
+  if (h->status) CK(cudaMemcpy(h->status, s->d_status, (size_t)s->n_chains * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bvg_sampler_device_out(bvg_sampler* s, bvg_out* d) {
+  if (!s || !d) return fail(-1, "sampler / output is NULL");
+  d->coef = s->d_coef; d->sigma = s->d_sigma; d->lambda = s->d_lambda; d->sigma_h = s->d_sigma_h;
+  d->sigma_v = s->d_sigma_v; d->status = s->d_status;
+  return 0;
+}
+
+double bvg_sampler_last_kernel_ms(bvg_sampler* s) {
+  if (!s || !s->timed) return -1.0;
+  cudaSetDevice(s->device);
+  if (cudaEventSynchronize(s->ev1) != cudaSuccess) return -1.0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+int64_t bvg_sampler_launch_count(bvg_sampler* s) { return s ? s->launches : 0; }
+
+static int one_shot(const bvg_spec* spec, const bvg_out* out, int want_tvp) {
+  if (!spec || !out) return fail(-1, "spec / out is NULL");
+  if ((spec->tvp ? 1 : 0) != want_tvp)
+    return fail(-10, want_tvp ? "bvg_bvartvpalg needs spec.tvp = 1" : "bvg_bvaralg needs spec.tvp = 0");
+  bvg_sampler* s = nullptr;
+  int rc = bvg_sampler_create(spec, &s);
+  if (rc) return rc;
+  rc = bvg_sampler_run_to_host(s, out, nullptr);
+  std::string keep = g_last_error;
+  bvg_sampler_destroy(s);
+  if (rc) g_last_error = keep;
+  return rc;
+}
+
+int bvg_bvaralg(const bvg_spec* spec, const bvg_out* out) { return one_shot(spec, out, 0); }
+int bvg_bvartvpalg(const bvg_spec* spec, const bvg_out* out) { return one_shot(spec, out, 1); }
+
+int bvg_moments(const double* dev_draws, int64_t chains, int64_t iters, int64_t rows, double* dev_sums,
+                double* dev_sumsq, void* cuda_stream) {
+  if (!dev_draws || !dev_sums || !dev_sumsq || rows < 1) return fail(-1, "invalid arguments to bvg_moments");
+  cudaError_t e = launch_moments(dev_draws, chains, iters, rows, dev_sums, dev_sumsq, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "moments kernel");
+  return 0;
+}
+
+int bvg_fp64_peak(double* tflops_fma, void* cuda_stream) {
+  if (!tflops_fma) return fail(-1, "output pointer is NULL");
+  if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");
+  cudaError_t e = launch_fp64_peak(tflops_fma, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "fp64 peak probe");
+  return 0;
+}
+
+}  // extern "C"

@@ -12,7 +12,7 @@
 namespace bvg {
 
 #if BVG_G > 0
-__global__ void __launch_bounds__(128) BVG_CAT(bvar_tile_kernel_g, BVG_G)(
+__global__ void __launch_bounds__(128, 8) BVG_CAT(bvar_tile_kernel_g, BVG_G)(
     const __grid_constant__ BvarModel m, const __grid_constant__ RngParams rp, double* state, int state_len,
     const __grid_constant__ BvarOut out, long long n_chains, int s0, int s1, int burnin, int smem_per_chain) {
   extern __shared__ double smem[];

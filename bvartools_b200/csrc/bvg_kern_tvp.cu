@@ -11,7 +11,7 @@
 namespace bvg {
 
 #if BVG_G > 0
-__global__ void __launch_bounds__(128) BVG_CAT(tvp_tile_kernel_g, BVG_G)(
+__global__ void __launch_bounds__(128, 6) BVG_CAT(tvp_tile_kernel_g, BVG_G)(
     const __grid_constant__ TvpModel m, const __grid_constant__ RngParams rp, double* state, int state_len,
     double* scratch, long long scratch_per_chain, const __grid_constant__ TvpOut out, long long n_chains, int s0,
     int s1, int burnin, int smem_per_chain) {

@@ -1,0 +1,183 @@
+"""Host-side mirror of the reference's sampler entry points, calling the CUDA library through the C ABI.
+
+  bvaralg(object)     <-> .bvaralg(object)     (R/RcppExports.R:4-6,  src/bvaralg.cpp:6)
+  bvartvpalg(object)  <-> .bvartvpalg(object)  (R/RcppExports.R:8-10, src/bvartvpalg.cpp:9)
+
+Same input list, same return value: `{data, model, priors, posteriors}` with `posteriors$a|b|c$coeffs` (rows x
+iterations), `$lambda`, TVP `$sigma`, and `posteriors$sigma${coeffs,sigma}` (src/bvaralg.cpp:562-627,
+src/bvartvpalg.cpp:555-626).  In addition `run_chains` runs many independent chains of one model in a single
+launch (the batched entry of SURVEY.md section 8b) and `ChainSampler` keeps the draws resident in HBM.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._lib import BvgError, check, lib, require_device
+
+__all__ = ["bvaralg", "bvartvpalg", "run_chains", "ChainSampler", "pinned_empty", "split_posteriors"]
+
+
+class _Pinned(np.ndarray):
+    """ndarray view of cudaHostAlloc memory; frees it when the base array dies."""
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """Page-locked host array (for overlapped device->host copies of the draws)."""
+    L = lib()
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = L.bvg_host_alloc(max(nbytes, 8))
+    if not ptr:
+        raise MemoryError("cudaHostAlloc failed")
+    buf = (C.c_char * max(nbytes, 8)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    class _Owner:
+        def __init__(self, p):
+            self.p = p
+
+        def __del__(self):
+            try:
+                L.bvg_host_free(self.p)
+            except Exception:
+                pass
+    out = arr.view(_Pinned)
+    out._owner = _Owner(ptr)
+    out._buf = buf
+    return out
+
+
+def _seed(seed):
+    if seed is None:
+        return int.from_bytes(os.urandom(8), "little")
+    return int(seed)
+
+
+class ChainSampler:
+    """Handle API: inputs uploaded once; retained draws stay in HBM until fetched (bvg_sampler_*)."""
+
+    def __init__(self, obj, n_chains=1, seed=None, chain_offset=0, device=-1, inject=None, **tuning):
+        require_device()
+        self.spec = _abi.spec_from_model(obj, n_chains=n_chains, seed=_seed(seed), chain_offset=chain_offset,
+                                         device=device, inject=inject, **tuning)
+        self.handle = C.c_void_p()
+        check(lib().bvg_sampler_create(C.byref(self.spec.c), C.byref(self.handle)))
+
+    def reset(self):
+        check(lib().bvg_sampler_reset(self.handle))
+
+    def run(self, stream=0):
+        check(lib().bvg_sampler_run(self.handle, C.c_void_p(stream)))
+
+    def sync(self):
+        check(lib().bvg_sampler_sync(self.handle))
+
+    def run_to_host(self, out: _abi.OutBuffers, stream=0):
+        check(lib().bvg_sampler_run_to_host(self.handle, C.byref(out.c), C.c_void_p(stream)))
+
+    def fetch(self, out: _abi.OutBuffers | None = None):
+        out = out or _abi.OutBuffers(self.spec)
+        check(lib().bvg_sampler_fetch(self.handle, C.byref(out.c)))
+        return out
+
+    def device_out(self):
+        d = _abi.BvgOut()
+        check(lib().bvg_sampler_device_out(self.handle, C.byref(d)))
+        return d
+
+    @property
+    def last_kernel_ms(self):
+        return lib().bvg_sampler_last_kernel_ms(self.handle)
+
+    @property
+    def launch_count(self):
+        return lib().bvg_sampler_launch_count(self.handle)
+
+    def close(self):
+        if self.handle:
+            lib().bvg_sampler_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run_chains(obj, n_chains=1, seed=None, chain_offset=0, device=-1, inject=None, pinned=False, **tuning):
+    """Run `n_chains` independent chains of one model; returns dict of [chain][iter][rows] arrays + 'status'."""
+    require_device()
+    spec = _abi.spec_from_model(obj, n_chains=n_chains, seed=_seed(seed), chain_offset=chain_offset, device=device,
+                                inject=inject, **tuning)
+    out = _abi.OutBuffers(spec, alloc=pinned_empty if pinned else None)
+    fn = lib().bvg_bvartvpalg if spec.c.tvp else lib().bvg_bvaralg
+    check(fn(C.byref(spec.c), C.byref(out.c)))
+    res = dict(out.arrays)
+    res["status"] = out.status
+    return res
+
+
+def split_posteriors(obj, arrays, chain=0):
+    """[iter][rows] draws of one chain -> the reference's `posteriors` list (rows x iterations matrices)."""
+    model = obj["model"]
+    Y = np.asarray(obj["data"]["Y"])
+    T, k = Y.shape
+    p = int(model["endogen"]["lags"])
+    n_a = k * k * p
+    n_b = 0
+    if "exogen" in model:
+        n_b = k * len(model["exogen"]["variables"]) * (int(model["exogen"]["lags"]) + 1)
+    n_c = k * len(model.get("deterministic", []))
+    n = n_a + n_b + n_c
+    tvp = bool(model.get("tvp"))
+    post = {"a0": None, "a": None, "b": None, "c": None, "sigma": None}
+    coef = arrays.get("coef")
+    lam = arrays.get("lambda")
+    off = 0
+    for name, cnt in (("a", n_a), ("b", n_b), ("c", n_c)):
+        if cnt > 0 and coef is not None:
+            d = {}
+            c_ = coef[chain]                                        # [iter][rows]
+            if tvp:
+                it = c_.shape[0]
+                cube = c_.reshape(it, T, n)                         # [iter][t][n]
+                d["coeffs"] = cube[:, :, off:off + cnt].reshape(it, T * cnt).T      # (cnt*T) x iter, time-major
+                d["sigma"] = arrays["sigma_v"][chain][:, off:off + cnt].T
+            else:
+                d["coeffs"] = c_[:, off:off + cnt].T
+            if lam is not None:
+                d["lambda"] = lam[chain][:, off:off + cnt].T
+            post[name] = d
+        off += cnt
+    sig = {"coeffs": arrays["sigma"][chain].T}
+    if "sigma_h" in arrays:
+        sh = arrays["sigma_h"][chain]                               # [iter][k] -> vec(diag(sigma_h)) k*k x iter
+        full = np.zeros((sh.shape[0], k, k))
+        full[:, np.arange(k), np.arange(k)] = sh
+        sig["sigma"] = full.reshape(sh.shape[0], k * k).T
+    post["sigma"] = sig
+    return post
+
+
+def _one(obj, want_tvp, seed, **kw):
+    if bool(obj["model"].get("tvp")) != want_tvp:
+        raise BvgError(-10, "model$tvp does not match the sampler called")
+    arrays = run_chains(obj, n_chains=1, seed=seed, **kw)
+    if arrays["status"][0] != 0:
+        raise BvgError(1, "a posterior precision matrix was not positive definite")
+    return {"data": obj["data"], "model": obj["model"], "priors": obj["priors"],
+            "posteriors": split_posteriors(obj, arrays, 0)}
+
+
+def bvaralg(obj, seed=None, **kw):
+    """Drop-in for `.bvaralg(object)`: one chain of the constant-parameter BVAR Gibbs sampler."""
+    return _one(obj, False, seed, **kw)
+
+
+def bvartvpalg(obj, seed=None, **kw):
+    """Drop-in for `.bvartvpalg(object)`: one chain of the TVP BVAR Gibbs sampler."""
+    return _one(obj, True, seed, **kw)

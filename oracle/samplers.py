@@ -283,12 +283,7 @@ def _stochvol_banded(y, h, sigma, h_init, constant, u, eps, table):
         rhs[0] += h_init[i] / sigma[i]
         c = sla.cholesky_banded(ab, lower=False)
         mean = sla.cho_solve_banded((c, False), rhs)
-        # R^-1 eps with R upper bidiagonal: back substitution
-        d, e = c[1], c[0]
-        w = np.zeros(tt)
-        w[-1] = eps[i][-1] / d[-1]
-        for t in range(tt - 2, -1, -1):
-            w[t] = (eps[i][t] - e[t + 1] * w[t + 1]) / d[t]
+        w = sla.solve_banded((0, 1), c, eps[i])          # R^-1 eps with R upper bidiagonal
         h[:, i] = mean + w
     return h
 
@@ -319,6 +314,7 @@ def bvartvpalg(obj, variates: VariateSource | None = None, literal=True, table="
 
     # zz: block diagonal kT x nT (:95-98);  a_hh: first-difference matrix (:116-117)
     Zt = [z[i * k:(i + 1) * k] for i in range(tt)]
+    Zarr = np.stack(Zt)
 
     sp = priors["sigma"]
     use_gamma = False
@@ -398,7 +394,7 @@ def bvartvpalg(obj, variates: VariateSource | None = None, literal=True, table="
             lam = new_lam
             a_mat = lam[:, None] * a_mat                                                  # :328
             a = a_mat.reshape(-1, order="F")
-        u = np.stack([y[:, t] - Zt[t] @ a_mat[:, t] for t in range(tt)], axis=1)          # :332-336
+        u = y - np.einsum("tkn,nt->kt", Zarr, a_mat)                                      # :332-336
 
         if sv:
             args = (u.T, h, sigma_h, h_init, h_const, vs.uniform("sv_u", draw, (k, tt)),
@@ -472,25 +468,16 @@ def _tvp_state_banded(Zt, sig_t, sigma_v_i, a_init, y, lam, eps):
     bw = n                                             # upper bandwidth: dense diagonal block + diagonal off-block
     ab = np.zeros((bw + 1, N))
     rhs = np.zeros(N)
+    rr, cc = np.triu_indices(n)
     for t in range(tt):
         Z = Zt[t] * lam[None, :]
         blk = Z.T @ sig_t[t] @ Z + np.diag((2.0 if t < tt - 1 else 1.0) * sigma_v_i)
-        for c in range(n):
-            for r in range(c + 1):
-                ab[bw + r - c, t * n + c] = blk[r, c]
+        ab[bw + rr - cc, t * n + cc] = blk[rr, cc]
         rhs[t * n:(t + 1) * n] = Z.T @ sig_t[t] @ y[:, t]
         if t < tt - 1:
-            for c in range(n):
-                ab[bw - n, (t + 1) * n + c] = -sigma_v_i[c]
+            ab[bw - n, (t + 1) * n + np.arange(n)] = -sigma_v_i
     rhs[:n] += sigma_v_i * a_init
     cb = sla.cholesky_banded(ab, lower=False)
     mean = sla.cho_solve_banded((cb, False), rhs)
-    # back substitution R w = eps with banded upper R
-    w = np.zeros(N)
-    for i in range(N - 1, -1, -1):
-        hi = min(N, i + bw + 1)
-        acc = eps[i]
-        for j in range(i + 1, hi):
-            acc -= cb[bw + i - j, j] * w[j]
-        w[i] = acc / cb[bw, i]
+    w = sla.solve_banded((0, bw), cb, eps)             # R w = eps, R upper banded
     return mean + w

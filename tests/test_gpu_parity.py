@@ -1,0 +1,258 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (libbvargpu.so), against the oracle on the
+same injected variates (tier 1: continuous <= 1e-10 relative, indicators bit-exact), plus size-independent
+properties at larger sizes and the statistical tier (tier 2)."""
+import ctypes as C
+import json
+import pathlib
+
+import numpy as np
+import pytest
+
+import helpers
+from test_kernel_logic_cpu import CASES
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+GOLD = pathlib.Path(__file__).resolve().parent / "golden"
+
+
+def _run(gpu, obj, n_chains, stacked=None, seed=0, **kw):
+    fn = gpu.bvg_bvartvpalg if obj["model"].get("tvp") else gpu.bvg_bvaralg
+    rc, out = helpers.run_abi(fn, obj, n_chains, stacked, seed=seed, **kw)
+    assert rc == 0, gpu.bvg_last_error()
+    return out
+
+
+@pytest.mark.parametrize("tpc", [0, 8, 32, 128])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_matches_oracle_injected(gpu, name, tpc):
+    """Every sampler variant x lanes-per-chain layout (sub-warp tile, full warp, CTA per chain)."""
+    builder, kw = CASES[name]
+    obj = builder()
+    table = kw.get("mixture", "ksc1998")
+    n_chains = 5                                        # ragged: not a multiple of chains per CTA
+    per, stacked = helpers.make_variates(obj, n_chains, seed=11)
+    out = _run(gpu, obj, n_chains, stacked, threads_per_chain=tpc, **kw)
+    want = helpers.oracle_stack(obj, per, table=table)
+    assert set(want) == set(out.arrays)
+    for key in want:
+        assert helpers.relerr(out.arrays[key], want[key]) < TOL, (name, tpc, key)
+    if "lambda" in want:
+        assert np.array_equal(out.arrays["lambda"], want["lambda"])
+    assert not out.status.any()
+
+
+def test_c3_full_size_ssvs_injected(gpu):
+    """Config c3 at full width (K=6, p=4, n=150, T=191; CTA per chain), few sweeps, vs the literal dense oracle."""
+    obj = helpers.model_c3(iterations=6, burnin=2)
+    per, stacked = helpers.make_variates(obj, 3, seed=5)
+    out = _run(gpu, obj, 3, stacked)
+    want = helpers.oracle_stack(obj, per, literal=True)
+    for key in want:
+        assert helpers.relerr(out.arrays[key], want[key]) < TOL, key
+    assert np.array_equal(out.arrays["lambda"], want["lambda"])
+
+
+def test_c4_shape_tvp_sv_injected(gpu):
+    """Config c4 shape (TVP-VAR(2), K=3, KSC SV) at T=60 against the structured oracle (the literal dense
+    (nT)^2 path is checked against the structured one in test_oracle.py)."""
+    obj = helpers.model_sv(tvp=True, nobs=62, iterations=5, burnin=2)
+    per, stacked = helpers.make_variates(obj, 3, seed=8)
+    out = _run(gpu, obj, 3, stacked)
+    want = helpers.oracle_stack(obj, per, literal=False)
+    for key in want:
+        assert helpers.relerr(out.arrays[key], want[key]) < 1e-8, key      # state dim nT = 1260
+
+
+def test_chunking_and_layout_invariance_philox(gpu):
+    """Same seed => bit-identical draws whatever the launch chunking or lanes per chain (counter-based RNG)."""
+    obj = helpers.model_c3(K=3, p=2, nobs=80, iterations=30, burnin=10)
+    ref = _run(gpu, obj, 37, seed=42)
+    for kw in (dict(sweeps_per_launch=7), dict(threads_per_chain=8), dict(threads_per_chain=64)):
+        other = _run(gpu, obj, 37, seed=42, **kw)
+        for key in ref.arrays:
+            if key == "lambda":
+                assert np.array_equal(ref.arrays[key], other.arrays[key]), (kw, key)
+            else:   # reductions are ordered differently per layout: equal to rounding, chunking alone is exact
+                np.testing.assert_allclose(other.arrays[key], ref.arrays[key], rtol=1e-9, atol=1e-12)
+    exact = _run(gpu, obj, 37, seed=42, sweeps_per_launch=7)
+    for key in ref.arrays:
+        assert np.array_equal(ref.arrays[key], exact.arrays[key]), key
+
+
+def test_sharding_invariance(gpu):
+    """Chains [offset, offset+m) of a shard equal the same global chains of the full job, bit for bit."""
+    obj = helpers.model_c1(iterations=40, burnin=10)
+    full = _run(gpu, obj, 96, seed=20240113)
+    for off, cnt in ((0, 48), (48, 48), (17, 5)):
+        part = _run(gpu, obj, cnt, seed=20240113, chain_offset=off)
+        for key in full.arrays:
+            assert np.array_equal(full.arrays[key][off:off + cnt], part.arrays[key]), (off, key)
+
+
+def test_matches_emulated_logic_philox(gpu, emu):
+    """Philox path: device transforms (log, cospi, exp) vs the host build of the same headers."""
+    obj = helpers.model_c1(iterations=25, burnin=5)
+    dev = _run(gpu, obj, 4, seed=3)
+    rc, host = helpers.run_abi(emu.emu_bvaralg, obj, 4, None, seed=3)
+    assert rc == 0
+    for key in dev.arrays:
+        np.testing.assert_allclose(dev.arrays[key], host.arrays[key], rtol=1e-7, atol=1e-9)
+
+
+def _mcse(x, nb=20):
+    n = (x.shape[0] // nb) * nb
+    bm = x[:n].reshape(nb, -1, *x.shape[1:]).mean(axis=1)
+    return bm.std(axis=0, ddof=1) / np.sqrt(nb)
+
+
+def test_tier2_c1_posterior_vs_analytic_and_readme(gpu):
+    """Tier 2, config c1/c2-A: full GPU sampler (Philox).  Posterior mean of a = OLS and E[Sigma] = SSE/63 within
+    4 MCSE; README table (README.md:240-299) means within 4 combined MCSE, SD ratio within 5 %; KS-consistent
+    marginals between two disjoint sets of chains."""
+    from scipy import stats
+    obj = helpers.model_c1(iterations=5000, burnin=1000)
+    out = _run(gpu, obj, 64, seed=1234567)
+    coef = out.arrays["coef"]                      # [chain][iter][21]
+    sig = out.arrays["sigma"]
+    assert np.isfinite(coef).all() and np.isfinite(sig).all() and not out.status.any()
+    ols = obj["initial"]["coefficients"]["draw"].reshape(-1)
+    chain_means = coef.mean(axis=1)                # independent chains -> exact MCSE across chains
+    mc = chain_means.std(axis=0, ddof=1) / np.sqrt(coef.shape[0])
+    assert np.all(np.abs(chain_means.mean(axis=0) - ols) < 4.0 * mc)
+    Y, Z = obj["data"]["Y"], obj["data"]["Z"]
+    U = Y - Z @ np.linalg.lstsq(Z, Y, rcond=None)[0]
+    expect = ((U.T @ U + 1e-4 * np.eye(3)) / 63.0).reshape(-1, order="F")
+    sm = sig.mean(axis=1)
+    smc = sm.std(axis=0, ddof=1) / np.sqrt(sig.shape[0])
+    assert np.all(np.abs(sm.mean(axis=0) - expect) < 4.0 * smc)
+    table = json.loads((GOLD / "readme_table_c1.json").read_text())
+    names = ["invest.01", "income.01", "cons.01", "invest.02", "income.02", "cons.02", "const"]
+    flat = coef.reshape(-1, 21)
+    for i, var in enumerate(["invest", "income", "cons"]):
+        for j, reg in enumerate(names):
+            row = table["coef"][var][reg]
+            col = j * 3 + i
+            assert abs(flat[:, col].mean() - row["Mean"]) < 4.0 * np.hypot(mc[col], row["TSSD"])
+            assert abs(flat[:, col].std(ddof=1) / row["SD"] - 1.0) < 0.05
+            for qn, qv in (("q2.5", 0.025), ("q50", 0.5), ("q97.5", 0.975)):
+                assert abs(np.quantile(flat[:, col], qv) - row[qn]) < 8.0 * row["TSSD"] * (1.0 if qv == 0.5 else 2.5)
+    a, b = coef[:32, ::10].reshape(-1, 21), coef[32:, ::10].reshape(-1, 21)
+    pvals = [stats.ks_2samp(a[:, c], b[:, c]).pvalue for c in range(21)]
+    assert min(pvals) > 1e-3 / 21
+
+
+def test_tier2_ssvs_vs_oracle_sampler(gpu):
+    """Tier 2 for SSVS: inclusion frequencies and posterior means of the GPU sampler vs the oracle sampler run
+    with NumPy's RNG (structured path), within 4 MCSE (chains are independent -> MCSE across chains)."""
+    obj = helpers.model_c3(K=3, p=2, nobs=120, iterations=1500, burnin=500)
+    dev = _run(gpu, obj, 48, seed=7)
+    lam_d = dev.arrays["lambda"].mean(axis=1)          # [chain][21]
+    coef_d = dev.arrays["coef"].mean(axis=1)
+    from oracle.samplers import bvaralg
+    from oracle.variates import VariateSource
+    lam_o, coef_o = [], []
+    for c in range(12):
+        r = bvaralg(obj, VariateSource(rng=np.random.default_rng(1000 + c)), literal=False)["posteriors"]
+        lam_o.append(np.concatenate([r["a"]["lambda"], r["c"]["lambda"]]).mean(axis=1))
+        coef_o.append(np.concatenate([r["a"]["coeffs"], r["c"]["coeffs"]]).mean(axis=1))
+    lam_o, coef_o = np.array(lam_o), np.array(coef_o)
+    for d, o in ((lam_d, lam_o), (coef_d, coef_o)):
+        se = np.hypot(d.std(axis=0, ddof=1) / np.sqrt(d.shape[0]), o.std(axis=0, ddof=1) / np.sqrt(o.shape[0]))
+        assert np.all(np.abs(d.mean(axis=0) - o.mean(axis=0)) < 4.0 * se + 1e-9)
+
+
+def test_tier2_tvp_sv_vs_oracle_sampler(gpu):
+    """Tier 2 for the TVP + KSC-SV sampler at a small shape: posterior means of the state path, state variances and
+    log-volatility driven Sigma_t vs the oracle sampler, within 4.5 MCSE (many marginals)."""
+    obj = helpers.model_sv(tvp=True, nobs=42, iterations=600, burnin=400)
+    dev = _run(gpu, obj, 32, seed=11)
+    from oracle.samplers import bvartvpalg
+    from oracle.variates import VariateSource
+    o_coef, o_sv, o_sig = [], [], []
+    for c in range(8):
+        r = bvartvpalg(obj, VariateSource(rng=np.random.default_rng(500 + c)), literal=False)["posteriors"]
+        per = [{"x": 0}]
+        stack = helpers.oracle_stack.__wrapped__ if hasattr(helpers.oracle_stack, "__wrapped__") else None
+        T = obj["data"]["Y"].shape[0]
+        parts = [r[nm] for nm in ("a", "c")]
+        it = parts[0]["coeffs"].shape[1]
+        cube = np.concatenate([p["coeffs"].reshape(T, -1, it) for p in parts], axis=1).reshape(-1, it)
+        o_coef.append(cube.mean(axis=1))
+        o_sv.append(np.concatenate([p["sigma"] for p in parts]).mean(axis=1))
+        o_sig.append(np.log(r["sigma"]["coeffs"].reshape(T, 9, it)[:, [0, 4, 8], :]).mean(axis=2).reshape(-1))
+    T = obj["data"]["Y"].shape[0]
+    d_coef = dev.arrays["coef"].mean(axis=1)
+    d_sv = dev.arrays["sigma_v"].mean(axis=1)
+    d_sig = np.log(dev.arrays["sigma"].reshape(32, -1, T, 9)[:, :, :, [0, 4, 8]]).mean(axis=1).reshape(32, -1)
+    for d, o in ((d_coef, np.array(o_coef)), (d_sv, np.array(o_sv)), (d_sig, np.array(o_sig))):
+        se = np.hypot(d.std(axis=0, ddof=1) / np.sqrt(d.shape[0]), o.std(axis=0, ddof=1) / np.sqrt(o.shape[0]))
+        assert np.all(np.abs(d.mean(axis=0) - o.mean(axis=0)) < 4.5 * se + 1e-9)
+
+
+def test_handle_api_resident_draws_and_moments(gpu):
+    """bvg_sampler_*: draws stay in HBM; bvg_moments reduces them on the device; fetch equals the one-shot call."""
+    from bvartools_b200 import ChainSampler, run_chains
+    from bvartools_b200._lib import check
+    obj = helpers.model_c1(iterations=200, burnin=50)
+    s = ChainSampler(obj, n_chains=130, seed=5)
+    s.run()
+    s.sync()
+    assert s.last_kernel_ms > 0 and s.launch_count >= 1
+    got = s.fetch()
+    one = run_chains(obj, n_chains=130, seed=5)
+    assert np.array_equal(got.arrays["coef"], one["coef"]) and np.array_equal(got.arrays["sigma"], one["sigma"])
+    import torch
+    d = s.device_out()
+    sums = torch.zeros(21, dtype=torch.float64, device="cuda")
+    sq = torch.zeros(21, dtype=torch.float64, device="cuda")
+    check(gpu.bvg_moments(C.cast(d.coef, C.c_void_p), 130, 200, 21, C.c_void_p(sums.data_ptr()),
+                          C.c_void_p(sq.data_ptr()), None))
+    torch.cuda.synchronize()
+    flat = one["coef"].reshape(-1, 21)
+    np.testing.assert_allclose(sums.cpu().numpy(), flat.sum(axis=0), rtol=1e-10)
+    np.testing.assert_allclose(sq.cpu().numpy(), (flat ** 2).sum(axis=0), rtol=1e-10)
+    s.reset()
+    s.run()
+    again = s.fetch()
+    assert np.array_equal(again.arrays["coef"], one["coef"])
+    s.close()
+
+
+def test_failure_paths(gpu):
+    from bvartools_b200 import run_chains
+    from bvartools_b200._lib import BvgError
+    obj = helpers.model_c1(iterations=5, burnin=1)
+    bad = json.loads(json.dumps({}))  # noqa: F841
+    obj_nan = helpers.model_c1(iterations=5, burnin=1)
+    obj_nan["data"]["Y"] = obj_nan["data"]["Y"].copy()
+    obj_nan["data"]["Y"][2, 1] = np.nan
+    with pytest.raises(BvgError, match="NAs"):
+        run_chains(obj_nan, 2)
+    obj_bad = helpers.model_c1(iterations=5, burnin=1, coef=dict(v_i=1, v_i_det=0.1))
+    obj_bad["priors"]["coefficients"]["v_i"] = -1e6 * np.eye(21)
+    res = run_chains(obj_bad, 3, seed=1)
+    assert res["status"].all()                          # flagged, call itself survives
+    good = run_chains(obj, 3, seed=1)
+    assert not good["status"].any()
+
+
+def test_reference_shaped_results(gpu):
+    """bvaralg / bvartvpalg / bvarpost / draw_posterior return the reference's structures (src/bvaralg.cpp:562-627,
+    src/bvartvpalg.cpp:555-626, R/bvarpost.R:111-119)."""
+    import bvartools_b200 as b
+    obj = helpers.model_c3(K=3, p=2, nobs=80, iterations=20, burnin=5)
+    r = b.bvaralg(obj, seed=1)
+    post = r["posteriors"]
+    assert post["a"]["coeffs"].shape == (18, 20) and post["a"]["lambda"].shape == (18, 20)
+    assert post["c"]["coeffs"].shape == (3, 20) and post["b"] is None and post["a0"] is None
+    assert post["sigma"]["coeffs"].shape == (9, 20)
+    tv = helpers.model_sv(tvp=True, nobs=30, iterations=6, burnin=2)
+    rt = b.bvartvpalg(tv, seed=2)["posteriors"]
+    T = tv["data"]["Y"].shape[0]
+    assert rt["a"]["coeffs"].shape == (18 * T, 6) and rt["a"]["sigma"].shape == (18, 6)
+    assert rt["c"]["coeffs"].shape == (3 * T, 6) and rt["sigma"]["coeffs"].shape == (9 * T, 6)
+    assert rt["sigma"]["sigma"].shape == (9, 6)
+    est = b.draw_posterior([obj, helpers.model_c1(iterations=10, burnin=2)], seed=3)
+    assert len(est) == 2 and est[0]["class"] == "bvar" and est[0]["A"].shape == (20, 18)
+    assert est[1]["Sigma"].shape == (10, 9) and est[0]["specifications"]["lags"]["p"] == 2

@@ -1,0 +1,134 @@
+"""CPU tests of the kernel LOGIC: the group-generic headers the CUDA kernels are built from, compiled with g++
+as a single-thread group (tests/emu -- test-only, never loaded by the product), against the oracle on injected
+variates.  Tier-1 bar (BASELINE.json north_star): continuous draws <= 1e-10 relative, indicators bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers
+
+TOL = 1e-10
+
+CASES = {
+    "c1_wishart_moment": (lambda: helpers.model_c1(iterations=40, burnin=10), dict(resid_mode=2)),
+    "c1_wishart_direct": (lambda: helpers.model_c1(iterations=40, burnin=10), dict(resid_mode=1)),
+    "c1_informative_prior": (lambda: helpers.model_c1(iterations=30, burnin=5, coef=dict(v_i=1, v_i_det=0.1),
+                                                     sigma=dict(df="k", scale=1)), {}),
+    "ssvs_moment": (lambda: helpers.model_c3(K=3, p=2, nobs=80), dict(resid_mode=2)),
+    "ssvs_direct": (lambda: helpers.model_c3(K=3, p=2, nobs=80), dict(resid_mode=1)),
+    "bvs_moment": (lambda: helpers.model_c3(K=3, p=2, nobs=80, bvs=True), dict(resid_mode=2)),
+    "bvs_direct": (lambda: helpers.model_c3(K=3, p=2, nobs=80, bvs=True), dict(resid_mode=1)),
+    "gamma": (lambda: helpers.model_c1(iterations=30, burnin=5, sigma=dict(shape=3, rate=1e-4),
+                                       coef=dict(v_i=1, v_i_det=0.1)), {}),
+    "sv_ksc": (lambda: helpers.model_sv(), {}),
+    "sv_ocsn": (lambda: helpers.model_sv(), dict(mixture="ocsn2007")),
+    "sv_bvs": (lambda: helpers.model_sv(bvs=True), {}),
+    "tvp_sv": (lambda: helpers.model_sv(tvp=True, nobs=30), {}),
+    "tvp_sv_bvs": (lambda: helpers.model_sv(tvp=True, nobs=30, bvs=True), {}),
+}
+
+
+def _tvp_wishart():
+    y = helpers.synth_var(2, 1, 28, 11)
+    m = helpers.gen_var(y, p=1, deterministic="const", iterations=8, burnin=3, tvp=True)
+    return helpers.add_priors(m, coef=dict(v_i=1, v_i_det=0.1, shape=3, rate=1e-4, rate_det=0.01),
+                              sigma=dict(df="k", scale=1))
+
+
+CASES["tvp_wishart"] = (_tvp_wishart, {})
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_kernel_logic_matches_oracle(emu, name):
+    builder, kw = CASES[name]
+    obj = builder()
+    table = kw.get("mixture", "ksc1998")
+    per, stacked = helpers.make_variates(obj, 2, seed=11)
+    fn = emu.emu_bvartvpalg if obj["model"].get("tvp") else emu.emu_bvaralg
+    rc, out = helpers.run_abi(fn, obj, 2, stacked, **kw)
+    assert rc == 0, emu.emu_last_error()
+    want = helpers.oracle_stack(obj, per, table=table)
+    assert set(want) == set(out.arrays)
+    for key in want:
+        assert helpers.relerr(out.arrays[key], want[key]) < TOL, (name, key)
+    if "lambda" in want:
+        assert np.array_equal(out.arrays["lambda"], want["lambda"])
+    assert not out.status.any()
+
+
+def test_chunked_launches_are_bit_identical(emu):
+    """State save/restore between kernel launches must not change anything (Philox sites are sweep-addressed)."""
+    obj = helpers.model_c3(K=3, p=2, nobs=80)
+    rc1, a = helpers.run_abi(emu.emu_bvaralg, obj, 3, None, seed=42)
+    rc2, b = helpers.run_abi(emu.emu_bvaralg, obj, 3, None, seed=42, sweeps_per_launch=7)
+    assert rc1 == 0 and rc2 == 0
+    for key in a.arrays:
+        assert np.array_equal(a.arrays[key], b.arrays[key]), key
+
+
+def test_sharding_invariance(emu):
+    """Chains are keyed by GLOBAL id: chains [2,5) computed alone equal chains 2..4 of a 6-chain call."""
+    obj = helpers.model_c1(iterations=15, burnin=5)
+    _, full = helpers.run_abi(emu.emu_bvaralg, obj, 6, None, seed=99)
+    _, part = helpers.run_abi(emu.emu_bvaralg, obj, 3, None, seed=99, chain_offset=2)
+    for key in full.arrays:
+        assert np.array_equal(full.arrays[key][2:5], part.arrays[key]), key
+    _, other = helpers.run_abi(emu.emu_bvaralg, obj, 6, None, seed=100)
+    assert not np.array_equal(full.arrays["coef"], other.arrays["coef"])
+
+
+def test_philox_known_answer(emu):
+    """Philox4x32-10 known-answer vectors of the Random123 distribution (kat_vectors)."""
+    out = (C.c_uint32 * 4)()
+    emu.emu_philox.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
+    emu.emu_philox(0, 0, 0, 0, 0, 0, out)
+    assert list(out) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    emu.emu_philox(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, out)
+    assert list(out) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    emu.emu_philox(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0, out)
+    assert list(out) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_variate_transforms_are_distributionally_right(emu):
+    """Box-Muller normals, uniforms, Marsaglia-Tsang gammas / chi-squares from the Philox stream: KS tests."""
+    from scipy import stats
+    emu.emu_variates.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                 C.POINTER(C.c_double)]
+    n = 200000
+    buf = np.empty(n)
+    ptr = buf.ctypes.data_as(C.POINTER(C.c_double))
+    emu.emu_variates(123, 5, 0, 3, n, 0, 0.0, ptr)
+    assert stats.kstest(buf, "uniform").pvalue > 1e-3 and buf.min() > 0 and buf.max() < 1
+    emu.emu_variates(123, 5, 0, 3, n, 1, 0.0, ptr)
+    assert stats.kstest(buf, "norm").pvalue > 1e-3
+    for shape in (0.4, 1.0, 3.5, 37.0):
+        emu.emu_variates(7, 1, 6, 0, n, 2, shape, ptr)
+        assert stats.kstest(buf, "gamma", args=(shape,)).pvalue > 1e-3, shape
+    emu.emu_variates(7, 1, 9, 0, n, 3, 74.0, ptr)
+    assert stats.kstest(buf, "chi2", args=(74.0,)).pvalue > 1e-3
+
+
+def test_invalid_specs_are_rejected(emu):
+    obj = helpers.model_c1()
+    spec = helpers._abi.spec_from_model(obj, n_chains=1)
+    out = helpers._abi.OutBuffers(spec)
+    spec.c.abi_version = 99
+    assert emu.emu_bvaralg(C.byref(spec.c), C.byref(out.c)) == -2
+    spec = helpers._abi.spec_from_model(obj, n_chains=1)
+    spec.keep["Y"][3] = np.nan
+    assert emu.emu_bvaralg(C.byref(spec.c), C.byref(out.c)) == -6
+    assert b"NAs" in emu.emu_last_error()
+    # SSVS + SV is illegal (src/bvaralg.cpp:116-118)
+    spec = helpers._abi.spec_from_model(helpers.model_sv(), n_chains=1)
+    spec.c.varsel = helpers._abi.VARSEL_SSVS
+    out = helpers._abi.OutBuffers(spec)
+    assert emu.emu_bvaralg(C.byref(spec.c), C.byref(out.c)) == -7
+    assert b"SSVS with stochastic volatility" in emu.emu_last_error()
+
+
+def test_non_spd_prior_flags_chain_status(emu):
+    obj = helpers.model_c1(iterations=5, burnin=1, coef=dict(v_i=1, v_i_det=0.1))
+    obj["priors"]["coefficients"]["v_i"] = -1e6 * np.eye(21)
+    rc, out = helpers.run_abi(emu.emu_bvaralg, obj, 2, None, seed=1)
+    assert rc == 0 and out.status.all()
