@@ -143,23 +143,19 @@ def test_tier2_c1_posterior_vs_analytic_and_readme(gpu):
 
 
 def test_tier2_ssvs_vs_oracle_sampler(gpu):
-    """Tier 2 for SSVS: inclusion frequencies and posterior means of the GPU sampler vs the oracle sampler run
-    with NumPy's RNG (structured path), within 4 MCSE (chains are independent -> MCSE across chains)."""
+    """Tier 2 for SSVS: inclusion frequencies and posterior means of the GPU sampler (Philox) vs the dense C
+    restatement of the reference sweep run with its own generator, 96 independent chains each; difference of the
+    across-chain means within 4.5 standard errors for every coefficient (42 comparisons)."""
+    import os
+    from oracle.dense_ref import bvar_dense
     obj = helpers.model_c3(K=3, p=2, nobs=120, iterations=1500, burnin=500)
-    dev = _run(gpu, obj, 48, seed=7)
-    lam_d = dev.arrays["lambda"].mean(axis=1)          # [chain][21]
-    coef_d = dev.arrays["coef"].mean(axis=1)
-    from oracle.samplers import bvaralg
-    from oracle.variates import VariateSource
-    lam_o, coef_o = [], []
-    for c in range(12):
-        r = bvaralg(obj, VariateSource(rng=np.random.default_rng(1000 + c)), literal=False)["posteriors"]
-        lam_o.append(np.concatenate([r["a"]["lambda"], r["c"]["lambda"]]).mean(axis=1))
-        coef_o.append(np.concatenate([r["a"]["coeffs"], r["c"]["coeffs"]]).mean(axis=1))
-    lam_o, coef_o = np.array(lam_o), np.array(coef_o)
-    for d, o in ((lam_d, lam_o), (coef_d, coef_o)):
+    dev = _run(gpu, obj, 96, seed=7)
+    ref = bvar_dense(obj, n_chains=96, seed=99, n_threads=os.cpu_count() or 1, dense_gemm=False)
+    assert 0.05 < dev.arrays["lambda"][:, :, :18].mean() < 0.95
+    for name in ("lambda", "coef"):
+        d, o = dev.arrays[name].mean(axis=1), ref[name].mean(axis=1)
         se = np.hypot(d.std(axis=0, ddof=1) / np.sqrt(d.shape[0]), o.std(axis=0, ddof=1) / np.sqrt(o.shape[0]))
-        assert np.all(np.abs(d.mean(axis=0) - o.mean(axis=0)) < 4.0 * se + 1e-9)
+        assert np.all(np.abs(d.mean(axis=0) - o.mean(axis=0)) < 4.5 * se + 1e-9), name
 
 
 def test_tier2_tvp_sv_vs_oracle_sampler(gpu):
