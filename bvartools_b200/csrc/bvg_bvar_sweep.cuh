@@ -17,6 +17,18 @@ namespace bvg {
 enum SigmaType : int { SIG_WISHART = 0, SIG_GAMMA = 1, SIG_SV = 2 };
 enum VarSel : int { VS_NONE = 0, VS_SSVS = 1, VS_BVS = 2 };
 enum ResidMode : int { RES_DIRECT = 1, RES_MOMENT = 2 };
+// compile-time feature mask of a kernel variant: code of features not in the mask is compiled out, which keeps
+// the headline kernel (Wishart prior, moment residuals, no variable selection) small enough for the I-cache
+enum Feat : int { F_SV = 1, F_VARSEL = 2, F_DIRECT = 4, F_GAMMA = 8, F_VIOFF = 16, F_ALL = 31 };
+BVG_HD int bvar_features_needed(int sigma_type, int varsel, int resid_mode, bool has_vi_off) {
+  int need = 0;
+  if (sigma_type == SIG_SV) need |= F_SV | F_DIRECT;
+  if (sigma_type == SIG_GAMMA) need |= F_GAMMA;
+  if (varsel != VS_NONE) need |= F_VARSEL;
+  if (resid_mode == RES_DIRECT) need |= F_DIRECT;
+  if (has_vi_off) need |= F_VIOFF;
+  return need;
+}
 
 // Model constants, shared by all chains of one model.  All pointers are device (or host, in tests/emu) memory.
 struct BvarModel {
@@ -153,6 +165,123 @@ BVG_HD void wishart_block(const Grp& g, const ChainRng& rng, int sweep, int k, d
   }
 }
 
+// Register version of the same block for small k (K <= 4, compile time): every lane redundantly runs the whole
+// K x K algebra on registers (no shared-memory traffic, no barriers); the variates were drawn before, in the
+// sweep's single generator pass: wn[] = strict-upper normals, x0[] = attempt-0 normals of the chi-squares.
+template <int K, class Grp>
+BVG_HD void wishart_block_reg(const Grp& g, const ChainRng& rng, int sweep, double df_post, const double* S,
+                              const double* wn, const double* x0, double* chis, double* sig, double* sigma_out,
+                              int& fail) {
+  const int tid = g.tid();
+  for (int i = tid; i < K; i += g.size())
+    chis[i] = sqrt(rng.chi2_from_x0(VB_WISH_C, sweep, i, df_post - (double)i, x0[i]));
+  g.sync();
+  double Ls[K][K], Mi[K][K], Sb[K][K], Ld[K][K], B[K][K], dinv[K];
+  // 1. S = Ls Ls'
+BVG_UNROLL
+  for (int j = 0; j < K; ++j) {
+    double d = S[j + K * j];
+BVG_UNROLL
+    for (int c = 0; c < j; ++c) d = fma(-Ls[j][c], Ls[j][c], d);
+    if (!(d > 0.0)) fail = 1;
+    const double rs = bvg_rsqrt(d);
+    dinv[j] = rs;
+BVG_UNROLL
+    for (int i = j + 1; i < K; ++i) {
+      double v = S[i + K * j];
+BVG_UNROLL
+      for (int c = 0; c < j; ++c) v = fma(-Ls[i][c], Ls[j][c], v);
+      Ls[i][j] = v * rs;
+    }
+  }
+  // 2. Mi = Ls^-1 (lower), Sbar = Mi' Mi
+BVG_UNROLL
+  for (int c = 0; c < K; ++c) {
+    Mi[c][c] = dinv[c];
+BVG_UNROLL
+    for (int i = c + 1; i < K; ++i) {
+      double v = 0.0;
+BVG_UNROLL
+      for (int mm = c; mm < i; ++mm) v = fma(Ls[i][mm], Mi[mm][c], v);
+      Mi[i][c] = -v * dinv[i];
+    }
+  }
+BVG_UNROLL
+  for (int i = 0; i < K; ++i)
+BVG_UNROLL
+    for (int j = 0; j <= i; ++j) {
+      double v = 0.0;
+BVG_UNROLL
+      for (int mm = i; mm < K; ++mm) v = fma(Mi[mm][i], Mi[mm][j], v);
+      Sb[i][j] = v;
+    }
+  // 3. Sbar = Ld Ld' with its true diagonal; D = Ld'
+BVG_UNROLL
+  for (int j = 0; j < K; ++j) {
+    double d = Sb[j][j];
+BVG_UNROLL
+    for (int c = 0; c < j; ++c) d = fma(-Ld[j][c], Ld[j][c], d);
+    if (!(d > 0.0)) fail = 1;
+    const double rs = bvg_rsqrt(d);
+    Ld[j][j] = 1.0 / rs;
+BVG_UNROLL
+    for (int i = j + 1; i < K; ++i) {
+      double v = Sb[i][j];
+BVG_UNROLL
+      for (int c = 0; c < j; ++c) v = fma(-Ld[i][c], Ld[j][c], v);
+      Ld[i][j] = v * rs;
+    }
+  }
+  // 4./5. B = A D (upper): A_rr = sqrt(chi2_r), A_rc = wn[tri(c-1)+r] (r < c), D_mc = Ld_cm
+BVG_UNROLL
+  for (int r = 0; r < K; ++r)
+BVG_UNROLL
+    for (int c = r; c < K; ++c) {
+      double v = 0.0;
+BVG_UNROLL
+      for (int mm = r; mm <= c; ++mm) {
+        const double arm = (mm == r) ? chis[r] : wn[tri(mm - 1) + r];
+        v = fma(arm, Ld[c][mm], v);
+      }
+      B[r][c] = v;
+    }
+  // 6. Sigma^-1 = B'B ; lane 0 publishes
+  if (tid == 0) {
+BVG_UNROLL
+    for (int i = 0; i < K; ++i)
+BVG_UNROLL
+      for (int j = 0; j < K; ++j) {
+        double v = 0.0;
+BVG_UNROLL
+        for (int mm = 0; mm <= (i < j ? i : j); ++mm) v = fma(B[mm][i], B[mm][j], v);
+        sig[i + K * j] = v;
+      }
+    if (sigma_out != nullptr) {
+      // Sigma = B^-1 B^-T
+      double Bi[K][K];
+BVG_UNROLL
+      for (int c = 0; c < K; ++c)
+BVG_UNROLL
+        for (int r = c; r >= 0; --r) {
+          double v = (r == c) ? 1.0 : 0.0;
+BVG_UNROLL
+          for (int mm = r + 1; mm <= c; ++mm) v = fma(-B[r][mm], Bi[mm][c], v);
+          Bi[r][c] = v / B[r][r];
+        }
+BVG_UNROLL
+      for (int i = 0; i < K; ++i)
+BVG_UNROLL
+        for (int j = 0; j < K; ++j) {
+          double v = 0.0;
+BVG_UNROLL
+          for (int mm = (i > j ? i : j); mm < K; ++mm) v = fma(Bi[i][mm], Bi[j][mm], v);
+          sigma_out[i + K * j] = v;
+        }
+    }
+  }
+  g.sync();
+}
+
 // general symmetric positive definite k x k inverse (full col-major), used for storing Sigma under the gamma prior
 template <class Grp>
 BVG_HD void small_spd_inverse(const Grp& g, const double* A, double* out, double* W1, double* W2, double* W3,
@@ -233,13 +362,17 @@ BVG_HD void sv_step(const Grp& g, const ChainRng& rng, int sweep, const BvarMode
 }
 
 // ---- the chain ---------------------------------------------------------------------------------------------
-template <class Grp>
+template <int FEAT, class Grp>
 BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, double* state, double* sm,
                        const BvarOut& out, long long chain_local, int sweep_begin, int sweep_end, int burnin) {
   const int G = g.size(), tid = g.tid();
   const int k = m.k, T = m.T, M = m.M, n = m.n, kk = k * k;
-  const bool sv = m.sigma_type == SIG_SV;
-  const bool direct = (m.resid_mode == RES_DIRECT) || sv;
+  const bool sv = (FEAT & F_SV) && m.sigma_type == SIG_SV;
+  const bool direct = (FEAT & F_DIRECT) && ((m.resid_mode == RES_DIRECT) || sv);
+  const int varsel = (FEAT & F_VARSEL) ? m.varsel : (int)VS_NONE;
+  const bool use_gamma = (FEAT & F_GAMMA) && m.sigma_type == SIG_GAMMA;
+  const double* vi_off = (FEAT & F_VIOFF) ? m.vi_off : nullptr;
+  const double* vmu_off = (FEAT & F_VIOFF) ? m.vmu_off : nullptr;
   // carve shared memory
   double* L = sm;           sm += tri(n);
   double* w = sm;           sm += n;
@@ -283,6 +416,21 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, do
     const bool keep = sweep >= burnin;
     const long long pos = (long long)sweep - burnin;
 
+    // ---- variates of this sweep that do not depend on the chain state, drawn in ONE pass through one generator
+    //      call site (no divergence between lanes): coefficient normals -> a[], and for the register Wishart block
+    //      its strict-upper normals -> W4[] and the attempt-0 normals of its chi-squares -> kv[]
+    const bool wish_reg = !sv && !use_gamma && k <= 4;
+    {
+      const int nwn = (k * (k - 1)) / 2;
+      const int n_items = n + (wish_reg ? nwn + k : 0);
+      for (int it = tid; it < n_items; it += G) {
+        int block = VB_COEF_N, idx = it;
+        double* dst = a + it;
+        if (it >= n + nwn) { block = VB_WISH_C; idx = it - n - nwn; dst = kv + idx; }
+        else if (it >= n) { block = VB_WISH_N; idx = it - n; dst = W4 + idx; }
+        *dst = rng.normal(block, sweep, idx);
+      }
+    }
     if (n > 0) {
       // ---- precision P = V^-1 + Lambda (z'Dz) Lambda and rhs b = V^-1 mu + Lambda z'Dy  (bvaralg.cpp:303-306)
       if (sv) {
@@ -312,7 +460,7 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, do
           w[r] = s;
         }
       }
-      const bool bvs = m.varsel == VS_BVS;
+      const bool bvs = varsel == VS_BVS;
       for (int r = tid; r < n; r += G) {
         const int j = r / k, i = r % k;
         double* Lr = L + tri(r);
@@ -323,24 +471,24 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, do
           if (sv) gv = (i == i2) ? GW[i * tri(M) + tri(j) + j2] : 0.0;
           else gv = m.XX[j + M * j2] * sig[i + k * i2];
           if (bvs) gv *= lr * lam[c];
-          if (m.vi_off != nullptr) gv += m.vi_off[tri(r) + c];
+          if (vi_off != nullptr) gv += vi_off[tri(r) + c];
           if (c == r) gv += vdiag[r];
           Lr[c] = gv;
           if (++i2 == k) { i2 = 0; ++j2; }
         }
         double b = w[r] * lr + vdiag[r] * m.mu[r];
-        if (m.vmu_off != nullptr) b += m.vmu_off[r];
+        if (vmu_off != nullptr) b += vmu_off[r];
         w[r] = b;
       }
       g.sync();
       // ---- a = L^-T (L^-1 b + eps)                                                  (bvaralg.cpp:306-307)
       chol_crout(g, L, dinv, w, n, fail);
-      for (int r = tid; r < n; r += G) w[r] += rng.normal(VB_COEF_N, sweep, r);
+      for (int r = tid; r < n; r += G) w[r] += a[r];            // eps drawn at the top of the sweep
       g.sync();
       back_solve_lt(g, L, dinv, w, a, n);
 
       // ---- SSVS (bvaralg.cpp:314-331)
-      if (m.varsel == VS_SSVS) {
+      if (varsel == VS_SSVS) {
         for (int r = tid; r < n; r += G) {
           if (!m.include[r]) continue;
           const double t0 = m.tau0[r], t1 = m.tau1[r], pi = m.inprior[r];
@@ -358,7 +506,7 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, do
 
     // ---- residuals and BVS -------------------------------------------------------------------------------
     // Dm = A_AG - A_ols  (moment mode)  /  U = Y - A_AG X  (direct mode), with A_AG = Lambda a (stale, :335)
-    const bool bvs = (m.varsel == VS_BVS) && n > 0;
+    const bool bvs = (varsel == VS_BVS) && n > 0;
     if (direct) {
       for (int e = tid; e < k * T; e += G) {
         const int i = e % k, t = e / k;
@@ -508,7 +656,7 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, do
         S[e] = s;
       }
       g.sync();
-      if (m.sigma_type == SIG_GAMMA) {
+      if (use_gamma) {
         for (int i = tid; i < k; i += G) {
           const double gs = rng.gamma(VB_OMEGA_G, sweep, i, m.g_shape_post[i]);
           kv[i] = gs * (1.0 / (m.g_rate[i] + S[i + k * i] * 0.5));                        // :484
@@ -529,8 +677,17 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, do
         // symmetrise exactly (moment mode computes both triangles independently)
         for (int e = tid; e < kk; e += G) { const int i = e % k, j = e / k; if (i < j) S[e] = S[j + k * i]; }
         g.sync();
-        wishart_block(g, rng, sweep, k, m.wish_df_post, S, sig, W4, keep, W1, W2, W3, W4 /*A then Sigma*/, kd, fail);
-        if (keep) for (int e = tid; e < kk; e += G) out_sig[e] = W4[e];
+        if (wish_reg) {
+          switch (k) {
+            case 1: wishart_block_reg<1>(g, rng, sweep, m.wish_df_post, S, W4, kv, kd, sig, out_sig, fail); break;
+            case 2: wishart_block_reg<2>(g, rng, sweep, m.wish_df_post, S, W4, kv, kd, sig, out_sig, fail); break;
+            case 3: wishart_block_reg<3>(g, rng, sweep, m.wish_df_post, S, W4, kv, kd, sig, out_sig, fail); break;
+            default: wishart_block_reg<4>(g, rng, sweep, m.wish_df_post, S, W4, kv, kd, sig, out_sig, fail); break;
+          }
+        } else {
+          wishart_block(g, rng, sweep, k, m.wish_df_post, S, sig, W4, keep, W1, W2, W3, W4 /*A then Sigma*/, kd, fail);
+          if (keep) for (int e = tid; e < kk; e += G) out_sig[e] = W4[e];
+        }
       }
       g.sync();
     }

@@ -11,9 +11,15 @@
 #if defined(__CUDACC__)
 #define BVG_HD __host__ __device__ __forceinline__
 #define BVG_D __device__ __forceinline__
+// out-of-line on the device: the variate generators are called from many sites and would otherwise be inlined
+// (Philox unrolled + log/cospi expansions) at each of them, blowing the kernel past the instruction cache
+#define BVG_HD_NOINLINE __host__ __device__ __noinline__
+#define BVG_UNROLL _Pragma("unroll")
 #else
+#define BVG_UNROLL
 #define BVG_HD inline
 #define BVG_D inline
+#define BVG_HD_NOINLINE inline
 #endif
 
 namespace bvg {
@@ -50,9 +56,7 @@ BVG_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 
 BVG_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
+  BVG_UNROLL
   for (int r = 0; r < 10; ++r) {
     const uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
     const uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
@@ -110,20 +114,22 @@ struct ChainRng {
     return rp->inj[block][(size_t)chain_local * (size_t)rp->inj_chain_stride[block] +
                           (size_t)sweep * (size_t)rp->inj_stride[block] + (size_t)idx];
   }
-  BVG_HD double uniform(int block, int sweep, int idx, int attempt = 0) const {
+  BVG_HD_NOINLINE double uniform(int block, int sweep, int idx, int attempt = 0) const {
     if (rp->inj[block]) return inj_at(block, sweep, idx);
     const Philox4 p = raw(block, sweep, idx, attempt);
     return u53(p.x, p.y);
   }
   // one site -> one normal (Box-Muller cosine branch; the sine is not used so that sites stay independent)
-  BVG_HD double normal(int block, int sweep, int idx, int attempt = 0) const {
+  BVG_HD_NOINLINE double normal(int block, int sweep, int idx, int attempt = 0) const {
     if (rp->inj[block]) return inj_at(block, sweep, idx);
     const Philox4 p = raw(block, sweep, idx, attempt);
     const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
     return sqrt(-2.0 * log(u1)) * bvg_cospi(2.0 * u2);
   }
-  // Gamma(shape, 1), Marsaglia-Tsang 2000 (shape < 1 boosted); attempts are separate sites
-  BVG_HD double gamma(int block, int sweep, int idx, double shape) const {
+  // Gamma(shape, 1), Marsaglia-Tsang 2000 (shape < 1 boosted); attempts are separate sites.  `x0` is the N(0,1)
+  // of attempt 0, i.e. normal(block, sweep, idx, 0): callers may draw it earlier together with other normals so
+  // that all lanes of a tile run one generator call site instead of diverging.
+  BVG_HD_NOINLINE double gamma_from_x0(int block, int sweep, int idx, double shape, double x0) const {
     if (rp->inj[block]) return inj_at(block, sweep, idx);
     double boost = 1.0, a = shape;
     if (a < 1.0) {
@@ -132,10 +138,13 @@ struct ChainRng {
       a += 1.0;
     }
     const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    double x = x0;
     for (int attempt = 0; attempt < 100; ++attempt) {
-      const Philox4 p = raw(block, sweep, idx, attempt);
-      const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
-      const double x = sqrt(-2.0 * log(u1)) * bvg_cospi(2.0 * u2);
+      if (attempt > 0) {
+        const Philox4 p = raw(block, sweep, idx, attempt);
+        const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
+        x = sqrt(-2.0 * log(u1)) * bvg_cospi(2.0 * u2);
+      }
       double v = 1.0 + c * x;
       if (v <= 0.0) continue;
       v = v * v * v;
@@ -144,6 +153,14 @@ struct ChainRng {
       if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v;
     }
     return boost * d;   // unreachable in practice (acceptance > 95 %)
+  }
+  BVG_HD double gamma(int block, int sweep, int idx, double shape) const {
+    if (rp->inj[block]) return inj_at(block, sweep, idx);
+    return gamma_from_x0(block, sweep, idx, shape, normal(block, sweep, idx, 0));
+  }
+  BVG_HD double chi2_from_x0(int block, int sweep, int idx, double df, double x0) const {
+    if (rp->inj[block]) return inj_at(block, sweep, idx);
+    return 2.0 * gamma_from_x0(block, sweep, idx, 0.5 * df, x0);
   }
   BVG_HD double chi2(int block, int sweep, int idx, double df) const {
     if (rp->inj[block]) return inj_at(block, sweep, idx);

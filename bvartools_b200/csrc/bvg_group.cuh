@@ -12,6 +12,7 @@
 namespace bvg {
 
 struct SerialGroup {
+  static constexpr bool kCheapBcast = true;
   BVG_HD int tid() const { return 0; }
   BVG_HD int size() const { return 1; }
   BVG_HD void sync() const {}
@@ -22,6 +23,7 @@ struct SerialGroup {
 #if defined(__CUDACC__)
 template <int G>
 struct TileGroup {
+  static constexpr bool kCheapBcast = true;   // register shuffles
   unsigned mask;
   int lane;   // 0..G-1
   __device__ __forceinline__ TileGroup() {
@@ -42,6 +44,7 @@ struct TileGroup {
 };
 
 struct BlockGroup {
+  static constexpr bool kCheapBcast = false;  // two __syncthreads per broadcast
   double* scratch;   // >= 33 doubles of shared memory
   __device__ __forceinline__ explicit BlockGroup(double* s) : scratch(s) {}
   __device__ __forceinline__ int tid() const { return threadIdx.x; }

@@ -3,16 +3,20 @@
 // lanes (several chains per warp / per CTA) or by a whole CTA; all sweeps of a launch run on-chip with the chain
 // state in shared memory; model constants and injected-variate tables stay in kernel-parameter constant space.
 #include "bvg_kernels.cuh"
-#ifndef BVG_G
-#error "compile with -DBVG_G=<0|4|8|16|32>"
+#if !defined(BVG_G) || !defined(BVG_FEAT)
+#error "compile with -DBVG_G=<0|4|8|16|32> -DBVG_FEAT=<0|2|31>"
 #endif
 #define BVG_CAT2(a, b) a##b
 #define BVG_CAT(a, b) BVG_CAT2(a, b)
+#define BVG_CAT4_(a, b, c, d) a##b##c##d
+#define BVG_CAT4(a, b, c, d) BVG_CAT4_(a, b, c, d)
+#define BVG_KNAME BVG_CAT4(bvar_kernel_g, BVG_G, _f, BVG_FEAT)
+#define BVG_LNAME BVG_CAT4(launch_bvar_g, BVG_G, _f, BVG_FEAT)
 
 namespace bvg {
 
 #if BVG_G > 0
-__global__ void __launch_bounds__(128, 8) BVG_CAT(bvar_tile_kernel_g, BVG_G)(
+__global__ void __launch_bounds__(128, 8) BVG_KNAME(
     const __grid_constant__ BvarModel m, const __grid_constant__ RngParams rp, double* state, int state_len,
     const __grid_constant__ BvarOut out, long long n_chains, int s0, int s1, int burnin, int smem_per_chain) {
   extern __shared__ double smem[];
@@ -23,11 +27,11 @@ __global__ void __launch_bounds__(128, 8) BVG_CAT(bvar_tile_kernel_g, BVG_G)(
   if (chain >= n_chains) return;
   TileGroup<G> g;
   const ChainRng rng(&rp, chain);
-  bvar_chain(g, m, rng, state + (size_t)chain * state_len, smem + (size_t)cib * smem_per_chain, out, chain, s0, s1,
+  bvar_chain<BVG_FEAT>(g, m, rng, state + (size_t)chain * state_len, smem + (size_t)cib * smem_per_chain, out, chain, s0, s1,
              burnin);
 }
 #else
-__global__ void BVG_CAT(bvar_tile_kernel_g, BVG_G)(
+__global__ void BVG_KNAME(
     const __grid_constant__ BvarModel m, const __grid_constant__ RngParams rp, double* state, int state_len,
     const __grid_constant__ BvarOut out, long long n_chains, int s0, int s1, int burnin, int smem_per_chain) {
   extern __shared__ double smem[];
@@ -35,16 +39,16 @@ __global__ void BVG_CAT(bvar_tile_kernel_g, BVG_G)(
   if (chain >= n_chains) return;
   BlockGroup g(smem);
   const ChainRng rng(&rp, chain);
-  bvar_chain(g, m, rng, state + (size_t)chain * state_len, smem + BVG_BLOCK_SCRATCH, out, chain, s0, s1, burnin);
+  bvar_chain<BVG_FEAT>(g, m, rng, state + (size_t)chain * state_len, smem + BVG_BLOCK_SCRATCH, out, chain, s0, s1, burnin);
 }
 #endif
 
-cudaError_t BVG_CAT(launch_bvar_g, BVG_G)(const LaunchPlan& plan, const BvarModel& m, const RngParams& rp,
+cudaError_t BVG_LNAME(const LaunchPlan& plan, const BvarModel& m, const RngParams& rp,
                                           double* state, int state_len, const BvarOut& out, long long n_chains,
                                           int sweep_begin, int sweep_end, int burnin, cudaStream_t stream) {
-  cudaError_t e = set_smem(BVG_CAT(bvar_tile_kernel_g, BVG_G), plan.smem_bytes);
+  cudaError_t e = set_smem(BVG_KNAME, plan.smem_bytes);
   if (e != cudaSuccess) return e;
-  BVG_CAT(bvar_tile_kernel_g, BVG_G)<<<plan.grid, plan.block_threads, plan.smem_bytes, stream>>>(
+  BVG_KNAME<<<plan.grid, plan.block_threads, plan.smem_bytes, stream>>>(
       m, rp, state, state_len, out, n_chains, sweep_begin, sweep_end, burnin, plan.smem_per_chain);
   return cudaGetLastError();
 }

@@ -55,16 +55,29 @@ cudaError_t plan_tvp(const TvpModel& m, long long n_chains, int requested_tpc, L
   return finish_plan(plan, per, n_chains, tpc);
 }
 
+typedef cudaError_t (*bvar_launcher)(BVG_BVAR_ARGS);
+
 cudaError_t launch_bvar(const LaunchPlan& plan, const BvarModel& m, const RngParams& rp, double* state,
                         int state_len, const BvarOut& out, long long n_chains, int s0, int s1, int burnin,
                         cudaStream_t stream) {
+  // smallest compiled feature variant that covers the model: 0 (lean), 2 (+ SSVS/BVS), 31 (everything)
+  const int need = bvar_features_needed(m.sigma_type, m.varsel, m.resid_mode, m.vi_off != nullptr);
+  const int fi = (need == 0) ? 0 : ((need & ~(int)F_VARSEL) == 0 ? 1 : 2);
+  static const bvar_launcher table[5][3] = {
+      {launch_bvar_g0_f0, launch_bvar_g0_f2, launch_bvar_g0_f31},
+      {launch_bvar_g4_f0, launch_bvar_g4_f2, launch_bvar_g4_f31},
+      {launch_bvar_g8_f0, launch_bvar_g8_f2, launch_bvar_g8_f31},
+      {launch_bvar_g16_f0, launch_bvar_g16_f2, launch_bvar_g16_f31},
+      {launch_bvar_g32_f0, launch_bvar_g32_f2, launch_bvar_g32_f31}};
+  int gi = 0;
   switch (plan.threads_per_chain) {
-    case 4: return launch_bvar_g4(plan, m, rp, state, state_len, out, n_chains, s0, s1, burnin, stream);
-    case 8: return launch_bvar_g8(plan, m, rp, state, state_len, out, n_chains, s0, s1, burnin, stream);
-    case 16: return launch_bvar_g16(plan, m, rp, state, state_len, out, n_chains, s0, s1, burnin, stream);
-    case 32: return launch_bvar_g32(plan, m, rp, state, state_len, out, n_chains, s0, s1, burnin, stream);
-    default: return launch_bvar_g0(plan, m, rp, state, state_len, out, n_chains, s0, s1, burnin, stream);
+    case 4: gi = 1; break;
+    case 8: gi = 2; break;
+    case 16: gi = 3; break;
+    case 32: gi = 4; break;
+    default: gi = 0;
   }
+  return table[gi][fi](plan, m, rp, state, state_len, out, n_chains, s0, s1, burnin, stream);
 }
 
 cudaError_t launch_tvp(const LaunchPlan& plan, const TvpModel& m, const RngParams& rp, double* state,

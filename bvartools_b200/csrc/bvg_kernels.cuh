@@ -31,12 +31,15 @@ cudaError_t launch_moments(const double* draws, long long chains, long long iter
                            double* sumsq, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* tflops, cudaStream_t stream);
 
-// per-instantiation launchers (one translation unit each, see Makefile): G = 4, 8, 16, 32 lanes per chain, 0 = CTA
-#define BVG_DECL_TILE(G)                                                                                          \
-  cudaError_t launch_bvar_g##G(const LaunchPlan&, const BvarModel&, const RngParams&, double*, int, const BvarOut&, \
-                               long long, int, int, int, cudaStream_t);                                            \
-  cudaError_t launch_tvp_g##G(const LaunchPlan&, const TvpModel&, const RngParams&, double*, int, double*,         \
-                              long long, const TvpOut&, long long, int, int, int, cudaStream_t);
+// per-instantiation launchers (one translation unit each, see Makefile): G = 4, 8, 16, 32 lanes per chain, 0 = one
+// CTA per chain; BVAR kernels additionally per compile-time feature mask (0 lean, 2 + variable selection, 31 all)
+#define BVG_BVAR_ARGS const LaunchPlan&, const BvarModel&, const RngParams&, double*, int, const BvarOut&, long long, int, int, int, cudaStream_t
+#define BVG_TVP_ARGS const LaunchPlan&, const TvpModel&, const RngParams&, double*, int, double*, long long, const TvpOut&, long long, int, int, int, cudaStream_t
+#define BVG_DECL_TILE(G)                          \
+  cudaError_t launch_bvar_g##G##_f0(BVG_BVAR_ARGS);  \
+  cudaError_t launch_bvar_g##G##_f2(BVG_BVAR_ARGS);  \
+  cudaError_t launch_bvar_g##G##_f31(BVG_BVAR_ARGS); \
+  cudaError_t launch_tvp_g##G(BVG_TVP_ARGS);
 BVG_DECL_TILE(0)
 BVG_DECL_TILE(4)
 BVG_DECL_TILE(8)

@@ -16,7 +16,7 @@ namespace bvg {
 //   fail is set when a pivot is not positive (or NaN).
 // Reference call sites: arma::chol + arma::solve in bvaralg.cpp:306-307, bvartvpalg.cpp:296-297, :429, :482.
 template <class Grp>
-BVG_HD void chol_crout(const Grp& g, double* L, double* dinv, double* b, int n, int& fail) {
+BVG_HD void chol_crout_generic(const Grp& g, double* L, double* dinv, double* b, int n, int& fail) {
   const int G = g.size(), tid = g.tid();
   const int bowner = n % G;
   for (int j = 0; j < n; ++j) {
@@ -55,9 +55,65 @@ BVG_HD void chol_crout(const Grp& g, double* L, double* dinv, double* b, int n, 
   }
 }
 
+// 1/sqrt(d): the device uses the FP64 rsqrt sequence (a few ulp, far inside the 1e-10 parity bar)
+BVG_HD double bvg_rsqrt(double d) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(d);
+#else
+  return 1.0 / sqrt(d);
+#endif
+}
+
+// Same factorisation for n + 1 <= G: ONE row per lane (lane r owns row r, lane n owns the rhs row).  The pivot
+// is broadcast by shuffle instead of a shared-memory round trip, so a column costs one barrier, and the row
+// pointer is fixed, so the inner loop is two LDS + one DFMA per element.
+template <class Grp>
+BVG_HD void chol_crout_rowlane(const Grp& g, double* L, double* dinv, double* b, int n, int& fail) {
+  const int r = g.tid();
+  const bool act = (r < n) || (b != nullptr && r == n);
+  double* Lr = (r < n) ? L + tri(r) : b;
+  for (int j = 0; j < n; ++j) {
+    const double* Lj = L + tri(j);
+    double s = 0.0;
+    if (act && r >= j) {
+      double s0 = Lr[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int c = 0;
+      for (; c + 3 < j; c += 4) {
+        s0 = fma(-Lr[c], Lj[c], s0);
+        s1 = fma(-Lr[c + 1], Lj[c + 1], s1);
+        s2 = fma(-Lr[c + 2], Lj[c + 2], s2);
+        s3 = fma(-Lr[c + 3], Lj[c + 3], s3);
+      }
+      for (; c < j; ++c) s0 = fma(-Lr[c], Lj[c], s0);
+      s = (s0 + s1) + (s2 + s3);
+    }
+    const double d = g.bcast(s, j);
+    if (!(d > 0.0)) fail = 1;
+    const double rs = bvg_rsqrt(d);
+    if (act && r > j) Lr[j] = s * rs;
+    if (r == j) dinv[j] = rs;
+    g.sync();
+  }
+}
+
+// a = L^-T w for n <= G: lane r keeps w_r in a register, a_i is broadcast by shuffle; no barriers in the loop.
+template <class Grp>
+BVG_HD void back_solve_lt_rowlane(const Grp& g, const double* L, const double* dinv, const double* w, double* a,
+                                  int n) {
+  const int r = g.tid();
+  double wr = (r < n) ? w[r] : 0.0;
+  const double dr = (r < n) ? dinv[r] : 0.0;
+  for (int i = n - 1; i >= 0; --i) {
+    const double ai = g.bcast(wr * dr, i);
+    if (r < i) wr = fma(-L[tri(i) + r], ai, wr);
+    if (r == i) a[i] = ai;
+  }
+  g.sync();
+}
+
 // a = L^-T w  (back substitution with the transposed factor); w is destroyed.  a may alias nothing in w.
 template <class Grp>
-BVG_HD void back_solve_lt(const Grp& g, const double* L, const double* dinv, double* w, double* a, int n) {
+BVG_HD void back_solve_lt_generic(const Grp& g, const double* L, const double* dinv, double* w, double* a, int n) {
   const int G = g.size(), tid = g.tid();
   for (int i = n - 1; i >= 0; --i) {
     const double ai = w[i] * dinv[i];
@@ -66,6 +122,18 @@ BVG_HD void back_solve_lt(const Grp& g, const double* L, const double* dinv, dou
     if (tid == 0) a[i] = ai;
     g.sync();
   }
+}
+
+template <class Grp>
+BVG_HD void chol_crout(const Grp& g, double* L, double* dinv, double* b, int n, int& fail) {
+  if (Grp::kCheapBcast && n + 1 <= g.size()) chol_crout_rowlane(g, L, dinv, b, n, fail);
+  else chol_crout_generic(g, L, dinv, b, n, fail);
+}
+
+template <class Grp>
+BVG_HD void back_solve_lt(const Grp& g, const double* L, const double* dinv, double* w, double* a, int n) {
+  if (Grp::kCheapBcast && n <= g.size()) back_solve_lt_rowlane(g, L, dinv, w, a, n);
+  else back_solve_lt_generic(g, L, dinv, w, a, n);
 }
 
 // w = L^-1 b in place (forward substitution), for factors whose rhs was not carried through chol_crout.

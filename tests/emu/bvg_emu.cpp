@@ -6,11 +6,54 @@
 // nothing in bvartools_b200/ loads it, it is not a fallback, and it does not exercise the parallel decomposition
 // (barriers, races) -- that is what the `-m gpu` parity tests and compute-sanitizer runs are for.
 #include <string.h>
+#include <barrier>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../bvartools_b200/csrc/bvg_prepare.hpp"
 
 using namespace bvg;
+
+// SPMD emulation of a G-lane tile with real threads: sync() is a barrier, bcast()/sum() go through a shared
+// exchange buffer with the same butterfly order as the device shuffles.  Slow, test-only.
+struct ThreadShared {
+  std::barrier<> bar;
+  std::vector<double> slot, slot2;
+  explicit ThreadShared(int G) : bar(G), slot(G), slot2(G) {}
+};
+struct ThreadGroup {
+  static constexpr bool kCheapBcast = true;
+  int lane, G;
+  ThreadShared* sh;
+  int tid() const { return lane; }
+  int size() const { return G; }
+  void sync() const { sh->bar.arrive_and_wait(); }
+  double bcast(double v, int src) const {
+    sh->slot[lane] = v;
+    sync();
+    const double r = sh->slot[src];
+    sync();
+    return r;
+  }
+  double sum(double v) const {
+    for (int o = G / 2; o > 0; o >>= 1) {
+      sh->slot[lane] = v;
+      sync();
+      v += sh->slot[lane ^ o];
+      sync();
+    }
+    return v;
+  }
+};
+
+template <class F>
+static void run_lanes(int G, F&& body) {
+  ThreadShared sh(G);
+  std::vector<std::thread> th;
+  for (int l = 0; l < G; ++l) th.emplace_back([&, l] { ThreadGroup g{l, G, &sh}; body(g); });
+  for (auto& t : th) t.join();
+}
 
 static std::string g_err;
 
@@ -54,12 +97,19 @@ extern "C" int emu_bvaralg(const bvg_spec* s, const bvg_out* o) {
   SerialGroup g;
   const int sweeps = s->iterations + s->burnin;
   const int chunk = s->sweeps_per_launch > 0 ? s->sweeps_per_launch : sweeps;
+  const int need = bvar_features_needed(m.sigma_type, m.varsel, m.resid_mode, m.vi_off != nullptr);
+  const int G = s->threads_per_chain;          // 0/1: single-thread group; 2..64: threaded SPMD emulation
   for (long long c = 0; c < s->n_chains; ++c) {
     std::vector<double> st(P.state0);
     ChainRng rng(&rp, c);
     for (int s0 = 0; s0 < sweeps; s0 += chunk) {
       const int s1 = s0 + chunk < sweeps ? s0 + chunk : sweeps;
-      bvar_chain(g, m, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin);
+      auto go = [&](const auto& grp) {           // same variant choice as launch_bvar()
+        if (need == 0) bvar_chain<0>(grp, m, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin);
+        else if ((need & ~(int)F_VARSEL) == 0) bvar_chain<F_VARSEL>(grp, m, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin);
+        else bvar_chain<F_ALL>(grp, m, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin);
+      };
+      if (G > 1) run_lanes(G, go); else go(g);
     }
     if (o->status) o->status[c] = status[c];
   }
@@ -90,7 +140,8 @@ extern "C" int emu_bvartvpalg(const bvg_spec* s, const bvg_out* o) {
     ChainRng rng(&rp, c);
     for (int s0 = 0; s0 < sweeps; s0 += chunk) {
       const int s1 = s0 + chunk < sweeps ? s0 + chunk : sweeps;
-      tvp_chain(g, m, rng, st.data(), scratch.data(), sm.data(), out, c, s0, s1, s->burnin);
+      auto go = [&](const auto& grp) { tvp_chain(grp, m, rng, st.data(), scratch.data(), sm.data(), out, c, s0, s1, s->burnin); };
+      if (s->threads_per_chain > 1) run_lanes(s->threads_per_chain, go); else go(g);
     }
     if (o->status) o->status[c] = status[c];
   }

@@ -28,8 +28,8 @@ def load_emu():
     srcs = [EMU_SRC] + list((ROOT / "bvartools_b200" / "csrc").glob("*.cuh")) + \
            list((ROOT / "bvartools_b200" / "csrc").glob("*.hpp")) + [ROOT / "include" / "bvargpu.h"]
     if not EMU_SO.exists() or any(s.stat().st_mtime > EMU_SO.stat().st_mtime for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-x", "c++",
-                               str(EMU_SRC), "-o", str(EMU_SO)])
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC",
+                               "-ffp-contract=off", "-x", "c++", str(EMU_SRC), "-o", str(EMU_SO)])
     lib = C.CDLL(str(EMU_SO))
     for fn in ("emu_bvaralg", "emu_bvartvpalg"):
         getattr(lib, fn).argtypes = [C.POINTER(_abi.BvgSpec), C.POINTER(_abi.BvgOut)]
