@@ -60,6 +60,19 @@ struct BvarModel {
   const double* omega_off;         // k x k off-diagonal part of the initial Sigma^-1 (gamma prior), zero diagonal
 };
 
+// The small read-only tables every sweep touches.  The CUDA kernels stage them once per CTA into shared memory
+// (LDS instead of L1-cached global loads on the hot path); the host emulation points them at the model's arrays.
+struct BvarConsts {
+  const double* XX; const double* YX; const double* Aols; const double* SSE; const double* S0;
+  const double* mu; const double* vdiag0;
+};
+BVG_HD int bvar_consts_len(int k, int M) { return M * M + 2 * k * M + 2 * k * k + 2 * k * M; }
+BVG_HD BvarConsts bvar_consts_of(const BvarModel& m) {
+  BvarConsts c;
+  c.XX = m.XX; c.YX = m.YX; c.Aols = m.Aols; c.SSE = m.SSE; c.S0 = m.S0; c.mu = m.mu; c.vdiag0 = m.vdiag0;
+  return c;
+}
+
 // Per-chain persistent state in global memory (between kernel launches), doubles:
 //   [0, k*k)            Sigma^-1 (col-major)           (const Sigma)          | unused for SV
 //   then n              vdiag   (diagonal of V^-1, changed by SSVS)
@@ -98,7 +111,7 @@ BVG_HD void small_chol(const Grp& g, const double* A, double* Lp, double* dinv, 
     Lp[e] = A[i + k * j];
   }
   g.sync();
-  chol_crout(g, Lp, dinv, (double*)nullptr, k, fail);
+  chol_crout_generic(g, Lp, dinv, (double*)nullptr, k, fail);   // k x k: keep the unrolled variant for the n x n factor
 }
 
 // The inverse-Wishart block (bvaralg.cpp:511-514,528): given S = S0 + u u' (full, col-major) draw
@@ -115,7 +128,7 @@ BVG_HD void wishart_block(const Grp& g, const ChainRng& rng, int sweep, int k, d
   tri_inverse(g, W1, kd, W2, k);
   mtm_lower(g, W2, W3, k);
   // 3. Sbar = Ld Ld'  (in place in W3, kd);  D = Ld' upper
-  chol_crout(g, W3, kd, (double*)nullptr, k, fail);
+  chol_crout_generic(g, W3, kd, (double*)nullptr, k, fail);
   fix_diag(g, W3, kd, k);
   // 4. Bartlett factor A (upper, full col-major in W4): A_ii = sqrt(chi2(df - i)), strict upper N(0,1) filled
   //    column by column (column i holds i normals)
@@ -363,8 +376,9 @@ BVG_HD void sv_step(const Grp& g, const ChainRng& rng, int sweep, const BvarMode
 
 // ---- the chain ---------------------------------------------------------------------------------------------
 template <int FEAT, class Grp>
-BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, double* state, double* sm,
-                       const BvarOut& out, long long chain_local, int sweep_begin, int sweep_end, int burnin) {
+BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, const ChainRng& rng, double* state,
+                       double* sm, const BvarOut& out, long long chain_local, int sweep_begin, int sweep_end,
+                       int burnin) {
   const int G = g.size(), tid = g.tid();
   const int k = m.k, T = m.T, M = m.M, n = m.n, kk = k * k;
   const bool sv = (FEAT & F_SV) && m.sigma_type == SIG_SV;
@@ -456,7 +470,7 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, do
         for (int r = tid; r < n; r += G) {
           const int j = r / k, i = r % k;
           double s = 0.0;
-          for (int i2 = 0; i2 < k; ++i2) s = fma(sig[i + k * i2], m.YX[i2 + k * j], s);   // (Sigma^-1 Y X')_ij
+          for (int i2 = 0; i2 < k; ++i2) s = fma(sig[i + k * i2], cs.YX[i2 + k * j], s);  // (Sigma^-1 Y X')_ij
           w[r] = s;
         }
       }
@@ -465,18 +479,33 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, do
         const int j = r / k, i = r % k;
         double* Lr = L + tri(r);
         const double lr = bvs ? lam[r] : 1.0;
-        int j2 = 0, i2 = 0;
-        for (int c = 0; c <= r; ++c) {
-          double gv;
-          if (sv) gv = (i == i2) ? GW[i * tri(M) + tri(j) + j2] : 0.0;
-          else gv = m.XX[j + M * j2] * sig[i + k * i2];
-          if (bvs) gv *= lr * lam[c];
-          if (vi_off != nullptr) gv += vi_off[tri(r) + c];
-          if (c == r) gv += vdiag[r];
-          Lr[c] = gv;
-          if (++i2 == k) { i2 = 0; ++j2; }
+        if (sv) {
+          int j2 = 0, i2 = 0;
+          for (int c = 0; c <= r; ++c) {
+            double gv = (i == i2) ? GW[i * tri(M) + tri(j) + j2] : 0.0;
+            if (bvs) gv *= lr * lam[c];
+            if (vi_off != nullptr) gv += vi_off[tri(r) + c];
+            if (c == r) gv += vdiag[r];
+            Lr[c] = gv;
+            if (++i2 == k) { i2 = 0; ++j2; }
+          }
+        } else {
+          // row (j,i) of (XX' (x) Sigma^-1): one XX entry per regressor block, k products each
+          const double* sigrow = sig + i;
+          int c = 0;
+          for (int j2 = 0; j2 <= j; ++j2) {
+            const double xv = cs.XX[j + M * j2];
+            const int i2max = (j2 < j) ? k - 1 : i;
+            for (int i2 = 0; i2 <= i2max; ++i2, ++c) {
+              double gv = xv * sigrow[k * i2];
+              if (bvs) gv *= lr * lam[c];
+              if (vi_off != nullptr) gv += vi_off[tri(r) + c];
+              Lr[c] = gv;
+            }
+          }
+          Lr[r] += vdiag[r];
         }
-        double b = w[r] * lr + vdiag[r] * m.mu[r];
+        double b = w[r] * lr + vdiag[r] * cs.mu[r];
         if (vmu_off != nullptr) b += vmu_off[r];
         w[r] = b;
       }
@@ -519,12 +548,12 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, do
       }
       g.sync();
     } else {
-      for (int r = tid; r < n; r += G) Dm[r] = (bvs ? lam[r] * a[r] : a[r]) - m.Aols[r];  // r = i + k j
+      for (int r = tid; r < n; r += G) Dm[r] = (bvs ? lam[r] * a[r] : a[r]) - cs.Aols[r];  // r = i + k j
       g.sync();
       for (int r = tid; r < n; r += G) {
         const int j = r / k, i = r % k;
         double s = 0.0;
-        for (int j2 = 0; j2 < M; ++j2) s = fma(Dm[i + k * j2], m.XX[j2 + M * j], s);
+        for (int j2 = 0; j2 < M; ++j2) s = fma(Dm[i + k * j2], cs.XX[j2 + M * j], s);
         Wm[r] = s;                                                                        // (D XX')_ij
       }
       g.sync();
@@ -556,12 +585,12 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, do
                   for (int i2 = 0; i2 < k; ++i2) v = fma(sig[i + k * i2], U[i2 + k * t], v);
                   cj = fma(m.X[j + M * t], v, cj);
                 }
-                gj = m.XX[j + M * j] * sig[i + k * i];
+                gj = cs.XX[j + M * j] * sig[i + k * i];
               }
             } else {
               // c_j = [Sigma^-1 (Y - A_AG X) X']_ij = -[Sigma^-1 D XX']_ij
               for (int i2 = 0; i2 < k; ++i2) cj = fma(-sig[i + k * i2], Wm[i2 + k * j], cj);
-              gj = m.XX[j + M * j] * sig[i + k * i];
+              gj = cs.XX[j + M * j] * sig[i + k * i];
             }
             const double ar = a[r];
             const double d0 = lam[r] * ar, d1 = (lam[r] - 1.0) * ar;
@@ -586,12 +615,12 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, do
         }
         g.sync();
       } else {
-        for (int r = tid; r < n; r += G) Dm[r] = a[r] - m.Aols[r];
+        for (int r = tid; r < n; r += G) Dm[r] = a[r] - cs.Aols[r];
         g.sync();
         for (int r = tid; r < n; r += G) {
           const int j = r / k, i = r % k;
           double s = 0.0;
-          for (int j2 = 0; j2 < M; ++j2) s = fma(Dm[i + k * j2], m.XX[j2 + M * j], s);
+          for (int j2 = 0; j2 < M; ++j2) s = fma(Dm[i + k * j2], cs.XX[j2 + M * j], s);
           Wm[r] = s;
         }
         g.sync();
@@ -628,10 +657,10 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, do
         W1[e] = S[i + k * (e - tri(i))];
       }
       g.sync();
-      chol_crout(g, W1, kd, W4, k, fail);
+      chol_crout_generic(g, W1, kd, W4, k, fail);
       for (int i = tid; i < k; i += G) W4[i] += rng.normal(VB_HINIT_N, sweep, i);
       g.sync();
-      back_solve_lt(g, W1, kd, W4, h_init, k);
+      back_solve_lt_generic(g, W1, kd, W4, h_init, k);
       if (keep) {
         // Sigma_t = diag(exp(h_t)) (solve of the diagonal block, :523-525); sigma_h (:526)
         for (int e = tid; e < kk * T; e += G) {
@@ -650,7 +679,7 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, do
         if (direct) {
           for (int t = 0; t < T; ++t) s = fma(U[i + k * t], U[j + k * t], s);
         } else {
-          s = m.SSE[e];
+          s = cs.SSE[e];
           for (int j2 = 0; j2 < M; ++j2) s = fma(Wm[i + k * j2], Dm[j + k * j2], s);
         }
         S[e] = s;
@@ -672,7 +701,7 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const ChainRng& rng, do
           for (int e = tid; e < kk; e += G) out_sig[e] = W4[e];
         }
       } else {
-        for (int e = tid; e < kk; e += G) S[e] += m.S0[e];
+        for (int e = tid; e < kk; e += G) S[e] += cs.S0[e];
         g.sync();
         // symmetrise exactly (moment mode computes both triangles independently)
         for (int e = tid; e < kk; e += G) { const int i = e % k, j = e / k; if (i < j) S[e] = S[j + k * i]; }

@@ -15,8 +15,26 @@
 
 namespace bvg {
 
+// copy the read-only tables of the model into the CTA's shared memory (all threads; ends with a CTA barrier)
+__device__ __forceinline__ BvarConsts stage_consts(const BvarModel& m, double* dst) {
+  BvarConsts c;
+  const int k = m.k, M = m.M, n = m.n;
+  const double* src[7] = {m.XX, m.YX, m.Aols, m.SSE, m.S0, m.mu, m.vdiag0};
+  const int len[7] = {M * M, k * M, k * M, k * k, k * k, n, n};
+  const double** out[7] = {&c.XX, &c.YX, &c.Aols, &c.SSE, &c.S0, &c.mu, &c.vdiag0};
+#pragma unroll
+  for (int a = 0; a < 7; ++a) {
+    if (src[a] != nullptr)
+      for (int e = threadIdx.x; e < len[a]; e += blockDim.x) dst[e] = src[a][e];
+    *out[a] = (src[a] != nullptr) ? dst : nullptr;
+    dst += len[a];
+  }
+  __syncthreads();
+  return c;
+}
+
 #if BVG_G > 0
-__global__ void __launch_bounds__(128, 8) BVG_KNAME(
+__global__ void __launch_bounds__(128, 7) BVG_KNAME(
     const __grid_constant__ BvarModel m, const __grid_constant__ RngParams rp, double* state, int state_len,
     const __grid_constant__ BvarOut out, long long n_chains, int s0, int s1, int burnin, int smem_per_chain) {
   extern __shared__ double smem[];
@@ -24,11 +42,12 @@ __global__ void __launch_bounds__(128, 8) BVG_KNAME(
   const int cpb = blockDim.x / G;
   const int cib = threadIdx.x / G;
   const long long chain = (long long)blockIdx.x * cpb + cib;
+  const BvarConsts cs = stage_consts(m, smem);
   if (chain >= n_chains) return;
   TileGroup<G> g;
   const ChainRng rng(&rp, chain);
-  bvar_chain<BVG_FEAT>(g, m, rng, state + (size_t)chain * state_len, smem + (size_t)cib * smem_per_chain, out, chain, s0, s1,
-             burnin);
+  double* mine = smem + bvar_consts_len(m.k, m.M) + (size_t)cib * smem_per_chain;
+  bvar_chain<BVG_FEAT>(g, m, cs, rng, state + (size_t)chain * state_len, mine, out, chain, s0, s1, burnin);
 }
 #else
 __global__ void BVG_KNAME(
@@ -38,8 +57,10 @@ __global__ void BVG_KNAME(
   const long long chain = blockIdx.x;
   if (chain >= n_chains) return;
   BlockGroup g(smem);
+  const BvarConsts cs = stage_consts(m, smem + BVG_BLOCK_SCRATCH);
   const ChainRng rng(&rp, chain);
-  bvar_chain<BVG_FEAT>(g, m, rng, state + (size_t)chain * state_len, smem + BVG_BLOCK_SCRATCH, out, chain, s0, s1, burnin);
+  double* mine = smem + BVG_BLOCK_SCRATCH + bvar_consts_len(m.k, m.M);
+  bvar_chain<BVG_FEAT>(g, m, cs, rng, state + (size_t)chain * state_len, mine, out, chain, s0, s1, burnin);
 }
 #endif
 

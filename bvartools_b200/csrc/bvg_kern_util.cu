@@ -10,25 +10,25 @@ static int pick_tile(int n_work) {
   return 4;
 }
 
-static cudaError_t finish_plan(LaunchPlan* plan, int per_chain_doubles, long long n_chains, int tpc) {
+static cudaError_t finish_plan(LaunchPlan* plan, int per_chain_doubles, long long n_chains, int tpc, int shared_doubles = 0) {
   if (tpc <= 32) {
     if (tpc != 4 && tpc != 8 && tpc != 16 && tpc != 32) return cudaErrorInvalidValue;
     plan->threads_per_chain = tpc;
     plan->smem_per_chain = per_chain_doubles;
     plan->block_threads = 128;
     plan->chains_per_block = 128 / tpc;
-    while (plan->chains_per_block > 1 && (size_t)plan->chains_per_block * per_chain_doubles * 8 > 200 * 1024) {
+    while (plan->chains_per_block > 1 && ((size_t)plan->chains_per_block * per_chain_doubles + shared_doubles) * 8 > 200 * 1024) {
       plan->chains_per_block >>= 1;
       plan->block_threads >>= 1;
     }
-    plan->smem_bytes = (size_t)plan->chains_per_block * per_chain_doubles * 8;
+    plan->smem_bytes = ((size_t)plan->chains_per_block * per_chain_doubles + shared_doubles) * 8;
   } else {
     if (tpc % 32 != 0 || tpc > 1024) return cudaErrorInvalidValue;
     plan->threads_per_chain = tpc;
     plan->smem_per_chain = per_chain_doubles;
     plan->block_threads = tpc;
     plan->chains_per_block = 1;
-    plan->smem_bytes = ((size_t)per_chain_doubles + BVG_BLOCK_SCRATCH) * 8;
+    plan->smem_bytes = ((size_t)per_chain_doubles + BVG_BLOCK_SCRATCH + shared_doubles) * 8;
   }
   if (plan->smem_bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
   plan->grid = (int)((n_chains + plan->chains_per_block - 1) / plan->chains_per_block);
@@ -42,7 +42,7 @@ cudaError_t plan_bvar(const BvarModel& m, long long n_chains, int requested_tpc,
     if ((size_t)per * 8 > 24 * 1024 || m.n > 64) tpc = (m.n > 96) ? 256 : 128;   // one CTA per chain
     else tpc = pick_tile(m.n > m.k ? m.n : m.k);
   }
-  return finish_plan(plan, per, n_chains, tpc);
+  return finish_plan(plan, per, n_chains, tpc, bvar_consts_len(m.k, m.M));
 }
 
 cudaError_t plan_tvp(const TvpModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan) {

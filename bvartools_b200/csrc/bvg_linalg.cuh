@@ -64,28 +64,27 @@ BVG_HD double bvg_rsqrt(double d) {
 #endif
 }
 
-// Same factorisation for n + 1 <= G: ONE row per lane (lane r owns row r, lane n owns the rhs row).  The pivot
-// is broadcast by shuffle instead of a shared-memory round trip, so a column costs one barrier, and the row
-// pointer is fixed, so the inner loop is two LDS + one DFMA per element.
+// Same factorisation for n + 1 <= G <= 32: ONE row per lane (lane r owns row r, lane n owns the rhs row).  The
+// pivot is broadcast by shuffle instead of a shared-memory round trip, so a column costs one barrier.  Both loops
+// are fully unrolled on the device (the column index becomes a compile-time constant, the early exit on n stays
+// dynamic): the body of the dot product is then exactly two LDS.64 with immediate offsets and one DFMA, with no
+// loop control or address arithmetic.
+#define BVG_ROWLANE_MAX 32
 template <class Grp>
 BVG_HD void chol_crout_rowlane(const Grp& g, double* L, double* dinv, double* b, int n, int& fail) {
   const int r = g.tid();
   const bool act = (r < n) || (b != nullptr && r == n);
-  double* Lr = (r < n) ? L + tri(r) : b;
-  for (int j = 0; j < n; ++j) {
+  double* Lr = (r < n) ? L + tri(r) : (b != nullptr ? b : L);
+  BVG_UNROLL
+  for (int j = 0; j < BVG_ROWLANE_MAX; ++j) {
+    if (j >= n) break;
     const double* Lj = L + tri(j);
     double s = 0.0;
     if (act && r >= j) {
-      double s0 = Lr[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int c = 0;
-      for (; c + 3 < j; c += 4) {
-        s0 = fma(-Lr[c], Lj[c], s0);
-        s1 = fma(-Lr[c + 1], Lj[c + 1], s1);
-        s2 = fma(-Lr[c + 2], Lj[c + 2], s2);
-        s3 = fma(-Lr[c + 3], Lj[c + 3], s3);
-      }
-      for (; c < j; ++c) s0 = fma(-Lr[c], Lj[c], s0);
-      s = (s0 + s1) + (s2 + s3);
+      double acc[4] = {Lr[j], 0.0, 0.0, 0.0};
+      BVG_UNROLL
+      for (int c = 0; c < j; ++c) acc[c & 3] = fma(-Lr[c], Lj[c], acc[c & 3]);
+      s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     }
     const double d = g.bcast(s, j);
     if (!(d > 0.0)) fail = 1;
@@ -96,16 +95,19 @@ BVG_HD void chol_crout_rowlane(const Grp& g, double* L, double* dinv, double* b,
   }
 }
 
-// a = L^-T w for n <= G: lane r keeps w_r in a register, a_i is broadcast by shuffle; no barriers in the loop.
+// a = L^-T w for n <= G <= 32: lane r keeps w_r in a register, a_i is broadcast by shuffle; no barriers in the loop.
 template <class Grp>
 BVG_HD void back_solve_lt_rowlane(const Grp& g, const double* L, const double* dinv, const double* w, double* a,
                                   int n) {
   const int r = g.tid();
   double wr = (r < n) ? w[r] : 0.0;
   const double dr = (r < n) ? dinv[r] : 0.0;
-  for (int i = n - 1; i >= 0; --i) {
+  const double* Lc = L + ((r < n) ? r : 0);
+  BVG_UNROLL
+  for (int i = BVG_ROWLANE_MAX - 1; i >= 0; --i) {
+    if (i >= n) continue;
     const double ai = g.bcast(wr * dr, i);
-    if (r < i) wr = fma(-L[tri(i) + r], ai, wr);
+    if (r < i) wr = fma(-Lc[tri(i)], ai, wr);
     if (r == i) a[i] = ai;
   }
   g.sync();
@@ -126,13 +128,13 @@ BVG_HD void back_solve_lt_generic(const Grp& g, const double* L, const double* d
 
 template <class Grp>
 BVG_HD void chol_crout(const Grp& g, double* L, double* dinv, double* b, int n, int& fail) {
-  if (Grp::kCheapBcast && n + 1 <= g.size()) chol_crout_rowlane(g, L, dinv, b, n, fail);
+  if (Grp::kCheapBcast && n + 1 <= g.size() && n <= BVG_ROWLANE_MAX) chol_crout_rowlane(g, L, dinv, b, n, fail);
   else chol_crout_generic(g, L, dinv, b, n, fail);
 }
 
 template <class Grp>
 BVG_HD void back_solve_lt(const Grp& g, const double* L, const double* dinv, double* w, double* a, int n) {
-  if (Grp::kCheapBcast && n <= g.size()) back_solve_lt_rowlane(g, L, dinv, w, a, n);
+  if (Grp::kCheapBcast && n <= g.size() && n <= BVG_ROWLANE_MAX) back_solve_lt_rowlane(g, L, dinv, w, a, n);
   else back_solve_lt_generic(g, L, dinv, w, a, n);
 }
 

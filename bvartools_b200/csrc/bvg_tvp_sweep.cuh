@@ -271,10 +271,10 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
         W1[e] = S[i + k * (e - tri(i))];
       }
       g.sync();
-      chol_crout(g, W1, kd, W4, k, fail);
+      chol_crout_generic(g, W1, kd, W4, k, fail);
       for (int i = tid; i < k; i += G) W4[i] += rng.normal(VB_HINIT_N, sweep, i);
       g.sync();
-      back_solve_lt(g, W1, kd, W4, h_init, k);                                         // :429
+      back_solve_lt_generic(g, W1, kd, W4, h_init, k);                                         // :429
       if (keep) {
         for (int e = tid; e < kk * T; e += G) {
           const int t = e / kk, f = e % kk, i = f % k, j = f / k;

@@ -97,6 +97,7 @@ extern "C" int emu_bvaralg(const bvg_spec* s, const bvg_out* o) {
   SerialGroup g;
   const int sweeps = s->iterations + s->burnin;
   const int chunk = s->sweeps_per_launch > 0 ? s->sweeps_per_launch : sweeps;
+  const BvarConsts cs = bvar_consts_of(m);
   const int need = bvar_features_needed(m.sigma_type, m.varsel, m.resid_mode, m.vi_off != nullptr);
   const int G = s->threads_per_chain;          // 0/1: single-thread group; 2..64: threaded SPMD emulation
   for (long long c = 0; c < s->n_chains; ++c) {
@@ -105,9 +106,9 @@ extern "C" int emu_bvaralg(const bvg_spec* s, const bvg_out* o) {
     for (int s0 = 0; s0 < sweeps; s0 += chunk) {
       const int s1 = s0 + chunk < sweeps ? s0 + chunk : sweeps;
       auto go = [&](const auto& grp) {           // same variant choice as launch_bvar()
-        if (need == 0) bvar_chain<0>(grp, m, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin);
-        else if ((need & ~(int)F_VARSEL) == 0) bvar_chain<F_VARSEL>(grp, m, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin);
-        else bvar_chain<F_ALL>(grp, m, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin);
+        if (need == 0) bvar_chain<0>(grp, m, cs, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin);
+        else if ((need & ~(int)F_VARSEL) == 0) bvar_chain<F_VARSEL>(grp, m, cs, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin);
+        else bvar_chain<F_ALL>(grp, m, cs, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin);
       };
       if (G > 1) run_lanes(G, go); else go(g);
     }
