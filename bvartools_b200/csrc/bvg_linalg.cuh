@@ -65,25 +65,32 @@ BVG_HD double bvg_rsqrt(double d) {
 }
 
 // Same factorisation for n + 1 <= G <= 32: ONE row per lane (lane r owns row r, lane n owns the rhs row).  The
-// pivot is broadcast by shuffle instead of a shared-memory round trip, so a column costs one barrier.  Both loops
-// are fully unrolled on the device (the column index becomes a compile-time constant, the early exit on n stays
-// dynamic): the body of the dot product is then exactly two LDS.64 with immediate offsets and one DFMA, with no
-// loop control or address arithmetic.
+// pivot is broadcast by shuffle instead of a shared-memory round trip, so a column costs one barrier.  The dot
+// product over the j already-final columns enters a 31-deep unrolled chain at depth j (switch with fall-through,
+// one uniform indirect branch per column): its body is two LDS.64 with immediate offsets and one DFMA per
+// element, without loop control, and -- unlike a fully unrolled factorisation -- the same ~100 instructions are
+// reused by every column, so the kernel stays inside the instruction cache.
 #define BVG_ROWLANE_MAX 32
+#define BVG_DOT_CASE(c) case (c) + 1: acc[(c) & 3] = fma(-Lr[c], Lj[c], acc[(c) & 3]);
 template <class Grp>
 BVG_HD void chol_crout_rowlane(const Grp& g, double* L, double* dinv, double* b, int n, int& fail) {
   const int r = g.tid();
   const bool act = (r < n) || (b != nullptr && r == n);
   double* Lr = (r < n) ? L + tri(r) : (b != nullptr ? b : L);
-  BVG_UNROLL
-  for (int j = 0; j < BVG_ROWLANE_MAX; ++j) {
-    if (j >= n) break;
-    const double* Lj = L + tri(j);
+  const double* Lj = L;
+  for (int j = 0; j < n; ++j) {
     double s = 0.0;
     if (act && r >= j) {
       double acc[4] = {Lr[j], 0.0, 0.0, 0.0};
-      BVG_UNROLL
-      for (int c = 0; c < j; ++c) acc[c & 3] = fma(-Lr[c], Lj[c], acc[c & 3]);
+      switch (j) {
+        BVG_DOT_CASE(30) BVG_DOT_CASE(29) BVG_DOT_CASE(28) BVG_DOT_CASE(27) BVG_DOT_CASE(26) BVG_DOT_CASE(25)
+        BVG_DOT_CASE(24) BVG_DOT_CASE(23) BVG_DOT_CASE(22) BVG_DOT_CASE(21) BVG_DOT_CASE(20) BVG_DOT_CASE(19)
+        BVG_DOT_CASE(18) BVG_DOT_CASE(17) BVG_DOT_CASE(16) BVG_DOT_CASE(15) BVG_DOT_CASE(14) BVG_DOT_CASE(13)
+        BVG_DOT_CASE(12) BVG_DOT_CASE(11) BVG_DOT_CASE(10) BVG_DOT_CASE(9) BVG_DOT_CASE(8) BVG_DOT_CASE(7)
+        BVG_DOT_CASE(6) BVG_DOT_CASE(5) BVG_DOT_CASE(4) BVG_DOT_CASE(3) BVG_DOT_CASE(2) BVG_DOT_CASE(1)
+        BVG_DOT_CASE(0)
+        default: break;
+      }
       s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     }
     const double d = g.bcast(s, j);
@@ -91,9 +98,11 @@ BVG_HD void chol_crout_rowlane(const Grp& g, double* L, double* dinv, double* b,
     const double rs = bvg_rsqrt(d);
     if (act && r > j) Lr[j] = s * rs;
     if (r == j) dinv[j] = rs;
+    Lj += j + 1;
     g.sync();
   }
 }
+#undef BVG_DOT_CASE
 
 // a = L^-T w for n <= G <= 32: lane r keeps w_r in a register, a_i is broadcast by shuffle; no barriers in the loop.
 template <class Grp>
@@ -102,13 +111,12 @@ BVG_HD void back_solve_lt_rowlane(const Grp& g, const double* L, const double* d
   const int r = g.tid();
   double wr = (r < n) ? w[r] : 0.0;
   const double dr = (r < n) ? dinv[r] : 0.0;
-  const double* Lc = L + ((r < n) ? r : 0);
-  BVG_UNROLL
-  for (int i = BVG_ROWLANE_MAX - 1; i >= 0; --i) {
-    if (i >= n) continue;
+  const double* Li = L + tri(n - 1) + ((r < n) ? r : 0);      // &L[n-1][r]
+  for (int i = n - 1; i >= 0; --i) {
     const double ai = g.bcast(wr * dr, i);
-    if (r < i) wr = fma(-Lc[tri(i)], ai, wr);
+    if (r < i) wr = fma(-Li[0], ai, wr);
     if (r == i) a[i] = ai;
+    Li -= i;
   }
   g.sync();
 }
