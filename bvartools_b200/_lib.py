@@ -60,10 +60,11 @@ def lib():
     L.bvg_post_normal_sur.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, dp, dp, dp, C.c_int, dp, dp, dp,
                                       C.c_uint64, C.c_int, dp]
     L.bvg_ssvs.argtypes = [C.c_int64, C.c_int, dp, dp, dp, dp, ip, C.c_int, dp, C.c_uint64, dp, dp]
-    L.bvg_bvs.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, ip, C.c_int, dp, dp,
-                          C.c_uint64, dp]
+    L.bvg_bvs.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, dp, dp, dp, C.c_int, dp, dp, C.c_int, dp, ip,
+                          C.c_int, dp, dp, C.c_uint64, dp]
     L.bvg_stochvol.argtypes = [C.c_int64, C.c_int, C.c_int, dp, dp, dp, dp, dp, C.c_int, dp, dp, C.c_uint64, dp, ip]
-    L.bvg_kalman_dk.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, C.c_uint64, dp]
+    L.bvg_kalman_dk.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, C.c_int, dp, dp, dp,
+                                C.c_uint64, dp]
     _lib = L
     return L
 

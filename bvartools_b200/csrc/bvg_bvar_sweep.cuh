@@ -315,7 +315,7 @@ BVG_HD void small_spd_inverse(const Grp& g, const double* A, double* out, double
 // per series.
 template <class Grp>
 BVG_HD void sv_step(const Grp& g, const ChainRng& rng, int sweep, const BvarModel& m, double* U, double* h,
-                    const double* sigma_h, const double* h_init, double* pr, double* rh) {
+                    const double* sigma_h, const double* h_init, double* pr, double* rh, int* s_out = nullptr) {
   const int G = g.size(), tid = g.tid(), k = m.k, T = m.T, J = m.n_mix;
   for (int e = tid; e < k * T; e += G) {
     const int i = e % k, t = e / k;
@@ -339,6 +339,7 @@ BVG_HD void sv_step(const Grp& g, const ChainRng& rng, int sweep, const BvarMode
     }
     int s = J - cnt;
     if (s > J - 1) s = J - 1;                                                      // reference: out of bounds
+    if (s_out != nullptr) s_out[t + T * i] = s;
     const double p = 1.0 / m.mix_s2[s];                                            // :101
     pr[i * T + t] = p;
     rh[i * T + t] = p * (ys - m.mix_mu[s]);                                        // :103 sigs * (y - mu_s)
@@ -511,7 +512,7 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
       }
       g.sync();
       // ---- a = L^-T (L^-1 b + eps)                                                  (bvaralg.cpp:306-307)
-      chol_crout(g, L, dinv, w, n, fail);
+      chol_crout_sel<true>(g, L, dinv, w, n, fail);
       for (int r = tid; r < n; r += G) w[r] += a[r];            // eps drawn at the top of the sweep
       g.sync();
       back_solve_lt(g, L, dinv, w, a, n);

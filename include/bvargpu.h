@@ -189,19 +189,24 @@ int bvg_post_normal_sur(int64_t B, int k, int T, int n, const double* y, const d
 int bvg_ssvs(int64_t B, int n, const double* a, const double* tau0, const double* tau1, const double* prob_prior,
              const int32_t* include, int n_include, const double* u, uint64_t seed, double* lambda_out,
              double* vdiag_out);
-/* bvs (src/bvs.cpp:73-159): constant parameters; lambda [B][n] (diagonal), sigma_i [B][k x k] */
-int bvg_bvs(int64_t B, int k, int T, int M, const double* y, const double* x, const double* a,
-            const double* lambda, const double* sigma_i, const double* prob_prior, const int32_t* include,
-            int n_include, const double* u1, const double* u2, uint64_t seed, double* lambda_out);
+/* bvs (src/bvs.cpp:73-159): y k x T and z kT x n shared; per problem a [B][n] (a_tv = 0) or [B][n x T]
+ * (a_tv = 1, time-varying coefficients, bvs.cpp:83-86,141-146), lambda [B][n] (the diagonal of the reference's
+ * n x n indicator matrix), sigma_i [B][k x k] (sigma_tv = 0) or [B][kT x k] (sigma_tv = 1, bvs.cpp:88-100) */
+int bvg_bvs(int64_t B, int k, int T, int n, const double* y, const double* z, const double* a, int a_tv,
+            const double* lambda, const double* sigma_i, int sigma_tv, const double* prob_prior,
+            const int32_t* include, int n_include, const double* u1, const double* u2, uint64_t seed,
+            double* lambda_out);
 /* stochvol_ksc1998 / stochvol_ocsn2007 / stoch_vol (src/stochvol_*.cpp:60-114): y,h [B][T x k] */
 int bvg_stochvol(int64_t B, int T, int k, const double* y, const double* h, const double* sigma,
                  const double* h_init, const double* constant, int mixture, const double* u, const double* eps,
                  uint64_t seed, double* h_out, int32_t* s_out);
-/* kalman_dk (src/kalman_dk.cpp:91-184): y k x T and z kT x n shared; per problem sigma_u (k x k),
- * sigma_v (n x n), B (n x n), a_init (n), P_init (n x n); out [B][n x (T+1)] */
+/* kalman_dk (src/kalman_dk.cpp:91-184): y k x T and z kT x n shared; per problem sigma_u (k x k, or kT x k
+ * when tv_mask & 1), sigma_v (n x n, or nT x n when tv_mask & 2), B (n x n, or nT x n when tv_mask & 4) -- the
+ * stacked forms of kalman_dk.cpp:99-121 --, a_init (n), P_init (n x n); out [B][n x (T+1)].
+ * eps: [B][n + T (k + n)] N(0,1) in the reference's consumption order, or NULL = Philox(seed) */
 int bvg_kalman_dk(int64_t B, int k, int T, int n, const double* y, const double* z, const double* sigma_u,
-                  const double* sigma_v, const double* Bmat, const double* a_init, const double* P_init,
-                  const double* eps, uint64_t seed, double* out);
+                  const double* sigma_v, const double* Bmat, int tv_mask, const double* a_init,
+                  const double* P_init, const double* eps, uint64_t seed, double* out);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@
 #include <thread>
 #include <vector>
 #include "../../bvartools_b200/csrc/bvg_prepare.hpp"
+#include "../../bvartools_b200/csrc/bvg_blocks.cuh"
 
 using namespace bvg;
 
@@ -168,4 +169,153 @@ extern "C" void emu_variates(uint64_t seed, uint64_t chain, int block, int sweep
 extern "C" void emu_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
   const Philox4 p = philox4x32_10(c0, c1, c2, c3, k0, k1);
   out[0] = p.x; out[1] = p.y; out[2] = p.z; out[3] = p.w;
+}
+
+// ---- stand-alone building blocks: the same *_problem templates the CUDA kernels of bvg_blocks.cu instantiate,
+//      one problem at a time on the host (single-thread group), same argument lists as the bvg_* entry points
+static RngParams block_rp(uint64_t seed) {
+  RngParams rp;
+  memset(&rp, 0, sizeof(rp));
+  rp.seed = seed;
+  return rp;
+}
+static void block_inject(RngParams& rp, int block, const double* p, int count) {
+  rp.inj[block] = p;
+  rp.inj_stride[block] = count;
+  rp.inj_chain_stride[block] = count;
+}
+static std::vector<unsigned char> block_mask(int n, const int32_t* include, int n_include) {
+  std::vector<unsigned char> m(n, include == nullptr ? 1 : 0);
+  if (include != nullptr) for (int i = 0; i < n_include; ++i) m[include[i]] = 1;
+  return m;
+}
+
+extern "C" int emu_post_normal(int64_t B, int k, int T, int M, const double* y, const double* x, const double* sigma_i,
+                               const double* a_prior, const double* v_i_prior, const double* eps, uint64_t seed,
+                               int method, double* out) {
+  const int n = k * M;
+  std::vector<double> XX((size_t)M * M, 0.0), YX((size_t)k * M, 0.0), sm(post_normal_smem_len(n));
+  for (int t = 0; t < T; ++t)
+    for (int j = 0; j < M; ++j) {
+      for (int j2 = 0; j2 < M; ++j2) XX[j + (size_t)M * j2] += x[j + (size_t)M * t] * x[j2 + (size_t)M * t];
+      for (int i = 0; i < k; ++i) YX[i + (size_t)k * j] += y[i + (size_t)k * t] * x[j + (size_t)M * t];
+    }
+  RngParams rp = block_rp(seed);
+  if (eps) block_inject(rp, VB_COEF_N, eps, n);
+  SerialGroup g;
+  int fl = 0;
+  for (int64_t b = 0; b < B; ++b) {
+    ChainRng rng(&rp, b);
+    post_normal_problem(g, rng, k, M, XX.data(), YX.data(), sigma_i + (size_t)b * k * k, a_prior, v_i_prior, sm.data(),
+                        out + (size_t)b * n, method, fl);
+  }
+  return fl;
+}
+
+extern "C" int emu_post_normal_sur(int64_t B, int k, int T, int n, const double* y, const double* z,
+                                   const double* sigma_i, int sigma_tv, const double* a_prior, const double* v_i_prior,
+                                   const double* eps, uint64_t seed, int method, double* out) {
+  std::vector<double> sm(post_normal_smem_len(n));
+  RngParams rp = block_rp(seed);
+  if (eps) block_inject(rp, VB_COEF_N, eps, n);
+  SerialGroup g;
+  int fl = 0;
+  const size_t ss = sigma_tv ? (size_t)k * T * k : (size_t)k * k;
+  for (int64_t b = 0; b < B; ++b) {
+    ChainRng rng(&rp, b);
+    post_normal_sur_problem(g, rng, k, T, n, y, z, sigma_i + (size_t)b * ss, sigma_tv, a_prior, v_i_prior, sm.data(),
+                            out + (size_t)b * n, method, fl);
+  }
+  return fl;
+}
+
+extern "C" int emu_bvs(int64_t B, int k, int T, int n, const double* y, const double* z, const double* a, int a_tv,
+                       const double* lambda, const double* sigma_i, int sigma_tv, const double* prob_prior,
+                       const int32_t* include, int n_include, const double* u1, const double* u2, uint64_t seed,
+                       double* lambda_out) {
+  std::vector<unsigned char> mask = block_mask(n, include, n_include);
+  std::vector<double> sm(2 * (size_t)k * T);
+  RngParams rp = block_rp(seed);
+  if (u1) block_inject(rp, VB_BVS_U1, u1, n);
+  if (u2) block_inject(rp, VB_BVS_U2, u2, n);
+  SerialGroup g;
+  const size_t as = a_tv ? (size_t)n * T : (size_t)n, ss = sigma_tv ? (size_t)k * T * k : (size_t)k * k;
+  for (int64_t b = 0; b < B; ++b) {
+    ChainRng rng(&rp, b);
+    bvs_problem(g, rng, k, T, n, y, z, a + (size_t)b * as, a_tv, lambda + (size_t)b * n, sigma_i + (size_t)b * ss,
+                sigma_tv, prob_prior, mask.data(), sm.data(), lambda_out + (size_t)b * n);
+  }
+  return 0;
+}
+
+extern "C" int emu_stochvol(int64_t B, int T, int k, const double* y, const double* h, const double* sigma,
+                            const double* h_init, const double* constant, int mixture, const double* u,
+                            const double* eps, uint64_t seed, double* h_out, int32_t* s_out) {
+  const int J = (mixture == BVG_MIX_OCSN2007) ? 10 : 7;
+  std::vector<double> tab(30, 0.0);
+  for (int j = 0; j < J; ++j) {
+    tab[j] = (J == 7) ? KSC_P[j] : OCSN_P[j];
+    tab[10 + j] = (J == 7) ? KSC_MU[j] - 1.2704 : OCSN_MU[j];
+    tab[20 + j] = (J == 7) ? KSC_S2[j] : OCSN_S2[j];
+  }
+  const size_t kt = (size_t)k * T;
+  RngParams rp = block_rp(seed);
+  if (u) block_inject(rp, VB_SV_U, u, (int)kt);
+  if (eps) block_inject(rp, VB_SV_N, eps, (int)kt);
+  BvarModel m;
+  memset(&m, 0, sizeof(m));
+  m.k = k; m.T = T; m.n_mix = J; m.sigma_type = SIG_SV;
+  m.mix_p = tab.data(); m.mix_mu = tab.data() + 10; m.mix_s2 = tab.data() + 20;
+  std::vector<double> U(kt), hh(kt), pr(kt), rh(kt);
+  std::vector<int> sidx(kt);
+  SerialGroup g;
+  for (int64_t b = 0; b < B; ++b) {
+    m.sv_const = constant + (size_t)b * k;
+    for (size_t e = 0; e < kt; ++e) {
+      const int i = (int)(e % k), t = (int)(e / k);
+      U[e] = y[(size_t)b * kt + t + (size_t)T * i];
+      hh[t + (size_t)T * i] = h[(size_t)b * kt + t + (size_t)T * i];
+    }
+    ChainRng rng(&rp, b);
+    sv_step(g, rng, 0, m, U.data(), hh.data(), sigma + (size_t)b * k, h_init + (size_t)b * k, pr.data(), rh.data(),
+            sidx.data());
+    for (size_t e = 0; e < kt; ++e) { h_out[(size_t)b * kt + e] = hh[e]; if (s_out) s_out[(size_t)b * kt + e] = sidx[e]; }
+  }
+  return 0;
+}
+
+extern "C" int emu_kalman_dk(int64_t B, int k, int T, int n, const double* y, const double* z, const double* sigma_u,
+                             const double* sigma_v, const double* Bmat, int tv, const double* a_init,
+                             const double* P_init, const double* eps, uint64_t seed, double* out) {
+  const int neps = n + T * (k + n);
+  std::vector<double> sm(kalman_smem_len(k, n)), scratch((size_t)kalman_scratch_len(k, T, n));
+  RngParams rp = block_rp(seed);
+  if (eps) block_inject(rp, VB_STATE_N, eps, neps);
+  SerialGroup g;
+  int fl = 0;
+  const size_t us = (tv & 1) ? (size_t)k * T * k : (size_t)k * k;
+  const size_t vs = (tv & 2) ? (size_t)n * T * n : (size_t)n * n;
+  const size_t bs = (tv & 4) ? (size_t)n * T * n : (size_t)n * n;
+  for (int64_t b = 0; b < B; ++b) {
+    ChainRng rng(&rp, b);
+    kalman_dk_problem(g, rng, k, T, n, y, z, sigma_u + (size_t)b * us, sigma_v + (size_t)b * vs, Bmat + (size_t)b * bs,
+                      tv, a_init + (size_t)b * n, P_init + (size_t)b * n * n, sm.data(), scratch.data(),
+                      out + (size_t)b * n * (T + 1), fl);
+  }
+  return fl;
+}
+
+extern "C" int emu_ssvs(int64_t B, int n, const double* a, const double* tau0, const double* tau1,
+                        const double* prob_prior, const int32_t* include, int n_include, const double* u,
+                        uint64_t seed, double* lambda_out, double* vdiag_out) {
+  std::vector<unsigned char> mask = block_mask(n, include, n_include);
+  RngParams rp = block_rp(seed);
+  if (u) block_inject(rp, VB_SSVS_U, u, n);
+  for (int64_t b = 0; b < B; ++b) {
+    ChainRng rng(&rp, b);
+    for (int r = 0; r < n; ++r)
+      ssvs_element(rng, r, a[(size_t)b * n + r], tau0[r], tau1[r], prob_prior[r], mask[r] != 0,
+                   lambda_out + (size_t)b * n + r, vdiag_out + (size_t)b * n + r);
+  }
+  return 0;
 }
