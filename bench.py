@@ -68,6 +68,15 @@ def flops_per_sweep(obj, resid_moment):
     return base + 2 * k * M * T + k * (k + 1) * T
 
 
+def kron_flops_per_sweep(obj):
+    """Linear-algebra flops of the flat-prior Kronecker sweep as executed: E L_X^-1 (k M (M+1)),
+    B^-1 applied to it (k (k+1) M), the n additions of A_ols, E E' (k (k+1) M), two k x k triple products and the
+    k x k inverse-Wishart block (7 k^3).  Variate generation is NOT included."""
+    T, k = obj["data"]["Y"].shape
+    M = obj["data"]["Z"].shape[1]
+    return k * M * (M + 1) + 2 * k * (k + 1) * M + k * M + 7 * k ** 3
+
+
 def survey_flops_per_sweep(obj):
     """SURVEY.md section 8d figure (direct residuals): 8424 flop for c1."""
     T, k = obj["data"]["Y"].shape
@@ -250,6 +259,7 @@ def main():
     elapsed_ms = e0.elapsed_time(e1)
     # duration of the sweep kernels of the last step, from the library's CUDA events on the launching stream
     last_sweep_ms = sampler.last_kernel_ms
+    kernel_name = sampler.kernel_name
     launches_per_step = int(sampler.launch_count) + 1          # + the moments kernel
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -303,7 +313,7 @@ def main():
     # ---- roofline of the dominant kernel (the sweep kernel): executed algorithmic FP64 flops / launch time
     moment = not (obj["model"].get("tvp") or obj["model"].get("sv")) and \
         obj["data"]["Y"].shape[0] > obj["data"]["Z"].shape[1]
-    fl_sweep = flops_per_sweep(obj, moment)
+    fl_sweep = kron_flops_per_sweep(obj) if kernel_name.startswith("kron") else flops_per_sweep(obj, moment)
     peak = C.c_double(0.0)
     check(L.bvg_fp64_peak(C.byref(peak), None))
     sweep_kernel_s = last_sweep_ms * 1e-3
@@ -316,7 +326,7 @@ def main():
     out_bytes = 8.0 * chains * it * sum(rows.values())
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value > 0 else None, "traffic": None,
-                "kernel": "tvp sweep kernel" if obj["model"].get("tvp") else "bvar sweep kernel",
+                "kernel": kernel_name,
                 "peak_source": "FP64 FMA probe kernel run live by bench.py (bvg_fp64_peak); MEASURED_PEAKS.json "
                                "has no FP64 entry",
                 "flops_per_sweep_executed": fl_sweep, "flops_per_sweep_survey": survey_flops_per_sweep(obj),

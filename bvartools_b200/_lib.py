@@ -52,6 +52,8 @@ def lib():
     L.bvg_sampler_last_kernel_ms.restype = C.c_double
     L.bvg_sampler_launch_count.argtypes = [vp]
     L.bvg_sampler_launch_count.restype = C.c_int64
+    L.bvg_sampler_kernel_name.argtypes = [vp]
+    L.bvg_sampler_kernel_name.restype = C.c_char_p
     L.bvg_sampler_destroy.argtypes = [vp]
     L.bvg_sampler_destroy.restype = None
     L.bvg_moments.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp]
@@ -82,6 +84,6 @@ def require_device():
 EXPORTED = ["bvg_version", "bvg_last_error", "bvg_device_count", "bvg_host_alloc", "bvg_host_free", "bvg_out_rows",
             "bvg_bvaralg", "bvg_bvartvpalg", "bvg_sampler_create", "bvg_sampler_reset", "bvg_sampler_run",
             "bvg_sampler_run_to_host", "bvg_sampler_fetch", "bvg_sampler_device_out", "bvg_sampler_sync",
-            "bvg_sampler_last_kernel_ms", "bvg_sampler_launch_count", "bvg_sampler_destroy",
+            "bvg_sampler_last_kernel_ms", "bvg_sampler_launch_count", "bvg_sampler_kernel_name", "bvg_sampler_destroy",
             "bvg_set_interrupt_poll", "bvg_moments", "bvg_fp64_peak", "bvg_post_normal", "bvg_post_normal_sur",
             "bvg_ssvs", "bvg_bvs", "bvg_stochvol", "bvg_kalman_dk"]

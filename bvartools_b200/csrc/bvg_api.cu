@@ -61,6 +61,7 @@ struct bvg_sampler {
   std::vector<cudaEvent_t> chunk_ev;
   bool timed = false;
   long long launches = 0;
+  char kernel_name[64] = {0};
 };
 
 static void rows_of(const Prepared& P, long long* coef, long long* sigma, long long* lambda, long long* sh,
@@ -236,6 +237,14 @@ int bvg_sampler_create(const bvg_spec* spec, bvg_sampler** out) {
     bvg_sampler_destroy(s);
     return fail(-52, "model does not fit the shared-memory kernels (n too large for this path) or invalid threads_per_chain");
   }
+  {
+    const int need = P.tvp ? 0 : bvar_features_needed(s->bm.sigma_type, s->bm.varsel, s->bm.resid_mode, s->bm.vi_off != nullptr);
+    const int tpc = s->plan.threads_per_chain;
+    if (P.tvp) snprintf(s->kernel_name, sizeof(s->kernel_name), "tvp_g%d", tpc <= 32 ? tpc : 0);
+    else if (s->plan.kron) snprintf(s->kernel_name, sizeof(s->kernel_name), "kron_k%d_g%d", P.k, tpc);
+    else snprintf(s->kernel_name, sizeof(s->kernel_name), "bvar_g%d_f%d", tpc <= 32 ? tpc : 0,
+                  need == 0 ? 0 : ((need & ~(int)F_VARSEL) == 0 ? 2 : 31));
+  }
   CKS(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
   CKS(cudaEventCreate(&s->ev0));
   CKS(cudaEventCreate(&s->ev1));
@@ -385,6 +394,7 @@ double bvg_sampler_last_kernel_ms(bvg_sampler* s) {
 }
 
 int64_t bvg_sampler_launch_count(bvg_sampler* s) { return s ? s->launches : 0; }
+const char* bvg_sampler_kernel_name(bvg_sampler* s) { return s ? s->kernel_name : ""; }
 
 static int one_shot(const bvg_spec* spec, const bvg_out* out, int want_tvp) {
   if (!spec || !out) return fail(-1, "spec / out is NULL");

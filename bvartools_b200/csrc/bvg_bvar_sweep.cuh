@@ -58,6 +58,9 @@ struct BvarModel {
   const double* sv_const;          // k   offset constant c                          (bvaralg.cpp:229)
   const double* mix_p; const double* mix_mu; const double* mix_s2;   // n_mix each
   const double* omega_off;         // k x k off-diagonal part of the initial Sigma^-1 (gamma prior), zero diagonal
+  // flat-prior Kronecker specialisation (bvg_kron_sweep.cuh); nullptr when the model does not qualify
+  const double* kron_Linv;         // tri(M) packed lower: inverse of the lower Cholesky factor of X X'
+  const double* kron_SS;           // k x k  S0 + SSE_ols
 };
 
 // The small read-only tables every sweep touches.  The CUDA kernels stage them once per CTA into shared memory

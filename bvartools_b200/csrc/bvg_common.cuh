@@ -13,7 +13,7 @@
 #define BVG_D __device__ __forceinline__
 // out-of-line on the device: the variate generators are called from many sites and would otherwise be inlined
 // (Philox unrolled + log/cospi expansions) at each of them, blowing the kernel past the instruction cache
-#define BVG_HD_NOINLINE __host__ __device__ __noinline__
+#define BVG_HD_NOINLINE static __host__ __device__ __noinline__
 #define BVG_UNROLL _Pragma("unroll")
 #else
 #define BVG_UNROLL
@@ -45,6 +45,7 @@ enum VarBlock : int {
 
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based: no state, any site can be drawn by any thread ------
 struct Philox4 { uint32_t x, y, z, w; };
+struct Normal2 { double a, b; };
 
 BVG_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
@@ -81,6 +82,21 @@ BVG_HD double bvg_cospi(double x) {
   return cos(3.14159265358979323846 * x);
 #endif
 }
+BVG_HD double bvg_sinpi(double x) {
+#if defined(__CUDA_ARCH__)
+  return sinpi(x);
+#else
+  return sin(3.14159265358979323846 * x);
+#endif
+}
+BVG_HD void bvg_sincospi(double x, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+  sincospi(x, s, c);
+#else
+  *s = sin(3.14159265358979323846 * x);
+  *c = cos(3.14159265358979323846 * x);
+#endif
+}
 
 // ---- random source of one chain ----------------------------------------------------------------------------
 // Injected variates (tier-1 parity tests): device arrays [chain][sweep][count] or nullptr per block.  Lives in
@@ -96,6 +112,64 @@ struct RngParams {
 
 // Site = (block, sweep, index[, attempt]).  Key = seed, counter = (index | attempt<<24, sweep, chain_lo,
 // chain_hi ^ block<<24): results are independent of thread mapping, launch chunking and GPU count.
+//
+// The generators proper are out-of-line FREE functions over by-value scalars (one copy of the Philox / log / sincospi
+// code per kernel, and no `this` pointer that would force the caller's ChainRng onto the stack); the ChainRng members
+// are inlined wrappers that test for injected variates first.
+BVG_HD Philox4 philox_site(uint64_t seed, uint64_t chain, int block, int sweep, int idx, int attempt) {
+  return philox4x32_10((uint32_t)idx | ((uint32_t)attempt << 24), (uint32_t)sweep, (uint32_t)chain,
+                       (uint32_t)(chain >> 32) ^ ((uint32_t)block << 24), (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+BVG_HD_NOINLINE double philox_uniform(uint64_t seed, uint64_t chain, int block, int sweep, int idx, int attempt) {
+  const Philox4 p = philox_site(seed, chain, block, sweep, idx, attempt);
+  return u53(p.x, p.y);
+}
+// Normals come in Box-Muller pairs: sites 2p and 2p+1 of a block are the cosine and sine branch of ONE Philox call
+// (counter index p).
+BVG_HD_NOINLINE Normal2 philox_normal_pair(uint64_t seed, uint64_t chain, int block, int sweep, int pair, int attempt) {
+  const Philox4 p = philox_site(seed, chain, block, sweep, pair, attempt);
+  const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
+  const double r = sqrt(-2.0 * log(u1));
+  Normal2 o;
+  o.a = r * bvg_cospi(2.0 * u2);
+  o.b = r * bvg_sinpi(2.0 * u2);
+  return o;
+}
+BVG_HD_NOINLINE double philox_normal(uint64_t seed, uint64_t chain, int block, int sweep, int idx, int attempt) {
+  const Philox4 p = philox_site(seed, chain, block, sweep, idx >> 1, attempt);
+  const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
+  const double r = sqrt(-2.0 * log(u1));
+  return (idx & 1) ? r * bvg_sinpi(2.0 * u2) : r * bvg_cospi(2.0 * u2);
+}
+// Gamma(shape, 1), Marsaglia-Tsang 2000 (shape < 1 boosted); attempts are separate sites.  `x0` is the N(0,1) of
+// attempt 0, i.e. philox_normal(.., idx, 0): callers may draw it earlier together with other normals so that all
+// lanes of a tile run one generator call site instead of diverging.
+BVG_HD_NOINLINE double philox_gamma_from_x0(uint64_t seed, uint64_t chain, int block, int sweep, int idx, double shape,
+                                            double x0) {
+  double boost = 1.0, a = shape;
+  if (a < 1.0) {
+    const Philox4 p = philox_site(seed, chain, block, sweep, idx, 255);
+    boost = pow(u53(p.x, p.y), 1.0 / a);
+    a += 1.0;
+  }
+  const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  double x = x0;
+  for (int attempt = 0; attempt < 100; ++attempt) {
+    if (attempt > 0) {
+      const Philox4 p = philox_site(seed, chain, block, sweep, idx, attempt);
+      const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
+      x = sqrt(-2.0 * log(u1)) * bvg_cospi(2.0 * u2);
+    }
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    const Philox4 q = philox_site(seed, chain, block, sweep, idx, attempt + 100);
+    const double u = u53(q.x, q.y);
+    if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v;
+  }
+  return boost * d;   // unreachable in practice (acceptance > 95 %)
+}
+
 struct ChainRng {
   uint64_t seed;
   uint64_t chain;                 // GLOBAL chain id
@@ -106,61 +180,43 @@ struct ChainRng {
       : seed(p->seed), chain(p->chain_offset + (uint64_t)local), rp(p), chain_local(local) {}
 
   BVG_HD Philox4 raw(int block, int sweep, int idx, int attempt) const {
-    return philox4x32_10((uint32_t)idx | ((uint32_t)attempt << 24), (uint32_t)sweep, (uint32_t)chain,
-                         (uint32_t)(chain >> 32) ^ ((uint32_t)block << 24), (uint32_t)seed, (uint32_t)(seed >> 32));
+    return philox_site(seed, chain, block, sweep, idx, attempt);
   }
   BVG_HD bool injected(int block) const { return rp->inj[block] != nullptr; }
   BVG_HD double inj_at(int block, int sweep, int idx) const {
     return rp->inj[block][(size_t)chain_local * (size_t)rp->inj_chain_stride[block] +
                           (size_t)sweep * (size_t)rp->inj_stride[block] + (size_t)idx];
   }
-  BVG_HD_NOINLINE double uniform(int block, int sweep, int idx, int attempt = 0) const {
+  BVG_HD double uniform(int block, int sweep, int idx, int attempt = 0) const {
     if (rp->inj[block]) return inj_at(block, sweep, idx);
-    const Philox4 p = raw(block, sweep, idx, attempt);
-    return u53(p.x, p.y);
+    return philox_uniform(seed, chain, block, sweep, idx, attempt);
   }
-  // one site -> one normal (Box-Muller cosine branch; the sine is not used so that sites stay independent)
-  BVG_HD_NOINLINE double normal(int block, int sweep, int idx, int attempt = 0) const {
+  // one member of a Box-Muller pair
+  BVG_HD double normal(int block, int sweep, int idx, int attempt = 0) const {
     if (rp->inj[block]) return inj_at(block, sweep, idx);
-    const Philox4 p = raw(block, sweep, idx, attempt);
-    const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
-    return sqrt(-2.0 * log(u1)) * bvg_cospi(2.0 * u2);
+    return philox_normal(seed, chain, block, sweep, idx, attempt);
   }
-  // Gamma(shape, 1), Marsaglia-Tsang 2000 (shape < 1 boosted); attempts are separate sites.  `x0` is the N(0,1)
-  // of attempt 0, i.e. normal(block, sweep, idx, 0): callers may draw it earlier together with other normals so
-  // that all lanes of a tile run one generator call site instead of diverging.
-  BVG_HD_NOINLINE double gamma_from_x0(int block, int sweep, int idx, double shape, double x0) const {
+  // normals of sites 2*pair and 2*pair+1 (`count` = sites in the block: an odd block's last pair has one member)
+  BVG_HD Normal2 normal_pair(int block, int sweep, int pair, int count) const {
+    if (rp->inj[block]) {
+      Normal2 o;
+      o.a = inj_at(block, sweep, 2 * pair);
+      o.b = (2 * pair + 1 < count) ? inj_at(block, sweep, 2 * pair + 1) : 0.0;
+      return o;
+    }
+    return philox_normal_pair(seed, chain, block, sweep, pair, 0);
+  }
+  BVG_HD double gamma_from_x0(int block, int sweep, int idx, double shape, double x0) const {
     if (rp->inj[block]) return inj_at(block, sweep, idx);
-    double boost = 1.0, a = shape;
-    if (a < 1.0) {
-      const Philox4 p = raw(block, sweep, idx, 255);
-      boost = pow(u53(p.x, p.y), 1.0 / a);
-      a += 1.0;
-    }
-    const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
-    double x = x0;
-    for (int attempt = 0; attempt < 100; ++attempt) {
-      if (attempt > 0) {
-        const Philox4 p = raw(block, sweep, idx, attempt);
-        const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
-        x = sqrt(-2.0 * log(u1)) * bvg_cospi(2.0 * u2);
-      }
-      double v = 1.0 + c * x;
-      if (v <= 0.0) continue;
-      v = v * v * v;
-      const Philox4 q = raw(block, sweep, idx, attempt + 100);
-      const double u = u53(q.x, q.y);
-      if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v;
-    }
-    return boost * d;   // unreachable in practice (acceptance > 95 %)
+    return philox_gamma_from_x0(seed, chain, block, sweep, idx, shape, x0);
   }
   BVG_HD double gamma(int block, int sweep, int idx, double shape) const {
     if (rp->inj[block]) return inj_at(block, sweep, idx);
-    return gamma_from_x0(block, sweep, idx, shape, normal(block, sweep, idx, 0));
+    return philox_gamma_from_x0(seed, chain, block, sweep, idx, shape, philox_normal(seed, chain, block, sweep, idx, 0));
   }
   BVG_HD double chi2_from_x0(int block, int sweep, int idx, double df, double x0) const {
     if (rp->inj[block]) return inj_at(block, sweep, idx);
-    return 2.0 * gamma_from_x0(block, sweep, idx, 0.5 * df, x0);
+    return 2.0 * philox_gamma_from_x0(seed, chain, block, sweep, idx, 0.5 * df, x0);
   }
   BVG_HD double chi2(int block, int sweep, int idx, double df) const {
     if (rp->inj[block]) return inj_at(block, sweep, idx);

@@ -36,6 +36,8 @@ static cudaError_t finish_plan(LaunchPlan* plan, int per_chain_doubles, long lon
 }
 
 cudaError_t plan_bvar(const BvarModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan) {
+  plan->kron = 0;
+  if (m.kron_Linv != nullptr) return plan_bvar_kron(m, n_chains, requested_tpc, plan);
   const int per = bvar_smem_len(m.k, m.T, m.M, m.n, m.sigma_type, m.resid_mode);
   int tpc = requested_tpc;
   if (tpc <= 0) {
@@ -46,6 +48,7 @@ cudaError_t plan_bvar(const BvarModel& m, long long n_chains, int requested_tpc,
 }
 
 cudaError_t plan_tvp(const TvpModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan) {
+  plan->kron = 0;
   const int per = tvp_smem_len(m.b.k, m.b.T, m.b.n, m.b.sigma_type);
   int tpc = requested_tpc;
   if (tpc <= 0) {
@@ -60,6 +63,7 @@ typedef cudaError_t (*bvar_launcher)(BVG_BVAR_ARGS);
 cudaError_t launch_bvar(const LaunchPlan& plan, const BvarModel& m, const RngParams& rp, double* state,
                         int state_len, const BvarOut& out, long long n_chains, int s0, int s1, int burnin,
                         cudaStream_t stream) {
+  if (plan.kron) return launch_bvar_kron(plan, m, rp, state, state_len, out, n_chains, s0, s1, burnin, stream);
   // smallest compiled feature variant that covers the model: 0 (lean), 2 (+ SSVS/BVS), 31 (everything)
   const int need = bvar_features_needed(m.sigma_type, m.varsel, m.resid_mode, m.vi_off != nullptr);
   const int fi = (need == 0) ? 0 : ((need & ~(int)F_VARSEL) == 0 ? 1 : 2);

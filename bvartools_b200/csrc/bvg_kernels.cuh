@@ -13,6 +13,8 @@ struct LaunchPlan {
   size_t smem_bytes;       // dynamic shared memory per block
   int smem_per_chain;      // doubles
   int grid;
+  int kron;                // 1 = flat-prior Kronecker sweep kernel (bvg_kern_kron.cu)
+  int kron_nb;             // its sweeps per round
 };
 
 #define BVG_BLOCK_SCRATCH 40   // doubles reserved in front of the chain's shared memory for BlockGroup
@@ -21,6 +23,10 @@ cudaError_t plan_bvar(const BvarModel& m, long long n_chains, int requested_tpc,
 cudaError_t launch_bvar(const LaunchPlan& plan, const BvarModel& m, const RngParams& rp, double* state,
                         int state_len, const BvarOut& out, long long n_chains, int sweep_begin, int sweep_end,
                         int burnin, cudaStream_t stream);
+
+#define BVG_BVAR_ARGS_NAMED const LaunchPlan& plan, const BvarModel& m, const RngParams& rp, double* state, int state_len, const BvarOut& out, long long n_chains, int s0, int s1, int burnin, cudaStream_t stream
+cudaError_t plan_bvar_kron(const BvarModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan);
+cudaError_t launch_bvar_kron(BVG_BVAR_ARGS_NAMED);
 
 cudaError_t plan_tvp(const TvpModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan);
 cudaError_t launch_tvp(const LaunchPlan& plan, const TvpModel& m, const RngParams& rp, double* state,

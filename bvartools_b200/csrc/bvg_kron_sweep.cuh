@@ -1,0 +1,243 @@
+// bvg_kron_sweep.cuh -- flat-prior specialisation of the constant-parameter BVAR sweep (configs c1 / c2: README.md:147-149
+// and vignettes/model-comparison.Rmd:58-60 both use v_i = 0).
+//
+// With V^-1 = 0 the posterior precision of bvaralg.cpp:305 is exactly Kronecker, P = (X X') (x) Sigma^-1, and so is its
+// (unique) upper Cholesky factor: chol(P) = R_X (x) R_S with X X' = R_X' R_X and Sigma^-1 = R_S' R_S.  The reference's
+// draw  a = P^-1 b + chol(P)^-1 eps  (bvaralg.cpp:306-307) therefore is, exactly,
+//     A = A_ols + R_S^-1 E L_X^-1 ,        E = reshape(eps, k, M),   L_X = R_X' (lower factor of X X', constant)
+// and the residual cross product needed by the Wishart block (bvaralg.cpp:364,511) collapses to
+//     u u' = SSE_ols + (A - A_ols) X X' (A - A_ols)' = SSE_ols + R_S^-1 (E E') R_S^-T .
+// The inverse-Wishart block (bvaralg.cpp:511, arma::wishrnd) draws Sigma^-1 = (A_B D)'(A_B D) with A_B the Bartlett
+// factor (upper) and D = chol(S^-1) (upper), S = S0 + u u'.  Writing S = U U' with U UPPER (the Cholesky factorisation
+// taken from the last row up), S^-1 = U^-T U^-1 and by uniqueness D = U^-1, so the new R_S = A_B U^-1 and
+//     R_S^-1 = U A_B^-1 ,        Sigma = R_S^-1 R_S^-T                                      (bvaralg.cpp:528)
+// -- no inverse of S and no second factorisation.  The chain state is W = R_S^-1 (k x k upper).  Same variates and the
+// same mapping eps -> a as the reference (tier-1 parity to rounding).  Everything random in the sweep (eps, A_B) is
+// independent of the chain state, so the kernels generate variates for a batch of sweeps in a throughput-bound phase
+// and run the short state recursion  W <- U(S0 + SSE + W E E' W') A_B^-1  separately (bvg_kern_kron.cu).
+// The general kernel (bvg_bvar_sweep.cuh) covers every other prior.
+#pragma once
+#include "bvg_bvar_sweep.cuh"
+
+namespace bvg {
+
+// constants of the model shared by all chains (staged in shared memory by the kernels)
+struct KronConsts {
+  const double* Linv;   // tri(M) packed lower row-major: L_X^-1
+  const double* Aols;   // k x M col-major
+  const double* SS;     // k x k col-major: S0 + SSE_ols
+};
+BVG_HD int kron_consts_len(int k, int M) { return tri(M) + k * M + k * k; }
+// record of one sweep of one chain: eps (n) | Bartlett normals (k(k-1)/2) | sqrt(chi2) (k) | G = E E' (k(k+1)/2) |
+// A_B^-1 (k(k+1)/2)
+BVG_HD int kron_variates_len(int k, int M) { return k * M + (k * (k - 1)) / 2 + k + k * (k + 1); }
+BVG_HD int kron_smem_len(int k, int M) { return kron_variates_len(k, M) + 1; }
+BVG_HD int kron_pairs(int k, int M) { return ((k * M + 1) >> 1) + (((k * (k - 1)) / 2 + 1) >> 1); }
+
+// Box-Muller pair `p` of the sweep's state-independent normals: coefficient normals first, then the Bartlett ones.
+// v = variates of (chain, sweep): [eps (n) | wn (NW) | chi (K)]
+BVG_HD void kron_gen_pair(const ChainRng& rng, int sweep, int p, int K, int M, double* v) {
+  const int n = K * M, NW = (K * (K - 1)) / 2, p_coef = (n + 1) >> 1;
+  int block = VB_COEF_N, pr = p, cnt = n;
+  double* dst = v;
+  if (p >= p_coef) { block = VB_WISH_N; pr = p - p_coef; cnt = NW; dst = v + n; }
+  const Normal2 nn = rng.normal_pair(block, sweep, pr, cnt);
+  dst[2 * pr] = nn.a;
+  if (2 * pr + 1 < cnt) dst[2 * pr + 1] = nn.b;
+}
+// sqrt(chi2(df - i)) of the Bartlett diagonal (Marsaglia-Tsang; attempt 0 uses normal(VB_WISH_C, sweep, i))
+BVG_HD double kron_gen_chi(const ChainRng& rng, int sweep, int i, double df_post) {
+  if (rng.injected(VB_WISH_C)) return sqrt(rng.inj_at(VB_WISH_C, sweep, i));
+  return sqrt(rng.chi2_from_x0(VB_WISH_C, sweep, i, df_post - (double)i, rng.normal(VB_WISH_C, sweep, i)));
+}
+
+// State-independent preparation of one sweep (flat, parallel work): G = E E' (lower packed, G_ij at tri(i) + j) and
+// Ai = A_B^-1 (upper packed by column, Ai_ij at tri(j) + i) from the sweep's variates.
+// eps: E col-major (i + K j), wn: strict-upper Bartlett normals column by column, chi: sqrt(chi2).
+template <int K>
+BVG_HD void kron_prep(const double* eps, const double* wn, const double* chi, int M, double* Gp, double* Aip) {
+  double Gm[K][K];
+BVG_UNROLL
+  for (int i = 0; i < K; ++i)
+BVG_UNROLL
+    for (int j = 0; j <= i; ++j) Gm[i][j] = 0.0;
+  for (int j2 = 0; j2 < M; ++j2) {
+    double e[K];
+BVG_UNROLL
+    for (int i = 0; i < K; ++i) e[i] = eps[i + K * j2];
+BVG_UNROLL
+    for (int i = 0; i < K; ++i)
+BVG_UNROLL
+      for (int j = 0; j <= i; ++j) Gm[i][j] = fma(e[i], e[j], Gm[i][j]);
+  }
+  double Ai[K][K];
+BVG_UNROLL
+  for (int c = 0; c < K; ++c) {
+    Ai[c][c] = 1.0 / chi[c];
+BVG_UNROLL
+    for (int r = c - 1; r >= 0; --r) {
+      double v = 0.0;
+BVG_UNROLL
+      for (int mm = r + 1; mm <= c; ++mm) v = fma(wn[tri(mm - 1) + r], Ai[mm][c], v);
+      Ai[r][c] = -v * Ai[r][r];
+    }
+  }
+BVG_UNROLL
+  for (int i = 0; i < K; ++i)
+BVG_UNROLL
+    for (int j = 0; j <= i; ++j) { Gp[tri(i) + j] = Gm[i][j]; Aip[tri(i) + j] = Ai[j][i]; }
+}
+
+// One step of the state recursion (the only state-dependent part of the sweep, a few dozen dependent FP64
+// operations): W (upper, registers) <- U(SS + W G W') Ai, with S = U U', U upper.  SSu: upper triangle of S0 + SSE.
+// fail is set on a non-positive pivot.
+template <int K>
+BVG_HD void kron_step_core(double (&W)[K][K], const double* Gp, const double* Aip, const double (&SSu)[K][K],
+                           int& fail) {
+  double Gm[K][K], Ai[K][K];
+BVG_UNROLL
+  for (int i = 0; i < K; ++i)
+BVG_UNROLL
+    for (int j = 0; j <= i; ++j) { Gm[i][j] = Gp[tri(i) + j]; Ai[j][i] = Aip[tri(i) + j]; }
+  // S = SS + W G W'  (upper triangle: S[i][j], i <= j)
+  double H[K][K], S[K][K];
+BVG_UNROLL
+  for (int i = 0; i < K; ++i)
+BVG_UNROLL
+    for (int j = 0; j < K; ++j) {
+      double v = 0.0;
+BVG_UNROLL
+      for (int c = i; c < K; ++c) v = fma(W[i][c], (c >= j) ? Gm[c][j] : Gm[j][c], v);
+      H[i][j] = v;
+    }
+BVG_UNROLL
+  for (int i = 0; i < K; ++i)
+BVG_UNROLL
+    for (int j = i; j < K; ++j) {
+      double v = SSu[i][j];
+BVG_UNROLL
+      for (int c = j; c < K; ++c) v = fma(H[i][c], W[j][c], v);
+      S[i][j] = v;
+    }
+  // S = U U', U upper: from the last column to the first
+  double U[K][K];
+BVG_UNROLL
+  for (int j = K - 1; j >= 0; --j) {
+    double d = S[j][j];
+BVG_UNROLL
+    for (int c = j + 1; c < K; ++c) d = fma(-U[j][c], U[j][c], d);
+    if (!(d > 0.0)) fail = 1;
+    const double rs = bvg_rsqrt(d);
+    U[j][j] = d * rs;
+BVG_UNROLL
+    for (int i = j - 1; i >= 0; --i) {
+      double v = S[i][j];
+BVG_UNROLL
+      for (int c = j + 1; c < K; ++c) v = fma(-U[i][c], U[j][c], v);
+      U[i][j] = v * rs;
+    }
+  }
+  // W = U A_B^-1
+BVG_UNROLL
+  for (int i = 0; i < K; ++i)
+BVG_UNROLL
+    for (int j = i; j < K; ++j) {
+      double v = 0.0;
+BVG_UNROLL
+      for (int mm = i; mm <= j; ++mm) v = fma(U[i][mm], Ai[mm][j], v);
+      W[i][j] = v;
+    }
+}
+
+// column j of the coefficient draw: a[:, j] = A_ols[:, j] + W (E L_X^-1)[:, j]     (bvaralg.cpp:306-307)
+// Wp: the K(K+1)/2 upper entries of W packed column by column (W_ij at tri(j) + i)
+template <int K>
+BVG_HD void kron_coef_col(const double* Wp, const double* eps, const KronConsts& cs, int M, int j, double* oc) {
+  double t[K];
+BVG_UNROLL
+  for (int i = 0; i < K; ++i) t[i] = 0.0;
+  for (int j2 = j; j2 < M; ++j2) {
+    const double li = cs.Linv[tri(j2) + j];
+BVG_UNROLL
+    for (int i = 0; i < K; ++i) t[i] = fma(eps[i + K * j2], li, t[i]);
+  }
+BVG_UNROLL
+  for (int i = 0; i < K; ++i) {
+    double d = 0.0;
+BVG_UNROLL
+    for (int i2 = i; i2 < K; ++i2) d = fma(Wp[tri(i2) + i], t[i2], d);
+    oc[i + K * j] = cs.Aols[i + K * j] + d;
+  }
+}
+// entry (i, j) of Sigma = W W'                                                       (bvaralg.cpp:528)
+template <int K>
+BVG_HD double kron_sigma_entry(const double* Wp, int i, int j) {
+  double v = 0.0;
+  for (int mm = (i > j ? i : j); mm < K; ++mm) v = fma(Wp[tri(mm) + i], Wp[tri(mm) + j], v);
+  return v;
+}
+
+// ---- group-generic chain (tile kernel for few sweeps per launch, and the host emulation of the arithmetic) --------
+// Chain state between launches: W (k x k upper, col-major) in the Sigma^-1 slot of the generic state layout.
+template <int K, class Grp>
+BVG_HD void bvar_kron_chain(const Grp& g, const BvarModel& m, const KronConsts& cs, const ChainRng& rng,
+                            double* state, double* sm, const BvarOut& out, long long chain_local, int sweep_begin,
+                            int sweep_end, int burnin) {
+  const int G = g.size(), tid = g.tid();
+  const int M = m.M, n = K * M;
+  constexpr int NW = (K * (K - 1)) / 2, KU = (K * (K + 1)) / 2;
+  double* v = sm;                  // [eps | wn | chi]
+  int fail = 0;
+  double W[K][K];
+BVG_UNROLL
+  for (int i = 0; i < K; ++i)
+BVG_UNROLL
+    for (int j = 0; j < K; ++j) W[i][j] = (i <= j) ? state[i + K * j] : 0.0;
+  const int n_pairs = kron_pairs(K, M);
+
+  for (int sweep = sweep_begin; sweep < sweep_end; ++sweep) {
+    const bool keep = sweep >= burnin;
+    const long long pos = (long long)sweep - burnin;
+    for (int it = tid; it < n_pairs + K; it += G) {
+      if (it < n_pairs) kron_gen_pair(rng, sweep, it, K, M, v);
+      else v[n + NW + (it - n_pairs)] = kron_gen_chi(rng, sweep, it - n_pairs, m.wish_df_post);
+    }
+    g.sync();
+    double Wp[KU];
+BVG_UNROLL
+    for (int j = 0; j < K; ++j)
+BVG_UNROLL
+      for (int i = 0; i <= j; ++i) Wp[tri(j) + i] = W[i][j];
+    if (keep) {
+      double* oc = out.coef + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n;
+      for (int j = tid; j < M; j += G) kron_coef_col<K>(Wp, v, cs, M, j, oc);
+    }
+    double SSu[K][K];
+BVG_UNROLL
+    for (int i = 0; i < K; ++i)
+BVG_UNROLL
+      for (int j = 0; j < K; ++j) SSu[i][j] = cs.SS[i + K * j];
+    if (tid == 0) kron_prep<K>(v, v + n, v + n + NW, M, v + n + NW + K, v + n + NW + K + KU);
+    g.sync();
+    kron_step_core<K>(W, v + n + NW + K, v + n + NW + K + KU, SSu, fail);       // every lane, redundantly, on registers
+    if (keep) {
+BVG_UNROLL
+      for (int j = 0; j < K; ++j)
+BVG_UNROLL
+        for (int i = 0; i <= j; ++i) Wp[tri(j) + i] = W[i][j];
+      double* os = out.sigma + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)(K * K);
+      for (int e = tid; e < K * K; e += G) os[e] = kron_sigma_entry<K>(Wp, e % K, e / K);
+    }
+    g.sync();     // the variates are rewritten by the next sweep
+  }
+  if (tid == 0) {
+BVG_UNROLL
+    for (int i = 0; i < K; ++i)
+BVG_UNROLL
+      for (int j = 0; j < K; ++j) state[i + K * j] = (i <= j) ? W[i][j] : 0.0;
+    if (fail) out.status[chain_local] = 1;
+  }
+  g.sync();
+}
+
+}  // namespace bvg

@@ -11,6 +11,7 @@
 #include <vector>
 #include "../../include/bvargpu.h"
 #include "bvg_tvp_sweep.cuh"
+#include "bvg_kron_sweep.cuh"
 
 namespace bvg {
 
@@ -25,7 +26,8 @@ struct Prepared {
   // offsets (doubles) into blob; -1 = absent
   long Y = -1, X = -1, XX = -1, YX = -1, Aols = -1, SSE = -1, mu = -1, vi_off = -1, vmu_off = -1, vdiag0 = -1,
        tau0 = -1, tau1 = -1, inprior = -1, S0 = -1, gshape = -1, grate = -1, svmu = -1, svvi = -1, svconst = -1,
-       mixp = -1, mixmu = -1, mixs2 = -1, omega_off = -1, vshape = -1, vrate = -1;
+       mixp = -1, mixmu = -1, mixs2 = -1, omega_off = -1, vshape = -1, vrate = -1, kLinv = -1, kSS = -1;
+  int kron = 0;   // 1 = flat-prior Kronecker sweep (bvg_kron_sweep.cuh)
   std::string error;
 
   long push(const double* p, size_t cnt) {
@@ -241,6 +243,30 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
         for (int e = 0; e < kk; ++e) SSE[e] = (double)sse[e];
         P.Aols = P.push(A);
         P.SSE = P.push(SSE);
+        // flat-prior Kronecker specialisation: V^-1 = 0, Wishart prior, no variable selection, k <= 4, and the
+        // caller left the residual mode to the library (an explicit mode selects the general kernel)
+        bool flat = (s->resid_mode == BVG_RESID_AUTO) && !P.tvp && P.sigma_type == BVG_SIGMA_WISHART &&
+                    P.varsel == BVG_VARSEL_NONE && P.vi_off < 0 && k <= 4;
+        for (int r = 0; r < n && flat; ++r) if (P.blob[P.vdiag0 + r] != 0.0) flat = false;
+        if (flat) {
+          // L_X^-1 in long double from the factor C (lower, col-major) computed above
+          std::vector<long double> Li((size_t)M * M, 0.0L);
+          for (int c = 0; c < M; ++c) {
+            Li[c + (size_t)M * c] = 1.0L / C[c + (size_t)M * c];
+            for (int i = c + 1; i < M; ++i) {
+              long double v = 0.0L;
+              for (int mm = c; mm < i; ++mm) v += C[i + (size_t)M * mm] * Li[mm + (size_t)M * c];
+              Li[i + (size_t)M * c] = -v / C[i + (size_t)M * i];
+            }
+          }
+          std::vector<double> lp((size_t)tri(M)), ss((size_t)kk);
+          for (int i = 0; i < M; ++i)
+            for (int c = 0; c <= i; ++c) lp[tri(i) + c] = (double)Li[i + (size_t)M * c];
+          for (int e = 0; e < kk; ++e) ss[e] = (double)(sse[e] + (long double)s->wishart_scale[e]);
+          P.kLinv = P.push(lp);
+          P.kSS = P.push(ss);
+          P.kron = 1;
+        }
         rm = BVG_RESID_MOMENT;
       } else {
         if (rm == BVG_RESID_MOMENT) BVG_FAIL(-9, "moment residual mode needs T > M and X of full row rank");
@@ -280,6 +306,8 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
     double* st = P.state0.data();
     for (int e = 0; e < kk; ++e) st[e] = sig0[e];
     for (int r = 0; r < n; ++r) { st[kk + r] = P.blob[P.vdiag0 + r]; st[kk + n + r] = 1.0; }
+    if (P.kron)   // the Kronecker sweep keeps B^-1 = chol(Sigma^-1)^-1 (upper) in the Sigma^-1 slot; the initial Sigma^-1 is diagonal
+      for (int i = 0; i < k; ++i) st[i + (size_t)k * i] = 1.0 / sqrt(sig0[i + (size_t)k * i]);
     if (P.sigma_type == BVG_SIGMA_SV) {
       double* sh = st + kk + 2 * n;
       for (int e = 0; e < T * k; ++e) sh[e] = s->sv_h[e];
@@ -304,6 +332,8 @@ static inline void bind_bvar(const Prepared& P, const double* base, const unsign
   m->sv_mu = at(base, P.svmu); m->sv_vi = at(base, P.svvi); m->sv_const = at(base, P.svconst);
   m->mix_p = at(base, P.mixp); m->mix_mu = at(base, P.mixmu); m->mix_s2 = at(base, P.mixs2);
   m->omega_off = at(base, P.omega_off);
+  m->kron_Linv = P.kron ? at(base, P.kLinv) : nullptr;
+  m->kron_SS = P.kron ? at(base, P.kSS) : nullptr;
 }
 
 static inline void bind_tvp(const Prepared& P, const double* base, const unsigned char* inc, TvpModel* m) {

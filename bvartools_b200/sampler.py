@@ -96,6 +96,10 @@ class ChainSampler:
     def launch_count(self):
         return lib().bvg_sampler_launch_count(self.handle)
 
+    @property
+    def kernel_name(self):
+        return lib().bvg_sampler_kernel_name(self.handle).decode()
+
     def close(self):
         if self.handle:
             lib().bvg_sampler_destroy(self.handle)

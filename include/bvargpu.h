@@ -161,6 +161,7 @@ int bvg_sampler_device_out(bvg_sampler* s, bvg_out* dev_out);   /* device pointe
 int bvg_sampler_sync(bvg_sampler* s);
 double bvg_sampler_last_kernel_ms(bvg_sampler* s);        /* CUDA-event time of the sweep kernels of the last run */
 int64_t bvg_sampler_launch_count(bvg_sampler* s);         /* kernels launched by the last run                 */
+const char* bvg_sampler_kernel_name(bvg_sampler* s);      /* which sweep kernel the plan selected, e.g. "kron_k3_g8" */
 void bvg_sampler_destroy(bvg_sampler* s);
 
 /* set a callback polled between kernel batches (Rcpp::checkUserInterrupt analogue, bvaralg.cpp:294-296);

@@ -94,7 +94,7 @@ extern "C" int emu_bvaralg(const bvg_spec* s, const bvg_out* o) {
   std::vector<int> status(s->n_chains, 0);
   out.status = status.data();
   out.iters = s->iterations;
-  std::vector<double> sm(bvar_smem_len(P.k, P.T, P.M, P.n, P.sigma_type, P.resid_mode) + 16);
+  std::vector<double> sm(bvar_smem_len(P.k, P.T, P.M, P.n, P.sigma_type, P.resid_mode) + kron_smem_len(P.k, P.M) + 16);
   SerialGroup g;
   const int sweeps = s->iterations + s->burnin;
   const int chunk = s->sweeps_per_launch > 0 ? s->sweeps_per_launch : sweeps;
@@ -107,7 +107,17 @@ extern "C" int emu_bvaralg(const bvg_spec* s, const bvg_out* o) {
     for (int s0 = 0; s0 < sweeps; s0 += chunk) {
       const int s1 = s0 + chunk < sweeps ? s0 + chunk : sweeps;
       auto go = [&](const auto& grp) {           // same variant choice as launch_bvar()
-        if (need == 0) bvar_chain<0>(grp, m, cs, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin);
+        if (P.kron) {
+          KronConsts kc;
+          kc.Linv = m.kron_Linv; kc.Aols = m.Aols; kc.SS = m.kron_SS;
+          switch (P.k) {
+            case 1: bvar_kron_chain<1>(grp, m, kc, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin); break;
+            case 2: bvar_kron_chain<2>(grp, m, kc, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin); break;
+            case 3: bvar_kron_chain<3>(grp, m, kc, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin); break;
+            default: bvar_kron_chain<4>(grp, m, kc, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin); break;
+          }
+        }
+        else if (need == 0) bvar_chain<0>(grp, m, cs, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin);
         else if ((need & ~(int)F_VARSEL) == 0) bvar_chain<F_VARSEL>(grp, m, cs, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin);
         else bvar_chain<F_ALL>(grp, m, cs, rng, st.data(), sm.data(), out, c, s0, s1, s->burnin);
       };

@@ -29,6 +29,21 @@ CASES = {
 }
 
 
+def _grid_model(p, K=3, **kw):
+    """One member of the p = 0:4 grid of config c2-B (flat prior, df = k) -> Kronecker sweep kernel when p > 0."""
+    x, names = helpers.e1_readme_sample()
+    ms = helpers.gen_var(x[:, :K], p=range(0, 5), deterministic="const", iterations=25, burnin=5, names=names[:K])
+    return helpers.add_priors(ms[p], coef=dict(v_i=0, v_i_det=0), sigma=dict(df="k", scale=1e-4))
+
+
+# resid_mode left to the library + flat prior => flat-prior Kronecker kernel (bvg_kron_sweep.cuh)
+CASES["kron_c1"] = (lambda: helpers.model_c1(iterations=40, burnin=10), {})
+for _p in range(0, 5):
+    CASES["kron_grid_p%d" % _p] = ((lambda p=_p: _grid_model(p)), {})
+CASES["kron_k2"] = (lambda: _grid_model(2, K=2), {})
+CASES["kron_k1"] = (lambda: _grid_model(3, K=1), {})
+
+
 def _tvp_wishart():
     y = helpers.synth_var(2, 1, 28, 11)
     m = helpers.gen_var(y, p=1, deterministic="const", iterations=8, burnin=3, tvp=True)
@@ -58,7 +73,7 @@ def test_kernel_logic_matches_oracle(emu, name):
 
 
 @pytest.mark.parametrize("G", [4, 32])
-@pytest.mark.parametrize("name", ["c1_wishart_moment", "c1_informative_prior", "ssvs_moment", "bvs_direct", "gamma",
+@pytest.mark.parametrize("name", ["kron_c1", "kron_grid_p4", "kron_k2", "c1_wishart_moment", "c1_informative_prior", "ssvs_moment", "bvs_direct", "gamma",
                                   "sv_bvs", "tvp_sv_bvs", "tvp_wishart"])
 def test_kernel_logic_spmd_lanes_match_oracle(emu, name, G):
     """Same check with the chain owned by G real threads (barriers + emulated shuffles): exercises the
