@@ -8,7 +8,9 @@ import pathlib
 from . import _abi
 
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "csrc" / "libbvargpu.so"
+import os as _os
+# BVG_LIB: alternative build of the same library (A/B timing experiments)
+LIB_PATH = pathlib.Path(_os.environ["BVG_LIB"]) if _os.environ.get("BVG_LIB") else _HERE / "csrc" / "libbvargpu.so"
 _lib = None
 
 

@@ -8,14 +8,18 @@
 //   B  the state recursion W <- U(S0 + SSE + W E E' W') A_B^-1 of round r, one THREAD per chain with W in registers
 //      (latency-bound, a few hundred dependent FP64 operations per sweep); its warp joins A when it is done, and
 //      the other CTAs resident on the SM fill the issue slots meanwhile;
-//   C  the state-independent products G = E E', A_B^-1 of round r+1, and the retained draws of round r: a = vec(A_ols + W E L_X^-1) and Sigma = W W', as flat (chain, sweep, column)
-//      items so that a warp writes consecutive addresses of the [chain][iter][row] output (coalesced).
+//   C  one thread per (chain, sweep): the state-independent products of round r+1 (G = E E', A_B^-1, T = E L_X^-1 in
+//      place) and the retained draws of round r (a = vec(A_ols + W T), Sigma = W W') staged in place in the records;
+//   D  a flat copy of the staged draws to the [chain][iter][row] output: a warp writes consecutive addresses.
 // Variates live in shared memory (double-buffered), W per sweep in a small history buffer; HBM sees only the draws.
 #include "bvg_kernels.cuh"
 #include "bvg_kron_sweep.cuh"
 
 namespace bvg {
 
+#ifndef BVG_KRON_MINB
+#define BVG_KRON_MINB 1
+#endif
 struct KronPlanDims {
   int CH;      // chains per CTA
   int NB;      // sweeps per round
@@ -31,16 +35,16 @@ struct FastDiv {
 };
 
 template <int K>
-__global__ void __launch_bounds__(512) bvar_kron_batch_kernel(
+__global__ void __launch_bounds__(512, BVG_KRON_MINB) bvar_kron_batch_kernel(
     const __grid_constant__ BvarModel m, const __grid_constant__ RngParams rp, double* state, int state_len,
     const __grid_constant__ BvarOut out, long long n_chains, int s0, int s1, int burnin,
     const __grid_constant__ KronPlanDims pd) {
   extern __shared__ double smem[];
   __shared__ int work_ctr[2];
-  constexpr int KU = (K * (K + 1)) / 2, NW = (K * (K - 1)) / 2;
+  constexpr int KU = (K * (K + 1)) / 2, NW = (K * (K - 1)) / 2, KK = K * K;
   const int M = m.M, n = K * M, CH = pd.CH, NB = pd.NB, VL = pd.VL;
   const int NT = blockDim.x, tid = threadIdx.x, lane = tid & 31;
-  // ---- shared memory: constants | variates [2][NB][CH][VL] | W history [NB + 1][CH][KU]
+  // ---- shared memory: constants | records [2][NB][CH][VL] | W history [NB + 1][CH][KU]
   KronConsts cs;
   double* p = smem;
   {
@@ -57,31 +61,58 @@ __global__ void __launch_bounds__(512) bvar_kron_batch_kernel(
   const int CHv = (int)((n_chains - chain0 < CH) ? (n_chains - chain0) : CH);   // valid chains of this CTA
   const int NP = kron_pairs(K, M);
   const int items_per_cs = NP + K;           // Box-Muller pairs + chi-squares per (chain, sweep)
-  const FastDiv dCH((unsigned)CHv), dNP((unsigned)NP), dM((unsigned)M);
+  const FastDiv dCH((unsigned)CHv), dNP((unsigned)NP);
+  const int o_wn = n, o_chi = n + NW, o_G = n + NW + K, o_Ai = n + NW + K + KU;   // record layout
 
-  // phase A for the sweeps [b0, b0 + nb) into variate buffer `buf`; work handed out in warp-sized chunks
-  auto phase_a = [&](int b0, int nb, int buf) {
-    const int total = CHv * nb * items_per_cs;
+  // stage 1a: variates of the sweeps [b0, b0 + nb) into record buffer `buf`; work handed out in chunks of 64 items.
+  // Item order: chi-squares first (their rejection loop diverges: keep them in the same warps), then Box-Muller
+  // pairs, two per lane and call so that two independent dependency chains are in flight.
+  auto gen_variates = [&](int b0, int nb, int buf) {
+    const int n_chi = (CHv * nb * K + 63) & ~63;             // padded: a 64-chunk holds only one kind of item
+    const int n_chi_real = CHv * nb * K;
+    const int n_pair = CHv * nb * NP;
+    const int total = n_chi + n_pair;
     double* vb = var + (size_t)buf * NB * CH * VL;
     for (;;) {
       int base = 0;
-      if (lane == 0) base = atomicAdd(&work_ctr[buf], 32);
+      if (lane == 0) base = atomicAdd(&work_ctr[buf], 64);
       base = __shfl_sync(0xffffffffu, base, 0);
       if (base >= total) break;
-      const int it = base + lane;
-      if (it < total) {
-        // chi-square items first (they diverge in the rejection loop; keep them in the same warps), then the pairs
-        const int n_chi = CHv * nb * K;
-        unsigned c, sw, q, rest;
-        if (it < n_chi) { q = (unsigned)it % K; rest = (unsigned)it / K; }
-        else dNP.divmod((unsigned)(it - n_chi), rest, q);
-        dCH.divmod(rest, sw, c);
-        const ChainRng rng(&rp, chain0 + c);
-        double* v = vb + (sw * (unsigned)CH + c) * (unsigned)VL;
-        if (it < n_chi) v[n + NW + q] = kron_gen_chi(rng, b0 + sw, q, m.wish_df_post);
-        else kron_gen_pair(rng, b0 + sw, q, K, M, v);
+      if (base < n_chi) {
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const int it = base + 32 * h + lane;
+          if (it < n_chi_real) {
+            unsigned c, sw;
+            const unsigned q = (unsigned)it % K;
+            dCH.divmod((unsigned)it / K, sw, c);
+            const ChainRng rng(&rp, chain0 + c);
+            vb[(sw * (unsigned)CH + c) * (unsigned)VL + o_chi + q] = kron_gen_chi(rng, b0 + sw, q, m.wish_df_post);
+          }
+        }
+      } else {
+        const int ia = base - n_chi + lane, ib = ia + 32;
+        unsigned ca, swa, qa, ra, cb, swb, qb, rb;
+        dNP.divmod((unsigned)(ia < n_pair ? ia : 0), ra, qa);
+        dCH.divmod(ra, swa, ca);
+        dNP.divmod((unsigned)(ib < n_pair ? ib : 0), rb, qb);
+        dCH.divmod(rb, swb, cb);
+        const ChainRng rga(&rp, chain0 + ca), rgb(&rp, chain0 + cb);
+        double* va = vb + (swa * (unsigned)CH + ca) * (unsigned)VL;
+        double* vc = vb + (swb * (unsigned)CH + cb) * (unsigned)VL;
+        if (ib < n_pair) kron_gen_pair_x2(rga, b0 + swa, qa, va, rgb, b0 + swb, qb, vc, K, M);
+        else if (ia < n_pair) kron_gen_pair(rga, b0 + swa, qa, K, M, va);
       }
     }
+  };
+  // stage 2a: state-independent products of the `nb` sweeps of buffer `buf`, one thread per (chain, sweep):
+  // G = E E', A_B^-1, then T = E L_X^-1 in place
+  auto prep = [&](int it, int buf) {
+    unsigned sw, c;
+    dCH.divmod((unsigned)it, sw, c);
+    double* v = var + (size_t)buf * NB * CH * VL + (sw * (unsigned)CH + c) * (unsigned)VL;
+    kron_prep<K>(v, v + o_wn, v + o_chi, M, v + o_G, v + o_Ai);
+    kron_t_inplace<K>(v, cs.Linv, M);
   };
 
   // chain state (threads < CHv): W upper in registers; so is the constant S0 + SSE
@@ -98,25 +129,14 @@ __global__ void __launch_bounds__(512) bvar_kron_batch_kernel(
 #pragma unroll
       for (int j = 0; j < K; ++j) W[i][j] = (i <= j) ? st[i + K * j] : 0.0;
   }
-  // state-independent products of the sweeps [.., nb) of buffer `buf`: G = E E', A_B^-1 (one thread per (chain, sweep))
-  auto phase_prep = [&](int nb, int buf) {
-    double* vb = var + (size_t)buf * NB * CH * VL;
-    for (int it = tid; it < CHv * nb; it += NT) {
-      unsigned sw, c;
-      dCH.divmod((unsigned)it, sw, c);
-      double* v = vb + (sw * (unsigned)CH + c) * (unsigned)VL;
-      kron_prep<K>(v, v + n, v + n + NW, M, v + n + NW + K, v + n + NW + K + KU);
-    }
-  };
   if (tid < 2) work_ctr[tid] = 0;
   __syncthreads();
   {
     const int nb0 = (s1 - s0 < NB) ? (s1 - s0) : NB;
-    phase_a(s0, nb0, 0);
+    gen_variates(s0, nb0, 0);
     __syncthreads();
-    phase_prep(nb0, 0);
+    for (int it = tid; it < CHv * nb0; it += NT) prep(it, 0);
   }
-  __syncthreads();
 
   int buf = 0;
   for (int b0 = s0; b0 < s1; b0 += NB, buf ^= 1) {
@@ -125,55 +145,62 @@ __global__ void __launch_bounds__(512) bvar_kron_batch_kernel(
     const int nb_next = (b1 < s1) ? ((s1 - b1 < NB) ? (s1 - b1) : NB) : 0;
     if (tid == 0) work_ctr[buf ^ 1] = 0;     // counter of the buffer filled in this round (idle since the last barrier)
     __syncthreads();
-    // ---- B (threads < CHv) ...
-    const double* vb = var + (size_t)buf * NB * CH * VL;
+    // ---- stage 1: state recursion of this round (threads < CHv) ...
+    double* vb = var + (size_t)buf * NB * CH * VL;
     if (tid < CHv) {
       for (int sw = 0; sw < nb; ++sw) {
-        double* wp = wh + ((size_t)sw * CH + tid) * KU;
+        double* wp = wh + (sw * CH + tid) * KU;
 #pragma unroll
         for (int j = 0; j < K; ++j)
 #pragma unroll
           for (int i = 0; i <= j; ++i) wp[tri(j) + i] = W[i][j];
-        const double* v = vb + (sw * CH + tid) * VL + n + NW + K;
-        kron_step_core<K>(W, v, v + KU, SSu, fail);
+        const double* v = vb + (sw * CH + tid) * VL;
+        kron_step_core<K>(W, v + o_G, v + o_Ai, SSu, fail);
       }
-      double* wp = wh + ((size_t)nb * CH + tid) * KU;
+      double* wp = wh + (nb * CH + tid) * KU;
 #pragma unroll
       for (int j = 0; j < K; ++j)
 #pragma unroll
         for (int i = 0; i <= j; ++i) wp[tri(j) + i] = W[i][j];
     }
-    // ---- ... overlapped with A of the next round (all warps; the B warp joins late)
-    if (nb_next > 0) phase_a(b1, nb_next, buf ^ 1);
+    // ---- ... overlapped with the variates of the next round (all warps; the recursion warp joins late)
+    if (nb_next > 0) gen_variates(b1, nb_next, buf ^ 1);
     __syncthreads();
-    // ---- C: retained draws of this round
+    // ---- stage 2: one thread per (chain, sweep): products of the next round; draws of this round, staged in place
     const int k0 = (b0 > burnin) ? b0 : burnin;        // first retained sweep of the round
-    if (b1 > k0) {
-      const int nk = b1 - k0, sw0 = k0 - b0;
-      const FastDiv dNK((unsigned)nk);
-      const int coef_items = CHv * nk * M;
-      for (int it = tid; it < coef_items; it += NT) {
-        unsigned j, rest, cu, swu;
-        dM.divmod((unsigned)it, rest, j);
-        dNK.divmod(rest, cu, swu);
-        const int sw = sw0 + (int)swu, c = (int)cu;
-        const long long pos = (long long)(b0 + sw) - burnin;
-        double* oc = out.coef + ((size_t)(chain0 + c) * (size_t)out.iters + (size_t)pos) * (size_t)n;
-        kron_coef_col<K>(wh + ((size_t)sw * CH + c) * KU, vb + ((size_t)sw * CH + c) * VL, cs, M, j, oc);
-      }
-      const int sig_items = CHv * nk * K * K;
-      for (int it = tid; it < sig_items; it += NT) {
-        unsigned cu, swu;
-        const int e = it % (K * K);
-        dNK.divmod((unsigned)it / (K * K), cu, swu);
-        const int sw = sw0 + (int)swu, c = (int)cu;
-        const long long pos = (long long)(b0 + sw) - burnin;
-        out.sigma[((size_t)(chain0 + c) * (size_t)out.iters + (size_t)pos) * (size_t)(K * K) + e] =
-            kron_sigma_entry<K>(wh + ((size_t)(sw + 1) * CH + c) * KU, e % K, e / K);
+    const int nk = (b1 > k0) ? b1 - k0 : 0, sw0 = k0 - b0;
+    const int n_prep = CHv * nb_next, n_out = CHv * nk;
+    for (int it = tid; it < n_prep + n_out; it += NT) {
+      if (it < n_prep) { prep(it, buf ^ 1); continue; }
+      unsigned swu, c;
+      dCH.divmod((unsigned)(it - n_prep), swu, c);
+      const int sw = sw0 + (int)swu;
+      double* v = vb + (sw * CH + c) * VL;
+      kron_coef_inplace<K>(wh + (sw * CH + c) * KU, v, cs.Aols, M);       // a = vec(A_ols + W T), W used by this sweep
+      kron_sigma<K>(wh + ((sw + 1) * CH + c) * KU, v + o_G);              // Sigma = W W', W after this sweep
+    }
+    if (nk > 0) {
+      __syncthreads();
+      // ---- stage 3: coalesced copy of the staged draws: per chain nk * n (resp. nk * K * K) consecutive doubles;
+      //      one warp per chain, lanes over consecutive addresses, (sweep, element) index kept incrementally
+      const long long pos0 = (long long)k0 - burnin;
+      const int warp = tid >> 5, n_warps = NT >> 5;
+      for (int c = warp; c < CHv; c += n_warps) {
+        double* dst = out.coef + ((size_t)(chain0 + c) * (size_t)out.iters + (size_t)pos0) * (size_t)n;
+        const double* src = vb + (sw0 * CH + c) * VL;
+        const int step_e = 32 % n, step_sw = 32 / n;
+        int e = lane % n, sw = lane / n;
+        for (int rem = lane; rem < nk * n; rem += 32) {
+          dst[rem] = src[sw * CH * VL + e];
+          e += step_e; sw += step_sw;
+          if (e >= n) { e -= n; ++sw; }
+        }
+        double* dsts = out.sigma + ((size_t)(chain0 + c) * (size_t)out.iters + (size_t)pos0) * (size_t)KK;
+        for (int rem = lane; rem < nk * KK; rem += 32)
+          dsts[rem] = src[(rem / KK) * CH * VL + o_G + (rem % KK)];
       }
     }
-    if (nb_next > 0) phase_prep(nb_next, buf ^ 1);
-    // (no barrier needed here: the next round starts with one, and A of the next round writes the other buffer)
+    // (the next round starts with a barrier; its variates go to the other buffer)
   }
   if (tid < CHv) {
     double* st = state + (size_t)(chain0 + tid) * state_len;
@@ -189,6 +216,8 @@ template <int K>
 static cudaError_t launch_k(const KronPlanDims& pd, BVG_BVAR_ARGS_NAMED) {
   cudaError_t e = set_smem(bvar_kron_batch_kernel<K>, plan.smem_bytes);
   if (e != cudaSuccess) return e;
+  // several CTAs per SM only co-reside when the L1 / shared-memory split favours shared memory
+  cudaFuncSetAttribute(bvar_kron_batch_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   bvar_kron_batch_kernel<K><<<plan.grid, plan.block_threads, plan.smem_bytes, stream>>>(
       m, rp, state, state_len, out, n_chains, s0, s1, burnin, pd);
   return cudaGetLastError();

@@ -45,6 +45,26 @@ BVG_HD void kron_gen_pair(const ChainRng& rng, int sweep, int p, int K, int M, d
   dst[2 * pr] = nn.a;
   if (2 * pr + 1 < cnt) dst[2 * pr + 1] = nn.b;
 }
+// two pairs (of possibly different chains / sweeps) at once: see philox_normal_pair_x2
+BVG_HD void kron_gen_pair_x2(const ChainRng& ra, int sweep_a, int pa, double* va, const ChainRng& rb, int sweep_b, int pb,
+                             double* vb, int K, int M) {
+  if (ra.injected(VB_COEF_N) || ra.injected(VB_WISH_N)) {
+    kron_gen_pair(ra, sweep_a, pa, K, M, va);
+    kron_gen_pair(rb, sweep_b, pb, K, M, vb);
+    return;
+  }
+  const int n = K * M, NW = (K * (K - 1)) / 2, p_coef = (n + 1) >> 1;
+  int blk_a = VB_COEF_N, pra = pa, cnt_a = n, blk_b = VB_COEF_N, prb = pb, cnt_b = n;
+  double* da = va;
+  double* db = vb;
+  if (pa >= p_coef) { blk_a = VB_WISH_N; pra = pa - p_coef; cnt_a = NW; da = va + n; }
+  if (pb >= p_coef) { blk_b = VB_WISH_N; prb = pb - p_coef; cnt_b = NW; db = vb + n; }
+  const Normal4 nn = philox_normal_pair_x2(ra.seed, ra.chain, blk_a, sweep_a, pra, rb.chain, blk_b, sweep_b, prb);
+  da[2 * pra] = nn.p.a;
+  if (2 * pra + 1 < cnt_a) da[2 * pra + 1] = nn.p.b;
+  db[2 * prb] = nn.q.a;
+  if (2 * prb + 1 < cnt_b) db[2 * prb + 1] = nn.q.b;
+}
 // sqrt(chi2(df - i)) of the Bartlett diagonal (Marsaglia-Tsang; attempt 0 uses normal(VB_WISH_C, sweep, i))
 BVG_HD double kron_gen_chi(const ChainRng& rng, int sweep, int i, double df_post) {
   if (rng.injected(VB_WISH_C)) return sqrt(rng.inj_at(VB_WISH_C, sweep, i));
@@ -149,32 +169,62 @@ BVG_UNROLL
     }
 }
 
-// column j of the coefficient draw: a[:, j] = A_ols[:, j] + W (E L_X^-1)[:, j]     (bvaralg.cpp:306-307)
-// Wp: the K(K+1)/2 upper entries of W packed column by column (W_ij at tri(j) + i)
+// T = E L_X^-1 in place (eps <- T, column by column: column j only needs the columns >= j)     [state independent]
 template <int K>
-BVG_HD void kron_coef_col(const double* Wp, const double* eps, const KronConsts& cs, int M, int j, double* oc) {
-  double t[K];
+BVG_HD void kron_t_inplace(double* eps, const double* Linv, int M) {
+  for (int j = 0; j < M; ++j) {
+    double t[K];
 BVG_UNROLL
-  for (int i = 0; i < K; ++i) t[i] = 0.0;
-  for (int j2 = j; j2 < M; ++j2) {
-    const double li = cs.Linv[tri(j2) + j];
+    for (int i = 0; i < K; ++i) t[i] = 0.0;
+    for (int j2 = j; j2 < M; ++j2) {
+      const double li = Linv[tri(j2) + j];
 BVG_UNROLL
-    for (int i = 0; i < K; ++i) t[i] = fma(eps[i + K * j2], li, t[i]);
-  }
+      for (int i = 0; i < K; ++i) t[i] = fma(eps[i + K * j2], li, t[i]);
+    }
 BVG_UNROLL
-  for (int i = 0; i < K; ++i) {
-    double d = 0.0;
-BVG_UNROLL
-    for (int i2 = i; i2 < K; ++i2) d = fma(Wp[tri(i2) + i], t[i2], d);
-    oc[i + K * j] = cs.Aols[i + K * j] + d;
+    for (int i = 0; i < K; ++i) eps[i + K * j] = t[i];
   }
 }
-// entry (i, j) of Sigma = W W'                                                       (bvaralg.cpp:528)
+// a = vec(A_ols + W T) in place (tvals <- a)                                          (bvaralg.cpp:306-307)
+// Wp: the K(K+1)/2 upper entries of W packed column by column (W_ij at tri(j) + i)
 template <int K>
-BVG_HD double kron_sigma_entry(const double* Wp, int i, int j) {
-  double v = 0.0;
-  for (int mm = (i > j ? i : j); mm < K; ++mm) v = fma(Wp[tri(mm) + i], Wp[tri(mm) + j], v);
-  return v;
+BVG_HD void kron_coef_inplace(const double* Wp, double* tvals, const double* Aols, int M) {
+  double W[K][K];
+BVG_UNROLL
+  for (int j = 0; j < K; ++j)
+BVG_UNROLL
+    for (int i = 0; i <= j; ++i) W[i][j] = Wp[tri(j) + i];
+  for (int j = 0; j < M; ++j) {
+    double t[K];
+BVG_UNROLL
+    for (int i = 0; i < K; ++i) t[i] = tvals[i + K * j];
+BVG_UNROLL
+    for (int i = 0; i < K; ++i) {
+      double d = Aols[i + K * j];
+BVG_UNROLL
+      for (int i2 = i; i2 < K; ++i2) d = fma(W[i][i2], t[i2], d);
+      tvals[i + K * j] = d;
+    }
+  }
+}
+// Sigma = W W' (full K x K, col-major) into dst                                        (bvaralg.cpp:528)
+template <int K>
+BVG_HD void kron_sigma(const double* Wp, double* dst) {
+  double W[K][K];
+BVG_UNROLL
+  for (int j = 0; j < K; ++j)
+BVG_UNROLL
+    for (int i = 0; i <= j; ++i) W[i][j] = Wp[tri(j) + i];
+BVG_UNROLL
+  for (int i = 0; i < K; ++i)
+BVG_UNROLL
+    for (int j = 0; j <= i; ++j) {
+      double v = 0.0;
+BVG_UNROLL
+      for (int mm = i; mm < K; ++mm) v = fma(W[i][mm], W[j][mm], v);
+      dst[i + K * j] = v;
+      dst[j + K * i] = v;
+    }
 }
 
 // ---- group-generic chain (tile kernel for few sweeps per launch, and the host emulation of the arithmetic) --------
@@ -208,25 +258,34 @@ BVG_UNROLL
     for (int j = 0; j < K; ++j)
 BVG_UNROLL
       for (int i = 0; i <= j; ++i) Wp[tri(j) + i] = W[i][j];
-    if (keep) {
-      double* oc = out.coef + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n;
-      for (int j = tid; j < M; j += G) kron_coef_col<K>(Wp, v, cs, M, j, oc);
-    }
     double SSu[K][K];
 BVG_UNROLL
     for (int i = 0; i < K; ++i)
 BVG_UNROLL
       for (int j = 0; j < K; ++j) SSu[i][j] = cs.SS[i + K * j];
-    if (tid == 0) kron_prep<K>(v, v + n, v + n + NW, M, v + n + NW + K, v + n + NW + K + KU);
+    double* Gp = v + n + NW + K;
+    double* Aip = Gp + KU;
+    if (tid == 0) {
+      kron_prep<K>(v, v + n, v + n + NW, M, Gp, Aip);
+      kron_t_inplace<K>(v, cs.Linv, M);
+      if (keep) kron_coef_inplace<K>(Wp, v, cs.Aols, M);
+    }
     g.sync();
-    kron_step_core<K>(W, v + n + NW + K, v + n + NW + K + KU, SSu, fail);       // every lane, redundantly, on registers
+    if (keep) {
+      double* oc = out.coef + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n;
+      for (int e = tid; e < n; e += G) oc[e] = v[e];
+    }
+    kron_step_core<K>(W, Gp, Aip, SSu, fail);       // every lane, redundantly, on registers
+    g.sync();
     if (keep) {
 BVG_UNROLL
       for (int j = 0; j < K; ++j)
 BVG_UNROLL
         for (int i = 0; i <= j; ++i) Wp[tri(j) + i] = W[i][j];
+      if (tid == 0) kron_sigma<K>(Wp, Gp);          // staged in the G / A_B^-1 slots (no longer needed)
+      g.sync();
       double* os = out.sigma + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)(K * K);
-      for (int e = tid; e < K * K; e += G) os[e] = kron_sigma_entry<K>(Wp, e % K, e / K);
+      for (int e = tid; e < K * K; e += G) os[e] = Gp[e];
     }
     g.sync();     // the variates are rewritten by the next sweep
   }
