@@ -48,6 +48,8 @@ struct bvg_sampler {
   double* d_state = nullptr;
   double* d_state0 = nullptr;   // one chain's initial state
   double* d_scratch = nullptr;  // TVP
+  double* d_work = nullptr;     // large-VAR path: per-chain matrices
+  bool large = false;
   long long scratch_per_chain = 0;
   double* d_inj[VB_COUNT] = {nullptr};
   // outputs (device)
@@ -114,7 +116,7 @@ int bvg_out_rows(const bvg_spec* spec, int64_t* coef_rows, int64_t* sigma_rows, 
 void bvg_sampler_destroy(bvg_sampler* s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  cudaFree(s->d_blob); cudaFree(s->d_include); cudaFree(s->d_state); cudaFree(s->d_state0); cudaFree(s->d_scratch);
+  cudaFree(s->d_blob); cudaFree(s->d_include); cudaFree(s->d_state); cudaFree(s->d_state0); cudaFree(s->d_scratch); cudaFree(s->d_work);
   for (int b = 0; b < VB_COUNT; ++b) cudaFree(s->d_inj[b]);
   cudaFree(s->d_coef); cudaFree(s->d_sigma); cudaFree(s->d_lambda); cudaFree(s->d_sigma_h); cudaFree(s->d_sigma_v);
   cudaFree(s->d_status);
@@ -232,7 +234,25 @@ int bvg_sampler_create(const bvg_spec* spec, bvg_sampler** out) {
     return fail(2, m);
   }
   cudaError_t pe = P.tvp ? plan_tvp(s->tm, s->n_chains, s->requested_tpc, &s->plan)
-                         : plan_bvar(s->bm, s->n_chains, s->requested_tpc, &s->plan);
+                         : plan_bvar(s->bm, s->n_chains, s->requested_tpc == -1 ? 0 : s->requested_tpc, &s->plan);
+  // large-VAR path: the precision matrix does not fit on chip (or the caller forces it with threads_per_chain = -1)
+  if (!P.tvp && (pe == cudaErrorInvalidConfiguration || s->requested_tpc == -1)) {
+    const bool ok = P.n > 0 && P.sigma_type == BVG_SIGMA_WISHART && P.varsel == BVG_VARSEL_NONE && P.vi_off < 0 && P.k <= 32;
+    if (!ok) {
+      bvg_sampler_destroy(s);
+      return fail(-53, "large models (n beyond the shared-memory kernels) are supported for a diagonal prior precision, "
+                       "a Wishart error-variance prior and no variable selection");
+    }
+    if (s->plan.kron) {   // the state holds W = chol(Sigma^-1)^-1 for the Kronecker kernel: store Sigma^-1 itself
+      for (int i = 0; i < P.k; ++i) s->P.state0[i + (size_t)P.k * i] = 1.0 / (s->P.state0[i + (size_t)P.k * i] * s->P.state0[i + (size_t)P.k * i]);
+      CKS(cudaMemcpy(s->d_state0, s->P.state0.data(), (size_t)P.state_len * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    s->large = true;
+    s->plan.kron = 0;
+    s->plan.threads_per_chain = 0;
+    CKS(cudaMalloc(&s->d_work, large_workspace_doubles(s->bm, s->n_chains) * sizeof(double)));
+    pe = cudaSuccess;
+  }
   if (pe != cudaSuccess) {
     bvg_sampler_destroy(s);
     return fail(-52, "model does not fit the shared-memory kernels (n too large for this path) or invalid threads_per_chain");
@@ -240,7 +260,8 @@ int bvg_sampler_create(const bvg_spec* spec, bvg_sampler** out) {
   {
     const int need = P.tvp ? 0 : bvar_features_needed(s->bm.sigma_type, s->bm.varsel, s->bm.resid_mode, s->bm.vi_off != nullptr);
     const int tpc = s->plan.threads_per_chain;
-    if (P.tvp) snprintf(s->kernel_name, sizeof(s->kernel_name), "tvp_g%d", tpc <= 32 ? tpc : 0);
+    if (s->large) snprintf(s->kernel_name, sizeof(s->kernel_name), "large_dmma_n%d", P.n);
+    else if (P.tvp) snprintf(s->kernel_name, sizeof(s->kernel_name), "tvp_g%d", tpc <= 32 ? tpc : 0);
     else if (s->plan.kron) snprintf(s->kernel_name, sizeof(s->kernel_name), "kron_k%d_g%d", P.k, tpc);
     else snprintf(s->kernel_name, sizeof(s->kernel_name), "bvar_g%d_f%d", tpc <= 32 ? tpc : 0,
                   need == 0 ? 0 : ((need & ~(int)F_VARSEL) == 0 ? 2 : 31));
@@ -268,6 +289,12 @@ static int launch_chunk(bvg_sampler* s, int s0, int s1, cudaStream_t stream) {
     BvarOut o;
     o.coef = s->d_coef; o.sigma = s->d_sigma; o.lambda = s->d_lambda; o.sigma_h = s->d_sigma_h;
     o.status = s->d_status; o.iters = P.iterations;
+    if (s->large) {
+      e = launch_bvar_large(s->bm, s->rp, s->d_state, P.state_len, s->d_work, o, s->n_chains, s0, s1, P.burnin, stream,
+                            &s->launches);
+      if (e != cudaSuccess) return cuda_fail(e, "large-VAR kernel launch");
+      return 0;
+    }
     e = launch_bvar(s->plan, s->bm, s->rp, s->d_state, P.state_len, o, s->n_chains, s0, s1, P.burnin, stream);
   }
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");

@@ -28,6 +28,12 @@ cudaError_t launch_bvar(const LaunchPlan& plan, const BvarModel& m, const RngPar
 cudaError_t plan_bvar_kron(const BvarModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan);
 cudaError_t launch_bvar_kron(BVG_BVAR_ARGS_NAMED);
 
+// large-VAR path (bvg_kern_large.cu): per-chain n x n matrices in HBM, blocked DMMA Cholesky
+size_t large_workspace_doubles(const BvarModel& m, long long n_chains);
+cudaError_t launch_bvar_large(const BvarModel& m, const RngParams& rp, double* state, int state_len, double* work,
+                              const BvarOut& out, long long n_chains, int s0, int s1, int burnin, cudaStream_t stream,
+                              long long* launches);
+
 cudaError_t plan_tvp(const TvpModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan);
 cudaError_t launch_tvp(const LaunchPlan& plan, const TvpModel& m, const RngParams& rp, double* state,
                        int state_len, double* scratch, long long scratch_per_chain, const TvpOut& out,

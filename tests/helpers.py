@@ -83,6 +83,20 @@ def model_sv(K=3, p=2, nobs=60, iterations=20, burnin=5, seed=320200, tvp=False,
                       bvs=dict(inprior=0.5, exclude_det=True) if bvs else None)
 
 
+def model_c5(K=20, p=4, nobs=204, iterations=200, burnin=50, seed=2042004):
+    """Config c5: large BVAR, K = 20, p = 4, const (n = 1620), Minnesota prior, sigma df = k, scale 1.
+    DGP: diagonally dominant stable VAR(1), AR(1)-correlated errors."""
+    rng = np.random.default_rng(seed)
+    A1 = 0.4 * np.eye(K) + rng.uniform(-0.02, 0.02, (K, K)) * (1 - np.eye(K))
+    idx = np.arange(K)
+    Lc = np.linalg.cholesky(0.3 ** np.abs(idx[:, None] - idx[None, :]))
+    y = np.zeros((nobs + 100, K))
+    for t in range(1, nobs + 100):
+        y[t] = 0.1 + A1 @ y[t - 1] + Lc @ rng.standard_normal(K)
+    m = gen_var(y[100:], p=p, deterministic="const", iterations=iterations, burnin=burnin)
+    return add_priors(m, coef=dict(minnesota=dict(kappa0=2, kappa1=0.5, kappa3=5)), sigma=dict(df="k", scale=1))
+
+
 # ---------------------------------------------------------------- injected variates
 def variate_kinds(obj):
     model, priors = obj["model"], obj["priors"]

@@ -64,6 +64,47 @@ def test_c4_shape_tvp_sv_injected(gpu):
         assert helpers.relerr(out.arrays[key], want[key]) < 1e-8, key      # state dim nT = 1260
 
 
+@pytest.mark.parametrize("case", ["n21", "n150", "n189"])
+def test_large_path_small_models_injected(gpu, case):
+    """The large-VAR path (per-chain matrices in HBM, blocked DMMA Cholesky) forced on models that also fit on chip
+    (threads_per_chain = -1), against the literal dense oracle: 1, 3 (ragged: 150 = 2 * 64 + 22) and 3 tiles."""
+    if case == "n21":
+        obj = helpers.model_c1(iterations=12, burnin=3, coef=dict(v_i=1, v_i_det=0.1), sigma=dict(df="k", scale=1))
+    else:
+        K, p = (6, 4) if case == "n150" else (7, 3)
+        y = helpers.synth_var(K, p, 150, 77)
+        m = helpers.gen_var(y, p=p, deterministic="const", iterations=6, burnin=2)
+        K = y.shape[1]
+        obj = helpers.add_priors(m, coef=dict(minnesota=dict(kappa0=2, kappa1=0.5, kappa3=5)), sigma=dict(df="k", scale=1))
+    per, stacked = helpers.make_variates(obj, 3, seed=21)
+    out = _run(gpu, obj, 3, stacked, threads_per_chain=-1)
+    want = helpers.oracle_stack(obj, per, literal=True)
+    for key in want:   # norm-wise per draw (the literal and the structured oracle themselves agree to ~5e-12 norm-wise,
+        # cond(XX') ~ 2.5e5 here; the element-wise metric is dominated by coefficients ~1e-4 of the largest one)
+        err = np.linalg.norm(out.arrays[key] - want[key], axis=2) / np.linalg.norm(want[key], axis=2)
+        assert err.max() < TOL, (case, key, err.max())
+    assert not out.status.any()
+    # Philox: the large path and the on-chip kernel draw the same chain (same sites, different arithmetic order)
+    a = _run(gpu, obj, 2, seed=5, threads_per_chain=-1)
+    b = _run(gpu, obj, 2, seed=5, resid_mode=1)
+    for key in a.arrays:
+        np.testing.assert_allclose(a.arrays[key], b.arrays[key], rtol=1e-8, atol=1e-11)
+
+
+def test_c5_full_size_large_var_injected(gpu):
+    """Config c5 at full width (K = 20, p = 4, n = 1620, T = 200, Minnesota prior): 2 chains x 3 sweeps against the
+    structured oracle (the literal dense kT x kT path is checked against the structured one in test_oracle.py);
+    norm-wise 1e-10 as in SURVEY.md Appendix D."""
+    obj = helpers.model_c5(iterations=2, burnin=1)
+    per, stacked = helpers.make_variates(obj, 2, seed=3)
+    out = _run(gpu, obj, 2, stacked)
+    want = helpers.oracle_stack(obj, per, literal=False)
+    for key in want:
+        err = np.linalg.norm(out.arrays[key] - want[key]) / np.linalg.norm(want[key])
+        assert err < TOL, (key, err)
+    assert not out.status.any()
+
+
 def test_chunking_and_layout_invariance_philox(gpu):
     """Same seed => bit-identical draws whatever the launch chunking or lanes per chain (counter-based RNG)."""
     obj = helpers.model_c3(K=3, p=2, nobs=80, iterations=30, burnin=10)
