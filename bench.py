@@ -46,6 +46,10 @@ def build_workload(name, iterations=None, burnin=None):
         it, bi = iterations or 500, 500 if burnin is None else burnin
         obj = helpers.model_sv(K=3, p=2, nobs=202, iterations=it, burnin=bi, tvp=True)
         label = "c4: synthetic TVP-VAR(2) K=3 T=200 + KSC-1998 SV, %d iter / %d burn-in" % (it, bi)
+    elif name == "c5":
+        it, bi = iterations or 200, 50 if burnin is None else burnin
+        obj = helpers.model_c5(iterations=it, burnin=bi)
+        label = "c5: synthetic large BVAR K=20 p=4 T=200 (n=1620), Minnesota prior, %d iter / %d burn-in" % (it, bi)
     else:
         raise SystemExit(f"unknown workload {name}")
     return obj, label
@@ -139,6 +143,8 @@ def cpu_reference_run(obj, label, steps, warmup, sample_sweeps, as_line, n_gpus=
     BVS) on all host cores: one chain per core like parallel::mclapply(mc.cores = ncores)."""
     cores = os.cpu_count() or 1
     is_c = not (obj["model"].get("tvp") or obj["model"].get("sv") or "bvs" in obj["priors"].get("coefficients", {}))
+    if obj["data"]["SUR"].shape[1] > 600:
+        is_c = False            # c5: the dense products go through LAPACK/OpenBLAS (NumPy oracle), as Armadillo would
     times = []
     if is_c:
         from oracle.dense_ref import bvar_dense
@@ -197,7 +203,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     obj, label = build_workload(args.workload, args.iterations or None, None if args.burnin < 0 else args.burnin)
-    cpu_sweeps = args.cpu_sweeps or {"c2a": 1500, "c3": 8, "c4": 2}.get(args.workload, 50)
+    cpu_sweeps = args.cpu_sweeps or {"c2a": 1500, "c3": 8, "c4": 2, "c5": 1}.get(args.workload, 50)
 
     if args.impl == "reference":
         if rank == 0:
@@ -215,7 +221,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     L = lib()
-    chains = args.chains or (4096 if args.workload == "c2a" else 1024)
+    chains = args.chains or {"c2a": 4096, "c5": 256}.get(args.workload, 1024)
     it, bi = obj["model"]["iterations"], obj["model"]["burnin"]
     seed = 20240113
     stream = torch.cuda.current_stream()
@@ -314,8 +320,16 @@ def main():
     moment = not (obj["model"].get("tvp") or obj["model"].get("sv")) and \
         obj["data"]["Y"].shape[0] > obj["data"]["Z"].shape[1]
     fl_sweep = kron_flops_per_sweep(obj) if kernel_name.startswith("kron") else flops_per_sweep(obj, moment)
+    if kernel_name.startswith("large"):
+        fl_sweep = survey_flops_per_sweep(obj)          # direct residuals, full n^3/3 Cholesky: 1.4246 Gflop for c5
     peak = C.c_double(0.0)
     check(L.bvg_fp64_peak(C.byref(peak), None))
+    dmma_peak = C.c_double(0.0)
+    check(L.bvg_dmma_peak(C.byref(dmma_peak), None))
+    peak_source = ("FP64 FMA probe kernel run live by bench.py (bvg_fp64_peak); MEASURED_PEAKS.json has no FP64 entry")
+    if kernel_name.startswith("large") and dmma_peak.value > peak.value:
+        peak = dmma_peak
+        peak_source = "FP64 DMMA (mma.sync m8n8k4) probe kernel run live by bench.py (bvg_dmma_peak)"
     sweep_kernel_s = last_sweep_ms * 1e-3
     achieved = fl_sweep * chains * (it + bi) / sweep_kernel_s / 1e12
     peaks = {}
@@ -327,8 +341,7 @@ def main():
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value > 0 else None, "traffic": None,
                 "kernel": kernel_name,
-                "peak_source": "FP64 FMA probe kernel run live by bench.py (bvg_fp64_peak); MEASURED_PEAKS.json "
-                               "has no FP64 entry",
+                "peak_source": peak_source, "fp64_dmma_peak_tflops": dmma_peak.value,
                 "flops_per_sweep_executed": fl_sweep, "flops_per_sweep_survey": survey_flops_per_sweep(obj),
                 "sweep_kernel_ms_per_step": last_sweep_ms, "sweep_share_of_step": last_sweep_ms / ms_per_step,
                 "hbm_write_GBps": out_bytes / sweep_kernel_s / 1e9, "hbm_peak_GBps": peaks.get("hbm_gbs")}

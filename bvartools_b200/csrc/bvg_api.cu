@@ -456,4 +456,12 @@ int bvg_fp64_peak(double* tflops_fma, void* cuda_stream) {
   return 0;
 }
 
+int bvg_dmma_peak(double* tflops, void* cuda_stream) {
+  if (!tflops) return fail(-1, "output pointer is NULL");
+  if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");
+  cudaError_t e = launch_dmma_peak(tflops, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "dmma peak probe");
+  return 0;
+}
+
 }  // extern "C"

@@ -152,6 +152,56 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters)
   if (s == 123.456) sink[0] = s;
 }
 
+// FP64 tensor-core (DMMA m8n8k4) peak: 8 independent accumulator tiles per warp
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* sink, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x * 1e-9 + i; c[i][1] = 1.0 + i; }
+  const double a = 1.0000001, b = 0.9999999;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) sink[0] = s;
+}
+
+cudaError_t launch_dmma_peak(double* tflops, cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  double* sink = nullptr;
+  cudaError_t e = cudaMalloc(&sink, 8);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 1 << 14, blocks = sms * 8, threads = 256;
+  dmma_peak_kernel<<<blocks, threads, 0, stream>>>(sink, 256);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, stream);
+    dmma_peak_kernel<<<blocks, threads, 0, stream>>>(sink, iters);
+    cudaEventRecord(e1, stream);
+    e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 8 * 8 * 4 * 8.0 * (double)iters * (double)blocks * (threads / 32);   // 512 flop per DMMA
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *tflops = best;
+  return e;
+}
+
 cudaError_t launch_fp64_peak(double* tflops, cudaStream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

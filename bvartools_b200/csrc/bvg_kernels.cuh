@@ -42,6 +42,7 @@ cudaError_t launch_tvp(const LaunchPlan& plan, const TvpModel& m, const RngParam
 cudaError_t launch_moments(const double* draws, long long chains, long long iters, long long rows, double* sums,
                            double* sumsq, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* tflops, cudaStream_t stream);
+cudaError_t launch_dmma_peak(double* tflops, cudaStream_t stream);
 
 // per-instantiation launchers (one translation unit each, see Makefile): G = 4, 8, 16, 32 lanes per chain, 0 = one
 // CTA per chain; BVAR kernels additionally per compile-time feature mask (0 lean, 2 + variable selection, 31 all)

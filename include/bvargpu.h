@@ -175,6 +175,8 @@ int bvg_moments(const double* dev_draws, int64_t chains, int64_t iters, int64_t 
 
 /* measured FP64 FMA throughput of the device (TFLOP/s) -- roofline denominator for the sweep kernels */
 int bvg_fp64_peak(double* tflops_fma, void* cuda_stream);
+/* measured FP64 tensor-core (DMMA m8n8k4) throughput (TFLOP/s) -- denominator for the large-VAR Cholesky */
+int bvg_dmma_peak(double* tflops, void* cuda_stream);
 
 /* ---- batched stand-alone building blocks (B independent problems per call; host pointers) ---------------- */
 /* post_normal (src/post_normal.cpp:61-93): out[b] = a_post + sqrtm(V_post) eps.  method 0 = symmetric
