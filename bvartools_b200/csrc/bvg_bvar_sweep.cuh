@@ -11,6 +11,7 @@
 // SV | gamma | Wishart -> store.
 #pragma once
 #include "bvg_linalg.cuh"
+#include "bvg_tiled.cuh"
 
 namespace bvg {
 
@@ -86,8 +87,8 @@ BVG_HD int bvar_state_len(int k, int T, int n, int sigma_type) {
 }
 
 // Shared-memory doubles needed per chain.
-BVG_HD int bvar_smem_len(int k, int T, int M, int n, int sigma_type, int resid_mode) {
-  int len = tri(n) + 5 * n           // L, w, a, dinv, vdiag, lam
+BVG_HD int bvar_smem_len(int k, int T, int M, int n, int sigma_type, int resid_mode, bool tiled = false) {
+  int len = (tiled ? tiled_len(n) + 8 : tri(n)) + 5 * n           // L, w, a, dinv, vdiag, lam
             + 6 * k * k + 2 * k      // sig, S, 4 k x k work, kd, kv
             + 2 * k * M;             // Dm, Wm
   if (resid_mode == RES_DIRECT || sigma_type == SIG_SV) len += k * T;                 // U
@@ -379,7 +380,9 @@ BVG_HD void sv_step(const Grp& g, const ChainRng& rng, int sweep, const BvarMode
 }
 
 // ---- the chain ---------------------------------------------------------------------------------------------
-template <int FEAT, class Grp>
+// TILED (CTA-per-chain device kernels only): L is 8 x 8 tile-packed and factorised with DMMA trailing updates
+// (bvg_tiled.cuh) instead of the row-packed Crout factorisation.
+template <int FEAT, class Grp, bool TILED = false>
 BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, const ChainRng& rng, double* state,
                        double* sm, const BvarOut& out, long long chain_local, int sweep_begin, int sweep_end,
                        int burnin) {
@@ -392,10 +395,10 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
   const double* vi_off = (FEAT & F_VIOFF) ? m.vi_off : nullptr;
   const double* vmu_off = (FEAT & F_VIOFF) ? m.vmu_off : nullptr;
   // carve shared memory
-  double* L = sm;           sm += tri(n);
+  double* L = sm;           sm += TILED ? tiled_len(n) : tri(n);
   double* w = sm;           sm += n;
   double* a = sm;           sm += n;
-  double* dinv = sm;        sm += n;
+  double* dinv = sm;        sm += TILED ? n + 8 : n;
   double* vdiag = sm;       sm += n;
   double* lam = sm;         sm += n;
   double* sig = sm;         sm += kk;
@@ -482,6 +485,9 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
       for (int r = tid; r < n; r += G) {
         const int j = r / k, i = r % k;
         double* Lr = L + tri(r);
+        // element (r, c): row-packed, or tile-packed with column stride 8 inside a tile and 64 between tiles
+        const int tbase = TILED ? ((((r >> 3) * ((r >> 3) + 1)) >> 1) << 6) + (r & 7) : 0;
+#define BVG_LSET(c, v) do { if (TILED) L[tbase + (((c) >> 3) << 6) + (((c) & 7) << 3)] = (v); else Lr[c] = (v); } while (0)
         const double lr = bvs ? lam[r] : 1.0;
         if (sv) {
           int j2 = 0, i2 = 0;
@@ -490,7 +496,7 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
             if (bvs) gv *= lr * lam[c];
             if (vi_off != nullptr) gv += vi_off[tri(r) + c];
             if (c == r) gv += vdiag[r];
-            Lr[c] = gv;
+            BVG_LSET(c, gv);
             if (++i2 == k) { i2 = 0; ++j2; }
           }
         } else {
@@ -504,21 +510,33 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
               double gv = xv * sigrow[k * i2];
               if (bvs) gv *= lr * lam[c];
               if (vi_off != nullptr) gv += vi_off[tri(r) + c];
-              Lr[c] = gv;
+              if (c == r) gv += vdiag[r];
+              BVG_LSET(c, gv);
             }
           }
-          Lr[r] += vdiag[r];
         }
+#undef BVG_LSET
         double b = w[r] * lr + vdiag[r] * cs.mu[r];
         if (vmu_off != nullptr) b += vmu_off[r];
         w[r] = b;
       }
       g.sync();
       // ---- a = L^-T (L^-1 b + eps)                                                  (bvaralg.cpp:306-307)
-      chol_crout_sel<true>(g, L, dinv, w, n, fail);
-      for (int r = tid; r < n; r += G) w[r] += a[r];            // eps drawn at the top of the sweep
-      g.sync();
-      back_solve_lt(g, L, dinv, w, a, n);
+#if defined(__CUDA_ARCH__)
+      if constexpr (TILED) {
+        tiled_finish_build(L, w, n);
+        tiled_chol(L, dinv, w, n, fail);
+        for (int r = tid; r < n; r += G) w[r] += a[r];
+        g.sync();
+        tiled_back_solve(L, dinv, w, a, n);
+      } else
+#endif
+      {
+        chol_crout_sel<true>(g, L, dinv, w, n, fail);
+        for (int r = tid; r < n; r += G) w[r] += a[r];            // eps drawn at the top of the sweep
+        g.sync();
+        back_solve_lt(g, L, dinv, w, a, n);
+      }
 
       // ---- SSVS (bvaralg.cpp:314-331)
       if (varsel == VS_SSVS) {

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128, 7) BVG_KNAME(
   bvar_chain<BVG_FEAT>(g, m, cs, rng, state + (size_t)chain * state_len, mine, out, chain, s0, s1, burnin);
 }
 #else
-__global__ void BVG_KNAME(
+__global__ void __launch_bounds__(512, 1) BVG_KNAME(
     const __grid_constant__ BvarModel m, const __grid_constant__ RngParams rp, double* state, int state_len,
     const __grid_constant__ BvarOut out, long long n_chains, int s0, int s1, int burnin, int smem_per_chain) {
   extern __shared__ double smem[];
@@ -60,7 +60,7 @@ __global__ void BVG_KNAME(
   const BvarConsts cs = stage_consts(m, smem + BVG_BLOCK_SCRATCH);
   const ChainRng rng(&rp, chain);
   double* mine = smem + BVG_BLOCK_SCRATCH + bvar_consts_len(m.k, m.M);
-  bvar_chain<BVG_FEAT>(g, m, cs, rng, state + (size_t)chain * state_len, mine, out, chain, s0, s1, burnin);
+  bvar_chain<BVG_FEAT, BlockGroup, true>(g, m, cs, rng, state + (size_t)chain * state_len, mine, out, chain, s0, s1, burnin);
 }
 #endif
 
