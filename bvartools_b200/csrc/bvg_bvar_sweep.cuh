@@ -70,7 +70,8 @@ struct BvarConsts {
   const double* XX; const double* YX; const double* Aols; const double* SSE; const double* S0;
   const double* mu; const double* vdiag0;
 };
-BVG_HD int bvar_consts_len(int k, int M) { return M * M + 2 * k * M + 2 * k * k + 2 * k * M; }
+// lean (CTA-per-chain kernels): mu and vdiag0 stay in global memory (read once per sweep and coefficient)
+BVG_HD int bvar_consts_len(int k, int M, bool lean = false) { return M * M + 2 * k * M + 2 * k * k + (lean ? 0 : 2 * k * M); }
 BVG_HD BvarConsts bvar_consts_of(const BvarModel& m) {
   BvarConsts c;
   c.XX = m.XX; c.YX = m.YX; c.Aols = m.Aols; c.SSE = m.SSE; c.S0 = m.S0; c.mu = m.mu; c.vdiag0 = m.vdiag0;
@@ -88,7 +89,7 @@ BVG_HD int bvar_state_len(int k, int T, int n, int sigma_type) {
 
 // Shared-memory doubles needed per chain.
 BVG_HD int bvar_smem_len(int k, int T, int M, int n, int sigma_type, int resid_mode, bool tiled = false) {
-  int len = (tiled ? tiled_len(n) + 8 : tri(n)) + 5 * n           // L, w, a, dinv, vdiag, lam
+  int len = (tiled ? tiled_len(n) + 8 - n : tri(n)) + 5 * n   // L, w (padded when tiled), a, dinv (not tiled), vdiag, lam
             + 6 * k * k + 2 * k      // sig, S, 4 k x k work, kd, kv
             + 2 * k * M;             // Dm, Wm
   if (resid_mode == RES_DIRECT || sigma_type == SIG_SV) len += k * T;                 // U
@@ -396,9 +397,9 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
   const double* vmu_off = (FEAT & F_VIOFF) ? m.vmu_off : nullptr;
   // carve shared memory
   double* L = sm;           sm += TILED ? tiled_len(n) : tri(n);
-  double* w = sm;           sm += n;
+  double* w = sm;           sm += TILED ? n + 8 : n;
   double* a = sm;           sm += n;
-  double* dinv = sm;        sm += TILED ? n + 8 : n;
+  double* dinv = sm;        sm += TILED ? 0 : n;
   double* vdiag = sm;       sm += n;
   double* lam = sm;         sm += n;
   double* sig = sm;         sm += kk;
@@ -525,10 +526,10 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
 #if defined(__CUDA_ARCH__)
       if constexpr (TILED) {
         tiled_finish_build(L, w, n);
-        tiled_chol(L, dinv, w, n, fail);
+        tiled_chol(L, w, n, fail);
         for (int r = tid; r < n; r += G) w[r] += a[r];
         g.sync();
-        tiled_back_solve(L, dinv, w, a, n);
+        tiled_back_solve(L, w, a, n);
       } else
 #endif
       {

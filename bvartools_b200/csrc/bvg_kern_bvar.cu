@@ -16,7 +16,7 @@
 namespace bvg {
 
 // copy the read-only tables of the model into the CTA's shared memory (all threads; ends with a CTA barrier)
-__device__ __forceinline__ BvarConsts stage_consts(const BvarModel& m, double* dst) {
+__device__ __forceinline__ BvarConsts stage_consts(const BvarModel& m, double* dst, bool lean = false) {
   BvarConsts c;
   const int k = m.k, M = m.M, n = m.n;
   const double* src[7] = {m.XX, m.YX, m.Aols, m.SSE, m.S0, m.mu, m.vdiag0};
@@ -24,6 +24,7 @@ __device__ __forceinline__ BvarConsts stage_consts(const BvarModel& m, double* d
   const double** out[7] = {&c.XX, &c.YX, &c.Aols, &c.SSE, &c.S0, &c.mu, &c.vdiag0};
 #pragma unroll
   for (int a = 0; a < 7; ++a) {
+    if (lean && a >= 5) { *out[a] = src[a]; continue; }           // mu, vdiag0 stay in global memory
     if (src[a] != nullptr)
       for (int e = threadIdx.x; e < len[a]; e += blockDim.x) dst[e] = src[a][e];
     *out[a] = (src[a] != nullptr) ? dst : nullptr;
@@ -57,9 +58,9 @@ __global__ void __launch_bounds__(512, 1) BVG_KNAME(
   const long long chain = blockIdx.x;
   if (chain >= n_chains) return;
   BlockGroup g(smem);
-  const BvarConsts cs = stage_consts(m, smem + BVG_BLOCK_SCRATCH);
+  const BvarConsts cs = stage_consts(m, smem + BVG_BLOCK_SCRATCH, true);
   const ChainRng rng(&rp, chain);
-  double* mine = smem + BVG_BLOCK_SCRATCH + bvar_consts_len(m.k, m.M);
+  double* mine = smem + BVG_BLOCK_SCRATCH + bvar_consts_len(m.k, m.M, true);
   bvar_chain<BVG_FEAT, BlockGroup, true>(g, m, cs, rng, state + (size_t)chain * state_len, mine, out, chain, s0, s1, burnin);
 }
 #endif

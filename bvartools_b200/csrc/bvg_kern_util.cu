@@ -41,11 +41,11 @@ cudaError_t plan_bvar(const BvarModel& m, long long n_chains, int requested_tpc,
   int per = bvar_smem_len(m.k, m.T, m.M, m.n, m.sigma_type, m.resid_mode);
   int tpc = requested_tpc;
   if (tpc <= 0) {
-    if ((size_t)per * 8 > 24 * 1024 || m.n > 64) tpc = (m.n > 96) ? 512 : 128;   // one CTA per chain
+    if ((size_t)per * 8 > 24 * 1024 || m.n > 64) tpc = (m.n > 96) ? 256 : 128;   // one CTA per chain (n = 150: two CTAs per SM)
     else tpc = pick_tile(m.n > m.k ? m.n : m.k);
   }
   if (tpc > 32) per = bvar_smem_len(m.k, m.T, m.M, m.n, m.sigma_type, m.resid_mode, true);   // tile-packed factor
-  return finish_plan(plan, per, n_chains, tpc, bvar_consts_len(m.k, m.M));
+  return finish_plan(plan, per, n_chains, tpc, bvar_consts_len(m.k, m.M, tpc > 32));
 }
 
 cudaError_t plan_tvp(const TvpModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan) {

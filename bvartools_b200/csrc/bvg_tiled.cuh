@@ -3,10 +3,17 @@
 // constant-parameter sweep (config c3: n = 150) in place of the row-cyclic Crout factorisation, whose n^2/2 dependent
 // dot products per sweep left the SM idle.  Device only.
 //
-// Layout: the matrix is padded to nt = ceil(n / 8) tile rows plus ONE extra tile row that carries the right-hand side
-// b' in its first row (augmented system: after the factorisation that row holds w' = (L^-1 b)').  Tile (I, J), J <= I,
-// lives at ((I (I + 1) / 2 + J) * 64, column-major inside the tile (element (i, j) at j * 8 + i): a warp reads a DMMA
-// A/B fragment (32 doubles) from one contiguous, conflict-free half tile.  The padding rows are an identity block.
+// Layout: the matrix is padded to nt = ceil(n / 8) tile rows.  Tile (I, J), J <= I, lives at (I (I + 1) / 2 + J) * 64,
+// column-major inside the tile (element (i, j) at j * 8 + i): a warp reads a DMMA A/B fragment (32 doubles) from one
+// contiguous, conflict-free half tile.  The padding rows are an identity block.  The right-hand side b (npad doubles,
+// zero padded) is carried along: on exit it holds w = L^-1 b.
+//
+// Algorithm (right-looking with look-ahead), per tile column p:
+//   panel     L(I,p) = A(I,p) T_p'  with T_p = L(p,p)^-1  -- two DMMAs per tile, no dependent substitution chain
+//   trailing  A(I,J) -= L(I,p) L(J,p)'                     -- two DMMAs per tile, accumulating into the tile
+//   look-ahead: warp 0 updates tile (p+1,p+1) first and factorises + inverts it in registers (row per lane, shuffle
+//   broadcasts) while the other warps finish the trailing update.  T_p overwrites the diagonal tile (L(p,p) itself is
+//   not needed again: the back substitution uses T_p' as well).
 // Reference call sites: arma::chol + arma::solve in bvaralg.cpp:306-307.
 #pragma once
 #include "bvg_group.cuh"
@@ -14,7 +21,7 @@
 namespace bvg {
 
 BVG_HD int tiled_nt(int n) { return (n + 7) >> 3; }
-BVG_HD int tiled_len(int n) { const int r = tiled_nt(n) + 1; return ((r * (r + 1)) >> 1) * 64; }
+BVG_HD int tiled_len(int n) { const int r = tiled_nt(n); return ((r * (r + 1)) >> 1) * 64; }
 BVG_HD int tiled_idx(int i, int j) {      // element (i, j), j <= i (tile-wise: J <= I)
   const int I = i >> 3, J = j >> 3;
   return ((((I * (I + 1)) >> 1) + J) << 6) + ((j & 7) << 3) + (i & 7);
@@ -22,113 +29,144 @@ BVG_HD int tiled_idx(int i, int j) {      // element (i, j), j <= i (tile-wise: 
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ void tiled_dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// identity padding + rhs row; call after the n x n lower triangle has been written, before tiled_chol
-__device__ __forceinline__ void tiled_finish_build(double* L, const double* b, int n) {
+// identity padding rows and zero padding of the right-hand side b (length npad); call after the n x n lower triangle
+// and b[0..n) have been written, before tiled_chol
+__device__ __forceinline__ void tiled_finish_build(double* L, double* b, int n) {
   const int nt = tiled_nt(n), npad = nt * 8, tid = threadIdx.x, G = blockDim.x;
-  // padding rows n .. npad-1 (inside the last tile row) and the upper part of diagonal tiles are never read except
-  // through whole-tile DMMA operands: zero the padding rows, unit diagonal
   for (int e = tid; e < (npad - n) * npad; e += G) {
     const int i = n + e / npad, j = e % npad;
     if (j <= i) L[tiled_idx(i, j)] = (i == j) ? 1.0 : 0.0;
   }
-  // strict upper triangle inside the diagonal tiles (read by the panel solve of nothing, but keep it clean)
-  for (int e = tid; e < nt * 64; e += G) {
-    const int I = e >> 6, jj = (e >> 3) & 7, ii = e & 7;
-    if (jj > ii) L[(((I * (I + 1)) >> 1) + I) * 64 + jj * 8 + ii] = 0.0;
-  }
-  // augmented tile row nt: row 0 = b', rows 1..7 = 0
-  for (int e = tid; e < npad * 8; e += G) {
-    const int j = e >> 3, ii = e & 7;
-    L[tiled_idx(npad + ii, j)] = (ii == 0 && j < n) ? b[j] : 0.0;
-  }
+  for (int e = n + tid; e < npad; e += G) b[e] = 0.0;
   __syncthreads();
 }
 
-// In-place Cholesky of the tile-packed matrix (true diagonal stored, dinv[j] = 1 / L_jj), rhs carried in the
-// augmented row: on exit w[j] = (L^-1 b)_j.  fail is set on a non-positive pivot.
-static __device__ __noinline__ void tiled_chol(double* L, double* dinv, double* w, int n, int& fail) {
+// One warp: Cholesky of the 8 x 8 diagonal tile D (lower part valid) and T = L^-1, written over D with an exactly
+// zero upper triangle.  Lane i (mod 8) keeps row i in registers; pivots and multipliers travel by shuffle.
+__device__ __forceinline__ void tiled_factor_invert(double* D, int& fail) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, i = lane & 7;
+  double a[8], rsv[8], x[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) a[c] = D[c * 8 + i];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const double d = __shfl_sync(FULL, a[j], j);
+    if (!(d > 0.0)) fail = 1;
+    const double rs = rsqrt(d);
+    rsv[j] = rs;
+    const double l = a[j] * rs;          // lane i >= j: L_ij   (lane j: sqrt(d))
+    a[j] = l;
+#pragma unroll
+    for (int c = j + 1; c < 8; ++c) a[c] = fma(-l, __shfl_sync(FULL, l, c), a[c]);
+  }
+  // column c = i of T: x_c = 1 / L_cc, x_r = -(sum_{c <= m < r} L_rm x_m) / L_rr
+#pragma unroll
+  for (int r = 0; r < 8; ++r) x[r] = (r == i) ? rsv[r] : 0.0;
+#pragma unroll
+  for (int r = 1; r < 8; ++r) {
+    double s = 0.0;
+#pragma unroll
+    for (int m = 0; m < r; ++m) s = fma(__shfl_sync(FULL, a[m], r), x[m], s);
+    if (r > i) x[r] = -rsv[r] * s;
+  }
+  __syncwarp();
+  if (lane < 8) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) D[i * 8 + r] = x[r];
+  }
+}
+
+// In-place Cholesky of the tile-packed matrix.  On exit the strictly-lower tiles hold L, the diagonal tiles hold
+// L(p,p)^-1, and b holds w = L^-1 b.  fail is set on a non-positive pivot.
+static __device__ __noinline__ void tiled_chol(double* L, double* b, int n, int& fail) {
   const int nt = tiled_nt(n), npad = nt * 8, tid = threadIdx.x, G = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = G >> 5;
   const int fr = lane >> 2, fk = lane & 3;
+  const int fo0 = fk * 8 + fr, fo1 = (4 + fk) * 8 + fr, co = (2 * fk) * 8 + fr;
+  if (warp == 0) tiled_factor_invert(L, fail);
+  __syncthreads();
   for (int p = 0; p < nt; ++p) {
-    double* D = L + (((p * (p + 1)) >> 1) + p) * 64;             // diagonal tile
-    // 1. factor the 8 x 8 diagonal tile (warp 0): lane i owns row i
-    if (warp == 0) {
-      for (int j = 0; j < 8; ++j) {
-        const double d = D[j * 8 + j];
-        __syncwarp();                                             // every lane has read the pivot before it is replaced
-        if (!(d > 0.0)) fail = 1;
-        const double rs = rsqrt(d);
-        if (lane == j) { D[j * 8 + j] = d * rs; dinv[p * 8 + j] = rs; }
-        else if (lane > j && lane < 8) D[j * 8 + lane] *= rs;
+    const double* Ti = L + (((p * (p + 1)) >> 1) + p) * 64;      // T_p = L(p,p)^-1
+    // ---- panel: L(I,p) = A(I,p) T_p', one tile per warp and pass; the last warp also maps the rhs block
+    {
+      const double t0 = Ti[fo0], t1 = Ti[fo1];                    // B fragment: B[k][n] = T[n][k]
+      for (int I = p + 1 + warp; I < nt; I += nwarp) {
+        double* TA = L + (((I * (I + 1)) >> 1) + p) * 64;
+        double c0 = 0.0, c1 = 0.0;
+        tiled_dmma(c0, c1, TA[fo0], t0);
+        tiled_dmma(c0, c1, TA[fo1], t1);
+        TA[co] = c0;
+        TA[co + 8] = c1;
+      }
+      if (warp == nwarp - 1) {
+        double s = 0.0;
+        const int i = lane & 7;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s = fma(Ti[c * 8 + i], b[p * 8 + c], s);
         __syncwarp();
-        // trailing 8 x 8 update: 64 elements over 32 lanes
-        for (int e = lane; e < 64; e += 32) {
-          const int i = e & 7, c = e >> 3;
-          if (c > j && i >= c) D[c * 8 + i] = fma(-D[j * 8 + i], D[j * 8 + c], D[c * 8 + i]);
-        }
-        __syncwarp();
+        if (lane < 8) b[p * 8 + i] = s;                           // w_p = T_p b_p
       }
     }
     __syncthreads();
-    // 2. panel: rows below the diagonal tile (incl. the rhs row), L(I,p) = A(I,p) L(p,p)^-T by forward substitution
-    const int rows_below = (npad + 8) - (p + 1) * 8;
-    for (int rr = tid; rr < rows_below; rr += G) {
-      const int i = (p + 1) * 8 + rr;
-      double* R = L + tiled_idx(i, p * 8);                        // element (i, 8p); next column is +8
-      double x[8];
+    if (p + 1 == nt) break;
+    // ---- trailing update of the rows below: rhs first, then the tiles
+    for (int r = (p + 1) * 8 + tid; r < npad; r += G) {
+      const double* R = L + tiled_idx(r, p * 8);                  // element (r, 8p); next column is +8
+      double s = b[r];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        double s = R[j * 8];
-#pragma unroll
-        for (int c = 0; c < j; ++c) s = fma(-x[c], D[c * 8 + j], s);
-        x[j] = s * dinv[p * 8 + j];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) R[j * 8] = x[j];
+      for (int c = 0; c < 8; ++c) s = fma(-R[c * 8], b[p * 8 + c], s);
+      b[r] = s;
     }
-    __syncthreads();
-    // 3. trailing update C(I,J) -= L(I,p) L(J,p)' for p < J <= I <= nt (the rhs tile row takes part, its own
-    //    diagonal tile (nt, nt) does not exist), one tile per warp and pass
-    const int m = nt - p;                                         // tile rows p+1 .. nt  -> m rows
-    const int ntile = ((m * (m + 1)) >> 1) - 1;                   // minus the (nt, nt) corner
-    for (int t = warp; t < ntile; t += nwarp) {
-      int a = 0;
-      while (((a + 1) * (a + 2)) >> 1 <= t) ++a;
-      const int bcol = t - ((a * (a + 1)) >> 1);
-      const int I = p + 1 + a, J = p + 1 + bcol;
+    const int m = nt - 1 - p;                                     // tile rows p+1 .. nt-1
+    const int ntile = (m * (m + 1)) >> 1;
+    // tile t = a (a + 1) / 2 + bc  <->  (I, J) = (p + 1 + a, p + 1 + bc); t = 0 is the next diagonal tile
+    int t, stride;
+    if (nwarp == 1) { t = 0; stride = 1; }
+    else if (warp == 0) { t = 0; stride = ntile; }                // warp 0: tile (p+1,p+1) only, then the look-ahead
+    else { t = warp; stride = nwarp - 1; }
+    int a = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while (((a + 1) * (a + 2)) >> 1 <= t) ++a;
+    while (((a * (a + 1)) >> 1) > t) --a;
+    int bc = t - ((a * (a + 1)) >> 1);
+    for (; t < ntile; t += stride) {
+      const int I = p + 1 + a, J = p + 1 + bc;
       const double* TA = L + (((I * (I + 1)) >> 1) + p) * 64;
-      const double* TBt = L + (((J * (J + 1)) >> 1) + p) * 64;
-      double* C = L + (((I * (I + 1)) >> 1) + J) * 64 + (2 * fk) * 8 + fr;
-      double c0 = 0.0, c1 = 0.0;
-      tiled_dmma(c0, c1, TA[fk * 8 + fr], TBt[fk * 8 + fr]);
-      tiled_dmma(c0, c1, TA[(4 + fk) * 8 + fr], TBt[(4 + fk) * 8 + fr]);
-      C[0] -= c0;
-      C[8] -= c1;
+      const double* TB = L + (((J * (J + 1)) >> 1) + p) * 64;
+      double* C = L + (((I * (I + 1)) >> 1) + J) * 64 + co;
+      double c0 = C[0], c1 = C[8];
+      tiled_dmma(c0, c1, -TA[fo0], TB[fo0]);
+      tiled_dmma(c0, c1, -TA[fo1], TB[fo1]);
+      C[0] = c0;
+      C[8] = c1;
+      bc += stride;
+      while (bc > a) { bc -= a + 1; ++a; }
+    }
+    if (warp == 0) {
+      __syncwarp();
+      tiled_factor_invert(L + ((((p + 1) * (p + 2)) >> 1) + p + 1) * 64, fail);
     }
     __syncthreads();
   }
-  for (int j = tid; j < n; j += G) w[j] = L[tiled_idx(npad, j)];
-  __syncthreads();
 }
 
-// a = L^-T v (back substitution with the transposed factor); v (n, shared) is destroyed.
-static __device__ __noinline__ void tiled_back_solve(const double* L, const double* dinv, double* v, double* a, int n) {
+// a = L^-T v (back substitution with the transposed factor; diagonal tiles hold L(p,p)^-1); v (npad, shared, zero
+// padded) is destroyed.
+static __device__ __noinline__ void tiled_back_solve(const double* L, double* v, double* a, int n) {
   const int nt = tiled_nt(n), tid = threadIdx.x, G = blockDim.x, lane = tid & 31, warp = tid >> 5;
   for (int p = nt - 1; p >= 0; --p) {
-    const double* D = L + (((p * (p + 1)) >> 1) + p) * 64;
+    const double* Ti = L + (((p * (p + 1)) >> 1) + p) * 64;
     if (warp == 0) {
-      // x_p = L(p,p)^-T v_p: 8 dependent steps, lane c keeps v[8p + c]
-      double vc = (lane < 8 && p * 8 + lane < n) ? v[p * 8 + lane] : 0.0;
-      for (int i = 7; i >= 0; --i) {
-        const double xi = __shfl_sync(0xffffffffu, vc, i) * dinv[p * 8 + i];
-        if (lane < i) vc = fma(-D[lane * 8 + i], xi, vc);          // L[i][lane]
-        if (lane == i) vc = xi;
-      }
-      if (lane < 8 && p * 8 + lane < n) { v[p * 8 + lane] = vc; a[p * 8 + lane] = vc; }
+      // x_p = T_p' v_p
+      const int i = lane & 7;
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) s = fma(Ti[i * 8 + r], v[p * 8 + r], s);
+      __syncwarp();
+      if (lane < 8) { v[p * 8 + i] = s; if (p * 8 + i < n) a[p * 8 + i] = s; }
     }
     __syncthreads();
     // v_c -= sum_{r in tile row p} L[r][c] x[r]  for the columns c < 8p
@@ -136,7 +174,7 @@ static __device__ __noinline__ void tiled_back_solve(const double* L, const doub
       const double* R = L + tiled_idx(p * 8, c);                   // element (8p, c); next row is +1
       double s = v[c];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) s = fma(-R[r], (p * 8 + r < n) ? v[p * 8 + r] : 0.0, s);
+      for (int r = 0; r < 8; ++r) s = fma(-R[r], v[p * 8 + r], s);
       v[c] = s;
     }
     __syncthreads();

@@ -66,6 +66,9 @@ tsamp = sum(samp_line.values()) or 1
 print("--- by source line (inst%, stall-sample%)")
 for line, n in per_line.most_common(top):
     print(f"{100 * n / tot:6.2f}%  {100 * samp_line[line] / tsamp:6.2f}%  {line[0] if line else '?'}:{line[1] if line else 0}")
+print("--- by source line, sorted by stall samples (stall-sample%, inst%)")
+for line, n in samp_line.most_common(top):
+    print(f"{100 * n / tsamp:6.2f}%  {100 * per_line[line] / tot:6.2f}%  {line[0] if line else '?'}:{line[1] if line else 0}")
 print("--- by opcode")
 for op, n in per_op.most_common(25):
     print(f"{100 * n / tot:6.2f}%  {op}")
