@@ -380,6 +380,43 @@ BVG_HD void sv_step(const Grp& g, const ChainRng& rng, int sweep, const BvarMode
   g.sync();
 }
 
+#if defined(__CUDACC__)
+// Tile-packed precision matrix for the CTA-per-chain kernels (bvg_tiled.cuh): P = V^-1 + Lambda (z'Dz) Lambda written
+// half tile by half tile (a warp stores 32 consecutive doubles: no bank conflicts, no per-row imbalance), identity
+// padding rows included.  GW != nullptr: SV form (block-diagonal weights), else XX' (x) Sigma^-1.   (bvaralg.cpp:303-305)
+__device__ __forceinline__ void tiled_build_precision(double* L, int n, int k, int M, const double* XX, const double* sig,
+                                                      const double* GW, const double* vdiag, const double* lam_bvs,
+                                                      const double* vi_off) {
+  const int nt = tiled_nt(n), lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int li = lane & 7, lj = lane >> 3;
+  const float kinv = 1.0f / (float)k;
+  const int triM = tri(M);
+  for (int I = warp; I < nt; I += nwarp) {
+    const int r = 8 * I + li;
+    const int jr = (int)(((float)r + 0.5f) * kinv), ir = r - jr * k;
+    const double lr = (lam_bvs != nullptr && r < n) ? lam_bvs[r] : 1.0;
+    double* row = L + (((I * (I + 1)) >> 1) << 6) + lane;
+    for (int J = 0; J <= I; ++J) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = 8 * J + lj + 4 * h;
+        double gv = 0.0;
+        if (r >= n) gv = (c == r) ? 1.0 : 0.0;
+        else if (c <= r) {
+          const int jc = (int)(((float)c + 0.5f) * kinv), ic = c - jc * k;
+          if (GW != nullptr) gv = (ir == ic) ? GW[ir * triM + tri(jr) + jc] : 0.0;
+          else gv = XX[jr + M * jc] * sig[ir + k * ic];
+          if (lam_bvs != nullptr) gv *= lr * lam_bvs[c];
+          if (vi_off != nullptr) gv += vi_off[tri(r) + c];
+          if (c == r) gv += vdiag[r];
+        }
+        row[J * 64 + 32 * h] = gv;
+      }
+    }
+  }
+}
+#endif
+
 // ---- the chain ---------------------------------------------------------------------------------------------
 // TILED (CTA-per-chain device kernels only): L is 8 x 8 tile-packed and factorised with DMMA trailing updates
 // (bvg_tiled.cuh) instead of the row-packed Crout factorisation.
@@ -483,49 +520,61 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
         }
       }
       const bool bvs = varsel == VS_BVS;
-      for (int r = tid; r < n; r += G) {
-        const int j = r / k, i = r % k;
-        double* Lr = L + tri(r);
-        // element (r, c): row-packed, or tile-packed with column stride 8 inside a tile and 64 between tiles
-        const int tbase = TILED ? ((((r >> 3) * ((r >> 3) + 1)) >> 1) << 6) + (r & 7) : 0;
-#define BVG_LSET(c, v) do { if (TILED) L[tbase + (((c) >> 3) << 6) + (((c) & 7) << 3)] = (v); else Lr[c] = (v); } while (0)
-        const double lr = bvs ? lam[r] : 1.0;
-        if (sv) {
-          int j2 = 0, i2 = 0;
-          for (int c = 0; c <= r; ++c) {
-            double gv = (i == i2) ? GW[i * tri(M) + tri(j) + j2] : 0.0;
-            if (bvs) gv *= lr * lam[c];
-            if (vi_off != nullptr) gv += vi_off[tri(r) + c];
-            if (c == r) gv += vdiag[r];
-            BVG_LSET(c, gv);
-            if (++i2 == k) { i2 = 0; ++j2; }
+#if defined(__CUDA_ARCH__)
+      if constexpr (TILED) {
+        for (int r = tid; r < tiled_nt(n) * 8; r += G) {
+          double b = 0.0;                                          // zero padding of the rhs
+          if (r < n) {
+            b = w[r] * (bvs ? lam[r] : 1.0) + vdiag[r] * cs.mu[r];
+            if (vmu_off != nullptr) b += vmu_off[r];
           }
-        } else {
-          // row (j,i) of (XX' (x) Sigma^-1): one XX entry per regressor block, k products each
-          const double* sigrow = sig + i;
-          int c = 0;
-          for (int j2 = 0; j2 <= j; ++j2) {
-            const double xv = cs.XX[j + M * j2];
-            const int i2max = (j2 < j) ? k - 1 : i;
-            for (int i2 = 0; i2 <= i2max; ++i2, ++c) {
-              double gv = xv * sigrow[k * i2];
+          w[r] = b;
+        }
+        tiled_build_precision(L, n, k, M, cs.XX, sig, sv ? GW : nullptr, vdiag, bvs ? lam : nullptr, vi_off);
+      } else
+#endif
+      {
+        for (int r = tid; r < n; r += G) {
+          const int j = r / k, i = r % k;
+          double* Lr = L + tri(r);
+#define BVG_LSET(c, v) Lr[c] = (v)
+          const double lr = bvs ? lam[r] : 1.0;
+          if (sv) {
+            int j2 = 0, i2 = 0;
+            for (int c = 0; c <= r; ++c) {
+              double gv = (i == i2) ? GW[i * tri(M) + tri(j) + j2] : 0.0;
               if (bvs) gv *= lr * lam[c];
               if (vi_off != nullptr) gv += vi_off[tri(r) + c];
               if (c == r) gv += vdiag[r];
               BVG_LSET(c, gv);
+              if (++i2 == k) { i2 = 0; ++j2; }
+            }
+          } else {
+            // row (j,i) of (XX' (x) Sigma^-1): one XX entry per regressor block, k products each
+            const double* sigrow = sig + i;
+            int c = 0;
+            for (int j2 = 0; j2 <= j; ++j2) {
+              const double xv = cs.XX[j + M * j2];
+              const int i2max = (j2 < j) ? k - 1 : i;
+              for (int i2 = 0; i2 <= i2max; ++i2, ++c) {
+                double gv = xv * sigrow[k * i2];
+                if (bvs) gv *= lr * lam[c];
+                if (vi_off != nullptr) gv += vi_off[tri(r) + c];
+                if (c == r) gv += vdiag[r];
+                BVG_LSET(c, gv);
+              }
             }
           }
-        }
 #undef BVG_LSET
-        double b = w[r] * lr + vdiag[r] * cs.mu[r];
-        if (vmu_off != nullptr) b += vmu_off[r];
-        w[r] = b;
+          double b = w[r] * lr + vdiag[r] * cs.mu[r];
+          if (vmu_off != nullptr) b += vmu_off[r];
+          w[r] = b;
+        }
       }
       g.sync();
       // ---- a = L^-T (L^-1 b + eps)                                                  (bvaralg.cpp:306-307)
 #if defined(__CUDA_ARCH__)
       if constexpr (TILED) {
-        tiled_finish_build(L, w, n);
         tiled_chol(L, w, n, fail);
         for (int r = tid; r < n; r += G) w[r] += a[r];
         g.sync();
@@ -720,8 +769,19 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
         }
         g.sync();
         if (keep) {
-          small_spd_inverse(g, sig, W4, W1, W2, W3, kd, k, fail);                         // :528
-          for (int e = tid; e < kk; e += G) out_sig[e] = W4[e];
+#if defined(__CUDA_ARCH__)
+          if constexpr (Grp::kIsBlock) {
+            if (tid < 32) {
+              const TileGroup<32> wg;
+              small_spd_inverse(wg, sig, W4, W1, W2, W3, kd, k, fail);
+              for (int e = tid; e < kk; e += 32) out_sig[e] = W4[e];
+            }
+          } else
+#endif
+          {
+            small_spd_inverse(g, sig, W4, W1, W2, W3, kd, k, fail);                       // :528
+            for (int e = tid; e < kk; e += G) out_sig[e] = W4[e];
+          }
         }
       } else {
         for (int e = tid; e < kk; e += G) S[e] += cs.S0[e];
@@ -737,8 +797,19 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
             default: wishart_block_reg<4>(g, rng, sweep, m.wish_df_post, S, W4, kv, kd, sig, out_sig, fail); break;
           }
         } else {
-          wishart_block(g, rng, sweep, k, m.wish_df_post, S, sig, W4, keep, W1, W2, W3, W4 /*A then Sigma*/, kd, fail);
-          if (keep) for (int e = tid; e < kk; e += G) out_sig[e] = W4[e];
+#if defined(__CUDA_ARCH__)
+          if constexpr (Grp::kIsBlock) {
+            if (tid < 32) {      // one warp, warp-level barriers only; the CTA meets again at the sync below
+              const TileGroup<32> wg;
+              wishart_block(wg, rng, sweep, k, m.wish_df_post, S, sig, W4, keep, W1, W2, W3, W4, kd, fail);
+              if (keep) for (int e = tid; e < kk; e += 32) out_sig[e] = W4[e];
+            }
+          } else
+#endif
+          {
+            wishart_block(g, rng, sweep, k, m.wish_df_post, S, sig, W4, keep, W1, W2, W3, W4 /*A then Sigma*/, kd, fail);
+            if (keep) for (int e = tid; e < kk; e += G) out_sig[e] = W4[e];
+          }
         }
       }
       g.sync();

@@ -45,11 +45,12 @@ __device__ __forceinline__ void tiled_finish_build(double* L, double* b, int n) 
 }
 
 // One warp: Cholesky of the 8 x 8 diagonal tile D (lower part valid) and T = L^-1, written over D with an exactly
-// zero upper triangle.  Lane i (mod 8) keeps row i in registers; pivots and multipliers travel by shuffle.
+// zero upper triangle.  Lane i (mod 8) keeps row i in registers; pivots and multipliers travel by shuffle; row j of
+// T is formed as soon as row j of L is final so that its arithmetic hides behind the next pivot's rsqrt.
 __device__ __forceinline__ void tiled_factor_invert(double* D, int& fail) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, i = lane & 7;
-  double a[8], rsv[8], x[8];
+  double a[8], x[8];      // a: row i of the tile / of L;  x: column i of T (x[r] = T[r][i])
 #pragma unroll
   for (int c = 0; c < 8; ++c) a[c] = D[c * 8 + i];
 #pragma unroll
@@ -57,21 +58,19 @@ __device__ __forceinline__ void tiled_factor_invert(double* D, int& fail) {
     const double d = __shfl_sync(FULL, a[j], j);
     if (!(d > 0.0)) fail = 1;
     const double rs = rsqrt(d);
-    rsv[j] = rs;
     const double l = a[j] * rs;          // lane i >= j: L_ij   (lane j: sqrt(d))
     a[j] = l;
+    if (j < 7) a[j + 1] = fma(-l, __shfl_sync(FULL, l, j + 1), a[j + 1]);   // next pivot column first
 #pragma unroll
-    for (int c = j + 1; c < 8; ++c) a[c] = fma(-l, __shfl_sync(FULL, l, c), a[c]);
-  }
-  // column c = i of T: x_c = 1 / L_cc, x_r = -(sum_{c <= m < r} L_rm x_m) / L_rr
+    for (int c = j + 2; c < 8; ++c) a[c] = fma(-l, __shfl_sync(FULL, l, c), a[c]);
+    // row j of T: T[j][i] = -(sum_{i <= m < j} L_jm T[m][i]) / L_jj  (i < j),  1 / L_jj  (i = j),  0  (i > j)
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-  for (int r = 0; r < 8; ++r) x[r] = (r == i) ? rsv[r] : 0.0;
-#pragma unroll
-  for (int r = 1; r < 8; ++r) {
-    double s = 0.0;
-#pragma unroll
-    for (int m = 0; m < r; ++m) s = fma(__shfl_sync(FULL, a[m], r), x[m], s);
-    if (r > i) x[r] = -rsv[r] * s;
+    for (int m = 0; m < j; ++m) {
+      const double ljm = __shfl_sync(FULL, a[m], j);
+      if (m & 1) s1 = fma(ljm, x[m], s1); else s0 = fma(ljm, x[m], s0);
+    }
+    x[j] = (i == j) ? rs : ((i < j) ? -rs * (s0 + s1) : 0.0);
   }
   __syncwarp();
   if (lane < 8) {
@@ -80,76 +79,116 @@ __device__ __forceinline__ void tiled_factor_invert(double* D, int& fail) {
   }
 }
 
-// In-place Cholesky of the tile-packed matrix.  On exit the strictly-lower tiles hold L, the diagonal tiles hold
-// L(p,p)^-1, and b holds w = L^-1 b.  fail is set on a non-positive pivot.
-static __device__ __noinline__ void tiled_chol(double* L, double* b, int n, int& fail) {
-  const int nt = tiled_nt(n), npad = nt * 8, tid = threadIdx.x, G = blockDim.x;
+#ifdef BVG_TILED_PROF   // tools/micro/chol_prof.cu: cycles per phase seen by thread 0 (slots 0-3) and by warp 1 (4-5)
+#define BVG_TP(slot) do { if (prof != nullptr && (tid == 0 || tid == 32)) { const long long now_ = clock64(); if ((slot) >= 0 && (tid == 0) == ((slot) < 4 || (slot) == 6)) prof[slot] += now_ - tp_; tp_ = now_; } } while (0)
+#define BVG_TP_ARG , long long* prof
+#define BVG_TP_INIT long long tp_ = clock64();
+#else
+#define BVG_TP(slot) do { } while (0)
+#define BVG_TP_ARG
+#define BVG_TP_INIT
+#endif
+
+// In-place Cholesky of the tile-packed matrix, left-looking by tile column with the accumulators in registers (no
+// read-modify-write of the trailing matrix in shared memory), except the diagonal tiles, which are kept up to date
+// right-looking so that warp 0 can start on the next one without an accumulation pass.  On exit the strictly-lower tiles hold L, the diagonal
+// tiles hold L(J,J)^-1, and b holds w = L^-1 b.  fail is set on a non-positive pivot.
+static __device__ __noinline__ void tiled_chol(double* L, double* b, int n, int& fail BVG_TP_ARG) {
+  const int nt = tiled_nt(n), tid = threadIdx.x, G = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = G >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   const int fo0 = fk * 8 + fr, fo1 = (4 + fk) * 8 + fr, co = (2 * fk) * 8 + fr;
-  if (warp == 0) tiled_factor_invert(L, fail);
-  __syncthreads();
-  for (int p = 0; p < nt; ++p) {
-    const double* Ti = L + (((p * (p + 1)) >> 1) + p) * 64;      // T_p = L(p,p)^-1
-    // ---- panel: L(I,p) = A(I,p) T_p', one tile per warp and pass; the last warp also maps the rhs block
+  const bool solo = (nwarp == 1);
+  const int nwork = solo ? 1 : nwarp - 1;                         // warps 1.. (warp 0 owns the diagonal tile)
+  const int wid = solo ? 0 : warp - 1;
+  BVG_TP_INIT
+  for (int J = 0; J < nt; ++J) {
+    double* rowJ = L + ((J * (J + 1)) >> 1) * 64;
+    double* D = rowJ + J * 64;
+    // ---- phase 1: A(I,J) -= sum_{q<J} L(I,q) L(J,q)' for I > J; warp 0 factorises the diagonal tile, which is
+    //      already up to date (the panel phase applies every column to the diagonal tiles below it)
+    if (warp == 0) {
+      tiled_factor_invert(D, fail);
+      BVG_TP(2);
+    }
+    if (warp != 0 || solo) {
+      for (int I = J + 1 + wid; I < nt; I += 2 * nwork) {
+        const int I2 = I + nwork;
+        double* r1 = L + ((I * (I + 1)) >> 1) * 64;
+        if (I2 < nt) {                                            // two row tiles share the L(J,q) fragments
+          double* r2 = L + ((I2 * (I2 + 1)) >> 1) * 64;
+          double c0 = r1[J * 64 + co], c1 = r1[J * 64 + co + 8], e0 = 0.0, e1 = 0.0;
+          double g0 = r2[J * 64 + co], g1 = r2[J * 64 + co + 8], h0 = 0.0, h1 = 0.0;
+#pragma unroll 2
+          for (int q = 0; q < J; ++q) {
+            const double v0 = rowJ[q * 64 + fo0], v1 = rowJ[q * 64 + fo1];
+            const double u0 = r1[q * 64 + fo0], u1 = r1[q * 64 + fo1];
+            const double y0 = r2[q * 64 + fo0], y1 = r2[q * 64 + fo1];
+            tiled_dmma(c0, c1, -u0, v0);
+            tiled_dmma(e0, e1, -u1, v1);
+            tiled_dmma(g0, g1, -y0, v0);
+            tiled_dmma(h0, h1, -y1, v1);
+          }
+          r1[J * 64 + co] = c0 + e0;  r1[J * 64 + co + 8] = c1 + e1;
+          r2[J * 64 + co] = g0 + h0;  r2[J * 64 + co + 8] = g1 + h1;
+        } else {
+          double c0 = r1[J * 64 + co], c1 = r1[J * 64 + co + 8], e0 = 0.0, e1 = 0.0;
+#pragma unroll 4
+          for (int q = 0; q < J; ++q) {
+            const double v0 = rowJ[q * 64 + fo0], v1 = rowJ[q * 64 + fo1];
+            tiled_dmma(c0, c1, -r1[q * 64 + fo0], v0);
+            tiled_dmma(e0, e1, -r1[q * 64 + fo1], v1);
+          }
+          r1[J * 64 + co] = c0 + e0;  r1[J * 64 + co + 8] = c1 + e1;
+        }
+      }
+      if (wid == nwork - 1) {
+        // rhs: b_J -= sum_{q<J} L(J,q) w_q ; lane = (row i, quarter of the q range)
+        const int i = lane & 7, part = lane >> 3;
+        double s = 0.0;
+        for (int q = part; q < J; q += 4) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) s = fma(rowJ[q * 64 + c * 8 + i], b[q * 8 + c], s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        if (lane < 8) b[J * 8 + i] -= s;
+      }
+      BVG_TP(4);
+    }
+    __syncthreads();
+    BVG_TP(tid == 0 ? 3 : 5);
+    // ---- phase 2: panel L(I,J) = A(I,J) T_J' (two DMMAs per tile), w_J = T_J b_J
     {
-      const double t0 = Ti[fo0], t1 = Ti[fo1];                    // B fragment: B[k][n] = T[n][k]
-      for (int I = p + 1 + warp; I < nt; I += nwarp) {
-        double* TA = L + (((I * (I + 1)) >> 1) + p) * 64;
-        double c0 = 0.0, c1 = 0.0;
+      const double t0 = D[fo0], t1 = D[fo1];                      // B fragment: B[k][n] = T[n][k]
+      for (int I = J + 1 + warp; I < nt; I += nwarp) {
+        double* TA = L + (((I * (I + 1)) >> 1) + J) * 64;
+        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
         tiled_dmma(c0, c1, TA[fo0], t0);
-        tiled_dmma(c0, c1, TA[fo1], t1);
-        TA[co] = c0;
-        TA[co + 8] = c1;
+        tiled_dmma(e0, e1, TA[fo1], t1);
+        TA[co] = c0 + e0;
+        TA[co + 8] = c1 + e1;
+        __syncwarp();
+        // right-looking for the diagonal tile of this row only: A(I,I) -= L(I,J) L(I,J)'
+        double* DI = L + (((I * (I + 1)) >> 1) + I) * 64;
+        const double u0 = TA[fo0], u1 = TA[fo1];
+        double d0 = DI[co], d1 = DI[co + 8], f0 = 0.0, f1 = 0.0;
+        tiled_dmma(d0, d1, -u0, u0);
+        tiled_dmma(f0, f1, -u1, u1);
+        DI[co] = d0 + f0;
+        DI[co + 8] = d1 + f1;
       }
       if (warp == nwarp - 1) {
         double s = 0.0;
         const int i = lane & 7;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) s = fma(Ti[c * 8 + i], b[p * 8 + c], s);
+        for (int c = 0; c < 8; ++c) s = fma(D[c * 8 + i], b[J * 8 + c], s);
         __syncwarp();
-        if (lane < 8) b[p * 8 + i] = s;                           // w_p = T_p b_p
+        if (lane < 8) b[J * 8 + i] = s;                           // w_J = T_J b_J
       }
     }
     __syncthreads();
-    if (p + 1 == nt) break;
-    // ---- trailing update of the rows below: rhs first, then the tiles
-    for (int r = (p + 1) * 8 + tid; r < npad; r += G) {
-      const double* R = L + tiled_idx(r, p * 8);                  // element (r, 8p); next column is +8
-      double s = b[r];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) s = fma(-R[c * 8], b[p * 8 + c], s);
-      b[r] = s;
-    }
-    const int m = nt - 1 - p;                                     // tile rows p+1 .. nt-1
-    const int ntile = (m * (m + 1)) >> 1;
-    // tile t = a (a + 1) / 2 + bc  <->  (I, J) = (p + 1 + a, p + 1 + bc); t = 0 is the next diagonal tile
-    int t, stride;
-    if (nwarp == 1) { t = 0; stride = 1; }
-    else if (warp == 0) { t = 0; stride = ntile; }                // warp 0: tile (p+1,p+1) only, then the look-ahead
-    else { t = warp; stride = nwarp - 1; }
-    int a = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-    while (((a + 1) * (a + 2)) >> 1 <= t) ++a;
-    while (((a * (a + 1)) >> 1) > t) --a;
-    int bc = t - ((a * (a + 1)) >> 1);
-    for (; t < ntile; t += stride) {
-      const int I = p + 1 + a, J = p + 1 + bc;
-      const double* TA = L + (((I * (I + 1)) >> 1) + p) * 64;
-      const double* TB = L + (((J * (J + 1)) >> 1) + p) * 64;
-      double* C = L + (((I * (I + 1)) >> 1) + J) * 64 + co;
-      double c0 = C[0], c1 = C[8];
-      tiled_dmma(c0, c1, -TA[fo0], TB[fo0]);
-      tiled_dmma(c0, c1, -TA[fo1], TB[fo1]);
-      C[0] = c0;
-      C[8] = c1;
-      bc += stride;
-      while (bc > a) { bc -= a + 1; ++a; }
-    }
-    if (warp == 0) {
-      __syncwarp();
-      tiled_factor_invert(L + ((((p + 1) * (p + 2)) >> 1) + p + 1) * 64, fail);
-    }
-    __syncthreads();
+    BVG_TP(0);
   }
 }
 
@@ -169,13 +208,19 @@ static __device__ __noinline__ void tiled_back_solve(const double* L, double* v,
       if (lane < 8) { v[p * 8 + i] = s; if (p * 8 + i < n) a[p * 8 + i] = s; }
     }
     __syncthreads();
-    // v_c -= sum_{r in tile row p} L[r][c] x[r]  for the columns c < 8p
+    // v_c -= sum_{r in tile row p} L[r][c] x[r]  for the columns c < 8p; the row order is rotated per lane so that the
+    // eight lanes of a tile hit different banks
     for (int c = tid; c < p * 8; c += G) {
       const double* R = L + tiled_idx(p * 8, c);                   // element (8p, c); next row is +1
-      double s = v[c];
+      const double* xp = v + p * 8;
+      double s0 = v[c], s1 = 0.0;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) s = fma(-R[r], v[p * 8 + r], s);
-      v[c] = s;
+      for (int t = 0; t < 8; t += 2) {
+        const int ra = (c + t) & 7, rb = (c + t + 1) & 7;
+        s0 = fma(-R[ra], xp[ra], s0);
+        s1 = fma(-R[rb], xp[rb], s1);
+      }
+      v[c] = s0 + s1;
     }
     __syncthreads();
   }
