@@ -183,7 +183,7 @@ BVG_HD void wishart_block(const Grp& g, const ChainRng& rng, int sweep, int k, d
   }
 }
 
-// Register version of the same block for small k (K <= 4, compile time): every lane redundantly runs the whole
+// Register version of the same block for small k (K <= 6, compile time): every lane redundantly runs the whole
 // K x K algebra on registers (no shared-memory traffic, no barriers); the variates were drawn before, in the
 // sweep's single generator pass: wn[] = strict-upper normals, x0[] = attempt-0 normals of the chi-squares.
 template <int K, class Grp>
@@ -478,7 +478,7 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
     // ---- variates of this sweep that do not depend on the chain state, drawn in ONE pass through one generator
     //      call site (no divergence between lanes): coefficient normals -> a[], and for the register Wishart block
     //      its strict-upper normals -> W4[] and the attempt-0 normals of its chi-squares -> kv[]
-    const bool wish_reg = !sv && !use_gamma && k <= 4;
+    const bool wish_reg = !sv && !use_gamma && k <= (Grp::kIsBlock ? 6 : 4);   // K = 5, 6: CTA kernels only
     {
       const int nwn = (k * (k - 1)) / 2;
       const int n_items = n + (wish_reg ? nwn + k : 0);
@@ -790,12 +790,25 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
         for (int e = tid; e < kk; e += G) { const int i = e % k, j = e / k; if (i < j) S[e] = S[j + k * i]; }
         g.sync();
         if (wish_reg) {
-          switch (k) {
-            case 1: wishart_block_reg<1>(g, rng, sweep, m.wish_df_post, S, W4, kv, kd, sig, out_sig, fail); break;
-            case 2: wishart_block_reg<2>(g, rng, sweep, m.wish_df_post, S, W4, kv, kd, sig, out_sig, fail); break;
-            case 3: wishart_block_reg<3>(g, rng, sweep, m.wish_df_post, S, W4, kv, kd, sig, out_sig, fail); break;
-            default: wishart_block_reg<4>(g, rng, sweep, m.wish_df_post, S, W4, kv, kd, sig, out_sig, fail); break;
+#define BVG_WISH_REG(grp)                                                                                                  \
+          switch (k) {                                                                                                     \
+            case 1: wishart_block_reg<1>(grp, rng, sweep, m.wish_df_post, S, W4, kv, kd, sig, out_sig, fail); break;       \
+            case 2: wishart_block_reg<2>(grp, rng, sweep, m.wish_df_post, S, W4, kv, kd, sig, out_sig, fail); break;       \
+            case 3: wishart_block_reg<3>(grp, rng, sweep, m.wish_df_post, S, W4, kv, kd, sig, out_sig, fail); break;       \
+            default: wishart_block_reg<4>(grp, rng, sweep, m.wish_df_post, S, W4, kv, kd, sig, out_sig, fail); break;      \
           }
+#if defined(__CUDA_ARCH__)
+          if constexpr (Grp::kIsBlock) {
+            if (tid < 32) {                                        // warp 0 alone; the CTA meets at the sync below
+              const TileGroup<32> wg;
+              if (k == 5) wishart_block_reg<5>(wg, rng, sweep, m.wish_df_post, S, W4, kv, kd, sig, out_sig, fail);
+              else if (k == 6) wishart_block_reg<6>(wg, rng, sweep, m.wish_df_post, S, W4, kv, kd, sig, out_sig, fail);
+              else { BVG_WISH_REG(wg) }
+            }
+          } else
+#endif
+          { BVG_WISH_REG(g) }
+#undef BVG_WISH_REG
         } else {
 #if defined(__CUDA_ARCH__)
           if constexpr (Grp::kIsBlock) {
