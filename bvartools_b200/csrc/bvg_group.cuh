@@ -14,6 +14,7 @@ namespace bvg {
 struct SerialGroup {
   static constexpr bool kCheapBcast = true;
   static constexpr bool kIsBlock = false;
+  static constexpr bool kWarp32 = false;
   BVG_HD int tid() const { return 0; }
   BVG_HD int size() const { return 1; }
   BVG_HD void sync() const {}
@@ -26,6 +27,7 @@ template <int G>
 struct TileGroup {
   static constexpr bool kCheapBcast = true;   // register shuffles
   static constexpr bool kIsBlock = false;
+  static constexpr bool kWarp32 = (G == 32);  // a full warp per chain: DMMA tile paths apply
   unsigned mask;
   int lane;   // 0..G-1
   __device__ __forceinline__ TileGroup() {
@@ -48,6 +50,7 @@ struct TileGroup {
 struct BlockGroup {
   static constexpr bool kCheapBcast = false;  // two __syncthreads per broadcast
   static constexpr bool kIsBlock = true;      // k x k blocks run on warp 0 alone (TileGroup<32>): no CTA barriers inside
+  static constexpr bool kWarp32 = false;
   double* scratch;   // >= 33 doubles of shared memory
   __device__ __forceinline__ explicit BlockGroup(double* s) : scratch(s) {}
   __device__ __forceinline__ int tid() const { return threadIdx.x; }

@@ -10,8 +10,13 @@
 
 namespace bvg {
 
+#if BVG_G == 32
+#define BVG_TVP_BOUNDS __launch_bounds__(128, 2)   // shared memory allows ~7 warps per SM anyway: registers are free
+#else
+#define BVG_TVP_BOUNDS __launch_bounds__(128, 6)
+#endif
 #if BVG_G > 0
-__global__ void __launch_bounds__(128, 6) BVG_CAT(tvp_tile_kernel_g, BVG_G)(
+__global__ void BVG_TVP_BOUNDS BVG_CAT(tvp_tile_kernel_g, BVG_G)(
     const __grid_constant__ TvpModel m, const __grid_constant__ RngParams rp, double* state, int state_len,
     double* scratch, long long scratch_per_chain, const __grid_constant__ TvpOut out, long long n_chains, int s0,
     int s1, int burnin, int smem_per_chain) {

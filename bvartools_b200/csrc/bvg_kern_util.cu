@@ -50,13 +50,23 @@ cudaError_t plan_bvar(const BvarModel& m, long long n_chains, int requested_tpc,
 
 cudaError_t plan_tvp(const TvpModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan) {
   plan->kron = 0;
-  const int per = tvp_smem_len(m.b.k, m.b.T, m.b.n, m.b.sigma_type);
+  int per = tvp_smem_len(m.b.k, m.b.T, m.b.n, m.b.sigma_type);
   int tpc = requested_tpc;
   if (tpc <= 0) {
     if ((size_t)per * 8 > 48 * 1024 || m.b.n > 64) tpc = (m.b.n > 96) ? 256 : 128;
     else tpc = pick_tile(m.b.n);
   }
-  return finish_plan(plan, per, n_chains, tpc);
+  const bool tiled = (tpc == 32) && tvp_tiled_ok(m.b.n);      // warp per chain, DMMA tile path
+  if (tiled) per = tvp_smem_len(m.b.k, m.b.T, m.b.n, m.b.sigma_type, true);
+  cudaError_t e = finish_plan(plan, per, n_chains, tpc);
+  if (e == cudaSuccess && tiled) {
+    // one chain per CTA: the chains (each a latency-bound sequential recursion) spread evenly over the SMs
+    plan->block_threads = 32;
+    plan->chains_per_block = 1;
+    plan->smem_bytes = (size_t)per * 8;
+    plan->grid = (int)n_chains;
+  }
+  return e;
 }
 
 typedef cudaError_t (*bvar_launcher)(BVG_BVAR_ARGS);

@@ -12,6 +12,7 @@
 // M_t (packed lower) is streamed through HBM: T tri(n) doubles written forward, read backward.
 #pragma once
 #include "bvg_bvar_sweep.cuh"
+#include "bvg_tvp_tiled.cuh"
 
 namespace bvg {
 
@@ -36,10 +37,12 @@ BVG_HD int tvp_state_len(int k, int T, int n, int sigma_type) {
   return k * k + 3 * n + (sigma_type == SIG_SV ? T * k + 2 * k : 0);
 }
 // global scratch per chain: T*tri(n) (M_t) + T*n (w_t + eps_t) + T*n (a path)
-BVG_HD long long tvp_scratch_len(int T, int n) { return (long long)T * (tri(n) + 2 * n); }
+// (the warp-per-chain tile path streams full 8 x 8 tiles: tiled_len(n) >= tri(n) doubles per period)
+BVG_HD bool tvp_tiled_ok(int n) { return n <= 32; }
+BVG_HD long long tvp_scratch_len(int T, int n) { return (long long)T * ((tvp_tiled_ok(n) ? tiled_len(n) : tri(n)) + 2 * n); }
 
-BVG_HD int tvp_smem_len(int k, int T, int n, int sigma_type) {
-  int len = 3 * tri(n) + 9 * n + 6 * k * k + 2 * k + k * T;
+BVG_HD int tvp_smem_len(int k, int T, int n, int sigma_type, bool tiled = false) {
+  int len = (tiled ? 2 * tiled_len(n) + 10 * (n + 8) : 3 * tri(n) + 9 * n) + 6 * k * k + 2 * k + k * T;
   if (sigma_type == SIG_SV) len += 3 * k * T + 2 * k;
   return len;
 }
@@ -70,18 +73,25 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
   const int k = m.k, T = m.T, M = m.M, n = m.n, kk = k * k, tn = tri(n);
   const bool sv = m.sigma_type == SIG_SV;
   const bool bvs = m.varsel == VS_BVS;
-  double* Dt = sm;      sm += tn;
-  double* Mi = sm;      sm += tn;
-  double* Cq = sm;      sm += tn;
-  double* wv = sm;      sm += n;      // rhs_t -> w_t
-  double* cvec = sm;    sm += n;      // Q M_t' w_t (carry into t+1)
-  double* dinv = sm;    sm += n;
-  double* q = sm;       sm += n;
-  double* a_init = sm;  sm += n;
-  double* lam = sm;     sm += n;
-  double* anext = sm;   sm += n;
-  double* tmp = sm;     sm += n;
-  double* tmp2 = sm;    sm += n;
+#if defined(__CUDA_ARCH__)
+  const bool tiled = Grp::kWarp32 && tvp_tiled_ok(n);   // warp per chain, n <= 32: DMMA tile path (bvg_tvp_tiled.cuh)
+#else
+  const bool tiled = false;
+#endif
+  const int nv = tiled ? n + 8 : n;                     // vectors are zero padded to whole tiles
+  double* Dt = sm;      sm += tiled ? tiled_len(n) : tn;
+  double* Mi = sm;      sm += tiled ? 0 : tn;
+  double* Cq = sm;      sm += tiled ? tiled_len(n) : tn;
+  double* wv = sm;      sm += nv;     // rhs_t -> w_t
+  double* cvec = sm;    sm += nv;     // Q M_t' w_t (carry into t+1)
+  double* dinv = sm;    sm += nv;
+  double* q = sm;       sm += nv;
+  double* a_init = sm;  sm += nv;
+  double* lam = sm;     sm += nv;
+  double* anext = sm;   sm += nv;
+  double* tmp = sm;     sm += nv;
+  double* tmp2 = sm;    sm += nv;
+  double* xl = sm;      sm += tiled ? nv : 0;
   double* sig = sm;     sm += kk;
   double* S = sm;       sm += kk;
   double* W1 = sm;      sm += kk;
@@ -93,8 +103,8 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
   double* U = sm;       sm += k * T;
   double* h = nullptr; double* ew = nullptr; double* svw = nullptr; double* sigma_h = nullptr; double* h_init = nullptr;
   if (sv) { h = sm; sm += k * T; ew = sm; sm += k * T; svw = sm; sm += k * T; sigma_h = sm; sm += k; h_init = sm; sm += k; }
-  double* Mpath = scratch;                         // [T][tn]
-  double* wpath = scratch + (size_t)T * tn;        // [T][n]
+  double* Mpath = scratch;                         // [T][tn]  (tiled: [T][tiled_len(n)])
+  double* wpath = scratch + (size_t)T * (tiled ? tiled_len(n) : tn);   // [T][n]
   double* apath = wpath + (size_t)T * n;           // [T][n]
   int fail = 0;
 
@@ -104,6 +114,7 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
   double* st_h = st_lam + n;
   for (int e = tid; e < kk; e += G) sig[e] = state[e];
   for (int e = tid; e < n; e += G) { q[e] = st_q[e]; a_init[e] = st_ai[e]; lam[e] = st_lam[e]; }
+  for (int e = n + tid; e < nv; e += G) { q[e] = 0.0; a_init[e] = 0.0; anext[e] = 0.0; }
   if (sv) {
     for (int e = tid; e < T * k; e += G) h[e] = st_h[e];
     for (int e = tid; e < k; e += G) { sigma_h[e] = st_h[T * k + e]; h_init[e] = st_h[T * k + k + e]; }
@@ -118,6 +129,14 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
       for (int e = tid; e < k * T; e += G) ew[e] = 1.0 / exp(sweep == 0 ? h[T * (e / T)] : h[e]);
       g.sync();
     }
+#if defined(__CUDA_ARCH__)
+    if (tiled) {
+      if constexpr (Grp::kWarp32)
+        tvp_state_draw_tiled(m, rng, sweep, sv, Dt, Cq, wv, cvec, xl, anext, tmp, q, a_init, bvs ? lam : nullptr, sig,
+                             ew, kv, Mpath, wpath, apath, fail);
+    } else
+#endif
+    {
     // ================= forward recursion =================
     for (int t = 0; t < T; ++t) {
       const double* xt = m.X + (size_t)M * t;
@@ -201,6 +220,7 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
       g.sync();
       for (int r = tid; r < n; r += G) anext[r] = tmp[r];
       g.sync();
+    }
     }
 
     // ================= BVS (bvartvpalg.cpp:300-330) and residuals (:332-336) =================
