@@ -338,13 +338,44 @@ def main():
     except Exception:
         pass
     out_bytes = 8.0 * chains * it * sum(rows.values())
-    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
-                "frac": achieved / peak.value if peak.value > 0 else None, "traffic": None,
-                "kernel": kernel_name,
-                "peak_source": peak_source, "fp64_dmma_peak_tflops": dmma_peak.value,
-                "flops_per_sweep_executed": fl_sweep, "flops_per_sweep_survey": survey_flops_per_sweep(obj),
-                "sweep_kernel_ms_per_step": last_sweep_ms, "sweep_share_of_step": last_sweep_ms / ms_per_step,
-                "hbm_write_GBps": out_bytes / sweep_kernel_s / 1e9, "hbm_peak_GBps": peaks.get("hbm_gbs")}
+    hbm_peak = peaks.get("hbm_gbs") or 6530.6
+    # ncu-measured DRAM bytes per launch of this kernel in this launch shape (profiles/r01_traffic.json, written from
+    # `ncu --set full` captures of this very command); null when there is no capture of this shape
+    traffic, traffic_note = None, None
+    try:
+        tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+        key = f"{args.workload}:{chains}:{it}:{bi}:{kernel_name}"
+        if key in tj:
+            traffic, traffic_note = tj[key]["dram_bytes_per_launch"], tj[key]["note"]
+    except Exception:
+        pass
+    n_sweep_launches = max(int(launches_per_step) - 1, 1)
+    fp64 = {"achieved_tflops": achieved, "peak_tflops": peak.value,
+            "frac": achieved / peak.value if peak.value > 0 else None, "peak_source": peak_source,
+            "fp64_dmma_peak_tflops": dmma_peak.value, "flops_per_sweep_executed": fl_sweep,
+            "flops_per_sweep_survey": survey_flops_per_sweep(obj)}
+    if kernel_name.startswith("kron"):
+        # flat-prior Kronecker kernel: ~550 flop and 240 B of output per chain-sweep; the applicable roofline of the
+        # two is HBM (algorithmic bytes = retained draws only, 8 (n + k^2) per chain and iteration)
+        gbps = out_bytes / sweep_kernel_s / 1e9
+        roofline = {"bound": "hbm", "achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak,
+                    "traffic": traffic, "traffic_note": traffic_note, "kernel": kernel_name,
+                    "algorithmic_bytes_per_launch": out_bytes / n_sweep_launches,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "B200_PROFILING.md fallback",
+                    "fp64": fp64}
+    else:
+        tensor = kernel_name.startswith("large") or kernel_name.startswith("bvar_g0") or kernel_name == "tvp_g32"
+        tpeak = max(peak.value, dmma_peak.value) if tensor else peak.value
+        roofline = {"bound": "tensor" if tensor else "fp64", "achieved": achieved, "peak": tpeak, "unit": "TFLOP/s",
+                    "frac": achieved / tpeak if tpeak > 0 else None, "traffic": traffic, "traffic_note": traffic_note,
+                    "kernel": kernel_name,
+                    "peak_source": ("FP64 DMMA (mma.sync m8n8k4) probe kernel run live by bench.py (bvg_dmma_peak)"
+                                    if tensor and dmma_peak.value >= peak.value else peak_source),
+                    "fp64_dmma_peak_tflops": dmma_peak.value, "flops_per_sweep_executed": fl_sweep,
+                    "flops_per_sweep_survey": survey_flops_per_sweep(obj)}
+    roofline.update({"sweep_kernel_ms_per_step": last_sweep_ms, "sweep_launches_per_step": n_sweep_launches,
+                     "sweep_share_of_step": last_sweep_ms / ms_per_step,
+                     "hbm_write_GBps": out_bytes / sweep_kernel_s / 1e9, "hbm_peak_GBps": hbm_peak})
     cpu = None
     if not args.no_cpu:
         cpu = cpu_reference_run(obj, label, 1, 0, cpu_sweeps, False)

@@ -59,3 +59,9 @@ cudaError_t BVG_CAT(launch_tvp_g, BVG_G)(const LaunchPlan& plan, const TvpModel&
 }
 
 }  // namespace bvg
+
+#if defined(BVG_TVP_PROF) && BVG_G == 32
+extern "C" int bvg_debug_tvp_prof(long long* out16) {   // measurement builds only (make EXTRA=-DBVG_TVP_PROF)
+  return (int)cudaMemcpyFromSymbol(out16, bvg::g_tvp_prof, 16 * sizeof(long long));
+}
+#endif

@@ -17,6 +17,14 @@
 namespace bvg {
 
 #if defined(__CUDACC__)
+#ifdef BVG_TVP_PROF   // cycles per phase of the state draw, accumulated by lane 0 of chain 0 (tools/micro, never in the product build)
+static __device__ long long g_tvp_prof[16];
+#define BVG_TVP_TICK(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now_ = clock64(); g_tvp_prof[slot] += now_ - tick_; tick_ = now_; } } while (0)
+#define BVG_TVP_TICK0 long long tick_ = clock64();
+#else
+#define BVG_TVP_TICK(slot) do { } while (0)
+#define BVG_TVP_TICK0
+#endif
 #define BVG_TT(P, I, J) ((P) + (((((I) * ((I) + 1)) >> 1) + (J)) << 6))
 
 // y_I = sum_{J <= I} M_IJ x_J  for all tile rows (lower block-triangular mat-vec); result for row 8 I + (lane & 7) is
@@ -77,6 +85,7 @@ static __device__ __noinline__ void tvp_state_draw_tiled(const BvarModel& m, con
   const float kinv = 1.0f / (float)k;
   const unsigned FULL = 0xffffffffu;
 
+  BVG_TVP_TICK0
   // ================= forward recursion =================
   for (int t = 0; t < T; ++t) {
     const double* xt = m.X + (size_t)M * t;
@@ -125,6 +134,7 @@ static __device__ __noinline__ void tvp_state_draw_tiled(const BvarModel& m, con
       wv[lane] = b;
     }
     __syncwarp();
+    BVG_TVP_TICK(0);
     // ---- L_tt, diagonal tiles replaced by their inverses
     for (int J = 0; J < nt; ++J) {
       double* D = BVG_TT(A, J, J);
@@ -157,6 +167,7 @@ static __device__ __noinline__ void tvp_state_draw_tiled(const BvarModel& m, con
         __syncwarp();
       }
     }
+    BVG_TVP_TICK(1);
     // ---- M_t = L_tt^-1 in place: row I from the finished rows above it
     for (int I = 1; I < nt; ++I) {
       double x0[NTMAX - 1], x1[NTMAX - 1];
@@ -196,6 +207,7 @@ static __device__ __noinline__ void tvp_state_draw_tiled(const BvarModel& m, con
         if (J < I) { double* X = BVG_TT(A, I, J); X[co] = x0[J]; X[co + 8] = x1[J]; }
       __syncwarp();
     }
+    BVG_TVP_TICK(2);
     // ---- w_t = M_t rhs_t
     {
       double wI[NTMAX];
@@ -206,12 +218,14 @@ static __device__ __noinline__ void tvp_state_draw_tiled(const BvarModel& m, con
         if (I < nt && lj == 0) wv[8 * I + li] = wI[I];
       __syncwarp();
     }
+    BVG_TVP_TICK(3);
     // ---- stream M_t and w_t + eps_t to HBM
     {
       double* Mg = Mpath + (size_t)t * TP;
       for (int e = lane; e < TP; e += 32) Mg[e] = A[e];
       if (lane < n) wpath[(size_t)t * n + lane] = wv[lane] + rng.normal(VB_STATE_N, sweep, t * n + lane);
     }
+    BVG_TVP_TICK(4);
     if (t < T - 1) {
       // ---- carry: Cq = Q M'M Q,  cvec = Q M' w
       for (int I = 0; I < nt; ++I) {
@@ -236,6 +250,7 @@ static __device__ __noinline__ void tvp_state_draw_tiled(const BvarModel& m, con
         if (J < nt && lj == 0) cvec[8 * J + li] = q[8 * J + li] * cJ[J];
     }
     __syncwarp();
+    BVG_TVP_TICK(5);
   }
 
   // ================= backward recursion =================
@@ -278,6 +293,7 @@ static __device__ __noinline__ void tvp_state_draw_tiled(const BvarModel& m, con
       }
     __syncwarp();
   }
+  BVG_TVP_TICK(6);
 }
 #undef BVG_TT
 #endif

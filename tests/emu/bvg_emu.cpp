@@ -25,6 +25,8 @@ struct ThreadShared {
 };
 struct ThreadGroup {
   static constexpr bool kCheapBcast = true;
+  static constexpr bool kIsBlock = false;
+  static constexpr bool kWarp32 = false;
   int lane, G;
   ThreadShared* sh;
   int tid() const { return lane; }

@@ -1,0 +1,32 @@
+#!/usr/bin/env python3
+"""Cycles per phase of the tiled TVP state draw (chain 0, lane 0).  Needs a measurement build of the library:
+    make -C bvartools_b200/csrc clean && make -C bvartools_b200/csrc -j16 EXTRA=-DBVG_TVP_PROF
+(rebuild without EXTRA afterwards: the product library carries no instrumentation)."""
+import ctypes as C
+import pathlib
+import sys
+
+ROOT = pathlib.Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+import helpers  # noqa: E402
+from bvartools_b200 import ChainSampler  # noqa: E402
+from bvartools_b200._lib import lib  # noqa: E402
+
+sweeps = 20
+obj = helpers.model_sv(K=3, p=2, nobs=202, iterations=sweeps // 2, burnin=sweeps // 2, tvp=True)
+s = ChainSampler(obj, n_chains=1024, seed=1, device=0)
+s.run(0)
+s.sync()
+import torch  # noqa: E402
+torch.cuda.synchronize()
+out = (C.c_longlong * 16)()
+rc = lib().bvg_debug_tvp_prof(out)
+T = 200
+names = ["build", "factor", "inverse", "w=M b", "stream+normals", "carry (M'M, cvec)", "backward (whole pass)"]
+tot = sum(out[:7])
+print("rc", rc, "kernel ms", s.last_kernel_ms)
+for i, nm in enumerate(names):
+    per_t = out[i] / (sweeps * T)
+    print(f"{nm:24s} {per_t:9.0f} cycles per period   {100.0 * out[i] / tot:5.1f} %")
+print(f"total {tot / (sweeps * T):.0f} cycles per period, {tot / sweeps / 1e6:.2f} Mcycles per sweep")
