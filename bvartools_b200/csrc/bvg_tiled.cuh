@@ -63,6 +63,8 @@ __device__ __forceinline__ void tiled_factor_invert(double* D, int& fail) {
     if (j < 7) a[j + 1] = fma(-l, __shfl_sync(FULL, l, j + 1), a[j + 1]);   // next pivot column first
 #pragma unroll
     for (int c = j + 2; c < 8; ++c) a[c] = fma(-l, __shfl_sync(FULL, l, c), a[c]);
+    // (an unscaled variant -- u_i u_c / d with the multiplier shuffles issued before the reciprocal -- measured 8 %
+    //  slower in tools/micro/chol_prof: __drcp_rn costs more than the shuffle it takes off the chain)
     // row j of T: T[j][i] = -(sum_{i <= m < j} L_jm T[m][i]) / L_jj  (i < j),  1 / L_jj  (i = j),  0  (i > j)
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
