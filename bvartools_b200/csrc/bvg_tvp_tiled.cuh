@@ -102,20 +102,32 @@ static __device__ __noinline__ void tvp_state_draw_tiled_nt(const BvarModel& m, 
   BVG_TVP_TICK(7);
 
   // ================= forward recursion =================
+  // x_t, y_t and eps_t of the NEXT period are fetched one period ahead (their L2 latency would otherwise sit in front
+  // of every period's build)
+  const int jr_lane = (int)(((float)lane + 0.5f) * kinv);
+  double x_next = (lane < n) ? m.X[jr_lane] : 0.0;
+  double y_next = (lane < k) ? m.Y[lane] : 0.0;
+  double eps_next = (lane < n) ? wpath[lane] : 0.0;
   for (int t = 0; t < T; ++t) {
-    const double* xt = m.X + (size_t)M * t;
-    const double* yt = m.Y + (size_t)k * t;
-    const double eps_t = (lane < n) ? wpath[(size_t)t * n + lane] : 0.0;   // used at the end of the period
-    if (lane < k) {
+    const double x_cur = x_next, y_cur = y_next, eps_t = eps_next;
+    if (t + 1 < T) {
+      x_next = (lane < n) ? m.X[(size_t)M * (t + 1) + jr_lane] : 0.0;
+      y_next = (lane < k) ? m.Y[(size_t)k * (t + 1) + lane] : 0.0;
+      eps_next = (lane < n) ? wpath[(size_t)(t + 1) * n + lane] : 0.0;
+    }
+    {
       double s;
-      if (sv) s = ew[t + T * lane] * yt[lane];
-      else { s = 0.0; for (int i2 = 0; i2 < k; ++i2) s = fma(sig[lane + k * i2], yt[i2], s); }
-      kv[lane] = s;
+      if (sv) s = (lane < k) ? ew[t + T * lane] * y_cur : 0.0;
+      else {
+        s = 0.0;
+        for (int i2 = 0; i2 < k; ++i2) {
+          const double yv = __shfl_sync(0xffffffffu, y_cur, i2);
+          if (lane < k) s = fma(sig[lane + k * i2], yv, s);
+        }
+      }
+      if (lane < k) kv[lane] = s;
     }
-    if (lane < NPAD) {
-      const int jr = (int)(((float)lane + 0.5f) * kinv);
-      xl[lane] = (lane < n) ? xt[jr] * (lam != nullptr ? lam[lane] : 1.0) : 0.0;
-    }
+    if (lane < NPAD) xl[lane] = (lane < n) ? x_cur * (lam != nullptr ? lam[lane] : 1.0) : 0.0;
     __syncwarp();
     const double ct = (t < T - 1) ? 2.0 : 1.0;
     // ---- D_t and rhs_t (branch-free: every load of the period is issued up front)
