@@ -322,6 +322,14 @@ template <class Grp>
 BVG_HD void sv_step(const Grp& g, const ChainRng& rng, int sweep, const BvarModel& m, double* U, double* h,
                     const double* sigma_h, const double* h_init, double* pr, double* rh, int* s_out = nullptr) {
   const int G = g.size(), tid = g.tid(), k = m.k, T = m.T, J = m.n_mix;
+  // mixture constants once per call (the reference recomputes sqrt(s2_j) and sd_j sqrt(2 pi) per element: same values)
+  double c_sd[10], c_den[10], c_mu[10], c_p[10];
+  for (int j = 0; j < J; ++j) {
+    c_sd[j] = sqrt(m.mix_s2[j]);
+    c_den[j] = c_sd[j] * 2.5066282746310002;
+    c_mu[j] = m.mix_mu[j];
+    c_p[j] = m.mix_p[j];
+  }
   for (int e = tid; e < k * T; e += G) {
     const int i = e % k, t = e / k;
     const double u = U[e];
@@ -330,9 +338,8 @@ BVG_HD void sv_step(const Grp& g, const ChainRng& rng, int sweep, const BvarMode
     double q[10];
     double qs = 0.0;
     for (int j = 0; j < J; ++j) {
-      const double sd = sqrt(m.mix_s2[j]);
-      const double z = (ys - (ht + m.mix_mu[j])) / sd;
-      q[j] = m.mix_p[j] * (exp(-0.5 * (z * z)) / (sd * 2.5066282746310002));     // :94 (arma::normpdf)
+      const double z = (ys - (ht + c_mu[j])) / c_sd[j];
+      q[j] = c_p[j] * (exp(-0.5 * (z * z)) / c_den[j]);                            // :94 (arma::normpdf)
       qs += q[j];
     }
     const double uu = rng.uniform(VB_SV_U, sweep, i * T + t);
@@ -347,34 +354,57 @@ BVG_HD void sv_step(const Grp& g, const ChainRng& rng, int sweep, const BvarMode
     if (s_out != nullptr) s_out[t + T * i] = s;
     const double p = 1.0 / m.mix_s2[s];                                            // :101
     pr[i * T + t] = p;
-    rh[i * T + t] = p * (ys - m.mix_mu[s]);                                        // :103 sigs * (y - mu_s)
+    rh[i * T + t] = p * (ys - c_mu[s]);                                            // :103 sigs * (y - mu_s)
   }
   g.sync();
-  for (int i = tid; i < k; i += G) {
-    const double si = 1.0 / sigma_h[i];                                            // hh / sigma(i), :99
+  // The draw  h = P^-1 rhs + chol(P)^-1 eps  with P = tridiag(diag = {2,...,2,1} si + p_t, off = -si)  (:99-104) through
+  // the lower bidiagonal factor  l_t^2 = c_t,  c_t = dg_t - si^2 / c_{t-1},  m_t = -si / l_t.  Only three SHORT
+  // recurrences stay sequential (one lane per series); everything else is parallel over (series, t):
+  //   (a) c_t = N_t / D_t by the division-free continued-fraction form  N_{t+1} = dg_{t+1} N_t - si^2 D_t, D_{t+1} = N_t
+  //   (b) w_t = b_t / l_t + (si / (l_{t-1} l_t)) w_{t-1}                 forward solve
+  //   (c) h_t = z_t / l_t + (si / l_t^2) h_{t+1},  z = w + eps            back substitution
+  // eps: the residual array U is free now and takes the normals, site (series, t) -> U[i T + t].
+  for (int e = tid; e < k * T; e += G) U[e] = rng.normal(VB_SV_N, sweep, e);
+  for (int i = tid; i < k; i += G) {                                               // (a): pr <- N_t, h <- D_t
+    const double si = 1.0 / sigma_h[i], si2 = si * si;                             // hh / sigma(i), :99
     double* p = pr + i * T;
-    double* r = rh + i * T;
-    // lower bidiagonal Cholesky of tridiag(diag = {2,...,2,1} si + p_t, off = -si); forward solve fused
-    double mprev = 0.0, wprev = 0.0;
-    for (int t = 0; t < T; ++t) {
+    double* hd = h + T * i;
+    double N = ((0 < T - 1) ? 2.0 : 1.0) * si + p[0], D = 1.0;
+    p[0] = N; hd[0] = D;
+    for (int t = 1; t < T; ++t) {
       const double dg = ((t < T - 1) ? 2.0 : 1.0) * si + p[t];
-      const double l = sqrt(dg - mprev * mprev);
-      double b = r[t];
-      if (t == 0) b += si * h_init[i];                                             // hh * 1 * h_init = e_1 h_init
-      const double w = (b - mprev * wprev) / l;
-      p[t] = l;                         // keep l_t
-      r[t] = w + rng.normal(VB_SV_N, sweep, i * T + t);                           // w + eps
-      mprev = -si / l;                  // m_t = L_{t+1,t}
-      wprev = w;
+      const double Nn = fma(dg, N, -si2 * D);
+      D = N; N = Nn;
+      if ((t & 3) == 3) {                                                          // joint power-of-two rescale: ratio exact
+        int ex;
+        (void)frexp(N, &ex);
+        N = ldexp(N, -ex); D = ldexp(D, -ex);
+      }
+      p[t] = N; hd[t] = D;
     }
-    // back substitution L' h = w + eps
-    double hn = 0.0;
-    for (int t = T - 1; t >= 0; --t) {
-      const double l = p[t];
-      const double mt = -si / l;
-      const double v = (t == T - 1) ? r[t] / l : (r[t] - mt * hn) / l;
-      h[t + T * i] = v;
-      hn = v;
+  }
+  g.sync();
+  for (int e = tid; e < k * T; e += G) {                                           // pr <- 1 / l_t ; non-positive pivot -> NaN
+    const double c = pr[e] / h[e];
+    pr[e] = 1.0 / sqrt(c);
+  }
+  g.sync();
+  for (int i = tid; i < k; i += G) {                                               // (b) and (c)
+    const double si = 1.0 / sigma_h[i];
+    const double* rl = pr + i * T;
+    double* r = rh + i * T;
+    const double* ep = U + i * T;
+    double w = (r[0] + si * h_init[i]) * rl[0];                                    // hh * 1 * h_init = e_1 h_init
+    r[0] = w + ep[0];
+    for (int t = 1; t < T; ++t) {
+      w = fma(si * rl[t - 1] * rl[t], w, r[t] * rl[t]);
+      r[t] = w + ep[t];                                                            // z_t = w_t + eps_t
+    }
+    double hn = r[T - 1] * rl[T - 1];
+    h[T - 1 + T * i] = hn;
+    for (int t = T - 2; t >= 0; --t) {
+      hn = fma(si * rl[t] * rl[t], hn, r[t] * rl[t]);
+      h[t + T * i] = hn;
     }
   }
   g.sync();

@@ -16,6 +16,14 @@
 
 namespace bvg {
 
+#if defined(BVG_TVP_PROF) && defined(__CUDA_ARCH__)
+#define BVG_TVPC_TICK0 long long tick_ = clock64();
+#define BVG_TVPC_TICK(slot) BVG_TVP_TICK(slot)
+#else
+#define BVG_TVPC_TICK0
+#define BVG_TVPC_TICK(slot) do { } while (0)
+#endif
+
 struct TvpModel {
   BvarModel b;                   // data, error-variance prior, BVS prior; mu/vdiag0/vi_off = prior of the initial state
   const double* v_shape_post;    // n  shape + T/2                                   (bvartvpalg.cpp:104)
@@ -224,7 +232,9 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
     }
 
     // ================= BVS (bvartvpalg.cpp:300-330) and residuals (:332-336) =================
+    BVG_TVPC_TICK0
     tvp_residuals(g, m, apath, lam, bvs, U);
+    BVG_TVPC_TICK(8);
     if (bvs) {
       for (int r = tid; r < n; r += G) {
         double newlam = lam[r];
@@ -268,6 +278,7 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
     if (keep) out_sig = out.sigma + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)(sv ? kk * T : kk);
     if (sv) {
       sv_step(g, rng, sweep, m, U, h, sigma_h, h_init, ew, svw);                       // :414
+      BVG_TVPC_TICK(9);
       for (int i = tid; i < k; i += G) {
         double ss = 0.0, prev = h_init[i];
         for (int t = 0; t < T; ++t) { const double d = h[t + T * i] - prev; ss = fma(d, d, ss); prev = h[t + T * i]; }
@@ -336,6 +347,7 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
       g.sync();
     }
 
+    BVG_TVPC_TICK(10);
     // ================= state variances (:469-477) and initial state (:480-482) =================
     for (int r = tid; r < n; r += G) {
       double ss = 0.0, prev = a_init[r];
@@ -344,6 +356,7 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
       tmp[r] = rng.gamma(VB_SIGV_G, sweep, r, tm.v_shape_post[r]) * scale;             // :476
     }
     g.sync();
+    BVG_TVPC_TICK(11);
     for (int r = tid; r < n; r += G) q[r] = tmp[r];
     g.sync();
     for (int r = tid; r < n; r += G) {
@@ -363,6 +376,7 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
     g.sync();
     back_solve_lt(g, Dt, dinv, wv, a_init, n);
 
+    BVG_TVPC_TICK(12);
     // ================= store (:502-551) =================
     if (keep) {
       double* oc = out.coef + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n * (size_t)T;
@@ -375,6 +389,7 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
       }
     }
     g.sync();
+    BVG_TVPC_TICK(13);
   }
 
   for (int e = tid; e < kk; e += G) state[e] = sig[e];
