@@ -45,39 +45,48 @@ __device__ __forceinline__ void tiled_finish_build(double* L, double* b, int n) 
 }
 
 // One warp: Cholesky of the 8 x 8 diagonal tile D (lower part valid) and T = L^-1, written over D with an exactly
-// zero upper triangle.  Lane i (mod 8) keeps row i in registers; pivots and multipliers travel by shuffle; row j of
-// T is formed as soon as row j of L is final so that its arithmetic hides behind the next pivot's rsqrt.
+// zero upper triangle.  EVERY lane factorises the whole tile redundantly in registers (36 broadcast loads, 112 FP64
+// operations, no shuffles: the chain from one pivot to the next is rsqrt -> multiply -> FMA); lane c (mod 8) then forms
+// column c of T by forward substitution.  Measured against a row-per-lane variant with shuffle broadcasts (132 cycles
+// of dependent latency per pivot plus 128 SHFL): 2.6 k -> see tools/micro/chol_prof, tvp_prof.
 __device__ __forceinline__ void tiled_factor_invert(double* D, int& fail) {
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31, i = lane & 7;
-  double a[8], x[8];      // a: row i of the tile / of L;  x: column i of T (x[r] = T[r][i])
+  const int lane = threadIdx.x & 31, c = lane & 7;
+  double L[8][8], rsv[8], x[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) a[c] = D[c * 8 + i];
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int i = j; i < 8; ++i) L[i][j] = D[j * 8 + i];
+  bool bad = false;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const double d = __shfl_sync(FULL, a[j], j);
-    if (!(d > 0.0)) fail = 1;
+    const double d = L[j][j];
+    bad = bad || !(d > 0.0);
     const double rs = rsqrt(d);
-    const double l = a[j] * rs;          // lane i >= j: L_ij   (lane j: sqrt(d))
-    a[j] = l;
-    if (j < 7) a[j + 1] = fma(-l, __shfl_sync(FULL, l, j + 1), a[j + 1]);   // next pivot column first
+    rsv[j] = rs;
 #pragma unroll
-    for (int c = j + 2; c < 8; ++c) a[c] = fma(-l, __shfl_sync(FULL, l, c), a[c]);
-    // (an unscaled variant -- u_i u_c / d with the multiplier shuffles issued before the reciprocal -- measured 8 %
-    //  slower in tools/micro/chol_prof: __drcp_rn costs more than the shuffle it takes off the chain)
-    // row j of T: T[j][i] = -(sum_{i <= m < j} L_jm T[m][i]) / L_jj  (i < j),  1 / L_jj  (i = j),  0  (i > j)
+    for (int i = j + 1; i < 8; ++i) L[i][j] *= rs;
+#pragma unroll
+    for (int cc = j + 1; cc < 8; ++cc)
+#pragma unroll
+      for (int i = cc; i < 8; ++i) L[i][cc] = fma(-L[i][j], L[cc][j], L[i][cc]);
+  }
+  if (bad) fail = 1;
+  // column c of T: x_c = 1 / L_cc, x_r = -(sum_{c <= m < r} L_rm x_m) / L_rr; entries above the diagonal stay zero
+#pragma unroll
+  for (int r = 0; r < 8; ++r) x[r] = (r == c) ? rsv[r] : 0.0;
+#pragma unroll
+  for (int r = 1; r < 8; ++r) {
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-    for (int m = 0; m < j; ++m) {
-      const double ljm = __shfl_sync(FULL, a[m], j);
-      if (m & 1) s1 = fma(ljm, x[m], s1); else s0 = fma(ljm, x[m], s0);
+    for (int m = 0; m < r; ++m) {
+      if (m & 1) s1 = fma(L[r][m], x[m], s1); else s0 = fma(L[r][m], x[m], s0);
     }
-    x[j] = (i == j) ? rs : ((i < j) ? -rs * (s0 + s1) : 0.0);
+    if (r > c) x[r] = -rsv[r] * (s0 + s1);
   }
   __syncwarp();
   if (lane < 8) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) D[i * 8 + r] = x[r];
+    for (int r = 0; r < 8; ++r) D[c * 8 + r] = x[r];
   }
 }
 

@@ -170,8 +170,10 @@ static __device__ __noinline__ void tvp_state_draw_tiled_nt(const BvarModel& m, 
 #pragma unroll
     for (int J = 0; J < NT; ++J) {
       double* D = BVG_TT(A, J, J);
+      BVG_TVP_TICK(1);
       tiled_factor_invert(D, fail);
       __syncwarp();
+      BVG_TVP_TICK(14);
       if (J + 1 < NT) {
         const double t0 = D[fo0], t1 = D[fo1];
         double p0[NT], p1[NT];

@@ -23,8 +23,8 @@ torch.cuda.synchronize()
 out = (C.c_longlong * 16)()
 rc = lib().bvg_debug_tvp_prof(out)
 T = 200
-names = ["build", "factor", "inverse", "w=M b + stream", "carry (M.M, cvec)", "(unused)", "backward (whole pass)", "normals prologue", "residuals", "sv_step", "sigma_h / h_init / Sigma out", "state variances", "a_init draw", "store"]
-tot = sum(out[:14])
+names = ["build", "factor", "inverse", "w=M b + stream", "carry (M.M, cvec)", "(unused)", "backward (whole pass)", "normals prologue", "residuals", "sv_step", "sigma_h / h_init / Sigma out", "state variances", "a_init draw", "store", "factor_invert only"]
+tot = sum(out[:15])
 print("rc", rc, "kernel ms", s.last_kernel_ms)
 for i, nm in enumerate(names):
     per_t = out[i] / (sweeps * T)
