@@ -363,8 +363,20 @@ def main():
                     "algorithmic_bytes_per_launch": out_bytes / n_sweep_launches,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "B200_PROFILING.md fallback",
                     "fp64": fp64}
+    elif kernel_name.startswith("tvp"):
+        # TVP sweep: the block-bidiagonal factor does not fit on chip and is streamed through HBM (written forward, read
+        # backward); SURVEY.md 8d algorithmic bytes = 2 * 8 * T * tri(n) per chain-sweep + the retained draws
+        T_, k_ = obj["data"]["Y"].shape
+        n_ = k_ * obj["data"]["Z"].shape[1]
+        stream_bytes = 2.0 * 8.0 * T_ * (n_ * (n_ + 1) / 2) * chains * (it + bi)
+        gbps = (stream_bytes + out_bytes) / sweep_kernel_s / 1e9
+        roofline = {"bound": "hbm", "achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak,
+                    "traffic": traffic, "traffic_note": traffic_note, "kernel": kernel_name,
+                    "algorithmic_bytes_per_launch": (stream_bytes + out_bytes) / n_sweep_launches,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "B200_PROFILING.md fallback",
+                    "fp64": fp64}
     else:
-        tensor = kernel_name.startswith("large") or kernel_name.startswith("bvar_g0") or kernel_name == "tvp_g32"
+        tensor = kernel_name.startswith("large") or kernel_name.startswith("bvar_g0")
         tpeak = max(peak.value, dmma_peak.value) if tensor else peak.value
         roofline = {"bound": "tensor" if tensor else "fp64", "achieved": achieved, "peak": tpeak, "unit": "TFLOP/s",
                     "frac": achieved / tpeak if tpeak > 0 else None, "traffic": traffic, "traffic_note": traffic_note,
