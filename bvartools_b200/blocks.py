@@ -261,3 +261,21 @@ def kalman_dk(y, z, sigma_u, sigma_v, B, a_init, P_init, *, seed=None, eps=None)
                               _p(ee), _seed(seed), _p(out)))
     res = out.reshape(nb, T + 1, n).transpose(0, 2, 1)
     return res[0] if single else res
+
+
+def loglik_normal(u, sigma):
+    """Log-likelihood of a multivariate normal per period (src/loglik_normal.cpp:37-58, R/RcppExports.R:313):
+    u is K x T, sigma K x K or the (K T) x K stack of per-period matrices; returns a length-T vector."""
+    require_device()
+    u = np.ascontiguousarray(np.asarray(u, dtype=np.float64))
+    sigma = np.asarray(sigma, dtype=np.float64)
+    if u.ndim != 2:
+        raise ValueError("u must be a K x T matrix")
+    k, T = u.shape
+    if sigma.ndim != 2 or sigma.shape[1] != k or sigma.shape[0] not in (k, k * T):
+        raise ValueError("sigma must be K x K or (K T) x K")
+    out = np.empty(T, dtype=np.float64)
+    uf, sf = _cm(u), _cm(sigma)
+    check(lib().bvg_loglik_normal(_p(uf), _p(sf), k, T, sigma.shape[0], 1, _p(out)))
+    return out
+

@@ -448,6 +448,112 @@ int bvg_moments(const double* dev_draws, int64_t chains, int64_t iters, int64_t 
   return 0;
 }
 
+int bvg_loglik_draws(const double* dev_coef, const double* dev_sigma, int64_t n_draws, int32_t k, int32_t M, int32_t T,
+                     int32_t tvp, int32_t tv_sigma, const double* dev_Y, const double* dev_X, double* dev_ll_t,
+                     void* cuda_stream) {
+  if (!dev_sigma || !dev_Y || !dev_ll_t || (M > 0 && (!dev_coef || !dev_X)))
+    return fail(-1, "invalid arguments to bvg_loglik_draws");
+  if (k < 1 || k > 32) return fail(-2, "bvg_loglik_draws supports 1 <= k <= 32");
+  if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");
+  cudaError_t e = launch_loglik_draws(k, M, T, tvp, tv_sigma, n_draws, dev_Y, dev_X, dev_coef, dev_sigma, dev_ll_t,
+                                      (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "log-likelihood kernel");
+  return 0;
+}
+
+int bvg_sampler_loglik(bvg_sampler* s, double* host_ll_t, void* cuda_stream) {
+  if (!s || !host_ll_t) return fail(-1, "sampler / output is NULL");
+  CK(cudaSetDevice(s->device));
+  const int T = s->P.T;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  double* d_ll = nullptr;
+  CK(cudaMalloc((void**)&d_ll, (size_t)T * sizeof(double)));
+  const int tv_sigma = (s->P.sigma_type == BVG_SIGMA_SV) ? 1 : 0;
+  int rc = bvg_loglik_draws(s->d_coef, s->d_sigma, (int64_t)s->n_chains * s->P.iterations, s->P.k, s->P.M, T, s->P.tvp,
+                            tv_sigma, s->bm.Y, s->bm.X, d_ll, cuda_stream);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(host_ll_t, d_ll, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "log-likelihood copy");
+  }
+  cudaFree(d_ll);
+  return rc;
+}
+
+int bvg_loglik_draws_host(const double* coef, const double* sigma, int64_t n_draws, int32_t k, int32_t M, int32_t T,
+                          int32_t tvp, int32_t tv_sigma, const double* Y, const double* X, double* ll_t) {
+  if (!sigma || !Y || !ll_t || (M > 0 && (!coef || !X)) || n_draws < 1)
+    return fail(-1, "invalid arguments to bvg_loglik_draws_host");
+  if (k < 1 || k > 32) return fail(-2, "bvg_loglik_draws_host supports 1 <= k <= 32");
+  if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");
+  const size_t cs = (size_t)k * M * (tvp ? T : 1), ss = (size_t)k * k * (tv_sigma ? T : 1);
+  // draws go through the device in chunks of <= 256 MB; the per-period sums of the chunks are added on the host
+  int64_t chunk = (int64_t)((256u << 20) / ((cs + ss) * sizeof(double)));
+  if (chunk < 1) chunk = 1;
+  if (chunk > n_draws) chunk = n_draws;
+  double *dY = nullptr, *dX = nullptr, *dc = nullptr, *ds = nullptr, *dl = nullptr;
+  std::vector<double> part((size_t)T);
+  int rc = 0;
+  cudaError_t e = cudaSuccess;
+  auto done = [&](int r) { cudaFree(dY); cudaFree(dX); cudaFree(dc); cudaFree(ds); cudaFree(dl); return r; };
+  if ((e = cudaMalloc((void**)&dY, (size_t)k * T * sizeof(double))) != cudaSuccess) return done(cuda_fail(e, "cudaMalloc"));
+  if (M > 0 && (e = cudaMalloc((void**)&dX, (size_t)M * T * sizeof(double))) != cudaSuccess) return done(cuda_fail(e, "cudaMalloc"));
+  if (M > 0 && (e = cudaMalloc((void**)&dc, (size_t)chunk * cs * sizeof(double))) != cudaSuccess) return done(cuda_fail(e, "cudaMalloc"));
+  if ((e = cudaMalloc((void**)&ds, (size_t)chunk * ss * sizeof(double))) != cudaSuccess) return done(cuda_fail(e, "cudaMalloc"));
+  if ((e = cudaMalloc((void**)&dl, (size_t)T * sizeof(double))) != cudaSuccess) return done(cuda_fail(e, "cudaMalloc"));
+  if ((e = cudaMemcpy(dY, Y, (size_t)k * T * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return done(cuda_fail(e, "cudaMemcpy"));
+  if (M > 0 && (e = cudaMemcpy(dX, X, (size_t)M * T * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return done(cuda_fail(e, "cudaMemcpy"));
+  for (int t = 0; t < T; ++t) ll_t[t] = 0.0;
+  for (int64_t d0 = 0; d0 < n_draws && rc == 0; d0 += chunk) {
+    const int64_t nd = (d0 + chunk <= n_draws) ? chunk : n_draws - d0;
+    if (M > 0 && (e = cudaMemcpy(dc, coef + (size_t)d0 * cs, (size_t)nd * cs * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return done(cuda_fail(e, "cudaMemcpy"));
+    if ((e = cudaMemcpy(ds, sigma + (size_t)d0 * ss, (size_t)nd * ss * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return done(cuda_fail(e, "cudaMemcpy"));
+    rc = bvg_loglik_draws(dc, ds, nd, k, M, T, tvp, tv_sigma, dY, dX, dl, nullptr);
+    if (rc) break;
+    if ((e = cudaMemcpy(part.data(), dl, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) return done(cuda_fail(e, "cudaMemcpy"));
+    for (int t = 0; t < T; ++t) ll_t[t] += part[t];
+  }
+  return done(rc);
+}
+
+int bvg_loglik_normal(const double* u, const double* sigma, int32_t k, int32_t T, int32_t sigma_rows, int64_t n_batch,
+                      double* out) {
+  if (!u || !sigma || !out || k < 1 || T < 1 || n_batch < 1) return fail(-1, "invalid arguments to bvg_loglik_normal");
+  if (sigma_rows != k && sigma_rows != k * T) return fail(-3, "sigma must be k x k or (k T) x k");
+  if (k > 32) return fail(-2, "bvg_loglik_normal supports k <= 32");
+  if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");
+  for (int64_t e = 0; e < n_batch * (int64_t)k * T; ++e)
+    if (u[e] != u[e]) return fail(-20, "Argument 'u' contains NAs.");
+  const int tv = sigma_rows > k ? 1 : 0;
+  const size_t sg_len = (size_t)k * k * (tv ? T : 1);
+  std::vector<double> sg(sg_len * (size_t)n_batch);
+  for (int64_t b = 0; b < n_batch; ++b) {
+    const double* src = sigma + (size_t)b * sigma_rows * k;
+    double* dst = sg.data() + (size_t)b * sg_len;
+    if (!tv) { for (size_t e = 0; e < sg_len; ++e) dst[e] = src[e]; }
+    else  // rows t k .. (t + 1) k - 1 of the (k T) x k column-major stack  (loglik_normal.cpp:47-48)
+      for (int t = 0; t < T; ++t)
+        for (int c = 0; c < k; ++c)
+          for (int r = 0; r < k; ++r) dst[(size_t)t * k * k + r + (size_t)k * c] = src[(size_t)t * k + r + (size_t)sigma_rows * c];
+  }
+  double *d_u = nullptr, *d_sg = nullptr, *d_out = nullptr;
+  CK(cudaMalloc((void**)&d_u, (size_t)n_batch * k * T * sizeof(double)));
+  CK(cudaMalloc((void**)&d_sg, sg.size() * sizeof(double)));
+  CK(cudaMalloc((void**)&d_out, (size_t)n_batch * T * sizeof(double)));
+  CK(cudaMemcpy(d_u, u, (size_t)n_batch * k * T * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_sg, sg.data(), sg.size() * sizeof(double), cudaMemcpyHostToDevice));
+  int rc = 0;
+  for (int64_t b = 0; b < n_batch && rc == 0; ++b)   // one "draw" whose residuals are the data: u = Y, no regressors
+    rc = bvg_loglik_draws(nullptr, d_sg + (size_t)b * sg_len, 1, k, 0, T, 0, tv, d_u + (size_t)b * k * T, nullptr,
+                          d_out + (size_t)b * T, nullptr);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpy(out, d_out, (size_t)n_batch * T * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = cuda_fail(e, "log-likelihood copy");
+  }
+  cudaFree(d_u); cudaFree(d_sg); cudaFree(d_out);
+  return rc;
+}
+
 int bvg_fp64_peak(double* tflops_fma, void* cuda_stream) {
   if (!tflops_fma) return fail(-1, "output pointer is NULL");
   if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");

@@ -39,6 +39,10 @@ cudaError_t launch_tvp(const LaunchPlan& plan, const TvpModel& m, const RngParam
                        int state_len, double* scratch, long long scratch_per_chain, const TvpOut& out,
                        long long n_chains, int sweep_begin, int sweep_end, int burnin, cudaStream_t stream);
 
+// log-likelihood of resident draws reduced to per-period sums (bvg_loglik.cu)
+cudaError_t launch_loglik_draws(int k, int M, int T, int tvp, int tv_sigma, long long n_draws, const double* dY,
+                                const double* dX, const double* d_coef, const double* d_sigma, double* d_ll_t,
+                                cudaStream_t stream);
 cudaError_t launch_moments(const double* draws, long long chains, long long iters, long long rows, double* sums,
                            double* sumsq, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* tflops, cudaStream_t stream);

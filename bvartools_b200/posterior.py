@@ -13,9 +13,12 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import sampler
+import ctypes as C
 
-__all__ = ["draw_posterior", "bvarpost", "bvar", "summary"]
+from . import sampler
+from ._lib import check, lib, require_device
+
+__all__ = ["draw_posterior", "bvarpost", "bvar", "summary", "summary_bvarlist", "information_criteria"]
 
 
 def bvar(y, x=None, A0=None, A=None, B=None, C=None, Sigma=None):
@@ -100,3 +103,54 @@ def summary(obj, ci=(0.025, 0.5, 0.975)):
         res[name] = {"mean": d.mean(axis=0), "sd": d.std(axis=0, ddof=1),
                      "quantiles": np.quantile(d, ci, axis=0)}
     return res
+
+
+def information_criteria(ll, tot_pars, tt):
+    """LL -> AIC / BIC / HQ as in R/summary.bvarlist.R:181-184 (tot_pars = NCOL(x) for a VAR, :62)."""
+    return {"LL": float(ll), "AIC": 2.0 * tot_pars - 2.0 * ll, "BIC": np.log(tt) * tot_pars - 2.0 * ll,
+            "HQ": 2.0 * np.log(np.log(tt)) * tot_pars - 2.0 * ll}
+
+
+def summary_bvarlist(objects):
+    """summary method for a list of `bvar` objects (R/summary.bvarlist.R:22-215): one row per model with p, s, LL, AIC,
+    BIC and HQ.  The reference loops over every draw in R and calls loglik_normal per draw (:160-180); here the draws
+    go through one fused device reduction (bvg_loglik_draws_host) that returns the per-period sums."""
+    require_device()
+    dp = C.POINTER(C.c_double)
+    rows = []
+    for obj in objects:
+        if obj.get("error"):
+            rows.append(None)                                   # :41-45 `next`
+            continue
+        y = np.ascontiguousarray(np.asarray(obj["y"], dtype=np.float64))          # T x K: (t, i) at i + K t
+        tt, k = y.shape
+        x = obj.get("x")
+        tvp_flags = obj["specifications"]["tvp"]
+        tvp = any(bool(v) for v in tvp_flags.values())
+        sv = bool(tvp_flags.get("Sigma"))
+        parts = [obj[name] for name in ("A", "B", "C") if obj.get(name) is not None]   # :65-76 cbind(A, B, C)
+        if parts and isinstance(parts[0], list):
+            coef = np.stack([np.concatenate([p[t] for p in parts], axis=1) for t in range(tt)], axis=1)  # [draw][T][n]
+        elif parts:
+            coef = np.concatenate(parts, axis=1)                                     # [draw][n]
+        else:
+            coef = None
+        m = 0 if x is None else np.asarray(x).shape[1]
+        xs = None if x is None else np.ascontiguousarray(np.asarray(x, dtype=np.float64))   # T x M: (t, j) at j + M t
+        sig = obj["Sigma"]
+        sig = np.stack(sig, axis=1) if isinstance(sig, list) else np.asarray(sig)    # [draw][T][k k] or [draw][k k]
+        sig = np.ascontiguousarray(sig, dtype=np.float64)
+        draws = sig.shape[0]
+        coef_c = None if coef is None else np.ascontiguousarray(coef, dtype=np.float64)
+        coef_is_tvp = coef_c is not None and coef_c.ndim == 3
+        ll_t = np.empty(tt, dtype=np.float64)
+        check(lib().bvg_loglik_draws_host(None if coef_c is None else coef_c.ctypes.data_as(dp), sig.ctypes.data_as(dp),
+                                          draws, k, m, tt, int(coef_is_tvp), int(sv), y.ctypes.data_as(dp),
+                                          None if xs is None else xs.ctypes.data_as(dp), ll_t.ctypes.data_as(dp)))
+        ll = float(np.sum(ll_t / draws))                                             # sum(rowMeans(LL)), :181
+        row = {"p": obj["specifications"]["lags"].get("p"), "s": obj["specifications"]["lags"].get("s")}
+        row.update(information_criteria(ll, m, tt))
+        row["ll_t"] = ll_t / draws
+        rows.append(row)
+    return rows
+

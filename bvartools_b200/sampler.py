@@ -100,6 +100,15 @@ class ChainSampler:
     def kernel_name(self):
         return lib().bvg_sampler_kernel_name(self.handle).decode()
 
+    def loglik(self, stream=0):
+        """Per-period log-likelihood SUMS over all retained draws resident on the device (chains x iterations):
+        the reduction behind summary.bvarlist (R/summary.bvarlist.R:160-186, src/loglik_normal.cpp:37-58).
+        Returns (ll_t, n_draws); LL of the reference = ll_t.sum() / n_draws."""
+        T = int(self.spec.c.T)
+        out = np.empty(T, dtype=np.float64)
+        check(lib().bvg_sampler_loglik(self.handle, out.ctypes.data_as(C.POINTER(C.c_double)), C.c_void_p(stream or 0)))
+        return out, int(self.spec.c.n_chains) * int(self.spec.c.iterations)
+
     def close(self):
         if self.handle:
             lib().bvg_sampler_destroy(self.handle)

@@ -173,6 +173,30 @@ void bvg_set_interrupt_poll(int (*poll)(void));
 int bvg_moments(const double* dev_draws, int64_t chains, int64_t iters, int64_t rows, double* dev_sums,
                 double* dev_sumsq, void* cuda_stream);
 
+/* ---- model comparison: log-likelihood of posterior draws ---------------------------------------
+ * Replaces the per-draw R loop of summary.bvarlist (R/summary.bvarlist.R:160-186), which calls
+ * loglik_normal (src/loglik_normal.cpp:37-58, R/RcppExports.R:313) once per draw:
+ *   LL[t, j] = -k/2 ln(2 pi) - ln|Sigma_t^(j)|/2 - u_t' (Sigma_t^(j))^-1 u_t / 2,   u_t = y_t - A_t^(j) x_t .
+ * dev_ll_t[t] (T doubles) receives the SUM over the n_draws draws (the caller divides by the number of draws; ranks
+ * all-reduce the sums); ll = sum_t dev_ll_t[t] / n_draws, AIC = 2 M - 2 ll, BIC = ln(T) M - 2 ll, HQ = 2 ln ln(T) M - 2 ll
+ * (tot_pars = NCOL(x) = M, R/summary.bvarlist.R:62,181-184).
+ * Layouts as produced by the samplers: dev_coef [draw][n] (tvp: [draw][T][n]), dev_sigma [draw][k*k] (tv_sigma:
+ * [draw][T][k*k]), dev_Y k x T, dev_X M x T column-major; all device pointers.  1 <= k <= 32. */
+int bvg_loglik_draws(const double* dev_coef, const double* dev_sigma, int64_t n_draws, int32_t k, int32_t M, int32_t T,
+                     int32_t tvp, int32_t tv_sigma, const double* dev_Y, const double* dev_X, double* dev_ll_t,
+                     void* cuda_stream);
+/* the same with every buffer on the HOST (draws of a finished `bvar` object, as summary.bvarlist receives them): the
+ * draws pass through the device in chunks; ll_t: T doubles on the host */
+int bvg_loglik_draws_host(const double* coef, const double* sigma, int64_t n_draws, int32_t k, int32_t M, int32_t T,
+                          int32_t tvp, int32_t tv_sigma, const double* Y, const double* X, double* ll_t);
+/* the same over all retained draws resident in a sampler (chains x iterations); host_ll_t: T doubles on the host */
+int bvg_sampler_loglik(bvg_sampler* s, double* host_ll_t, void* cuda_stream);
+/* stand-alone block, host buffers: loglik_normal(u, sigma) of src/loglik_normal.cpp:37-58 for n_batch problems.
+ * u: k x T per problem; sigma: k x k (sigma_rows = k) or the (k T) x k stack of per-period matrices (sigma_rows = k T),
+ * column-major as in R; out: T per problem.  NaN in u -> -20 (the R wrapper's stop()). */
+int bvg_loglik_normal(const double* u, const double* sigma, int32_t k, int32_t T, int32_t sigma_rows, int64_t n_batch,
+                      double* out);
+
 /* measured FP64 FMA throughput of the device (TFLOP/s) -- roofline denominator for the sweep kernels */
 int bvg_fp64_peak(double* tflops_fma, void* cuda_stream);
 /* measured FP64 tensor-core (DMMA m8n8k4) throughput (TFLOP/s) -- denominator for the large-VAR Cholesky */

@@ -239,3 +239,56 @@ def kalman_dk(y, z, sigma_u, sigma_v, B, a_init, P_init, eps0, eps_y, eps_a):
         kv = slice(i * nvars, (i + 1) * nvars)
         a[:, i + 1] = B[kv] @ a[:, i] + sigma_v[kv] @ r[:, i]
     return a + aplus
+
+
+def loglik_normal(u, sigma):
+    """src/loglik_normal.cpp:37-58, literally: part_a = -k log(2 pi) / 2, part_b = -log(det(Sigma)) / 2,
+    part_c = -u_t' solve(Sigma, I) u_t / 2; sigma with more rows than u is the (k T) x k stack of per-period blocks."""
+    u = np.asarray(u, dtype=float)
+    sigma = np.asarray(sigma, dtype=float)
+    k, t = u.shape
+    dmat = np.eye(k)
+    result = np.zeros(t)
+    part_a = -k * np.log(2 * np.pi) / 2
+    if sigma.shape[0] > k:
+        for i in range(t):
+            blk = sigma[i * k:(i + 1) * k, :]
+            part_b = -np.log(np.linalg.det(blk)) / 2
+            part_c = -float(u[:, i] @ np.linalg.solve(blk, dmat) @ u[:, i]) / 2
+            result[i] = part_a + part_b + part_c
+    else:
+        part_b = -np.log(np.linalg.det(sigma)) / 2
+        si = np.linalg.solve(sigma, dmat)
+        for i in range(t):
+            part_c = -float(u[:, i] @ si @ u[:, i]) / 2
+            result[i] = part_a + part_b + part_c
+    return result
+
+
+def summary_bvarlist_row(y, x, temp_pars, sigma_draws, tvp=False, sv=False):
+    """The per-model body of R/summary.bvarlist.R:143-185 for a `bvar` object: y (T x K), x (T x M), temp_pars =
+    cbind(A, B, C) draws (draws x n; TVP: list over periods), sigma_draws (draws x K^2; SV: list over periods).
+    Returns dict(LL, AIC, BIC, HQ, ll_t = rowMeans(LL))."""
+    y = np.asarray(y, dtype=float)
+    tt, k = y.shape
+    xm = np.asarray(x, dtype=float).T                      # :60 x <- t(object$x)
+    tot_pars = xm.shape[0]
+    draws = temp_pars[0].shape[0] if tvp else temp_pars.shape[0]
+    LL = np.full((tt, draws), np.nan)
+    yt = y.T
+    for j in range(draws):
+        if tvp:
+            u = np.empty_like(yt)
+            for period in range(tt):
+                u[:, period] = yt[:, period] - temp_pars[period][j].reshape(k, -1, order="F") @ xm[:, period]
+        else:
+            u = yt - temp_pars[j].reshape(k, -1, order="F") @ xm
+        if sv:
+            sigma = np.vstack([sigma_draws[period][j].reshape(k, k, order="F") for period in range(tt)])
+        else:
+            sigma = sigma_draws[j].reshape(k, k, order="F")
+        LL[:, j] = loglik_normal(u, sigma)
+    ll = float(np.sum(LL.mean(axis=1)))
+    return {"LL": ll, "AIC": 2 * tot_pars - 2 * ll, "BIC": np.log(tt) * tot_pars - 2 * ll,
+            "HQ": 2 * np.log(np.log(tt)) * tot_pars - 2 * ll, "ll_t": LL.mean(axis=1)}
+
