@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--cpu-sweeps", type=int, default=0, help="sweeps per chain of the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-loglik", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -279,6 +280,27 @@ def main():
     value = total_draws / (ms_per_step * 1e-3)
     post_mean = (sums / (world * chains * it)).cpu().numpy()
     tpc_used = sampler.spec.c.threads_per_chain
+
+    # ---- next-row kernel: summary.bvarlist log-likelihood over the draws resident in HBM
+    model_cmp = None
+    if not args.no_loglik:
+        try:
+            ll_ms = []
+            for i in range(4):
+                fence()
+                t0 = time.perf_counter()
+                ll_tot, n_dr = sampler.loglik_total(stream.cuda_stream)
+                dt = time.perf_counter() - t0
+                if i > 0:
+                    ll_ms.append(dt * 1e3)
+            rd_bytes = 8.0 * chains * it * (rows["coef"] + rows["sigma"])
+            ms = float(np.median(ll_ms))
+            model_cmp = {"what": "bvg_sampler_loglik_total: log-likelihood of summary.bvarlist over all resident draws "
+                                 "(R/summary.bvarlist.R:160-186), incl. the result D2H; bound: HBM (draws read once)", "ms": ms,
+                         "draws_per_s": n_dr / (ms * 1e-3), "read_GBps": rd_bytes / (ms * 1e-3) / 1e9,
+                         "LL": float(ll_tot / n_dr)}
+        except Exception as exc:       # never let the auxiliary measurement break the bench line
+            model_cmp = {"error": str(exc)}
 
     # ---- end to end through the public API: host inputs -> H2D -> sweeps -> D2H into pinned host memory
     e2e = None
@@ -388,6 +410,23 @@ def main():
     roofline.update({"sweep_kernel_ms_per_step": last_sweep_ms, "sweep_launches_per_step": n_sweep_launches,
                      "sweep_share_of_step": last_sweep_ms / ms_per_step,
                      "hbm_write_GBps": out_bytes / sweep_kernel_s / 1e9, "hbm_peak_GBps": hbm_peak})
+    if model_cmp and "read_GBps" in model_cmp:
+        model_cmp["hbm_frac"] = model_cmp["read_GBps"] / hbm_peak
+        if not args.no_cpu and not obj["model"].get("tvp") and not obj["model"].get("sv"):
+            # the reference's per-draw loop (oracle restatement of R/summary.bvarlist.R:160-180) on a bounded sample
+            from oracle import blocks as ob
+            rng = np.random.default_rng(0)
+            Yh, Zh = obj["data"]["Y"], obj["data"]["Z"]
+            kk_ = Yh.shape[1]
+            nd = 2000
+            ols = np.linalg.lstsq(Zh, Yh, rcond=None)[0].T
+            pars = np.stack([(ols + 0.01 * rng.standard_normal(ols.shape)).reshape(-1, order="F") for _ in range(nd)])
+            sg = np.stack([np.cov((Yh - Zh @ ols.T).T).reshape(-1, order="F") for _ in range(nd)])
+            t0 = time.perf_counter()
+            ob.summary_bvarlist_row(Yh, Zh, pars, sg)
+            dtc = time.perf_counter() - t0
+            model_cmp["cpu_baseline"] = {"draws_per_s": nd / dtc, "cores": 1, "kind": "port",
+                                         "sample": f"{nd} draws, oracle/blocks.py summary_bvarlist_row (per-draw loop)"}
     cpu = None
     if not args.no_cpu:
         cpu = cpu_reference_run(obj, label, 1, 0, cpu_sweeps, False)
@@ -402,7 +441,7 @@ def main():
                        "l2": f"retained draws {out_bytes / 1e9:.2f} GB per step per GPU >> 126 MB L2 (no flush needed)",
                        "threads_per_chain": tpc_used or "auto"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "model_comparison": model_cmp,
             "posterior_mean_first3": [float(v) for v in post_mean[:3]]}
     print(json.dumps(line), flush=True)
     if world > 1:

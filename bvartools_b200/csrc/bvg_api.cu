@@ -516,6 +516,128 @@ int bvg_loglik_draws_host(const double* coef, const double* sigma, int64_t n_dra
   return done(rc);
 }
 
+// OLS moments of a VAR on the host: XX' (M x M), A_ols (k x M), SSE_ols (k x k); false when X'X is (numerically) singular
+static bool host_ols_moments(const double* Y, const double* X, int k, int M, int T, std::vector<double>& XX,
+                             std::vector<double>& A, std::vector<double>& SSE) {
+  if (T <= M || M < 1) return false;
+  XX.assign((size_t)M * M, 0.0); A.assign((size_t)k * M, 0.0); SSE.assign((size_t)k * k, 0.0);
+  std::vector<double> YX((size_t)k * M, 0.0);
+  for (int t = 0; t < T; ++t) {
+    const double* xt = X + (size_t)M * t;
+    const double* yt = Y + (size_t)k * t;
+    for (int j = 0; j < M; ++j) {
+      for (int j2 = 0; j2 < M; ++j2) XX[j + (size_t)M * j2] += xt[j] * xt[j2];
+      for (int i = 0; i < k; ++i) YX[i + (size_t)k * j] += yt[i] * xt[j];
+    }
+  }
+  std::vector<long double> Cm((size_t)M * M);
+  for (size_t e = 0; e < Cm.size(); ++e) Cm[e] = XX[e];
+  if (!chol_ld(Cm, M)) return false;
+  long double dmin = Cm[0], dmax = Cm[0];
+  for (int j = 0; j < M; ++j) { const long double dd = Cm[j + (size_t)M * j]; if (dd < dmin) dmin = dd; if (dd > dmax) dmax = dd; }
+  if (dmin < 1e-7L * dmax) return false;
+  std::vector<long double> b(M), u(k), sse((size_t)k * k, 0.0L);
+  for (int i = 0; i < k; ++i) {
+    for (int j = 0; j < M; ++j) b[j] = YX[i + (size_t)k * j];
+    for (int j = 0; j < M; ++j) {
+      long double v = b[j];
+      for (int c = 0; c < j; ++c) v -= Cm[j + (size_t)M * c] * b[c];
+      b[j] = v / Cm[j + (size_t)M * j];
+    }
+    for (int j = M - 1; j >= 0; --j) {
+      long double v = b[j];
+      for (int c = j + 1; c < M; ++c) v -= Cm[c + (size_t)M * j] * b[c];
+      b[j] = v / Cm[j + (size_t)M * j];
+    }
+    for (int j = 0; j < M; ++j) A[i + (size_t)k * j] = (double)b[j];
+  }
+  for (int t = 0; t < T; ++t) {
+    for (int i = 0; i < k; ++i) {
+      long double v = Y[i + (size_t)k * t];
+      for (int j = 0; j < M; ++j) v -= (long double)A[i + (size_t)k * j] * X[j + (size_t)M * t];
+      u[i] = v;
+    }
+    for (int i = 0; i < k; ++i)
+      for (int j = 0; j < k; ++j) sse[i + (size_t)k * j] += u[i] * u[j];
+  }
+  for (int e = 0; e < k * k; ++e) SSE[e] = (double)sse[e];
+  return true;
+}
+
+int bvg_sampler_loglik_total(bvg_sampler* s, double* total, void* cuda_stream) {
+  if (!s || !total) return fail(-1, "sampler / output is NULL");
+  CK(cudaSetDevice(s->device));
+  const bool fast = !s->P.tvp && s->P.sigma_type != BVG_SIGMA_SV && s->P.M > 0 && s->bm.XX && s->bm.Aols && s->bm.SSE &&
+                    s->P.k <= 32;
+  if (!fast) {                           // time-varying coefficients / variances: per-period kernel, summed on the host
+    std::vector<double> ll((size_t)s->P.T);
+    int rc = bvg_sampler_loglik(s, ll.data(), cuda_stream);
+    if (rc) return rc;
+    double t = 0.0;
+    for (double v : ll) t += v;
+    *total = t;
+    return 0;
+  }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  double* d_tot = nullptr;
+  CK(cudaMalloc((void**)&d_tot, sizeof(double)));
+  cudaError_t e = launch_loglik_total(s->P.k, s->P.M, s->P.T, (long long)s->n_chains * s->P.iterations, s->bm.XX,
+                                      s->bm.Aols, s->bm.SSE, s->d_coef, s->d_sigma, d_tot, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(total, d_tot, sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_tot);
+  if (e != cudaSuccess) return cuda_fail(e, "total log-likelihood kernel");
+  return 0;
+}
+
+int bvg_loglik_total_host(const double* coef, const double* sigma, int64_t n_draws, int32_t k, int32_t M, int32_t T,
+                          const double* Y, const double* X, double* total) {
+  if (!coef || !sigma || !Y || !X || !total || n_draws < 1 || M < 1)
+    return fail(-1, "invalid arguments to bvg_loglik_total_host");
+  if (k < 1 || k > 32) return fail(-2, "bvg_loglik_total_host supports 1 <= k <= 32");
+  if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");
+  std::vector<double> XX, A, SSE;
+  if (!host_ols_moments(Y, X, k, M, T, XX, A, SSE)) {           // no OLS projection: per-period path
+    std::vector<double> ll((size_t)T);
+    int rc = bvg_loglik_draws_host(coef, sigma, n_draws, k, M, T, 0, 0, Y, X, ll.data());
+    if (rc) return rc;
+    double t = 0.0;
+    for (double v : ll) t += v;
+    *total = t;
+    return 0;
+  }
+  const size_t cs = (size_t)k * M, ss = (size_t)k * k;
+  int64_t chunk = (int64_t)((256u << 20) / ((cs + ss) * sizeof(double)));
+  if (chunk < 1) chunk = 1;
+  if (chunk > n_draws) chunk = n_draws;
+  double *dXX = nullptr, *dA = nullptr, *dS = nullptr, *dc = nullptr, *ds = nullptr, *dt = nullptr;
+  cudaError_t e = cudaSuccess;
+  auto done = [&](int r) { cudaFree(dXX); cudaFree(dA); cudaFree(dS); cudaFree(dc); cudaFree(ds); cudaFree(dt); return r; };
+#define BVG_TRY(call) do { if ((e = (call)) != cudaSuccess) return done(cuda_fail(e, #call)); } while (0)
+  BVG_TRY(cudaMalloc((void**)&dXX, XX.size() * sizeof(double)));
+  BVG_TRY(cudaMalloc((void**)&dA, A.size() * sizeof(double)));
+  BVG_TRY(cudaMalloc((void**)&dS, SSE.size() * sizeof(double)));
+  BVG_TRY(cudaMalloc((void**)&dc, (size_t)chunk * cs * sizeof(double)));
+  BVG_TRY(cudaMalloc((void**)&ds, (size_t)chunk * ss * sizeof(double)));
+  BVG_TRY(cudaMalloc((void**)&dt, sizeof(double)));
+  BVG_TRY(cudaMemcpy(dXX, XX.data(), XX.size() * sizeof(double), cudaMemcpyHostToDevice));
+  BVG_TRY(cudaMemcpy(dA, A.data(), A.size() * sizeof(double), cudaMemcpyHostToDevice));
+  BVG_TRY(cudaMemcpy(dS, SSE.data(), SSE.size() * sizeof(double), cudaMemcpyHostToDevice));
+  double sum = 0.0;
+  for (int64_t d0 = 0; d0 < n_draws; d0 += chunk) {
+    const int64_t nd = (d0 + chunk <= n_draws) ? chunk : n_draws - d0;
+    BVG_TRY(cudaMemcpy(dc, coef + (size_t)d0 * cs, (size_t)nd * cs * sizeof(double), cudaMemcpyHostToDevice));
+    BVG_TRY(cudaMemcpy(ds, sigma + (size_t)d0 * ss, (size_t)nd * ss * sizeof(double), cudaMemcpyHostToDevice));
+    BVG_TRY(launch_loglik_total(k, M, T, nd, dXX, dA, dS, dc, ds, dt, nullptr));
+    double part = 0.0;
+    BVG_TRY(cudaMemcpy(&part, dt, sizeof(double), cudaMemcpyDeviceToHost));
+    sum += part;
+  }
+#undef BVG_TRY
+  *total = sum;
+  return done(0);
+}
+
 int bvg_loglik_normal(const double* u, const double* sigma, int32_t k, int32_t T, int32_t sigma_rows, int64_t n_batch,
                       double* out) {
   if (!u || !sigma || !out || k < 1 || T < 1 || n_batch < 1) return fail(-1, "invalid arguments to bvg_loglik_normal");

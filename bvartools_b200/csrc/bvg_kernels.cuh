@@ -43,6 +43,9 @@ cudaError_t launch_tvp(const LaunchPlan& plan, const TvpModel& m, const RngParam
 cudaError_t launch_loglik_draws(int k, int M, int T, int tvp, int tv_sigma, long long n_draws, const double* dY,
                                 const double* dX, const double* d_coef, const double* d_sigma, double* d_ll_t,
                                 cudaStream_t stream);
+cudaError_t launch_loglik_total(int k, int M, int T, long long n_draws, const double* dXX, const double* dAols,
+                                const double* dSSE, const double* d_coef, const double* d_sigma, double* d_total,
+                                cudaStream_t stream);
 cudaError_t launch_moments(const double* draws, long long chains, long long iters, long long rows, double* sums,
                            double* sumsq, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* tflops, cudaStream_t stream);

@@ -143,14 +143,23 @@ def summary_bvarlist(objects):
         draws = sig.shape[0]
         coef_c = None if coef is None else np.ascontiguousarray(coef, dtype=np.float64)
         coef_is_tvp = coef_c is not None and coef_c.ndim == 3
-        ll_t = np.empty(tt, dtype=np.float64)
-        check(lib().bvg_loglik_draws_host(None if coef_c is None else coef_c.ctypes.data_as(dp), sig.ctypes.data_as(dp),
-                                          draws, k, m, tt, int(coef_is_tvp), int(sv), y.ctypes.data_as(dp),
-                                          None if xs is None else xs.ctypes.data_as(dp), ll_t.ctypes.data_as(dp)))
-        ll = float(np.sum(ll_t / draws))                                             # sum(rowMeans(LL)), :181
         row = {"p": obj["specifications"]["lags"].get("p"), "s": obj["specifications"]["lags"].get("s")}
+        if coef_c is not None and not coef_is_tvp and not sv:
+            # constant model: total log-likelihood straight from cross moments (HBM-bound, no loop over periods)
+            tot = C.c_double(0.0)
+            check(lib().bvg_loglik_total_host(coef_c.ctypes.data_as(dp), sig.ctypes.data_as(dp), draws, k, m, tt,
+                                              y.ctypes.data_as(dp), xs.ctypes.data_as(dp), C.byref(tot)))
+            ll = tot.value / draws
+            row["ll_t"] = None
+        else:
+            ll_t = np.empty(tt, dtype=np.float64)
+            check(lib().bvg_loglik_draws_host(None if coef_c is None else coef_c.ctypes.data_as(dp),
+                                              sig.ctypes.data_as(dp), draws, k, m, tt, int(coef_is_tvp), int(sv),
+                                              y.ctypes.data_as(dp), None if xs is None else xs.ctypes.data_as(dp),
+                                              ll_t.ctypes.data_as(dp)))
+            ll = float(np.sum(ll_t / draws))                                         # sum(rowMeans(LL)), :181
+            row["ll_t"] = ll_t / draws
         row.update(information_criteria(ll, m, tt))
-        row["ll_t"] = ll_t / draws
         rows.append(row)
     return rows
 

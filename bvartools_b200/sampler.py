@@ -109,6 +109,13 @@ class ChainSampler:
         check(lib().bvg_sampler_loglik(self.handle, out.ctypes.data_as(C.POINTER(C.c_double)), C.c_void_p(stream or 0)))
         return out, int(self.spec.c.n_chains) * int(self.spec.c.iterations)
 
+    def loglik_total(self, stream=0):
+        """Total log-likelihood SUM over all resident retained draws (all that LL / AIC / BIC / HQ need); constant
+        models take the HBM-bound cross-moment kernel (no pass over the periods).  Returns (total, n_draws)."""
+        tot = C.c_double(0.0)
+        check(lib().bvg_sampler_loglik_total(self.handle, C.byref(tot), C.c_void_p(stream or 0)))
+        return tot.value, int(self.spec.c.n_chains) * int(self.spec.c.iterations)
+
     def close(self):
         if self.handle:
             lib().bvg_sampler_destroy(self.handle)

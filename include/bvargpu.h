@@ -191,6 +191,13 @@ int bvg_loglik_draws_host(const double* coef, const double* sigma, int64_t n_dra
                           int32_t tvp, int32_t tv_sigma, const double* Y, const double* X, double* ll_t);
 /* the same over all retained draws resident in a sampler (chains x iterations); host_ll_t: T doubles on the host */
 int bvg_sampler_loglik(bvg_sampler* s, double* host_ll_t, void* cuda_stream);
+/* TOTAL log-likelihood sum_draws sum_t LL[t, draw] -- all the information criteria need.  For constant-parameter,
+ * constant-variance models this does not loop over the periods: sum_t u_t' Sigma^-1 u_t = tr(Sigma^-1 S) with
+ * S = SSE_ols + (A - A_ols) XX' (A - A_ols)', an HBM-bound pass over the draws; other models (and a rank-deficient X)
+ * fall back to the per-period kernel.  *total on the host. */
+int bvg_sampler_loglik_total(bvg_sampler* s, double* total, void* cuda_stream);
+int bvg_loglik_total_host(const double* coef, const double* sigma, int64_t n_draws, int32_t k, int32_t M, int32_t T,
+                          const double* Y, const double* X, double* total);
 /* stand-alone block, host buffers: loglik_normal(u, sigma) of src/loglik_normal.cpp:37-58 for n_batch problems.
  * u: k x T per problem; sigma: k x k (sigma_rows = k) or the (k T) x k stack of per-period matrices (sigma_rows = k T),
  * column-major as in R; out: T per problem.  NaN in u -> -20 (the R wrapper's stop()). */

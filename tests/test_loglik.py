@@ -112,7 +112,8 @@ def test_summary_bvarlist_matches_oracle_loop(gpu, case):
         want = ob.summary_bvarlist_row(obj["data"]["Y"], obj["data"]["Z"], pars, sig, tvp=tvp, sv=sv)
         for key in ("LL", "AIC", "BIC", "HQ"):
             assert abs(row[key] - want[key]) <= TOL * abs(want[key]), (case, key, row[key], want[key])
-        assert helpers.relerr(row["ll_t"], want["ll_t"]) < TOL
+        if row["ll_t"] is not None:
+            assert helpers.relerr(row["ll_t"], want["ll_t"]) < TOL
 
 
 @pytest.mark.gpu
@@ -136,6 +137,8 @@ def test_resident_draws_and_host_draws_agree_and_shard(gpu):
         want += ob.loglik_normal(u, sig[j].reshape(k, k, order="F"))
     assert n_full == 12 * 30
     assert helpers.relerr(ll_full, want) < TOL
+    tot, n_tot = full.loglik_total()                       # cross-moment kernel: no pass over the periods
+    assert n_tot == n_full and abs(tot - want.sum()) <= TOL * abs(want.sum())
     parts = np.zeros(T)
     for off, cnt in ((0, 5), (5, 7)):
         s = ChainSampler(obj, n_chains=cnt, seed=5, chain_offset=off)
@@ -145,3 +148,31 @@ def test_resident_draws_and_host_draws_agree_and_shard(gpu):
         s.close()
     np.testing.assert_allclose(parts, ll_full, rtol=1e-12)
     full.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,p", [(1, 1), (3, 4), (6, 2)])
+def test_total_kernel_matches_per_period_kernel(gpu, k, p):
+    """The HBM-bound total (cross-moment form) against the per-period kernel and the oracle on random draws."""
+    import ctypes as C
+    from bvartools_b200._lib import check, lib
+    rng = np.random.default_rng(10 * k + p)
+    y = helpers.synth_var(k, p, 90, 4)
+    m = helpers.gen_var(y, p=p, deterministic="const", iterations=5, burnin=1)
+    Y, Z = np.ascontiguousarray(m["data"]["Y"]), np.ascontiguousarray(m["data"]["Z"])
+    T, M = Z.shape
+    draws = 37
+    ols = np.linalg.lstsq(Z, Y, rcond=None)[0].T                                   # k x M
+    coef = np.stack([(ols + 0.05 * rng.standard_normal(ols.shape)).reshape(-1, order="F") for _ in range(draws)])
+    sig = np.stack([_spd(rng, k).reshape(-1, order="F") for _ in range(draws)])
+    dp = C.POINTER(C.c_double)
+    tot = C.c_double(0.0)
+    check(lib().bvg_loglik_total_host(coef.ctypes.data_as(dp), sig.ctypes.data_as(dp), draws, k, M, T,
+                                      Y.ctypes.data_as(dp), Z.ctypes.data_as(dp), C.byref(tot)))
+    ll_t = np.empty(T)
+    check(lib().bvg_loglik_draws_host(coef.ctypes.data_as(dp), sig.ctypes.data_as(dp), draws, k, M, T, 0, 0,
+                                      Y.ctypes.data_as(dp), Z.ctypes.data_as(dp), ll_t.ctypes.data_as(dp)))
+    want = ob.summary_bvarlist_row(Y, Z, coef, sig)
+    assert abs(ll_t.sum() / draws - want["LL"]) <= TOL * abs(want["LL"])
+    assert abs(tot.value / draws - want["LL"]) <= TOL * abs(want["LL"])
+

@@ -1,0 +1,19 @@
+#!/usr/bin/env python3
+"""Time bvg_sampler_loglik on the c2-A draws (4096 chains x 5000 retained) -- run plain or under
+`ncu --metrics gpu__time_duration.sum` to split it into its kernels."""
+import pathlib, sys, time
+ROOT = pathlib.Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import helpers
+from bvartools_b200 import ChainSampler
+chains, it = int(sys.argv[1]) if len(sys.argv) > 1 else 4096, int(sys.argv[2]) if len(sys.argv) > 2 else 5000
+obj = helpers.model_c1(iterations=it, burnin=100)
+s = ChainSampler(obj, n_chains=chains, seed=1, device=0)
+s.run(0); s.sync()
+for i in range(3):
+    t0 = time.perf_counter(); ll, n = s.loglik(); dt = time.perf_counter() - t0
+    print(f"loglik: {dt * 1e3:.2f} ms for {n} draws -> {n / dt / 1e6:.1f} M draws/s, {240 * n / dt / 1e9:.1f} GB/s, LL {ll.sum() / n:.6f}")
+for i in range(3):
+    t0 = time.perf_counter(); tot, n = s.loglik_total(); dt = time.perf_counter() - t0
+    print(f"loglik_total: {dt * 1e3:.2f} ms for {n} draws -> {n / dt / 1e6:.1f} M draws/s, {240 * n / dt / 1e9:.1f} GB/s, LL {tot / n:.6f}")
+
