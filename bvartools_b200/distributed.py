@@ -10,7 +10,8 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["shard", "shard_weighted", "model_cost", "run_sharded", "allreduce_moments", "gather_draws"]
+__all__ = ["shard", "shard_weighted", "model_cost", "run_sharded", "allreduce_moments", "gather_draws",
+           "allreduce_information_criteria"]
 
 
 def shard(n_items: int, rank: int, world: int):
@@ -89,6 +90,24 @@ def allreduce_moments(draws, device=None):
     mean = acc[:rows] / cnt
     var = (acc[rows:2 * rows] - cnt * mean * mean) / max(cnt - 1.0, 1.0)
     return mean, var, int(cnt)
+
+
+def allreduce_information_criteria(ll_sum, n_draws, tot_pars, tt, device=None):
+    """Model-comparison row over ALL ranks' chains: all-reduce of this rank's log-likelihood sums --
+    a scalar (`ChainSampler.loglik_total`) or the T per-period sums (`ChainSampler.loglik`) -- and draw count; every
+    rank gets dict(LL, AIC, BIC, HQ) as in R/summary.bvarlist.R:181-184."""
+    import torch
+    from .posterior import information_criteria
+    dist, _, world = _dist()
+    v = np.atleast_1d(np.asarray(ll_sum, dtype=np.float64))
+    acc = torch.empty(v.size + 1, dtype=torch.float64, device=device or "cpu")
+    acc[:v.size] = torch.from_numpy(v)
+    acc[v.size] = float(n_draws)
+    if dist is not None and world > 1:
+        dist.all_reduce(acc)
+    acc = acc.cpu().numpy()
+    ll = float(acc[:v.size].sum() / acc[v.size])
+    return information_criteria(ll, tot_pars, tt)
 
 
 def gather_draws(local, n_chains_total, dst=0):

@@ -40,7 +40,17 @@ def _worker(rank, world, port, total, q):
         coef = res["coef"] if res else np.zeros((0, 12, 21))
         mean, var, cnt = D.allreduce_moments(coef)
         gathered = D.gather_draws(coef, total, dst=0)
-        q.put((rank, off, coef.shape[0], mean, var, cnt, gathered))
+        # model-comparison row: this rank's log-likelihood sums (oracle loop standing in for the device reduction)
+        from oracle import blocks as ob
+        Y, Z = obj["data"]["Y"], obj["data"]["Z"]
+        ll_t = np.zeros(Y.shape[0])
+        sig = res["sigma"] if res else np.zeros((0, 12, 9))
+        for c in range(coef.shape[0]):
+            for j in range(coef.shape[1]):
+                u = Y.T - coef[c, j].reshape(3, -1, order="F") @ Z.T
+                ll_t += ob.loglik_normal(u, sig[c, j].reshape(3, 3, order="F"))
+        ic = D.allreduce_information_criteria(ll_t, coef.shape[0] * coef.shape[1], Z.shape[1], Y.shape[0])
+        q.put((rank, off, coef.shape[0], mean, var, cnt, gathered, ic))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -59,13 +69,19 @@ def test_sharded_job_equals_single_process_job(world, total):
         p.join(timeout=60)
         assert p.exitcode == 0
     obj = helpers.model_c1(iterations=12, burnin=3)
-    full = _emu_runner(obj, total, 77)["coef"]
+    full_res = _emu_runner(obj, total, 77)
+    full = full_res["coef"]
+    from oracle import blocks as ob
+    want_ic = ob.summary_bvarlist_row(obj["data"]["Y"], obj["data"]["Z"], full.reshape(-1, 21),
+                                      full_res["sigma"].reshape(-1, 9))
     got.sort(key=lambda t: t[0])
     assert sum(g[2] for g in got) == total
     assert [g[1] for g in got] == [D.shard(total, r, world)[0] for r in range(world)]
     flat = full.reshape(-1, 21)
-    for rank, off, cnt_local, mean, var, cnt, gathered in got:
+    for rank, off, cnt_local, mean, var, cnt, gathered, ic in got:
         assert cnt == flat.shape[0]
+        for key in ("LL", "AIC", "BIC", "HQ"):
+            assert abs(ic[key] - want_ic[key]) <= 1e-10 * abs(want_ic[key]), key
         np.testing.assert_allclose(mean, flat.mean(axis=0), rtol=1e-12, atol=1e-14)
         np.testing.assert_allclose(var, flat.var(axis=0, ddof=1), rtol=1e-9)
         if rank == 0:
