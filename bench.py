@@ -2,7 +2,7 @@
 """bench.py -- retained Gibbs draws/sec (chains x iterations, whole box) of the B200 sampler, next to the
 reference-faithful CPU restatement timed on the same box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2a|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2a|c2b|c3|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 A step = one pass of the hot path over one batch: `chains` independent chains x (iterations + burnin) sweeps of the
@@ -183,6 +183,146 @@ def cpu_reference_run(obj, label, steps, warmup, sample_sweeps, as_line, n_gpus=
             "gpu_launches": 0}
 
 
+def run_grid(args, rank, world, local_rank):
+    """Workload c2-B: the p = 0:4 model grid (vignettes/model-comparison.Rmd:44-60), `chains` chains per model and GPU,
+    followed by the model-comparison table (summary.bvarlist) from the draws resident in HBM."""
+    import torch
+    import torch.distributed as dist
+    import helpers
+    from bvartools_b200 import ChainSampler, _abi, pinned_empty
+    from bvartools_b200 import distributed as D
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    it = args.iterations or 5000
+    bi = 1000 if args.burnin < 0 else args.burnin
+    models = helpers.model_grid_c2b(iterations=it, burnin=bi)
+    chains = args.chains or 1024
+    stream = torch.cuda.current_stream()
+    seed = 20240113
+    samplers = [ChainSampler(m, n_chains=chains, seed=seed + 1000 * i, chain_offset=rank * chains, device=local_rank)
+                for i, m in enumerate(models)]
+    rows = [s.spec.out_rows() for s in samplers]
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def table():
+        out = []
+        for s, m in zip(samplers, models):
+            tot, nd = s.loglik_total(stream.cuda_stream)
+            T_, M_ = m["data"]["Z"].shape
+            out.append(D.allreduce_information_criteria(tot, nd, M_, T_, device=dev if world > 1 else None))
+        return out
+
+    side = [torch.cuda.Stream(device=dev) for _ in samplers]   # one stream per model: 1024-chain launches overlap
+
+    def step():
+        for s, st in zip(samplers, side):
+            st.wait_stream(stream)
+            s.reset()
+            s.run(st.cuda_stream)
+        for st in side:
+            stream.wait_stream(st)
+        return table()
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    fence()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    e0.record(stream)
+    for _ in range(args.steps):
+        tab = step()
+    e1.record(stream)
+    fence()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    if rank == 0:
+        clocks.stop_flag.set()
+        clocks.join(timeout=3)
+    sweep_ms = sum(s.last_kernel_ms for s in samplers)
+    launches = sum(int(s.launch_count) for s in samplers) + 2 * len(samplers)       # + total-loglik + reduce kernels
+    kernels = [s.kernel_name for s in samplers]
+    total_draws = world * chains * it * len(models)
+    out_bytes = sum(8.0 * chains * it * sum(r.values()) for r in rows)
+    # ---- end to end: host inputs -> sweeps -> all draws to pinned host memory -> table
+    e2e = None
+    if not args.no_e2e:
+        hosts = [_abi.OutBuffers(s.spec, alloc=pinned_empty) for s in samplers]
+        d2h = sum(sum(a.nbytes for a in h.arrays.values()) + h.status.nbytes for h in hosts)
+        for s in samplers:
+            s.close()
+        times, h2d = [], 0
+        for i in range(1 + args.steps):
+            fence()
+            t0 = time.perf_counter()
+            tab_e = []
+            for j, m in enumerate(models):
+                s = ChainSampler(m, n_chains=chains, seed=seed + 1000 * j, chain_offset=rank * chains, device=local_rank)
+                s.run_to_host(hosts[j], stream.cuda_stream)
+                tot, nd = s.loglik_total(stream.cuda_stream)
+                tab_e.append(tot / nd)
+                h2d += sum(v.nbytes for v in s.spec.keep.values()) if i == 0 else 0
+                s.close()
+            fence()
+            if i >= 1:
+                times.append(time.perf_counter() - t0)
+        te = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_draws / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
+               "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": float(te.item()) * 1e3,
+               "api": "per model: ChainSampler(model).run_to_host(pinned out) + loglik_total", "checksum": float(tab_e[2])}
+    else:
+        for s in samplers:
+            s.close()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs") or 6530.6
+    gbps = out_bytes / (sweep_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak,
+                "traffic": None, "kernel": ",".join(sorted(set(kernels))),
+                "algorithmic_bytes_per_step": out_bytes, "sweep_kernel_ms_per_step": sweep_ms,
+                "sweep_share_of_step": sweep_ms / ms_per_step,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "B200_PROFILING.md fallback"}
+    cpu = None
+    if not args.no_cpu:
+        cpu = cpu_reference_run(models[2], "c2-B, p = 2 member of the grid", 1, 0, args.cpu_sweeps or 1500, False)
+    par = "1 GPU" if world == 1 else f"every model's chains sharded over {world} GPUs by global chain id; NCCL all-reduce of one log-likelihood sum per model"
+    line = {"metric": METRIC, "value": total_draws / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "e1 data set (shipped fixture)",
+            "config": {"workload": "c2-B: e1 VAR(p)+const grid p = 0:4 on the common sample (T = 71), v_i = 0, df = k, "
+                                   "scale = 1e-4, %d iter / %d burn-in, + summary.bvarlist table" % (it, bi),
+                       "chains_per_model_per_gpu": chains, "chains_total": chains * world * len(models),
+                       "parallelism": par,
+                       "l2": f"retained draws {out_bytes / 1e9:.2f} GB per step per GPU >> 126 MB L2 (no flush needed)"},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches * args.steps, "roofline": roofline,
+            "cpu_baseline": cpu,
+            "model_comparison": [{"p": i, **{k: float(v) for k, v in r.items()}} for i, r in enumerate(tab)]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,7 +343,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    obj, label = build_workload(args.workload, args.iterations or None, None if args.burnin < 0 else args.burnin)
+    if args.workload == "c2b" and args.impl != "reference":
+        return run_grid(args, rank, world, local_rank)
+    obj, label = build_workload("c2a" if args.workload == "c2b" else args.workload, args.iterations or None,
+                                None if args.burnin < 0 else args.burnin)
     cpu_sweeps = args.cpu_sweeps or {"c2a": 1500, "c3": 8, "c4": 2, "c5": 1}.get(args.workload, 50)
 
     if args.impl == "reference":

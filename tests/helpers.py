@@ -47,6 +47,14 @@ def model_c1(iterations=50, burnin=10, coef=None, sigma=None, **kw):
                       ssvs=kw.get("ssvs"), bvs=kw.get("bvs"))
 
 
+def model_grid_c2b(iterations=5000, burnin=1000, p=(0, 1, 2, 3, 4)):
+    """Config c2-B: the model-comparison grid of vignettes/model-comparison.Rmd:44-60 -- e1, p = 0:4 + const on the
+    common sample (T = 71), priors v_i = 0, v_i_det = 0, df = "k", scale = 1e-4.  Returns the list of models."""
+    x, names = e1_readme_sample()
+    ms = gen_var(x, p=list(p), deterministic="const", iterations=iterations, burnin=burnin, names=names)
+    return [add_priors(m, coef=dict(v_i=0, v_i_det=0), sigma=dict(df="k", scale=1e-4)) for m in ms]
+
+
 def synth_var(K, p, nobs, seed, intercept=0.1):
     """Stationary Gaussian VAR(p) data in the style of SURVEY.md 8d (c3)."""
     rng = np.random.default_rng(seed)
