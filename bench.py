@@ -219,15 +219,10 @@ def run_grid(args, rank, world, local_rank):
             out.append(D.allreduce_information_criteria(tot, nd, M_, T_, device=dev if world > 1 else None))
         return out
 
-    side = [torch.cuda.Stream(device=dev) for _ in samplers]   # one stream per model: 1024-chain launches overlap
-
     def step():
-        for s, st in zip(samplers, side):
-            st.wait_stream(stream)
-            s.reset()
-            s.run(st.cuda_stream)
-        for st in side:
-            stream.wait_stream(st)
+        for s in samplers:           # back to back on one stream: each launch already fills the SMs evenly (running the
+            s.reset()                # models on separate streams measured no faster: 35.8 vs 36.3 ms per step)
+            s.run(stream.cuda_stream)
         return table()
 
     for _ in range(max(args.warmup, 1)):
