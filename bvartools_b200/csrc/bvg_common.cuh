@@ -98,6 +98,42 @@ BVG_HD void bvg_sincospi(double x, double* s, double* c) {
 #endif
 }
 
+// cos(2 pi u), sin(2 pi u) for u in (0, 1): the Box-Muller angle.  The general-purpose cospi / sinpi pair was 45 % of
+// the executed instructions of the flat-prior kernel (profiles/r01_c2a_final_*): each carries its own argument
+// reduction and special-case handling.  Here the range is known: t = 4 u, q = rint(t) in {0..4}, phi = (pi / 2)(t - q)
+// in [-pi/4, pi/4]; sin(phi) and cos(phi) by their Taylor polynomials in phi^2 (truncation < 1e-16 at pi/4), then a
+// rotation by q quarter turns.  Same code on host (tests/emu) and device.
+BVG_HD void bvg_sincos2pi(double u, double* sn, double* cs) {
+  const double t = 4.0 * u;
+  const double qd = rint(t);
+  const int q = (int)qd;
+  const double x = (t - qd) * 1.5707963267948966;
+  const double z = x * x;
+  double ps = 2.8114572543455206e-15;
+  ps = fma(ps, z, -7.647163731819816e-13);
+  ps = fma(ps, z, 1.6059043836821613e-10);
+  ps = fma(ps, z, -2.505210838544172e-08);
+  ps = fma(ps, z, 2.7557319223985893e-06);
+  ps = fma(ps, z, -0.0001984126984126984);
+  ps = fma(ps, z, 0.008333333333333333);
+  ps = fma(ps, z, -0.16666666666666666);
+  ps = fma(ps, z, 1.0);
+  double pc = -1.5619206968586225e-16;
+  pc = fma(pc, z, 4.779477332387385e-14);
+  pc = fma(pc, z, -1.1470745597729725e-11);
+  pc = fma(pc, z, 2.08767569878681e-09);
+  pc = fma(pc, z, -2.755731922398589e-07);
+  pc = fma(pc, z, 2.48015873015873e-05);
+  pc = fma(pc, z, -0.001388888888888889);
+  pc = fma(pc, z, 0.041666666666666664);
+  pc = fma(pc, z, -0.5);
+  pc = fma(pc, z, 1.0);
+  const double s = x * ps, c = pc;
+  const double a = (q & 1) ? s : c, b = (q & 1) ? c : s;           // |cos|, |sin| before the quadrant signs
+  *cs = (((q + 1) >> 1) & 1) ? -a : a;                              // q = 0: c  1: -s  2: -c  3: s  4: c
+  *sn = ((q >> 1) & 1) ? -b : b;                                    // q = 0: s  1: c   2: -s  3: -c 4: s
+}
+
 // ---- random source of one chain ----------------------------------------------------------------------------
 // Injected variates (tier-1 parity tests): device arrays [chain][sweep][count] or nullptr per block.  Lives in
 // kernel parameter (constant) space; the chain only keeps a pointer to it so that the Philox path carries no
@@ -131,8 +167,10 @@ BVG_HD_NOINLINE Normal2 philox_normal_pair(uint64_t seed, uint64_t chain, int bl
   const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
   const double r = sqrt(-2.0 * log(u1));
   Normal2 o;
-  o.a = r * bvg_cospi(2.0 * u2);
-  o.b = r * bvg_sinpi(2.0 * u2);
+  double sn, cs;
+  bvg_sincos2pi(u2, &sn, &cs);
+  o.a = r * cs;
+  o.b = r * sn;
   return o;
 }
 // Two independent pairs at once (two chains / two sites): the two Philox + log + sincospi dependency chains are
@@ -147,17 +185,22 @@ BVG_HD_NOINLINE Normal4 philox_normal_pair_x2(uint64_t seed, uint64_t chain_a, i
   const double la = log(ua1), lb = log(ub1);
   const double ra = sqrt(-2.0 * la), rb = sqrt(-2.0 * lb);
   Normal4 o;
-  o.p.a = ra * bvg_cospi(2.0 * ua2);
-  o.q.a = rb * bvg_cospi(2.0 * ub2);
-  o.p.b = ra * bvg_sinpi(2.0 * ua2);
-  o.q.b = rb * bvg_sinpi(2.0 * ub2);
+  double sa, ca, sb, cb;
+  bvg_sincos2pi(ua2, &sa, &ca);
+  bvg_sincos2pi(ub2, &sb, &cb);
+  o.p.a = ra * ca;
+  o.q.a = rb * cb;
+  o.p.b = ra * sa;
+  o.q.b = rb * sb;
   return o;
 }
 BVG_HD_NOINLINE double philox_normal(uint64_t seed, uint64_t chain, int block, int sweep, int idx, int attempt) {
   const Philox4 p = philox_site(seed, chain, block, sweep, idx >> 1, attempt);
   const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
   const double r = sqrt(-2.0 * log(u1));
-  return (idx & 1) ? r * bvg_sinpi(2.0 * u2) : r * bvg_cospi(2.0 * u2);
+  double sn, cs;
+  bvg_sincos2pi(u2, &sn, &cs);
+  return (idx & 1) ? r * sn : r * cs;
 }
 // Gamma(shape, 1), Marsaglia-Tsang 2000 (shape < 1 boosted); attempts are separate sites.  `x0` is the N(0,1) of
 // attempt 0, i.e. philox_normal(.., idx, 0): callers may draw it earlier together with other normals so that all
@@ -176,7 +219,9 @@ BVG_HD_NOINLINE double philox_gamma_from_x0(uint64_t seed, uint64_t chain, int b
     if (attempt > 0) {
       const Philox4 p = philox_site(seed, chain, block, sweep, idx, attempt);
       const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
-      x = sqrt(-2.0 * log(u1)) * bvg_cospi(2.0 * u2);
+      double sn, cs;
+      bvg_sincos2pi(u2, &sn, &cs);
+      x = sqrt(-2.0 * log(u1)) * cs;
     }
     double v = 1.0 + c * x;
     if (v <= 0.0) continue;
