@@ -190,7 +190,6 @@ def run_grid(args, rank, world, local_rank):
     import torch.distributed as dist
     import helpers
     from bvartools_b200 import ChainSampler, _abi, pinned_empty
-    from bvartools_b200 import distributed as D
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -212,11 +211,20 @@ def run_grid(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def table():
-        out = []
-        for s, m in zip(samplers, models):
+        # one log-likelihood sum and draw count per model; a single all-reduce for the whole grid
+        from bvartools_b200.posterior import information_criteria
+        acc = torch.zeros(2 * len(samplers), dtype=torch.float64)
+        for i, s in enumerate(samplers):
             tot, nd = s.loglik_total(stream.cuda_stream)
+            acc[2 * i], acc[2 * i + 1] = tot, float(nd)
+        if world > 1:
+            acc = acc.to(dev)
+            dist.all_reduce(acc)
+            acc = acc.cpu()
+        out = []
+        for i, m in enumerate(models):
             T_, M_ = m["data"]["Z"].shape
-            out.append(D.allreduce_information_criteria(tot, nd, M_, T_, device=dev if world > 1 else None))
+            out.append(information_criteria(float(acc[2 * i] / acc[2 * i + 1]), M_, T_))
         return out
 
     def step():
