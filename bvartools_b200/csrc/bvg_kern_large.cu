@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "bvg_kernels.cuh"
+#include "bvg_tiled.cuh"
 
 namespace bvg {
 
@@ -172,51 +173,75 @@ __global__ void __launch_bounds__(128) large_gemm_kernel(const __grid_constant__
 }
 
 // ---- L[J,J] = chol(A[J,J]) and its inverse --------------------------------------------------------------------------
-// grid: chains; block 256.  Right-looking in shared memory; the strict upper triangle of the tile is zeroed.
+// grid: chains; block 256.  The 64 x 64 diagonal block is factorised as 8 x 8 tiles in shared memory by the CTA-wide
+// DMMA Cholesky of bvg_tiled.cuh (diagonal tiles factorised + inverted in registers, panels and updates as tile
+// products), then inverted tile row by tile row:  M_II = T_I,  M_IJ = -T_I sum_{J <= q < I} L_Iq M_qJ  (one tile per warp).
+// Only the inverse is written out (linv): the trailing kernels and the solve never read the diagonal block itself.
 __global__ void __launch_bounds__(256) large_potrf_kernel(const __grid_constant__ LargeDims d, int J, double* __restrict__ mats,
                                                           double* __restrict__ linv, int* __restrict__ status) {
   extern __shared__ double potrf_sm[];
-  double (*L)[TB + 1] = (double (*)[TB + 1])potrf_sm;
-  double (*Mi)[TB + 1] = (double (*)[TB + 1])(potrf_sm + TB * (TB + 1));
-  __shared__ int bad;
+  constexpr int NTT = TB / 8;                                  // tile rows of the block
+  double* Lt = potrf_sm;                                       // tiled_len(TB) doubles, tile (I, Jt) at (I (I + 1) / 2 + Jt) * 64
+  double* rhs = Lt + tiled_len(TB);                            // TB zeros: tiled_chol carries a right-hand side along
   const long long chain = blockIdx.x;
-  const int npad = d.npad, tid = threadIdx.x;
+  const int npad = d.npad, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int li = lane & 7, lj = lane >> 3, fr = lane >> 2, fk = lane & 3;
+  const int fo0 = fk * 8 + fr, fo1 = fo0 + 32, co = (2 * fk) * 8 + fr, to0 = fr * 8 + fk, to1 = to0 + 4;
   double* A = mats + (size_t)chain * d.mat_stride + (size_t)J * TB * npad + (size_t)J * TB;
-  if (tid == 0) bad = 0;
-  for (int e = tid; e < TB * TB; e += blockDim.x) { const int r = e % TB, c = e / TB; L[r][c] = (c <= r) ? A[(size_t)c * npad + r] : 0.0; }
+  // load the lower tiles: a warp fetches half a tile per pass (8 consecutive rows of 4 columns)
+  for (int t = warp; t < (NTT * (NTT + 1)) / 2; t += nwarp) {
+    int I = 0;
+    while (((I + 1) * (I + 2)) / 2 <= t) ++I;
+    const int Jt = t - (I * (I + 1)) / 2;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = 8 * I + li, c = 8 * Jt + lj + 4 * h;
+      Lt[t * 64 + lane + 32 * h] = (c <= r) ? A[(size_t)c * npad + r] : 0.0;
+    }
+  }
+  for (int e = tid; e < TB; e += blockDim.x) rhs[e] = 0.0;
   __syncthreads();
-  for (int j = 0; j < TB; ++j) {
-    const double dj = L[j][j];
-    if (tid == 0 && !(dj > 0.0)) bad = 1;
-    const double rs = 1.0 / sqrt(dj);
-    __syncthreads();
-    for (int r = j + tid; r < TB; r += blockDim.x) L[r][j] = (r == j) ? dj * rs : L[r][j] * rs;
-    __syncthreads();
-    // trailing update of the lower triangle: L[r][c] -= L[r][j] L[c][j], j < c <= r
-    for (int e = tid; e < (TB - j - 1) * (TB - j - 1); e += blockDim.x) {
-      const int r = j + 1 + e % (TB - j - 1), c = j + 1 + e / (TB - j - 1);
-      if (c <= r) L[r][c] = fma(-L[r][j], L[c][j], L[r][c]);
+  int fail = 0;
+  tiled_chol(Lt, rhs, TB, fail);
+  if (fail && tid == 0) status[chain] = 1;                      // warp 0 sees every pivot
+#define BVG_LT(I, Jt) (Lt + ((((I) * ((I) + 1)) >> 1) + (Jt)) * 64)
+  for (int I = 1; I < NTT; ++I) {
+    double x0 = 0.0, x1 = 0.0;
+    const int Jt = warp;                                        // one tile of row I per warp (I <= 7 < nwarp = 8)
+    if (Jt < I) {
+      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+      for (int q = Jt; q < I; ++q) {
+        const double* LA = BVG_LT(I, q);
+        const double* MB = BVG_LT(q, Jt);
+        tiled_dmma(c0, c1, LA[fo0], MB[to0]);
+        tiled_dmma(e0, e1, LA[fo1], MB[to1]);
+      }
+      x0 = c0 + e0; x1 = c1 + e1;
+    }
+    __syncthreads();                                            // every warp has read row I of L
+    if (Jt < I) {
+      double* X = BVG_LT(I, Jt);
+      X[co] = x0; X[co + 8] = x1;
+      __syncwarp();
+      const double* TI = BVG_LT(I, I);
+      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+      tiled_dmma(c0, c1, -TI[fo0], X[to0]);
+      tiled_dmma(e0, e1, -TI[fo1], X[to1]);
+      X[co] = c0 + e0; X[co + 8] = c1 + e1;
     }
     __syncthreads();
   }
-  // inverse of the lower-triangular factor, one column per thread
-  for (int c = tid; c < TB; c += blockDim.x) {
-    for (int r = 0; r < c; ++r) Mi[r][c] = 0.0;
-    Mi[c][c] = 1.0 / L[c][c];
-    for (int r = c + 1; r < TB; ++r) {
-      double s = 0.0;
-      for (int mm = c; mm < r; ++mm) s = fma(L[r][mm], Mi[mm][c], s);
-      Mi[r][c] = -s / L[r][r];
-    }
-  }
-  __syncthreads();
+  // Minv, col-major TB x TB with an exactly zero upper triangle
   double* Lo = linv + (size_t)chain * d.linv_stride + (size_t)J * TB * TB;
-  for (int e = tid; e < TB * TB; e += blockDim.x) {
-    const int r = e % TB, c = e / TB;
-    A[(size_t)c * npad + r] = L[r][c];
-    Lo[e] = Mi[r][c];                                       // col-major TB x TB
+  for (int t = warp; t < NTT * NTT; t += nwarp) {
+    const int I = t % NTT, Jt = t / NTT;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = 8 * I + li, c = 8 * Jt + lj + 4 * h;
+      Lo[(size_t)c * TB + r] = (Jt <= I) ? BVG_LT(I, Jt)[lane + 32 * h] : 0.0;
+    }
   }
-  if (tid == 0 && bad) status[chain] = 1;
+#undef BVG_LT
 }
 
 // ---- L[I,J] = A[I,J] L[J,J]^-T = A[I,J] Minv'   (I > J) -------------------------------------------------------------
@@ -416,7 +441,7 @@ cudaError_t launch_bvar_large(const BvarModel& m, const RngParams& rp, double* s
   double* avec = rhs + (size_t)n_chains * d.npad;
   const size_t gemm_smem = (size_t)2 * NSTAGE * KC * LDS_ * 8 + NSTAGE * 8;
   const size_t trsm_smem = (size_t)2 * TB * LDS_ * 8 + 8;
-  const size_t potrf_smem = (size_t)2 * TB * (TB + 1) * 8;
+  const size_t potrf_smem = ((size_t)tiled_len(TB) + TB + 8) * 8;
   const size_t solve_smem = ((size_t)d.npad + 9 * TB + TB * (TB + 1)) * 8;
   const size_t post_smem = ((size_t)BVG_BLOCK_SCRATCH + d.n + (size_t)d.k * d.T + 6 * d.k * d.k + 2 * d.k) * 8;
   cudaError_t e;
