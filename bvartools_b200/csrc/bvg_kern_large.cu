@@ -122,17 +122,21 @@ __global__ void __launch_bounds__(128) large_gemm_kernel(const __grid_constant__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto issue = [&](int chunk) {                             // one elected thread: 2 * KC bulk copies of 512 B
+  // warp 0 issues the 2 * KC bulk copies (512 B each) of a chunk, one per lane and pass: a single elected thread
+  // looping over them kept its warp -- and, through the next CTA barrier, the whole CTA -- waiting
+  auto issue = [&](int chunk) {
     const int s = chunk % NSTAGE;
     const uint32_t bytes = (uint32_t)(TB * sizeof(double));
-    mbar_expect_tx(&bars[s], bytes * KC * (diag ? 1 : 2));
-    for (int c = 0; c < KC; ++c) {
+    if (lane == 0) mbar_expect_tx(&bars[s], bytes * KC * (diag ? 1 : 2));
+    __syncwarp();
+    for (int cc = lane; cc < 2 * KC; cc += 32) {
+      const int c = cc % KC, isB = cc / KC;
       const size_t col = (size_t)(chunk * KC + c) * npad;
-      tma_bulk_g2s(sA + (s * KC + c) * LDS_, A + col + (size_t)I * TB, bytes, &bars[s]);
-      if (!diag) tma_bulk_g2s(sB + (s * KC + c) * LDS_, A + col + (size_t)J * TB, bytes, &bars[s]);
+      if (!isB) tma_bulk_g2s(sA + (s * KC + c) * LDS_, A + col + (size_t)I * TB, bytes, &bars[s]);
+      else if (!diag) tma_bulk_g2s(sB + (s * KC + c) * LDS_, A + col + (size_t)J * TB, bytes, &bars[s]);
     }
   };
-  if (tid == 0) for (int c = 0; c < NSTAGE - 1 && c < nchunk; ++c) issue(c);
+  if (warp == 0) for (int c = 0; c < NSTAGE - 1 && c < nchunk; ++c) issue(c);
   double acc[4][4][2];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -157,7 +161,7 @@ __global__ void __launch_bounds__(128) large_gemm_kernel(const __grid_constant__
         for (int b = 0; b < 4; ++b) dmma(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
     }
     __syncthreads();                                        // everyone is done with stage s (and the older ones)
-    if (tid == 0 && chunk + NSTAGE - 1 < nchunk) issue(chunk + NSTAGE - 1);
+    if (warp == 0 && chunk + NSTAGE - 1 < nchunk) issue(chunk + NSTAGE - 1);
   }
   // epilogue: A[I,J] -= acc
 #pragma unroll
@@ -257,17 +261,20 @@ __global__ void __launch_bounds__(128) large_trsm_kernel(const __grid_constant__
   double* A = mats + (size_t)chain * d.mat_stride + (size_t)J * TB * npad + (size_t)I * TB;
   const double* Mg = linv + (size_t)chain * d.linv_stride + (size_t)J * TB * TB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wr = warp >> 1, wc = warp & 1;
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  {
     const uint32_t bytes = (uint32_t)(TB * sizeof(double));
-    mbar_expect_tx(bar, bytes * 2 * TB);
-    for (int c = 0; c < TB; ++c) {
-      tma_bulk_g2s(sA + c * LDS_, A + (size_t)c * npad, bytes, bar);
-      tma_bulk_g2s(sM + c * LDS_, Mg + (size_t)c * TB, bytes, bar);
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(bar, bytes * 2 * TB);
+    }
+    __syncthreads();
+    for (int cc = tid; cc < 2 * TB; cc += blockDim.x) {      // 128 bulk copies, one per thread
+      const int c = cc % TB;
+      if (cc < TB) tma_bulk_g2s(sA + c * LDS_, A + (size_t)c * npad, bytes, bar);
+      else tma_bulk_g2s(sM + c * LDS_, Mg + (size_t)c * TB, bytes, bar);
     }
   }
-  __syncthreads();
   mbar_wait(bar, 0);
   double acc[4][4][2];
 #pragma unroll
