@@ -21,10 +21,16 @@
 
 namespace bvg {
 
+#ifndef BVG_LARGE_KC
+#define BVG_LARGE_KC 8       // swept on B200 (c5): (16,3) 479 ms, (32,2) 542, (32,3) 692, (8,3) 473, (8,4) 472, (8,5) 469, (4,6) 525
+#endif
+#ifndef BVG_LARGE_NSTAGE
+#define BVG_LARGE_NSTAGE 4
+#endif
 static constexpr int TB = 64;        // tile / block-column width
-static constexpr int KC = 16;        // k-chunk of the GEMM pipeline
+static constexpr int KC = BVG_LARGE_KC;        // k-chunk of the GEMM pipeline
 static constexpr int LDS_ = 68;      // shared-memory column stride (doubles): conflict-free DMMA fragment loads
-static constexpr int NSTAGE = 3;
+static constexpr int NSTAGE = BVG_LARGE_NSTAGE;
 
 // ---- PTX helpers: mbarrier + TMA 1-D bulk copy + FP64 MMA ---------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
