@@ -66,15 +66,16 @@ struct LargeDims {
 };
 
 // ---- P and b ---------------------------------------------------------------------------------------------------
-// grid: (tile pairs I >= J, chains); block 256.  sig = state (k x k col-major, Sigma^-1).
+// Only block column 0 of P is materialised here (+ the right-hand side): every other tile is generated inside the
+// epilogue of the trailing-update kernel that first touches it (large_gemm_kernel), which saves one write and one
+// read of the whole matrix per sweep.
+// grid: (nt row tiles, chains); block 256.  sig = state (k x k col-major, Sigma^-1).
 __global__ void __launch_bounds__(256) large_build_kernel(const __grid_constant__ BvarModel m, const __grid_constant__ LargeDims d,
                                                           const double* __restrict__ state, int state_len,
                                                           double* __restrict__ mats, double* __restrict__ rhs) {
   __shared__ double sig[1024];                       // k <= 32 on this path (checked by the host)
   const long long chain = blockIdx.y;
-  int tp = blockIdx.x, I = 0;
-  while ((I + 1) * (I + 2) / 2 <= tp) ++I;
-  const int J = tp - I * (I + 1) / 2;
+  const int I = blockIdx.x, J = 0;
   const int k = d.k, kk = k * k, n = d.n, npad = d.npad;
   const double* st = state + (size_t)chain * state_len;
   for (int e = threadIdx.x; e < kk; e += blockDim.x) sig[e] = st[e];
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(256) large_build_kernel(const __grid_constant_
     }
     A[(size_t)c * npad + r] = v;
   }
-  if (J == 0) {                                      // rhs rows of this row tile
+  {                                                  // rhs rows of this row tile
     double* b = rhs + (size_t)chain * npad;
     for (int rr = threadIdx.x; rr < TB; rr += blockDim.x) {
       const int r = I * TB + rr;
@@ -112,8 +113,11 @@ __global__ void __launch_bounds__(256) large_build_kernel(const __grid_constant_
 
 // ---- A[I,J] -= sum_{K<J} L[I,K] L[J,K]'   (I >= J) ---------------------------------------------------------------
 // grid: (nt - J row tiles, chains); block 128 = 4 warps, warp (wr, wc) owns the 32 x 32 quadrant of the 64 x 64 tile.
-__global__ void __launch_bounds__(128) large_gemm_kernel(const __grid_constant__ LargeDims d, int J, double* __restrict__ mats) {
+__global__ void __launch_bounds__(128, 5) large_gemm_kernel(const __grid_constant__ LargeDims d, int J, double* __restrict__ mats,
+                                                         const double* __restrict__ XX, const double* __restrict__ state,
+                                                         int state_len) {
   extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ double sig[1024];                             // Sigma^-1 of the chain (k <= 32): P is generated in the epilogue
   double* sA = (double*)smraw;                             // [NSTAGE][KC][LDS_]
   double* sB = sA + NSTAGE * KC * LDS_;
   uint64_t* bars = (uint64_t*)(sB + NSTAGE * KC * LDS_);
@@ -123,6 +127,8 @@ __global__ void __launch_bounds__(128) large_gemm_kernel(const __grid_constant__
   const int kdim = J * TB, nchunk = kdim / KC;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wr = warp >> 1, wc = warp & 1;
   const bool diag = (I == J);
+  const double* st = state + (size_t)chain * state_len;
+  for (int e = tid; e < d.k * d.k; e += blockDim.x) sig[e] = st[e];
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -169,17 +175,38 @@ __global__ void __launch_bounds__(128) large_gemm_kernel(const __grid_constant__
     __syncthreads();                                        // everyone is done with stage s (and the older ones)
     if (warp == 0 && chunk + NSTAGE - 1 < nchunk) issue(chunk + NSTAGE - 1);
   }
-  // epilogue: A[I,J] -= acc
+  // epilogue: A[I,J] = P[I,J] - acc with P = XX' (x) Sigma^-1 + diag(V^-1) generated on the fly (identity padding rows);
+  // the strict upper triangle of a diagonal tile is never read
+  {
+    const int k = d.k, kk = k * k, n = d.n, M = d.M;
+    int jr[4], ir[4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int a = 0; a < 4; ++a) {
       const int r = I * TB + wr * 32 + a * 8 + fr;
-      const int c = J * TB + wc * 32 + b * 8 + 2 * fk;
-      double* p0 = A + (size_t)c * npad + r;
-      p0[0] -= acc[a][b][0];
-      p0[npad] -= acc[a][b][1];
+      jr[a] = r / k; ir[a] = r - jr[a] * k;
     }
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = J * TB + wc * 32 + b * 8 + 2 * fk + h;
+        const int jc = c / k, ic = c - jc * k;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int r = I * TB + wr * 32 + a * 8 + fr;
+          double v = 0.0;
+          if (r < n && c < n) {
+            if (c <= r) {
+              v = XX[jr[a] + (size_t)M * jc] * sig[ir[a] + k * ic];
+              if (r == c) v += st[kk + r];
+            }
+          } else if (r == c) {
+            v = 1.0;
+          }
+          A[(size_t)c * npad + r] = v - acc[a][b][h];
+        }
+      }
+  }
 }
 
 // ---- L[J,J] = chol(A[J,J]) and its inverse --------------------------------------------------------------------------
@@ -465,11 +492,11 @@ cudaError_t launch_bvar_large(const BvarModel& m, const RngParams& rp, double* s
   if ((e = set_smem(large_post_kernel, post_smem)) != cudaSuccess) return e;
   const unsigned nc = (unsigned)n_chains;
   for (int sweep = s0; sweep < s1; ++sweep) {
-    large_build_kernel<<<dim3(d.nt * (d.nt + 1) / 2, nc), 256, 0, stream>>>(m, d, state, state_len, mats, rhs);
+    large_build_kernel<<<dim3(d.nt, nc), 256, 0, stream>>>(m, d, state, state_len, mats, rhs);
     *launches += 1;
     for (int J = 0; J < d.nt; ++J) {
       if (J > 0) {
-        large_gemm_kernel<<<dim3(d.nt - J, nc), 128, gemm_smem, stream>>>(d, J, mats);
+        large_gemm_kernel<<<dim3(d.nt - J, nc), 128, gemm_smem, stream>>>(d, J, mats, m.XX, state, state_len);
         *launches += 1;
       }
       large_potrf_kernel<<<nc, 256, potrf_smem, stream>>>(d, J, mats, linv, out.status);
