@@ -469,8 +469,9 @@ int bvg_sampler_loglik(bvg_sampler* s, double* host_ll_t, void* cuda_stream) {
   double* d_ll = nullptr;
   CK(cudaMalloc((void**)&d_ll, (size_t)T * sizeof(double)));
   const int tv_sigma = (s->P.sigma_type == BVG_SIGMA_SV) ? 1 : 0;
+  const BvarModel& bm = s->P.tvp ? s->tm.b : s->bm;          // the TVP sampler keeps its data in the TvpModel
   int rc = bvg_loglik_draws(s->d_coef, s->d_sigma, (int64_t)s->n_chains * s->P.iterations, s->P.k, s->P.M, T, s->P.tvp,
-                            tv_sigma, s->bm.Y, s->bm.X, d_ll, cuda_stream);
+                            tv_sigma, bm.Y, bm.X, d_ll, cuda_stream);
   if (rc == 0) {
     cudaError_t e = cudaMemcpyAsync(host_ll_t, d_ll, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -176,3 +176,33 @@ def test_total_kernel_matches_per_period_kernel(gpu, k, p):
     assert abs(ll_t.sum() / draws - want["LL"]) <= TOL * abs(want["LL"])
     assert abs(tot.value / draws - want["LL"]) <= TOL * abs(want["LL"])
 
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tvp", [False, True])
+def test_resident_draws_time_varying_models(gpu, tvp):
+    """ChainSampler.loglik / loglik_total on SV and TVP-SV draws resident in HBM against the oracle loop."""
+    from bvartools_b200 import ChainSampler, _abi
+    obj = helpers.model_sv(tvp=tvp, nobs=30, iterations=6, burnin=2)
+    s = ChainSampler(obj, n_chains=3, seed=9)
+    s.run(0)
+    ll_t, n = s.loglik()
+    tot, n2 = s.loglik_total()
+    host = _abi.OutBuffers(s.spec)
+    s.fetch(host)
+    s.close()
+    Y, Z = obj["data"]["Y"], obj["data"]["Z"]
+    T, k = Y.shape
+    want = np.zeros(T)
+    coef, sig = host.arrays["coef"], host.arrays["sigma"]
+    for c in range(coef.shape[0]):
+        for j in range(coef.shape[1]):
+            u = np.empty((k, T))
+            for t in range(T):
+                a = coef[c, j].reshape(T, -1)[t] if tvp else coef[c, j]
+                u[:, t] = Y[t] - a.reshape(k, -1, order="F") @ Z[t]
+            stack = np.vstack([sig[c, j].reshape(T, k * k)[t].reshape(k, k, order="F") for t in range(T)])
+            want += ob.loglik_normal(u, stack)
+    assert n == n2 == 3 * 6
+    assert helpers.relerr(ll_t, want) < TOL
+    assert abs(tot - want.sum()) <= TOL * abs(want.sum())
+
