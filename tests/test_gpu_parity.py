@@ -121,6 +121,27 @@ def test_chunking_and_layout_invariance_philox(gpu):
         assert np.array_equal(ref.arrays[key], exact.arrays[key]), key
 
 
+@pytest.mark.parametrize("case", ["c3_cta_tiled", "tvp_warp_tiled", "large"])
+def test_run_to_run_determinism_of_the_tile_kernels(gpu, case):
+    """Same seed, same launch shape => bit-identical draws on repeated runs (compute-sanitizer is not available on the
+    GPU pool: a shared-memory race in the DMMA tile kernels would show up here as run-to-run noise)."""
+    kw = {}
+    if case == "c3_cta_tiled":
+        obj, chains = helpers.model_c3(iterations=4, burnin=2), 5
+    elif case == "tvp_warp_tiled":
+        obj, chains = helpers.model_sv(tvp=True, nobs=40, iterations=3, burnin=1), 9
+    else:
+        y = helpers.synth_var(6, 4, 150, 77)
+        m = helpers.gen_var(y, p=4, deterministic="const", iterations=3, burnin=1)
+        obj = helpers.add_priors(m, coef=dict(minnesota=dict(kappa0=2, kappa1=0.5, kappa3=5)), sigma=dict(df="k", scale=1))
+        chains, kw = 3, dict(threads_per_chain=-1)
+    first = _run(gpu, obj, chains, seed=123, **kw)
+    for _ in range(3):
+        again = _run(gpu, obj, chains, seed=123, **kw)
+        for key in first.arrays:
+            assert np.array_equal(first.arrays[key], again.arrays[key]), (case, key)
+
+
 def test_sharding_invariance(gpu):
     """Chains [offset, offset+m) of a shard equal the same global chains of the full job, bit for bit."""
     obj = helpers.model_c1(iterations=40, burnin=10)
