@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <cmath>
 #include <string>
 #include <vector>
 #include "bvg_kernels.cuh"
@@ -675,6 +676,61 @@ int bvg_loglik_normal(const double* u, const double* sigma, int32_t k, int32_t T
   }
   cudaFree(d_u); cudaFree(d_sg); cudaFree(d_out);
   return rc;
+}
+
+int bvg_summary_draws(const double* dev_draws, int64_t n_draws, int64_t rows, const double* probs, int32_t n_probs,
+                      double* mean, double* sd, double* quantiles, void* cuda_stream) {
+  if (!dev_draws || n_draws < 1 || rows < 1 || n_probs < 0 || n_probs > 16 || (n_probs > 0 && (!probs || !quantiles)))
+    return fail(-1, "invalid arguments to bvg_summary_draws");
+  for (int q = 0; q < n_probs; ++q)
+    if (!(probs[q] >= 0.0 && probs[q] <= 1.0)) return fail(-4, "probabilities must lie in [0, 1]");
+  if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  double *d_sums = nullptr, *d_sq = nullptr, *d_ss = nullptr, *d_p = nullptr, *d_q = nullptr;
+  cudaError_t e = cudaSuccess;
+  auto done = [&](int r) { cudaFree(d_sums); cudaFree(d_sq); cudaFree(d_ss); cudaFree(d_p); cudaFree(d_q); return r; };
+#define BVG_TRY(call) do { if ((e = (call)) != cudaSuccess) return done(cuda_fail(e, #call)); } while (0)
+  BVG_TRY(cudaMalloc((void**)&d_sums, (size_t)rows * 8));
+  BVG_TRY(cudaMalloc((void**)&d_sq, (size_t)rows * 8));
+  BVG_TRY(cudaMalloc((void**)&d_ss, (size_t)rows * 8));
+  BVG_TRY(launch_moments(dev_draws, 1, n_draws, rows, d_sums, d_sq, st));
+  BVG_TRY(launch_centered_ss(dev_draws, n_draws, rows, d_sums, d_ss, st));
+  std::vector<double> hs((size_t)rows), hss((size_t)rows);
+  BVG_TRY(cudaMemcpyAsync(hs.data(), d_sums, (size_t)rows * 8, cudaMemcpyDeviceToHost, st));
+  BVG_TRY(cudaMemcpyAsync(hss.data(), d_ss, (size_t)rows * 8, cudaMemcpyDeviceToHost, st));
+  if (n_probs > 0) {
+    BVG_TRY(cudaMalloc((void**)&d_p, (size_t)n_probs * 8));
+    BVG_TRY(cudaMalloc((void**)&d_q, (size_t)n_probs * rows * 8));
+    BVG_TRY(cudaMemcpyAsync(d_p, probs, (size_t)n_probs * 8, cudaMemcpyHostToDevice, st));
+    BVG_TRY(launch_quantiles(dev_draws, n_draws, rows, d_p, n_probs, d_q, st));
+    BVG_TRY(cudaMemcpyAsync(quantiles, d_q, (size_t)n_probs * rows * 8, cudaMemcpyDeviceToHost, st));
+  }
+  BVG_TRY(cudaStreamSynchronize(st));
+#undef BVG_TRY
+  for (int64_t r = 0; r < rows; ++r) {
+    if (mean) mean[r] = hs[r] / (double)n_draws;
+    if (sd) sd[r] = (n_draws > 1) ? std::sqrt(hss[r] / (double)(n_draws - 1)) : 0.0;
+  }
+  return done(0);
+}
+
+int bvg_sampler_summary(bvg_sampler* s, int32_t which, const double* probs, int32_t n_probs, double* mean, double* sd,
+                        double* quantiles, void* cuda_stream) {
+  if (!s) return fail(-1, "sampler is NULL");
+  CK(cudaSetDevice(s->device));
+  const double* buf = nullptr;
+  long long rows = 0;
+  switch (which) {
+    case 0: buf = s->d_coef; rows = s->rows_coef; break;
+    case 1: buf = s->d_sigma; rows = s->rows_sigma; break;
+    case 2: buf = s->d_lambda; rows = s->rows_lambda; break;
+    case 3: buf = s->d_sigma_h; rows = s->rows_sigma_h; break;
+    case 4: buf = s->d_sigma_v; rows = s->rows_sigma_v; break;
+    default: return fail(-1, "which must be 0 (coef), 1 (sigma), 2 (lambda), 3 (sigma_h) or 4 (sigma_v)");
+  }
+  if (!buf || rows < 1) return fail(-6, "the sampler has no such output");
+  return bvg_summary_draws(buf, (int64_t)s->n_chains * s->P.iterations, rows, probs, n_probs, mean, sd, quantiles,
+                           cuda_stream);
 }
 
 int bvg_fp64_peak(double* tflops_fma, void* cuda_stream) {

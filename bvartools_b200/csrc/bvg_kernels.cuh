@@ -46,6 +46,11 @@ cudaError_t launch_loglik_draws(int k, int M, int T, int tvp, int tv_sigma, long
 cudaError_t launch_loglik_total(int k, int M, int T, long long n_draws, const double* dXX, const double* dAols,
                                 const double* dSSE, const double* d_coef, const double* d_sigma, double* d_total,
                                 cudaStream_t stream);
+// posterior summaries of resident draws (bvg_summary.cu): exact type-7 quantiles by radix select, centred sum of squares
+cudaError_t launch_quantiles(const double* draws, long long n_draws, long long rows, const double* d_probs, int n_probs,
+                             double* d_out, cudaStream_t stream);
+cudaError_t launch_centered_ss(const double* draws, long long n_draws, long long rows, const double* d_sums, double* d_ss,
+                               cudaStream_t stream);
 cudaError_t launch_moments(const double* draws, long long chains, long long iters, long long rows, double* sums,
                            double* sumsq, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* tflops, cudaStream_t stream);

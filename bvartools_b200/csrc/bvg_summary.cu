@@ -1,0 +1,257 @@
+// bvg_summary.cu -- posterior summaries of a draw buffer that stays in HBM: what summary.bvar takes
+// from coda::summary.mcmc for every coefficient (R/summary.bvar.R:121-140) -- mean, SD, naive SE and the quantiles
+// (R's default type 7) -- pooled over all draws of all chains, without shipping the draws to the host.
+//
+// Quantiles are EXACT order statistics found by an 8-pass MSB radix select on order-preserving 64-bit keys:
+//   pass p: every row keeps one 256-bin histogram per requested probability, restricted to the elements whose top p
+//           bytes equal the prefix selected so far (shared-memory histograms, warp-aggregated atomics, merged into a
+//           global table); a one-CTA kernel then picks the bin that holds the wanted rank and extends the prefix.
+//   after 8 passes the prefix IS the key of x_(lo), lo = floor((N - 1) p); one more pass finds its upper neighbour
+//           (the smallest element above it, or itself when it is duplicated), and Q = x_lo + (h - lo)(x_hi - x_lo).
+// Every pass streams the buffer once (HBM-bound: 8 bytes per element and pass); the multi-GPU version all-reduces the
+// histogram table between the two kernels of a pass.
+#include "bvg_kernels.cuh"
+
+namespace bvg {
+
+static constexpr int SUM_THREADS = 256;
+
+__device__ __forceinline__ unsigned long long dkey(double x) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+struct SelDims {
+  long long n_draws, rows;
+  int n_probs, pass;           // pass 0..7
+  int row0, row_cnt;           // row chunk of this launch (shared-memory histograms: row_cnt * n_probs * 256 counters)
+};
+
+// prefix[row][q]: key bytes selected so far (top `pass` bytes valid); hist[row][q][256] global counters
+__global__ void __launch_bounds__(SUM_THREADS) select_hist_kernel(const __grid_constant__ SelDims d,
+                                                                   const double* __restrict__ draws,
+                                                                   const unsigned long long* __restrict__ prefix,
+                                                                   unsigned int* __restrict__ hist) {
+  extern __shared__ unsigned int sh[];                       // [row_cnt][nq][256]
+  const int nq = (d.pass == 0) ? 1 : d.n_probs;              // pass 0: all probabilities share the empty prefix
+  const int nbin = d.row_cnt * nq * 256;
+  for (int e = threadIdx.x; e < nbin; e += blockDim.x) sh[e] = 0;
+  __syncthreads();
+  const int shift = 56 - 8 * d.pass;
+  const unsigned long long himask = (d.pass == 0) ? 0ull : (~0ull << (64 - 8 * d.pass));
+  // every thread stays on ONE row of the chunk (its targets' prefixes live in registers) and walks the draws with a
+  // grid-wide stride; consecutive threads read consecutive rows of a draw (contiguous in memory)
+  const long long nthr = (long long)gridDim.x * blockDim.x;
+  const long long per_pass = nthr / d.row_cnt;               // draws covered by one grid-wide step
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (per_pass > 0 && gt < per_pass * d.row_cnt) {
+    const int rl = (int)(gt % d.row_cnt);
+    unsigned long long pf[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) pf[q] = (d.pass > 0 && q < nq) ? prefix[(size_t)(d.row0 + rl) * d.n_probs + q] : 0ull;
+    unsigned int* myh = sh + (size_t)rl * nq * 256;
+    for (long long dr = gt / d.row_cnt; dr < d.n_draws; dr += per_pass) {
+      const unsigned long long key = dkey(draws[dr * d.rows + d.row0 + rl]);
+      const unsigned int bin = (unsigned int)(key >> shift) & 255u;
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if (q < nq && ((key ^ pf[q]) & himask) == 0ull) atomicAdd(&myh[q * 256 + bin], 1u);
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nbin; e += blockDim.x) {
+    const unsigned int v = sh[e];
+    if (v) {
+      const int rl = e / (nq * 256), rem = e % (nq * 256), q = rem / 256, b = rem % 256;
+      if (d.pass == 0) { for (int qq = 0; qq < d.n_probs; ++qq) atomicAdd(&hist[((size_t)(d.row0 + rl) * d.n_probs + qq) * 256 + b], v); }
+      else atomicAdd(&hist[((size_t)(d.row0 + rl) * d.n_probs + q) * 256 + b], v);
+    }
+  }
+}
+
+// one thread per (row, probability): find the bin holding the wanted rank, extend the prefix, clear the histogram
+__global__ void select_pick_kernel(long long rows, int n_probs, int pass, unsigned long long* __restrict__ prefix,
+                                   long long* __restrict__ rank, unsigned int* __restrict__ hist) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * n_probs) return;
+  unsigned int* h = hist + (size_t)t * 256;
+  long long r = rank[t], cum = 0;
+  int b = 0;
+  for (; b < 255; ++b) {
+    if (cum + (long long)h[b] > r) break;
+    cum += h[b];
+  }
+  rank[t] = r - cum;
+  prefix[t] |= (unsigned long long)b << (56 - 8 * pass);
+  for (int e = 0; e < 256; ++e) h[e] = 0;
+}
+
+// upper neighbour of x_lo: count of elements <= x_lo and the smallest key above it, per (row, probability)
+__global__ void __launch_bounds__(SUM_THREADS) select_next_kernel(const __grid_constant__ SelDims d,
+                                                                   const double* __restrict__ draws,
+                                                                   const unsigned long long* __restrict__ prefix,
+                                                                   unsigned long long* __restrict__ cnt_le,
+                                                                   unsigned long long* __restrict__ min_gt) {
+  // same mapping over all rows: a thread stays on one row, keeps count / minimum per probability in registers and
+  // publishes them once
+  const long long nthr = (long long)gridDim.x * blockDim.x;
+  const long long per_pass = nthr / d.rows;
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (per_pass == 0) {                                        // more rows than threads: one row at a time per thread
+    for (long long r = gt; r < d.rows; r += nthr)
+      for (int q = 0; q < d.n_probs; ++q) {
+        const size_t t = (size_t)r * d.n_probs + q;
+        const unsigned long long lo = prefix[t];
+        unsigned long long c = 0ull, mn = ~0ull;
+        for (long long dr = 0; dr < d.n_draws; ++dr) {
+          const unsigned long long key = dkey(draws[dr * d.rows + r]);
+          if (key == lo) ++c; else if (key > lo && key < mn) mn = key;
+        }
+        cnt_le[t] = c; min_gt[t] = mn;
+      }
+    return;
+  }
+  if (gt >= per_pass * d.rows) return;
+  const long long r = gt % d.rows;
+  unsigned long long lo[16], c[16], mn[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) { lo[q] = (q < d.n_probs) ? prefix[(size_t)r * d.n_probs + q] : 0ull; c[q] = 0ull; mn[q] = ~0ull; }
+  for (long long dr = gt / d.rows; dr < d.n_draws; dr += per_pass) {
+    const unsigned long long key = dkey(draws[dr * d.rows + r]);
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if (q < d.n_probs) {
+        if (key == lo[q]) ++c[q];
+        else if (key > lo[q] && key < mn[q]) mn[q] = key;
+      }
+  }
+#pragma unroll
+  for (int q = 0; q < 16; ++q)
+    if (q < d.n_probs) {
+      const size_t t = (size_t)r * d.n_probs + q;
+      if (c[q]) atomicAdd(&cnt_le[t], c[q]);
+      if (mn[q] != ~0ull) atomicMin(&min_gt[t], mn[q]);
+    }
+}
+
+__global__ void select_finish_kernel(long long rows, int n_probs, long long n_draws, const double* __restrict__ probs,
+                                     const unsigned long long* __restrict__ prefix, const long long* __restrict__ rank_in_eq,
+                                     const unsigned long long* __restrict__ cnt_eq, const unsigned long long* __restrict__ min_gt,
+                                     double* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * n_probs) return;
+  const int q = (int)(t % n_probs);
+  const long long r = t / n_probs;
+  const double h = (double)(n_draws - 1) * probs[q];
+  const double lo = floor(h);
+  const double xlo = dunkey(prefix[t]);
+  // rank_in_eq: 0-based position of x_(lo) among the elements equal to it; the next order statistic is the same
+  // value when more duplicates follow, else the smallest element above it (the maximum has no successor: h == lo)
+  double xhi = xlo;
+  if (h > lo) {
+    const bool dup_follows = (unsigned long long)(rank_in_eq[t] + 1) < cnt_eq[t];
+    if (!dup_follows && min_gt[t] != ~0ull) xhi = dunkey(min_gt[t]);
+  }
+  out[(size_t)q * rows + r] = xlo + (h - lo) * (xhi - xlo);              // quantile type 7
+}
+
+__global__ void select_init_kernel(long long rows, int n_probs, long long n_draws, const double* __restrict__ probs,
+                                   unsigned long long* __restrict__ prefix, long long* __restrict__ rank,
+                                   unsigned long long* __restrict__ cnt_eq, unsigned long long* __restrict__ min_gt) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * n_probs) return;
+  const double h = (double)(n_draws - 1) * probs[t % n_probs];
+  prefix[t] = 0ull;
+  rank[t] = (long long)floor(h);
+  cnt_eq[t] = 0ull;
+  min_gt[t] = ~0ull;
+}
+
+// second pass of the standard deviation: ss[r] = sum (x - mean_r)^2 (no E[x^2] - mean^2 cancellation)
+__global__ void __launch_bounds__(256) centered_ss_kernel(const double* __restrict__ draws, long long n_draws, long long rows,
+                                                          const double* __restrict__ sums, double* __restrict__ ss) {
+  const long long nthr = (long long)gridDim.x * blockDim.x;
+  const long long per_pass = nthr / rows;
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (per_pass == 0) {
+    for (long long r = gt; r < rows; r += nthr) {
+      const double mu = sums[r] / (double)n_draws;
+      double acc = 0.0;
+      for (long long dr = 0; dr < n_draws; ++dr) { const double v = draws[dr * rows + r] - mu; acc = fma(v, v, acc); }
+      ss[r] = acc;
+    }
+    return;
+  }
+  if (gt >= per_pass * rows) return;
+  const long long r = gt % rows;
+  const double mu = sums[r] / (double)n_draws;
+  double acc = 0.0;
+  for (long long dr = gt / rows; dr < n_draws; dr += per_pass) { const double v = draws[dr * rows + r] - mu; acc = fma(v, v, acc); }
+  atomicAdd(&ss[r], acc);
+}
+
+cudaError_t launch_centered_ss(const double* draws, long long n_draws, long long rows, const double* d_sums, double* d_ss,
+                               cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(d_ss, 0, (size_t)rows * 8, stream);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  centered_ss_kernel<<<sms * 8, 256, 0, stream>>>(draws, n_draws, rows, d_sums, d_ss);
+  return cudaGetLastError();
+}
+
+// quantiles[q][row] (device) of draws [n_draws][rows] (device); probs (device, n_probs)
+cudaError_t launch_quantiles(const double* draws, long long n_draws, long long rows, const double* d_probs, int n_probs,
+                             double* d_out, cudaStream_t stream) {
+  if (n_draws < 1 || rows < 1 || n_probs < 1 || n_probs > 16) return cudaErrorInvalidValue;
+  const size_t nt = (size_t)rows * n_probs;
+  unsigned long long *prefix = nullptr, *cnt_eq = nullptr, *min_gt = nullptr;
+  long long* rank = nullptr;
+  unsigned int* hist = nullptr;
+  cudaError_t e;
+  if ((e = cudaMallocAsync((void**)&prefix, nt * 8, stream)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&rank, nt * 8, stream)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&cnt_eq, nt * 8, stream)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&min_gt, nt * 8, stream)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&hist, nt * 256 * 4, stream)) != cudaSuccess) return e;
+  cudaMemsetAsync(hist, 0, nt * 256 * 4, stream);
+  const int tb = 128, gb = (int)((nt + tb - 1) / tb);
+  select_init_kernel<<<gb, tb, 0, stream>>>(rows, n_probs, n_draws, d_probs, prefix, rank, cnt_eq, min_gt);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // rows per launch so that the shared histograms fit (<= 96 KB: two CTAs per SM)
+  int row_chunk = (int)((96 * 1024) / ((size_t)n_probs * 256 * 4));
+  if (row_chunk < 1) row_chunk = 1;
+  if (row_chunk > rows) row_chunk = (int)rows;
+  cudaFuncSetAttribute(select_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  int grid = sms * 2;
+  for (int pass = 0; pass < 8; ++pass) {
+    for (int r0 = 0; r0 < rows; r0 += row_chunk) {
+      SelDims d;
+      d.n_draws = n_draws; d.rows = rows; d.n_probs = n_probs; d.pass = pass;
+      d.row0 = r0; d.row_cnt = (int)((r0 + row_chunk <= rows) ? row_chunk : rows - r0);
+      const size_t smem = (size_t)d.row_cnt * ((pass == 0) ? 1 : n_probs) * 256 * 4;
+      select_hist_kernel<<<grid, SUM_THREADS, smem, stream>>>(d, draws, prefix, hist);
+    }
+    select_pick_kernel<<<gb, tb, 0, stream>>>(rows, n_probs, pass, prefix, rank, hist);
+  }
+  // after the last pass rank[t] = position of x_(lo) among its duplicates; count them and find the next larger key
+  {
+    SelDims d;
+    d.n_draws = n_draws; d.rows = rows; d.n_probs = n_probs; d.pass = 8; d.row0 = 0; d.row_cnt = (int)rows;
+    select_next_kernel<<<sms * 8, SUM_THREADS, 0, stream>>>(d, draws, prefix, cnt_eq, min_gt);
+  }
+  select_finish_kernel<<<gb, tb, 0, stream>>>(rows, n_probs, n_draws, d_probs, prefix, rank, cnt_eq, min_gt, d_out);
+  e = cudaGetLastError();
+  cudaFreeAsync(prefix, stream); cudaFreeAsync(rank, stream); cudaFreeAsync(cnt_eq, stream);
+  cudaFreeAsync(min_gt, stream); cudaFreeAsync(hist, stream);
+  return e;
+}
+
+}  // namespace bvg

@@ -116,6 +116,27 @@ class ChainSampler:
         check(lib().bvg_sampler_loglik_total(self.handle, C.byref(tot), C.c_void_p(stream or 0)))
         return tot.value, int(self.spec.c.n_chains) * int(self.spec.c.iterations)
 
+    _WHICH = {"coef": 0, "sigma": 1, "lambda": 2, "sigma_h": 3, "sigma_v": 4}
+
+    def summary(self, which="coef", ci=0.95, probs=None, stream=0):
+        """Posterior summary of one output over ALL retained draws resident on the device (chains x iterations), as
+        summary.bvar / coda::summary.mcmc report them (R/summary.bvar.R:110-140): mean, sd, naive_se and the quantiles
+        (ci_low, 0.5, ci_high) of R's type 7 -- exact order statistics from a radix select in HBM.  For `lambda` the
+        mean is the posterior inclusion frequency."""
+        if probs is None:
+            lo = (1.0 - ci) / 2.0
+            probs = (lo, 0.5, 1.0 - lo)
+        probs = np.ascontiguousarray(probs, dtype=np.float64)
+        rows = int(self.spec.out_rows()[which])
+        mean, sd = np.empty(rows), np.empty(rows)
+        q = np.empty((probs.size, rows))
+        dp = C.POINTER(C.c_double)
+        check(lib().bvg_sampler_summary(self.handle, self._WHICH[which], probs.ctypes.data_as(dp), probs.size,
+                                        mean.ctypes.data_as(dp), sd.ctypes.data_as(dp), q.ctypes.data_as(dp),
+                                        C.c_void_p(stream or 0)))
+        n = int(self.spec.c.n_chains) * int(self.spec.c.iterations)
+        return {"mean": mean, "sd": sd, "naive_se": sd / np.sqrt(n), "quantiles": q, "probs": probs, "n": n}
+
     def close(self):
         if self.handle:
             lib().bvg_sampler_destroy(self.handle)

@@ -204,6 +204,18 @@ int bvg_loglik_total_host(const double* coef, const double* sigma, int64_t n_dra
 int bvg_loglik_normal(const double* u, const double* sigma, int32_t k, int32_t T, int32_t sigma_rows, int64_t n_batch,
                       double* out);
 
+/* ---- posterior summaries of resident draws -------------------------------------------------------
+ * What summary.bvar takes from coda::summary.mcmc for every coefficient (R/summary.bvar.R:121-140): Mean, SD (naive SE =
+ * SD / sqrt(N) follows) and the quantiles, R's default type 7 -- exact order statistics by an 8-pass radix select on the
+ * device -- pooled over all n_draws draws of the buffer [n_draws][rows] (device pointer).  Inclusion frequencies are
+ * the means of the lambda buffer.  mean, sd: rows doubles; quantiles: [n_probs][rows]; host pointers (mean / sd may be
+ * NULL).  The time-series SE of coda (spectrum0.ar) is not computed. */
+int bvg_summary_draws(const double* dev_draws, int64_t n_draws, int64_t rows, const double* probs, int32_t n_probs,
+                      double* mean, double* sd, double* quantiles, void* cuda_stream);
+/* the same for an output of a sampler: which = 0 coef, 1 sigma, 2 lambda, 3 sigma_h, 4 sigma_v */
+int bvg_sampler_summary(bvg_sampler* s, int32_t which, const double* probs, int32_t n_probs, double* mean, double* sd,
+                        double* quantiles, void* cuda_stream);
+
 /* measured FP64 FMA throughput of the device (TFLOP/s) -- roofline denominator for the sweep kernels */
 int bvg_fp64_peak(double* tflops_fma, void* cuda_stream);
 /* measured FP64 tensor-core (DMMA m8n8k4) throughput (TFLOP/s) -- denominator for the large-VAR Cholesky */
