@@ -448,6 +448,28 @@ def main():
         except Exception as exc:       # never let the auxiliary measurement break the bench line
             model_cmp = {"error": str(exc)}
 
+    # ---- next-row kernel: summary.bvar statistics (mean, SD, exact 2.5 / 50 / 97.5 % quantiles) of
+    #      the coefficient draws resident in HBM
+    post_summary = None
+    if not args.no_loglik:
+        try:
+            sm_ms = []
+            for i in range(3):
+                fence()
+                t0 = time.perf_counter()
+                sm = sampler.summary("coef")
+                dt = time.perf_counter() - t0
+                if i > 0:
+                    sm_ms.append(dt * 1e3)
+            ms = float(np.median(sm_ms))
+            nbytes = 8.0 * chains * it * rows["coef"]
+            post_summary = {"what": "bvg_sampler_summary(coef): moments + 8-pass radix select + neighbour pass over all "
+                                    "resident draws (R/summary.bvar.R:121-140)", "ms": ms, "values": chains * it * rows["coef"],
+                            "passes": 11, "stream_GBps": 11 * nbytes / (ms * 1e-3) / 1e9,
+                            "median_first3": [float(v) for v in sm["quantiles"][1][:3]]}
+        except Exception as exc:
+            post_summary = {"error": str(exc)}
+
     # ---- end to end through the public API: host inputs -> H2D -> sweeps -> D2H into pinned host memory
     e2e = None
     if not args.no_e2e:
@@ -587,7 +609,7 @@ def main():
                        "l2": f"retained draws {out_bytes / 1e9:.2f} GB per step per GPU >> 126 MB L2 (no flush needed)",
                        "threads_per_chain": tpc_used or "auto"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "model_comparison": model_cmp,
+            "roofline": roofline, "cpu_baseline": cpu, "model_comparison": model_cmp, "posterior_summary": post_summary,
             "posterior_mean_first3": [float(v) for v in post_mean[:3]]}
     print(json.dumps(line), flush=True)
     if world > 1:

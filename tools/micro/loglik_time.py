@@ -17,3 +17,8 @@ for i in range(3):
     t0 = time.perf_counter(); tot, n = s.loglik_total(); dt = time.perf_counter() - t0
     print(f"loglik_total: {dt * 1e3:.2f} ms for {n} draws -> {n / dt / 1e6:.1f} M draws/s, {240 * n / dt / 1e9:.1f} GB/s, LL {tot / n:.6f}")
 
+for which in ("coef", "sigma"):
+    for i in range(2):
+        t0 = time.perf_counter(); sm = s.summary(which); dt = time.perf_counter() - t0
+    rows = sm["mean"].size
+    print(f"summary({which}): {dt * 1e3:.2f} ms for {sm['n']} draws x {rows} rows; 10 streaming passes -> {10 * 8 * rows * sm['n'] / dt / 1e9:.1f} GB/s; median[0] {sm['quantiles'][1][0]:.6f}")
