@@ -32,6 +32,7 @@ struct SelDims {
 };
 
 // prefix[row][q]: key bytes selected so far (top `pass` bytes valid); hist[row][q][256] global counters
+template <int NQ>   // NQ >= histograms per row of this pass (1 in pass 0, n_probs afterwards): the target loop unrolls exactly
 __global__ void __launch_bounds__(SUM_THREADS) select_hist_kernel(const __grid_constant__ SelDims d,
                                                                    const double* __restrict__ draws,
                                                                    const unsigned long long* __restrict__ prefix,
@@ -50,16 +51,16 @@ __global__ void __launch_bounds__(SUM_THREADS) select_hist_kernel(const __grid_c
   const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (per_pass > 0 && gt < per_pass * d.row_cnt) {
     const int rl = (int)(gt % d.row_cnt);
-    unsigned long long pf[16];
+    unsigned long long pf[NQ];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) pf[q] = (d.pass > 0 && q < nq) ? prefix[(size_t)(d.row0 + rl) * d.n_probs + q] : 0ull;
+    for (int q = 0; q < NQ; ++q) pf[q] = (d.pass > 0 && q < nq) ? prefix[(size_t)(d.row0 + rl) * d.n_probs + q] : 0ull;
     unsigned int* myh = sh + (size_t)rl * nq * 256;
     for (long long dr = gt / d.row_cnt; dr < d.n_draws; dr += per_pass) {
       const unsigned long long key = dkey(draws[dr * d.rows + d.row0 + rl]);
       const unsigned int bin = (unsigned int)(key >> shift) & 255u;
 #pragma unroll
-      for (int q = 0; q < 16; ++q)
-        if (q < nq && ((key ^ pf[q]) & himask) == 0ull) atomicAdd(&myh[q * 256 + bin], 1u);
+      for (int q = 0; q < NQ; ++q)
+        if ((NQ == 1 || q < nq) && ((key ^ pf[q]) & himask) == 0ull) atomicAdd(&myh[q * 256 + bin], 1u);
     }
   }
   __syncthreads();
@@ -91,6 +92,7 @@ __global__ void select_pick_kernel(long long rows, int n_probs, int pass, unsign
 }
 
 // upper neighbour of x_lo: count of elements <= x_lo and the smallest key above it, per (row, probability)
+template <int NQ>
 __global__ void __launch_bounds__(SUM_THREADS) select_next_kernel(const __grid_constant__ SelDims d,
                                                                    const double* __restrict__ draws,
                                                                    const unsigned long long* __restrict__ prefix,
@@ -117,20 +119,20 @@ __global__ void __launch_bounds__(SUM_THREADS) select_next_kernel(const __grid_c
   }
   if (gt >= per_pass * d.rows) return;
   const long long r = gt % d.rows;
-  unsigned long long lo[16], c[16], mn[16];
+  unsigned long long lo[NQ], c[NQ], mn[NQ];
 #pragma unroll
-  for (int q = 0; q < 16; ++q) { lo[q] = (q < d.n_probs) ? prefix[(size_t)r * d.n_probs + q] : 0ull; c[q] = 0ull; mn[q] = ~0ull; }
+  for (int q = 0; q < NQ; ++q) { lo[q] = (q < d.n_probs) ? prefix[(size_t)r * d.n_probs + q] : 0ull; c[q] = 0ull; mn[q] = ~0ull; }
   for (long long dr = gt / d.rows; dr < d.n_draws; dr += per_pass) {
     const unsigned long long key = dkey(draws[dr * d.rows + r]);
 #pragma unroll
-    for (int q = 0; q < 16; ++q)
+    for (int q = 0; q < NQ; ++q)
       if (q < d.n_probs) {
         if (key == lo[q]) ++c[q];
         else if (key > lo[q] && key < mn[q]) mn[q] = key;
       }
   }
 #pragma unroll
-  for (int q = 0; q < 16; ++q)
+  for (int q = 0; q < NQ; ++q)
     if (q < d.n_probs) {
       const size_t t = (size_t)r * d.n_probs + q;
       if (c[q]) atomicAdd(&cnt_le[t], c[q]);
@@ -229,7 +231,15 @@ cudaError_t launch_quantiles(const double* draws, long long n_draws, long long r
   int row_chunk = (int)((96 * 1024) / ((size_t)n_probs * 256 * 4));
   if (row_chunk < 1) row_chunk = 1;
   if (row_chunk > rows) row_chunk = (int)rows;
-  cudaFuncSetAttribute(select_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  // compile-time target counts: 1 (pass 0), then n_probs rounded up to 2 / 3 / 4 / 8 / 16
+  auto hist_launch = [&](const SelDims& d, int grid_, size_t smem_) {
+    const int nq = (d.pass == 0) ? 1 : n_probs;
+#define BVG_HL(N) do { cudaFuncSetAttribute(select_hist_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+                       select_hist_kernel<N><<<grid_, SUM_THREADS, smem_, stream>>>(d, draws, prefix, hist); } while (0)
+    if (nq == 1) BVG_HL(1); else if (nq == 2) BVG_HL(2); else if (nq == 3) BVG_HL(3); else if (nq == 4) BVG_HL(4);
+    else if (nq <= 8) BVG_HL(8); else BVG_HL(16);
+#undef BVG_HL
+  };
   int grid = sms * 2;
   for (int pass = 0; pass < 8; ++pass) {
     for (int r0 = 0; r0 < rows; r0 += row_chunk) {
@@ -237,7 +247,7 @@ cudaError_t launch_quantiles(const double* draws, long long n_draws, long long r
       d.n_draws = n_draws; d.rows = rows; d.n_probs = n_probs; d.pass = pass;
       d.row0 = r0; d.row_cnt = (int)((r0 + row_chunk <= rows) ? row_chunk : rows - r0);
       const size_t smem = (size_t)d.row_cnt * ((pass == 0) ? 1 : n_probs) * 256 * 4;
-      select_hist_kernel<<<grid, SUM_THREADS, smem, stream>>>(d, draws, prefix, hist);
+      hist_launch(d, grid, smem);
     }
     select_pick_kernel<<<gb, tb, 0, stream>>>(rows, n_probs, pass, prefix, rank, hist);
   }
@@ -245,7 +255,10 @@ cudaError_t launch_quantiles(const double* draws, long long n_draws, long long r
   {
     SelDims d;
     d.n_draws = n_draws; d.rows = rows; d.n_probs = n_probs; d.pass = 8; d.row0 = 0; d.row_cnt = (int)rows;
-    select_next_kernel<<<sms * 8, SUM_THREADS, 0, stream>>>(d, draws, prefix, cnt_eq, min_gt);
+#define BVG_NL(N) select_next_kernel<N><<<sms * 8, SUM_THREADS, 0, stream>>>(d, draws, prefix, cnt_eq, min_gt)
+    if (n_probs == 1) BVG_NL(1); else if (n_probs == 2) BVG_NL(2); else if (n_probs == 3) BVG_NL(3);
+    else if (n_probs == 4) BVG_NL(4); else if (n_probs <= 8) BVG_NL(8); else BVG_NL(16);
+#undef BVG_NL
   }
   select_finish_kernel<<<gb, tb, 0, stream>>>(rows, n_probs, n_draws, d_probs, prefix, rank, cnt_eq, min_gt, d_out);
   e = cudaGetLastError();
