@@ -733,6 +733,54 @@ int bvg_sampler_summary(bvg_sampler* s, int32_t which, const double* probs, int3
                            cuda_stream);
 }
 
+int bvg_irf_draws(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
+                  int64_t n_draws, int32_t k, int32_t p, int32_t n_ahead, int32_t type, int32_t impulse, int32_t response,
+                  int32_t shock_kind, double shock, int32_t cumulative, double* dev_out, void* cuda_stream) {
+  if (!dev_out || n_draws < 1 || (p > 0 && !dev_coef)) return fail(-1, "invalid arguments to bvg_irf_draws");
+  if (type < 0 || type > 2) return fail(-7, "Argument 'type' not known.");      // feir / oir / gir (R/irf.bvar.R:84)
+  if ((type != 0 || shock_kind != 0) && !dev_sigma)
+    return fail(-8, "OIR, GIR, SGIR require that the 'bvar' x contains draws of 'Sigma'.");   // R/irf.bvar.R:107-110
+  if (shock_kind < 0 || shock_kind > 2) return fail(-9, "Invalid specification of argument 'shock'.");
+  if (k < 1 || k > 32 || impulse < 0 || impulse >= k || response < 0 || response >= k || n_ahead < 0 || p < 0)
+    return fail(-2, "bvg_irf_draws: need 1 <= k <= 32, 0 <= impulse, response < k, n_ahead >= 0");
+  if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");
+  cudaError_t e = launch_irf_draws(dev_coef, coef_stride, dev_sigma, sigma_stride, n_draws, k, p, n_ahead, type, impulse,
+                                   response, shock_kind, shock, cumulative, dev_out, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "impulse-response kernel");
+  return 0;
+}
+
+int bvg_sampler_irf(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, int32_t impulse, int32_t response,
+                    int32_t shock_kind, double shock, int32_t cumulative, int32_t period, const double* probs,
+                    int32_t n_probs, double* quantiles, double* mean, double* host_draws, void* cuda_stream) {
+  if (!s) return fail(-1, "sampler is NULL");
+  CK(cudaSetDevice(s->device));
+  const int k = s->P.k, T = s->P.T;
+  if (p < 0 || (long long)k * k * p > (long long)s->P.n) return fail(-2, "p lags do not fit the coefficient vector");
+  const bool tv_coef = s->P.tvp != 0, tv_sig = s->P.sigma_type == BVG_SIGMA_SV;
+  if (tv_coef || tv_sig) {
+    if (period < 0) period = T - 1;                                              // R/irf.bvar.R:127-133 (1-based there)
+    if (period >= T) return fail(-11, "Implausible specification of argument 'period'.");
+  }
+  const long long nd = (long long)s->n_chains * s->P.iterations;
+  const double* coef = s->d_coef + (tv_coef ? (size_t)period * s->P.n : 0);
+  const double* sig = s->d_sigma + (tv_sig ? (size_t)period * k * k : 0);
+  double* d_out = nullptr;
+  CK(cudaMalloc((void**)&d_out, (size_t)nd * (n_ahead + 1) * sizeof(double)));
+  int rc = bvg_irf_draws(coef, s->rows_coef, sig, s->rows_sigma, nd, k, p, n_ahead, type, impulse, response, shock_kind,
+                         shock, cumulative, d_out, cuda_stream);
+  if (rc == 0 && (n_probs > 0 || mean))
+    rc = bvg_summary_draws(d_out, nd, n_ahead + 1, probs, n_probs, mean, nullptr, quantiles, cuda_stream);
+  if (rc == 0 && host_draws) {
+    cudaError_t e = cudaMemcpyAsync(host_draws, d_out, (size_t)nd * (n_ahead + 1) * sizeof(double), cudaMemcpyDeviceToHost,
+                                    (cudaStream_t)cuda_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "impulse-response copy");
+  }
+  cudaFree(d_out);
+  return rc;
+}
+
 int bvg_fp64_peak(double* tflops_fma, void* cuda_stream) {
   if (!tflops_fma) return fail(-1, "output pointer is NULL");
   if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");

@@ -51,6 +51,10 @@ cudaError_t launch_quantiles(const double* draws, long long n_draws, long long r
                              double* d_out, cudaStream_t stream);
 cudaError_t launch_centered_ss(const double* draws, long long n_draws, long long rows, const double* d_sums, double* d_ss,
                                cudaStream_t stream);
+// impulse responses per draw (bvg_postest.cu)
+cudaError_t launch_irf_draws(const double* coef, long long coef_stride, const double* sigma, long long sigma_stride,
+                             long long n_draws, int k, int p, int h, int type, int impulse, int response, int shock_kind,
+                             double shock, int cumulative, double* d_out, cudaStream_t stream);
 cudaError_t launch_moments(const double* draws, long long chains, long long iters, long long rows, double* sums,
                            double* sumsq, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* tflops, cudaStream_t stream);

@@ -1,0 +1,115 @@
+// bvg_postest.cu -- per-draw post-estimation on draws resident in HBM: impulse responses.
+//
+// irf.bvar (R/irf.bvar.R:78-216) loops over every posterior draw in R and calls .ir (src/ir.cpp:4-72), which builds the
+// forecast-error responses Phi_i = sum_{j=1..min(i,p)} Phi_{i-j} A_j (k x k each) and returns
+// theta_i = (Phi_i P)[response, impulse] for the transformation P of the requested type; the bands are quantiles over
+// the draws.  Only row `response` of Phi_i is ever used, so one THREAD per draw propagates that row vector
+// (phi_i = sum_j phi_{i-j} A_j: k^2 p products per horizon instead of k^3 p) against column `impulse` of P:
+//   feir  P = I shock                      oir  P = L diag(L)^-1 shock, L = chol(Sigma) lower      (ir.cpp:28-34)
+//   gir   P = Sigma / Sigma_jj shock                                                                 (ir.cpp:38-41)
+// shock = number, or "sd" / "nsd": +- L_jj for oir, +- sqrt(Sigma_jj) otherwise (R/irf.bvar.R:176-188).
+// Output [draw][h + 1] (cumulated on request, R/irf.bvar.R:204-206) stays on the device; the bands come from the radix
+// select of bvg_summary.cu.  Structural types (sir, sgir) need A0 draws, which this sampler does not produce.
+#include "bvg_kernels.cuh"
+
+namespace bvg {
+
+struct IrfDims {
+  long long n_draws, coef_stride, sigma_stride;
+  int k, p, h, type, impulse, response, shock_kind, cumulative;
+  double shock;
+};
+
+static constexpr int IRF_KMAX = 32;
+
+__global__ void __launch_bounds__(128) irf_draws_kernel(const __grid_constant__ IrfDims d, const double* __restrict__ coef,
+                                                        const double* __restrict__ sigma, double* __restrict__ out) {
+  extern __shared__ double sm[];                       // per thread: ring of p row vectors (k each) + column of P (k)
+  const int k = d.k, p = d.p, h = d.h;
+  const int per_thread = (p + 1) * k;
+  double* ring = sm + (size_t)threadIdx.x * per_thread;     // phi_{i-1..i-p}, slot (i mod p)
+  double* pc = ring + p * k;                                 // P[:, impulse]
+  for (long long dr = (long long)blockIdx.x * blockDim.x + threadIdx.x; dr < d.n_draws;
+       dr += (long long)gridDim.x * blockDim.x) {
+    const double* A = coef + dr * d.coef_stride;             // k x (k p), column-major: A_j[a][b] at a + k (b + k (j - 1))
+    const double* S = sigma + dr * d.sigma_stride;           // k x k
+    const int jm = d.impulse, rs = d.response;
+    // ---- column `impulse` of P and the size of the shock
+    double shock = d.shock;
+    if (d.type == 1) {
+      // L = chol(Sigma) lower, column jm: only rows >= jm are non-zero; needs the leading jm + 1 columns of L
+      double Lc[IRF_KMAX * (IRF_KMAX + 1) / 2];
+      for (int c = 0; c <= jm; ++c)
+        for (int i = c; i < k; ++i) {
+          double s = S[i + k * c];
+          for (int m = 0; m < c; ++m) s = fma(-Lc[(i * (i + 1)) / 2 + m], Lc[(c * (c + 1)) / 2 + m], s);
+          Lc[(i * (i + 1)) / 2 + c] = (i == c) ? sqrt(s) : s / Lc[(c * (c + 1)) / 2 + c];
+        }
+      const double ljj = Lc[(jm * (jm + 1)) / 2 + jm];
+      if (d.shock_kind != 0) shock = (d.shock_kind == 2) ? -ljj : ljj;
+      for (int i = 0; i < k; ++i) pc[i] = (i >= jm) ? Lc[(i * (i + 1)) / 2 + jm] / ljj * shock : 0.0;
+    } else {
+      if (d.shock_kind != 0) { const double sdv = sqrt(S[jm + k * jm]); shock = (d.shock_kind == 2) ? -sdv : sdv; }
+      if (d.type == 2) { const double sjj = S[jm + k * jm]; for (int i = 0; i < k; ++i) pc[i] = S[i + k * jm] / sjj * shock; }
+      else for (int i = 0; i < k; ++i) pc[i] = (i == jm) ? shock : 0.0;
+    }
+    // ---- phi_0 = e_response'
+    double* o = out + dr * (h + 1);
+    double acc = 0.0;
+    {
+      const double th = pc[rs];
+      acc = th;
+      o[0] = th;
+    }
+    if (p > 0) for (int b = 0; b < k; ++b) ring[b] = (b == rs) ? 1.0 : 0.0;     // slot 0 = phi_0
+    for (int i = 1; i <= h; ++i) {
+      double* cur = (p > 0) ? ring + (i % p) * k : nullptr;
+      double th = 0.0;
+      if (p > 0) {
+        // phi_i[b] = sum_{j=1..min(i,p)} sum_a phi_{i-j}[a] A_j[a][b]; slot (i mod p) still holds phi_{i-p}: read it last
+        double nw[IRF_KMAX];
+        for (int b = 0; b < k; ++b) nw[b] = 0.0;
+        const int jmax = (i < p) ? i : p;
+        for (int j = 1; j <= jmax; ++j) {
+          const double* ph = ring + ((i - j) % p) * k;
+          const double* Aj = A + (size_t)k * k * (j - 1);
+          for (int b = 0; b < k; ++b) {
+            double s = nw[b];
+            for (int a = 0; a < k; ++a) s = fma(ph[a], Aj[a + k * b], s);
+            nw[b] = s;
+          }
+        }
+        for (int b = 0; b < k; ++b) { cur[b] = nw[b]; th = fma(nw[b], pc[b], th); }
+      }
+      acc += th;
+      o[i] = d.cumulative ? acc : th;
+    }
+  }
+}
+
+cudaError_t launch_irf_draws(const double* coef, long long coef_stride, const double* sigma, long long sigma_stride,
+                             long long n_draws, int k, int p, int h, int type, int impulse, int response, int shock_kind,
+                             double shock, int cumulative, double* d_out, cudaStream_t stream) {
+  if (k < 1 || k > IRF_KMAX || p < 0 || h < 0 || type < 0 || type > 2 || impulse < 0 || impulse >= k || response < 0 ||
+      response >= k || n_draws < 1)
+    return cudaErrorInvalidValue;
+  IrfDims d;
+  d.n_draws = n_draws; d.coef_stride = coef_stride; d.sigma_stride = sigma_stride;
+  d.k = k; d.p = p; d.h = h; d.type = type; d.impulse = impulse; d.response = response; d.shock_kind = shock_kind;
+  d.cumulative = cumulative; d.shock = shock;
+  int threads = 128;
+  size_t smem = (size_t)threads * (p + 1) * k * 8;
+  while (smem > 96 * 1024 && threads > 32) { threads >>= 1; smem = (size_t)threads * (p + 1) * k * 8; }
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(irf_draws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long want = (n_draws + threads - 1) / threads;
+  int grid = (int)((want < (long long)sms * 8) ? want : (long long)sms * 8);
+  irf_draws_kernel<<<grid, threads, smem, stream>>>(d, coef, sigma, d_out);
+  return cudaGetLastError();
+}
+
+}  // namespace bvg

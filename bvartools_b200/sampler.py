@@ -63,6 +63,7 @@ class ChainSampler:
         require_device()
         self.spec = _abi.spec_from_model(obj, n_chains=n_chains, seed=_seed(seed), chain_offset=chain_offset,
                                          device=device, inject=inject, **tuning)
+        self.lags = int(obj.get("model", {}).get("endogen", {}).get("lags", 0))     # p: A = first k*k*p coefficients
         self.handle = C.c_void_p()
         check(lib().bvg_sampler_create(C.byref(self.spec.c), C.byref(self.handle)))
 
@@ -136,6 +137,38 @@ class ChainSampler:
                                         C.c_void_p(stream or 0)))
         n = int(self.spec.c.n_chains) * int(self.spec.c.iterations)
         return {"mean": mean, "sd": sd, "naive_se": sd / np.sqrt(n), "quantiles": q, "probs": probs, "n": n}
+
+    def irf(self, impulse, response, n_ahead=5, ci=0.95, shock=1, type="feir", cumulative=False, keep_draws=False,
+            period=None, p=None, stream=0):
+        """Impulse responses over ALL retained draws resident on the device (irf.bvar, R/irf.bvar.R:78-216): `impulse`
+        / `response` are 0-based variable indices, `shock` a number or "sd" / "nsd", `type` "feir" / "oir" / "gir".
+        Returns the (n_ahead + 1) x 3 band matrix (ci_low, median, ci_high) like the reference, or the draws
+        (draws x (n_ahead + 1)) with keep_draws."""
+        types = {"feir": 0, "oir": 1, "gir": 2}
+        if type not in types:
+            if type in ("sir", "sgir"):
+                raise ValueError("Structural IR requires that draws of 'A0' are contained in the 'bvar' x.")
+            raise ValueError("Argument 'type' not known.")
+        if isinstance(shock, str):
+            if shock not in ("sd", "nsd"):
+                raise ValueError("Invalid specification of argument 'shock'.")
+            kind, val = (1 if shock == "sd" else 2), 0.0
+        else:
+            kind, val = 0, float(shock)
+        k = int(self.spec.c.k)
+        if p is None:
+            p = self.lags
+        lo = (1.0 - ci) / 2.0
+        probs = np.ascontiguousarray([lo, 0.5, 1.0 - lo])
+        n = int(self.spec.c.n_chains) * int(self.spec.c.iterations)
+        q = np.empty((3, n_ahead + 1))
+        draws = np.empty((n, n_ahead + 1)) if keep_draws else None
+        dp = C.POINTER(C.c_double)
+        check(lib().bvg_sampler_irf(self.handle, int(p), int(n_ahead), types[type], int(impulse), int(response), kind, val,
+                                    int(bool(cumulative)), -1 if period is None else int(period), probs.ctypes.data_as(dp),
+                                    0 if keep_draws else 3, q.ctypes.data_as(dp), None,
+                                    None if draws is None else draws.ctypes.data_as(dp), C.c_void_p(stream or 0)))
+        return draws if keep_draws else q.T
 
     def close(self):
         if self.handle:

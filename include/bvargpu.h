@@ -216,6 +216,23 @@ int bvg_summary_draws(const double* dev_draws, int64_t n_draws, int64_t rows, co
 int bvg_sampler_summary(bvg_sampler* s, int32_t which, const double* probs, int32_t n_probs, double* mean, double* sd,
                         double* quantiles, void* cuda_stream);
 
+/* ---- impulse responses per draw --------------------------------------------------------------------
+ * Replaces the per-draw loop of irf.bvar (R/irf.bvar.R:140-216) around .ir (src/ir.cpp:4-72): for every draw
+ * theta_i = (Phi_i P)[response, impulse], i = 0..n_ahead, Phi_i = sum_j Phi_{i-j} A_j.
+ * type: 0 feir, 1 oir, 2 gir (sir / sgir need A0 draws: not produced by these samplers); impulse / response 0-based;
+ * shock_kind: 0 = the number `shock`, 1 = "sd", 2 = "nsd" (R/irf.bvar.R:176-188); cumulative as in :204-206.
+ * dev_coef: draw d starts at dev_coef + d * coef_stride, its first k*k*p doubles are A = [A_1 .. A_p] column-major;
+ * dev_sigma likewise (k x k).  dev_out: [n_draws][n_ahead + 1] on the device. */
+int bvg_irf_draws(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
+                  int64_t n_draws, int32_t k, int32_t p, int32_t n_ahead, int32_t type, int32_t impulse, int32_t response,
+                  int32_t shock_kind, double shock, int32_t cumulative, double* dev_out, void* cuda_stream);
+/* on the retained draws of a sampler + the bands of irf.bvar (type-7 quantiles over all draws, :208-213): quantiles
+ * [n_probs][n_ahead + 1], mean [n_ahead + 1] (may be NULL), host_draws [draws][n_ahead + 1] (keep_draws; may be NULL) on
+ * the host.  period: 0-based period for TVP / SV draws, < 0 = the last one (:127-133). */
+int bvg_sampler_irf(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, int32_t impulse, int32_t response,
+                    int32_t shock_kind, double shock, int32_t cumulative, int32_t period, const double* probs,
+                    int32_t n_probs, double* quantiles, double* mean, double* host_draws, void* cuda_stream);
+
 /* measured FP64 FMA throughput of the device (TFLOP/s) -- roofline denominator for the sweep kernels */
 int bvg_fp64_peak(double* tflops_fma, void* cuda_stream);
 /* measured FP64 tensor-core (DMMA m8n8k4) throughput (TFLOP/s) -- denominator for the large-VAR Cholesky */

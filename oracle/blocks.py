@@ -292,3 +292,59 @@ def summary_bvarlist_row(y, x, temp_pars, sigma_draws, tvp=False, sv=False):
     return {"LL": ll, "AIC": 2 * tot_pars - 2 * ll, "BIC": np.log(tt) * tot_pars - 2 * ll,
             "HQ": 2 * np.log(np.log(tt)) * tot_pars - 2 * ll, "ll_t": LL.mean(axis=1)}
 
+
+def ir(A, Sigma, h, type, impulse, response, shock=1.0):
+    """src/ir.cpp:4-72, literally (full Phi matrices): A is k x (k p), impulse / response 1-based as in R."""
+    coef = np.asarray(A, dtype=float)
+    k = coef.shape[0]
+    p = coef.shape[1] // k
+    p_cols = h * k if h < p else coef.shape[1]
+    P = np.eye(k)
+    if type == "feir":
+        P = P * shock
+    elif type == "oir":
+        P = np.linalg.cholesky(np.asarray(Sigma, dtype=float))          # trans(chol(Sigma)) = lower factor
+        P = P @ np.diag(1.0 / np.diag(P)) * shock
+    elif type == "gir":
+        S = np.asarray(Sigma, dtype=float)
+        P = S / S[impulse - 1, impulse - 1] * shock
+    else:
+        raise ValueError("type")
+    phi = np.zeros(((h + 1) * k, k))
+    phi[:k] = np.eye(k)
+    theta = np.zeros(h + 1)
+    theta[0] = (np.eye(k) @ P)[response - 1, impulse - 1]
+    A_temp = np.zeros((k, h * k))
+    A_temp[:, :p_cols] = coef[:, :p_cols]
+    for i in range(1, h + 1):
+        phi_temp = np.zeros((k, k))
+        for j in range(1, i + 1):
+            phi_temp = phi_temp + phi[(i - j) * k:(i - j + 1) * k] @ A_temp[:, (j - 1) * k:j * k]
+        phi[i * k:(i + 1) * k] = phi_temp
+        theta[i] = (phi_temp @ P)[response - 1, impulse - 1]
+    return theta
+
+
+def irf_bvar(A_draws, Sigma_draws, k, impulse, response, n_ahead=5, ci=0.95, shock=1, type="feir", cumulative=False,
+             keep_draws=False):
+    """R/irf.bvar.R:140-216 for a constant-parameter `bvar`: A_draws (draws x k^2 p), Sigma_draws (draws x k^2),
+    impulse / response 1-based.  Returns the (n_ahead + 1) x 3 band matrix or the draws."""
+    res = []
+    for i in range(A_draws.shape[0]):
+        A = A_draws[i].reshape(k, -1, order="F") if A_draws.shape[1] else np.zeros((k, k))
+        S = Sigma_draws[i].reshape(k, k, order="F")
+        if isinstance(shock, str):
+            sh = np.linalg.cholesky(S).T[impulse - 1, impulse - 1] if type == "oir" else np.sqrt(S[impulse - 1, impulse - 1])
+            if shock == "nsd":
+                sh = -sh
+        else:
+            sh = shock
+        res.append(ir(A, S, n_ahead, type, impulse, response, sh))
+    result = np.array(res)
+    if cumulative:
+        result = np.cumsum(result, axis=1)
+    if keep_draws:
+        return result
+    lo = (1 - ci) / 2
+    return np.quantile(result, [lo, 0.5, 1 - lo], axis=0).T
+

@@ -1,0 +1,77 @@
+"""Impulse responses per draw: the device kernel + radix-select bands against the oracle restatement
+of .ir (src/ir.cpp:4-72) and irf.bvar (R/irf.bvar.R:140-216).  CPU: the oracle against the textbook recursion."""
+import numpy as np
+import pytest
+
+import helpers
+from oracle import blocks as ob
+
+TOL = 1e-10
+
+
+def test_oracle_ir_matches_companion_powers():
+    """FEIR Phi_i = J C^i J' with the companion matrix C (Luetkepohl 2006, 2.1.22)."""
+    rng = np.random.default_rng(1)
+    k, p, h = 3, 2, 7
+    A = rng.standard_normal((k, k * p)) * 0.3
+    C = np.zeros((k * p, k * p))
+    C[:k] = A
+    C[k:, :-k] = np.eye(k * (p - 1))
+    S = np.eye(k)
+    for imp in range(1, k + 1):
+        for resp in range(1, k + 1):
+            th = ob.ir(A, S, h, "feir", imp, resp)
+            want = [np.linalg.matrix_power(C, i)[:k, :k][resp - 1, imp - 1] for i in range(h + 1)]
+            np.testing.assert_allclose(th, want, rtol=1e-12, atol=1e-14)
+    # h < p: only the first h lags enter (ir.cpp:17-21)
+    th = ob.ir(A, S, 1, "feir", 1, 2)
+    np.testing.assert_allclose(th, [0.0, A[1, 0]], atol=1e-15)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("type_,shock,cumulative", [("feir", 1, False), ("feir", 2.5, True), ("oir", 1, False),
+                                                    ("oir", "sd", False), ("gir", "nsd", True), ("gir", 0.5, False)])
+def test_irf_on_resident_draws_matches_oracle(gpu, type_, shock, cumulative):
+    from bvartools_b200 import ChainSampler, _abi
+    obj = helpers.model_c1(iterations=40, burnin=10)
+    s = ChainSampler(obj, n_chains=4, seed=6)
+    s.run(0)
+    host = _abi.OutBuffers(s.spec)
+    s.fetch(host)
+    k, p = 3, 2
+    coef = host.arrays["coef"].reshape(-1, host.arrays["coef"].shape[-1])
+    sig = host.arrays["sigma"].reshape(-1, k * k)
+    A_draws = coef[:, :k * k * p]
+    for imp, resp, h in ((0, 1, 6), (2, 2, 1), (1, 0, 12)):
+        kw = dict(n_ahead=h, ci=0.9, shock=shock, type=type_, cumulative=cumulative)
+        want_d = ob.irf_bvar(A_draws, sig, k, imp + 1, resp + 1, keep_draws=True, **kw)
+        got_d = s.irf(imp, resp, keep_draws=True, **kw)
+        assert helpers.relerr(got_d, want_d) < TOL, (type_, imp, resp)
+        want_b = ob.irf_bvar(A_draws, sig, k, imp + 1, resp + 1, **kw)
+        got_b = s.irf(imp, resp, **kw)
+        np.testing.assert_allclose(got_b, want_b, rtol=1e-10, atol=1e-14)
+    with pytest.raises(ValueError):
+        s.irf(0, 1, type="sir")
+    s.close()
+
+
+@pytest.mark.gpu
+def test_irf_of_tvp_sv_draws_at_a_period(gpu):
+    from bvartools_b200 import ChainSampler, _abi
+    obj = helpers.model_sv(tvp=True, nobs=30, iterations=8, burnin=2)
+    s = ChainSampler(obj, n_chains=3, seed=2)
+    s.run(0)
+    host = _abi.OutBuffers(s.spec)
+    s.fetch(host)
+    Y = obj["data"]["Y"]
+    T, k = Y.shape
+    p = s.lags
+    n = host.arrays["coef"].shape[-1] // T
+    coef = host.arrays["coef"].reshape(-1, T, n)
+    sig = host.arrays["sigma"].reshape(-1, T, k * k)
+    for period in (None, 0, 11):
+        t = T - 1 if period is None else period
+        want = ob.irf_bvar(coef[:, t, :k * k * p], sig[:, t], k, 1, 2, n_ahead=5, type="oir", shock="sd", keep_draws=True)
+        got = s.irf(0, 1, n_ahead=5, type="oir", shock="sd", keep_draws=True, period=period)
+        assert helpers.relerr(got, want) < TOL
+    s.close()
