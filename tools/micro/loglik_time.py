@@ -22,3 +22,7 @@ for which in ("coef", "sigma"):
         t0 = time.perf_counter(); sm = s.summary(which); dt = time.perf_counter() - t0
     rows = sm["mean"].size
     print(f"summary({which}): {dt * 1e3:.2f} ms for {sm['n']} draws x {rows} rows; 10 streaming passes -> {10 * 8 * rows * sm['n'] / dt / 1e9:.1f} GB/s; median[0] {sm['quantiles'][1][0]:.6f}")
+for typ in ("feir", "oir"):
+    for i in range(2):
+        t0 = time.perf_counter(); b = s.irf(0, 1, n_ahead=20, type=typ, shock="sd" if typ == "oir" else 1); dt = time.perf_counter() - t0
+    print(f"irf({typ}, h=20): {dt * 1e3:.2f} ms for {chains * it} draws (kernel + 3-quantile bands over 21 horizons); median h=1: {b[1, 1]:.6f}")
