@@ -99,7 +99,34 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.device, self.rows, self.stop_flag = device, [], threading.Event()
 
+    def _run_nvml(self):
+        """NVML in-process: a sample every ~2 ms, so that even a 50 ms timed region is covered by tens of samples."""
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(self.device))
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        while not self.stop_flag.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            try:
+                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+            except Exception:
+                pw = float("nan")
+            try:
+                rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            except Exception:
+                rs = 0
+            self.rows.append([str(self.device), str(sm), str(mx), f"{pw:.2f}", hex(rs)] +
+                             [("Active" if rs & bits[n] else "Not Active")
+                              for n in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+            self.stop_flag.wait(0.002)
+
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass                                   # no NVML bindings: fall back to polling nvidia-smi
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
@@ -113,7 +140,8 @@ class ClockSampler(threading.Thread):
     def summary(self):
         def num(v):
             try:
-                return float(v)
+                f = float(v)
+                return None if f != f else f
             except ValueError:
                 return None
         sm = [num(r[1]) for r in self.rows if len(r) > 8 and num(r[1]) is not None]
