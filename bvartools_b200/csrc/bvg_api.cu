@@ -781,6 +781,51 @@ int bvg_sampler_irf(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, in
   return rc;
 }
 
+int bvg_fevd_draws(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
+                   int64_t n_draws, int32_t k, int32_t p, int32_t n_ahead, int32_t type, int32_t response,
+                   int32_t normalise_gir, double* host_out, void* cuda_stream) {
+  if (!host_out || n_draws < 1 || (p > 0 && !dev_coef)) return fail(-1, "invalid arguments to bvg_fevd_draws");
+  if (!dev_sigma) return fail(-8, "Argument 'object' must include draws of the variance-covariance matrix Sigma.");
+  if (type != 1 && type != 2) return fail(-7, "The specified type of the used impulse response is not known.");
+  if (k < 1 || k > 32 || response < 0 || response >= k || n_ahead < 0 || p < 0)
+    return fail(-2, "bvg_fevd_draws: need 1 <= k <= 32, 0 <= response < k, n_ahead >= 0");
+  if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const size_t nout = (size_t)(n_ahead + 1) * k;
+  double* d_out = nullptr;
+  CK(cudaMalloc((void**)&d_out, nout * sizeof(double)));
+  cudaError_t e = launch_fevd_draws(dev_coef, coef_stride, dev_sigma, sigma_stride, n_draws, k, p, n_ahead, type, response,
+                                    d_out, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, d_out, nout * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return cuda_fail(e, "variance-decomposition kernel");
+  if (type == 2 && normalise_gir)                                               // R/fevd.bvar.R:167-171
+    for (int i = 0; i <= n_ahead; ++i) {
+      double sum = 0.0;
+      for (int c = 0; c < k; ++c) sum += host_out[(size_t)i * k + c];
+      for (int c = 0; c < k; ++c) host_out[(size_t)i * k + c] /= sum;
+    }
+  return 0;
+}
+
+int bvg_sampler_fevd(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, int32_t response, int32_t normalise_gir,
+                     int32_t period, double* host_out, void* cuda_stream) {
+  if (!s) return fail(-1, "sampler is NULL");
+  CK(cudaSetDevice(s->device));
+  const int k = s->P.k, T = s->P.T;
+  if (p < 0 || (long long)k * k * p > (long long)s->P.n) return fail(-2, "p lags do not fit the coefficient vector");
+  const bool tv_coef = s->P.tvp != 0, tv_sig = s->P.sigma_type == BVG_SIGMA_SV;
+  if (tv_coef || tv_sig) {
+    if (period < 0) period = T - 1;
+    if (period >= T) return fail(-11, "Implausible specification of argument 'period'.");
+  }
+  const double* coef = s->d_coef + (tv_coef ? (size_t)period * s->P.n : 0);
+  const double* sig = s->d_sigma + (tv_sig ? (size_t)period * k * k : 0);
+  return bvg_fevd_draws(coef, s->rows_coef, sig, s->rows_sigma, (int64_t)s->n_chains * s->P.iterations, k, p, n_ahead,
+                        type, response, normalise_gir, host_out, cuda_stream);
+}
+
 int bvg_fp64_peak(double* tflops_fma, void* cuda_stream) {
   if (!tflops_fma) return fail(-1, "output pointer is NULL");
   if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");

@@ -112,4 +112,135 @@ cudaError_t launch_irf_draws(const double* coef, long long coef_stride, const do
   return cudaGetLastError();
 }
 
+// ---- forecast error variance decomposition (fevd.bvar, R/fevd.bvar.R:72-186; .vardecomp, src/vardecomp.cpp:4-87) ------
+// Per draw, with phi_i = row `response` of Phi_i:  numerator_i[c] = sum_{l<=i} (phi_l P)[c]^2,
+// mse_i = sum_{l<=i} phi_l Sigma phi_l',  result_i[c] = numerator_i[c] / sigmajj / mse_i  (sigmajj = sqrt(Sigma_rr) for gir,
+// 1 for oir -- exactly as the reference normalises).  fevd.bvar returns the MEAN over the draws of the (h + 1) x k table:
+// a thread per draw, warp-shuffle sums, per-warp slots in shared memory, per-CTA partials reduced in a fixed order.
+struct FevdDims {
+  long long n_draws, coef_stride, sigma_stride;
+  int k, p, h, type, response;                    // type 1 oir, 2 gir
+};
+
+__global__ void __launch_bounds__(128) fevd_draws_kernel(const __grid_constant__ FevdDims d, const double* __restrict__ coef,
+                                                         const double* __restrict__ sigma, double* __restrict__ partial) {
+  extern __shared__ double sm[];
+  const int k = d.k, p = d.p, h = d.h, nout = (h + 1) * k;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  double* wacc = sm;                                         // [nwarp][nout] per-warp sums
+  double* ring0 = wacc + (size_t)nwarp * nout;
+  const int per_thread = p * k + 2 * k;
+  double* ring = ring0 + (size_t)threadIdx.x * per_thread;   // phi ring (p x k) | numerator (k) | v = phi P (k)
+  double* num = ring + p * k;
+  double* v = num + k;
+  for (int e = threadIdx.x; e < nwarp * nout; e += blockDim.x) wacc[e] = 0.0;
+  __syncthreads();
+  const long long nthr = (long long)gridDim.x * blockDim.x;
+  const long long rounds = (d.n_draws + nthr - 1) / nthr;    // every thread of a warp runs the same number of rounds
+  for (long long rd = 0; rd < rounds; ++rd) {
+    const long long dr = rd * nthr + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = dr < d.n_draws;
+    const double* A = coef + (live ? dr : 0) * d.coef_stride;
+    const double* S = sigma + (live ? dr : 0) * d.sigma_stride;
+    double Lc[IRF_KMAX * (IRF_KMAX + 1) / 2];
+    double sigmajj = 1.0;
+    if (d.type == 1) {                                       // P = chol(Sigma)' = L (lower)
+      for (int c = 0; c < k; ++c)
+        for (int i = c; i < k; ++i) {
+          double s = S[i + k * c];
+          for (int m = 0; m < c; ++m) s = fma(-Lc[(i * (i + 1)) / 2 + m], Lc[(c * (c + 1)) / 2 + m], s);
+          Lc[(i * (i + 1)) / 2 + c] = (i == c) ? sqrt(s) : s / Lc[(c * (c + 1)) / 2 + c];
+        }
+    } else {
+      sigmajj = sqrt(S[d.response + k * d.response]);
+    }
+    for (int b = 0; b < k; ++b) num[b] = 0.0;
+    double mse = 0.0;
+    for (int i = 0; i <= h; ++i) {
+      // phi_i into a local row
+      double ph[IRF_KMAX];
+      if (i == 0) { for (int b = 0; b < k; ++b) ph[b] = (b == d.response) ? 1.0 : 0.0; }
+      else {
+        for (int b = 0; b < k; ++b) ph[b] = 0.0;
+        const int jmax = (i < p) ? i : p;
+        for (int j = 1; j <= jmax; ++j) {
+          const double* pv = ring + ((i - j) % p) * k;
+          const double* Aj = A + (size_t)k * k * (j - 1);
+          for (int b = 0; b < k; ++b) {
+            double s = ph[b];
+            for (int a = 0; a < k; ++a) s = fma(pv[a], Aj[a + k * b], s);
+            ph[b] = s;
+          }
+        }
+      }
+      if (p > 0) for (int b = 0; b < k; ++b) ring[(i % p) * k + b] = ph[b];
+      // v = phi P ;  mse += phi Sigma phi'
+      for (int c = 0; c < k; ++c) {
+        double s = 0.0;
+        if (d.type == 1) { for (int a = c; a < k; ++a) s = fma(ph[a], Lc[(a * (a + 1)) / 2 + c], s); }
+        else { for (int a = 0; a < k; ++a) s = fma(ph[a], S[a + k * c], s); }
+        v[c] = s;
+      }
+      double q = 0.0;
+      for (int c = 0; c < k; ++c) {
+        double s = 0.0;
+        for (int a = 0; a < k; ++a) s = fma(ph[a], S[a + k * c], s);
+        q = fma(s, ph[c], q);
+      }
+      mse += q;
+      for (int c = 0; c < k; ++c) {
+        num[c] = fma(v[c], v[c], num[c]);
+        double r = live ? num[c] / sigmajj / mse : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (lane == 0) wacc[(size_t)warp * nout + i * k + c] += r;
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nout; e += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < nwarp; ++w) s += wacc[(size_t)w * nout + e];
+    partial[(size_t)blockIdx.x * nout + e] = s;
+  }
+}
+
+__global__ void fevd_reduce_kernel(const double* __restrict__ partial, int n_part, int nout, double inv_n, double* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nout) return;
+  double s = 0.0;
+  for (int b = 0; b < n_part; ++b) s += partial[(size_t)b * nout + e];
+  out[e] = s * inv_n;
+}
+
+// d_out: (h + 1) x k row-major = result[i][c], the mean over the draws
+cudaError_t launch_fevd_draws(const double* coef, long long coef_stride, const double* sigma, long long sigma_stride,
+                              long long n_draws, int k, int p, int h, int type, int response, double* d_out,
+                              cudaStream_t stream) {
+  if (k < 1 || k > IRF_KMAX || p < 0 || h < 0 || (type != 1 && type != 2) || response < 0 || response >= k || n_draws < 1)
+    return cudaErrorInvalidValue;
+  FevdDims d;
+  d.n_draws = n_draws; d.coef_stride = coef_stride; d.sigma_stride = sigma_stride;
+  d.k = k; d.p = p; d.h = h; d.type = type; d.response = response;
+  const int nout = (h + 1) * k;
+  int threads = 128;
+  auto bytes = [&](int t) { return ((size_t)(t / 32) * nout + (size_t)t * (p * k + 2 * k)) * 8; };
+  while (bytes(threads) > 96 * 1024 && threads > 32) threads >>= 1;
+  if (bytes(threads) > 200 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(fevd_draws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(threads));
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long want = (n_draws + threads - 1) / threads;
+  int grid = (int)((want < (long long)sms * 4) ? want : (long long)sms * 4);
+  double* partial = nullptr;
+  if ((e = cudaMallocAsync((void**)&partial, (size_t)grid * nout * 8, stream)) != cudaSuccess) return e;
+  fevd_draws_kernel<<<grid, threads, bytes(threads), stream>>>(d, coef, sigma, partial);
+  fevd_reduce_kernel<<<(nout + 127) / 128, 128, 0, stream>>>(partial, grid, nout, 1.0 / (double)n_draws, d_out);
+  e = cudaGetLastError();
+  cudaFreeAsync(partial, stream);
+  return e;
+}
+
 }  // namespace bvg

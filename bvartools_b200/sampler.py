@@ -170,6 +170,21 @@ class ChainSampler:
                                     None if draws is None else draws.ctypes.data_as(dp), C.c_void_p(stream or 0)))
         return draws if keep_draws else q.T
 
+    def fevd(self, response, n_ahead=5, type="oir", normalise_gir=False, period=None, p=None, stream=0):
+        """Forecast error variance decomposition averaged over ALL retained draws resident on the device (fevd.bvar,
+        R/fevd.bvar.R:72-186): the (n_ahead + 1) x k table for the 0-based `response` variable; type "oir" or "gir"."""
+        types = {"oir": 1, "gir": 2}
+        if type not in types:
+            if type in ("sir", "sgir"):
+                raise ValueError("Structural FEVD requires that draws of 'A0' are contained in the 'bvar' object.")
+            raise ValueError("The specified type of the used impulse response is not known.")
+        k = int(self.spec.c.k)
+        out = np.empty((n_ahead + 1, k))
+        check(lib().bvg_sampler_fevd(self.handle, int(self.lags if p is None else p), int(n_ahead), types[type],
+                                     int(response), int(bool(normalise_gir)), -1 if period is None else int(period),
+                                     out.ctypes.data_as(C.POINTER(C.c_double)), C.c_void_p(stream or 0)))
+        return out
+
     def close(self):
         if self.handle:
             lib().bvg_sampler_destroy(self.handle)

@@ -233,6 +233,17 @@ int bvg_sampler_irf(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, in
                     int32_t shock_kind, double shock, int32_t cumulative, int32_t period, const double* probs,
                     int32_t n_probs, double* quantiles, double* mean, double* host_draws, void* cuda_stream);
 
+/* ---- forecast error variance decomposition per draw -----------------------------------------------
+ * Replaces the per-draw loop of fevd.bvar (R/fevd.bvar.R:128-165) around .vardecomp (src/vardecomp.cpp:4-87) and its
+ * rowMeans over the draws: host_out is the (n_ahead + 1) x k table (row i = horizon, column c = shock variable; row-major),
+ * the MEAN over all draws.  type: 1 oir, 2 gir (sir / sgir need A0 draws); response 0-based; normalise_gir as :167-171.
+ * Buffer layouts as in bvg_irf_draws. */
+int bvg_fevd_draws(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
+                   int64_t n_draws, int32_t k, int32_t p, int32_t n_ahead, int32_t type, int32_t response,
+                   int32_t normalise_gir, double* host_out, void* cuda_stream);
+int bvg_sampler_fevd(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, int32_t response, int32_t normalise_gir,
+                     int32_t period, double* host_out, void* cuda_stream);
+
 /* measured FP64 FMA throughput of the device (TFLOP/s) -- roofline denominator for the sweep kernels */
 int bvg_fp64_peak(double* tflops_fma, void* cuda_stream);
 /* measured FP64 tensor-core (DMMA m8n8k4) throughput (TFLOP/s) -- denominator for the large-VAR Cholesky */

@@ -348,3 +348,55 @@ def irf_bvar(A_draws, Sigma_draws, k, impulse, response, n_ahead=5, ci=0.95, sho
     lo = (1 - ci) / 2
     return np.quantile(result, [lo, 0.5, 1 - lo], axis=0).T
 
+
+def vardecomp(A, Sigma, h, type, response):
+    """src/vardecomp.cpp:4-87, literally; response 1-based.  Returns the (h + 1) x k table of one draw."""
+    a = np.asarray(A, dtype=float)
+    sigma = np.asarray(Sigma, dtype=float)
+    k = a.shape[0]
+    p = a.shape[1] // k
+    p_cols = h * k if h < p else a.shape[1]
+    if type == "oir":
+        P = np.linalg.cholesky(sigma)
+        sigma_mse = sigma
+    elif type == "gir":
+        P = sigma
+        sigma_mse = sigma
+    else:
+        raise ValueError("type")
+    sigmajj = np.sqrt(sigma[response - 1, response - 1]) if type == "gir" else 1.0
+    A_temp = np.zeros((k, h * k))
+    A_temp[:, :p_cols] = a[:, :p_cols]
+    result = np.zeros((h + 1, k))
+    numerator = np.zeros((h + 1, k))
+    mse = np.zeros(h + 1)
+    ejt = np.zeros((1, k))
+    ejt[0, response - 1] = 1
+    phi = np.zeros(((h + 1) * k, k))
+    phi_temp = np.eye(k)
+    phi[:k] = phi_temp
+    numerator[0] = np.square(ejt @ phi_temp @ P)
+    mse[0] = (ejt @ phi_temp @ sigma_mse @ phi_temp.T @ ejt.T).item()
+    result[0] = numerator[0] / sigmajj / mse[0]
+    for i in range(1, h + 1):
+        phi_temp = np.zeros((k, k))
+        for j in range(1, i + 1):
+            phi_temp = phi_temp + phi[(i - j) * k:(i - j + 1) * k] @ A_temp[:, (j - 1) * k:j * k]
+        phi[i * k:(i + 1) * k] = phi_temp
+        numerator[i] = numerator[i - 1] + np.square(ejt @ phi_temp @ P)
+        mse[i] = mse[i - 1] + (ejt @ phi_temp @ sigma_mse @ phi_temp.T @ ejt.T).item()
+        result[i] = numerator[i] / sigmajj / mse[i]
+    return result
+
+
+def fevd_bvar(A_draws, Sigma_draws, k, response, n_ahead=5, type="oir", normalise_gir=False):
+    """R/fevd.bvar.R:128-175 for a constant-parameter `bvar`: the mean over the draws of .vardecomp."""
+    acc = np.zeros((n_ahead + 1, k))
+    for i in range(A_draws.shape[0]):
+        A = A_draws[i].reshape(k, -1, order="F") if A_draws.shape[1] else np.zeros((k, k))
+        acc += vardecomp(A, Sigma_draws[i].reshape(k, k, order="F"), n_ahead, type, response)
+    result = acc / A_draws.shape[0]
+    if type == "gir" and normalise_gir:
+        result = result / result.sum(axis=1, keepdims=True)
+    return result
+

@@ -75,3 +75,36 @@ def test_irf_of_tvp_sv_draws_at_a_period(gpu):
         got = s.irf(0, 1, n_ahead=5, type="oir", shock="sd", keep_draws=True, period=period)
         assert helpers.relerr(got, want) < TOL
     s.close()
+
+
+def test_oracle_vardecomp_oir_rows_sum_to_one():
+    """Orthogonalised FEVD shares of a response add up to one at every horizon (Luetkepohl 2006, 2.3.37)."""
+    rng = np.random.default_rng(2)
+    k, p, h = 3, 2, 6
+    A = rng.standard_normal((k, k * p)) * 0.3
+    B = rng.standard_normal((k, k))
+    S = B @ B.T + np.eye(k)
+    for resp in range(1, k + 1):
+        np.testing.assert_allclose(ob.vardecomp(A, S, h, "oir", resp).sum(axis=1), 1.0, rtol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("type_,norm", [("oir", False), ("gir", False), ("gir", True)])
+def test_fevd_on_resident_draws_matches_oracle(gpu, type_, norm):
+    from bvartools_b200 import ChainSampler, _abi
+    obj = helpers.model_c1(iterations=50, burnin=10)
+    s = ChainSampler(obj, n_chains=5, seed=8)
+    s.run(0)
+    host = _abi.OutBuffers(s.spec)
+    s.fetch(host)
+    k, p = 3, 2
+    coef = host.arrays["coef"].reshape(-1, host.arrays["coef"].shape[-1])
+    sig = host.arrays["sigma"].reshape(-1, k * k)
+    for resp, h in ((0, 5), (2, 1), (1, 10)):
+        want = ob.fevd_bvar(coef[:, :k * k * p], sig, k, resp + 1, n_ahead=h, type=type_, normalise_gir=norm)
+        got = s.fevd(resp, n_ahead=h, type=type_, normalise_gir=norm)
+        assert helpers.relerr(got, want) < TOL, (type_, resp, h)
+    with pytest.raises(ValueError):
+        s.fevd(0, type="sgir")
+    s.close()
+
