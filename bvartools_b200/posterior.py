@@ -18,7 +18,7 @@ import ctypes as C
 from . import sampler
 from ._lib import check, lib, require_device
 
-__all__ = ["draw_posterior", "bvarpost", "bvar", "summary", "summary_bvarlist", "information_criteria"]
+__all__ = ["draw_posterior", "bvarpost", "bvar", "summary", "summary_bvarlist", "information_criteria", "thin"]
 
 
 def bvar(y, x=None, A0=None, A=None, B=None, C=None, Sigma=None):
@@ -103,6 +103,28 @@ def summary(obj, ci=(0.025, 0.5, 0.975)):
         res[name] = {"mean": d.mean(axis=0), "sd": d.std(axis=0, ddof=1),
                      "quantiles": np.quantile(d, ci, axis=0)}
     return res
+
+
+def thin(obj, thin=10):
+    """thin.bvar (R/thin.bvar.R:31-67): keep every `thin`-th draw (positions thin, 2 thin, ... in R's 1-based count) of
+    every draw matrix of a `bvar` object.  Plain row indexing on the host object -- no device path is needed."""
+    out = dict(obj)
+    draws = None
+    for name in ("A0", "A", "B", "C", "Sigma"):
+        d = obj.get(name)
+        if d is not None:
+            draws = (d[0] if isinstance(d, list) else d).shape[0]
+            break
+    if draws is None:
+        return out
+    pos = np.arange(thin, draws + 1, thin) - 1
+    for base in ("A", "B", "C", "A0", "Sigma"):
+        for name in (base, base + "_sigma", base + "_lambda"):
+            d = obj.get(name)
+            if d is None:
+                continue
+            out[name] = [np.asarray(x)[pos] for x in d] if isinstance(d, list) else np.asarray(d)[pos]
+    return out
 
 
 def information_criteria(ll, tot_pars, tt):
