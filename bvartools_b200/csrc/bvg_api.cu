@@ -826,6 +826,65 @@ int bvg_sampler_fevd(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, i
                         type, response, normalise_gir, host_out, cuda_stream);
 }
 
+int bvg_forecast_draws(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
+                       int64_t n_draws, int32_t k, int32_t p, int32_t tot, int32_t n_ahead, const double* pred,
+                       const double* dev_eps, uint64_t seed, double* dev_out, void* cuda_stream) {
+  if (!dev_sigma || !pred || !dev_out || n_draws < 1) return fail(-1, "invalid arguments to bvg_forecast_draws");
+  if (k < 1 || k > 32 || p < 0 || n_ahead < 1 || tot < k || (p > 0 && tot < k * p))
+    return fail(-2, "bvg_forecast_draws: need 1 <= k <= 32, n_ahead >= 1, tot >= k max(p, 1)");
+  const int na = (p == 0) ? tot - k : tot;                     // columns of A = cbind(A, B, C) (R/predict.bvar.R:70-171)
+  const int use_a = (na > 0 && dev_coef != nullptr) ? 1 : 0;
+  if (na > 0 && !dev_coef) return fail(-1, "coefficient draws are missing");
+  if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  double* d_pred = nullptr;
+  const size_t pb = (size_t)tot * (n_ahead + 1) * sizeof(double);
+  CK(cudaMalloc((void**)&d_pred, pb));
+  cudaError_t e = cudaMemcpyAsync(d_pred, pred, pb, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    e = launch_forecast_draws(dev_coef, coef_stride, dev_sigma, sigma_stride, n_draws, k, p, tot, n_ahead, use_a, d_pred,
+                              dev_eps, seed, dev_out, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_pred);
+  if (e != cudaSuccess) return cuda_fail(e, "forecast kernel");
+  return 0;
+}
+
+int bvg_sampler_forecast(bvg_sampler* s, int32_t p, int32_t tot, int32_t n_ahead, const double* pred, const double* host_eps,
+                         uint64_t seed, const double* probs, int32_t n_probs, double* quantiles, double* mean,
+                         double* host_draws, void* cuda_stream) {
+  if (!s) return fail(-1, "sampler is NULL");
+  CK(cudaSetDevice(s->device));
+  const int k = s->P.k, T = s->P.T;
+  const bool tv_coef = s->P.tvp != 0, tv_sig = s->P.sigma_type == BVG_SIGMA_SV;
+  const long long nd = (long long)s->n_chains * s->P.iterations;
+  const double* coef = s->d_coef + (tv_coef ? (size_t)(T - 1) * s->P.n : 0);      // last period (R/predict.bvar.R:73,85,146)
+  const double* sig = s->d_sigma + (tv_sig ? (size_t)(T - 1) * k * k : 0);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const size_t ob = (size_t)nd * n_ahead * k * sizeof(double);
+  double *d_out = nullptr, *d_eps = nullptr;
+  CK(cudaMalloc((void**)&d_out, ob));
+  int rc = 0;
+  if (host_eps) {
+    cudaError_t e = cudaMalloc((void**)&d_eps, ob);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_eps, host_eps, ob, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "forecast eps upload");
+  }
+  if (rc == 0)
+    rc = bvg_forecast_draws(coef, s->rows_coef, sig, s->rows_sigma, nd, k, p, tot, n_ahead, pred, d_eps, seed, d_out,
+                            cuda_stream);
+  if (rc == 0 && (n_probs > 0 || mean))
+    rc = bvg_summary_draws(d_out, nd, (int64_t)n_ahead * k, probs, n_probs, mean, nullptr, quantiles, cuda_stream);
+  if (rc == 0 && host_draws) {
+    cudaError_t e = cudaMemcpyAsync(host_draws, d_out, ob, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "forecast copy");
+  }
+  cudaFree(d_out);
+  cudaFree(d_eps);
+  return rc;
+}
+
 int bvg_fp64_peak(double* tflops_fma, void* cuda_stream) {
   if (!tflops_fma) return fail(-1, "output pointer is NULL");
   if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");

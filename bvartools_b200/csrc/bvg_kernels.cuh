@@ -58,6 +58,9 @@ cudaError_t launch_irf_draws(const double* coef, long long coef_stride, const do
 cudaError_t launch_fevd_draws(const double* coef, long long coef_stride, const double* sigma, long long sigma_stride,
                               long long n_draws, int k, int p, int h, int type, int response, double* d_out,
                               cudaStream_t stream);
+cudaError_t launch_forecast_draws(const double* coef, long long coef_stride, const double* sigma, long long sigma_stride,
+                                  long long n_draws, int k, int p, int tot, int h, int use_a, const double* d_pred,
+                                  const double* d_eps, unsigned long long seed, double* d_out, cudaStream_t stream);
 cudaError_t launch_moments(const double* draws, long long chains, long long iters, long long rows, double* sums,
                            double* sumsq, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* tflops, cudaStream_t stream);

@@ -11,6 +11,7 @@
 // Output [draw][h + 1] (cumulated on request, R/irf.bvar.R:204-206) stays on the device; the bands come from the radix
 // select of bvg_summary.cu.  Structural types (sir, sgir) need A0 draws, which this sampler does not produce.
 #include "bvg_kernels.cuh"
+#include "bvg_blocks.cuh"
 
 namespace bvg {
 
@@ -241,6 +242,90 @@ cudaError_t launch_fevd_draws(const double* coef, long long coef_stride, const d
   e = cudaGetLastError();
   cudaFreeAsync(partial, stream);
   return e;
+}
+
+// ---- forecasts (predict.bvar, R/predict.bvar.R:36-260; .draw_forecast, src/draw_forecast.cpp:6-51) ------------------
+// Per draw: n_ahead simulated periods  y_{T+j+1} = A pred_j + u_j,  u_j = Sigma^{1/2} eps_j  with the SYMMETRIC square root
+// (eig_sym in the reference, :27-28; cyclic Jacobi here -- the root of a positive definite matrix is unique), the lag
+// block of pred shifted every period (:41-45).  pred is the reference's prediction matrix (rows: y lags | exogenous |
+// deterministic; column 0 = data at T, later columns = the future exogenous / deterministic values), shared by all draws.
+// One thread per draw, its matrices in a private slice of shared memory.  eps: injected [draw][n_ahead][k] or Philox.
+struct FcstDims {
+  long long n_draws, coef_stride, sigma_stride;
+  int k, p, tot, h, use_a;
+  unsigned long long seed;
+};
+static constexpr int VB_FORECAST = 40;            // variate block id of the forecast errors (site = draw, period, variable)
+
+__global__ void __launch_bounds__(128) forecast_draws_kernel(const __grid_constant__ FcstDims d, const double* __restrict__ coef,
+                                                             const double* __restrict__ sigma, const double* __restrict__ pred0,
+                                                             const double* __restrict__ eps, double* __restrict__ out) {
+  extern __shared__ double sm[];
+  const int k = d.k, p = d.p, tot = d.tot, h = d.h, kk = k * k;
+  const int per_thread = 3 * kk + tot + k;
+  double* Ae = sm + (size_t)threadIdx.x * per_thread;       // Sigma -> eigenvalues on the diagonal
+  double* V = Ae + kk;
+  double* Rt = V + kk;                                       // Sigma^{1/2}
+  double* col = Rt + kk;                                     // current column of pred
+  double* u = col + tot;
+  const SerialGroup g;
+  const int na = d.use_a ? ((p == 0) ? tot - k : tot) : 0;   // columns of A
+  for (long long dr = (long long)blockIdx.x * blockDim.x + threadIdx.x; dr < d.n_draws;
+       dr += (long long)gridDim.x * blockDim.x) {
+    const double* A = coef + dr * d.coef_stride;             // k x na column-major
+    const double* S = sigma + dr * d.sigma_stride;
+    for (int e = 0; e < kk; ++e) Ae[e] = S[e];
+    jacobi_eig_sym(g, Ae, V, k);
+    sym_func(g, Ae, V, Rt, k, 0);
+    for (int r = 0; r < tot; ++r) col[r] = pred0[r];         // column 0
+    double* o = out + dr * (size_t)h * k;
+    for (int j = 0; j < h; ++j) {
+      for (int i = 0; i < k; ++i) {
+        double s = 0.0;
+        for (int c = 0; c < k; ++c) {
+          const double e = (eps != nullptr) ? eps[(dr * h + j) * k + c]
+                                            : philox_normal(d.seed, (unsigned long long)dr, VB_FORECAST, j, c, 0);
+          s = fma(Rt[i + k * c], e, s);
+        }
+        u[i] = s;
+      }
+      // y_next = A x + u   (x = whole column, or its rows k.. when p = 0; plain random walk without coefficients)
+      for (int i = 0; i < k; ++i) {
+        double s = u[i];
+        if (d.use_a) { for (int c = 0; c < na; ++c) s = fma(A[i + k * c], col[(p == 0 ? k : 0) + c], s); }
+        else s += col[i];
+        o[(size_t)j * k + i] = s;
+      }
+      // next column: new y on top, lags shifted down, exogenous / deterministic rows from pred
+      for (int l = p - 1; l >= 1; --l)
+        for (int i = 0; i < k; ++i) col[l * k + i] = col[(l - 1) * k + i];
+      for (int i = 0; i < k; ++i) col[i] = o[(size_t)j * k + i];
+      const int ylen = (p > 0) ? k * p : k;
+      for (int r = ylen; r < tot; ++r) col[r] = pred0[(size_t)(j + 1) * tot + r];
+    }
+  }
+}
+
+cudaError_t launch_forecast_draws(const double* coef, long long coef_stride, const double* sigma, long long sigma_stride,
+                                  long long n_draws, int k, int p, int tot, int h, int use_a, const double* d_pred,
+                                  const double* d_eps, unsigned long long seed, double* d_out, cudaStream_t stream) {
+  if (k < 1 || k > IRF_KMAX || p < 0 || h < 1 || tot < k || n_draws < 1 || ((p > 0) && tot < k * p)) return cudaErrorInvalidValue;
+  FcstDims d;
+  d.n_draws = n_draws; d.coef_stride = coef_stride; d.sigma_stride = sigma_stride;
+  d.k = k; d.p = p; d.tot = tot; d.h = h; d.use_a = use_a; d.seed = seed;
+  int threads = 128;
+  auto bytes = [&](int t) { return (size_t)t * (3 * k * k + tot + k) * 8; };
+  while (bytes(threads) > 96 * 1024 && threads > 32) threads >>= 1;
+  if (bytes(threads) > 200 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(forecast_draws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(threads));
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long want = (n_draws + threads - 1) / threads;
+  int grid = (int)((want < (long long)sms * 8) ? want : (long long)sms * 8);
+  forecast_draws_kernel<<<grid, threads, bytes(threads), stream>>>(d, coef, sigma, d_pred, d_eps, d_out);
+  return cudaGetLastError();
 }
 
 }  // namespace bvg

@@ -64,6 +64,7 @@ class ChainSampler:
         self.spec = _abi.spec_from_model(obj, n_chains=n_chains, seed=_seed(seed), chain_offset=chain_offset,
                                          device=device, inject=inject, **tuning)
         self.lags = int(obj.get("model", {}).get("endogen", {}).get("lags", 0))     # p: A = first k*k*p coefficients
+        self._obj = obj
         self.handle = C.c_void_p()
         check(lib().bvg_sampler_create(C.byref(self.spec.c), C.byref(self.handle)))
 
@@ -184,6 +185,54 @@ class ChainSampler:
                                      int(response), int(bool(normalise_gir)), -1 if period is None else int(period),
                                      out.ctypes.data_as(C.POINTER(C.c_double)), C.c_void_p(stream or 0)))
         return out
+
+    def predict(self, n_ahead=10, new_x=None, new_d=None, ci=0.95, seed=None, eps=None, keep_draws=False, stream=0):
+        """Forecasts from ALL retained draws resident on the device (predict.bvar, R/predict.bvar.R:36-260).  The
+        prediction matrix is set up as in the reference (:176-201): last p observations of y, `new_x` (n_ahead x m)
+        for exogenous regressors, `new_d` (n_ahead x n) for deterministic terms -- zeros when omitted, exactly like the
+        reference (pass ones to keep an intercept).  Returns {variable index: (n_ahead x 3) bands (ci_low, median,
+        ci_high)} or the draws [draws][n_ahead][k] with keep_draws.  `eps`: injected N(0,1) of that shape (tests)."""
+        Y, Z = np.asarray(self._obj["data"]["Y"]), np.asarray(self._obj["data"]["Z"])
+        tt, k = Y.shape
+        p = self.lags
+        n_x = Z.shape[1] - k * p                            # exogenous + deterministic regressors
+        n_det = 0 if new_d is None and new_x is not None else n_x
+        if new_x is not None:
+            new_x = np.atleast_2d(np.asarray(new_x, dtype=np.float64))
+            n_det = n_x - new_x.shape[1]
+        tot = (k * p if p > 0 else k) + n_x
+        pred = np.zeros((tot, n_ahead + 1))
+        ylen = k * p if p > 0 else k
+        pred[:ylen, 0] = (Y[tt - 1::-1][:p].reshape(-1) if p > 0 else Y[tt - 1])     # t(y[tt:(tt - p + 1), ])
+        if n_x > 0:
+            pred[ylen:, 0] = Z[tt - 1, k * p:]                                       # latest observation of x / d
+            fut = np.zeros((n_ahead, n_x))
+            if new_x is not None:
+                if new_x.shape[0] < n_ahead:
+                    raise ValueError("Longer time series required for argument 'new_x'.")
+                fut[:, :new_x.shape[1]] = new_x[:n_ahead]
+            if new_d is not None:
+                new_d = np.asarray(new_d, dtype=np.float64).reshape(-1, n_det)
+                if new_d.shape[0] != n_ahead:
+                    raise ValueError("Length of argument 'new_d' must be equal to 'n.ahead'.")
+                fut[:, n_x - n_det:] = new_d
+            pred[ylen:, 1:] = fut.T
+        predf = np.ascontiguousarray(pred.reshape(-1, order="F"))
+        lo = (1.0 - ci) / 2.0
+        probs = np.ascontiguousarray([lo, 0.5, 1.0 - lo])
+        n = int(self.spec.c.n_chains) * int(self.spec.c.iterations)
+        q = np.empty((3, n_ahead * k))
+        draws = np.empty((n, n_ahead, k)) if keep_draws else None
+        dp = C.POINTER(C.c_double)
+        epsc = None if eps is None else np.ascontiguousarray(eps, dtype=np.float64)
+        check(lib().bvg_sampler_forecast(self.handle, p, tot, int(n_ahead), predf.ctypes.data_as(dp),
+                                         None if epsc is None else epsc.ctypes.data_as(dp), _seed(seed), probs.ctypes.data_as(dp),
+                                         0 if keep_draws else 3, q.ctypes.data_as(dp), None,
+                                         None if draws is None else draws.ctypes.data_as(dp), C.c_void_p(stream or 0)))
+        if keep_draws:
+            return draws
+        q = q.reshape(3, n_ahead, k)
+        return {i: q[:, :, i].T for i in range(k)}
 
     def close(self):
         if self.handle:

@@ -244,6 +244,24 @@ int bvg_fevd_draws(const double* dev_coef, int64_t coef_stride, const double* de
 int bvg_sampler_fevd(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, int32_t response, int32_t normalise_gir,
                      int32_t period, double* host_out, void* cuda_stream);
 
+/* ---- forecasts per draw -----------------------------------------------------------------------------
+ * Replaces the per-draw loop of predict.bvar (R/predict.bvar.R:203-217) around .draw_forecast
+ * (src/draw_forecast.cpp:6-51): y_{T+j+1} = A pred_j + Sigma^{1/2} eps_j with the symmetric square root, lags shifted.
+ * pred: the reference's prediction matrix, tot x (n_ahead + 1) column-major on the HOST (rows: k*p lags of y | exogenous
+ * | deterministic; column 0 = data at T, later columns = future exogenous / deterministic values, :176-201).  The first
+ * k * (tot, or tot - k when p = 0) doubles of a coefficient draw are A = cbind(A, B, C), column-major.  dev_eps: injected
+ * N(0,1) [n_draws][n_ahead][k] on the device, or NULL = Philox4x32-10 keyed (seed; draw, period, variable).
+ * dev_out: [n_draws][n_ahead][k] on the device. */
+int bvg_forecast_draws(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
+                       int64_t n_draws, int32_t k, int32_t p, int32_t tot, int32_t n_ahead, const double* pred,
+                       const double* dev_eps, uint64_t seed, double* dev_out, void* cuda_stream);
+/* on the retained draws of a sampler (TVP / SV: the last period) + the bands of predict.bvar (:219-221): quantiles
+ * [n_probs][n_ahead * k] (entry j * k + i = horizon j + 1, variable i), mean, host_draws [draws][n_ahead][k] (may be NULL),
+ * host_eps injected normals on the HOST (may be NULL) */
+int bvg_sampler_forecast(bvg_sampler* s, int32_t p, int32_t tot, int32_t n_ahead, const double* pred, const double* host_eps,
+                         uint64_t seed, const double* probs, int32_t n_probs, double* quantiles, double* mean,
+                         double* host_draws, void* cuda_stream);
+
 /* measured FP64 FMA throughput of the device (TFLOP/s) -- roofline denominator for the sweep kernels */
 int bvg_fp64_peak(double* tflops_fma, void* cuda_stream);
 /* measured FP64 tensor-core (DMMA m8n8k4) throughput (TFLOP/s) -- denominator for the large-VAR Cholesky */

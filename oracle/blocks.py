@@ -400,3 +400,26 @@ def fevd_bvar(A_draws, Sigma_draws, k, response, n_ahead=5, type="oir", normalis
         result = result / result.sum(axis=1, keepdims=True)
     return result
 
+
+def draw_forecast(a, sigma, pred, k, p, eps):
+    """src/draw_forecast.cpp:6-51 for one draw, literally (non-structural: a0_i = I): a = k x n_tot coefficient matrix or
+    None, sigma k x k, pred tot x (n_ahead + 1), eps (n_ahead x k) the injected arma::randn(k) of each period."""
+    pred = np.array(pred, dtype=float)
+    n_ahead = pred.shape[1] - 1
+    use_a = a is not None
+    n_tot = a.shape[1] if use_a else 0
+    for j in range(n_ahead):
+        eigval, eigvec = np.linalg.eigh(np.asarray(sigma, dtype=float))
+        u = eigvec @ np.diag(np.sqrt(eigval)) @ eigvec.T @ eps[j]
+        if use_a:
+            if p == 0:
+                pred[:k, j + 1] = a @ pred[k:k + n_tot, j] + u
+            else:
+                pred[:k, j + 1] = a @ pred[:, j] + u
+        else:
+            pred[:k, j + 1] = pred[:, j] + u
+        if p > 1:
+            for l in range(p - 1):
+                pred[(l + 1) * k:(l + 2) * k, j + 1] = pred[l * k:(l + 1) * k, j]
+    return pred
+
