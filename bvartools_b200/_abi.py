@@ -21,7 +21,7 @@ _ip = C.POINTER(C.c_int32)
 
 INJECT_FIELDS = ["coef_normal", "ssvs_u", "bvs_u1", "bvs_u2", "sv_u", "sv_normal", "sigma_h_gamma",
                  "h_init_normal", "omega_gamma", "wishart_chi2", "wishart_normal", "state_normal",
-                 "sigma_v_gamma", "a_init_normal"]
+                 "sigma_v_gamma", "a_init_normal", "psi_normal"]
 
 
 class BvgInject(C.Structure):
@@ -40,7 +40,7 @@ class BvgSpec(C.Structure):
         ("sigma_type", C.c_int32), ("wishart_df", C.c_double), ("wishart_scale", _dp),
         ("sigma_shape", _dp), ("sigma_rate", _dp), ("sv_mu", _dp), ("sv_vi", _dp), ("sv_sigma_h", _dp),
         ("sv_constant", _dp), ("sv_h", _dp), ("sv_mixture", C.c_int32), ("sigma_i", _dp),
-        ("tvp_shape", _dp), ("tvp_rate", _dp), ("a_init", _dp),
+        ("tvp_shape", _dp), ("tvp_rate", _dp), ("a_init", _dp), ("psi_mu", _dp), ("psi_vi", _dp),
         ("resid_mode", C.c_int32), ("threads_per_chain", C.c_int32), ("sweeps_per_launch", C.c_int32),
         ("inject", C.POINTER(BvgInject)),
     ]
@@ -100,8 +100,9 @@ def spec_from_model(obj, n_chains=1, seed=0, chain_offset=0, device=-1, resid_mo
     data, model, priors, initial = obj["data"], obj["model"], obj["priors"], obj["initial"]
     if model.get("structural"):
         raise NotImplementedError("structural models are not on the accelerated path (SURVEY.md section 8f-4)")
-    if "psi" in priors:
-        raise NotImplementedError("the covariance (psi) block is not on the accelerated path (SURVEY.md 8f-4)")
+    if "psi" in priors and (model.get("tvp") or any(key in priors["psi"] for key in ("ssvs", "bvs"))):
+        raise NotImplementedError("covariance (psi) block: TVP models and variable selection on psi are not on the "
+                                  "accelerated path (SURVEY.md 8f-4)")
     Y = np.asarray(data["Y"], dtype=np.float64)          # T x k
     T, k = Y.shape
     Z = data.get("Z")
@@ -170,6 +171,9 @@ def spec_from_model(obj, n_chains=1, seed=0, chain_offset=0, device=-1, resid_mo
             c.sigma_type = SIGMA_GAMMA
             sp.set("sigma_shape", _f(ps["shape"]))
             sp.set("sigma_rate", _f(ps["rate"]))
+    if "psi" in priors:                                   # covariance block (bvaralg.cpp:157-162)
+        sp.set("psi_mu", _f(priors["psi"]["mu"]))
+        sp.set("psi_vi", _f(np.asarray(priors["psi"]["v_i"], dtype=np.float64)))
     c.resid_mode, c.threads_per_chain, c.sweeps_per_launch = resid_mode, threads_per_chain, sweeps_per_launch
     if inject:
         st = BvgInject()

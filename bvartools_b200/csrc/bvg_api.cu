@@ -212,8 +212,9 @@ int bvg_sampler_create(const bvg_spec* spec, bvg_sampler** out) {
                                    spec->inject->sigma_h_gamma, spec->inject->h_init_normal,
                                    spec->inject->omega_gamma, spec->inject->wishart_chi2,
                                    spec->inject->wishart_normal, spec->inject->state_normal,
-                                   spec->inject->sigma_v_gamma, spec->inject->a_init_normal};
-    const int cnt[VB_COUNT] = {n, n, n, n, k * T, k * T, k, k, k, k, k * (k - 1) / 2, n * T, n, n};
+                                   spec->inject->sigma_v_gamma, spec->inject->a_init_normal,
+                                   spec->inject->psi_normal};
+    const int cnt[VB_COUNT] = {n, n, n, n, k * T, k * T, k, k, k, k, k * (k - 1) / 2, n * T, n, n, k * (k - 1) / 2};
     for (int b = 0; b < VB_COUNT; ++b) {
       if (!ptr[b] || cnt[b] == 0) continue;
       const size_t bytes = (size_t)s->n_chains * s->sweeps * cnt[b] * sizeof(double);

@@ -59,6 +59,10 @@ struct BvarModel {
   const double* sv_const;          // k   offset constant c                          (bvaralg.cpp:229)
   const double* mix_p; const double* mix_mu; const double* mix_s2;   // n_mix each
   const double* omega_off;         // k x k off-diagonal part of the initial Sigma^-1 (gamma prior), zero diagonal
+  // covariance (psi) block (bvaralg.cpp:373-455); n_psi = 0: none
+  int n_psi;                       // k (k - 1) / 2
+  const double* psi_vi;            // n_psi x n_psi prior precision (col-major)
+  const double* psi_vmu;           // n_psi  prior precision times prior mean
   // flat-prior Kronecker specialisation (bvg_kron_sweep.cuh); nullptr when the model does not qualify
   const double* kron_Linv;         // tri(M) packed lower: inverse of the lower Cholesky factor of X X'
   const double* kron_SS;           // k x k  S0 + SSE_ols
@@ -83,17 +87,19 @@ BVG_HD BvarConsts bvar_consts_of(const BvarModel& m) {
 //   then n              vdiag   (diagonal of V^-1, changed by SSVS)
 //   then n              lambda  (0/1)
 //   SV only: then T*k   h (col-major T x k: h_ti at t + T i), then k sigma_h, then k h_init
-BVG_HD int bvar_state_len(int k, int T, int n, int sigma_type) {
-  return k * k + 2 * n + (sigma_type == SIG_SV ? T * k + 2 * k : 0);
+//   covariance block only: then k  diagonal of Omega^-1 (gamma prior), then n_psi  psi (strict lower triangle of Psi by rows)
+BVG_HD int bvar_state_len(int k, int T, int n, int sigma_type, int n_psi = 0) {
+  return k * k + 2 * n + (sigma_type == SIG_SV ? T * k + 2 * k : 0) + (n_psi > 0 ? k + n_psi : 0);
 }
 
 // Shared-memory doubles needed per chain.
-BVG_HD int bvar_smem_len(int k, int T, int M, int n, int sigma_type, int resid_mode, bool tiled = false) {
+BVG_HD int bvar_smem_len(int k, int T, int M, int n, int sigma_type, int resid_mode, bool tiled = false, int n_psi = 0) {
   int len = (tiled ? tiled_len(n) + 8 - n : tri(n)) + 5 * n   // L, w (padded when tiled), a, dinv (not tiled), vdiag, lam
             + 6 * k * k + 2 * k      // sig, S, 4 k x k work, kd, kv
             + 2 * k * M;             // Dm, Wm
   if (resid_mode == RES_DIRECT || sigma_type == SIG_SV) len += k * T;                 // U
   if (sigma_type == SIG_SV) len += 3 * k * T + k * tri(M) + 2 * k;                    // h, ew, sv work, GW, sigma_h, h_init
+  if (n_psi > 0) len += tri(n_psi) + 3 * n_psi + k + k * k;                           // psi system, rhs, psi, dinv, omega diag, Psi
   return len;
 }
 
@@ -416,7 +422,7 @@ BVG_HD void sv_step(const Grp& g, const ChainRng& rng, int sweep, const BvarMode
 // padding rows included.  GW != nullptr: SV form (block-diagonal weights), else XX' (x) Sigma^-1.   (bvaralg.cpp:303-305)
 __device__ __forceinline__ void tiled_build_precision(double* L, int n, int k, int M, const double* XX, const double* sig,
                                                       const double* GW, const double* vdiag, const double* lam_bvs,
-                                                      const double* vi_off) {
+                                                      const double* vi_off, const double* PsiM = nullptr) {
   const int nt = tiled_nt(n), lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int li = lane & 7, lj = lane >> 3;
   const float kinv = 1.0f / (float)k;
@@ -434,7 +440,9 @@ __device__ __forceinline__ void tiled_build_precision(double* L, int n, int k, i
         if (r >= n) gv = (c == r) ? 1.0 : 0.0;
         else if (c <= r) {
           const int jc = (int)(((float)c + 0.5f) * kinv), ic = c - jc * k;
-          if (GW != nullptr) gv = (ir == ic) ? GW[ir * triM + tri(jr) + jc] : 0.0;
+          if (GW != nullptr && PsiM != nullptr) {                     // SV with the covariance block: Psi' Omega_t^-1 Psi
+            for (int q = (ir > ic ? ir : ic); q < k; ++q) gv = fma(GW[q * triM + tri(jr) + jc], PsiM[q + k * ir] * PsiM[q + k * ic], gv);
+          } else if (GW != nullptr) gv = (ir == ic) ? GW[ir * triM + tri(jr) + jc] : 0.0;
           else gv = XX[jr + M * jc] * sig[ir + k * ic];
           if (lam_bvs != nullptr) gv *= lr * lam_bvs[c];
           if (vi_off != nullptr) gv += vi_off[tri(r) + c];
@@ -486,6 +494,15 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
     h = sm; sm += k * T;  ew = sm; sm += k * T;  svw = sm; sm += k * T;  GW = sm; sm += k * tri(M);
     sigma_h = sm; sm += k;  h_init = sm; sm += k;
   }
+  // covariance (psi) block (bvaralg.cpp:373-455): only compiled into the variants that know gamma / SV variances
+  const int npsi = (FEAT & (F_GAMMA | F_SV)) ? m.n_psi : 0;
+  const bool covar = npsi > 0;
+  double* pL = nullptr; double* prhs = nullptr; double* psi = nullptr; double* pdinv = nullptr; double* omd = nullptr;
+  double* PsiM = nullptr;
+  if (covar) {
+    pL = sm; sm += tri(npsi);  prhs = sm; sm += npsi;  psi = sm; sm += npsi;  pdinv = sm; sm += npsi;
+    omd = sm; sm += k;  PsiM = sm; sm += kk;
+  }
   int fail = 0;
 
   // load state
@@ -498,6 +515,16 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
   if (sv) {
     for (int e = tid; e < T * k; e += G) h[e] = st_h[e];
     for (int e = tid; e < k; e += G) { sigma_h[e] = st_h[T * k + e]; h_init[e] = st_h[T * k + k + e]; }
+  }
+  double* st_tail = state + bvar_state_len(k, T, n, m.sigma_type);       // [omega diagonal (k) | psi (npsi)]
+  if (covar) {
+    for (int e = tid; e < k; e += G) omd[e] = st_tail[e];
+    for (int e = tid; e < npsi; e += G) psi[e] = st_tail[k + e];
+    g.sync();
+    for (int e = tid; e < kk; e += G) {                                  // Psi: unit lower, row i holds psi[tri(i-1) ..]
+      const int i = e % k, a = e / k;
+      PsiM[e] = (i == a) ? 1.0 : ((a < i) ? psi[(i * (i - 1)) / 2 + a] : 0.0);
+    }
   }
   g.sync();
 
@@ -537,7 +564,20 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
         for (int r = tid; r < n; r += G) {
           const int j = r / k, i = r % k;
           double s = 0.0;
-          for (int t = 0; t < T; ++t) s = fma(m.X[j + M * t] * ew[t + T * i], m.Y[i + k * t], s);
+          if (covar) {
+            // Sigma_t^-1 = Psi' Omega_t^-1 Psi:  (Sigma_t^-1 y_t)_i = sum_{q >= i} Psi_qi w_tq (Psi y_t)_q   (:495-497)
+            for (int t = 0; t < T; ++t) {
+              double v = 0.0;
+              for (int q = i; q < k; ++q) {
+                double py = 0.0;
+                for (int b = 0; b <= q; ++b) py = fma(PsiM[q + k * b], m.Y[b + k * t], py);
+                v = fma(PsiM[q + k * i] * ew[t + T * q], py, v);
+              }
+              s = fma(m.X[j + M * t], v, s);
+            }
+          } else {
+            for (int t = 0; t < T; ++t) s = fma(m.X[j + M * t] * ew[t + T * i], m.Y[i + k * t], s);
+          }
           w[r] = s;
         }
         g.sync();
@@ -560,7 +600,7 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
           }
           w[r] = b;
         }
-        tiled_build_precision(L, n, k, M, cs.XX, sig, sv ? GW : nullptr, vdiag, bvs ? lam : nullptr, vi_off);
+        tiled_build_precision(L, n, k, M, cs.XX, sig, sv ? GW : nullptr, vdiag, bvs ? lam : nullptr, vi_off, (sv && covar) ? PsiM : nullptr);
       } else
 #endif
       {
@@ -572,7 +612,10 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
           if (sv) {
             int j2 = 0, i2 = 0;
             for (int c = 0; c <= r; ++c) {
-              double gv = (i == i2) ? GW[i * tri(M) + tri(j) + j2] : 0.0;
+              double gv = 0.0;
+              if (covar) {   // sum_q GW_q[j, j2] Psi_qi Psi_qi2
+                for (int q = (i > i2 ? i : i2); q < k; ++q) gv = fma(GW[q * tri(M) + tri(j) + j2], PsiM[q + k * i] * PsiM[q + k * i2], gv);
+              } else if (i == i2) gv = GW[i * tri(M) + tri(j) + j2];
               if (bvs) gv *= lr * lam[c];
               if (vi_off != nullptr) gv += vi_off[tri(r) + c];
               if (c == r) gv += vdiag[r];
@@ -729,6 +772,57 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
       }
     }
 
+    // ---- covariance (psi) block (bvaralg.cpp:373-455) ----------------------------------------------------------
+    // Row i of U regressed on -U[0:i]: the posterior precision is V_psi^-1 + blockdiag_i(sum_t w_ti u_{0:i,t} u_{0:i,t}'),
+    // w_ti the Omega^-1 diagonal of the PREVIOUS sweep (:384).  Then U <- Psi U (:454).
+    if (covar) {
+      for (int e = tid; e < tri(npsi); e += G) {
+        int r = 0; while (tri(r + 1) <= e) ++r;
+        const int c = e - tri(r);
+        int i = 1; while ((i * (i + 1)) / 2 <= r) ++i;                // psi index r = i (i - 1) / 2 + a  ->  row i, column a
+        const int a = r - (i * (i - 1)) / 2;
+        int i2 = 1; while ((i2 * (i2 + 1)) / 2 <= c) ++i2;
+        const int b = c - (i2 * (i2 - 1)) / 2;
+        double v = m.psi_vi[r + (size_t)npsi * c];
+        if (i == i2) {
+          double s = 0.0;
+          for (int t = 0; t < T; ++t) {
+            const double wt = sv ? ew[t + T * i] : omd[i];
+            s = fma(U[a + k * t] * wt, U[b + k * t], s);
+          }
+          v += s;
+        }
+        pL[e] = v;
+      }
+      for (int r = tid; r < npsi; r += G) {
+        int i = 1; while ((i * (i + 1)) / 2 <= r) ++i;
+        const int a = r - (i * (i - 1)) / 2;
+        double s = 0.0;
+        for (int t = 0; t < T; ++t) {
+          const double wt = sv ? ew[t + T * i] : omd[i];
+          s = fma(-U[a + k * t] * wt, U[i + k * t], s);
+        }
+        prhs[r] = m.psi_vmu[r] + s;                                                       // :393
+      }
+      g.sync();
+      chol_crout_generic(g, pL, pdinv, prhs, npsi, fail);
+      for (int r = tid; r < npsi; r += G) prhs[r] += rng.normal(VB_PSI_N, sweep, r);      // :394
+      g.sync();
+      back_solve_lt_generic(g, pL, pdinv, prhs, psi, npsi);
+      for (int e = tid; e < kk; e += G) {
+        const int i = e % k, a = e / k;
+        PsiM[e] = (i == a) ? 1.0 : ((a < i) ? psi[(i * (i - 1)) / 2 + a] : 0.0);        // :451-453
+      }
+      g.sync();
+      for (int t = tid; t < T; t += G)                                                    // u = Psi u, :454
+        for (int i = k - 1; i >= 1; --i) {
+          double s = U[i + k * t];
+          for (int a = 0; a < i; ++a) s = fma(PsiM[i + k * a], U[a + k * t], s);
+          U[i + k * t] = s;
+        }
+      g.sync();
+    }
+
     // ---- error variances ---------------------------------------------------------------------------------
     double* out_sig = nullptr;
     if (keep) out_sig = out.sigma + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)(sv ? kk * T : kk);
@@ -765,6 +859,22 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
       back_solve_lt_generic(g, W1, kd, W4, h_init, k);
       if (keep) {
         // Sigma_t = diag(exp(h_t)) (solve of the diagonal block, :523-525); sigma_h (:526)
+        if (covar) {
+          // Sigma_t = (Psi' Omega_t^-1 Psi)^-1 = Pi diag(exp(h_t)) Pi',  Pi = Psi^-1 (unit lower), :495-497,523-525
+          for (int c = tid; c < k; c += G)
+            for (int i = 0; i < k; ++i) {
+              double s = (i == c) ? 1.0 : 0.0;
+              if (i > c) { s = 0.0; for (int a = c; a < i; ++a) s = fma(-PsiM[i + k * a], W1[a + k * c], s); }
+              W1[i + k * c] = (i >= c) ? s : 0.0;
+            }
+          g.sync();
+          for (int e = tid; e < kk * T; e += G) {
+            const int t = e / kk, f = e % kk, i = f % k, j = f / k;
+            double s = 0.0;
+            for (int q = 0; q <= (i < j ? i : j); ++q) s = fma(W1[i + k * q] * (1.0 / (1.0 / exp(h[t + T * q]))), W1[j + k * q], s);
+            out_sig[e] = s;
+          }
+        } else
         for (int e = tid; e < kk * T; e += G) {
           const int t = e / kk, f = e % kk, i = f % k, j = f / k;
           out_sig[e] = (i == j) ? 1.0 / (1.0 / exp(h[t + T * i])) : 0.0;
@@ -798,6 +908,22 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
           sig[e] = (i == j) ? kv[i] : m.omega_off[e];                                     // :507
         }
         g.sync();
+        if (covar) {                                                                      // :504-505
+          for (int i = tid; i < k; i += G) omd[i] = kv[i];
+          for (int e = tid; e < kk; e += G) W1[e] = sig[e];                               // omega_i
+          g.sync();
+          for (int e = tid; e < kk; e += G) {                                             // sigma_i = Psi' omega_i Psi
+            const int a = e % k, b = e / k;
+            double s = 0.0;
+            for (int i = a; i < k; ++i) {
+              double v = 0.0;
+              for (int i2 = b; i2 < k; ++i2) v = fma(W1[i + k * i2], PsiM[i2 + k * b], v);
+              s = fma(PsiM[i + k * a], v, s);
+            }
+            sig[e] = s;
+          }
+          g.sync();
+        }
         if (keep) {
 #if defined(__CUDA_ARCH__)
           if constexpr (Grp::kIsBlock) {
@@ -876,6 +1002,10 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
   if (sv) {
     for (int e = tid; e < T * k; e += G) st_h[e] = h[e];
     for (int e = tid; e < k; e += G) { st_h[T * k + e] = sigma_h[e]; st_h[T * k + k + e] = h_init[e]; }
+  }
+  if (covar) {
+    for (int e = tid; e < k; e += G) st_tail[e] = omd[e];
+    for (int e = tid; e < npsi; e += G) st_tail[k + e] = psi[e];
   }
   if (fail && tid == 0) out.status[chain_local] = 1;
   g.sync();

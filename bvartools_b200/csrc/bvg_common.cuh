@@ -40,7 +40,8 @@ enum VarBlock : int {
   VB_STATE_N = 11, // N(0,1) x n*T         TVP state path                   bvartvpalg.cpp:297
   VB_SIGV_G = 12,  // Gamma(shape,1) x n   TVP state precisions             bvartvpalg.cpp:476
   VB_AINIT_N = 13, // N(0,1) x n           TVP initial state                bvartvpalg.cpp:482
-  VB_COUNT = 14
+  VB_PSI_N = 14,   // N(0,1) x k(k-1)/2    covariance (psi) block           bvaralg.cpp:394
+  VB_COUNT = 15
 };
 
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based: no state, any site can be drawn by any thread ------

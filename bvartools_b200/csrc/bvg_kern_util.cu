@@ -38,13 +38,13 @@ static cudaError_t finish_plan(LaunchPlan* plan, int per_chain_doubles, long lon
 cudaError_t plan_bvar(const BvarModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan) {
   plan->kron = 0;
   if (m.kron_Linv != nullptr) return plan_bvar_kron(m, n_chains, requested_tpc, plan);
-  int per = bvar_smem_len(m.k, m.T, m.M, m.n, m.sigma_type, m.resid_mode);
+  int per = bvar_smem_len(m.k, m.T, m.M, m.n, m.sigma_type, m.resid_mode, false, m.n_psi);
   int tpc = requested_tpc;
   if (tpc <= 0) {
     if ((size_t)per * 8 > 24 * 1024 || m.n > 64) tpc = (m.n > 96) ? 256 : 128;   // one CTA per chain (n = 150: two CTAs per SM)
     else tpc = pick_tile(m.n > m.k ? m.n : m.k);
   }
-  if (tpc > 32) per = bvar_smem_len(m.k, m.T, m.M, m.n, m.sigma_type, m.resid_mode, true);   // tile-packed factor
+  if (tpc > 32) per = bvar_smem_len(m.k, m.T, m.M, m.n, m.sigma_type, m.resid_mode, true, m.n_psi);   // tile-packed factor
   return finish_plan(plan, per, n_chains, tpc, bvar_consts_len(m.k, m.M, tpc > 32));
 }
 

@@ -28,6 +28,8 @@ struct Prepared {
        tau0 = -1, tau1 = -1, inprior = -1, S0 = -1, gshape = -1, grate = -1, svmu = -1, svvi = -1, svconst = -1,
        mixp = -1, mixmu = -1, mixs2 = -1, omega_off = -1, vshape = -1, vrate = -1, kLinv = -1, kSS = -1;
   int kron = 0;   // 1 = flat-prior Kronecker sweep (bvg_kron_sweep.cuh)
+  int n_psi = 0;  // k (k - 1) / 2 when the covariance (psi) block is active, else 0
+  long psi_mu = -1, psi_vi = -1, psi_vmu = -1;
   std::string error;
 
   long push(const double* p, size_t cnt) {
@@ -181,8 +183,30 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
     }
   }
 
+  // ---- covariance (psi) block (bvaralg.cpp:157-204): prior mean / precision of the k (k - 1) / 2 free elements
+  if (s->psi_mu != nullptr || s->psi_vi != nullptr) {
+    if (!s->psi_mu || !s->psi_vi) BVG_FAIL(-4, "priors$psi needs both mu and v_i");
+    if (P.tvp) BVG_FAIL(-5, "the covariance (psi) block of TVP models is not supported");
+    if (P.sigma_type == BVG_SIGMA_WISHART) BVG_FAIL(-5, "the covariance (psi) block needs a gamma or SV error prior");
+    if (k < 2) BVG_FAIL(-5, "the covariance (psi) block needs at least two endogenous variables");
+    if (P.sigma_type == BVG_SIGMA_SV && P.varsel == BVG_VARSEL_BVS)
+      BVG_FAIL(-5, "BVS on the coefficients together with SV and the covariance (psi) block is not supported");
+    P.n_psi = k * (k - 1) / 2;
+    if (has_nan(s->psi_mu, P.n_psi) || has_nan(s->psi_vi, (size_t)P.n_psi * P.n_psi)) BVG_FAIL(-6, "priors$psi contains NAs.");
+    P.psi_mu = P.push(s->psi_mu, P.n_psi);
+    P.psi_vi = P.push(s->psi_vi, (size_t)P.n_psi * P.n_psi);
+    std::vector<double> vm((size_t)P.n_psi, 0.0);                                  // psi_prior_vi * psi_prior_mu, :393
+    for (int r = 0; r < P.n_psi; ++r)
+      for (int c = 0; c < P.n_psi; ++c) vm[r] += s->psi_vi[r + (size_t)P.n_psi * c] * s->psi_mu[c];
+    P.psi_vmu = P.push(vm);
+  }
+
   // ---- residual mode and cross moments
   int rm = s->resid_mode;
+  if (P.n_psi > 0) {
+    if (rm == BVG_RESID_MOMENT) BVG_FAIL(-5, "the covariance (psi) block needs the residuals themselves (direct mode)");
+    rm = BVG_RESID_DIRECT;
+  }
   if (rm != BVG_RESID_AUTO && rm != BVG_RESID_DIRECT && rm != BVG_RESID_MOMENT) BVG_FAIL(-5, "invalid resid_mode");
   if (P.tvp || P.sigma_type == BVG_SIGMA_SV || n == 0) {
     if (rm == BVG_RESID_MOMENT) BVG_FAIL(-5, "moment residual mode needs a constant-parameter, constant-variance VAR");
@@ -301,11 +325,15 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
       for (int i = 0; i < k; ++i) { sh[T * k + i] = s->sv_sigma_h[i]; sh[T * k + k + i] = s->sv_h[0 + (size_t)T * i]; }
     }
   } else {
-    P.state_len = bvar_state_len(k, T, n, P.sigma_type);
+    P.state_len = bvar_state_len(k, T, n, P.sigma_type, P.n_psi);
     P.state0.assign(P.state_len, 0.0);
     double* st = P.state0.data();
     for (int e = 0; e < kk; ++e) st[e] = sig0[e];
     for (int r = 0; r < n; ++r) { st[kk + r] = P.blob[P.vdiag0 + r]; st[kk + n + r] = 1.0; }
+    if (P.n_psi > 0) {   // tail of the state: diagonal of Omega^-1 (gamma prior), then psi = 0 (Psi = I, bvaralg.cpp:187)
+      double* tail = st + P.state_len - (k + P.n_psi);
+      for (int i = 0; i < k; ++i) tail[i] = sig0[i + (size_t)k * i];
+    }
     if (P.kron)   // the Kronecker sweep keeps B^-1 = chol(Sigma^-1)^-1 (upper) in the Sigma^-1 slot; the initial Sigma^-1 is diagonal
       for (int i = 0; i < k; ++i) st[i + (size_t)k * i] = 1.0 / sqrt(sig0[i + (size_t)k * i]);
     if (P.sigma_type == BVG_SIGMA_SV) {
@@ -332,6 +360,7 @@ static inline void bind_bvar(const Prepared& P, const double* base, const unsign
   m->sv_mu = at(base, P.svmu); m->sv_vi = at(base, P.svvi); m->sv_const = at(base, P.svconst);
   m->mix_p = at(base, P.mixp); m->mix_mu = at(base, P.mixmu); m->mix_s2 = at(base, P.mixs2);
   m->omega_off = at(base, P.omega_off);
+  m->n_psi = P.n_psi; m->psi_vi = at(base, P.psi_vi); m->psi_vmu = at(base, P.psi_vmu);
   m->kron_Linv = P.kron ? at(base, P.kLinv) : nullptr;
   m->kron_SS = P.kron ? at(base, P.kSS) : nullptr;
 }

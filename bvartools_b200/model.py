@@ -306,8 +306,8 @@ def add_priors(obj, coef=None, sigma=None, ssvs=None, bvs=None):
     """Attach priors and initial values (R/add_priors.bvarmodel.R:160-621).
 
     Restated branches: regular / Minnesota / SSVS / BVS coefficient priors, TVP state-variance priors, Wishart /
-    gamma / SV error priors, OLS initial values.  The covariance (psi) block (`sigma$covar`) is outside the
-    accelerated path and raises.
+    gamma / SV error priors, the covariance (psi) block (`sigma$covar`, constant-parameter models), OLS initial
+    values.  Variable selection on the covariances and the TVP psi block are outside the accelerated path and raise.
     """
     coef = dict(_DEF_COEF) if coef is None else dict(coef)
     sigma = dict(_DEF_SIGMA) if sigma is None else dict(sigma)
@@ -323,8 +323,9 @@ def add_priors(obj, coef=None, sigma=None, ssvs=None, bvs=None):
         raise ValueError("If 'coef$v_i' is not specified, at least 'coef$minnesota' or 'coef$ssvs' must be specified.")
     if len(sigma) < 2:
         raise ValueError("Argument 'sigma' must be at least of length 2.")
-    if sigma.get("covar"):
-        raise NotImplementedError("sigma$covar (psi block) is outside the accelerated path (SURVEY.md section 8f-4)")
+    covar = bool(sigma.get("covar"))
+    if covar and any(o["model"]["tvp"] for o in objs):
+        raise NotImplementedError("sigma$covar for TVP models is outside the accelerated path (SURVEY.md section 8f-4)")
 
     any_sv = any(o["model"]["sv"] for o in objs)
     if any_sv:
@@ -436,6 +437,16 @@ def add_priors(obj, coef=None, sigma=None, ssvs=None, bvs=None):
                 pc["rate"] = np.full((tot_par, 1), float(coef["rate"]))
                 if n_det > 0 and coef.get("rate_det") is not None:
                     pc["rate"][tot_par - n_struct - n_det: tot_par - n_struct, 0] = coef["rate_det"]
+
+        # covariance priors (R/add_priors.bvarmodel.R:494-503): psi ~ N(0, v_i^-1 I) on the k (k - 1) / 2 free elements
+        if covar and structural:
+            raise ValueError("Error covariances and structural coefficients cannot be estimated at the same time.")
+        if covar and not structural and k > 1:
+            if not o["model"]["sv"] and error_prior != "gamma":
+                raise ValueError("The covariance block needs a gamma ('sigma$shape', 'sigma$rate') or stochastic-volatility "
+                                 "error prior.")
+            n_covar = k * (k - 1) // 2
+            pri["psi"] = {"mu": np.zeros((n_covar, 1)), "v_i": np.diag(np.full(n_covar, float(coef["v_i"])))}
 
         ps = pri["sigma"] = {}
         if o["model"]["sv"]:

@@ -68,6 +68,7 @@ typedef struct bvg_inject {
   const double* state_normal;   /* n*T          */
   const double* sigma_v_gamma;  /* n            */
   const double* a_init_normal;  /* n            */
+  const double* psi_normal;     /* k(k-1)/2  covariance (psi) block, bvaralg.cpp:394 */
 } bvg_inject;
 
 /* The flat POD the Rcpp glue fills from the `bvarmodel` list (what src/bvaralg.cpp:9-249 and
@@ -115,6 +116,10 @@ typedef struct bvg_spec {
   const double* tvp_shape; /* n */
   const double* tvp_rate;  /* n */
   const double* a_init;    /* n */
+  /* priors$psi: covariance block of the constant-parameter sampler (bvaralg.cpp:157-162,373-455); NULL = none.
+   * Needs a gamma or SV error prior; variable selection on psi and TVP models are not supported (-5). */
+  const double* psi_mu;    /* k(k-1)/2 */
+  const double* psi_vi;    /* k(k-1)/2 x k(k-1)/2, column-major */
   /* tuning / testing */
   int32_t resid_mode;       /* BVG_RESID_*                                 */
   int32_t threads_per_chain; /* 0 = auto; 1,2,4,8,16,32 (sub-warp tiles) or a multiple of 32 (CTA per chain) */

@@ -6,8 +6,9 @@
 `literal=True` materialises the same dense matrices the reference builds (kron(I_T, Sigma^-1), the T x T SV system,
 the (nT) x (nT) TVP system) and runs the same LAPACK-level operations; `literal=False` evaluates the identical
 formulas through their Kronecker / banded structure (used for long tier-2 runs; proven equal to the literal
-path to <= 1e-10 in tests/test_oracle.py).  The covariance (psi) block and structural models are outside the
-accelerated path and raise.  Random variates come from a VariateSource (injected arrays
+path to <= 1e-10 in tests/test_oracle.py).  The covariance (psi) block of the constant-parameter sampler
+(bvaralg.cpp:373-455, gamma / SV errors) is restated literally; its SSVS / BVS twins, the TVP psi block and
+structural models are outside the accelerated path and raise.  Random variates come from a VariateSource (injected arrays
 or a NumPy Generator) in the site order of oracle/variates.py.
 """
 from __future__ import annotations
@@ -48,8 +49,9 @@ def _unpack_common(obj):
     n_c = k * len(model.get("deterministic", []))
     if model.get("structural"):
         raise NotImplementedError("structural models are outside the accelerated path (SURVEY.md 8f-4)")
-    if "psi" in priors:
-        raise NotImplementedError("covariance (psi) block is outside the accelerated path (SURVEY.md 8f-4)")
+    if "psi" in priors and (model.get("tvp") or any(key in priors["psi"] for key in ("ssvs", "bvs"))):
+        raise NotImplementedError("covariance (psi) block: TVP models and variable selection on psi are outside the "
+                                  "accelerated path (SURVEY.md 8f-4)")
     return data, model, priors, initial, y, k, tt, z, n_tot, n_a, n_b, n_c
 
 
@@ -133,6 +135,16 @@ def bvaralg(obj, variates: VariateSource | None = None, literal=True, table="ksc
         sigma_i = omega_i.copy()
     # per-period precision blocks: sig_t[t] is k x k.  Initially only the diagonal of sigma_i is used (:246).
     sig_t = np.tile(np.diag(np.diag(sigma_i))[None], (tt, 1, 1))
+    # covariance (psi) block, bvaralg.cpp:157-204,247-249,373-455: priors$psi = {mu, v_i}
+    covar = "psi" in priors
+    if covar:
+        if not (sv or use_gamma):
+            raise ValueError("The covariance block needs a gamma or stochastic-volatility error prior.")
+        psi_prior_mu = np.asarray(priors["psi"]["mu"], dtype=np.float64).reshape(-1)
+        psi_prior_vi = np.asarray(priors["psi"]["v_i"], dtype=np.float64)
+        n_psi = k * (k - 1) // 2
+        omega_diag = np.tile(np.diag(sigma_i), tt)                    # diag_omega_i = diag_sigma_i at the start, :247-249
+        Psi = np.eye(k)
 
     iters, burnin = int(model["iterations"]), int(model["burnin"])
     draws_coef = np.zeros((n_tot, iters))
@@ -207,6 +219,24 @@ def bvaralg(obj, variates: VariateSource | None = None, literal=True, table="ksc
         else:
             u = y
 
+        if covar:                                                                            # :373-455
+            psi_y = u[1:, :].reshape(-1, order="F")                                          # :376
+            psi_z = np.zeros(((k - 1) * tt, n_psi))
+            cov_omega = np.zeros((k - 1) * tt)
+            for i in range(1, k):
+                for j in range(tt):
+                    psi_z[j * (k - 1) + i - 1, i * (i - 1) // 2:(i + 1) * i // 2] = -u[0:i, j]          # :379-382
+                    cov_omega[j * (k - 1) + i - 1] = omega_diag[j * k + i]                                # :384
+            zo = psi_z.T * cov_omega[None, :]
+            psi_post_v = psi_prior_vi + zo @ psi_z                                           # :392
+            psi_post_mu = sla.solve(psi_post_v, psi_prior_vi @ psi_prior_mu + zo @ psi_y)    # :393
+            psi = psi_post_mu + sla.solve_triangular(sla.cholesky(psi_post_v, lower=False),
+                                                     vs.normal("psi_normal", draw, (n_psi,)), lower=False)   # :394
+            Psi = np.eye(k)
+            for i in range(1, k):
+                Psi[i, 0:i] = psi[i * (i - 1) // 2:(i + 1) * i // 2]                        # :451-453
+            u = Psi @ u                                                                      # :454
+
         if sv:
             h = stochvol_mixture(u.T, h, sigma_h, h_init, h_const,
                                  vs.uniform("sv_u", draw, (k, tt)), vs.normal("sv_normal", draw, (k, tt)),
@@ -225,6 +255,9 @@ def bvaralg(obj, variates: VariateSource | None = None, literal=True, table="ksc
                                                 vs.normal("h_init_normal", draw, (k,)), lower=False)
             sig_t = np.zeros((tt, k, k))
             sig_t[:, np.arange(k), np.arange(k)] = 1.0 / np.exp(h)                           # :494
+            if covar:
+                omega_diag = (1.0 / np.exp(h)).reshape(-1)                                   # vectorise(trans(h)), :494
+                sig_t = np.einsum("ia,ti,ib->tab", Psi, 1.0 / np.exp(h), Psi)                # Psi' Omega_t^-1 Psi, :495-497
         else:
             if use_gamma:
                 sse = u @ u.T
@@ -232,6 +265,9 @@ def bvaralg(obj, variates: VariateSource | None = None, literal=True, table="ksc
                 for i in range(k):
                     omega_i[i, i] = g[i] * (1.0 / (s_prior_rate[i] + sse[i, i] * 0.5))      # :484
                 sigma_i = omega_i.copy()                                                     # :507
+                if covar:
+                    omega_diag = np.tile(np.diag(omega_i), tt)                               # kron(diag_tt, omega_i), :504
+                    sigma_i = Psi.T @ omega_i @ Psi                                          # :505
             else:
                 Sbar = sla.solve(prior_scale + u @ u.T, diag_k)                              # :511
                 sigma_i = wishrnd(Sbar, vs.chi2("wishart_chi2", draw, post_df - np.arange(k)),

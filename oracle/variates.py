@@ -96,6 +96,8 @@ def draw_variates(dims: dict, sweeps: int, rng: np.random.Generator, kinds) -> d
             out[kind] = rng.chisquare(np.broadcast_to(dims["df"] - np.arange(k), (sweeps, k)))
         elif kind == "wishart_normal":
             out[kind] = rng.standard_normal((sweeps, k * (k - 1) // 2))
+        elif kind == "psi_normal":
+            out[kind] = rng.standard_normal((sweeps, k * (k - 1) // 2))
         elif kind == "state_normal":
             out[kind] = rng.standard_normal((sweeps, n * T))
         elif kind == "sigma_v_gamma":

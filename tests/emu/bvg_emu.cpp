@@ -71,8 +71,8 @@ static void fill_rng(const bvg_spec* s, const Prepared& P, RngParams* rp) {
                                  s->inject->sv_u, s->inject->sv_normal, s->inject->sigma_h_gamma,
                                  s->inject->h_init_normal, s->inject->omega_gamma, s->inject->wishart_chi2,
                                  s->inject->wishart_normal, s->inject->state_normal, s->inject->sigma_v_gamma,
-                                 s->inject->a_init_normal};
-  const int cnt[VB_COUNT] = {n, n, n, n, k * T, k * T, k, k, k, k, k * (k - 1) / 2, n * T, n, n};
+                                 s->inject->a_init_normal, s->inject->psi_normal};
+  const int cnt[VB_COUNT] = {n, n, n, n, k * T, k * T, k, k, k, k, k * (k - 1) / 2, n * T, n, n, k * (k - 1) / 2};
   for (int b = 0; b < VB_COUNT; ++b) {
     rp->inj[b] = ptr[b];
     rp->inj_stride[b] = cnt[b];
@@ -96,7 +96,7 @@ extern "C" int emu_bvaralg(const bvg_spec* s, const bvg_out* o) {
   std::vector<int> status(s->n_chains, 0);
   out.status = status.data();
   out.iters = s->iterations;
-  std::vector<double> sm(bvar_smem_len(P.k, P.T, P.M, P.n, P.sigma_type, P.resid_mode) + kron_smem_len(P.k, P.M) + 16);
+  std::vector<double> sm(bvar_smem_len(P.k, P.T, P.M, P.n, P.sigma_type, P.resid_mode, false, P.n_psi) + kron_smem_len(P.k, P.M) + 16);
   SerialGroup g;
   const int sweeps = s->iterations + s->burnin;
   const int chunk = s->sweeps_per_launch > 0 ? s->sweeps_per_launch : sweeps;

@@ -83,11 +83,19 @@ def model_c3(K=6, p=4, nobs=195, iterations=30, burnin=10, seed=195006, bvs=Fals
                       ssvs=dict(inprior=0.5, semiautomatic=(0.01, 10.0), exclude_det=True))
 
 
-def model_sv(K=3, p=2, nobs=60, iterations=20, burnin=5, seed=320200, tvp=False, bvs=False):
+def model_sv(K=3, p=2, nobs=60, iterations=20, burnin=5, seed=320200, tvp=False, bvs=False, covar=False):
     y = synth_var(K, p, nobs, seed)
     m = gen_var(y, p=p, deterministic="const", iterations=iterations, burnin=burnin, tvp=tvp, sv=True)
     return add_priors(m, coef=dict(v_i=1, v_i_det=0.1, shape=3, rate=1e-4, rate_det=0.01),
-                      sigma=dict(shape=3, rate=1e-4, mu=0, v_i=0.01, sigma_h=0.05, constant=1e-4),
+                      sigma=dict(shape=3, rate=1e-4, mu=0, v_i=0.01, sigma_h=0.05, constant=1e-4, covar=covar),
+                      bvs=dict(inprior=0.5, exclude_det=True) if bvs else None)
+
+
+def model_covar_gamma(K=3, p=2, nobs=70, iterations=20, burnin=5, seed=77, bvs=False):
+    """Covariance (psi) block with inverse-gamma variances (sigma = list(shape, rate, covar = TRUE))."""
+    y = synth_var(K, p, nobs, seed)
+    m = gen_var(y, p=p, deterministic="const", iterations=iterations, burnin=burnin)
+    return add_priors(m, coef=dict(v_i=1, v_i_det=0.1), sigma=dict(shape=3, rate=1e-4, covar=True),
                       bvs=dict(inprior=0.5, exclude_det=True) if bvs else None)
 
 
@@ -124,6 +132,8 @@ def variate_kinds(obj):
         kinds += ["wishart_chi2", "wishart_normal"]
     else:
         kinds += ["omega_gamma"]
+    if "psi" in priors:
+        kinds += ["psi_normal"]
     return kinds
 
 

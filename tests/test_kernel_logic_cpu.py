@@ -24,6 +24,10 @@ CASES = {
     "sv_ksc": (lambda: helpers.model_sv(), {}),
     "sv_ocsn": (lambda: helpers.model_sv(), dict(mixture="ocsn2007")),
     "sv_bvs": (lambda: helpers.model_sv(bvs=True), {}),
+    "covar_gamma": (lambda: helpers.model_covar_gamma(), {}),
+    "covar_gamma_k4_bvs": (lambda: helpers.model_covar_gamma(K=4, p=1, bvs=True), {}),
+    "covar_sv": (lambda: helpers.model_sv(covar=True), {}),
+    "covar_sv_k2": (lambda: helpers.model_sv(K=2, p=1, covar=True), {}),
     "tvp_sv": (lambda: helpers.model_sv(tvp=True, nobs=30), {}),
     "tvp_sv_bvs": (lambda: helpers.model_sv(tvp=True, nobs=30, bvs=True), {}),
 }
