@@ -21,7 +21,7 @@ _ip = C.POINTER(C.c_int32)
 
 INJECT_FIELDS = ["coef_normal", "ssvs_u", "bvs_u1", "bvs_u2", "sv_u", "sv_normal", "sigma_h_gamma",
                  "h_init_normal", "omega_gamma", "wishart_chi2", "wishart_normal", "state_normal",
-                 "sigma_v_gamma", "a_init_normal", "psi_normal"]
+                 "sigma_v_gamma", "a_init_normal", "psi_normal", "psi_u1", "psi_u2"]
 
 
 class BvgInject(C.Structure):
@@ -41,6 +41,8 @@ class BvgSpec(C.Structure):
         ("sigma_shape", _dp), ("sigma_rate", _dp), ("sv_mu", _dp), ("sv_vi", _dp), ("sv_sigma_h", _dp),
         ("sv_constant", _dp), ("sv_h", _dp), ("sv_mixture", C.c_int32), ("sigma_i", _dp),
         ("tvp_shape", _dp), ("tvp_rate", _dp), ("a_init", _dp), ("psi_mu", _dp), ("psi_vi", _dp),
+        ("psi_varsel", C.c_int32), ("psi_tau0", _dp), ("psi_tau1", _dp), ("psi_inprior", _dp), ("psi_include", _ip),
+        ("psi_n_include", C.c_int32),
         ("resid_mode", C.c_int32), ("threads_per_chain", C.c_int32), ("sweeps_per_launch", C.c_int32),
         ("inject", C.POINTER(BvgInject)),
     ]
@@ -88,7 +90,8 @@ class Spec:
         return {
             "coef": n * T if self.c.tvp else n,
             "sigma": k * k * T if sv else k * k,
-            "lambda": n if self.c.varsel != VARSEL_NONE else 0,
+            "lambda": (n if self.c.varsel != VARSEL_NONE else 0) +
+                      (k * (k - 1) // 2 if self.c.psi_varsel != VARSEL_NONE else 0),
             "sigma_h": k if sv else 0,
             "sigma_v": n if self.c.tvp else 0,
         }
@@ -100,9 +103,8 @@ def spec_from_model(obj, n_chains=1, seed=0, chain_offset=0, device=-1, resid_mo
     data, model, priors, initial = obj["data"], obj["model"], obj["priors"], obj["initial"]
     if model.get("structural"):
         raise NotImplementedError("structural models are not on the accelerated path (SURVEY.md section 8f-4)")
-    if "psi" in priors and (model.get("tvp") or any(key in priors["psi"] for key in ("ssvs", "bvs"))):
-        raise NotImplementedError("covariance (psi) block: TVP models and variable selection on psi are not on the "
-                                  "accelerated path (SURVEY.md 8f-4)")
+    if "psi" in priors and model.get("tvp"):
+        raise NotImplementedError("the covariance (psi) block of TVP models is not on the accelerated path (SURVEY.md 8f-4)")
     Y = np.asarray(data["Y"], dtype=np.float64)          # T x k
     T, k = Y.shape
     Z = data.get("Z")
@@ -174,6 +176,20 @@ def spec_from_model(obj, n_chains=1, seed=0, chain_offset=0, device=-1, resid_mo
     if "psi" in priors:                                   # covariance block (bvaralg.cpp:157-162)
         sp.set("psi_mu", _f(priors["psi"]["mu"]))
         sp.set("psi_vi", _f(np.asarray(priors["psi"]["v_i"], dtype=np.float64)))
+        psel = None
+        if "ssvs" in priors["psi"]:
+            c.psi_varsel = VARSEL_SSVS
+            psel = priors["psi"]["ssvs"]
+            sp.set("psi_tau0", _f(psel["tau0"]))
+            sp.set("psi_tau1", _f(psel["tau1"]))
+        if "bvs" in priors["psi"]:
+            c.psi_varsel = VARSEL_BVS
+            psel = priors["psi"]["bvs"]
+        if psel is not None:
+            sp.set("psi_inprior", _f(psel["inprior"]))
+            pinc = np.ascontiguousarray(np.asarray(psel["include"], dtype=np.int64).reshape(-1) - 1, dtype=np.int32)
+            sp.set("psi_include", pinc)
+            c.psi_n_include = pinc.shape[0]
     c.resid_mode, c.threads_per_chain, c.sweeps_per_launch = resid_mode, threads_per_chain, sweeps_per_launch
     if inject:
         st = BvgInject()

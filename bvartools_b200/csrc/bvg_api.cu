@@ -73,7 +73,7 @@ static void rows_of(const Prepared& P, long long* coef, long long* sigma, long l
   const bool svm = P.sigma_type == BVG_SIGMA_SV;
   *coef = P.tvp ? n * T : n;
   *sigma = svm ? k * k * T : k * k;
-  *lambda = (P.varsel != BVG_VARSEL_NONE) ? n : 0;
+  *lambda = ((P.varsel != BVG_VARSEL_NONE) ? n : 0) + ((P.psi_varsel != BVG_VARSEL_NONE) ? k * (k - 1) / 2 : 0);
   *sh = svm ? k : 0;
   *sv = P.tvp ? n : 0;
 }
@@ -104,6 +104,7 @@ int bvg_out_rows(const bvg_spec* spec, int64_t* coef_rows, int64_t* sigma_rows, 
   Prepared P;
   P.k = spec->k; P.T = spec->T; P.M = spec->M; P.n = spec->k * spec->M; P.tvp = spec->tvp ? 1 : 0;
   P.sigma_type = spec->sigma_type; P.varsel = spec->varsel;
+  P.psi_varsel = (spec->psi_mu != nullptr) ? spec->psi_varsel : BVG_VARSEL_NONE;
   long long a, b, c, d, e;
   rows_of(P, &a, &b, &c, &d, &e);
   if (coef_rows) *coef_rows = a;
@@ -213,8 +214,8 @@ int bvg_sampler_create(const bvg_spec* spec, bvg_sampler** out) {
                                    spec->inject->omega_gamma, spec->inject->wishart_chi2,
                                    spec->inject->wishart_normal, spec->inject->state_normal,
                                    spec->inject->sigma_v_gamma, spec->inject->a_init_normal,
-                                   spec->inject->psi_normal};
-    const int cnt[VB_COUNT] = {n, n, n, n, k * T, k * T, k, k, k, k, k * (k - 1) / 2, n * T, n, n, k * (k - 1) / 2};
+                                   spec->inject->psi_normal, spec->inject->psi_u1, spec->inject->psi_u2};
+    const int cnt[VB_COUNT] = {n, n, n, n, k * T, k * T, k, k, k, k, k * (k - 1) / 2, n * T, n, n, k * (k - 1) / 2, k * (k - 1) / 2, k * (k - 1) / 2};
     for (int b = 0; b < VB_COUNT; ++b) {
       if (!ptr[b] || cnt[b] == 0) continue;
       const size_t bytes = (size_t)s->n_chains * s->sweeps * cnt[b] * sizeof(double);

@@ -61,8 +61,12 @@ struct BvarModel {
   const double* omega_off;         // k x k off-diagonal part of the initial Sigma^-1 (gamma prior), zero diagonal
   // covariance (psi) block (bvaralg.cpp:373-455); n_psi = 0: none
   int n_psi;                       // k (k - 1) / 2
-  const double* psi_vi;            // n_psi x n_psi prior precision (col-major)
-  const double* psi_vmu;           // n_psi  prior precision times prior mean
+  const double* psi_vi;            // n_psi x n_psi prior precision (col-major); its diagonal lives in the chain state
+  const double* psi_vmu;           // n_psi  OFF-diagonal part of (prior precision times prior mean)
+  const double* psi_mu;            // n_psi  prior mean
+  int psi_varsel;                  // VS_* on the covariances (bvaralg.cpp:396-449)
+  const double* psi_tau0; const double* psi_tau1; const double* psi_inprior;      // n_psi each
+  const unsigned char* psi_include;                                               // n_psi
   // flat-prior Kronecker specialisation (bvg_kron_sweep.cuh); nullptr when the model does not qualify
   const double* kron_Linv;         // tri(M) packed lower: inverse of the lower Cholesky factor of X X'
   const double* kron_SS;           // k x k  S0 + SSE_ols
@@ -87,9 +91,10 @@ BVG_HD BvarConsts bvar_consts_of(const BvarModel& m) {
 //   then n              vdiag   (diagonal of V^-1, changed by SSVS)
 //   then n              lambda  (0/1)
 //   SV only: then T*k   h (col-major T x k: h_ti at t + T i), then k sigma_h, then k h_init
-//   covariance block only: then k  diagonal of Omega^-1 (gamma prior), then n_psi  psi (strict lower triangle of Psi by rows)
+//   covariance block only: then k  diagonal of Omega^-1 (gamma prior), n_psi  psi (strict lower triangle of Psi by rows),
+//                          n_psi  diagonal of the psi prior precision (SSVS), n_psi  psi inclusion indicators
 BVG_HD int bvar_state_len(int k, int T, int n, int sigma_type, int n_psi = 0) {
-  return k * k + 2 * n + (sigma_type == SIG_SV ? T * k + 2 * k : 0) + (n_psi > 0 ? k + n_psi : 0);
+  return k * k + 2 * n + (sigma_type == SIG_SV ? T * k + 2 * k : 0) + (n_psi > 0 ? k + 3 * n_psi : 0);
 }
 
 // Shared-memory doubles needed per chain.
@@ -99,7 +104,7 @@ BVG_HD int bvar_smem_len(int k, int T, int M, int n, int sigma_type, int resid_m
             + 2 * k * M;             // Dm, Wm
   if (resid_mode == RES_DIRECT || sigma_type == SIG_SV) len += k * T;                 // U
   if (sigma_type == SIG_SV) len += 3 * k * T + k * tri(M) + 2 * k;                    // h, ew, sv work, GW, sigma_h, h_init
-  if (n_psi > 0) len += tri(n_psi) + 3 * n_psi + k + k * k;                           // psi system, rhs, psi, dinv, omega diag, Psi
+  if (n_psi > 0) len += tri(n_psi) + 6 * n_psi + k + k * k;   // psi system, rhs, psi, dinv, prior diag, lambda, work, omega diag, Psi
   return len;
 }
 
@@ -498,11 +503,13 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
   const int npsi = (FEAT & (F_GAMMA | F_SV)) ? m.n_psi : 0;
   const bool covar = npsi > 0;
   double* pL = nullptr; double* prhs = nullptr; double* psi = nullptr; double* pdinv = nullptr; double* omd = nullptr;
-  double* PsiM = nullptr;
+  double* PsiM = nullptr; double* pvd = nullptr; double* plam = nullptr; double* pwork = nullptr;
   if (covar) {
     pL = sm; sm += tri(npsi);  prhs = sm; sm += npsi;  psi = sm; sm += npsi;  pdinv = sm; sm += npsi;
+    pvd = sm; sm += npsi;  plam = sm; sm += npsi;  pwork = sm; sm += npsi;
     omd = sm; sm += k;  PsiM = sm; sm += kk;
   }
+  const int pvs = covar ? m.psi_varsel : VS_NONE;
   int fail = 0;
 
   // load state
@@ -519,7 +526,7 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
   double* st_tail = state + bvar_state_len(k, T, n, m.sigma_type);       // [omega diagonal (k) | psi (npsi)]
   if (covar) {
     for (int e = tid; e < k; e += G) omd[e] = st_tail[e];
-    for (int e = tid; e < npsi; e += G) psi[e] = st_tail[k + e];
+    for (int e = tid; e < npsi; e += G) { psi[e] = st_tail[k + e]; pvd[e] = st_tail[k + npsi + e]; plam[e] = st_tail[k + 2 * npsi + e]; }
     g.sync();
     for (int e = tid; e < kk; e += G) {                                  // Psi: unit lower, row i holds psi[tri(i-1) ..]
       const int i = e % k, a = e / k;
@@ -718,7 +725,23 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
           if (gate) {
             double cj = 0.0, gj = 0.0;
             if (direct) {
-              if (sv) {
+              if (sv && covar) {
+                // Sigma_t^-1 = Psi' Omega_t^-1 Psi (previous sweep's Psi):  c_j = sum_t x_jt (Sigma_t^-1 u_t)_i,
+                // g_j = sum_t x_jt^2 (Sigma_t^-1)_ii
+                for (int t = 0; t < T; ++t) {
+                  double v = 0.0, s2 = 0.0;
+                  for (int q = i; q < k; ++q) {
+                    double pu = 0.0;
+                    for (int b = 0; b <= q; ++b) pu = fma(PsiM[q + k * b], U[b + k * t], pu);
+                    const double pw = PsiM[q + k * i] * ew[t + T * q];
+                    v = fma(pw, pu, v);
+                    s2 = fma(pw, PsiM[q + k * i], s2);
+                  }
+                  const double x = m.X[j + M * t];
+                  cj = fma(x, v, cj);
+                  gj = fma(x * x, s2, gj);
+                }
+              } else if (sv) {
                 for (int t = 0; t < T; ++t) {
                   const double xw = m.X[j + M * t] * ew[t + T * i];
                   cj = fma(xw, U[i + k * t], cj);
@@ -783,13 +806,14 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
         const int a = r - (i * (i - 1)) / 2;
         int i2 = 1; while ((i2 * (i2 + 1)) / 2 <= c) ++i2;
         const int b = c - (i2 * (i2 - 1)) / 2;
-        double v = m.psi_vi[r + (size_t)npsi * c];
+        double v = (r == c) ? pvd[r] : m.psi_vi[r + (size_t)npsi * c];
         if (i == i2) {
           double s = 0.0;
           for (int t = 0; t < T; ++t) {
             const double wt = sv ? ew[t + T * i] : omd[i];
             s = fma(U[a + k * t] * wt, U[b + k * t], s);
           }
+          if (pvs == VS_BVS) s *= plam[r] * plam[c];                                     // psi_z = psi_z_bvs Lambda, :388-391
           v += s;
         }
         pL[e] = v;
@@ -802,13 +826,63 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
           const double wt = sv ? ew[t + T * i] : omd[i];
           s = fma(-U[a + k * t] * wt, U[i + k * t], s);
         }
-        prhs[r] = m.psi_vmu[r] + s;                                                       // :393
+        if (pvs == VS_BVS) s *= plam[r];
+        prhs[r] = m.psi_vmu[r] + pvd[r] * m.psi_mu[r] + s;                                // :393
       }
       g.sync();
       chol_crout_generic(g, pL, pdinv, prhs, npsi, fail);
       for (int r = tid; r < npsi; r += G) prhs[r] += rng.normal(VB_PSI_N, sweep, r);      // :394
       g.sync();
       back_solve_lt_generic(g, pL, pdinv, prhs, psi, npsi);
+      if (pvs == VS_SSVS) {                                                               // :401-418
+        for (int r = tid; r < npsi; r += G) {
+          if (!m.psi_include[r]) continue;
+          const double t0 = m.psi_tau0[r], t1 = m.psi_tau1[r], pi = m.psi_inprior[r];
+          const double t0sq = t0 * t0, t1sq = t1 * t1, pr = psi[r];
+          const double u0 = 1.0 / t0 * exp(-((pr * pr) / (2.0 * t0sq))) * (1.0 - pi);
+          const double u1 = 1.0 / t1 * exp(-((pr * pr) / (2.0 * t1sq))) * pi;
+          const double p = u1 / (u0 + u1);
+          const double ld = bernoulli_rbinom(p, rng.uniform(VB_PSI_U1, sweep, r));
+          plam[r] = ld;
+          pvd[r] = (ld == 0.0) ? 1.0 / t0sq : 1.0 / t1sq;
+        }
+        g.sync();
+      }
+      if (pvs == VS_BVS) {                                                                // :420-448
+        // stale psi_AG = Lambda psi; equation i only: residual(delta) = rb_it + u_at delta with
+        // rb_it = u_it + sum_a' u_a't lambda_ia' psi_ia',  delta0 = -lambda psi, delta1 = (1 - lambda) psi
+        for (int r = tid; r < npsi; r += G) {
+          double newlam = plam[r];
+          if (m.psi_include[r]) {
+            int i = 1; while ((i * (i + 1)) / 2 <= r) ++i;
+            const int a = r - (i * (i - 1)) / 2;
+            const double lp0 = log(1.0 - m.psi_inprior[r]), lp1 = log(m.psi_inprior[r]);
+            const double g1 = log(rng.uniform(VB_PSI_U1, sweep, r));
+            const bool gate = (plam[r] == 1.0) ? (g1 < lp1) : (g1 < lp0);
+            if (gate) {
+              double cj = 0.0, gj = 0.0;
+              for (int t = 0; t < T; ++t) {
+                double rb = U[i + k * t];
+                for (int a2 = 0; a2 < i; ++a2) rb = fma(U[a2 + k * t], plam[(i * (i - 1)) / 2 + a2] * psi[(i * (i - 1)) / 2 + a2], rb);
+                const double wt = sv ? ew[t + T * i] : omd[i];
+                const double ua = U[a + k * t];
+                cj = fma(ua * wt, rb, cj);
+                gj = fma(ua * wt, ua, gj);
+              }
+              const double pr = psi[r];
+              const double d0 = -plam[r] * pr, d1 = (1.0 - plam[r]) * pr;
+              const double dq = 2.0 * (d1 - d0) * cj + (d1 * d1 - d0 * d0) * gj;          // q1 - q0
+              const double bayes = -0.5 * dq + (lp1 - lp0);
+              const double g2 = log(rng.uniform(VB_PSI_U2, sweep, r));
+              newlam = (bayes >= g2) ? 1.0 : 0.0;
+            }
+          }
+          pwork[r] = newlam;
+        }
+        g.sync();
+        for (int r = tid; r < npsi; r += G) { plam[r] = pwork[r]; psi[r] *= pwork[r]; }   // :446
+        g.sync();
+      }
       for (int e = tid; e < kk; e += G) {
         const int i = e % k, a = e / k;
         PsiM[e] = (i == a) ? 1.0 : ((a < i) ? psi[(i * (i - 1)) / 2 + a] : 0.0);        // :451-453
@@ -988,10 +1062,16 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
     if (keep && n > 0) {
       double* oc = out.coef + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n;
       for (int r = tid; r < n; r += G) oc[r] = a[r];
-      if (out.lambda != nullptr) {
-        double* ol = out.lambda + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n;
+      if (out.lambda != nullptr && varsel != VS_NONE) {
+        const int lrows = n + ((pvs != VS_NONE) ? npsi : 0);
+        double* ol = out.lambda + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)lrows;
         for (int r = tid; r < n; r += G) ol[r] = lam[r];
       }
+    }
+    if (keep && pvs != VS_NONE && out.lambda != nullptr) {                                // draws_lambda_a0, :530-532
+      const int l0 = (varsel != VS_NONE) ? n : 0;
+      double* ol = out.lambda + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)(l0 + npsi) + l0;
+      for (int r = tid; r < npsi; r += G) ol[r] = plam[r];
     }
     g.sync();
   }
@@ -1005,7 +1085,7 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
   }
   if (covar) {
     for (int e = tid; e < k; e += G) st_tail[e] = omd[e];
-    for (int e = tid; e < npsi; e += G) st_tail[k + e] = psi[e];
+    for (int e = tid; e < npsi; e += G) { st_tail[k + e] = psi[e]; st_tail[k + npsi + e] = pvd[e]; st_tail[k + 2 * npsi + e] = plam[e]; }
   }
   if (fail && tid == 0) out.status[chain_local] = 1;
   g.sync();

@@ -29,7 +29,9 @@ struct Prepared {
        mixp = -1, mixmu = -1, mixs2 = -1, omega_off = -1, vshape = -1, vrate = -1, kLinv = -1, kSS = -1;
   int kron = 0;   // 1 = flat-prior Kronecker sweep (bvg_kron_sweep.cuh)
   int n_psi = 0;  // k (k - 1) / 2 when the covariance (psi) block is active, else 0
-  long psi_mu = -1, psi_vi = -1, psi_vmu = -1;
+  int psi_varsel = 0;
+  long psi_mu = -1, psi_vi = -1, psi_vmu = -1, psi_tau0 = -1, psi_tau1 = -1, psi_inprior = -1;
+  std::vector<unsigned char> psi_include;
   std::string error;
 
   long push(const double* p, size_t cnt) {
@@ -189,16 +191,34 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
     if (P.tvp) BVG_FAIL(-5, "the covariance (psi) block of TVP models is not supported");
     if (P.sigma_type == BVG_SIGMA_WISHART) BVG_FAIL(-5, "the covariance (psi) block needs a gamma or SV error prior");
     if (k < 2) BVG_FAIL(-5, "the covariance (psi) block needs at least two endogenous variables");
-    if (P.sigma_type == BVG_SIGMA_SV && P.varsel == BVG_VARSEL_BVS)
-      BVG_FAIL(-5, "BVS on the coefficients together with SV and the covariance (psi) block is not supported");
     P.n_psi = k * (k - 1) / 2;
     if (has_nan(s->psi_mu, P.n_psi) || has_nan(s->psi_vi, (size_t)P.n_psi * P.n_psi)) BVG_FAIL(-6, "priors$psi contains NAs.");
     P.psi_mu = P.push(s->psi_mu, P.n_psi);
     P.psi_vi = P.push(s->psi_vi, (size_t)P.n_psi * P.n_psi);
-    std::vector<double> vm((size_t)P.n_psi, 0.0);                                  // psi_prior_vi * psi_prior_mu, :393
-    for (int r = 0; r < P.n_psi; ++r)
-      for (int c = 0; c < P.n_psi; ++c) vm[r] += s->psi_vi[r + (size_t)P.n_psi * c] * s->psi_mu[c];
+    std::vector<double> vm((size_t)P.n_psi, 0.0);       // OFF-diagonal part of psi_prior_vi * psi_prior_mu (:393); the
+    for (int r = 0; r < P.n_psi; ++r)                   // diagonal of the prior precision lives in the chain state (SSVS)
+      for (int c = 0; c < P.n_psi; ++c)
+        if (c != r) vm[r] += s->psi_vi[r + (size_t)P.n_psi * c] * s->psi_mu[c];
     P.psi_vmu = P.push(vm);
+    P.psi_varsel = s->psi_varsel;
+    if (P.psi_varsel != BVG_VARSEL_NONE && P.psi_varsel != BVG_VARSEL_SSVS && P.psi_varsel != BVG_VARSEL_BVS)
+      BVG_FAIL(-5, "invalid psi_varsel");
+    if (P.psi_varsel != BVG_VARSEL_NONE) {
+      if (P.psi_varsel == BVG_VARSEL_SSVS && P.sigma_type == BVG_SIGMA_SV)
+        BVG_FAIL(-11, "Not allowed to use SSVS with stochastic volatility.");      // bvaralg.cpp:173-175
+      if (!s->psi_inprior || !s->psi_include || s->psi_n_include < 0) BVG_FAIL(-4, "priors$psi variable selection: inprior / include missing");
+      if (P.psi_varsel == BVG_VARSEL_SSVS && (!s->psi_tau0 || !s->psi_tau1)) BVG_FAIL(-4, "priors$psi$ssvs: tau0 / tau1 missing");
+      P.psi_inprior = P.push(s->psi_inprior, P.n_psi);
+      if (P.psi_varsel == BVG_VARSEL_SSVS) { P.psi_tau0 = P.push(s->psi_tau0, P.n_psi); P.psi_tau1 = P.push(s->psi_tau1, P.n_psi); }
+      P.psi_include.assign((size_t)P.n_psi, 0);
+      for (int e = 0; e < s->psi_n_include; ++e) {
+        const int pos = s->psi_include[e];
+        if (pos < 0 || pos >= P.n_psi) BVG_FAIL(-5, "priors$psi: include position out of range");
+        P.psi_include[pos] = 1;
+      }
+      if ((int)P.include.size() < n) P.include.resize((size_t)n, 0);              // device mask: [coefficients (n) | psi (n_psi)]
+      P.include.insert(P.include.end(), P.psi_include.begin(), P.psi_include.end());
+    }
   }
 
   // ---- residual mode and cross moments
@@ -330,9 +350,14 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
     double* st = P.state0.data();
     for (int e = 0; e < kk; ++e) st[e] = sig0[e];
     for (int r = 0; r < n; ++r) { st[kk + r] = P.blob[P.vdiag0 + r]; st[kk + n + r] = 1.0; }
-    if (P.n_psi > 0) {   // tail of the state: diagonal of Omega^-1 (gamma prior), then psi = 0 (Psi = I, bvaralg.cpp:187)
-      double* tail = st + P.state_len - (k + P.n_psi);
+    if (P.n_psi > 0) {   // tail of the state: diagonal of Omega^-1 (gamma prior) | psi = 0 (Psi = I, bvaralg.cpp:187) |
+      //                      diagonal of the psi prior precision (changed by SSVS) | psi inclusion indicators (all 1)
+      double* tail = st + P.state_len - (k + 3 * P.n_psi);
       for (int i = 0; i < k; ++i) tail[i] = sig0[i + (size_t)k * i];
+      for (int r = 0; r < P.n_psi; ++r) {
+        tail[k + P.n_psi + r] = s->psi_vi[r + (size_t)P.n_psi * r];
+        tail[k + 2 * P.n_psi + r] = 1.0;
+      }
     }
     if (P.kron)   // the Kronecker sweep keeps B^-1 = chol(Sigma^-1)^-1 (upper) in the Sigma^-1 slot; the initial Sigma^-1 is diagonal
       for (int i = 0; i < k; ++i) st[i + (size_t)k * i] = 1.0 / sqrt(sig0[i + (size_t)k * i]);
@@ -360,7 +385,10 @@ static inline void bind_bvar(const Prepared& P, const double* base, const unsign
   m->sv_mu = at(base, P.svmu); m->sv_vi = at(base, P.svvi); m->sv_const = at(base, P.svconst);
   m->mix_p = at(base, P.mixp); m->mix_mu = at(base, P.mixmu); m->mix_s2 = at(base, P.mixs2);
   m->omega_off = at(base, P.omega_off);
-  m->n_psi = P.n_psi; m->psi_vi = at(base, P.psi_vi); m->psi_vmu = at(base, P.psi_vmu);
+  m->n_psi = P.n_psi; m->psi_vi = at(base, P.psi_vi); m->psi_vmu = at(base, P.psi_vmu); m->psi_mu = at(base, P.psi_mu);
+  m->psi_varsel = P.psi_varsel; m->psi_tau0 = at(base, P.psi_tau0); m->psi_tau1 = at(base, P.psi_tau1);
+  m->psi_inprior = at(base, P.psi_inprior);
+  m->psi_include = (inc != nullptr && P.psi_varsel != BVG_VARSEL_NONE) ? inc + P.n : nullptr;
   m->kron_Linv = P.kron ? at(base, P.kLinv) : nullptr;
   m->kron_SS = P.kron ? at(base, P.kSS) : nullptr;
 }

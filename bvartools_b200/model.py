@@ -343,6 +343,7 @@ def add_priors(obj, coef=None, sigma=None, ssvs=None, bvs=None):
         if error_prior == "wishart" and any(o["model"]["structural"] for o in objs):
             raise ValueError("Structural models may not use a Wishart prior.")
     minnesota = coef.get("minnesota") is not None
+    use_ssvs_error = use_bvs_error = False
     use_ssvs = ssvs is not None
     if use_ssvs:
         ssvs = dict(ssvs)
@@ -353,7 +354,12 @@ def add_priors(obj, coef=None, sigma=None, ssvs=None, bvs=None):
         ssvs.setdefault("exclude_det", False)
         minnesota = False
         if ssvs.get("covar"):
-            raise NotImplementedError("SSVS on covariances is outside the accelerated path")
+            if error_prior == "wishart":
+                raise ValueError("If SSVS should be applied to error covariances, argument 'sigma$shape' and "
+                                 "'sigma$rate' must be specified.")
+            if ssvs.get("tau") is None:
+                raise ValueError("If SSVS should be applied to error covariances, argument 'ssvs$tau' must be specified.")
+            use_ssvs_error = True
     use_bvs = bvs is not None
     if use_bvs:
         bvs = dict(bvs)
@@ -361,7 +367,9 @@ def add_priors(obj, coef=None, sigma=None, ssvs=None, bvs=None):
             raise ValueError("If BVS should be applied, argument 'bvs$inprior' must be specified.")
         bvs.setdefault("exclude_det", False)
         if bvs.get("covar"):
-            raise NotImplementedError("BVS on covariances is outside the accelerated path")
+            if error_prior == "wishart":
+                raise ValueError("If BVS should be applied to error covariances, argument 'sigma$shape' must be specified.")
+            use_bvs_error = True
     if use_ssvs and use_bvs:
         raise ValueError("SSVS and BVS cannot be applied at the same time.")
 
@@ -447,6 +455,14 @@ def add_priors(obj, coef=None, sigma=None, ssvs=None, bvs=None):
                                  "error prior.")
             n_covar = k * (k - 1) // 2
             pri["psi"] = {"mu": np.zeros((n_covar, 1)), "v_i": np.diag(np.full(n_covar, float(coef["v_i"])))}
+            if use_ssvs_error:                               # :505-511
+                pri["psi"]["ssvs"] = {"inprior": np.full((n_covar, 1), float(ssvs["inprior"])),
+                                      "include": np.arange(1, n_covar + 1).reshape(-1, 1),
+                                      "tau0": np.full((n_covar, 1), float(ssvs["tau"][0])),
+                                      "tau1": np.full((n_covar, 1), float(ssvs["tau"][1]))}
+            if use_bvs_error:                                # :514-517
+                pri["psi"]["bvs"] = {"inprior": np.full((n_covar, 1), float(bvs["inprior"])),
+                                     "include": np.arange(1, n_covar + 1).reshape(-1, 1)}
 
         ps = pri["sigma"] = {}
         if o["model"]["sv"]:

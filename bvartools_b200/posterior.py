@@ -73,6 +73,17 @@ def bvarpost(obj, seed=None, **kw):
     draws in a `bvar` object."""
     res = sampler.bvartvpalg(obj, seed=seed, **kw) if obj["model"].get("tvp") else sampler.bvaralg(obj, seed=seed, **kw)
     post = res["posteriors"]
+    if post["sigma"] is not None and "lambda" in post["sigma"]:
+        # psi indicators -> k^2 rows, NA on the diagonal, the same draw in both triangles (R/bvarpost.R:64-71)
+        k = np.asarray(obj["data"]["Y"]).shape[1]
+        lam = np.asarray(post["sigma"]["lambda"])
+        full = np.full((k * k, lam.shape[1]), np.nan)
+        lower = [i + k * j for j in range(k) for i in range(k) if i > j]            # which(lower.tri), column-major
+        upper = [i + k * j for j in range(k) for i in range(k) if i < j]
+        full[lower] = lam
+        full[upper] = lam
+        post = dict(post)
+        post["sigma"] = dict(post["sigma"], **{"lambda": full})
     return bvar(y=obj["data"]["Y"], x=obj["data"]["Z"], A0=None, A=post["a"], B=post["b"], C=post["c"],
                 Sigma=post["sigma"])
 

@@ -275,6 +275,17 @@ def split_posteriors(obj, arrays, chain=0):
     post = {"a0": None, "a": None, "b": None, "c": None, "sigma": None}
     coef = arrays.get("coef")
     lam = arrays.get("lambda")
+    # the lambda buffer holds [coefficient indicators (n, if selection on coefficients) | psi indicators (k (k - 1) / 2)]
+    n_psi = k * (k - 1) // 2
+    pc = obj.get("priors", {}).get("coefficients", {})
+    coef_sel = ("ssvs" in pc) or ("bvs" in pc)
+    pp = obj.get("priors", {}).get("psi", {})
+    psi_sel = ("ssvs" in pp) or ("bvs" in pp)
+    psi_lam = None
+    if lam is not None and psi_sel:
+        psi_lam = lam[chain][:, (n if coef_sel else 0):(n if coef_sel else 0) + n_psi].T      # draws_lambda_a0, bvaralg.cpp:604-611
+    if not coef_sel:
+        lam = None
     off = 0
     for name, cnt in (("a", n_a), ("b", n_b), ("c", n_c)):
         if cnt > 0 and coef is not None:
@@ -297,6 +308,8 @@ def split_posteriors(obj, arrays, chain=0):
         full = np.zeros((sh.shape[0], k, k))
         full[:, np.arange(k), np.arange(k)] = sh
         sig["sigma"] = full.reshape(sh.shape[0], k * k).T
+    if psi_lam is not None:
+        sig["lambda"] = psi_lam
     post["sigma"] = sig
     return post
 

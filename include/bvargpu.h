@@ -69,6 +69,8 @@ typedef struct bvg_inject {
   const double* sigma_v_gamma;  /* n            */
   const double* a_init_normal;  /* n            */
   const double* psi_normal;     /* k(k-1)/2  covariance (psi) block, bvaralg.cpp:394 */
+  const double* psi_u1;         /* k(k-1)/2  SSVS Bernoulli / BVS prior gate on psi, bvaralg.cpp:409,424 */
+  const double* psi_u2;         /* k(k-1)/2  BVS acceptance on psi, bvaralg.cpp:437 */
 } bvg_inject;
 
 /* The flat POD the Rcpp glue fills from the `bvarmodel` list (what src/bvaralg.cpp:9-249 and
@@ -117,9 +119,17 @@ typedef struct bvg_spec {
   const double* tvp_rate;  /* n */
   const double* a_init;    /* n */
   /* priors$psi: covariance block of the constant-parameter sampler (bvaralg.cpp:157-162,373-455); NULL = none.
-   * Needs a gamma or SV error prior; variable selection on psi and TVP models are not supported (-5). */
+   * Needs a gamma or SV error prior; TVP models are not supported (-5). */
   const double* psi_mu;    /* k(k-1)/2 */
   const double* psi_vi;    /* k(k-1)/2 x k(k-1)/2, column-major */
+  /* priors$psi$ssvs / $bvs: variable selection on the covariances (bvaralg.cpp:164-202,396-449); the inclusion draws
+   * are appended to the `lambda` output: rows [n (if coefficient selection is on) | k(k-1)/2] */
+  int32_t psi_varsel;          /* BVG_VARSEL_* */
+  const double* psi_tau0;      /* k(k-1)/2, SSVS */
+  const double* psi_tau1;      /* k(k-1)/2, SSVS */
+  const double* psi_inprior;   /* k(k-1)/2 */
+  const int32_t* psi_include;  /* 0-based positions taking part */
+  int32_t psi_n_include;
   /* tuning / testing */
   int32_t resid_mode;       /* BVG_RESID_*                                 */
   int32_t threads_per_chain; /* 0 = auto; 1,2,4,8,16,32 (sub-warp tiles) or a multiple of 32 (CTA per chain) */

@@ -49,9 +49,8 @@ def _unpack_common(obj):
     n_c = k * len(model.get("deterministic", []))
     if model.get("structural"):
         raise NotImplementedError("structural models are outside the accelerated path (SURVEY.md 8f-4)")
-    if "psi" in priors and (model.get("tvp") or any(key in priors["psi"] for key in ("ssvs", "bvs"))):
-        raise NotImplementedError("covariance (psi) block: TVP models and variable selection on psi are outside the "
-                                  "accelerated path (SURVEY.md 8f-4)")
+    if "psi" in priors and model.get("tvp"):
+        raise NotImplementedError("covariance (psi) block of TVP models is outside the accelerated path (SURVEY.md 8f-4)")
     return data, model, priors, initial, y, k, tt, z, n_tot, n_a, n_b, n_c
 
 
@@ -145,6 +144,25 @@ def bvaralg(obj, variates: VariateSource | None = None, literal=True, table="ksc
         n_psi = k * (k - 1) // 2
         omega_diag = np.tile(np.diag(sigma_i), tt)                    # diag_omega_i = diag_sigma_i at the start, :247-249
         Psi = np.eye(k)
+        psi_ssvs = "ssvs" in priors["psi"]                            # :164-172
+        psi_bvs = "bvs" in priors["psi"]                              # :177-183
+        if sv and psi_ssvs:
+            raise ValueError("Not allowed to use SSVS with stochastic volatility.")          # :173-175
+        if psi_ssvs:
+            pv = priors["psi"]["ssvs"]
+            psi_incl_prior = np.asarray(pv["inprior"], dtype=np.float64).reshape(-1)
+            psi_tau0 = np.asarray(pv["tau0"], dtype=np.float64).reshape(-1)
+            psi_tau1 = np.asarray(pv["tau1"], dtype=np.float64).reshape(-1)
+        if psi_bvs:
+            pv = priors["psi"]["bvs"]
+            psi_lp0 = np.log(1.0 - np.asarray(pv["inprior"], dtype=np.float64).reshape(-1))
+            psi_lp1 = np.log(np.asarray(pv["inprior"], dtype=np.float64).reshape(-1))
+        psi_varsel = psi_ssvs or psi_bvs
+        if psi_varsel:
+            psi_include = np.asarray(pv["include"], dtype=np.int64).reshape(-1) - 1          # :190
+            psi_lam = np.ones(n_psi)
+            psi_prior_vi = psi_prior_vi.copy()
+    draws_psi_lambda = None
 
     iters, burnin = int(model["iterations"]), int(model["burnin"])
     draws_coef = np.zeros((n_tot, iters))
@@ -227,11 +245,44 @@ def bvaralg(obj, variates: VariateSource | None = None, literal=True, table="ksc
                 for j in range(tt):
                     psi_z[j * (k - 1) + i - 1, i * (i - 1) // 2:(i + 1) * i // 2] = -u[0:i, j]          # :379-382
                     cov_omega[j * (k - 1) + i - 1] = omega_diag[j * k + i]                                # :384
+            psi_z_bvs = psi_z
+            if psi_bvs:
+                psi_z = psi_z_bvs * psi_lam[None, :]                                         # :388-391
             zo = psi_z.T * cov_omega[None, :]
             psi_post_v = psi_prior_vi + zo @ psi_z                                           # :392
             psi_post_mu = sla.solve(psi_post_v, psi_prior_vi @ psi_prior_mu + zo @ psi_y)    # :393
             psi = psi_post_mu + sla.solve_triangular(sla.cholesky(psi_post_v, lower=False),
                                                      vs.normal("psi_normal", draw, (n_psi,)), lower=False)   # :394
+            if psi_ssvs:                                                                     # :401-418
+                u0 = 1.0 / psi_tau0 * np.exp(-(psi ** 2 / (2.0 * psi_tau0 ** 2))) * (1.0 - psi_incl_prior)
+                u1 = 1.0 / psi_tau1 * np.exp(-(psi ** 2 / (2.0 * psi_tau1 ** 2))) * psi_incl_prior
+                post_incl = u1 / (u0 + u1)
+                uu = vs.uniform("psi_u1", draw, (n_psi,))
+                for i in psi_include:
+                    ld = float(bernoulli_rbinom(post_incl[i], uu[i]))
+                    psi_lam[i] = ld
+                    psi_prior_vi[i, i] = 1.0 / psi_tau0[i] ** 2 if ld == 0 else 1.0 / psi_tau1[i] ** 2
+            if psi_bvs:                                                                      # :420-448
+                psi_AG = psi_lam * psi
+                g1 = np.log(vs.uniform("psi_u1", draw, (n_psi,)))
+                g2 = np.log(vs.uniform("psi_u2", draw, (n_psi,)))
+                new_lam = psi_lam.copy()
+                for j in psi_include:
+                    if psi_lam[j] == 1 and g1[j] >= psi_lp1[j]:
+                        continue
+                    if psi_lam[j] == 0 and g1[j] >= psi_lp0[j]:
+                        continue
+                    th0 = psi_AG.copy()
+                    th1 = psi_AG.copy()
+                    th0[j] = 0.0
+                    th1[j] = psi[j]
+                    r0 = psi_y - psi_z_bvs @ th0
+                    r1 = psi_y - psi_z_bvs @ th1
+                    l0 = -float(r0 @ (cov_omega * r0)) / 2.0 + psi_lp0[j]
+                    l1 = -float(r1 @ (cov_omega * r1)) / 2.0 + psi_lp1[j]
+                    new_lam[j] = 1.0 if (l1 - l0) >= g2[j] else 0.0
+                psi_lam = new_lam
+                psi = psi_lam * psi                                                          # :446
             Psi = np.eye(k)
             for i in range(1, k):
                 Psi[i, 0:i] = psi[i * (i - 1) // 2:(i + 1) * i // 2]                        # :451-453
@@ -286,6 +337,10 @@ def bvaralg(obj, variates: VariateSource | None = None, literal=True, table="ksc
                 draws_coef[:, pos] = a
                 if varsel:
                     draws_lambda[:, pos] = lam
+            if covar and psi_varsel:
+                if draws_psi_lambda is None:
+                    draws_psi_lambda = np.zeros((n_psi, iters))
+                draws_psi_lambda[:, pos] = psi_lam                                           # :530-532
 
     posteriors = {"a0": None, "a": None, "b": None, "c": None, "sigma": None}
     if use_a:
@@ -293,6 +348,8 @@ def bvaralg(obj, variates: VariateSource | None = None, literal=True, table="ksc
     posteriors["sigma"] = {"coeffs": draws_sigma}
     if sv:
         posteriors["sigma"]["sigma"] = draws_sigma_sigma
+    if draws_psi_lambda is not None:
+        posteriors["sigma"]["lambda"] = draws_psi_lambda                                     # :604-611
     return {"data": obj["data"], "model": obj["model"], "priors": obj["priors"], "posteriors": posteriors}
 
 

@@ -98,6 +98,8 @@ def draw_variates(dims: dict, sweeps: int, rng: np.random.Generator, kinds) -> d
             out[kind] = rng.standard_normal((sweeps, k * (k - 1) // 2))
         elif kind == "psi_normal":
             out[kind] = rng.standard_normal((sweeps, k * (k - 1) // 2))
+        elif kind in ("psi_u1", "psi_u2"):
+            out[kind] = rng.random((sweeps, k * (k - 1) // 2))
         elif kind == "state_normal":
             out[kind] = rng.standard_normal((sweeps, n * T))
         elif kind == "sigma_v_gamma":

@@ -71,8 +71,8 @@ static void fill_rng(const bvg_spec* s, const Prepared& P, RngParams* rp) {
                                  s->inject->sv_u, s->inject->sv_normal, s->inject->sigma_h_gamma,
                                  s->inject->h_init_normal, s->inject->omega_gamma, s->inject->wishart_chi2,
                                  s->inject->wishart_normal, s->inject->state_normal, s->inject->sigma_v_gamma,
-                                 s->inject->a_init_normal, s->inject->psi_normal};
-  const int cnt[VB_COUNT] = {n, n, n, n, k * T, k * T, k, k, k, k, k * (k - 1) / 2, n * T, n, n, k * (k - 1) / 2};
+                                 s->inject->a_init_normal, s->inject->psi_normal, s->inject->psi_u1, s->inject->psi_u2};
+  const int cnt[VB_COUNT] = {n, n, n, n, k * T, k * T, k, k, k, k, k * (k - 1) / 2, n * T, n, n, k * (k - 1) / 2, k * (k - 1) / 2, k * (k - 1) / 2};
   for (int b = 0; b < VB_COUNT; ++b) {
     rp->inj[b] = ptr[b];
     rp->inj_stride[b] = cnt[b];

@@ -83,20 +83,22 @@ def model_c3(K=6, p=4, nobs=195, iterations=30, burnin=10, seed=195006, bvs=Fals
                       ssvs=dict(inprior=0.5, semiautomatic=(0.01, 10.0), exclude_det=True))
 
 
-def model_sv(K=3, p=2, nobs=60, iterations=20, burnin=5, seed=320200, tvp=False, bvs=False, covar=False):
+def model_sv(K=3, p=2, nobs=60, iterations=20, burnin=5, seed=320200, tvp=False, bvs=False, covar=False, psi_bvs=False):
     y = synth_var(K, p, nobs, seed)
     m = gen_var(y, p=p, deterministic="const", iterations=iterations, burnin=burnin, tvp=tvp, sv=True)
     return add_priors(m, coef=dict(v_i=1, v_i_det=0.1, shape=3, rate=1e-4, rate_det=0.01),
                       sigma=dict(shape=3, rate=1e-4, mu=0, v_i=0.01, sigma_h=0.05, constant=1e-4, covar=covar),
-                      bvs=dict(inprior=0.5, exclude_det=True) if bvs else None)
+                      bvs=dict(inprior=0.5, exclude_det=True, covar=psi_bvs) if (bvs or psi_bvs) else None)
 
 
-def model_covar_gamma(K=3, p=2, nobs=70, iterations=20, burnin=5, seed=77, bvs=False):
-    """Covariance (psi) block with inverse-gamma variances (sigma = list(shape, rate, covar = TRUE))."""
+def model_covar_gamma(K=3, p=2, nobs=70, iterations=20, burnin=5, seed=77, bvs=False, psi_sel=None):
+    """Covariance (psi) block with inverse-gamma variances (sigma = list(shape, rate, covar = TRUE)); psi_sel =
+    "ssvs" / "bvs": variable selection on the covariances as well (ssvs$covar / bvs$covar)."""
     y = synth_var(K, p, nobs, seed)
     m = gen_var(y, p=p, deterministic="const", iterations=iterations, burnin=burnin)
-    return add_priors(m, coef=dict(v_i=1, v_i_det=0.1), sigma=dict(shape=3, rate=1e-4, covar=True),
-                      bvs=dict(inprior=0.5, exclude_det=True) if bvs else None)
+    ssvs = dict(inprior=0.5, tau=(0.05, 10.0), exclude_det=True, covar=True) if psi_sel == "ssvs" else None
+    bv = dict(inprior=0.5, exclude_det=True, covar=(psi_sel == "bvs")) if (bvs or psi_sel == "bvs") else None
+    return add_priors(m, coef=dict(v_i=1, v_i_det=0.1), sigma=dict(shape=3, rate=1e-4, covar=True), ssvs=ssvs, bvs=bv)
 
 
 def model_c5(K=20, p=4, nobs=204, iterations=200, burnin=50, seed=2042004):
@@ -134,6 +136,10 @@ def variate_kinds(obj):
         kinds += ["omega_gamma"]
     if "psi" in priors:
         kinds += ["psi_normal"]
+        if "ssvs" in priors["psi"]:
+            kinds += ["psi_u1"]
+        if "bvs" in priors["psi"]:
+            kinds += ["psi_u1", "psi_u2"]
     return kinds
 
 
@@ -183,8 +189,11 @@ def oracle_stack(obj, per_chain, literal=True, table="ksc1998"):
             res["sigma_v"].append(np.concatenate([p["sigma"] for p in parts], axis=0).T)
         elif parts:
             res["coef"].append(np.concatenate([p["coeffs"] for p in parts], axis=0).T)
-        if parts and "lambda" in parts[0]:
-            res["lambda"].append(np.concatenate([p["lambda"] for p in parts], axis=0).T)
+        lam_rows = [p["lambda"] for p in parts] if parts and "lambda" in parts[0] else []
+        if "lambda" in r["sigma"]:                          # psi inclusion draws follow the coefficient ones in the buffer
+            lam_rows.append(r["sigma"]["lambda"])
+        if lam_rows:
+            res["lambda"].append(np.concatenate(lam_rows, axis=0).T)
         res["sigma"].append(r["sigma"]["coeffs"].T)
         if "sigma" in r["sigma"]:
             res["sigma_h"].append(r["sigma"]["sigma"].reshape(k, k, -1)[np.arange(k), np.arange(k)].T)

@@ -26,6 +26,9 @@ CASES = {
     "sv_bvs": (lambda: helpers.model_sv(bvs=True), {}),
     "covar_gamma": (lambda: helpers.model_covar_gamma(), {}),
     "covar_gamma_k4_bvs": (lambda: helpers.model_covar_gamma(K=4, p=1, bvs=True), {}),
+    "covar_gamma_psi_ssvs": (lambda: helpers.model_covar_gamma(psi_sel="ssvs"), {}),
+    "covar_gamma_psi_bvs": (lambda: helpers.model_covar_gamma(K=4, p=1, psi_sel="bvs"), {}),
+    "covar_sv_psi_bvs": (lambda: helpers.model_sv(covar=True, psi_bvs=True), {}),
     "covar_sv": (lambda: helpers.model_sv(covar=True), {}),
     "covar_sv_k2": (lambda: helpers.model_sv(K=2, p=1, covar=True), {}),
     "tvp_sv": (lambda: helpers.model_sv(tvp=True, nobs=30), {}),
