@@ -220,6 +220,28 @@ def test_tier2_ssvs_vs_oracle_sampler(gpu):
         assert np.all(np.abs(d.mean(axis=0) - o.mean(axis=0)) < 4.5 * se + 1e-9), name
 
 
+def test_tier2_covariance_block_vs_oracle_sampler(gpu):
+    """Tier 2 for the covariance (psi) block with BVS on the covariances (gamma variances): posterior means of the
+    coefficients, of Sigma and the psi inclusion frequencies of the GPU sampler (Philox) vs the oracle sampler with its
+    own NumPy generator; across-chain means within 4.5 standard errors."""
+    from oracle.samplers import bvaralg
+    from oracle.variates import VariateSource
+    obj = helpers.model_covar_gamma(K=3, p=1, nobs=90, iterations=500, burnin=300, psi_sel="bvs")
+    dev = _run(gpu, obj, 48, seed=21)
+    o = {"coef": [], "sigma": [], "lambda": []}
+    for c in range(12):
+        r = bvaralg(obj, VariateSource(rng=np.random.default_rng(900 + c)), literal=False)["posteriors"]
+        o["coef"].append(np.concatenate([r[nm]["coeffs"] for nm in ("a", "c")]).mean(axis=1))
+        o["sigma"].append(r["sigma"]["coeffs"].mean(axis=1))
+        o["lambda"].append(np.concatenate([np.concatenate([r[nm]["lambda"] for nm in ("a", "c")]),
+                                           r["sigma"]["lambda"]]).mean(axis=1))
+    assert 0.02 < dev.arrays["lambda"][:, :, -3:].mean() < 0.98
+    for name in ("coef", "sigma", "lambda"):
+        d, oo = dev.arrays[name].mean(axis=1), np.array(o[name])
+        se = np.hypot(d.std(axis=0, ddof=1) / np.sqrt(d.shape[0]), oo.std(axis=0, ddof=1) / np.sqrt(oo.shape[0]))
+        assert np.all(np.abs(d.mean(axis=0) - oo.mean(axis=0)) < 4.5 * se + 1e-9), name
+
+
 def test_tier2_tvp_sv_vs_oracle_sampler(gpu):
     """Tier 2 for the TVP + KSC-SV sampler at a small shape: posterior means of the state path, state variances and
     log-volatility driven Sigma_t vs the oracle sampler, within 4.5 MCSE (many marginals)."""
