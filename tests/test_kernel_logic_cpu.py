@@ -61,6 +61,23 @@ def _tvp_wishart():
 CASES["tvp_wishart"] = (_tvp_wishart, {})
 
 
+def _exogen(sv=False, ssvs=False):
+    """VARX: two exogenous regressors with one lag (B coefficients, R/gen_var.R:143-161) next to lags and a constant."""
+    y = helpers.synth_var(3, 2, 80, 5)
+    x = np.random.default_rng(1).standard_normal((80, 2))
+    m = helpers.gen_var(y, p=2, exogen=x, s=1, deterministic="const", iterations=12, burnin=3, sv=sv)
+    if sv:
+        return helpers.add_priors(m, coef=dict(v_i=1, v_i_det=0.1),
+                                  sigma=dict(shape=3, rate=1e-4, mu=0, v_i=0.01, sigma_h=0.05, constant=1e-4, covar=True))
+    return helpers.add_priors(m, coef=dict(v_i=1, v_i_det=0.1), sigma=dict(df="k", scale=1),
+                              ssvs=dict(inprior=0.5, tau=(0.05, 10.0), exclude_det=True) if ssvs else None)
+
+
+CASES["exogen_wishart"] = (_exogen, {})
+CASES["exogen_ssvs"] = (lambda: _exogen(ssvs=True), {})
+CASES["exogen_sv_covar"] = (lambda: _exogen(sv=True), {})
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_kernel_logic_matches_oracle(emu, name):
     builder, kw = CASES[name]
