@@ -18,7 +18,8 @@ import ctypes as C
 from . import sampler
 from ._lib import check, lib, require_device
 
-__all__ = ["draw_posterior", "bvarpost", "bvar", "summary", "summary_bvarlist", "information_criteria", "thin"]
+__all__ = ["draw_posterior", "bvarpost", "bvar", "summary", "summary_bvarlist", "information_criteria", "thin", "irf",
+           "fevd"]
 
 
 def bvar(y, x=None, A0=None, A=None, B=None, C=None, Sigma=None):
@@ -195,4 +196,82 @@ def summary_bvarlist(objects):
         row.update(information_criteria(ll, m, tt))
         rows.append(row)
     return rows
+
+
+def _device_draws(obj, period):
+    """A (draws x k^2 p) and Sigma (draws x k^2) of a `bvar` object as device tensors (torch is only the allocator)."""
+    import torch
+    require_device()
+    y = np.asarray(obj["y"])
+    tt, k = y.shape
+    A = obj.get("A")
+    if isinstance(A, list):
+        A = A[tt - 1 if period is None else period]
+    S = obj.get("Sigma")
+    if isinstance(S, list):
+        S = S[tt - 1 if period is None else period]
+    if S is None:
+        raise ValueError("Argument 'object' must include draws of the variance-covariance matrix Sigma.")
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    draws = S.shape[0]
+    A = np.zeros((draws, 0)) if A is None else np.ascontiguousarray(A, dtype=np.float64)
+    p = A.shape[1] // (k * k)
+    dA = torch.from_numpy(A).cuda() if A.size else None
+    dS = torch.from_numpy(S).cuda()
+    return k, p, draws, dA, dS
+
+
+def irf(obj, impulse, response, n_ahead=5, ci=0.95, shock=1, type="feir", cumulative=False, keep_draws=False,
+        period=None):
+    """irf.bvar (R/irf.bvar.R:78-216) for a host `bvar` object: `impulse` / `response` are 0-based variable positions.
+    The draws are uploaded once; the per-draw responses and their bands are computed on the device."""
+    import torch
+    types = {"feir": 0, "oir": 1, "gir": 2}
+    if type not in types:
+        if type in ("sir", "sgir"):
+            raise ValueError("Structural IR requires that draws of 'A0' are contained in the 'bvar' x.")
+        raise ValueError("Argument 'type' not known.")
+    if isinstance(shock, str):
+        if shock not in ("sd", "nsd"):
+            raise ValueError("Invalid specification of argument 'shock'.")
+        kind, val = (1 if shock == "sd" else 2), 0.0
+    else:
+        kind, val = 0, float(shock)
+    k, p, draws, dA, dS = _device_draws(obj, period)
+    if p == 0:
+        raise ValueError("Impulse responses only supported for models with p > 0, i.e. argument 'x' must contain "
+                         "element 'A', or structural models.")
+    out = torch.empty((draws, n_ahead + 1), dtype=torch.float64, device="cuda")
+    vp = C.c_void_p
+    check(lib().bvg_irf_draws(vp(dA.data_ptr()), dA.shape[1], vp(dS.data_ptr()), k * k, draws, k, p, int(n_ahead),
+                              types[type], int(impulse), int(response), kind, val, int(bool(cumulative)),
+                              vp(out.data_ptr()), None))
+    if keep_draws:
+        return out.cpu().numpy()
+    lo = (1.0 - ci) / 2.0
+    probs = np.ascontiguousarray([lo, 0.5, 1.0 - lo])
+    q = np.empty((3, n_ahead + 1))
+    dp = C.POINTER(C.c_double)
+    check(lib().bvg_summary_draws(vp(out.data_ptr()), draws, n_ahead + 1, probs.ctypes.data_as(dp), 3, None, None,
+                                  q.ctypes.data_as(dp), None))
+    return q.T
+
+
+def fevd(obj, response, n_ahead=5, type="oir", normalise_gir=False, period=None):
+    """fevd.bvar (R/fevd.bvar.R:72-186) for a host `bvar` object: (n_ahead + 1) x k table, mean over the draws."""
+    types = {"oir": 1, "gir": 2}
+    if type not in types:
+        if type in ("sir", "sgir"):
+            raise ValueError("Structural FEVD requires that draws of 'A0' are contained in the 'bvar' object.")
+        raise ValueError("The specified type of the used impulse response is not known.")
+    k, p, draws, dA, dS = _device_draws(obj, period)
+    if p == 0:
+        raise ValueError("Variance decompositions only supported for models with p > 0, i.e. argument 'object' must "
+                         "contain element 'A', or structural models.")
+    out = np.empty((n_ahead + 1, k))
+    vp = C.c_void_p
+    check(lib().bvg_fevd_draws(vp(dA.data_ptr()), dA.shape[1], vp(dS.data_ptr()), k * k, draws, k, p, int(n_ahead),
+                               types[type], int(response), int(bool(normalise_gir)),
+                               out.ctypes.data_as(C.POINTER(C.c_double)), None))
+    return out
 

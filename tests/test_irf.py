@@ -108,3 +108,17 @@ def test_fevd_on_resident_draws_matches_oracle(gpu, type_, norm):
         s.fevd(0, type="sgir")
     s.close()
 
+
+@pytest.mark.gpu
+def test_irf_and_fevd_of_a_host_bvar_object(gpu):
+    """Package-level irf() / fevd() on a `bvar` object (draws on the host, as the reference's methods receive them)."""
+    import bvartools_b200 as bt
+    obj = helpers.model_c1(iterations=60, burnin=10)
+    fit = bt.draw_posterior(obj, seed=4)
+    k = 3
+    A, S = np.asarray(fit["A"]), np.asarray(fit["Sigma"])
+    want = ob.irf_bvar(A, S, k, 1, 2, n_ahead=8, type="oir", shock="sd", ci=0.9)
+    np.testing.assert_allclose(bt.irf(fit, 0, 1, n_ahead=8, type="oir", shock="sd", ci=0.9), want, rtol=1e-10, atol=1e-14)
+    want_v = ob.fevd_bvar(A, S, k, 3, n_ahead=6, type="gir", normalise_gir=True)
+    assert helpers.relerr(bt.fevd(fit, 2, n_ahead=6, type="gir", normalise_gir=True), want_v) < TOL
+
