@@ -485,16 +485,31 @@ def main():
             for i in range(3):
                 fence()
                 t0 = time.perf_counter()
-                sm = sampler.summary("coef")
+                sm = sampler.summary("coef", ts_se=False)
                 dt = time.perf_counter() - t0
                 if i > 0:
                     sm_ms.append(dt * 1e3)
             ms = float(np.median(sm_ms))
+            ts_ms = []
+            for i in range(3):
+                fence()
+                t0 = time.perf_counter()
+                ts = sampler.time_series_se("coef")
+                dt = time.perf_counter() - t0
+                if i > 0:
+                    ts_ms.append(dt * 1e3)
             nbytes = 8.0 * chains * it * rows["coef"]
             post_summary = {"what": "bvg_sampler_summary(coef): moments + 8-pass radix select + neighbour pass over all "
                                     "resident draws (R/summary.bvar.R:121-140)", "ms": ms, "values": chains * it * rows["coef"],
                             "passes": 11, "stream_GBps": 11 * nbytes / (ms * 1e-3) / 1e9,
-                            "median_first3": [float(v) for v in sm["quantiles"][1][:3]]}
+                            "median_first3": [float(v) for v in sm["quantiles"][1][:3]],
+                            "time_series_se": {"what": "bvg_sampler_tsse(coef): coda spectrum0.ar per chain and row "
+                                                       "(means, autocovariances to lag floor(10 log10 iter), "
+                                                       "Levinson-Durbin + AIC), pooled over chains",
+                                               "ms": float(np.median(ts_ms)),
+                                               "first3": [float(v) for v in ts[:3]],
+                                               "naive_se_first3": [float(v) for v in
+                                                                   (sm["sd"] / np.sqrt(chains * it))[:3]]}}
         except Exception as exc:
             post_summary = {"error": str(exc)}
 

@@ -735,6 +735,39 @@ int bvg_sampler_summary(bvg_sampler* s, int32_t which, const double* probs, int3
                            cuda_stream);
 }
 
+int bvg_tsse_draws(const double* dev_draws, int64_t n_chains, int64_t iters, int64_t rows, double* tsse,
+                   void* cuda_stream) {
+  if (!dev_draws || !tsse || n_chains < 1 || iters < 1 || rows < 1) return fail(-1, "invalid arguments to bvg_tsse_draws");
+  if (iters < 3 || iters >= 2500000) return fail(-2, "bvg_tsse_draws: need 3 <= iterations per chain < 2.5e6");
+  if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  double* d_out = nullptr;
+  CK(cudaMalloc((void**)&d_out, (size_t)rows * 8));
+  cudaError_t e = launch_tsse(dev_draws, n_chains, iters, rows, d_out, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tsse, d_out, (size_t)rows * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return cuda_fail(e, "time-series SE kernels");
+  return 0;
+}
+
+int bvg_sampler_tsse(bvg_sampler* s, int32_t which, double* tsse, void* cuda_stream) {
+  if (!s) return fail(-1, "sampler is NULL");
+  CK(cudaSetDevice(s->device));
+  const double* buf = nullptr;
+  long long rows = 0;
+  switch (which) {
+    case 0: buf = s->d_coef; rows = s->rows_coef; break;
+    case 1: buf = s->d_sigma; rows = s->rows_sigma; break;
+    case 2: buf = s->d_lambda; rows = s->rows_lambda; break;
+    case 3: buf = s->d_sigma_h; rows = s->rows_sigma_h; break;
+    case 4: buf = s->d_sigma_v; rows = s->rows_sigma_v; break;
+    default: return fail(-1, "which must be 0 (coef), 1 (sigma), 2 (lambda), 3 (sigma_h) or 4 (sigma_v)");
+  }
+  if (!buf || rows < 1) return fail(-6, "the sampler has no such output");
+  return bvg_tsse_draws(buf, (int64_t)s->n_chains, (int64_t)s->P.iterations, rows, tsse, cuda_stream);
+}
+
 int bvg_irf_draws(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
                   int64_t n_draws, int32_t k, int32_t p, int32_t n_ahead, int32_t type, int32_t impulse, int32_t response,
                   int32_t shock_kind, double shock, int32_t cumulative, double* dev_out, void* cuda_stream) {

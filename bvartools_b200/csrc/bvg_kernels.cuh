@@ -49,6 +49,8 @@ cudaError_t launch_loglik_total(int k, int M, int T, long long n_draws, const do
 // posterior summaries of resident draws (bvg_summary.cu): exact type-7 quantiles by radix select, centred sum of squares
 cudaError_t launch_quantiles(const double* draws, long long n_draws, long long rows, const double* d_probs, int n_probs,
                              double* d_out, cudaStream_t stream);
+cudaError_t launch_tsse(const double* draws, long long n_chains, long long iters, long long rows, double* d_out,
+                        cudaStream_t stream);
 cudaError_t launch_centered_ss(const double* draws, long long n_draws, long long rows, const double* d_sums, double* d_ss,
                                cudaStream_t stream);
 // impulse responses per draw (bvg_postest.cu)

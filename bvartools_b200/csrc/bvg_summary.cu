@@ -267,4 +267,177 @@ cudaError_t launch_quantiles(const double* draws, long long n_draws, long long r
   return e;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Time-series SE of coda::summary.mcmc (the "Time-series SE" column summary.bvar copies: R/summary.bvar.R:133,141,195,
+// 203).  coda is an un-vendored CRAN dependency; its spectrum0.ar fits an AR(m) by Yule-Walker (stats::ar.yw, AIC order
+// selection, order.max = min(n - 1, floor(10 log10 n))) to every series and returns var.pred / (1 - sum ar)^2; the SE is
+// sqrt(spec / n), and for several chains (summary.mcmc.list) sqrt(mean_c spec_c / (n chains)).
+// draws: [chain][iter][row].  Three passes: per-chain means (+ the slope sum of the lm(x ~ t) degeneracy check),
+// autocovariances for lags 0..L from shared-memory tiles of 32 rows, and one thread per series for Levinson-Durbin.
+static constexpr int TS_ROWS = 32;        // rows per CTA tile (one 256-byte line per period)
+static constexpr int TS_SEG = 128;        // periods per shared-memory segment
+static constexpr int TS_LG = 8;           // lags per work item
+static constexpr int TS_MAXLAG = 63;
+
+// sums[chain][row] = sum_t x, tsum[chain][row] = sum_t t x  (t = 0..iters-1)
+__global__ void __launch_bounds__(256) tsse_mean_kernel(const double* __restrict__ draws, long long iters, long long rows,
+                                                        double* __restrict__ sums, double* __restrict__ tsum) {
+  __shared__ double red[2][8][TS_ROWS];
+  const long long chain = blockIdx.x;
+  const int r = threadIdx.x % TS_ROWS, sl = threadIdx.x / TS_ROWS;
+  const long long row = (long long)blockIdx.y * TS_ROWS + r;
+  const double* base = draws + (size_t)chain * (size_t)iters * (size_t)rows;
+  double s = 0.0, st = 0.0;
+  if (row < rows)
+    for (long long t = sl; t < iters; t += 8) {
+      const double v = base[(size_t)t * (size_t)rows + row];
+      s += v;
+      st = fma((double)t, v, st);
+    }
+  red[0][sl][r] = s; red[1][sl][r] = st;
+  __syncthreads();
+  if (sl == 0 && row < rows) {
+    double a = 0.0, b = 0.0;
+    for (int j = 0; j < 8; ++j) { a += red[0][j][r]; b += red[1][j][r]; }
+    sums[(size_t)chain * rows + row] = a;
+    tsum[(size_t)chain * rows + row] = b;
+  }
+}
+
+// acov[chain][row][l] = (1/n) sum_{t < n - l} (x_t - m)(x_{t+l} - m),  l = 0..L
+__global__ void __launch_bounds__(256) tsse_acov_kernel(const double* __restrict__ draws, long long iters, long long rows,
+                                                        int L, const double* __restrict__ sums, double* __restrict__ acov) {
+  extern __shared__ double ts_sm[];                      // [(TS_SEG + halo)][TS_ROWS], then the slice reduction buffer
+  const int nlg = (L + TS_LG) / TS_LG;                   // lag groups of 8
+  const int halo = nlg * TS_LG;
+  const int items = TS_ROWS * nlg;                       // <= 256
+  const int slices = 256 / items;
+  const long long chain = blockIdx.x;
+  const long long row0 = (long long)blockIdx.y * TS_ROWS;
+  const double* base = draws + (size_t)chain * (size_t)iters * (size_t)rows;
+  const int item = threadIdx.x % items, sl = threadIdx.x / items;
+  const int r = item % TS_ROWS, lg = item / TS_ROWS;
+  const bool worker = sl < slices;
+  const int lr = threadIdx.x % TS_ROWS;
+  const double mean = (row0 + lr < rows) ? sums[(size_t)chain * rows + row0 + lr] / (double)iters : 0.0;
+  double acc[TS_LG];
+#pragma unroll
+  for (int j = 0; j < TS_LG; ++j) acc[j] = 0.0;
+  for (long long t0 = 0; t0 < iters; t0 += TS_SEG) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < (TS_SEG + halo) * TS_ROWS; idx += 256) {
+      const long long t = t0 + idx / TS_ROWS;            // idx % TS_ROWS == lr (256 is a multiple of 32)
+      double v = 0.0;
+      if (t < iters && row0 + lr < rows) v = base[(size_t)t * (size_t)rows + row0 + lr] - mean;
+      ts_sm[idx] = v;
+    }
+    __syncthreads();
+    if (worker) {
+      const double* col = ts_sm + r + (size_t)lg * TS_LG * TS_ROWS;
+      for (int t = sl; t < TS_SEG; t += slices) {
+        const double a = ts_sm[t * TS_ROWS + r];
+        const double* c = col + t * TS_ROWS;
+#pragma unroll
+        for (int j = 0; j < TS_LG; ++j) acc[j] = fma(a, c[j * TS_ROWS], acc[j]);
+      }
+    }
+  }
+  __syncthreads();
+  double* red = ts_sm;                                   // [slices][items][TS_LG]
+  if (worker)
+#pragma unroll
+    for (int j = 0; j < TS_LG; ++j) red[((size_t)sl * items + item) * TS_LG + j] = acc[j];
+  __syncthreads();
+  if (sl == 0 && row0 + r < rows) {
+#pragma unroll
+    for (int j = 0; j < TS_LG; ++j) {
+      const int l = lg * TS_LG + j;
+      if (l > L) break;
+      double s = 0.0;
+      for (int q = 0; q < slices; ++q) s += red[((size_t)q * items + item) * TS_LG + j];
+      acov[((size_t)chain * rows + row0 + r) * (size_t)(L + 1) + l] = s / (double)iters;
+    }
+  }
+}
+
+// spec[chain][row] = var.pred / (1 - sum ar)^2 of the AIC-selected Yule-Walker fit (0 for a degenerate series)
+__global__ void tsse_spec_kernel(long long n_series, long long iters, int L, const double* __restrict__ sums,
+                                 const double* __restrict__ tsum, const double* __restrict__ acov,
+                                 double* __restrict__ spec) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_series) return;
+  const double n = (double)iters;
+  const double* r = acov + (size_t)e * (size_t)(L + 1);
+  // residual sd of lm(x ~ t): SSR = n c0 - Sxy^2 / Sxx
+  const double tbar = 0.5 * (n - 1.0);
+  const double sxy = tsum[e] - tbar * sums[e];
+  const double sxx = n * (n * n - 1.0) / 12.0;
+  double ssr = n * r[0] - ((sxx > 0.0) ? sxy * sxy / sxx : 0.0);
+  if (ssr < 0.0) ssr = 0.0;
+  if (iters < 2 || sqrt(ssr / (n - 1.0)) < 1.5e-8) { spec[e] = 0.0; return; }
+  double phi[TS_MAXLAG + 1], prev[TS_MAXLAG + 1];
+  double v = r[0];
+  double best_aic = n * log(v) + 2.0, best_v = v, best_sum = 0.0;
+  int best_m = 0;
+  for (int m = 1; m <= L; ++m) {
+    double num = r[m];
+    for (int j = 1; j < m; ++j) num = fma(-prev[j], r[m - j], num);
+    const double kappa = num / v;
+    for (int j = 1; j < m; ++j) phi[j] = fma(-kappa, prev[m - j], prev[j]);
+    phi[m] = kappa;
+    v *= (1.0 - kappa * kappa);
+    double sum = 0.0;
+    for (int j = 1; j <= m; ++j) { prev[j] = phi[j]; sum += phi[j]; }
+    const double aic = n * log(v) + 2.0 * m + 2.0;
+    if (aic < best_aic) { best_aic = aic; best_v = v; best_sum = sum; best_m = m; }   // NaN never wins (nanargmin)
+  }
+  const double var_pred = best_v * n / (n - (double)(best_m + 1));
+  const double d = 1.0 - best_sum;
+  spec[e] = var_pred / (d * d);
+}
+
+__global__ void tsse_combine_kernel(long long n_chains, long long iters, long long rows, const double* __restrict__ spec,
+                                    double* __restrict__ out) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  double s = 0.0;
+  for (long long c = 0; c < n_chains; ++c) s += spec[(size_t)c * rows + row];
+  out[row] = sqrt(s / (double)n_chains / ((double)iters * (double)n_chains));
+}
+
+// d_out[rows] (device) <- time-series SE of draws [n_chains][iters][rows] (device)
+cudaError_t launch_tsse(const double* draws, long long n_chains, long long iters, long long rows, double* d_out,
+                        cudaStream_t stream) {
+  if (n_chains < 1 || iters < 1 || rows < 1) return cudaErrorInvalidValue;
+  int L = (int)floor(10.0 * log10((double)iters));
+  if ((long long)L > iters - 1) L = (int)(iters - 1);
+  if (L > TS_MAXLAG) return cudaErrorInvalidValue;
+  const long long tiles = (rows + TS_ROWS - 1) / TS_ROWS;
+  if (n_chains > 0x7fffffffLL || tiles > 65535) return cudaErrorInvalidValue;
+  const size_t ns = (size_t)n_chains * (size_t)rows;
+  double *sums = nullptr, *tsum = nullptr, *acov = nullptr, *spec = nullptr;
+  cudaError_t e;
+  if ((e = cudaMallocAsync((void**)&sums, ns * 8, stream)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&tsum, ns * 8, stream)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&spec, ns * 8, stream)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&acov, ns * (size_t)(L + 1) * 8, stream)) != cudaSuccess) return e;
+  const dim3 grid((unsigned)n_chains, (unsigned)tiles);
+  tsse_mean_kernel<<<grid, 256, 0, stream>>>(draws, iters, rows, sums, tsum);
+  const int nlg = (L + TS_LG) / TS_LG;
+  size_t smem = (size_t)(TS_SEG + nlg * TS_LG) * TS_ROWS * 8;
+  const size_t red = (size_t)256 * TS_LG * 8;
+  if (red > smem) smem = red;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tsse_acov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr_set = true;
+  }
+  tsse_acov_kernel<<<grid, 256, smem, stream>>>(draws, iters, rows, L, sums, acov);
+  tsse_spec_kernel<<<(unsigned)((ns + 127) / 128), 128, 0, stream>>>((long long)ns, iters, L, sums, tsum, acov, spec);
+  tsse_combine_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(n_chains, iters, rows, spec, d_out);
+  e = cudaGetLastError();
+  cudaFreeAsync(sums, stream); cudaFreeAsync(tsum, stream); cudaFreeAsync(spec, stream); cudaFreeAsync(acov, stream);
+  return e;
+}
+
 }  // namespace bvg

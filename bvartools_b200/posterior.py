@@ -105,15 +105,32 @@ def draw_posterior(obj, FUN=None, mc_cores=None, seed=None, **kw):
     return out[0] if only_one else out
 
 
-def summary(obj, ci=(0.025, 0.5, 0.975)):
-    """Posterior means, SDs and quantiles of a `bvar` object (R/summary.bvar.R:121-140)."""
+def summary(obj, ci=(0.025, 0.5, 0.975), n_chains=1):
+    """Posterior means, SDs, naive and time-series SEs and quantiles of a `bvar` object (R/summary.bvar.R:121-140,
+    185-203, i.e. coda::summary.mcmc per draw matrix).  The draw matrices are uploaded once and reduced on the device
+    (bvg_summary_draws: exact type-7 quantiles; bvg_tsse_draws: spectrum0.ar).  n_chains: the draws are `n_chains`
+    equally long chains stacked chain-major (1 = a single chain, as in the reference)."""
+    import torch
+    require_device()
+    dp = C.POINTER(C.c_double)
+    probs = np.ascontiguousarray(ci, dtype=np.float64)
     res = {}
-    for name in ("A", "B", "C", "Sigma"):
+    for name in ("A0", "A", "B", "C", "Sigma"):
         d = obj.get(name)
         if d is None or isinstance(d, list):
             continue
-        res[name] = {"mean": d.mean(axis=0), "sd": d.std(axis=0, ddof=1),
-                     "quantiles": np.quantile(d, ci, axis=0)}
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        n, rows = d.shape
+        dev = torch.from_numpy(d).cuda()
+        mean, sd, q = np.empty(rows), np.empty(rows), np.empty((probs.size, rows))
+        check(lib().bvg_summary_draws(C.c_void_p(dev.data_ptr()), n, rows, probs.ctypes.data_as(dp), probs.size,
+                                      mean.ctypes.data_as(dp), sd.ctypes.data_as(dp), q.ctypes.data_as(dp), None))
+        res[name] = {"mean": mean, "sd": sd, "naive_se": sd / np.sqrt(n), "quantiles": q}
+        if n % n_chains == 0 and n // n_chains >= 3:
+            ts = np.empty(rows)
+            check(lib().bvg_tsse_draws(C.c_void_p(dev.data_ptr()), n_chains, n // n_chains, rows,
+                                       ts.ctypes.data_as(dp), None))
+            res[name]["ts_se"] = ts
     return res
 
 

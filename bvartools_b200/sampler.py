@@ -120,11 +120,12 @@ class ChainSampler:
 
     _WHICH = {"coef": 0, "sigma": 1, "lambda": 2, "sigma_h": 3, "sigma_v": 4}
 
-    def summary(self, which="coef", ci=0.95, probs=None, stream=0):
+    def summary(self, which="coef", ci=0.95, probs=None, stream=0, ts_se=True):
         """Posterior summary of one output over ALL retained draws resident on the device (chains x iterations), as
         summary.bvar / coda::summary.mcmc report them (R/summary.bvar.R:110-140): mean, sd, naive_se and the quantiles
-        (ci_low, 0.5, ci_high) of R's type 7 -- exact order statistics from a radix select in HBM.  For `lambda` the
-        mean is the posterior inclusion frequency."""
+        (ci_low, 0.5, ci_high) of R's type 7 -- exact order statistics from a radix select in HBM -- and ts_se, coda's
+        time-series SE (AR spectral estimate at frequency zero per chain).  For `lambda` the mean is the posterior
+        inclusion frequency."""
         if probs is None:
             lo = (1.0 - ci) / 2.0
             probs = (lo, 0.5, 1.0 - lo)
@@ -137,7 +138,19 @@ class ChainSampler:
                                         mean.ctypes.data_as(dp), sd.ctypes.data_as(dp), q.ctypes.data_as(dp),
                                         C.c_void_p(stream or 0)))
         n = int(self.spec.c.n_chains) * int(self.spec.c.iterations)
-        return {"mean": mean, "sd": sd, "naive_se": sd / np.sqrt(n), "quantiles": q, "probs": probs, "n": n}
+        res = {"mean": mean, "sd": sd, "naive_se": sd / np.sqrt(n), "quantiles": q, "probs": probs, "n": n}
+        if ts_se and int(self.spec.c.iterations) >= 3:
+            res["ts_se"] = self.time_series_se(which, stream)
+        return res
+
+    def time_series_se(self, which="coef", stream=0):
+        """coda's "Time-series SE" of one output (R/summary.bvar.R:133,141): spectrum0.ar -- an AIC-selected
+        Yule-Walker AR fit -- per chain and row on the device, pooled over the chains as summary.mcmc.list does."""
+        rows = int(self.spec.out_rows()[which])
+        ts = np.empty(rows)
+        check(lib().bvg_sampler_tsse(self.handle, self._WHICH[which], ts.ctypes.data_as(C.POINTER(C.c_double)),
+                                     C.c_void_p(stream or 0)))
+        return ts
 
     def irf(self, impulse, response, n_ahead=5, ci=0.95, shock=1, type="feir", cumulative=False, keep_draws=False,
             period=None, p=None, stream=0):

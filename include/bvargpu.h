@@ -224,12 +224,22 @@ int bvg_loglik_normal(const double* u, const double* sigma, int32_t k, int32_t T
  * SD / sqrt(N) follows) and the quantiles, R's default type 7 -- exact order statistics by an 8-pass radix select on the
  * device -- pooled over all n_draws draws of the buffer [n_draws][rows] (device pointer).  Inclusion frequencies are
  * the means of the lambda buffer.  mean, sd: rows doubles; quantiles: [n_probs][rows]; host pointers (mean / sd may be
- * NULL).  The time-series SE of coda (spectrum0.ar) is not computed. */
+ * NULL).  The time-series SE is a separate call: bvg_tsse_draws. */
 int bvg_summary_draws(const double* dev_draws, int64_t n_draws, int64_t rows, const double* probs, int32_t n_probs,
                       double* mean, double* sd, double* quantiles, void* cuda_stream);
 /* the same for an output of a sampler: which = 0 coef, 1 sigma, 2 lambda, 3 sigma_h, 4 sigma_v */
 int bvg_sampler_summary(bvg_sampler* s, int32_t which, const double* probs, int32_t n_probs, double* mean, double* sd,
                         double* quantiles, void* cuda_stream);
+
+/* Time-series SE of coda::summary.mcmc (the column summary.bvar copies at R/summary.bvar.R:133,141,195,203): coda's
+ * spectrum0.ar -- Yule-Walker AR fit with AIC order selection (stats::ar.yw, order.max = min(n - 1, floor(10 log10 n)))
+ * per chain and row, spec = var.pred / (1 - sum ar)^2 (0 when the residuals of lm(x ~ time) vanish) -- and, as in
+ * summary.mcmc.list, tsse[row] = sqrt(mean_chains spec / (iters n_chains)).  dev_draws: [n_chains][iters][rows] on the
+ * device; tsse: rows doubles on the host.  coda is not vendored by the reference: see oracle/blocks.py spectrum0_ar. */
+int bvg_tsse_draws(const double* dev_draws, int64_t n_chains, int64_t iters, int64_t rows, double* tsse,
+                   void* cuda_stream);
+/* the same for an output of a sampler (which as in bvg_sampler_summary) */
+int bvg_sampler_tsse(bvg_sampler* s, int32_t which, double* tsse, void* cuda_stream);
 
 /* ---- impulse responses per draw --------------------------------------------------------------------
  * Replaces the per-draw loop of irf.bvar (R/irf.bvar.R:140-216) around .ir (src/ir.cpp:4-72): for every draw

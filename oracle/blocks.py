@@ -293,6 +293,52 @@ def summary_bvarlist_row(y, x, temp_pars, sigma_draws, tvp=False, sv=False):
             "HQ": 2 * np.log(np.log(tt)) * tot_pars - 2 * ll, "ll_t": LL.mean(axis=1)}
 
 
+def spectrum0_ar(x):
+    """coda::spectrum0.ar for ONE series (the time-series SE of coda::summary.mcmc, which summary.bvar reports:
+    R/summary.bvar.R:133,141,195,203).  PARITY UNPINNED: coda (CRAN, un-vendored; DESCRIPTION Imports: coda) and
+    stats::ar.yw are absent here; this restates their published algorithm --
+      * if the residuals of lm(x ~ 1:n) have sd < 1.5e-8 (all.equal to 0) the spectrum is 0;
+      * otherwise ar(x, aic = TRUE) by Yule-Walker: order.max = min(n - 1, floor(10 log10 n)), autocovariances with
+        divisor n around the sample mean, Levinson-Durbin recursion, AIC_m = n log(v_m) + 2 m + 2, first minimiser,
+        var.pred = v_m n / (n - (m + 1)), and spec = var.pred / (1 - sum(ar))^2.
+    Returns (spec, order)."""
+    x = np.asarray(x, dtype=float).reshape(-1)
+    n = x.size
+    z = np.arange(1, n + 1, dtype=float)
+    zc = z - z.mean()
+    xc = x - x.mean()
+    resid = xc - zc * (zc @ xc) / (zc @ zc)
+    if n < 2 or np.sqrt(resid @ resid / (n - 1)) < 1.5e-8:
+        return 0.0, 0
+    L = min(n - 1, int(np.floor(10.0 * np.log10(n))))
+    r = np.array([xc[:n - l] @ xc[l:] / n for l in range(L + 1)])
+    v = np.empty(L + 1)
+    v[0] = r[0]
+    coefs = [np.zeros(0)]
+    phi = np.zeros(0)
+    for m in range(1, L + 1):
+        kappa = (r[m] - phi @ r[m - 1:0:-1]) / v[m - 1] if m > 1 else r[1] / v[0]
+        phi = np.concatenate([phi - kappa * phi[::-1], [kappa]])
+        v[m] = v[m - 1] * (1.0 - kappa * kappa)
+        coefs.append(phi.copy())
+    with np.errstate(divide="ignore", invalid="ignore"):
+        aic = n * np.log(v) + 2.0 * np.arange(L + 1) + 2.0
+    order = int(np.nanargmin(aic))
+    var_pred = v[order] * n / (n - (order + 1))
+    return float(var_pred / (1.0 - coefs[order].sum()) ** 2), order
+
+
+def time_series_se(draws, n_chains):
+    """coda::summary.mcmc.list: draws [n_chains * iters][rows] (chain-major) -> sqrt(mean_c spec0_c / (iters n_chains));
+    one chain gives summary.mcmc's sqrt(spec0 / iters)."""
+    d = np.asarray(draws, dtype=float)
+    rows = d.shape[1]
+    it = d.shape[0] // n_chains
+    d = d.reshape(n_chains, it, rows)
+    spec = np.array([[spectrum0_ar(d[c, :, r])[0] for r in range(rows)] for c in range(n_chains)])
+    return np.sqrt(spec.mean(axis=0) / (it * n_chains))
+
+
 def ir(A, Sigma, h, type, impulse, response, shock=1.0):
     """src/ir.cpp:4-72, literally (full Phi matrices): A is k x (k p), impulse / response 1-based as in R."""
     coef = np.asarray(A, dtype=float)
