@@ -19,7 +19,7 @@ from . import sampler
 from ._lib import check, lib, require_device
 
 __all__ = ["draw_posterior", "bvarpost", "bvar", "summary", "summary_bvarlist", "information_criteria", "thin", "irf",
-           "fevd"]
+           "fevd", "predict"]
 
 
 def bvar(y, x=None, A0=None, A=None, B=None, C=None, Sigma=None):
@@ -291,4 +291,72 @@ def fevd(obj, response, n_ahead=5, type="oir", normalise_gir=False, period=None)
                                types[type], int(response), int(bool(normalise_gir)),
                                out.ctypes.data_as(C.POINTER(C.c_double)), None))
     return out
+
+
+def predict(obj, n_ahead=10, new_x=None, new_d=None, ci=0.95, seed=None, eps=None, keep_draws=False, period=None):
+    """predict.bvar (R/predict.bvar.R:36-260) for a host `bvar` object: the prediction matrix is built as in :176-201
+    (last p observations of y; `new_x` / `new_d` future exogenous / deterministic values, zeros when omitted as in the
+    reference), the draws cbind(A, B, C) and Sigma are uploaded once and every draw is simulated forward on the device
+    (bvg_forecast_draws).  Returns {variable index: (n_ahead x 3) bands} or the draws [draws][n_ahead][k]."""
+    import torch
+    from .sampler import _seed
+    require_device()
+    y = np.asarray(obj["y"], dtype=np.float64)
+    tt, k = y.shape
+    pick = lambda d: d[tt - 1 if period is None else period]
+    parts = []
+    for name in ("A", "B", "C"):
+        d = obj.get(name)
+        if d is not None:
+            parts.append(np.asarray(pick(d) if isinstance(d, list) else d, dtype=np.float64))
+    if not parts:
+        raise ValueError("Argument 'object' must contain draws of at least one of 'A', 'B' or 'C'.")
+    S = obj.get("Sigma")
+    if S is None:
+        raise ValueError("Argument 'object' must include draws of the variance-covariance matrix Sigma.")
+    S = np.ascontiguousarray(pick(S) if isinstance(S, list) else S, dtype=np.float64)
+    coef = np.ascontiguousarray(np.concatenate(parts, axis=1))
+    draws = coef.shape[0]
+    A = obj.get("A")
+    p = 0 if A is None else (A[0] if isinstance(A, list) else np.asarray(A)).shape[1] // (k * k)
+    n_x = coef.shape[1] // k - k * p
+    x = None if obj.get("x") is None else np.asarray(obj["x"], dtype=np.float64)
+    n_det = 0 if new_d is None and new_x is not None else n_x
+    if new_x is not None:
+        new_x = np.atleast_2d(np.asarray(new_x, dtype=np.float64))
+        n_det = n_x - new_x.shape[1]
+    ylen = k * p if p > 0 else k
+    tot = ylen + n_x
+    pred = np.zeros((tot, n_ahead + 1))
+    pred[:ylen, 0] = y[tt - 1::-1][:p].reshape(-1) if p > 0 else y[tt - 1]
+    if n_x > 0:
+        pred[ylen:, 0] = x[tt - 1, k * p:]
+        fut = np.zeros((n_ahead, n_x))
+        if new_x is not None:
+            if new_x.shape[0] < n_ahead:
+                raise ValueError("Longer time series required for argument 'new_x'.")
+            fut[:, :new_x.shape[1]] = new_x[:n_ahead]
+        if new_d is not None:
+            new_d = np.asarray(new_d, dtype=np.float64).reshape(-1, n_det)
+            if new_d.shape[0] != n_ahead:
+                raise ValueError("Length of argument 'new_d' must be equal to 'n.ahead'.")
+            fut[:, n_x - n_det:] = new_d
+        pred[ylen:, 1:] = fut.T
+    predf = np.ascontiguousarray(pred.reshape(-1, order="F"))
+    dA, dS = torch.from_numpy(coef).cuda(), torch.from_numpy(S).cuda()
+    dE = None if eps is None else torch.from_numpy(np.ascontiguousarray(eps, dtype=np.float64)).cuda()
+    out = torch.empty((draws, n_ahead, k), dtype=torch.float64, device="cuda")
+    vp, dp = C.c_void_p, C.POINTER(C.c_double)
+    check(lib().bvg_forecast_draws(vp(dA.data_ptr()), coef.shape[1], vp(dS.data_ptr()), k * k, draws, k, p, tot,
+                                   int(n_ahead), predf.ctypes.data_as(dp), None if dE is None else vp(dE.data_ptr()),
+                                   _seed(seed), vp(out.data_ptr()), None))
+    if keep_draws:
+        return out.cpu().numpy()
+    lo = (1.0 - ci) / 2.0
+    probs = np.ascontiguousarray([lo, 0.5, 1.0 - lo])
+    q = np.empty((3, n_ahead * k))
+    check(lib().bvg_summary_draws(vp(out.data_ptr()), draws, n_ahead * k, probs.ctypes.data_as(dp), 3, None, None,
+                                  q.ctypes.data_as(dp), None))
+    q = q.reshape(3, n_ahead, k)
+    return {i: q[:, :, i].T for i in range(k)}
 

@@ -65,3 +65,28 @@ def test_forecast_matches_oracle(gpu, case):
     f2 = s.predict(n_ahead=h, new_d=new_d, seed=5, keep_draws=True)
     assert np.isfinite(f1).all() and np.array_equal(f1, f2)
     s.close()
+
+
+def test_predict_of_a_host_bvar_object(gpu):
+    """Package-level predict() on a `bvar` object (draws on the host, as predict.bvar receives them)."""
+    import bvartools_b200 as bt
+    obj = helpers.model_c1(iterations=40, burnin=5)
+    fit = bt.draw_posterior(obj, seed=6)
+    Y = obj["data"]["Y"]
+    T, k = Y.shape
+    h = 5
+    coef = np.concatenate([np.asarray(fit[n]) for n in ("A", "B", "C") if fit.get(n) is not None], axis=1)
+    p = np.asarray(fit["A"]).shape[1] // (k * k)
+    sig = np.asarray(fit["Sigma"])
+    eps = np.random.default_rng(8).standard_normal((coef.shape[0], h, k))
+    new_d = np.ones(h)
+    got = bt.predict(fit, n_ahead=h, new_d=new_d, eps=eps, keep_draws=True)
+    pred = _pred_matrix(obj, p, h, new_d)
+    want = np.empty_like(got)
+    for d in range(coef.shape[0]):
+        want[d] = ob.draw_forecast(coef[d].reshape(k, -1, order="F"), sig[d].reshape(k, k, order="F"), pred, k, p,
+                                   eps[d])[:k, 1:].T
+    assert helpers.relerr(got, want) < TOL
+    bands = bt.predict(fit, n_ahead=h, new_d=new_d, eps=eps, ci=0.9)
+    for i in range(k):
+        np.testing.assert_allclose(bands[i], np.quantile(want[:, :, i], [0.05, 0.5, 0.95], axis=0).T, rtol=1e-10, atol=1e-13)
