@@ -266,6 +266,7 @@ cudaError_t plan_bvar_kron(const BvarModel& m, long long n_chains, int requested
   const int k = m.k, M = m.M, KU = (k * (k + 1)) / 2;
   const int VL = kron_variates_len(k, M) | 1;            // odd stride: the threads of phase B hit different banks
   int NB = 8;
+  while (NB < 64 && CH * NB < 448) NB <<= 1;      // few chains per CTA: longer rounds keep >= 448 (chain, sweep) items per round
   auto bytes = [&](int nb) {
     return ((size_t)kron_consts_len(k, M) + 2 * (size_t)nb * CH * VL + (size_t)(nb + 1) * CH * KU) * 8;
   };
