@@ -221,6 +221,8 @@ def run_grid(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        from bvartools_b200.distributed import bind_to_gpu_numa
+        bind_to_gpu_numa(local_rank)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     it = args.iterations or 5000
@@ -393,6 +395,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        from bvartools_b200.distributed import bind_to_gpu_numa
+        bind_to_gpu_numa(local_rank)          # pinned output buffers on the GPU's own NUMA node
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     L = lib()

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["shard", "shard_weighted", "model_cost", "run_sharded", "allreduce_moments", "gather_draws",
+__all__ = ["shard", "shard_weighted", "model_cost", "run_sharded", "allreduce_moments", "gather_draws", "bind_to_gpu_numa",
            "allreduce_information_criteria"]
 
 
@@ -48,6 +48,22 @@ def shard_weighted(costs, world: int):
         bounds.append(max(bounds[-1], min(idx, len(costs))))
     bounds.append(len(costs))
     return [(bounds[r], bounds[r + 1] - bounds[r]) for r in range(world)]
+
+
+def bind_to_gpu_numa(device: int = 0) -> bool:
+    """Pin the calling process to the CPU cores nearest to CUDA device `device` (NVML's ideal affinity), so that the
+    pinned host buffers the draws are copied into are first-touched on that GPU's NUMA node.  One rank per GPU: call it
+    before allocating the output buffers.  Returns False (and changes nothing) when NVML is unavailable."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device)
+        bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode()))
+        return True
+    except Exception:
+        return False
 
 
 def _dist():
