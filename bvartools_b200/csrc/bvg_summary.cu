@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256) tsse_acov_kernel(const double* __restrict
   const int nlg = (L + TS_LG) / TS_LG;                   // lag groups of 8
   const int halo = nlg * TS_LG;
   const int items = TS_ROWS * nlg;                       // <= 256
-  const int slices = 256 / items;
+  const int slices = (nlg <= 1) ? 8 : (nlg == 2) ? 4 : (nlg <= 4) ? 2 : 1;   // power of two, slices * items <= 256
   const long long chain = blockIdx.x;
   const long long row0 = (long long)blockIdx.y * TS_ROWS;
   const double* base = draws + (size_t)chain * (size_t)iters * (size_t)rows;
@@ -333,12 +333,21 @@ __global__ void __launch_bounds__(256) tsse_acov_kernel(const double* __restrict
     }
     __syncthreads();
     if (worker) {
-      const double* col = ts_sm + r + (size_t)lg * TS_LG * TS_ROWS;
-      for (int t = sl; t < TS_SEG; t += slices) {
-        const double a = ts_sm[t * TS_ROWS + r];
-        const double* c = col + t * TS_ROWS;
+      // a slice owns span consecutive periods (a multiple of 8): per block of 8 periods the 8 values x_t and the 15
+      // lagged values x_{t+l0 .. t+l0+14} are read once into registers and feed 64 FMAs
+      const int span = TS_SEG / slices;
+      const double* xr = ts_sm + r;
+      const int l0 = lg * TS_LG;
+      for (int t = sl * span; t < (sl + 1) * span; t += 8) {
+        double a[8], w[15];
 #pragma unroll
-        for (int j = 0; j < TS_LG; ++j) acc[j] = fma(a, c[j * TS_ROWS], acc[j]);
+        for (int i = 0; i < 8; ++i) a[i] = xr[(t + i) * TS_ROWS];
+#pragma unroll
+        for (int i = 0; i < 15; ++i) w[i] = xr[(t + l0 + i) * TS_ROWS];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < TS_LG; ++j) acc[j] = fma(a[i], w[i + j], acc[j]);
       }
     }
   }
@@ -396,13 +405,20 @@ __global__ void tsse_spec_kernel(long long n_series, long long iters, int L, con
   spec[e] = var_pred / (d * d);
 }
 
-__global__ void tsse_combine_kernel(long long n_chains, long long iters, long long rows, const double* __restrict__ spec,
-                                    double* __restrict__ out) {
-  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= rows) return;
+// one CTA of 128 threads per row; fixed summation order (strided partial sums, then a tree): deterministic
+__global__ void __launch_bounds__(128) tsse_combine_kernel(long long n_chains, long long iters, long long rows,
+                                                           const double* __restrict__ spec, double* __restrict__ out) {
+  __shared__ double part[128];
+  const long long row = blockIdx.x;
   double s = 0.0;
-  for (long long c = 0; c < n_chains; ++c) s += spec[(size_t)c * rows + row];
-  out[row] = sqrt(s / (double)n_chains / ((double)iters * (double)n_chains));
+  for (long long c = threadIdx.x; c < n_chains; c += 128) s += spec[(size_t)c * rows + row];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 64; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) part[threadIdx.x] += part[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[row] = sqrt(part[0] / (double)n_chains / ((double)iters * (double)n_chains));
 }
 
 // d_out[rows] (device) <- time-series SE of draws [n_chains][iters][rows] (device)
@@ -434,7 +450,7 @@ cudaError_t launch_tsse(const double* draws, long long n_chains, long long iters
   }
   tsse_acov_kernel<<<grid, 256, smem, stream>>>(draws, iters, rows, L, sums, acov);
   tsse_spec_kernel<<<(unsigned)((ns + 127) / 128), 128, 0, stream>>>((long long)ns, iters, L, sums, tsum, acov, spec);
-  tsse_combine_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(n_chains, iters, rows, spec, d_out);
+  tsse_combine_kernel<<<(unsigned)rows, 128, 0, stream>>>(n_chains, iters, rows, spec, d_out);
   e = cudaGetLastError();
   cudaFreeAsync(sums, stream); cudaFreeAsync(tsum, stream); cudaFreeAsync(spec, stream); cudaFreeAsync(acov, stream);
   return e;
