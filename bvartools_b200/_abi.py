@@ -21,7 +21,8 @@ _ip = C.POINTER(C.c_int32)
 
 INJECT_FIELDS = ["coef_normal", "ssvs_u", "bvs_u1", "bvs_u2", "sv_u", "sv_normal", "sigma_h_gamma",
                  "h_init_normal", "omega_gamma", "wishart_chi2", "wishart_normal", "state_normal",
-                 "sigma_v_gamma", "a_init_normal", "psi_normal", "psi_u1", "psi_u2"]
+                 "sigma_v_gamma", "a_init_normal", "psi_normal", "psi_u1", "psi_u2", "psi_sigma_v_gamma",
+                 "psi_init_normal"]
 
 
 class BvgInject(C.Structure):
@@ -42,7 +43,7 @@ class BvgSpec(C.Structure):
         ("sv_constant", _dp), ("sv_h", _dp), ("sv_mixture", C.c_int32), ("sigma_i", _dp),
         ("tvp_shape", _dp), ("tvp_rate", _dp), ("a_init", _dp), ("psi_mu", _dp), ("psi_vi", _dp),
         ("psi_varsel", C.c_int32), ("psi_tau0", _dp), ("psi_tau1", _dp), ("psi_inprior", _dp), ("psi_include", _ip),
-        ("psi_n_include", C.c_int32),
+        ("psi_n_include", C.c_int32), ("psi_shape", _dp), ("psi_rate", _dp), ("psi_init", _dp),
         ("resid_mode", C.c_int32), ("threads_per_chain", C.c_int32), ("sweeps_per_launch", C.c_int32),
         ("inject", C.POINTER(BvgInject)),
     ]
@@ -87,9 +88,10 @@ class Spec:
         """rows per retained draw of (coef, sigma, lambda, sigma_h, sigma_v) -- mirrors bvg_out_rows()."""
         k, T, n = self.c.k, self.c.T, self.n
         sv = self.c.sigma_type == SIGMA_SV
+        tv_sigma = sv or (bool(self.c.tvp) and bool(self.c.psi_mu))      # TVP + covariance block: Sigma_t per period
         return {
             "coef": n * T if self.c.tvp else n,
-            "sigma": k * k * T if sv else k * k,
+            "sigma": k * k * T if tv_sigma else k * k,
             "lambda": (n if self.c.varsel != VARSEL_NONE else 0) +
                       (k * (k - 1) // 2 if self.c.psi_varsel != VARSEL_NONE else 0),
             "sigma_h": k if sv else 0,
@@ -103,8 +105,9 @@ def spec_from_model(obj, n_chains=1, seed=0, chain_offset=0, device=-1, resid_mo
     data, model, priors, initial = obj["data"], obj["model"], obj["priors"], obj["initial"]
     if model.get("structural"):
         raise NotImplementedError("structural models are not on the accelerated path (SURVEY.md section 8f-4)")
-    if "psi" in priors and model.get("tvp"):
-        raise NotImplementedError("the covariance (psi) block of TVP models is not on the accelerated path (SURVEY.md 8f-4)")
+    if "psi" in priors and model.get("tvp") and ("bvs" in priors["psi"] or "bvs" in priors.get("coefficients", {})):
+        raise NotImplementedError("BVS together with the covariance (psi) block of a TVP model is not on the "
+                                  "accelerated path (bvartvpalg.cpp:365-398; SURVEY.md 8f-4)")
     Y = np.asarray(data["Y"], dtype=np.float64)          # T x k
     T, k = Y.shape
     Z = data.get("Z")
@@ -176,6 +179,10 @@ def spec_from_model(obj, n_chains=1, seed=0, chain_offset=0, device=-1, resid_mo
     if "psi" in priors:                                   # covariance block (bvaralg.cpp:157-162)
         sp.set("psi_mu", _f(priors["psi"]["mu"]))
         sp.set("psi_vi", _f(np.asarray(priors["psi"]["v_i"], dtype=np.float64)))
+        if model.get("tvp"):                              # bvartvpalg.cpp:147-150,169
+            sp.set("psi_shape", _f(priors["psi"]["shape"]))
+            sp.set("psi_rate", _f(priors["psi"]["rate"]))
+            sp.set("psi_init", _f(initial["psi"]["draw"]))
         psel = None
         if "ssvs" in priors["psi"]:
             c.psi_varsel = VARSEL_SSVS

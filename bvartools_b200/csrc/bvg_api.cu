@@ -67,12 +67,15 @@ struct bvg_sampler {
   char kernel_name[64] = {0};
 };
 
+// Sigma is stored per period with stochastic volatility and for TVP models with the covariance block (bvartvpalg.cpp:505)
+static inline bool tv_sigma_of(const Prepared& P) { return P.sigma_type == BVG_SIGMA_SV || (P.tvp && P.n_psi > 0); }
+
 static void rows_of(const Prepared& P, long long* coef, long long* sigma, long long* lambda, long long* sh,
                     long long* sv) {
   const long long k = P.k, T = P.T, n = P.n;
   const bool svm = P.sigma_type == BVG_SIGMA_SV;
   *coef = P.tvp ? n * T : n;
-  *sigma = svm ? k * k * T : k * k;
+  *sigma = tv_sigma_of(P) ? k * k * T : k * k;
   *lambda = ((P.varsel != BVG_VARSEL_NONE) ? n : 0) + ((P.psi_varsel != BVG_VARSEL_NONE) ? k * (k - 1) / 2 : 0);
   *sh = svm ? k : 0;
   *sv = P.tvp ? n : 0;
@@ -214,8 +217,10 @@ int bvg_sampler_create(const bvg_spec* spec, bvg_sampler** out) {
                                    spec->inject->omega_gamma, spec->inject->wishart_chi2,
                                    spec->inject->wishart_normal, spec->inject->state_normal,
                                    spec->inject->sigma_v_gamma, spec->inject->a_init_normal,
-                                   spec->inject->psi_normal, spec->inject->psi_u1, spec->inject->psi_u2};
-    const int cnt[VB_COUNT] = {n, n, n, n, k * T, k * T, k, k, k, k, k * (k - 1) / 2, n * T, n, n, k * (k - 1) / 2, k * (k - 1) / 2, k * (k - 1) / 2};
+                                   spec->inject->psi_normal, spec->inject->psi_u1, spec->inject->psi_u2,
+                                   spec->inject->psi_sigma_v_gamma, spec->inject->psi_init_normal};
+    const int np = k * (k - 1) / 2;
+    const int cnt[VB_COUNT] = {n, n, n, n, k * T, k * T, k, k, k, k, np, n * T, n, n, P.tvp ? np * T : np, np, np, np, np};
     for (int b = 0; b < VB_COUNT; ++b) {
       if (!ptr[b] || cnt[b] == 0) continue;
       const size_t bytes = (size_t)s->n_chains * s->sweeps * cnt[b] * sizeof(double);
@@ -471,7 +476,7 @@ int bvg_sampler_loglik(bvg_sampler* s, double* host_ll_t, void* cuda_stream) {
   cudaStream_t st = (cudaStream_t)cuda_stream;
   double* d_ll = nullptr;
   CK(cudaMalloc((void**)&d_ll, (size_t)T * sizeof(double)));
-  const int tv_sigma = (s->P.sigma_type == BVG_SIGMA_SV) ? 1 : 0;
+  const int tv_sigma = tv_sigma_of(s->P) ? 1 : 0;
   const BvarModel& bm = s->P.tvp ? s->tm.b : s->bm;          // the TVP sampler keeps its data in the TvpModel
   int rc = bvg_loglik_draws(s->d_coef, s->d_sigma, (int64_t)s->n_chains * s->P.iterations, s->P.k, s->P.M, T, s->P.tvp,
                             tv_sigma, bm.Y, bm.X, d_ll, cuda_stream);
@@ -571,7 +576,7 @@ static bool host_ols_moments(const double* Y, const double* X, int k, int M, int
 int bvg_sampler_loglik_total(bvg_sampler* s, double* total, void* cuda_stream) {
   if (!s || !total) return fail(-1, "sampler / output is NULL");
   CK(cudaSetDevice(s->device));
-  const bool fast = !s->P.tvp && s->P.sigma_type != BVG_SIGMA_SV && s->P.M > 0 && s->bm.XX && s->bm.Aols && s->bm.SSE &&
+  const bool fast = !s->P.tvp && !tv_sigma_of(s->P) && s->P.M > 0 && s->bm.XX && s->bm.Aols && s->bm.SSE &&
                     s->P.k <= 32;
   if (!fast) {                           // time-varying coefficients / variances: per-period kernel, summed on the host
     std::vector<double> ll((size_t)s->P.T);
@@ -792,7 +797,7 @@ int bvg_sampler_irf(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, in
   CK(cudaSetDevice(s->device));
   const int k = s->P.k, T = s->P.T;
   if (p < 0 || (long long)k * k * p > (long long)s->P.n) return fail(-2, "p lags do not fit the coefficient vector");
-  const bool tv_coef = s->P.tvp != 0, tv_sig = s->P.sigma_type == BVG_SIGMA_SV;
+  const bool tv_coef = s->P.tvp != 0, tv_sig = tv_sigma_of(s->P);
   if (tv_coef || tv_sig) {
     if (period < 0) period = T - 1;                                              // R/irf.bvar.R:127-133 (1-based there)
     if (period >= T) return fail(-11, "Implausible specification of argument 'period'.");
@@ -850,7 +855,7 @@ int bvg_sampler_fevd(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, i
   CK(cudaSetDevice(s->device));
   const int k = s->P.k, T = s->P.T;
   if (p < 0 || (long long)k * k * p > (long long)s->P.n) return fail(-2, "p lags do not fit the coefficient vector");
-  const bool tv_coef = s->P.tvp != 0, tv_sig = s->P.sigma_type == BVG_SIGMA_SV;
+  const bool tv_coef = s->P.tvp != 0, tv_sig = tv_sigma_of(s->P);
   if (tv_coef || tv_sig) {
     if (period < 0) period = T - 1;
     if (period >= T) return fail(-11, "Implausible specification of argument 'period'.");
@@ -891,7 +896,7 @@ int bvg_sampler_forecast(bvg_sampler* s, int32_t p, int32_t tot, int32_t n_ahead
   if (!s) return fail(-1, "sampler is NULL");
   CK(cudaSetDevice(s->device));
   const int k = s->P.k, T = s->P.T;
-  const bool tv_coef = s->P.tvp != 0, tv_sig = s->P.sigma_type == BVG_SIGMA_SV;
+  const bool tv_coef = s->P.tvp != 0, tv_sig = tv_sigma_of(s->P);
   const long long nd = (long long)s->n_chains * s->P.iterations;
   const double* coef = s->d_coef + (tv_coef ? (size_t)(T - 1) * s->P.n : 0);      // last period (R/predict.bvar.R:73,85,146)
   const double* sig = s->d_sigma + (tv_sig ? (size_t)(T - 1) * k * k : 0);

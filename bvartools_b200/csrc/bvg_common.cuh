@@ -40,10 +40,12 @@ enum VarBlock : int {
   VB_STATE_N = 11, // N(0,1) x n*T         TVP state path                   bvartvpalg.cpp:297
   VB_SIGV_G = 12,  // Gamma(shape,1) x n   TVP state precisions             bvartvpalg.cpp:476
   VB_AINIT_N = 13, // N(0,1) x n           TVP initial state                bvartvpalg.cpp:482
-  VB_PSI_N = 14,   // N(0,1) x k(k-1)/2    covariance (psi) block           bvaralg.cpp:394
+  VB_PSI_N = 14,   // N(0,1) x k(k-1)/2 (TVP: x T)  covariance (psi) block   bvaralg.cpp:394, bvartvpalg.cpp:363
   VB_PSI_U1 = 15,  // U(0,1) x k(k-1)/2    SSVS Bernoulli / BVS gate on psi bvaralg.cpp:409,424
   VB_PSI_U2 = 16,  // U(0,1) x k(k-1)/2    BVS acceptance on psi            bvaralg.cpp:437
-  VB_COUNT = 17
+  VB_PSI_G = 17,   // Gamma(shape,1) x k(k-1)/2  TVP psi state precisions     bvartvpalg.cpp:492
+  VB_PSI_IN = 18,  // N(0,1) x k(k-1)/2    TVP psi initial state             bvartvpalg.cpp:498
+  VB_COUNT = 19
 };
 
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based: no state, any site can be drawn by any thread ------

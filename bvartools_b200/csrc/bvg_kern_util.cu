@@ -50,13 +50,13 @@ cudaError_t plan_bvar(const BvarModel& m, long long n_chains, int requested_tpc,
 
 cudaError_t plan_tvp(const TvpModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan) {
   plan->kron = 0;
-  int per = tvp_smem_len(m.b.k, m.b.T, m.b.n, m.b.sigma_type);
+  int per = tvp_smem_len(m.b.k, m.b.T, m.b.n, m.b.sigma_type, false, m.b.n_psi);
   int tpc = requested_tpc;
   if (tpc <= 0) {
     if ((size_t)per * 8 > 48 * 1024 || m.b.n > 64) tpc = (m.b.n > 96) ? 256 : 128;
     else tpc = pick_tile(m.b.n);
   }
-  const bool tiled = (tpc == 32) && tvp_tiled_ok(m.b.n);      // warp per chain, DMMA tile path
+  const bool tiled = (tpc == 32) && tvp_tiled_ok(m.b.n, m.b.n_psi);      // warp per chain, DMMA tile path
   if (tiled) per = tvp_smem_len(m.b.k, m.b.T, m.b.n, m.b.sigma_type, true);
   cudaError_t e = finish_plan(plan, per, n_chains, tpc);
   if (e == cudaSuccess && tiled) {

@@ -26,7 +26,8 @@ struct Prepared {
   // offsets (doubles) into blob; -1 = absent
   long Y = -1, X = -1, XX = -1, YX = -1, Aols = -1, SSE = -1, mu = -1, vi_off = -1, vmu_off = -1, vdiag0 = -1,
        tau0 = -1, tau1 = -1, inprior = -1, S0 = -1, gshape = -1, grate = -1, svmu = -1, svvi = -1, svconst = -1,
-       mixp = -1, mixmu = -1, mixs2 = -1, omega_off = -1, vshape = -1, vrate = -1, kLinv = -1, kSS = -1;
+       mixp = -1, mixmu = -1, mixs2 = -1, omega_off = -1, vshape = -1, vrate = -1, kLinv = -1, kSS = -1,
+       psi_vshape = -1, psi_vrate = -1;
   int kron = 0;   // 1 = flat-prior Kronecker sweep (bvg_kron_sweep.cuh)
   int n_psi = 0;  // k (k - 1) / 2 when the covariance (psi) block is active, else 0
   int psi_varsel = 0;
@@ -188,7 +189,6 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
   // ---- covariance (psi) block (bvaralg.cpp:157-204): prior mean / precision of the k (k - 1) / 2 free elements
   if (s->psi_mu != nullptr || s->psi_vi != nullptr) {
     if (!s->psi_mu || !s->psi_vi) BVG_FAIL(-4, "priors$psi needs both mu and v_i");
-    if (P.tvp) BVG_FAIL(-5, "the covariance (psi) block of TVP models is not supported");
     if (P.sigma_type == BVG_SIGMA_WISHART) BVG_FAIL(-5, "the covariance (psi) block needs a gamma or SV error prior");
     if (k < 2) BVG_FAIL(-5, "the covariance (psi) block needs at least two endogenous variables");
     P.n_psi = k * (k - 1) / 2;
@@ -218,6 +218,23 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
       }
       if ((int)P.include.size() < n) P.include.resize((size_t)n, 0);              // device mask: [coefficients (n) | psi (n_psi)]
       P.include.insert(P.include.end(), P.psi_include.begin(), P.psi_include.end());
+    }
+    if (P.tvp) {
+      // time-varying covariances (bvartvpalg.cpp:143-176): random-walk states with inverse-gamma variances
+      if (P.psi_varsel != BVG_VARSEL_NONE) BVG_FAIL(-5, "BVS on the covariances of a TVP model is not supported");
+      if (P.varsel != BVG_VARSEL_NONE) BVG_FAIL(-5, "BVS together with the covariance block of a TVP model is not supported");
+      if (k > BVG_TVP_PSI_MAXK) BVG_FAIL(-5, "the covariance block of a TVP model supports at most 8 endogenous variables");
+      if (P.n_psi > n) BVG_FAIL(-5, "the covariance block of a TVP model needs k (k - 1) / 2 <= number of coefficients");
+      if (!s->psi_shape || !s->psi_rate || !s->psi_init) BVG_FAIL(-4, "priors$psi shape / rate or initial$psi$draw missing");
+      if (has_nan(s->psi_shape, P.n_psi) || has_nan(s->psi_rate, P.n_psi) || has_nan(s->psi_init, P.n_psi))
+        BVG_FAIL(-6, "priors$psi contains NAs.");
+      std::vector<double> ps((size_t)P.n_psi);
+      for (int r = 0; r < P.n_psi; ++r) {
+        ps[r] = s->psi_shape[r] + 0.5 * T;                                           // bvartvpalg.cpp:149
+        if (!(s->psi_rate[r] > 0.0)) BVG_FAIL(-5, "priors$psi$rate must be positive");
+      }
+      P.psi_vshape = P.push(ps);
+      P.psi_vrate = P.push(s->psi_rate, P.n_psi);
     }
   }
 
@@ -334,16 +351,18 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
 
   // ---- initial chain state
   if (P.tvp) {
-    P.state_len = tvp_state_len(k, T, n, P.sigma_type);
+    P.state_len = tvp_state_len(k, T, n, P.sigma_type, P.n_psi);
     P.state0.assign(P.state_len, 0.0);
     double* st = P.state0.data();
     for (int e = 0; e < kk; ++e) st[e] = sig0[e];
     for (int r = 0; r < n; ++r) { st[kk + r] = 1.0 / s->tvp_rate[r]; st[kk + n + r] = s->a_init[r]; st[kk + 2 * n + r] = 1.0; }
+    double* sh = st + kk + 3 * n;
     if (P.sigma_type == BVG_SIGMA_SV) {
-      double* sh = st + kk + 3 * n;
       for (int e = 0; e < T * k; ++e) sh[e] = s->sv_h[e];
       for (int i = 0; i < k; ++i) { sh[T * k + i] = s->sv_sigma_h[i]; sh[T * k + k + i] = s->sv_h[0 + (size_t)T * i]; }
+      sh += T * k + 2 * k;
     }
+    for (int r = 0; r < P.n_psi; ++r) { sh[r] = 1.0 / s->psi_rate[r]; sh[P.n_psi + r] = s->psi_init[r]; }   // :175-176,169
   } else {
     P.state_len = bvar_state_len(k, T, n, P.sigma_type, P.n_psi);
     P.state0.assign(P.state_len, 0.0);
@@ -397,6 +416,8 @@ static inline void bind_tvp(const Prepared& P, const double* base, const unsigne
   bind_bvar(P, base, inc, &m->b);
   m->v_shape_post = at(base, P.vshape);
   m->v_rate = at(base, P.vrate);
+  m->psi_shape_post = at(base, P.psi_vshape);
+  m->psi_rate = at(base, P.psi_vrate);
 }
 
 }  // namespace bvg

@@ -24,10 +24,15 @@ namespace bvg {
 #define BVG_TVPC_TICK(slot) do { } while (0)
 #endif
 
+#define BVG_TVP_PSI_MAXK 8      // the psi block of TVP models keeps k x k matrices in registers / local memory
+
 struct TvpModel {
   BvarModel b;                   // data, error-variance prior, BVS prior; mu/vdiag0/vi_off = prior of the initial state
   const double* v_shape_post;    // n  shape + T/2                                   (bvartvpalg.cpp:104)
   const double* v_rate;          // n                                                (bvartvpalg.cpp:105)
+  // covariance (psi) block (bvartvpalg.cpp:143-176): b.n_psi, b.psi_mu, b.psi_vi (full matrix) + state variances
+  const double* psi_shape_post;  // n_psi  shape + T/2                               (bvartvpalg.cpp:149)
+  const double* psi_rate;        // n_psi                                            (bvartvpalg.cpp:150)
 };
 
 struct TvpOut {
@@ -41,17 +46,20 @@ struct TvpOut {
 };
 
 // state: [0,kk) Sigma_u^-1 | n q = diag(Sigma_v^-1) | n a_init | n lambda | SV: T*k h, k sigma_h, k h_init
-BVG_HD int tvp_state_len(int k, int T, int n, int sigma_type) {
-  return k * k + 3 * n + (sigma_type == SIG_SV ? T * k + 2 * k : 0);
+//        | covar: n_psi psi state precisions, n_psi psi_init, T*kk Sigma_t^-1 = Psi_t' Omega_t^-1 Psi_t
+BVG_HD int tvp_state_len(int k, int T, int n, int sigma_type, int n_psi = 0) {
+  return k * k + 3 * n + (sigma_type == SIG_SV ? T * k + 2 * k : 0) + (n_psi > 0 ? 2 * n_psi + T * k * k : 0);
 }
 // global scratch per chain: T*tri(n) (M_t) + T*n (w_t + eps_t) + T*n (a path)
 // (the warp-per-chain tile path streams full 8 x 8 tiles: tiled_len(n) >= tri(n) doubles per period)
-BVG_HD bool tvp_tiled_ok(int n) { return n <= 32; }
+// (models with the psi block run the generic recursion: their Sigma_t^-1 is a full matrix per period)
+BVG_HD bool tvp_tiled_ok(int n, int n_psi = 0) { return n <= 32 && n_psi == 0; }
 BVG_HD long long tvp_scratch_len(int T, int n) { return (long long)T * ((tvp_tiled_ok(n) ? tiled_len(n) : tri(n)) + 2 * n); }
 
-BVG_HD int tvp_smem_len(int k, int T, int n, int sigma_type, bool tiled = false) {
+BVG_HD int tvp_smem_len(int k, int T, int n, int sigma_type, bool tiled = false, int n_psi = 0) {
   int len = (tiled ? 2 * tiled_len(n) + 10 * (n + 8) : 3 * tri(n) + 9 * n) + 6 * k * k + 2 * k + k * T;
   if (sigma_type == SIG_SV) len += 3 * k * T + 2 * k;
+  if (n_psi > 0) len += T * k * k + T * n_psi + 2 * n_psi;
   return len;
 }
 
@@ -72,6 +80,86 @@ BVG_HD void tvp_residuals(const Grp& g, const BvarModel& m, const double* apath,
   g.sync();
 }
 
+// One equation with time-varying coefficients:  y_t = x_t' b_t + e_t,  e_t ~ N(0, 1 / w_t),  b_t = b_{t-1} + v_t,
+// v_t ~ N(0, diag(1 / q)).  Row i of the covariance draw of bvartvpalg.cpp:339-363 is exactly this with
+// x_t = -u_{0..i-1,t}, y_t = u_{i,t}, w_t = omega_{i,t}^-1: psi_z only couples the i elements of row i and the state
+// variances are diagonal, so the (n_psi T)^2 precision of :361 decouples into k - 1 independent block-tridiagonal
+// systems whose Cholesky factors are the matching sub-blocks of the joint factor -- the per-row draws with the matching
+// entries of the normal vector ARE the joint draw.  Same recursion as the coefficient draw (see the file header).
+// X[xs * t + c] (times xsign), Y[ys * t], w[ws * t]; normals from site VB_PSI_N, index t * site_stride + site_off + r;
+// draws to out[out_stride * t + r].
+template <class Grp>
+BVG_HD void tvp_single_eq_draw(const Grp& g, const ChainRng& rng, int sweep, int nn, int T, const double* X, int xs,
+                               double xsign, const double* Y, int ys, const double* w, int ws, const double* q,
+                               const double* b_init, int site_stride, int site_off, double* Dt, double* Mi, double* Cq,
+                               double* wv, double* cvec, double* dinv, double* anext, double* tmp, double* tmp2,
+                               double* Mpath, double* wpath, double* out, int out_stride, int& fail) {
+  const int G = g.size(), tid = g.tid(), tn = tri(nn);
+  for (int t = 0; t < T; ++t) {
+    const double* xt = X + (size_t)xs * t;
+    const double wt = w[(size_t)ws * t], yt = Y[(size_t)ys * t];
+    const double ct = (t < T - 1) ? 2.0 : 1.0;
+    for (int r = tid; r < nn; r += G) {
+      double* Dr = Dt + tri(r);
+      const double xr = xsign * xt[r];
+      for (int c = 0; c <= r; ++c) {
+        double gv = xr * (xsign * xt[c]) * wt;
+        if (c == r) gv += ct * q[r];
+        if (t > 0) gv -= Cq[tri(r) + c];
+        Dr[c] = gv;
+      }
+      double b = xr * (wt * yt);
+      b += (t == 0) ? q[r] * b_init[r] : cvec[r];
+      wv[r] = b;
+    }
+    g.sync();
+    chol_crout(g, Dt, dinv, wv, nn, fail);
+    tri_inverse(g, Dt, dinv, Mi, nn);
+    double* Mg = Mpath + (size_t)t * tn;
+    for (int e = tid; e < tn; e += G) Mg[e] = Mi[e];
+    for (int r = tid; r < nn; r += G)
+      wpath[(size_t)t * nn + r] = wv[r] + rng.normal(VB_PSI_N, sweep, t * site_stride + site_off + r);
+    if (t < T - 1) {
+      mtm_lower(g, Mi, Cq, nn);
+      int i = 0;
+      for (int e = tid; e < tn; e += G) {
+        while (tri(i + 1) <= e) ++i;
+        Cq[e] *= q[i] * q[e - tri(i)];
+      }
+      for (int r = tid; r < nn; r += G) {
+        double s = 0.0;
+        for (int mm = r; mm < nn; ++mm) s = fma(Mi[tri(mm) + r], wv[mm], s);
+        cvec[r] = q[r] * s;
+      }
+    }
+    g.sync();
+  }
+  for (int t = T - 1; t >= 0; --t) {
+    const double* Mg = Mpath + (size_t)t * tn;
+    for (int e = tid; e < tn; e += G) Mi[e] = Mg[e];
+    for (int r = tid; r < nn; r += G) tmp[r] = wpath[(size_t)t * nn + r];
+    g.sync();
+    for (int r = tid; r < nn; r += G) {
+      double s = 0.0;
+      if (t < T - 1) {
+        const double* Mr = Mi + tri(r);
+        for (int c = 0; c <= r; ++c) s = fma(Mr[c], q[c] * anext[c], s);
+      }
+      tmp2[r] = tmp[r] + s;
+    }
+    g.sync();
+    for (int r = tid; r < nn; r += G) {
+      double s = 0.0;
+      for (int mm = r; mm < nn; ++mm) s = fma(Mi[tri(mm) + r], tmp2[mm], s);
+      out[(size_t)out_stride * t + r] = s;
+      tmp[r] = s;
+    }
+    g.sync();
+    for (int r = tid; r < nn; r += G) anext[r] = tmp[r];
+    g.sync();
+  }
+}
+
 template <class Grp>
 BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, double* state, double* scratch,
                       double* sm, const TvpOut& out, long long chain_local, int sweep_begin, int sweep_end,
@@ -81,8 +169,10 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
   const int k = m.k, T = m.T, M = m.M, n = m.n, kk = k * k, tn = tri(n);
   const bool sv = m.sigma_type == SIG_SV;
   const bool bvs = m.varsel == VS_BVS;
+  const int n_psi = m.n_psi;
+  const bool covar = n_psi > 0;
 #if defined(__CUDA_ARCH__)
-  const bool tiled = Grp::kWarp32 && tvp_tiled_ok(n);   // warp per chain, n <= 32: DMMA tile path (bvg_tvp_tiled.cuh)
+  const bool tiled = Grp::kWarp32 && tvp_tiled_ok(n, n_psi);   // warp per chain, n <= 32: DMMA tile path (bvg_tvp_tiled.cuh)
 #else
   const bool tiled = false;
 #endif
@@ -111,6 +201,8 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
   double* U = sm;       sm += k * T;
   double* h = nullptr; double* ew = nullptr; double* svw = nullptr; double* sigma_h = nullptr; double* h_init = nullptr;
   if (sv) { h = sm; sm += k * T; ew = sm; sm += k * T; svw = sm; sm += k * T; sigma_h = sm; sm += k; h_init = sm; sm += k; }
+  double* sigt = nullptr; double* psip = nullptr; double* pq = nullptr; double* pinit = nullptr;
+  if (covar) { sigt = sm; sm += T * kk; psip = sm; sm += T * n_psi; pq = sm; sm += n_psi; pinit = sm; sm += n_psi; }
   double* Mpath = scratch;                         // [T][tn]  (tiled: [T][tiled_len(n)])
   double* wpath = scratch + (size_t)T * (tiled ? tiled_len(n) : tn);   // [T][n]
   double* apath = wpath + (size_t)T * n;           // [T][n]
@@ -120,6 +212,11 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
   double* st_ai = st_q + n;
   double* st_lam = st_ai + n;
   double* st_h = st_lam + n;
+  double* st_psi = st_h + (sv ? T * k + 2 * k : 0);     // n_psi pq | n_psi psi_init | T*kk Sigma_t^-1
+  if (covar) {
+    for (int e = tid; e < n_psi; e += G) { pq[e] = st_psi[e]; pinit[e] = st_psi[n_psi + e]; }
+    for (int e = tid; e < T * kk; e += G) sigt[e] = st_psi[2 * n_psi + e];
+  }
   for (int e = tid; e < kk; e += G) sig[e] = state[e];
   for (int e = tid; e < n; e += G) { q[e] = st_q[e]; a_init[e] = st_ai[e]; lam[e] = st_lam[e]; }
   for (int e = n + tid; e < nv; e += G) { q[e] = 0.0; a_init[e] = 0.0; anext[e] = 0.0; }
@@ -137,6 +234,15 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
       for (int e = tid; e < k * T; e += G) ew[e] = 1.0 / exp(sweep == 0 ? h[T * (e / T)] : h[e]);
       g.sync();
     }
+    if (covar && sweep == 0) {
+      // before the first psi draw Sigma_t^-1 is the diagonal initial value (bvartvpalg.cpp:224-233)
+      for (int e = tid; e < T * kk; e += G) {
+        const int t = e / kk, f = e % kk, i = f % k, j = f / k;
+        sigt[e] = (i == j) ? (sv ? ew[t + T * i] : sig[i + k * i]) : 0.0;
+      }
+      g.sync();
+    }
+    const bool svd = sv && !covar;                      // diagonal Sigma_t^-1 read from ew; covar: full matrix per period
 #if defined(__CUDA_ARCH__)
     if (tiled) {
       if constexpr (Grp::kWarp32)
@@ -149,11 +255,12 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
     for (int t = 0; t < T; ++t) {
       const double* xt = m.X + (size_t)M * t;
       const double* yt = m.Y + (size_t)k * t;
+      const double* sgt = covar ? sigt + (size_t)kk * t : sig;
       // kv = Sigma_t^-1 y_t
       for (int i = tid; i < k; i += G) {
         double s;
-        if (sv) s = ew[t + T * i] * yt[i];
-        else { s = 0.0; for (int i2 = 0; i2 < k; ++i2) s = fma(sig[i + k * i2], yt[i2], s); }
+        if (svd) s = ew[t + T * i] * yt[i];
+        else { s = 0.0; for (int i2 = 0; i2 < k; ++i2) s = fma(sgt[i + k * i2], yt[i2], s); }
         kv[i] = s;
       }
       g.sync();
@@ -166,8 +273,8 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
         int j2 = 0, i2 = 0;
         for (int c = 0; c <= r; ++c) {
           double sv_ii;
-          if (sv) sv_ii = (i == i2) ? ew[t + T * i] : 0.0;
-          else sv_ii = sig[i + k * i2];
+          if (svd) sv_ii = (i == i2) ? ew[t + T * i] : 0.0;
+          else sv_ii = sgt[i + k * i2];
           double gv = xr * (xt[j2] * (bvs ? lam[c] : 1.0)) * sv_ii;
           if (c == r) gv += ct * q[r];
           if (t > 0) gv -= Cq[tri(r) + c];
@@ -273,9 +380,30 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
       tvp_residuals(g, m, apath, lam, false, U);
     }
 
+    // ================= covariance (psi) block (bvartvpalg.cpp:339-407) =================
+    if (covar) {
+      for (int i = 1; i < k; ++i) {
+        const int o = (i * (i - 1)) / 2;
+        tvp_single_eq_draw(g, rng, sweep, i, T, U, k, -1.0, U + i, k, sv ? ew + (size_t)T * i : sig + i + k * i, sv ? 1 : 0,
+                           pq + o, pinit + o, n_psi, o, Dt, Mi, Cq, wv, cvec, dinv, anext, tmp, tmp2, Mpath, wpath,
+                           psip + o, n_psi, fail);
+      }
+      // u_t <- Psi_t u_t (:406): rows from the last to the first, in place
+      for (int t = tid; t < T; t += G) {
+        const double* ps = psip + (size_t)n_psi * t;
+        double* ut = U + (size_t)k * t;
+        for (int i = k - 1; i >= 1; --i) {
+          double s = ut[i];
+          for (int j = 0; j < i; ++j) s = fma(ps[(i * (i - 1)) / 2 + j], ut[j], s);
+          ut[i] = s;
+        }
+      }
+      g.sync();
+    }
+
     // ================= error variances =================
     double* out_sig = nullptr;
-    if (keep) out_sig = out.sigma + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)(sv ? kk * T : kk);
+    if (keep) out_sig = out.sigma + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)((sv || covar) ? kk * T : kk);
     if (sv) {
       sv_step(g, rng, sweep, m, U, h, sigma_h, h_init, ew, svw);                       // :414
       BVG_TVPC_TICK(9);
@@ -307,10 +435,11 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
       g.sync();
       back_solve_lt_generic(g, W1, kd, W4, h_init, k);                                         // :429
       if (keep) {
-        for (int e = tid; e < kk * T; e += G) {
-          const int t = e / kk, f = e % kk, i = f % k, j = f / k;
-          out_sig[e] = (i == j) ? 1.0 / (1.0 / exp(h[t + T * i])) : 0.0;               // :507-509
-        }
+        if (!covar)
+          for (int e = tid; e < kk * T; e += G) {
+            const int t = e / kk, f = e % kk, i = f % k, j = f / k;
+            out_sig[e] = (i == j) ? 1.0 / (1.0 / exp(h[t + T * i])) : 0.0;             // :507-509
+          }
         double* osh = out.sigma_h + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)k;
         for (int i = tid; i < k; i += G) osh[i] = kv[i];
       }
@@ -323,7 +452,10 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
         S[e] = s;
       }
       g.sync();
-      if (m.sigma_type == SIG_GAMMA) {
+      if (m.sigma_type == SIG_GAMMA && covar) {
+        // bvartvpalg.cpp:433-437,454-455: the drawn omega_i never reaches diag_omega_i (only the SV branch refreshes
+        // it, :446), so Sigma_t^-1 = Psi_t' Omega_0^-1 Psi_t with the INITIAL measurement precisions -- restated as is
+      } else if (m.sigma_type == SIG_GAMMA) {
         for (int i = tid; i < k; i += G) {
           const double gs = rng.gamma(VB_OMEGA_G, sweep, i, m.g_shape_post[i]);
           kv[i] = gs * (1.0 / (m.g_rate[i] + S[i + k * i] * 0.5));                     // :436
@@ -345,6 +477,67 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
         if (keep) for (int e = tid; e < kk; e += G) out_sig[e] = W4[e];
       }
       g.sync();
+    }
+
+    if (covar) {
+      // Sigma_t^-1 = Psi_t' Omega_t^-1 Psi_t (:448,455) and the stored Sigma_t = Psi_t^-1 Omega_t Psi_t^-T (:507-509)
+      for (int t = tid; t < T; t += G) {
+        const double* ps = psip + (size_t)n_psi * t;
+        double P[BVG_TVP_PSI_MAXK][BVG_TVP_PSI_MAXK], om[BVG_TVP_PSI_MAXK];
+        for (int i = 0; i < k; ++i) {
+          om[i] = sv ? 1.0 / exp(h[t + T * i]) : sig[i + k * i];
+          for (int j = 0; j < k; ++j) P[i][j] = (i == j) ? 1.0 : ((j < i) ? ps[(i * (i - 1)) / 2 + j] : 0.0);
+        }
+        double* sg = sigt + (size_t)kk * t;
+        for (int a = 0; a < k; ++a)
+          for (int c = 0; c <= a; ++c) {
+            double s = 0.0;
+            for (int b = a; b < k; ++b) s = fma(P[b][a] * om[b], P[b][c], s);
+            sg[a + k * c] = s; sg[c + k * a] = s;
+          }
+        if (keep) {
+          // unit-lower inverse by forward substitution, in place of P
+          for (int i = 1; i < k; ++i)
+            for (int c = 0; c < i; ++c) {
+              double s = -P[i][c];
+              for (int j = c + 1; j < i; ++j) s = fma(-P[i][j], (j > c) ? P[j][c] : 0.0, s);
+              P[i][c] = s;
+            }
+          // (rows above i already hold the inverse when row i is formed: P[i][j] on the right is the ORIGINAL row i)
+          double* os = out_sig + (size_t)kk * t;
+          for (int a = 0; a < k; ++a)
+            for (int c = 0; c <= a; ++c) {
+              double s = 0.0;
+              for (int b = 0; b <= c; ++b) s = fma(P[a][b] / om[b], P[c][b], s);
+              os[a + k * c] = s; os[c + k * a] = s;
+            }
+        }
+      }
+      g.sync();
+      // psi state variances (:485-493) and initial state (:495-498)
+      for (int r = tid; r < n_psi; r += G) {
+        double ss = 0.0, prev = pinit[r];
+        for (int t = 0; t < T; ++t) { const double v = psip[(size_t)n_psi * t + r]; const double d = v - prev; ss = fma(d, d, ss); prev = v; }
+        tmp[r] = rng.gamma(VB_PSI_G, sweep, r, tm.psi_shape_post[r]) * (1.0 / (tm.psi_rate[r] + ss * 0.5));
+      }
+      g.sync();
+      for (int r = tid; r < n_psi; r += G) pq[r] = tmp[r];
+      g.sync();
+      for (int r = tid; r < n_psi; r += G) {
+        double* Dr = Dt + tri(r);
+        double b = pq[r] * psip[r];
+        for (int c = 0; c < n_psi; ++c) {
+          const double v = m.psi_vi[r + n_psi * c];
+          if (c <= r) Dr[c] = v + ((c == r) ? pq[r] : 0.0);
+          b = fma(v, m.psi_mu[c], b);
+        }
+        wv[r] = b;
+      }
+      g.sync();
+      chol_crout(g, Dt, dinv, wv, n_psi, fail);
+      for (int r = tid; r < n_psi; r += G) wv[r] += rng.normal(VB_PSI_IN, sweep, r);
+      g.sync();
+      back_solve_lt(g, Dt, dinv, wv, pinit, n_psi);
     }
 
     BVG_TVPC_TICK(10);
@@ -397,6 +590,10 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
   if (sv) {
     for (int e = tid; e < T * k; e += G) st_h[e] = h[e];
     for (int e = tid; e < k; e += G) { st_h[T * k + e] = sigma_h[e]; st_h[T * k + k + e] = h_init[e]; }
+  }
+  if (covar) {
+    for (int e = tid; e < n_psi; e += G) { st_psi[e] = pq[e]; st_psi[n_psi + e] = pinit[e]; }
+    for (int e = tid; e < T * kk; e += G) st_psi[2 * n_psi + e] = sigt[e];
   }
   if (fail && tid == 0) out.status[chain_local] = 1;
   g.sync();

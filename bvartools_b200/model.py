@@ -307,7 +307,7 @@ def add_priors(obj, coef=None, sigma=None, ssvs=None, bvs=None):
 
     Restated branches: regular / Minnesota / SSVS / BVS coefficient priors, TVP state-variance priors, Wishart /
     gamma / SV error priors, the covariance (psi) block (`sigma$covar`, constant-parameter models), OLS initial
-    values.  Variable selection on the covariances and the TVP psi block are outside the accelerated path and raise.
+    values.
     """
     coef = dict(_DEF_COEF) if coef is None else dict(coef)
     sigma = dict(_DEF_SIGMA) if sigma is None else dict(sigma)
@@ -324,8 +324,6 @@ def add_priors(obj, coef=None, sigma=None, ssvs=None, bvs=None):
     if len(sigma) < 2:
         raise ValueError("Argument 'sigma' must be at least of length 2.")
     covar = bool(sigma.get("covar"))
-    if covar and any(o["model"]["tvp"] for o in objs):
-        raise NotImplementedError("sigma$covar for TVP models is outside the accelerated path (SURVEY.md section 8f-4)")
 
     any_sv = any(o["model"]["sv"] for o in objs)
     if any_sv:
@@ -455,6 +453,9 @@ def add_priors(obj, coef=None, sigma=None, ssvs=None, bvs=None):
                                  "error prior.")
             n_covar = k * (k - 1) // 2
             pri["psi"] = {"mu": np.zeros((n_covar, 1)), "v_i": np.diag(np.full(n_covar, float(coef["v_i"])))}
+            if o["model"]["tvp"]:                            # :499-502
+                pri["psi"]["shape"] = np.full((n_covar, 1), float(coef["shape"]))
+                pri["psi"]["rate"] = np.full((n_covar, 1), float(coef["rate"]))
             if use_ssvs_error:                               # :505-511
                 pri["psi"]["ssvs"] = {"inprior": np.full((n_covar, 1), float(ssvs["inprior"])),
                                       "include": np.arange(1, n_covar + 1).reshape(-1, 1),
@@ -505,6 +506,15 @@ def add_priors(obj, coef=None, sigma=None, ssvs=None, bvs=None):
             u = y - y.mean(axis=1, keepdims=True)
         if o["model"]["tvp"] and tot_par > 0:
             ini["coefficients"]["sigma_i"] = np.diag(1.0 / pri["coefficients"]["rate"][:, 0])
+        if covar and not structural and k > 1:               # :586-598 (psi by OLS of u on -u, then u <- Psi u)
+            yc = np.kron(-u.T, np.eye(k))
+            yc = np.delete(yc, [j * k + i for j in range(k) for i in range(j + 1)], axis=1)
+            psi0 = np.linalg.solve(yc.T @ yc, yc.T @ u.reshape(-1, 1, order="F"))
+            ini["psi"] = {"draw": psi0}
+            Psi = np.eye(k)
+            for j in range(1, k):
+                Psi[j, :j] = psi0[(j - 1) * j // 2: (j - 1) * j // 2 + j, 0]
+            u = Psi @ u
         uvar = u.var(axis=1, ddof=1)
         if o["model"]["sv"]:
             ini["sigma"] = {"h": np.log(np.tile(uvar[None, :], (tt, 1))),

@@ -68,9 +68,11 @@ typedef struct bvg_inject {
   const double* state_normal;   /* n*T          */
   const double* sigma_v_gamma;  /* n            */
   const double* a_init_normal;  /* n            */
-  const double* psi_normal;     /* k(k-1)/2  covariance (psi) block, bvaralg.cpp:394 */
+  const double* psi_normal;     /* k(k-1)/2  covariance (psi) block, bvaralg.cpp:394; TVP: k(k-1)/2 * T, period-major, bvartvpalg.cpp:363 */
   const double* psi_u1;         /* k(k-1)/2  SSVS Bernoulli / BVS prior gate on psi, bvaralg.cpp:409,424 */
   const double* psi_u2;         /* k(k-1)/2  BVS acceptance on psi, bvaralg.cpp:437 */
+  const double* psi_sigma_v_gamma; /* k(k-1)/2  Gamma(shape + T/2, 1), TVP psi state precisions, bvartvpalg.cpp:492 */
+  const double* psi_init_normal;   /* k(k-1)/2  TVP psi initial state, bvartvpalg.cpp:498 */
 } bvg_inject;
 
 /* The flat POD the Rcpp glue fills from the `bvarmodel` list (what src/bvaralg.cpp:9-249 and
@@ -130,6 +132,12 @@ typedef struct bvg_spec {
   const double* psi_inprior;   /* k(k-1)/2 */
   const int32_t* psi_include;  /* 0-based positions taking part */
   int32_t psi_n_include;
+  /* TVP models (bvartvpalg.cpp:143-176,339-407,485-499): the free elements of Psi_t follow random walks; inverse-gamma
+   * prior of their state variances and the initial draw (initial$psi$draw).  NULL for constant-parameter models.
+   * Variable selection on the covariances or the coefficients is not available together with the TVP psi block (-5). */
+  const double* psi_shape;     /* k(k-1)/2 */
+  const double* psi_rate;      /* k(k-1)/2 */
+  const double* psi_init;      /* k(k-1)/2 */
   /* tuning / testing */
   int32_t resid_mode;       /* BVG_RESID_*                                 */
   int32_t threads_per_chain; /* 0 = auto; 1,2,4,8,16,32 (sub-warp tiles) or a multiple of 32 (CTA per chain) */

@@ -49,8 +49,6 @@ def _unpack_common(obj):
     n_c = k * len(model.get("deterministic", []))
     if model.get("structural"):
         raise NotImplementedError("structural models are outside the accelerated path (SURVEY.md 8f-4)")
-    if "psi" in priors and model.get("tvp"):
-        raise NotImplementedError("covariance (psi) block of TVP models is outside the accelerated path (SURVEY.md 8f-4)")
     return data, model, priors, initial, y, k, tt, z, n_tot, n_a, n_b, n_c
 
 
@@ -433,10 +431,31 @@ def bvartvpalg(obj, variates: VariateSource | None = None, literal=True, table="
         sigma_u_i = omega_i.copy()
     sig_t = np.tile(np.diag(np.diag(sigma_u_i))[None], (tt, 1, 1))    # :230
 
+    # covariance (psi) block of the TVP sampler (:143-158, 165-186)
+    covar = "psi" in priors
+    if covar:
+        pp = priors["psi"]
+        if "bvs" in pp:
+            raise NotImplementedError("BVS on the time-varying covariances (:365-398) is not restated")
+        n_psi = k * (k - 1) // 2
+        psi_prior_mu = np.asarray(pp["mu"], dtype=np.float64).reshape(-1)
+        psi_prior_vi = np.asarray(pp["v_i"], dtype=np.float64)
+        psi_post_shape = np.asarray(pp["shape"], dtype=np.float64).reshape(-1) + 0.5 * tt      # :149
+        psi_prior_rate = np.asarray(pp["rate"], dtype=np.float64).reshape(-1)
+        psi_init = np.asarray(initial["psi"]["draw"], dtype=np.float64).reshape(-1).copy()      # :169
+        psi_sigma_v_i = 1.0 / psi_prior_rate                                                     # :175-176
+        Hpsi = np.eye(n_psi * tt)
+        ip = np.arange(n_psi * (tt - 1))
+        Hpsi[ip + n_psi, ip] = -1.0                                                              # :172-173
+        # diag_omega_i = diag_sigma_u_i at the start (:231-233); only the SV branch ever refreshes it (:446) -- with
+        # the inverse-gamma prior the drawn omega_i (:436) never reaches it, so the measurement variances of a
+        # gamma + covar TVP model stay at their initial values in the reference.  Restated as is.
+        omega_diag = np.tile(np.diag(sigma_u_i), tt).astype(np.float64)
+
     iters, burnin = int(model["iterations"]), int(model["burnin"])
     draws_coef = np.zeros((n * tt, iters))
     draws_sigma_v = np.zeros((n, iters))
-    per_t_sigma = sv
+    per_t_sigma = sv or covar
     draws_sigma_u = np.zeros((k * k * tt if per_t_sigma else k * k, iters))
     draws_sigma_sigma = np.zeros((k * k, iters)) if sv else None
     draws_lambda = np.zeros((n, iters)) if bvs else None
@@ -489,6 +508,26 @@ def bvartvpalg(obj, variates: VariateSource | None = None, literal=True, table="
             a = a_mat.reshape(-1, order="F")
         u = y - np.einsum("tkn,nt->kt", Zarr, a_mat)                                      # :332-336
 
+        if covar:                                                                         # :339-407
+            psi_y = u[1:, :].reshape(-1, order="F")
+            psi_z = np.zeros(((k - 1) * tt, n_psi * tt))
+            dco = np.zeros((k - 1) * tt)
+            for i in range(1, k):
+                for j in range(tt):
+                    psi_z[j * (k - 1) + i - 1, j * n_psi + i * (i - 1) // 2: j * n_psi + (i + 1) * i // 2] = -u[:i, j]
+                    dco[j * (k - 1) + i - 1] = omega_diag[j * k + i]                      # :350
+            pzz = psi_z.T * dco[None, :]                                                  # :359
+            phsh = Hpsi.T @ np.kron(np.eye(tt), np.diag(psi_sigma_v_i)) @ Hpsi            # :360
+            ppv = phsh + pzz @ psi_z
+            ppm = sla.solve(ppv, phsh @ np.tile(psi_init, tt) + pzz @ psi_y)              # :362
+            psi = ppm + sla.solve_triangular(sla.cholesky(ppv, lower=False),
+                                             vs.normal("psi_normal", draw, (n_psi * tt,)), lower=False)   # :363
+            Psi_t = np.tile(np.eye(k)[None], (tt, 1, 1))
+            for j in range(tt):
+                for i in range(1, k):
+                    Psi_t[j, i, :i] = psi[j * n_psi + i * (i - 1) // 2: j * n_psi + (i + 1) * i // 2]      # :400-404
+            u = np.einsum("tab,bt->at", Psi_t, u)                                         # :406
+
         if sv:
             args = (u.T, h, sigma_h, h_init, h_const, vs.uniform("sv_u", draw, (k, tt)),
                     vs.normal("sv_normal", draw, (k, tt)))
@@ -505,6 +544,9 @@ def bvartvpalg(obj, variates: VariateSource | None = None, literal=True, table="
                                                 vs.normal("h_init_normal", draw, (k,)), lower=False)
             sig_t = np.zeros((tt, k, k))
             sig_t[:, np.arange(k), np.arange(k)] = 1.0 / np.exp(h)                        # :446
+            if covar:
+                omega_diag = (1.0 / np.exp(h)).reshape(-1)                                # period-major: vectorise(h.t())
+                sig_t = np.einsum("tba,tb,tbc->tac", Psi_t, 1.0 / np.exp(h), Psi_t)       # :448
         else:
             if use_gamma:
                 sse = u @ u.T
@@ -516,11 +558,15 @@ def bvartvpalg(obj, variates: VariateSource | None = None, literal=True, table="
                 # prior without covar is therefore not usable in the reference TVP sampler; we follow the evident
                 # intent (diag_sigma_u_i = kron(I_T, omega_i)).
                 sigma_u_i = omega_i.copy()
+            elif covar:
+                raise ValueError("the covariance block needs a gamma or stochastic-volatility prior")
             else:
                 Sbar = sla.solve(prior_scale + u @ u.T, diag_k)                           # :461
                 sigma_u_i = wishrnd(Sbar, vs.chi2("wishart_chi2", draw, post_df - np.arange(k)),
                                     vs.normal("wishart_normal", draw, (k * (k - 1) // 2,)))
             sig_t = np.tile(sigma_u_i[None], (tt, 1, 1))
+            if covar:                                                                     # :454-455 (frozen diag_omega_i)
+                sig_t = np.einsum("tba,tb,tbc->tac", Psi_t, omega_diag.reshape(tt, k), Psi_t)
 
         # state variances and initial state (:469-483)
         a_lag = np.concatenate([a_init, a[: (tt - 1) * n]])
@@ -532,12 +578,23 @@ def bvartvpalg(obj, variates: VariateSource | None = None, literal=True, table="
         a_init = imu + sla.solve_triangular(sla.cholesky(iv, lower=False),
                                             vs.normal("a_init_normal", draw, (n,)), lower=False)
 
+        if covar:                                                                         # :485-499
+            psi_lag = np.concatenate([psi_init, psi[: (tt - 1) * n_psi]])
+            psi_v = (psi - psi_lag).reshape(n_psi, tt, order="F")
+            psc = 1.0 / (psi_prior_rate + (psi_v ** 2).sum(axis=1) * 0.5)
+            psi_sigma_v_i = vs.gamma("psi_sigma_v_gamma", draw, psi_post_shape) * psc     # :492
+            piv = psi_prior_vi + np.diag(psi_sigma_v_i)
+            pim = sla.solve(piv, psi_prior_vi @ psi_prior_mu + psi_sigma_v_i * psi[:n_psi])
+            psi_init = pim + sla.solve_triangular(sla.cholesky(piv, lower=False),
+                                                  vs.normal("psi_init_normal", draw, (n_psi,)), lower=False)   # :498
+
         if draw >= burnin:
             pos = draw - burnin
             if per_t_sigma:
                 for i in range(tt):
                     draws_sigma_u[i * k * k:(i + 1) * k * k, pos] = sla.solve(sig_t[i], diag_k).reshape(-1, order="F")
-                draws_sigma_sigma[:, pos] = np.diag(sigma_h).reshape(-1, order="F")
+                if sv:
+                    draws_sigma_sigma[:, pos] = np.diag(sigma_h).reshape(-1, order="F")
             else:
                 draws_sigma_u[:, pos] = sla.solve(sigma_u_i, diag_k).reshape(-1, order="F")
             draws_coef[:, pos] = a

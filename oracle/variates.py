@@ -97,6 +97,10 @@ def draw_variates(dims: dict, sweeps: int, rng: np.random.Generator, kinds) -> d
         elif kind == "wishart_normal":
             out[kind] = rng.standard_normal((sweeps, k * (k - 1) // 2))
         elif kind == "psi_normal":
+            out[kind] = rng.standard_normal((sweeps, k * (k - 1) // 2 * (T if dims.get("tvp_psi") else 1)))
+        elif kind == "psi_sigma_v_gamma":
+            out[kind] = rng.standard_gamma(np.broadcast_to(dims["shape_psi"], (sweeps, k * (k - 1) // 2)))
+        elif kind == "psi_init_normal":
             out[kind] = rng.standard_normal((sweeps, k * (k - 1) // 2))
         elif kind in ("psi_u1", "psi_u2"):
             out[kind] = rng.random((sweeps, k * (k - 1) // 2))

@@ -71,8 +71,10 @@ static void fill_rng(const bvg_spec* s, const Prepared& P, RngParams* rp) {
                                  s->inject->sv_u, s->inject->sv_normal, s->inject->sigma_h_gamma,
                                  s->inject->h_init_normal, s->inject->omega_gamma, s->inject->wishart_chi2,
                                  s->inject->wishart_normal, s->inject->state_normal, s->inject->sigma_v_gamma,
-                                 s->inject->a_init_normal, s->inject->psi_normal, s->inject->psi_u1, s->inject->psi_u2};
-  const int cnt[VB_COUNT] = {n, n, n, n, k * T, k * T, k, k, k, k, k * (k - 1) / 2, n * T, n, n, k * (k - 1) / 2, k * (k - 1) / 2, k * (k - 1) / 2};
+                                 s->inject->a_init_normal, s->inject->psi_normal, s->inject->psi_u1, s->inject->psi_u2,
+                                 s->inject->psi_sigma_v_gamma, s->inject->psi_init_normal};
+  const int np = k * (k - 1) / 2;
+  const int cnt[VB_COUNT] = {n, n, n, n, k * T, k * T, k, k, k, k, np, n * T, n, n, P.tvp ? np * T : np, np, np, np, np};
   for (int b = 0; b < VB_COUNT; ++b) {
     rp->inj[b] = ptr[b];
     rp->inj_stride[b] = cnt[b];
@@ -144,7 +146,7 @@ extern "C" int emu_bvartvpalg(const bvg_spec* s, const bvg_out* o) {
   std::vector<int> status(s->n_chains, 0);
   out.status = status.data();
   out.iters = s->iterations;
-  std::vector<double> sm(tvp_smem_len(P.k, P.T, P.n, P.sigma_type) + 16);
+  std::vector<double> sm(tvp_smem_len(P.k, P.T, P.n, P.sigma_type, false, P.n_psi) + 16);
   std::vector<double> scratch((size_t)tvp_scratch_len(P.T, P.n));
   SerialGroup g;
   const int sweeps = s->iterations + s->burnin;

@@ -101,6 +101,17 @@ def model_covar_gamma(K=3, p=2, nobs=70, iterations=20, burnin=5, seed=77, bvs=F
     return add_priors(m, coef=dict(v_i=1, v_i_det=0.1), sigma=dict(shape=3, rate=1e-4, covar=True), ssvs=ssvs, bvs=bv)
 
 
+def model_tvp_covar(K=3, p=1, nobs=24, iterations=8, burnin=3, seed=41, sv=True):
+    """TVP-VAR with time-varying covariances (Psi_t random walks, bvartvpalg.cpp:339-407) and SV or inverse-gamma
+    measurement variances."""
+    y = synth_var(K, p, nobs, seed)
+    m = gen_var(y, p=p, deterministic="const", iterations=iterations, burnin=burnin, tvp=True, sv=sv)
+    sigma = dict(shape=3, rate=1e-4, covar=True)
+    if sv:
+        sigma.update(mu=0, v_i=0.01, sigma_h=0.05, constant=1e-4)
+    return add_priors(m, coef=dict(v_i=1, v_i_det=0.1, shape=3, rate=1e-4, rate_det=0.01), sigma=sigma)
+
+
 def model_c5(K=20, p=4, nobs=204, iterations=200, burnin=50, seed=2042004):
     """Config c5: large BVAR, K = 20, p = 4, const (n = 1620), Minnesota prior, sigma df = k, scale 1.
     DGP: diagonally dominant stable VAR(1), AR(1)-correlated errors."""
@@ -136,6 +147,8 @@ def variate_kinds(obj):
         kinds += ["omega_gamma"]
     if "psi" in priors:
         kinds += ["psi_normal"]
+        if model.get("tvp"):
+            kinds += ["psi_sigma_v_gamma", "psi_init_normal"]
         if "ssvs" in priors["psi"]:
             kinds += ["psi_u1"]
         if "bvs" in priors["psi"]:
@@ -159,6 +172,9 @@ def make_variates(obj, n_chains, seed):
         dims["df"] = float(ps["df"]) + T
     if obj["model"].get("tvp"):
         dims["shape_v"] = np.asarray(obj["priors"]["coefficients"]["shape"], dtype=np.float64).reshape(-1) + 0.5 * T
+        if "psi" in obj["priors"]:
+            dims["tvp_psi"] = True
+            dims["shape_psi"] = np.asarray(obj["priors"]["psi"]["shape"], dtype=np.float64).reshape(-1) + 0.5 * T
     rng = np.random.default_rng(seed)
     per_chain = [draw_variates(dims, sweeps, rng, variate_kinds(obj)) for _ in range(n_chains)]
     stacked = {kname: np.stack([pc[kname].reshape(sweeps, -1) for pc in per_chain]) for kname in per_chain[0]}

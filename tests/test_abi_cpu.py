@@ -65,6 +65,23 @@ def test_no_cpu_fallback_without_device():
     assert res.get("error") is True
 
 
+def test_post_estimation_calls_fail_loudly_without_device():
+    """summary / irf / fevd / predict of host objects go through the device or raise: no NumPy fallback."""
+    L = lib()
+    if L.bvg_device_count() > 0:
+        pytest.skip("a GPU is present")
+    import bvartools_b200 as b
+    import numpy as np
+    rng = np.random.default_rng(0)
+    fit = {"y": rng.standard_normal((20, 2)), "x": rng.standard_normal((20, 5)), "A": rng.standard_normal((30, 4)),
+           "C": rng.standard_normal((30, 2)), "Sigma": np.tile(np.eye(2).reshape(-1), (30, 1))}
+    for call in (lambda: b.summary(fit), lambda: b.irf(fit, 0, 1), lambda: b.fevd(fit, 0), lambda: b.predict(fit, 3)):
+        with pytest.raises(BvgError, match="no CUDA device"):
+            call()
+    from bvartools_b200.distributed import bind_to_gpu_numa
+    assert bind_to_gpu_numa(0) is False
+
+
 def test_product_never_imports_the_oracle_or_the_emulator():
     for path in list((ROOT / "bvartools_b200").rglob("*.py")) + list((ROOT / "bvartools_b200" / "csrc").glob("*")):
         if path.is_file() and path.suffix in (".py", ".cu", ".cuh", ".hpp", ".cpp"):

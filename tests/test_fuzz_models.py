@@ -12,16 +12,21 @@ def _random_model(rng):
     k = int(rng.integers(1, 6))
     p = int(rng.integers(0, 4))
     nobs = int(rng.integers(24, 70))
-    kind = str(rng.choice(["wishart", "gamma", "sv", "gamma_covar", "sv_covar", "tvp_sv", "tvp_wishart"]))
+    kind = str(rng.choice(["wishart", "gamma", "sv", "gamma_covar", "sv_covar", "tvp_sv", "tvp_wishart", "tvp_sv_covar",
+                           "tvp_gamma_covar"]))
     sel = str(rng.choice(["none", "ssvs", "bvs"]))
     det = str(rng.choice(["const", "none", "both"])) if p > 0 else "const"
     tvp, sv = kind.startswith("tvp"), "sv" in kind
     y = helpers.synth_var(k, max(p, 1), nobs, int(rng.integers(1, 1000)))
     m = helpers.gen_var(y, p=p, deterministic=det, iterations=6, burnin=2, tvp=tvp, sv=sv)
-    if kind in ("gamma", "gamma_covar"):
-        sigma = dict(shape=3, rate=1e-3, covar=(kind == "gamma_covar" and k > 1))
+    tvp_covar = kind in ("tvp_sv_covar", "tvp_gamma_covar") and k > 1 and k * (k - 1) // 2 <= k * (k * p + (det != "none"))
+    if tvp_covar:
+        sel = "none"                                       # BVS is not combined with the TVP covariance block
+    if kind in ("gamma", "gamma_covar", "tvp_gamma_covar"):
+        sigma = dict(shape=3, rate=1e-3, covar=((kind == "gamma_covar" and k > 1) or tvp_covar))
     elif sv:
-        sigma = dict(shape=3, rate=1e-4, mu=0, v_i=0.01, sigma_h=0.05, constant=1e-4, covar=(kind == "sv_covar" and k > 1))
+        sigma = dict(shape=3, rate=1e-4, mu=0, v_i=0.01, sigma_h=0.05, constant=1e-4,
+                     covar=((kind == "sv_covar" and k > 1) or tvp_covar))
     else:
         sigma = dict(df="k", scale=1)
     ssvs = dict(inprior=0.5, tau=(0.05, 10.0), exclude_det=bool(rng.integers(0, 2))) if sel == "ssvs" and not sv and not tvp else None

@@ -59,6 +59,10 @@ def _tvp_wishart():
 
 
 CASES["tvp_wishart"] = (_tvp_wishart, {})
+CASES["tvp_covar_sv"] = (lambda: helpers.model_tvp_covar(), {})
+CASES["tvp_covar_sv_k4"] = (lambda: helpers.model_tvp_covar(K=4, p=1, nobs=20, iterations=6, burnin=2), {})
+CASES["tvp_covar_sv_k2"] = (lambda: helpers.model_tvp_covar(K=2, p=2, nobs=22), {})
+CASES["tvp_covar_gamma"] = (lambda: helpers.model_tvp_covar(sv=False), {})
 
 
 def _exogen(sv=False, ssvs=False):
@@ -98,7 +102,7 @@ def test_kernel_logic_matches_oracle(emu, name):
 
 @pytest.mark.parametrize("G", [4, 32])
 @pytest.mark.parametrize("name", ["kron_c1", "kron_grid_p4", "kron_k2", "c1_wishart_moment", "c1_informative_prior", "ssvs_moment", "bvs_direct", "gamma",
-                                  "sv_bvs", "tvp_sv_bvs", "tvp_wishart"])
+                                  "sv_bvs", "tvp_sv_bvs", "tvp_wishart", "tvp_covar_sv", "tvp_covar_gamma"])
 def test_kernel_logic_spmd_lanes_match_oracle(emu, name, G):
     """Same check with the chain owned by G real threads (barriers + emulated shuffles): exercises the
     one-row-per-lane Cholesky / back substitution, the register Wishart block and the work distribution."""
