@@ -120,8 +120,8 @@ typedef struct bvg_spec {
   const double* tvp_shape; /* n */
   const double* tvp_rate;  /* n */
   const double* a_init;    /* n */
-  /* priors$psi: covariance block of the constant-parameter sampler (bvaralg.cpp:157-162,373-455); NULL = none.
-   * Needs a gamma or SV error prior; TVP models are not supported (-5). */
+  /* priors$psi: covariance block (bvaralg.cpp:157-162,373-455; TVP models: bvartvpalg.cpp:143-176,339-407); NULL = none.
+   * Needs a gamma or SV error prior.  sigma output of a TVP model with this block: [T][k*k] per draw. */
   const double* psi_mu;    /* k(k-1)/2 */
   const double* psi_vi;    /* k(k-1)/2 x k(k-1)/2, column-major */
   /* priors$psi$ssvs / $bvs: variable selection on the covariances (bvaralg.cpp:164-202,396-449); the inclusion draws
