@@ -105,9 +105,6 @@ def spec_from_model(obj, n_chains=1, seed=0, chain_offset=0, device=-1, resid_mo
     data, model, priors, initial = obj["data"], obj["model"], obj["priors"], obj["initial"]
     if model.get("structural"):
         raise NotImplementedError("structural models are not on the accelerated path (SURVEY.md section 8f-4)")
-    if "psi" in priors and model.get("tvp") and ("bvs" in priors["psi"] or "bvs" in priors.get("coefficients", {})):
-        raise NotImplementedError("BVS together with the covariance (psi) block of a TVP model is not on the "
-                                  "accelerated path (bvartvpalg.cpp:365-398; SURVEY.md 8f-4)")
     Y = np.asarray(data["Y"], dtype=np.float64)          # T x k
     T, k = Y.shape
     Z = data.get("Z")

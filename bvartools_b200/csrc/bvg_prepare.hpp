@@ -221,8 +221,7 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
     }
     if (P.tvp) {
       // time-varying covariances (bvartvpalg.cpp:143-176): random-walk states with inverse-gamma variances
-      if (P.psi_varsel != BVG_VARSEL_NONE) BVG_FAIL(-5, "BVS on the covariances of a TVP model is not supported");
-      if (P.varsel != BVG_VARSEL_NONE) BVG_FAIL(-5, "BVS together with the covariance block of a TVP model is not supported");
+      if (P.psi_varsel == BVG_VARSEL_SSVS) BVG_FAIL(-7, "SSVS cannot be used with models with time varying parameter.");
       if (k > BVG_TVP_PSI_MAXK) BVG_FAIL(-5, "the covariance block of a TVP model supports at most 8 endogenous variables");
       if (P.n_psi > n) BVG_FAIL(-5, "the covariance block of a TVP model needs k (k - 1) / 2 <= number of coefficients");
       if (!s->psi_shape || !s->psi_rate || !s->psi_init) BVG_FAIL(-4, "priors$psi shape / rate or initial$psi$draw missing");
@@ -362,7 +361,7 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
       for (int i = 0; i < k; ++i) { sh[T * k + i] = s->sv_sigma_h[i]; sh[T * k + k + i] = s->sv_h[0 + (size_t)T * i]; }
       sh += T * k + 2 * k;
     }
-    for (int r = 0; r < P.n_psi; ++r) { sh[r] = 1.0 / s->psi_rate[r]; sh[P.n_psi + r] = s->psi_init[r]; }   // :175-176,169
+    for (int r = 0; r < P.n_psi; ++r) { sh[r] = 1.0 / s->psi_rate[r]; sh[P.n_psi + r] = s->psi_init[r]; sh[2 * P.n_psi + r] = 1.0; }   // :175-176,169,180
   } else {
     P.state_len = bvar_state_len(k, T, n, P.sigma_type, P.n_psi);
     P.state0.assign(P.state_len, 0.0);

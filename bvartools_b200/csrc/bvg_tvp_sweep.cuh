@@ -46,9 +46,9 @@ struct TvpOut {
 };
 
 // state: [0,kk) Sigma_u^-1 | n q = diag(Sigma_v^-1) | n a_init | n lambda | SV: T*k h, k sigma_h, k h_init
-//        | covar: n_psi psi state precisions, n_psi psi_init, T*kk Sigma_t^-1 = Psi_t' Omega_t^-1 Psi_t
+//        | covar: n_psi psi state precisions, n_psi psi_init, n_psi psi lambda, T*kk Sigma_t^-1 = Psi_t' Omega_t^-1 Psi_t
 BVG_HD int tvp_state_len(int k, int T, int n, int sigma_type, int n_psi = 0) {
-  return k * k + 3 * n + (sigma_type == SIG_SV ? T * k + 2 * k : 0) + (n_psi > 0 ? 2 * n_psi + T * k * k : 0);
+  return k * k + 3 * n + (sigma_type == SIG_SV ? T * k + 2 * k : 0) + (n_psi > 0 ? 3 * n_psi + T * k * k : 0);
 }
 // global scratch per chain: T*tri(n) (M_t) + T*n (w_t + eps_t) + T*n (a path)
 // (the warp-per-chain tile path streams full 8 x 8 tiles: tiled_len(n) >= tri(n) doubles per period)
@@ -59,7 +59,7 @@ BVG_HD long long tvp_scratch_len(int T, int n) { return (long long)T * ((tvp_til
 BVG_HD int tvp_smem_len(int k, int T, int n, int sigma_type, bool tiled = false, int n_psi = 0) {
   int len = (tiled ? 2 * tiled_len(n) + 10 * (n + 8) : 3 * tri(n) + 9 * n) + 6 * k * k + 2 * k + k * T;
   if (sigma_type == SIG_SV) len += 3 * k * T + 2 * k;
-  if (n_psi > 0) len += T * k * k + T * n_psi + 2 * n_psi;
+  if (n_psi > 0) len += T * k * k + T * n_psi + 4 * n_psi;
   return len;
 }
 
@@ -86,12 +86,12 @@ BVG_HD void tvp_residuals(const Grp& g, const BvarModel& m, const double* apath,
 // variances are diagonal, so the (n_psi T)^2 precision of :361 decouples into k - 1 independent block-tridiagonal
 // systems whose Cholesky factors are the matching sub-blocks of the joint factor -- the per-row draws with the matching
 // entries of the normal vector ARE the joint draw.  Same recursion as the coefficient draw (see the file header).
-// X[xs * t + c] (times xsign), Y[ys * t], w[ws * t]; normals from site VB_PSI_N, index t * site_stride + site_off + r;
+// X[xs * t + c] (times xsign, times lam[c] when BVS masks the regressors), Y[ys * t], w[ws * t]; normals from site VB_PSI_N, index t * site_stride + site_off + r;
 // draws to out[out_stride * t + r].
 template <class Grp>
 BVG_HD void tvp_single_eq_draw(const Grp& g, const ChainRng& rng, int sweep, int nn, int T, const double* X, int xs,
-                               double xsign, const double* Y, int ys, const double* w, int ws, const double* q,
-                               const double* b_init, int site_stride, int site_off, double* Dt, double* Mi, double* Cq,
+                               double xsign, const double* Y, int ys, const double* w, int ws, const double* lam,
+                               const double* q, const double* b_init, int site_stride, int site_off, double* Dt, double* Mi, double* Cq,
                                double* wv, double* cvec, double* dinv, double* anext, double* tmp, double* tmp2,
                                double* Mpath, double* wpath, double* out, int out_stride, int& fail) {
   const int G = g.size(), tid = g.tid(), tn = tri(nn);
@@ -101,9 +101,9 @@ BVG_HD void tvp_single_eq_draw(const Grp& g, const ChainRng& rng, int sweep, int
     const double ct = (t < T - 1) ? 2.0 : 1.0;
     for (int r = tid; r < nn; r += G) {
       double* Dr = Dt + tri(r);
-      const double xr = xsign * xt[r];
+      const double xr = xsign * xt[r] * (lam ? lam[r] : 1.0);                  // psi_z = psi_z_bvs Lambda (:354-357)
       for (int c = 0; c <= r; ++c) {
-        double gv = xr * (xsign * xt[c]) * wt;
+        double gv = xr * (xsign * xt[c] * (lam ? lam[c] : 1.0)) * wt;
         if (c == r) gv += ct * q[r];
         if (t > 0) gv -= Cq[tri(r) + c];
         Dr[c] = gv;
@@ -202,7 +202,13 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
   double* h = nullptr; double* ew = nullptr; double* svw = nullptr; double* sigma_h = nullptr; double* h_init = nullptr;
   if (sv) { h = sm; sm += k * T; ew = sm; sm += k * T; svw = sm; sm += k * T; sigma_h = sm; sm += k; h_init = sm; sm += k; }
   double* sigt = nullptr; double* psip = nullptr; double* pq = nullptr; double* pinit = nullptr;
-  if (covar) { sigt = sm; sm += T * kk; psip = sm; sm += T * n_psi; pq = sm; sm += n_psi; pinit = sm; sm += n_psi; }
+  double* plam = nullptr; double* pnew = nullptr;
+  const bool psi_bvs = covar && m.psi_varsel == VS_BVS;
+  if (covar) {
+    sigt = sm; sm += T * kk; psip = sm; sm += T * n_psi; pq = sm; sm += n_psi; pinit = sm; sm += n_psi;
+    plam = sm; sm += n_psi; pnew = sm; sm += n_psi;
+  }
+  const int lam_rows = (bvs ? n : 0) + (psi_bvs ? n_psi : 0);
   double* Mpath = scratch;                         // [T][tn]  (tiled: [T][tiled_len(n)])
   double* wpath = scratch + (size_t)T * (tiled ? tiled_len(n) : tn);   // [T][n]
   double* apath = wpath + (size_t)T * n;           // [T][n]
@@ -214,8 +220,8 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
   double* st_h = st_lam + n;
   double* st_psi = st_h + (sv ? T * k + 2 * k : 0);     // n_psi pq | n_psi psi_init | T*kk Sigma_t^-1
   if (covar) {
-    for (int e = tid; e < n_psi; e += G) { pq[e] = st_psi[e]; pinit[e] = st_psi[n_psi + e]; }
-    for (int e = tid; e < T * kk; e += G) sigt[e] = st_psi[2 * n_psi + e];
+    for (int e = tid; e < n_psi; e += G) { pq[e] = st_psi[e]; pinit[e] = st_psi[n_psi + e]; plam[e] = st_psi[2 * n_psi + e]; }
+    for (int e = tid; e < T * kk; e += G) sigt[e] = st_psi[3 * n_psi + e];
   }
   for (int e = tid; e < kk; e += G) sig[e] = state[e];
   for (int e = tid; e < n; e += G) { q[e] = st_q[e]; a_init[e] = st_ai[e]; lam[e] = st_lam[e]; }
@@ -355,11 +361,12 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
             for (int t = 0; t < T; ++t) {
               const double x = m.X[j + M * t];
               double v, sii;
-              if (sv) { sii = ew[t + T * i]; v = sii * U[i + k * t]; }
+              if (svd) { sii = ew[t + T * i]; v = sii * U[i + k * t]; }
               else {
-                sii = sig[i + k * i];
+                const double* sgt = covar ? sigt + (size_t)kk * t : sig;
+                sii = sgt[i + k * i];
                 v = 0.0;
-                for (int i2 = 0; i2 < k; ++i2) v = fma(sig[i + k * i2], U[i2 + k * t], v);
+                for (int i2 = 0; i2 < k; ++i2) v = fma(sgt[i + k * i2], U[i2 + k * t], v);
               }
               const double ar = apath[(size_t)t * n + r];
               const double d0 = lam[r] * ar, d1 = (lam[r] - 1.0) * ar;
@@ -385,8 +392,47 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
       for (int i = 1; i < k; ++i) {
         const int o = (i * (i - 1)) / 2;
         tvp_single_eq_draw(g, rng, sweep, i, T, U, k, -1.0, U + i, k, sv ? ew + (size_t)T * i : sig + i + k * i, sv ? 1 : 0,
-                           pq + o, pinit + o, n_psi, o, Dt, Mi, Cq, wv, cvec, dinv, anext, tmp, tmp2, Mpath, wpath,
-                           psip + o, n_psi, fail);
+                           psi_bvs ? plam + o : nullptr, pq + o, pinit + o, n_psi, o, Dt, Mi, Cq, wv, cvec, dinv, anext,
+                           tmp, tmp2, Mpath, wpath, psip + o, n_psi, fail);
+      }
+      if (psi_bvs) {
+        // BVS on the time-varying covariances (:365-398).  psi_AG = Lambda psi is computed once (:372), so the
+        // decisions of different positions are independent given the pre-sweep Lambda; theta0 / theta1 differ only in
+        // row r = (i, j), i.e. only the residuals of equation i:  e0_t = u_it + sum_{j' != j} u_j't lam_j' psi_j't,
+        // e1_t = e0_t + u_jt psi_rt, and l1 - l0 = -1/2 sum_t w_it (e1_t^2 - e0_t^2) + log prior odds.
+        for (int r = tid; r < n_psi; r += G) {
+          double newlam = plam[r];
+          if (m.psi_include[r]) {
+            int i = 1;
+            while ((i * (i + 1)) / 2 <= r) ++i;
+            const int o = (i * (i - 1)) / 2, j = r - o;
+            const double lp0 = log(1.0 - m.psi_inprior[r]), lp1 = log(m.psi_inprior[r]);
+            const double g1 = log(rng.uniform(VB_PSI_U1, sweep, r));
+            const bool gate = (plam[r] == 1.0) ? (g1 < lp1) : (g1 < lp0);
+            if (gate) {
+              double dq = 0.0;
+              for (int t = 0; t < T; ++t) {
+                const double* ut = U + (size_t)k * t;
+                const double* ps = psip + (size_t)n_psi * t + o;
+                double e0 = ut[i];
+                for (int j2 = 0; j2 < i; ++j2)
+                  if (j2 != j) e0 = fma(ut[j2], plam[o + j2] * ps[j2], e0);
+                const double d = ut[j] * ps[j];
+                const double wt = sv ? ew[t + T * i] : sig[i + k * i];
+                dq = fma(wt, d * (2.0 * e0 + d), dq);
+              }
+              const double bayes = -0.5 * dq + (lp1 - lp0);
+              const double g2 = log(rng.uniform(VB_PSI_U2, sweep, r));
+              newlam = (bayes >= g2) ? 1.0 : 0.0;
+            }
+          }
+          pnew[r] = newlam;
+        }
+        g.sync();
+        for (int r = tid; r < n_psi; r += G) plam[r] = pnew[r];
+        g.sync();
+        for (int e = tid; e < n_psi * T; e += G) psip[e] *= plam[e % n_psi];                 // :396
+        g.sync();
       }
       // u_t <- Psi_t u_t (:406): rows from the last to the first, in place
       for (int t = tid; t < T; t += G) {
@@ -576,9 +622,10 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
       for (int e = tid; e < n * T; e += G) oc[e] = apath[e];
       double* ov = out.sigma_v + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n;
       for (int r = tid; r < n; r += G) ov[r] = 1.0 / q[r];                             // :525
-      if (out.lambda != nullptr) {
-        double* ol = out.lambda + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n;
-        for (int r = tid; r < n; r += G) ol[r] = lam[r];
+      if (out.lambda != nullptr && lam_rows > 0) {
+        double* ol = out.lambda + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)lam_rows;
+        if (bvs) for (int r = tid; r < n; r += G) ol[r] = lam[r];
+        if (psi_bvs) for (int r = tid; r < n_psi; r += G) ol[(bvs ? n : 0) + r] = plam[r];   // draws_lambda_a0, :517-519
       }
     }
     g.sync();
@@ -592,8 +639,8 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
     for (int e = tid; e < k; e += G) { st_h[T * k + e] = sigma_h[e]; st_h[T * k + k + e] = h_init[e]; }
   }
   if (covar) {
-    for (int e = tid; e < n_psi; e += G) { st_psi[e] = pq[e]; st_psi[n_psi + e] = pinit[e]; }
-    for (int e = tid; e < T * kk; e += G) st_psi[2 * n_psi + e] = sigt[e];
+    for (int e = tid; e < n_psi; e += G) { st_psi[e] = pq[e]; st_psi[n_psi + e] = pinit[e]; st_psi[2 * n_psi + e] = plam[e]; }
+    for (int e = tid; e < T * kk; e += G) st_psi[3 * n_psi + e] = sigt[e];
   }
   if (fail && tid == 0) out.status[chain_local] = 1;
   g.sync();

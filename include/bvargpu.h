@@ -134,7 +134,8 @@ typedef struct bvg_spec {
   int32_t psi_n_include;
   /* TVP models (bvartvpalg.cpp:143-176,339-407,485-499): the free elements of Psi_t follow random walks; inverse-gamma
    * prior of their state variances and the initial draw (initial$psi$draw).  NULL for constant-parameter models.
-   * Variable selection on the covariances or the coefficients is not available together with the TVP psi block (-5). */
+   * BVS on the time-varying covariances (psi_varsel = BVG_VARSEL_BVS, bvartvpalg.cpp:365-398) is supported; SSVS is not
+   * defined for TVP models (-7). */
   const double* psi_shape;     /* k(k-1)/2 */
   const double* psi_rate;      /* k(k-1)/2 */
   const double* psi_init;      /* k(k-1)/2 */

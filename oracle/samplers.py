@@ -435,9 +435,14 @@ def bvartvpalg(obj, variates: VariateSource | None = None, literal=True, table="
     covar = "psi" in priors
     if covar:
         pp = priors["psi"]
-        if "bvs" in pp:
-            raise NotImplementedError("BVS on the time-varying covariances (:365-398) is not restated")
         n_psi = k * (k - 1) // 2
+        psi_bvs = "bvs" in pp                                                                    # :152-157,177-185
+        if psi_bvs:
+            psel = pp["bvs"]
+            psi_lprior0 = np.log(1.0 - np.asarray(psel["inprior"], dtype=np.float64).reshape(-1))
+            psi_lprior1 = np.log(np.asarray(psel["inprior"], dtype=np.float64).reshape(-1))
+            psi_include = np.asarray(psel["include"], dtype=np.int64).reshape(-1) - 1
+            psi_lam = np.ones(n_psi)
         psi_prior_mu = np.asarray(pp["mu"], dtype=np.float64).reshape(-1)
         psi_prior_vi = np.asarray(pp["v_i"], dtype=np.float64)
         psi_post_shape = np.asarray(pp["shape"], dtype=np.float64).reshape(-1) + 0.5 * tt      # :149
@@ -459,6 +464,7 @@ def bvartvpalg(obj, variates: VariateSource | None = None, literal=True, table="
     draws_sigma_u = np.zeros((k * k * tt if per_t_sigma else k * k, iters))
     draws_sigma_sigma = np.zeros((k * k, iters)) if sv else None
     draws_lambda = np.zeros((n, iters)) if bvs else None
+    draws_psi_lambda = np.zeros((n_psi, iters)) if covar and psi_bvs else None
 
     if literal:
         H = np.eye(n * tt)
@@ -516,12 +522,37 @@ def bvartvpalg(obj, variates: VariateSource | None = None, literal=True, table="
                 for j in range(tt):
                     psi_z[j * (k - 1) + i - 1, j * n_psi + i * (i - 1) // 2: j * n_psi + (i + 1) * i // 2] = -u[:i, j]
                     dco[j * (k - 1) + i - 1] = omega_diag[j * k + i]                      # :350
+            if psi_bvs:
+                psi_z_bvs = psi_z
+                psi_z = psi_z_bvs * np.tile(psi_lam, tt)[None, :]                         # :354-357
             pzz = psi_z.T * dco[None, :]                                                  # :359
             phsh = Hpsi.T @ np.kron(np.eye(tt), np.diag(psi_sigma_v_i)) @ Hpsi            # :360
             ppv = phsh + pzz @ psi_z
             ppm = sla.solve(ppv, phsh @ np.tile(psi_init, tt) + pzz @ psi_y)              # :362
             psi = ppm + sla.solve_triangular(sla.cholesky(ppv, lower=False),
                                              vs.normal("psi_normal", draw, (n_psi * tt,)), lower=False)   # :363
+            if psi_bvs:                                                                   # :365-398
+                psi_mat = psi.reshape(n_psi, tt, order="F")
+                psi_AG = psi_lam[:, None] * psi_mat                                       # :372 (stale inside the loop)
+                pg1 = np.log(vs.uniform("psi_u1", draw, (n_psi,)))
+                pg2 = np.log(vs.uniform("psi_u2", draw, (n_psi,)))
+                new_plam = psi_lam.copy()
+                for j in psi_include:
+                    if psi_lam[j] == 1 and pg1[j] >= psi_lprior1[j]:
+                        continue
+                    if psi_lam[j] == 0 and pg1[j] >= psi_lprior0[j]:
+                        continue
+                    th0 = psi_AG.copy()
+                    th1 = psi_AG.copy()
+                    th0[j] = 0.0
+                    th1[j] = psi_mat[j]
+                    r0 = psi_y - psi_z_bvs @ th0.reshape(-1, order="F")
+                    r1 = psi_y - psi_z_bvs @ th1.reshape(-1, order="F")
+                    l0 = -float(r0 @ (dco * r0)) / 2 + psi_lprior0[j]
+                    l1 = -float(r1 @ (dco * r1)) / 2 + psi_lprior1[j]
+                    new_plam[j] = 1.0 if (l1 - l0) >= pg2[j] else 0.0
+                psi_lam = new_plam
+                psi = (psi_lam[:, None] * psi_mat).reshape(-1, order="F")                 # :396
             Psi_t = np.tile(np.eye(k)[None], (tt, 1, 1))
             for j in range(tt):
                 for i in range(1, k):
@@ -601,12 +632,16 @@ def bvartvpalg(obj, variates: VariateSource | None = None, literal=True, table="
             draws_sigma_v[:, pos] = 1.0 / sigma_v_i                                       # :525
             if bvs:
                 draws_lambda[:, pos] = lam
+            if covar and psi_bvs:
+                draws_psi_lambda[:, pos] = psi_lam                                        # :517-519
 
     posteriors = {"a0": None, "a": None, "b": None, "c": None, "sigma": None}
     _split_rows(posteriors, draws_coef, draws_lambda, n_a, n_b, n_c, tvp_T=tt, sig=draws_sigma_v)
     posteriors["sigma"] = {"coeffs": draws_sigma_u}
     if sv:
         posteriors["sigma"]["sigma"] = draws_sigma_sigma
+    if draws_psi_lambda is not None:
+        posteriors["sigma"]["lambda"] = draws_psi_lambda                                  # :605-613
     return {"data": obj["data"], "model": obj["model"], "priors": obj["priors"], "posteriors": posteriors}
 
 

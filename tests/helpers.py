@@ -101,7 +101,7 @@ def model_covar_gamma(K=3, p=2, nobs=70, iterations=20, burnin=5, seed=77, bvs=F
     return add_priors(m, coef=dict(v_i=1, v_i_det=0.1), sigma=dict(shape=3, rate=1e-4, covar=True), ssvs=ssvs, bvs=bv)
 
 
-def model_tvp_covar(K=3, p=1, nobs=24, iterations=8, burnin=3, seed=41, sv=True):
+def model_tvp_covar(K=3, p=1, nobs=24, iterations=8, burnin=3, seed=41, sv=True, bvs=False, psi_bvs=False):
     """TVP-VAR with time-varying covariances (Psi_t random walks, bvartvpalg.cpp:339-407) and SV or inverse-gamma
     measurement variances."""
     y = synth_var(K, p, nobs, seed)
@@ -109,7 +109,8 @@ def model_tvp_covar(K=3, p=1, nobs=24, iterations=8, burnin=3, seed=41, sv=True)
     sigma = dict(shape=3, rate=1e-4, covar=True)
     if sv:
         sigma.update(mu=0, v_i=0.01, sigma_h=0.05, constant=1e-4)
-    return add_priors(m, coef=dict(v_i=1, v_i_det=0.1, shape=3, rate=1e-4, rate_det=0.01), sigma=sigma)
+    return add_priors(m, coef=dict(v_i=1, v_i_det=0.1, shape=3, rate=1e-4, rate_det=0.01), sigma=sigma,
+                      bvs=dict(inprior=0.5, exclude_det=True, covar=psi_bvs) if (bvs or psi_bvs) else None)
 
 
 def model_c5(K=20, p=4, nobs=204, iterations=200, burnin=50, seed=2042004):

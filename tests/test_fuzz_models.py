@@ -20,8 +20,6 @@ def _random_model(rng):
     y = helpers.synth_var(k, max(p, 1), nobs, int(rng.integers(1, 1000)))
     m = helpers.gen_var(y, p=p, deterministic=det, iterations=6, burnin=2, tvp=tvp, sv=sv)
     tvp_covar = kind in ("tvp_sv_covar", "tvp_gamma_covar") and k > 1 and k * (k - 1) // 2 <= k * (k * p + (det != "none"))
-    if tvp_covar:
-        sel = "none"                                       # BVS is not combined with the TVP covariance block
     if kind in ("gamma", "gamma_covar", "tvp_gamma_covar"):
         sigma = dict(shape=3, rate=1e-3, covar=((kind == "gamma_covar" and k > 1) or tvp_covar))
     elif sv:
@@ -31,6 +29,8 @@ def _random_model(rng):
         sigma = dict(df="k", scale=1)
     ssvs = dict(inprior=0.5, tau=(0.05, 10.0), exclude_det=bool(rng.integers(0, 2))) if sel == "ssvs" and not sv and not tvp else None
     bvs = dict(inprior=0.5, exclude_det=bool(rng.integers(0, 2))) if sel == "bvs" else None
+    if bvs is not None and tvp_covar:
+        bvs["covar"] = bool(rng.integers(0, 2))            # BVS on the time-varying covariances as well
     obj = helpers.add_priors(m, coef=dict(v_i=1, v_i_det=0.1, shape=3, rate=1e-4, rate_det=0.01), sigma=sigma, ssvs=ssvs,
                              bvs=bvs)
     return obj, (k, p, nobs, kind, sel, det)

@@ -63,6 +63,8 @@ CASES["tvp_covar_sv"] = (lambda: helpers.model_tvp_covar(), {})
 CASES["tvp_covar_sv_k4"] = (lambda: helpers.model_tvp_covar(K=4, p=1, nobs=20, iterations=6, burnin=2), {})
 CASES["tvp_covar_sv_k2"] = (lambda: helpers.model_tvp_covar(K=2, p=2, nobs=22), {})
 CASES["tvp_covar_gamma"] = (lambda: helpers.model_tvp_covar(sv=False), {})
+CASES["tvp_covar_sv_psi_bvs"] = (lambda: helpers.model_tvp_covar(K=4, p=1, nobs=20, iterations=8, burnin=2, psi_bvs=True), {})
+CASES["tvp_covar_gamma_bvs"] = (lambda: helpers.model_tvp_covar(sv=False, bvs=True), {})
 
 
 def _exogen(sv=False, ssvs=False):
