@@ -432,27 +432,32 @@ cudaError_t launch_tsse(const double* draws, long long n_chains, long long iters
   if (n_chains > 0x7fffffffLL || tiles > 65535) return cudaErrorInvalidValue;
   const size_t ns = (size_t)n_chains * (size_t)rows;
   double *sums = nullptr, *tsum = nullptr, *acov = nullptr, *spec = nullptr;
+  auto release = [&]() {
+    if (sums) cudaFreeAsync(sums, stream);
+    if (tsum) cudaFreeAsync(tsum, stream);
+    if (spec) cudaFreeAsync(spec, stream);
+    if (acov) cudaFreeAsync(acov, stream);
+  };
   cudaError_t e;
-  if ((e = cudaMallocAsync((void**)&sums, ns * 8, stream)) != cudaSuccess) return e;
-  if ((e = cudaMallocAsync((void**)&tsum, ns * 8, stream)) != cudaSuccess) return e;
-  if ((e = cudaMallocAsync((void**)&spec, ns * 8, stream)) != cudaSuccess) return e;
-  if ((e = cudaMallocAsync((void**)&acov, ns * (size_t)(L + 1) * 8, stream)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&sums, ns * 8, stream)) != cudaSuccess ||
+      (e = cudaMallocAsync((void**)&tsum, ns * 8, stream)) != cudaSuccess ||
+      (e = cudaMallocAsync((void**)&spec, ns * 8, stream)) != cudaSuccess ||
+      (e = cudaMallocAsync((void**)&acov, ns * (size_t)(L + 1) * 8, stream)) != cudaSuccess) {
+    release();
+    return e;
+  }
   const dim3 grid((unsigned)n_chains, (unsigned)tiles);
   tsse_mean_kernel<<<grid, 256, 0, stream>>>(draws, iters, rows, sums, tsum);
   const int nlg = (L + TS_LG) / TS_LG;
   size_t smem = (size_t)(TS_SEG + nlg * TS_LG) * TS_ROWS * 8;
   const size_t red = (size_t)256 * TS_LG * 8;
   if (red > smem) smem = red;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(tsse_acov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(tsse_acov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);   // per device: cheap
   tsse_acov_kernel<<<grid, 256, smem, stream>>>(draws, iters, rows, L, sums, acov);
   tsse_spec_kernel<<<(unsigned)((ns + 127) / 128), 128, 0, stream>>>((long long)ns, iters, L, sums, tsum, acov, spec);
   tsse_combine_kernel<<<(unsigned)rows, 128, 0, stream>>>(n_chains, iters, rows, spec, d_out);
   e = cudaGetLastError();
-  cudaFreeAsync(sums, stream); cudaFreeAsync(tsum, stream); cudaFreeAsync(spec, stream); cudaFreeAsync(acov, stream);
+  release();
   return e;
 }
 
