@@ -216,11 +216,17 @@ cudaError_t launch_quantiles(const double* draws, long long n_draws, long long r
   long long* rank = nullptr;
   unsigned int* hist = nullptr;
   cudaError_t e;
-  if ((e = cudaMallocAsync((void**)&prefix, nt * 8, stream)) != cudaSuccess) return e;
-  if ((e = cudaMallocAsync((void**)&rank, nt * 8, stream)) != cudaSuccess) return e;
-  if ((e = cudaMallocAsync((void**)&cnt_eq, nt * 8, stream)) != cudaSuccess) return e;
-  if ((e = cudaMallocAsync((void**)&min_gt, nt * 8, stream)) != cudaSuccess) return e;
-  if ((e = cudaMallocAsync((void**)&hist, nt * 256 * 4, stream)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&prefix, nt * 8, stream)) != cudaSuccess ||
+      (e = cudaMallocAsync((void**)&rank, nt * 8, stream)) != cudaSuccess ||
+      (e = cudaMallocAsync((void**)&cnt_eq, nt * 8, stream)) != cudaSuccess ||
+      (e = cudaMallocAsync((void**)&min_gt, nt * 8, stream)) != cudaSuccess ||
+      (e = cudaMallocAsync((void**)&hist, nt * 256 * 4, stream)) != cudaSuccess) {
+    if (prefix) cudaFreeAsync(prefix, stream);
+    if (rank) cudaFreeAsync(rank, stream);
+    if (cnt_eq) cudaFreeAsync(cnt_eq, stream);
+    if (min_gt) cudaFreeAsync(min_gt, stream);
+    return e;
+  }
   cudaMemsetAsync(hist, 0, nt * 256 * 4, stream);
   const int tb = 128, gb = (int)((nt + tb - 1) / tb);
   select_init_kernel<<<gb, tb, 0, stream>>>(rows, n_probs, n_draws, d_probs, prefix, rank, cnt_eq, min_gt);
