@@ -11,7 +11,7 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = ["shard", "shard_weighted", "model_cost", "run_sharded", "allreduce_moments", "gather_draws", "bind_to_gpu_numa",
-           "allreduce_information_criteria"]
+           "allreduce_information_criteria", "allreduce_time_series_se"]
 
 
 def shard(n_items: int, rank: int, world: int):
@@ -124,6 +124,22 @@ def allreduce_information_criteria(ll_sum, n_draws, tot_pars, tt, device=None):
     acc = acc.cpu().numpy()
     ll = float(acc[:v.size].sum() / acc[v.size])
     return information_criteria(ll, tot_pars, tt)
+
+
+def allreduce_time_series_se(ts_local, n_chains_local, device=None):
+    """Time-series SE over ALL ranks' chains from each rank's `ChainSampler.time_series_se` (coda pools chains as
+    sqrt(mean_c spec_c / (iters * chains)), so ts_r^2 * chains_r^2 = sum_c spec_c / iters adds up across ranks):
+    all-reduce of (ts_r^2 chains_r^2, chains_r).  Pass zeros and 0 for an empty shard."""
+    import torch
+    dist, _, world = _dist()
+    ts = np.asarray(ts_local, dtype=np.float64).reshape(-1)
+    acc = torch.empty(ts.size + 1, dtype=torch.float64, device=device or "cpu")
+    acc[:ts.size] = torch.from_numpy(ts * ts * float(n_chains_local) ** 2)
+    acc[ts.size] = float(n_chains_local)
+    if dist is not None and world > 1:
+        dist.all_reduce(acc)
+    acc = acc.cpu().numpy()
+    return np.sqrt(acc[:ts.size]) / acc[ts.size]
 
 
 def gather_draws(local, n_chains_total, dst=0):

@@ -50,7 +50,10 @@ def _worker(rank, world, port, total, q):
                 u = Y.T - coef[c, j].reshape(3, -1, order="F") @ Z.T
                 ll_t += ob.loglik_normal(u, sig[c, j].reshape(3, 3, order="F"))
         ic = D.allreduce_information_criteria(ll_t, coef.shape[0] * coef.shape[1], Z.shape[1], Y.shape[0])
-        q.put((rank, off, coef.shape[0], mean, var, cnt, gathered, ic))
+        # time-series SE: this rank's pooled value (oracle restatement standing in for bvg_sampler_tsse)
+        ts_local = ob.time_series_se(coef.reshape(-1, 21), coef.shape[0]) if coef.shape[0] else np.zeros(21)
+        ts = D.allreduce_time_series_se(ts_local, coef.shape[0])
+        q.put((rank, off, coef.shape[0], mean, var, cnt, gathered, ic, ts))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -78,8 +81,10 @@ def test_sharded_job_equals_single_process_job(world, total):
     assert sum(g[2] for g in got) == total
     assert [g[1] for g in got] == [D.shard(total, r, world)[0] for r in range(world)]
     flat = full.reshape(-1, 21)
-    for rank, off, cnt_local, mean, var, cnt, gathered, ic in got:
+    want_ts = ob.time_series_se(flat, total)
+    for rank, off, cnt_local, mean, var, cnt, gathered, ic, ts in got:
         assert cnt == flat.shape[0]
+        np.testing.assert_allclose(ts, want_ts, rtol=1e-12)
         for key in ("LL", "AIC", "BIC", "HQ"):
             assert abs(ic[key] - want_ic[key]) <= 1e-10 * abs(want_ic[key]), key
         np.testing.assert_allclose(mean, flat.mean(axis=0), rtol=1e-12, atol=1e-14)
