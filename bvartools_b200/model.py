@@ -39,7 +39,8 @@ def _lagname(base: Sequence[str], i: int, width: int, sep: str = ".") -> list[st
 
 
 def gen_var(data, p=2, exogen=None, s=None, deterministic="const", seasonal=False, structural=False,
-            tvp=False, sv=False, fcst=None, iterations=50000, burnin=5000, names=None, exo_names=None):
+            tvp=False, sv=False, fcst=None, iterations=50000, burnin=5000, names=None, exo_names=None,
+            frequency=1, start_cycle=1):
     """VAR model generator (R/gen_var.R:74-305).
 
     `data` is a (rows x k) array (the R version takes a `ts`).  `p` (and `s`) may be a sequence: all models then
@@ -50,10 +51,10 @@ def gen_var(data, p=2, exogen=None, s=None, deterministic="const", seasonal=Fals
     if names is None:
         names = [f"y{i + 1}" for i in range(k)] if k > 1 else ["y"]
     names = list(names)
-    if seasonal:
-        raise NotImplementedError("seasonal dummies are outside the accelerated path (SURVEY.md section 8f)")
     if deterministic not in ("none", "const", "trend", "both"):
         raise ValueError("Argument 'deterministic' must be 'none', 'const', 'trend' or 'both'.")
+    if seasonal and deterministic not in ("const", "both"):                       # R/gen_var.R:91-93
+        raise ValueError("Argument 'deterministic' must be either 'const' or 'both' when using 'seasonal = TRUE'.")
     if k == 1 and structural:
         raise ValueError("Model must contain at least two endogenous variables for structural analysis.")
 
@@ -92,6 +93,19 @@ def gen_var(data, p=2, exogen=None, s=None, deterministic="const", seasonal=Fals
         cols.append(np.arange(1, tt + 1, dtype=np.float64)[:, None])
         colnames.append("trend")
         det_name.append("trend")
+    if seasonal and int(frequency) > 1:
+        # R/gen_var.R:188-203: frequency - 1 dummies; the R version reads frequency / cycle from the `ts` attributes,
+        # here `frequency` and `start_cycle` (cycle, 1-based, of the first row of `data`) are arguments
+        freq = int(frequency)
+        cyc = (int(start_cycle) - 1 + drop + np.arange(tt)) % freq + 1
+        first = int(np.argmax(cyc == 1)) + 1                                       # which(cycle(temp) == 1)[1]
+        pos = (list(range(1, freq + 1)) * 2)[first - 1: first + freq - 2]
+        for i in range(freq - 1):
+            s_temp = np.zeros(freq)
+            s_temp[pos[i] - 1] = 1.0
+            cols.append(np.resize(s_temp, tt)[:, None])                            # rep(s_temp, length.out = tt)
+            colnames.append(f"season.{i + 1}")
+            det_name.append(f"season.{i + 1}")
     temp = np.hstack(cols)
 
     model = {"type": "VAR", "endogen": {"variables": names, "lags": 0}}

@@ -101,6 +101,23 @@ def test_gen_var_grid_shares_sample():
     assert all(p["priors"]["sigma"]["df"] == 3.0 for p in pri)
 
 
+def test_seasonal_dummies_follow_the_cycle():
+    """R/gen_var.R:188-203: frequency - 1 dummies, the first one on the first cycle-1 row of the trimmed sample."""
+    from bvartools_b200 import model as M
+    y = helpers.synth_var(2, 1, 30, 3)
+    m = M.gen_var(y, p=1, deterministic="const", seasonal=True, frequency=4, start_cycle=2, iterations=5, burnin=2)
+    assert m["model"]["deterministic"] == ["const", "season.1", "season.2", "season.3"]
+    Z = m["data"]["Z"]
+    # first row of the trimmed sample is cycle 3: cycle 1 arrives at row 3 (1-based) -> dummies on cycles 1, 2, 3
+    assert Z[:6, -3].tolist() == [0, 0, 1, 0, 0, 0] and Z[:6, -2].tolist() == [0, 0, 0, 1, 0, 0]
+    assert Z[:6, -1].tolist() == [1, 0, 0, 0, 1, 0]
+    assert np.all(Z[:, -3:].sum(axis=1) <= 1)
+    obj = M.add_priors(m, coef=dict(v_i=1, v_i_det=0.1), sigma=dict(df="k", scale=1))
+    assert obj["priors"]["coefficients"]["v_i"].shape == (2 * (2 + 4), 2 * (2 + 4))
+    with pytest.raises(ValueError, match="seasonal"):
+        M.gen_var(y, p=1, deterministic="trend", seasonal=True, frequency=4)
+
+
 def test_minnesota_and_ssvs_priors():
     obj = helpers.gen_var(helpers.synth_var(4, 2, 90, 3), p=2, deterministic="const", iterations=5, burnin=1)
     m = helpers.add_priors(obj, coef=dict(minnesota=dict(kappa0=2, kappa1=0.5, kappa3=5)), sigma=dict(df="k", scale=1))
