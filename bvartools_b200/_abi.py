@@ -44,6 +44,7 @@ class BvgSpec(C.Structure):
         ("tvp_shape", _dp), ("tvp_rate", _dp), ("a_init", _dp), ("psi_mu", _dp), ("psi_vi", _dp),
         ("psi_varsel", C.c_int32), ("psi_tau0", _dp), ("psi_tau1", _dp), ("psi_inprior", _dp), ("psi_include", _ip),
         ("psi_n_include", C.c_int32), ("psi_shape", _dp), ("psi_rate", _dp), ("psi_init", _dp),
+        ("structural", C.c_int32),
         ("resid_mode", C.c_int32), ("threads_per_chain", C.c_int32), ("sweeps_per_launch", C.c_int32),
         ("inject", C.POINTER(BvgInject)),
     ]
@@ -82,7 +83,9 @@ class Spec:
 
     @property
     def n(self):
-        return self.c.k * self.c.M
+        """coefficient rows per draw: k M, plus the k (k - 1) / 2 structural (A0) coefficients"""
+        k = self.c.k
+        return k * self.c.M + (k * (k - 1) // 2 if self.c.structural else 0)
 
     def out_rows(self):
         """rows per retained draw of (coef, sigma, lambda, sigma_h, sigma_v) -- mirrors bvg_out_rows()."""
@@ -103,15 +106,17 @@ def spec_from_model(obj, n_chains=1, seed=0, chain_offset=0, device=-1, resid_mo
                     threads_per_chain=0, sweeps_per_launch=0, mixture="ksc1998", inject=None) -> Spec:
     """bvarmodel list -> bvg_spec (the unpacking of src/bvaralg.cpp:9-249 / src/bvartvpalg.cpp:11-279)."""
     data, model, priors, initial = obj["data"], obj["model"], obj["priors"], obj["initial"]
-    if model.get("structural"):
-        raise NotImplementedError("structural models are not on the accelerated path (SURVEY.md section 8f-4)")
+    structural = bool(model.get("structural"))
+    if structural and model.get("tvp"):
+        raise NotImplementedError("structural TVP models are not on the accelerated path (SURVEY.md section 8f-4)")
     Y = np.asarray(data["Y"], dtype=np.float64)          # T x k
     T, k = Y.shape
     Z = data.get("Z")
     M = 0 if Z is None else np.asarray(Z).shape[1]
-    n = k * M
+    n = k * M + (k * (k - 1) // 2 if structural and k > 1 else 0)
     sp = Spec()
     c = sp.c
+    c.structural = 1 if structural and k > 1 else 0
     c.abi_version, c.device = ABI_VERSION, device
     c.k, c.T, c.M = k, T, M
     c.tvp = 1 if model.get("tvp") else 0

@@ -77,6 +77,10 @@ static void rows_of(const Prepared& P, long long* coef, long long* sigma, long l
   *coef = P.tvp ? n * T : n;
   *sigma = tv_sigma_of(P) ? k * k * T : k * k;
   *lambda = ((P.varsel != BVG_VARSEL_NONE) ? n : 0) + ((P.psi_varsel != BVG_VARSEL_NONE) ? k * (k - 1) / 2 : 0);
+  if (P.structural) {                       // stored rows: [a | b | c | a0]; the mask itself is not an output
+    *coef = P.n_user;
+    *lambda = (P.varsel_user != BVG_VARSEL_NONE) ? P.n_user : 0;
+  }
   *sh = svm ? k : 0;
   *sv = P.tvp ? n : 0;
 }
@@ -471,6 +475,7 @@ int bvg_loglik_draws(const double* dev_coef, const double* dev_sigma, int64_t n_
 
 int bvg_sampler_loglik(bvg_sampler* s, double* host_ll_t, void* cuda_stream) {
   if (!s || !host_ll_t) return fail(-1, "sampler / output is NULL");
+  if (s->P.structural) return fail(-6, "the log-likelihood kernels do not cover structural models");
   CK(cudaSetDevice(s->device));
   const int T = s->P.T;
   cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -575,6 +580,7 @@ static bool host_ols_moments(const double* Y, const double* X, int k, int M, int
 
 int bvg_sampler_loglik_total(bvg_sampler* s, double* total, void* cuda_stream) {
   if (!s || !total) return fail(-1, "sampler / output is NULL");
+  if (s->P.structural) return fail(-6, "the log-likelihood kernels do not cover structural models");
   CK(cudaSetDevice(s->device));
   const bool fast = !s->P.tvp && !tv_sigma_of(s->P) && s->P.M > 0 && s->bm.XX && s->bm.Aols && s->bm.SSE &&
                     s->P.k <= 32;

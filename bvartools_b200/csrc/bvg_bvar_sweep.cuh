@@ -60,6 +60,7 @@ struct BvarModel {
   const double* mix_p; const double* mix_mu; const double* mix_s2;   // n_mix each
   const double* omega_off;         // k x k off-diagonal part of the initial Sigma^-1 (gamma prior), zero diagonal
   // covariance (psi) block (bvaralg.cpp:373-455); n_psi = 0: none
+  int a0_from;                     // structural models: first internal row of the -y block (k M_user); -1 otherwise
   int n_psi;                       // k (k - 1) / 2
   const double* psi_vi;            // n_psi x n_psi prior precision (col-major); its diagonal lives in the chain state
   const double* psi_vmu;           // n_psi  OFF-diagonal part of (prior precision times prior mean)
@@ -1059,7 +1060,23 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
     }
 
     // ---- store (bvaralg.cpp:518-559)
-    if (keep && n > 0) {
+    if (keep && n > 0 && m.a0_from >= 0) {
+      // structural model: the kept rows [a | b | c | a0 (variable j, equation i > j)] of the masked augmented system
+      const int a0 = m.a0_from, n_out = a0 + (k * (k - 1)) / 2;
+      double* oc = out.coef + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n_out;
+      double* ol = (out.lambda != nullptr) ? out.lambda + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n_out
+                                           : nullptr;
+      for (int r = tid; r < n; r += G) {
+        int o = r;
+        if (r >= a0) {
+          const int j = (r - a0) / k, i = (r - a0) % k;
+          if (i <= j) continue;
+          o = a0 + j * (k - 1) - (j * (j - 1)) / 2 + (i - j - 1);
+        }
+        oc[o] = a[r];
+        if (ol != nullptr) ol[o] = lam[r];
+      }
+    } else if (keep && n > 0) {
       double* oc = out.coef + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n;
       for (int r = tid; r < n; r += G) oc[r] = a[r];
       if (out.lambda != nullptr && varsel != VS_NONE) {

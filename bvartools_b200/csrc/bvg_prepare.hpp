@@ -30,6 +30,10 @@ struct Prepared {
        psi_vshape = -1, psi_vrate = -1;
   int kron = 0;   // 1 = flat-prior Kronecker sweep (bvg_kron_sweep.cuh)
   int n_psi = 0;  // k (k - 1) / 2 when the covariance (psi) block is active, else 0
+  // structural models (A0): the sampler runs on the regressors [x; -y] with the positions (variable j, equation i <= j)
+  // of the -y block permanently masked; n_user = k M_user + k (k - 1) / 2 rows are stored, varsel_user is what the
+  // caller asked for (the mask itself rides on the BVS machinery), a0_from = k M_user (first row of the A0 block)
+  int structural = 0, n_user = 0, varsel_user = 0, a0_from = -1;
   int psi_varsel = 0;
   long psi_mu = -1, psi_vi = -1, psi_vmu = -1, psi_tau0 = -1, psi_tau1 = -1, psi_inprior = -1;
   std::vector<unsigned char> psi_include;
@@ -74,7 +78,80 @@ static const double OCSN_S2[10] = {0.11265, 0.17788, 0.26768, 0.40611, 0.62699, 
 
 #define BVG_FAIL(code, msg) do { P.error = (msg); return (code); } while (0)
 
+static inline int prepare_impl(const bvg_spec* s, Prepared& P);
+
+// internal coefficient index of user row r (reference order [a | b | c | a0], a0 by variable j then equation i > j)
+static inline int structural_pos(int r, int k, int Mu) {
+  if (r < k * Mu) return r;
+  int q = r - k * Mu;
+  for (int j = 0; j < k; ++j) {
+    if (q < k - 1 - j) return k * (Mu + j) + j + 1 + q;
+    q -= k - 1 - j;
+  }
+  return -1;
+}
+
+// Structural models (model$structural, R/gen_var.R:243-251; the A0 columns of data$SUR): equation i also has the
+// regressors -y_jt, j < i.  z = [kron(x', I_k) | y_A0] is the column selection of kron([x; -y]', I_k) that drops
+// (variable j, equation i <= j), so the reference's posterior precision is the kept block of the precision of the
+// augmented VAR with those positions masked; masked positions decouple (prior identity) and are zeroed after the draw --
+// exactly what BVS does with lambda = 0 on positions that are never re-drawn.  The model is therefore rewritten as a
+// BVS model on M + k regressors (empty `include` when the caller uses no selection) and prepared as usual.
 static inline int prepare(const bvg_spec* s, Prepared& P) {
+  if (s == nullptr) BVG_FAIL(-1, "spec is NULL");
+  if (!s->structural) return prepare_impl(s, P);
+  const int k = s->k, T = s->T, Mu = s->M;
+  if (k < 2) BVG_FAIL(-7, "Model must contain at least two endogenous variables for structural analysis.");
+  if (k > 64 || T < 2 || Mu < 0 || !s->Y || (Mu > 0 && !s->X)) BVG_FAIL(-3, "invalid dimensions or missing data");
+  if (s->tvp) BVG_FAIL(-5, "structural TVP models are not supported");
+  if (s->varsel == BVG_VARSEL_SSVS) BVG_FAIL(-5, "SSVS on a structural model is not supported");
+  if (s->sigma_type == BVG_SIGMA_WISHART) BVG_FAIL(-7, "Structural models may not use a Wishart prior.");
+  if (s->psi_mu || s->psi_vi) BVG_FAIL(-7, "Error covariances and structural coefficients cannot be estimated at the same time.");
+  if (!s->mu || !s->Vi) BVG_FAIL(-4, "priors$coefficients$mu / v_i missing");
+  const int Ma = Mu + k, na = k * Ma, nu = k * Mu + k * (k - 1) / 2;
+  std::vector<double> X((size_t)Ma * T), mu((size_t)na, 0.0), inprior((size_t)na, 0.5);
+  for (int t = 0; t < T; ++t) {
+    for (int j = 0; j < Mu; ++j) X[j + (size_t)Ma * t] = s->X[j + (size_t)Mu * t];
+    for (int j = 0; j < k; ++j) X[Mu + j + (size_t)Ma * t] = -s->Y[j + (size_t)k * t];
+  }
+  std::vector<int> pos((size_t)nu);
+  for (int r = 0; r < nu; ++r) pos[r] = structural_pos(r, k, Mu);
+  std::vector<double> Vi((size_t)na * na, 0.0);
+  for (int r = 0; r < na; ++r) Vi[r + (size_t)na * r] = 1.0;                 // masked positions: N(0, 1), never used
+  for (int r = 0; r < nu; ++r) {
+    mu[pos[r]] = s->mu[r];
+    if (s->vi_dense) {
+      for (int c = 0; c < nu; ++c) Vi[pos[r] + (size_t)na * pos[c]] = s->Vi[r + (size_t)nu * c];
+    } else {
+      Vi[pos[r] + (size_t)na * pos[r]] = s->Vi[r];
+    }
+  }
+  std::vector<int32_t> include;
+  if (s->varsel == BVG_VARSEL_BVS) {
+    if (!s->inprior || s->n_include < 0 || (s->n_include > 0 && !s->include)) BVG_FAIL(-4, "inclusion prior / include index missing");
+    for (int r = 0; r < nu; ++r) inprior[pos[r]] = s->inprior[r];
+    for (int e = 0; e < s->n_include; ++e) {
+      if (s->include[e] < 0 || s->include[e] >= nu) BVG_FAIL(-8, "include index out of range");
+      include.push_back(pos[s->include[e]]);
+    }
+  }
+  bvg_spec eff = *s;
+  eff.structural = 0;
+  eff.M = Ma; eff.X = X.data(); eff.mu = mu.data(); eff.Vi = Vi.data(); eff.vi_dense = 1;
+  eff.varsel = BVG_VARSEL_BVS; eff.inprior = inprior.data();
+  eff.include = include.empty() ? nullptr : include.data(); eff.n_include = (int32_t)include.size();
+  eff.resid_mode = BVG_RESID_DIRECT;                                          // [x; -y] fits y exactly: no OLS moments
+  const int rc = prepare_impl(&eff, P);
+  if (rc) return rc;
+  P.structural = 1; P.n_user = nu; P.varsel_user = s->varsel; P.a0_from = k * Mu;
+  // lambda = 0 on the masked positions (state: Sigma^-1 (k k) | prior diagonal (n) | lambda (n) | ...)
+  std::vector<unsigned char> kept((size_t)na, 0);
+  for (int r = 0; r < nu; ++r) kept[pos[r]] = 1;
+  for (int r = 0; r < na; ++r) if (!kept[r]) P.state0[(size_t)k * k + na + r] = 0.0;
+  return 0;
+}
+
+static inline int prepare_impl(const bvg_spec* s, Prepared& P) {
   if (s == nullptr) BVG_FAIL(-1, "spec is NULL");
   if (s->abi_version != BVG_ABI_VERSION) BVG_FAIL(-2, "bvg_spec.abi_version does not match this library");
   if (s->k < 1 || s->T < 2 || s->M < 0) BVG_FAIL(-3, "invalid dimensions (need k >= 1, T >= 2, M >= 0)");
@@ -392,6 +469,7 @@ static inline const double* at(const double* base, long off) { return off < 0 ? 
 
 static inline void bind_bvar(const Prepared& P, const double* base, const unsigned char* inc, BvarModel* m) {
   m->k = P.k; m->T = P.T; m->M = P.M; m->n = P.n;
+  m->a0_from = P.a0_from;
   m->sigma_type = P.sigma_type; m->varsel = P.varsel; m->resid_mode = P.resid_mode; m->n_mix = P.n_mix;
   m->Y = at(base, P.Y); m->X = at(base, P.X); m->XX = at(base, P.XX); m->YX = at(base, P.YX);
   m->Aols = at(base, P.Aols); m->SSE = at(base, P.SSE); m->mu = at(base, P.mu);

@@ -45,6 +45,8 @@ def bvar(y, x=None, A0=None, A=None, B=None, C=None, Sigma=None):
         sig = np.asarray(entry["sigma"]).T if isinstance(entry, dict) and "sigma" in entry else None
         return draws, lam, sig, tvp
 
+    if A0 is not None:
+        out["A0"], out["A0_lambda"], out["A0_sigma"], spec["tvp"]["A0"] = fill(A0, k * k)
     if A is not None:
         rows = np.asarray(A["coeffs"] if isinstance(A, dict) else A).shape[0]
         n_a = rows if rows % (k * k) == 0 and rows // (k * k) < tt else rows // tt
@@ -85,7 +87,21 @@ def bvarpost(obj, seed=None, **kw):
         full[upper] = lam
         post = dict(post)
         post["sigma"] = dict(post["sigma"], **{"lambda": full})
-    return bvar(y=obj["data"]["Y"], x=obj["data"]["Z"], A0=None, A=post["a"], B=post["b"], C=post["c"],
+    A0 = None
+    if obj["model"].get("structural") and post.get("a0") is not None:
+        # k^2 x draws with the identity and the strict lower triangle (column-major) = the a0 draws (R/bvarpost.R:73-108)
+        k = np.asarray(obj["data"]["Y"]).shape[1]
+        lower = [i + k * j for j in range(k) for i in range(k) if i > j]
+        a0 = post["a0"]
+        draws = np.asarray(a0["coeffs"]).shape[1]
+        coeffs = np.tile(np.eye(k).reshape(-1, 1, order="F"), (1, draws))
+        coeffs[lower] = a0["coeffs"]
+        A0 = {"coeffs": coeffs}
+        if "lambda" in a0:
+            lam = np.full((k * k, draws), np.nan)
+            lam[lower] = a0["lambda"]
+            A0["lambda"] = lam
+    return bvar(y=obj["data"]["Y"], x=obj["data"]["Z"], A0=A0, A=post["a"], B=post["b"], C=post["c"],
                 Sigma=post["sigma"])
 
 

@@ -283,7 +283,8 @@ def split_posteriors(obj, arrays, chain=0):
     if "exogen" in model:
         n_b = k * len(model["exogen"]["variables"]) * (int(model["exogen"]["lags"]) + 1)
     n_c = k * len(model.get("deterministic", []))
-    n = n_a + n_b + n_c
+    n_a0 = k * (k - 1) // 2 if model.get("structural") and k > 1 else 0       # last rows (bvaralg.cpp:262-263)
+    n = n_a + n_b + n_c + n_a0
     tvp = bool(model.get("tvp"))
     post = {"a0": None, "a": None, "b": None, "c": None, "sigma": None}
     coef = arrays.get("coef")
@@ -300,7 +301,7 @@ def split_posteriors(obj, arrays, chain=0):
     if not coef_sel:
         lam = None
     off = 0
-    for name, cnt in (("a", n_a), ("b", n_b), ("c", n_c)):
+    for name, cnt in (("a", n_a), ("b", n_b), ("c", n_c), ("a0", n_a0)):
         if cnt > 0 and coef is not None:
             d = {}
             c_ = coef[chain]                                        # [iter][rows]

@@ -139,6 +139,13 @@ typedef struct bvg_spec {
   const double* psi_shape;     /* k(k-1)/2 */
   const double* psi_rate;      /* k(k-1)/2 */
   const double* psi_init;      /* k(k-1)/2 */
+  /* model$structural (R/gen_var.R:243-251): equation i also contains -y_jt, j < i (the A0 columns of data$SUR).  With
+   * structural = 1 every per-coefficient array (mu, Vi, inprior, include; the coef / lambda outputs; injected coef_normal
+   * excepted, see below) has k M + k(k-1)/2 entries in the reference's order [a | b | c | a0], a0 by variable j then
+   * equation i > j.  X stays the M x T regressor matrix WITHOUT the -y block (the library appends it).  Needs a gamma or SV
+   * error prior (R/add_priors.bvarmodel.R); SSVS, TVP and the covariance block are not available with it (-5 / -7).
+   * Injected coefficient-level variates (tests) are indexed by the INTERNAL position i + k m over the M + k regressors. */
+  int32_t structural;
   /* tuning / testing */
   int32_t resid_mode;       /* BVG_RESID_*                                 */
   int32_t threads_per_chain; /* 0 = auto; 1,2,4,8,16,32 (sub-warp tiles) or a multiple of 32 (CTA per chain) */

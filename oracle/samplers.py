@@ -8,7 +8,7 @@ the (nT) x (nT) TVP system) and runs the same LAPACK-level operations; `literal=
 formulas through their Kronecker / banded structure (used for long tier-2 runs; proven equal to the literal
 path to <= 1e-10 in tests/test_oracle.py).  The covariance (psi) block of the constant-parameter sampler
 (bvaralg.cpp:373-455, gamma / SV errors) is restated literally; its SSVS / BVS twins, the TVP psi block and
-structural models are outside the accelerated path and raise.  Random variates come from a VariateSource (injected arrays
+structural TVP models are outside the accelerated path and raise.  Random variates come from a VariateSource (injected arrays
 or a NumPy Generator) in the site order of oracle/variates.py.
 """
 from __future__ import annotations
@@ -47,8 +47,8 @@ def _unpack_common(obj):
     if "exogen" in model:
         n_b = k * len(model["exogen"]["variables"]) * (int(model["exogen"]["lags"]) + 1)
     n_c = k * len(model.get("deterministic", []))
-    if model.get("structural"):
-        raise NotImplementedError("structural models are outside the accelerated path (SURVEY.md 8f-4)")
+    if model.get("structural") and model.get("tvp"):
+        raise NotImplementedError("structural TVP models are outside the accelerated path (SURVEY.md 8f-4)")
     return data, model, priors, initial, y, k, tt, z, n_tot, n_a, n_b, n_c
 
 
@@ -343,6 +343,11 @@ def bvaralg(obj, variates: VariateSource | None = None, literal=True, table="ksc
     posteriors = {"a0": None, "a": None, "b": None, "c": None, "sigma": None}
     if use_a:
         _split_rows(posteriors, draws_coef, draws_lambda, n_a, n_b, n_c)
+        if model.get("structural") and k > 1:                                                # :553-557,595-601
+            a0_from = n_a + n_b + n_c
+            posteriors["a0"] = {"coeffs": draws_coef[a0_from:]}
+            if draws_lambda is not None:
+                posteriors["a0"]["lambda"] = draws_lambda[a0_from:]
     posteriors["sigma"] = {"coeffs": draws_sigma}
     if sv:
         posteriors["sigma"]["sigma"] = draws_sigma_sigma

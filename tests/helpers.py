@@ -113,6 +113,17 @@ def model_tvp_covar(K=3, p=1, nobs=24, iterations=8, burnin=3, seed=41, sv=True,
                       bvs=dict(inprior=0.5, exclude_det=True, covar=psi_bvs) if (bvs or psi_bvs) else None)
 
 
+def model_structural(K=3, p=1, nobs=50, iterations=12, burnin=4, seed=9, sv=False, bvs=False):
+    """Structural VAR (A0 coefficients: equation i contains -y_j, j < i) with inverse-gamma or SV error variances."""
+    y = synth_var(K, p, nobs, seed)
+    m = gen_var(y, p=p, deterministic="const", iterations=iterations, burnin=burnin, structural=True, sv=sv)
+    sigma = dict(shape=3, rate=1e-3)
+    if sv:
+        sigma.update(mu=0, v_i=0.01, sigma_h=0.05, constant=1e-4)
+    return add_priors(m, coef=dict(v_i=1, v_i_det=0.1), sigma=sigma,
+                      bvs=dict(inprior=0.5, exclude_det=True) if bvs else None)
+
+
 def model_c5(K=20, p=4, nobs=204, iterations=200, burnin=50, seed=2042004):
     """Config c5: large BVAR, K = 20, p = 4, const (n = 1620), Minnesota prior, sigma df = k, scale 1.
     DGP: diagonally dominant stable VAR(1), AR(1)-correlated errors."""
@@ -179,6 +190,16 @@ def make_variates(obj, n_chains, seed):
     rng = np.random.default_rng(seed)
     per_chain = [draw_variates(dims, sweeps, rng, variate_kinds(obj)) for _ in range(n_chains)]
     stacked = {kname: np.stack([pc[kname].reshape(sweeps, -1) for pc in per_chain]) for kname in per_chain[0]}
+    if obj["model"].get("structural") and k > 1:
+        # the library runs structural models on the regressors [x; -y] (M + k of them) with the positions
+        # (variable j, equation i <= j) masked: coefficient-level injected arrays are indexed by the internal position
+        Mu = obj["data"]["Z"].shape[1]
+        pos = list(range(k * Mu)) + [k * (Mu + j) + i for j in range(k) for i in range(j + 1, k)]
+        for kname in ("coef_normal", "bvs_u1", "bvs_u2"):
+            if kname in stacked:
+                full = np.full(stacked[kname].shape[:2] + (k * (Mu + k),), 0.5)
+                full[:, :, pos] = stacked[kname]
+                stacked[kname] = full
     return per_chain, stacked
 
 
@@ -197,7 +218,7 @@ def oracle_stack(obj, per_chain, literal=True, table="ksc1998"):
     k = obj["data"]["Y"].shape[1]
     for inj in per_chain:
         r = fn(obj, VariateSource(injected=inj), literal=literal, table=table)["posteriors"]
-        parts = [r[nm] for nm in ("a", "b", "c") if r.get(nm) is not None]
+        parts = [r[nm] for nm in ("a", "b", "c", "a0") if r.get(nm) is not None]
         if obj["model"].get("tvp"):
             T = obj["data"]["Y"].shape[0]
             it = parts[0]["coeffs"].shape[1]

@@ -13,14 +13,17 @@ def _random_model(rng):
     p = int(rng.integers(0, 4))
     nobs = int(rng.integers(24, 70))
     kind = str(rng.choice(["wishart", "gamma", "sv", "gamma_covar", "sv_covar", "tvp_sv", "tvp_wishart", "tvp_sv_covar",
-                           "tvp_gamma_covar"]))
+                           "tvp_gamma_covar", "structural_gamma", "structural_sv"]))
     sel = str(rng.choice(["none", "ssvs", "bvs"]))
     det = str(rng.choice(["const", "none", "both"])) if p > 0 else "const"
     tvp, sv = kind.startswith("tvp"), "sv" in kind
+    structural = kind.startswith("structural") and k > 1
+    if structural and sel == "ssvs":
+        sel = "none"                                       # SSVS is not combined with structural coefficients
     y = helpers.synth_var(k, max(p, 1), nobs, int(rng.integers(1, 1000)))
-    m = helpers.gen_var(y, p=p, deterministic=det, iterations=6, burnin=2, tvp=tvp, sv=sv)
+    m = helpers.gen_var(y, p=p, deterministic=det, iterations=6, burnin=2, tvp=tvp, sv=sv, structural=structural)
     tvp_covar = kind in ("tvp_sv_covar", "tvp_gamma_covar") and k > 1 and k * (k - 1) // 2 <= k * (k * p + (det != "none"))
-    if kind in ("gamma", "gamma_covar", "tvp_gamma_covar"):
+    if kind in ("gamma", "gamma_covar", "tvp_gamma_covar", "structural_gamma"):
         sigma = dict(shape=3, rate=1e-3, covar=((kind == "gamma_covar" and k > 1) or tvp_covar))
     elif sv:
         sigma = dict(shape=3, rate=1e-4, mu=0, v_i=0.01, sigma_h=0.05, constant=1e-4,

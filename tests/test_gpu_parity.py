@@ -358,3 +358,28 @@ def test_tvp_covariance_block_through_the_mirror(gpu):
     assert np.isfinite(ll[0]["LL"])
     bands = bt.irf(fit, 0, 1, n_ahead=4, type="oir")
     assert bands.shape == (5, 3) and np.isfinite(bands).all()
+
+
+@pytest.mark.gpu
+def test_structural_model_through_the_mirror(gpu):
+    """Structural VAR through draw_posterior: A0 draws (identity + strict lower triangle), reproducible, and the
+    lower-triangular elements agree with the oracle sampler's posterior means within Monte-Carlo error."""
+    import bvartools_b200 as bt
+    from oracle import samplers as osamp
+    from oracle.variates import VariateSource
+    obj = helpers.model_structural(K=3, p=1, nobs=80, iterations=400, burnin=100)
+    fit = bt.draw_posterior(obj, seed=21)
+    assert not fit.get("error"), fit.get("message")
+    k = 3
+    A0 = np.asarray(fit["A0"])
+    assert A0.shape == (400, k * k)
+    M = A0.reshape(400, k, k, order="F")
+    assert np.all(M[:, np.arange(k), np.arange(k)] == 1.0) and np.all(np.triu(M, 1) == 0.0)
+    assert np.abs(M[:, 1, 0]).max() > 0
+    again = bt.draw_posterior(obj, seed=21)
+    assert np.array_equal(np.asarray(again["A0"]), A0)
+    ref = osamp.bvaralg(obj, VariateSource(rng=np.random.default_rng(5)), literal=True)["posteriors"]["a0"]["coeffs"]
+    lower = [i + k * j for j in range(k) for i in range(k) if i > j]
+    got_m, ref_m = A0[:, lower].mean(axis=0), ref.mean(axis=1)
+    se = np.sqrt(A0[:, lower].var(axis=0, ddof=1) / 400 + ref.var(axis=1, ddof=1) / 400)
+    assert np.all(np.abs(got_m - ref_m) < 6.0 * se), (got_m, ref_m, se)

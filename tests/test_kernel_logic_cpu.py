@@ -64,6 +64,11 @@ CASES["tvp_covar_sv_k4"] = (lambda: helpers.model_tvp_covar(K=4, p=1, nobs=20, i
 CASES["tvp_covar_sv_k2"] = (lambda: helpers.model_tvp_covar(K=2, p=2, nobs=22), {})
 CASES["tvp_covar_gamma"] = (lambda: helpers.model_tvp_covar(sv=False), {})
 CASES["tvp_covar_sv_psi_bvs"] = (lambda: helpers.model_tvp_covar(K=4, p=1, nobs=20, iterations=8, burnin=2, psi_bvs=True), {})
+CASES["structural_gamma"] = (lambda: helpers.model_structural(), {})
+CASES["structural_gamma_k4_p2"] = (lambda: helpers.model_structural(K=4, p=2, nobs=60), {})
+CASES["structural_sv"] = (lambda: helpers.model_structural(sv=True), {})
+CASES["structural_gamma_bvs"] = (lambda: helpers.model_structural(bvs=True), {})
+CASES["structural_sv_bvs_k2"] = (lambda: helpers.model_structural(K=2, p=2, sv=True, bvs=True), {})
 CASES["tvp_covar_gamma_bvs"] = (lambda: helpers.model_tvp_covar(sv=False, bvs=True), {})
 
 
