@@ -782,16 +782,29 @@ int bvg_sampler_tsse(bvg_sampler* s, int32_t which, double* tsse, void* cuda_str
 int bvg_irf_draws(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
                   int64_t n_draws, int32_t k, int32_t p, int32_t n_ahead, int32_t type, int32_t impulse, int32_t response,
                   int32_t shock_kind, double shock, int32_t cumulative, double* dev_out, void* cuda_stream) {
+  if (type == 3 || type == 4) return fail(-12, "Structural IR requires that draws of 'A0' are contained in the 'bvar' x.");
+  return bvg_irf_draws_a0(dev_coef, coef_stride, dev_sigma, sigma_stride, nullptr, 0, 0, n_draws, k, p, n_ahead, type, impulse,
+                          response, shock_kind, shock, cumulative, dev_out, cuda_stream);
+}
+
+int bvg_irf_draws_a0(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
+                     const double* dev_a0, int64_t a0_stride, int32_t a0_compact, int64_t n_draws, int32_t k, int32_t p,
+                     int32_t n_ahead, int32_t type, int32_t impulse, int32_t response, int32_t shock_kind, double shock,
+                     int32_t cumulative, double* dev_out, void* cuda_stream) {
   if (!dev_out || n_draws < 1 || (p > 0 && !dev_coef)) return fail(-1, "invalid arguments to bvg_irf_draws");
-  if (type < 0 || type > 2) return fail(-7, "Argument 'type' not known.");      // feir / oir / gir (R/irf.bvar.R:84)
-  if ((type != 0 || shock_kind != 0) && !dev_sigma)
-    return fail(-8, "OIR, GIR, SGIR require that the 'bvar' x contains draws of 'Sigma'.");   // R/irf.bvar.R:107-110
+  if (type < 0 || type > 4) return fail(-7, "Argument 'type' not known.");      // feir / oir / gir / sir / sgir (R/irf.bvar.R:84)
+  if (type >= 3 && !dev_a0)
+    return fail(-12, "Structural IR requires that draws of 'A0' are contained in the 'bvar' x.");   // R/irf.bvar.R:101-104
+  if (type >= 3 && !a0_compact && k > 16) return fail(-2, "structural impulse responses from full A0 matrices need k <= 16");
+  if ((type == 1 || type == 2 || type == 4 || shock_kind != 0) && !dev_sigma)
+    return fail(-8, "OIR, GIR, SGIR require that the 'bvar' x contains draws of 'Sigma'.");   // R/irf.bvar.R:112-115
   if (shock_kind < 0 || shock_kind > 2) return fail(-9, "Invalid specification of argument 'shock'.");
   if (k < 1 || k > 32 || impulse < 0 || impulse >= k || response < 0 || response >= k || n_ahead < 0 || p < 0)
     return fail(-2, "bvg_irf_draws: need 1 <= k <= 32, 0 <= impulse, response < k, n_ahead >= 0");
   if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");
   cudaError_t e = launch_irf_draws(dev_coef, coef_stride, dev_sigma, sigma_stride, n_draws, k, p, n_ahead, type, impulse,
-                                   response, shock_kind, shock, cumulative, dev_out, (cudaStream_t)cuda_stream);
+                                   response, shock_kind, shock, cumulative, dev_out, (cudaStream_t)cuda_stream, dev_a0,
+                                   a0_stride, a0_compact ? 2 : 1);
   if (e != cudaSuccess) return cuda_fail(e, "impulse-response kernel");
   return 0;
 }
@@ -813,8 +826,13 @@ int bvg_sampler_irf(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, in
   const double* sig = s->d_sigma + (tv_sig ? (size_t)period * k * k : 0);
   double* d_out = nullptr;
   CK(cudaMalloc((void**)&d_out, (size_t)nd * (n_ahead + 1) * sizeof(double)));
-  int rc = bvg_irf_draws(coef, s->rows_coef, sig, s->rows_sigma, nd, k, p, n_ahead, type, impulse, response, shock_kind,
-                         shock, cumulative, d_out, cuda_stream);
+  const double* a0 = nullptr;                     // structural sampler: compact a0 rows at the end of every coefficient draw
+  if (type >= 3) {
+    if (!s->P.structural) { cudaFree(d_out); return fail(-12, "Structural IR requires that draws of 'A0' are contained in the 'bvar' x."); }
+    a0 = s->d_coef + s->P.a0_from;
+  }
+  int rc = bvg_irf_draws_a0(coef, s->rows_coef, sig, s->rows_sigma, a0, s->rows_coef, 1, nd, k, p, n_ahead, type, impulse,
+                            response, shock_kind, shock, cumulative, d_out, cuda_stream);
   if (rc == 0 && (n_probs > 0 || mean))
     rc = bvg_summary_draws(d_out, nd, n_ahead + 1, probs, n_probs, mean, nullptr, quantiles, cuda_stream);
   if (rc == 0 && host_draws) {

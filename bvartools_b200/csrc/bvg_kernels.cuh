@@ -56,7 +56,8 @@ cudaError_t launch_centered_ss(const double* draws, long long n_draws, long long
 // impulse responses per draw (bvg_postest.cu)
 cudaError_t launch_irf_draws(const double* coef, long long coef_stride, const double* sigma, long long sigma_stride,
                              long long n_draws, int k, int p, int h, int type, int impulse, int response, int shock_kind,
-                             double shock, int cumulative, double* d_out, cudaStream_t stream);
+                             double shock, int cumulative, double* d_out, cudaStream_t stream, const double* a0 = nullptr,
+                             long long a0_stride = 0, int a0_mode = 0);
 cudaError_t launch_fevd_draws(const double* coef, long long coef_stride, const double* sigma, long long sigma_stride,
                               long long n_draws, int k, int p, int h, int type, int response, double* d_out,
                               cudaStream_t stream);

@@ -9,22 +9,27 @@
 //   gir   P = Sigma / Sigma_jj shock                                                                 (ir.cpp:38-41)
 // shock = number, or "sd" / "nsd": +- L_jj for oir, +- sqrt(Sigma_jj) otherwise (R/irf.bvar.R:176-188).
 // Output [draw][h + 1] (cumulated on request, R/irf.bvar.R:204-206) stays on the device; the bands come from the radix
-// select of bvg_summary.cu.  Structural types (sir, sgir) need A0 draws, which this sampler does not produce.
+// select of bvg_summary.cu.  Structural types (ir.cpp:35-37,42-46): sir P = A0^-1 shock, sgir P = A0^-1 Sigma / Sigma_jj
+// shock -- column `impulse` of P is one k x k solve per draw (Gaussian elimination with partial pivoting on a full A0,
+// forward substitution when A0 arrives as the sampler's compact strict lower triangle).
 #include "bvg_kernels.cuh"
 #include "bvg_blocks.cuh"
 
 namespace bvg {
 
 struct IrfDims {
-  long long n_draws, coef_stride, sigma_stride;
+  long long n_draws, coef_stride, sigma_stride, a0_stride;
   int k, p, h, type, impulse, response, shock_kind, cumulative;
+  int a0_mode;        // 0 none, 1 full k x k column-major, 2 compact strict lower triangle (by column), unit diagonal
   double shock;
 };
+static constexpr int IRF_A0_KMAX = 16;
 
 static constexpr int IRF_KMAX = 32;
 
 __global__ void __launch_bounds__(128) irf_draws_kernel(const __grid_constant__ IrfDims d, const double* __restrict__ coef,
-                                                        const double* __restrict__ sigma, double* __restrict__ out) {
+                                                        const double* __restrict__ sigma, const double* __restrict__ a0,
+                                                        double* __restrict__ out) {
   extern __shared__ double sm[];                       // per thread: ring of p row vectors (k each) + column of P (k)
   const int k = d.k, p = d.p, h = d.h;
   const int per_thread = (p + 1) * k;
@@ -51,8 +56,42 @@ __global__ void __launch_bounds__(128) irf_draws_kernel(const __grid_constant__ 
       for (int i = 0; i < k; ++i) pc[i] = (i >= jm) ? Lc[(i * (i + 1)) / 2 + jm] / ljj * shock : 0.0;
     } else {
       if (d.shock_kind != 0) { const double sdv = sqrt(S[jm + k * jm]); shock = (d.shock_kind == 2) ? -sdv : sdv; }
-      if (d.type == 2) { const double sjj = S[jm + k * jm]; for (int i = 0; i < k; ++i) pc[i] = S[i + k * jm] / sjj * shock; }
+      if (d.type == 2 || d.type == 4) { const double sjj = S[jm + k * jm]; for (int i = 0; i < k; ++i) pc[i] = S[i + k * jm] / sjj * shock; }
       else for (int i = 0; i < k; ++i) pc[i] = (i == jm) ? shock : 0.0;
+      if (d.type >= 3) {
+        // pc <- A0^-1 pc  (sir: A0^-1 e_j shock;  sgir: A0^-1 Sigma[:, j] / Sigma_jj shock)
+        const double* A0 = a0 + dr * d.a0_stride;
+        if (d.a0_mode == 2) {
+          // unit lower, element (i, c), i > c, at c (k - 1) - c (c - 1) / 2 + (i - c - 1)
+          for (int i = 1; i < k; ++i) {
+            double sv = pc[i];
+            for (int c = 0; c < i; ++c) sv = fma(-A0[c * (k - 1) - (c * (c - 1)) / 2 + (i - c - 1)], pc[c], sv);
+            pc[i] = sv;
+          }
+        } else {
+          double W[IRF_A0_KMAX * IRF_A0_KMAX];
+          for (int e = 0; e < k * k; ++e) W[e] = A0[e];
+          for (int c = 0; c < k; ++c) {
+            int pv = c;
+            for (int i = c + 1; i < k; ++i) if (fabs(W[i + k * c]) > fabs(W[pv + k * c])) pv = i;
+            if (pv != c) {
+              for (int e = 0; e < k; ++e) { const double tw = W[c + k * e]; W[c + k * e] = W[pv + k * e]; W[pv + k * e] = tw; }
+              const double tb = pc[c]; pc[c] = pc[pv]; pc[pv] = tb;
+            }
+            const double piv = W[c + k * c];
+            for (int i = c + 1; i < k; ++i) {
+              const double f = W[i + k * c] / piv;
+              for (int e = c + 1; e < k; ++e) W[i + k * e] = fma(-f, W[c + k * e], W[i + k * e]);
+              pc[i] = fma(-f, pc[c], pc[i]);
+            }
+          }
+          for (int i = k - 1; i >= 0; --i) {
+            double sv = pc[i];
+            for (int e = i + 1; e < k; ++e) sv = fma(-W[i + k * e], pc[e], sv);
+            pc[i] = sv / W[i + k * i];
+          }
+        }
+      }
     }
     // ---- phi_0 = e_response'
     double* o = out + dr * (h + 1);
@@ -90,12 +129,15 @@ __global__ void __launch_bounds__(128) irf_draws_kernel(const __grid_constant__ 
 
 cudaError_t launch_irf_draws(const double* coef, long long coef_stride, const double* sigma, long long sigma_stride,
                              long long n_draws, int k, int p, int h, int type, int impulse, int response, int shock_kind,
-                             double shock, int cumulative, double* d_out, cudaStream_t stream) {
-  if (k < 1 || k > IRF_KMAX || p < 0 || h < 0 || type < 0 || type > 2 || impulse < 0 || impulse >= k || response < 0 ||
+                             double shock, int cumulative, double* d_out, cudaStream_t stream, const double* a0,
+                             long long a0_stride, int a0_mode) {
+  if (k < 1 || k > IRF_KMAX || p < 0 || h < 0 || type < 0 || type > 4 || impulse < 0 || impulse >= k || response < 0 ||
       response >= k || n_draws < 1)
     return cudaErrorInvalidValue;
+  if (type >= 3 && (a0 == nullptr || a0_mode < 1 || a0_mode > 2 || (a0_mode == 1 && k > IRF_A0_KMAX))) return cudaErrorInvalidValue;
   IrfDims d;
   d.n_draws = n_draws; d.coef_stride = coef_stride; d.sigma_stride = sigma_stride;
+  d.a0_stride = a0_stride; d.a0_mode = (type >= 3) ? a0_mode : 0;
   d.k = k; d.p = p; d.h = h; d.type = type; d.impulse = impulse; d.response = response; d.shock_kind = shock_kind;
   d.cumulative = cumulative; d.shock = shock;
   int threads = 128;
@@ -109,7 +151,7 @@ cudaError_t launch_irf_draws(const double* coef, long long coef_stride, const do
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   long long want = (n_draws + threads - 1) / threads;
   int grid = (int)((want < (long long)sms * 8) ? want : (long long)sms * 8);
-  irf_draws_kernel<<<grid, threads, smem, stream>>>(d, coef, sigma, d_out);
+  irf_draws_kernel<<<grid, threads, smem, stream>>>(d, coef, sigma, a0, d_out);
   return cudaGetLastError();
 }
 

@@ -259,11 +259,11 @@ def irf(obj, impulse, response, n_ahead=5, ci=0.95, shock=1, type="feir", cumula
     """irf.bvar (R/irf.bvar.R:78-216) for a host `bvar` object: `impulse` / `response` are 0-based variable positions.
     The draws are uploaded once; the per-draw responses and their bands are computed on the device."""
     import torch
-    types = {"feir": 0, "oir": 1, "gir": 2}
+    types = {"feir": 0, "oir": 1, "gir": 2, "sir": 3, "sgir": 4}
     if type not in types:
-        if type in ("sir", "sgir"):
-            raise ValueError("Structural IR requires that draws of 'A0' are contained in the 'bvar' x.")
         raise ValueError("Argument 'type' not known.")
+    if type in ("sir", "sgir") and obj.get("A0") is None:
+        raise ValueError("Structural IR requires that draws of 'A0' are contained in the 'bvar' x.")
     if isinstance(shock, str):
         if shock not in ("sd", "nsd"):
             raise ValueError("Invalid specification of argument 'shock'.")
@@ -271,14 +271,22 @@ def irf(obj, impulse, response, n_ahead=5, ci=0.95, shock=1, type="feir", cumula
     else:
         kind, val = 0, float(shock)
     k, p, draws, dA, dS = _device_draws(obj, period)
-    if p == 0:
+    structural = type in ("sir", "sgir")
+    if p == 0 and not structural:                                  # R/irf.bvar.R:96-98
         raise ValueError("Impulse responses only supported for models with p > 0, i.e. argument 'x' must contain "
                          "element 'A', or structural models.")
     out = torch.empty((draws, n_ahead + 1), dtype=torch.float64, device="cuda")
     vp = C.c_void_p
-    check(lib().bvg_irf_draws(vp(dA.data_ptr()), dA.shape[1], vp(dS.data_ptr()), k * k, draws, k, p, int(n_ahead),
-                              types[type], int(impulse), int(response), kind, val, int(bool(cumulative)),
-                              vp(out.data_ptr()), None))
+    d0 = None
+    if structural:
+        A0 = obj["A0"]
+        if isinstance(A0, list):
+            A0 = A0[np.asarray(obj["y"]).shape[0] - 1 if period is None else period]
+        d0 = torch.from_numpy(np.ascontiguousarray(A0, dtype=np.float64)).cuda()      # draws x k^2, column-major matrices
+    check(lib().bvg_irf_draws_a0(None if dA is None else vp(dA.data_ptr()), 0 if dA is None else dA.shape[1],
+                                 vp(dS.data_ptr()), k * k, None if d0 is None else vp(d0.data_ptr()), k * k, 0, draws, k, p,
+                                 int(n_ahead), types[type], int(impulse), int(response), kind, val,
+                                 int(bool(cumulative)), vp(out.data_ptr()), None))
     if keep_draws:
         return out.cpu().numpy()
     lo = (1.0 - ci) / 2.0

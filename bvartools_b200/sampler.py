@@ -155,14 +155,15 @@ class ChainSampler:
     def irf(self, impulse, response, n_ahead=5, ci=0.95, shock=1, type="feir", cumulative=False, keep_draws=False,
             period=None, p=None, stream=0):
         """Impulse responses over ALL retained draws resident on the device (irf.bvar, R/irf.bvar.R:78-216): `impulse`
-        / `response` are 0-based variable indices, `shock` a number or "sd" / "nsd", `type` "feir" / "oir" / "gir".
+        / `response` are 0-based variable indices, `shock` a number or "sd" / "nsd", `type` "feir" / "oir" / "gir", and
+        for structural models "sir" / "sgir".
         Returns the (n_ahead + 1) x 3 band matrix (ci_low, median, ci_high) like the reference, or the draws
         (draws x (n_ahead + 1)) with keep_draws."""
-        types = {"feir": 0, "oir": 1, "gir": 2}
+        types = {"feir": 0, "oir": 1, "gir": 2, "sir": 3, "sgir": 4}
         if type not in types:
-            if type in ("sir", "sgir"):
-                raise ValueError("Structural IR requires that draws of 'A0' are contained in the 'bvar' x.")
             raise ValueError("Argument 'type' not known.")
+        if type in ("sir", "sgir") and not self.spec.c.structural:
+            raise ValueError("Structural IR requires that draws of 'A0' are contained in the 'bvar' x.")
         if isinstance(shock, str):
             if shock not in ("sd", "nsd"):
                 raise ValueError("Invalid specification of argument 'shock'.")

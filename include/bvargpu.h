@@ -260,13 +260,21 @@ int bvg_sampler_tsse(bvg_sampler* s, int32_t which, double* tsse, void* cuda_str
 /* ---- impulse responses per draw --------------------------------------------------------------------
  * Replaces the per-draw loop of irf.bvar (R/irf.bvar.R:140-216) around .ir (src/ir.cpp:4-72): for every draw
  * theta_i = (Phi_i P)[response, impulse], i = 0..n_ahead, Phi_i = sum_j Phi_{i-j} A_j.
- * type: 0 feir, 1 oir, 2 gir (sir / sgir need A0 draws: not produced by these samplers); impulse / response 0-based;
+ * type: 0 feir, 1 oir, 2 gir (sir / sgir: bvg_irf_draws_a0); impulse / response 0-based;
  * shock_kind: 0 = the number `shock`, 1 = "sd", 2 = "nsd" (R/irf.bvar.R:176-188); cumulative as in :204-206.
  * dev_coef: draw d starts at dev_coef + d * coef_stride, its first k*k*p doubles are A = [A_1 .. A_p] column-major;
  * dev_sigma likewise (k x k).  dev_out: [n_draws][n_ahead + 1] on the device. */
 int bvg_irf_draws(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
                   int64_t n_draws, int32_t k, int32_t p, int32_t n_ahead, int32_t type, int32_t impulse, int32_t response,
                   int32_t shock_kind, double shock, int32_t cumulative, double* dev_out, void* cuda_stream);
+/* the same with the structural types (src/ir.cpp:35-37,42-46): type 3 sir P = A0^-1 shock, 4 sgir P = A0^-1 Sigma / Sigma_jj
+ * shock.  dev_a0: draw d starts at dev_a0 + d * a0_stride; a0_compact = 0: the full k x k matrix, column-major (k <= 16);
+ * a0_compact = 1: the k(k-1)/2 free elements of the unit lower-triangular A0 by column -- the a0 rows the structural
+ * sampler stores at the end of every coefficient draw.  Types 0-2 ignore dev_a0. */
+int bvg_irf_draws_a0(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
+                     const double* dev_a0, int64_t a0_stride, int32_t a0_compact, int64_t n_draws, int32_t k, int32_t p,
+                     int32_t n_ahead, int32_t type, int32_t impulse, int32_t response, int32_t shock_kind, double shock,
+                     int32_t cumulative, double* dev_out, void* cuda_stream);
 /* on the retained draws of a sampler + the bands of irf.bvar (type-7 quantiles over all draws, :208-213): quantiles
  * [n_probs][n_ahead + 1], mean [n_ahead + 1] (may be NULL), host_draws [draws][n_ahead + 1] (keep_draws; may be NULL) on
  * the host.  period: 0-based period for TVP / SV draws, < 0 = the last one (:127-133). */

@@ -339,7 +339,7 @@ def time_series_se(draws, n_chains):
     return np.sqrt(spec.mean(axis=0) / (it * n_chains))
 
 
-def ir(A, Sigma, h, type, impulse, response, shock=1.0):
+def ir(A, Sigma, h, type, impulse, response, shock=1.0, A0=None):
     """src/ir.cpp:4-72, literally (full Phi matrices): A is k x (k p), impulse / response 1-based as in R."""
     coef = np.asarray(A, dtype=float)
     k = coef.shape[0]
@@ -354,6 +354,12 @@ def ir(A, Sigma, h, type, impulse, response, shock=1.0):
     elif type == "gir":
         S = np.asarray(Sigma, dtype=float)
         P = S / S[impulse - 1, impulse - 1] * shock
+    elif type == "sir":                                                  # :35-37
+        P = np.linalg.solve(np.asarray(A0, dtype=float), np.eye(k)) * shock
+    elif type == "sgir":                                                 # :42-46
+        S = np.asarray(Sigma, dtype=float)
+        P = np.linalg.solve(np.asarray(A0, dtype=float), np.eye(k))
+        P = P @ S / S[impulse - 1, impulse - 1] * shock
     else:
         raise ValueError("type")
     phi = np.zeros(((h + 1) * k, k))
@@ -372,7 +378,7 @@ def ir(A, Sigma, h, type, impulse, response, shock=1.0):
 
 
 def irf_bvar(A_draws, Sigma_draws, k, impulse, response, n_ahead=5, ci=0.95, shock=1, type="feir", cumulative=False,
-             keep_draws=False):
+             keep_draws=False, A0_draws=None):
     """R/irf.bvar.R:140-216 for a constant-parameter `bvar`: A_draws (draws x k^2 p), Sigma_draws (draws x k^2),
     impulse / response 1-based.  Returns the (n_ahead + 1) x 3 band matrix or the draws."""
     res = []
@@ -385,7 +391,8 @@ def irf_bvar(A_draws, Sigma_draws, k, impulse, response, n_ahead=5, ci=0.95, sho
                 sh = -sh
         else:
             sh = shock
-        res.append(ir(A, S, n_ahead, type, impulse, response, sh))
+        A0 = None if A0_draws is None else A0_draws[i].reshape(k, k, order="F")
+        res.append(ir(A, S, n_ahead, type, impulse, response, sh, A0))
     result = np.array(res)
     if cumulative:
         result = np.cumsum(result, axis=1)

@@ -122,3 +122,35 @@ def test_irf_and_fevd_of_a_host_bvar_object(gpu):
     want_v = ob.fevd_bvar(A, S, k, 3, n_ahead=6, type="gir", normalise_gir=True)
     assert helpers.relerr(bt.fevd(fit, 2, n_ahead=6, type="gir", normalise_gir=True), want_v) < TOL
 
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("type", ["sir", "sgir"])
+def test_structural_impulse_responses(gpu, type):
+    """sir / sgir (src/ir.cpp:35-37,42-46) from the A0 draws of a structural model: resident draws (compact a0 rows) and
+    the host `bvar` object (full A0 matrices) against the literal restatement."""
+    import bvartools_b200 as bt
+    from bvartools_b200 import ChainSampler, _abi
+    obj = helpers.model_structural(K=3, p=2, nobs=60, iterations=40, burnin=10)
+    k = 3
+    s = ChainSampler(obj, n_chains=2, seed=5)
+    s.run(0)
+    host = _abi.OutBuffers(s.spec)
+    s.fetch(host)
+    coef = host.arrays["coef"].reshape(-1, host.arrays["coef"].shape[-1])
+    sig = host.arrays["sigma"].reshape(coef.shape[0], -1)
+    n_a = k * k * 2
+    a0c = coef[:, -3:]
+    A0 = np.tile(np.eye(k).reshape(-1, order="F"), (coef.shape[0], 1))
+    lower = [i + k * j for j in range(k) for i in range(k) if i > j]
+    A0[:, lower] = a0c
+    want = ob.irf_bvar(coef[:, :n_a], sig, k, 1, 3, n_ahead=6, type=type, shock="sd", keep_draws=True, A0_draws=A0)
+    got = s.irf(0, 2, n_ahead=6, type=type, shock="sd", keep_draws=True)
+    assert helpers.relerr(got, want) < TOL
+    s.close()
+    fit = bt.draw_posterior(obj, seed=5)
+    wantf = ob.irf_bvar(np.asarray(fit["A"]), np.asarray(fit["Sigma"]), k, 2, 3, n_ahead=5, type=type, shock=1, ci=0.9,
+                        A0_draws=np.asarray(fit["A0"]))
+    np.testing.assert_allclose(bt.irf(fit, 1, 2, n_ahead=5, type=type, ci=0.9), wantf, rtol=1e-10, atol=1e-14)
+    with pytest.raises(ValueError, match="A0"):
+        bt.irf({k_: v for k_, v in fit.items() if k_ != "A0"}, 1, 2, type=type)
