@@ -848,9 +848,22 @@ int bvg_sampler_irf(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, in
 int bvg_fevd_draws(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
                    int64_t n_draws, int32_t k, int32_t p, int32_t n_ahead, int32_t type, int32_t response,
                    int32_t normalise_gir, double* host_out, void* cuda_stream) {
+  if (type == 3 || type == 4)
+    return fail(-12, "Structural FEVD requires that draws of 'A0' are contained in the 'bvar' object.");
+  return bvg_fevd_draws_a0(dev_coef, coef_stride, dev_sigma, sigma_stride, nullptr, 0, 0, n_draws, k, p, n_ahead, type, response,
+                           normalise_gir, host_out, cuda_stream);
+}
+
+int bvg_fevd_draws_a0(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
+                      const double* dev_a0, int64_t a0_stride, int32_t a0_compact, int64_t n_draws, int32_t k, int32_t p,
+                      int32_t n_ahead, int32_t type, int32_t response, int32_t normalise_gir, double* host_out,
+                      void* cuda_stream) {
   if (!host_out || n_draws < 1 || (p > 0 && !dev_coef)) return fail(-1, "invalid arguments to bvg_fevd_draws");
   if (!dev_sigma) return fail(-8, "Argument 'object' must include draws of the variance-covariance matrix Sigma.");
-  if (type != 1 && type != 2) return fail(-7, "The specified type of the used impulse response is not known.");
+  if (type < 1 || type > 4) return fail(-7, "The specified type of the used impulse response is not known.");
+  if (type >= 3 && !dev_a0)
+    return fail(-12, "Structural FEVD requires that draws of 'A0' are contained in the 'bvar' object.");   // R/fevd.bvar.R:98-101
+  if (type >= 3 && !a0_compact && k > 16) return fail(-2, "structural decompositions from full A0 matrices need k <= 16");
   if (k < 1 || k > 32 || response < 0 || response >= k || n_ahead < 0 || p < 0)
     return fail(-2, "bvg_fevd_draws: need 1 <= k <= 32, 0 <= response < k, n_ahead >= 0");
   if (bvg_device_count() == 0) return fail(-50, "no CUDA device available");
@@ -859,12 +872,12 @@ int bvg_fevd_draws(const double* dev_coef, int64_t coef_stride, const double* de
   double* d_out = nullptr;
   CK(cudaMalloc((void**)&d_out, nout * sizeof(double)));
   cudaError_t e = launch_fevd_draws(dev_coef, coef_stride, dev_sigma, sigma_stride, n_draws, k, p, n_ahead, type, response,
-                                    d_out, st);
+                                    d_out, st, dev_a0, a0_stride, a0_compact ? 2 : 1);
   if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, d_out, nout * sizeof(double), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(d_out);
   if (e != cudaSuccess) return cuda_fail(e, "variance-decomposition kernel");
-  if (type == 2 && normalise_gir)                                               // R/fevd.bvar.R:167-171
+  if ((type == 2 || type == 4) && normalise_gir)                                // R/fevd.bvar.R:166-170
     for (int i = 0; i <= n_ahead; ++i) {
       double sum = 0.0;
       for (int c = 0; c < k; ++c) sum += host_out[(size_t)i * k + c];
@@ -886,8 +899,13 @@ int bvg_sampler_fevd(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, i
   }
   const double* coef = s->d_coef + (tv_coef ? (size_t)period * s->P.n : 0);
   const double* sig = s->d_sigma + (tv_sig ? (size_t)period * k * k : 0);
-  return bvg_fevd_draws(coef, s->rows_coef, sig, s->rows_sigma, (int64_t)s->n_chains * s->P.iterations, k, p, n_ahead,
-                        type, response, normalise_gir, host_out, cuda_stream);
+  const double* a0 = nullptr;
+  if (type == 3 || type == 4) {
+    if (!s->P.structural) return fail(-12, "Structural FEVD requires that draws of 'A0' are contained in the 'bvar' object.");
+    a0 = s->d_coef + s->P.a0_from;
+  }
+  return bvg_fevd_draws_a0(coef, s->rows_coef, sig, s->rows_sigma, a0, s->rows_coef, 1, (int64_t)s->n_chains * s->P.iterations,
+                           k, p, n_ahead, type, response, normalise_gir, host_out, cuda_stream);
 }
 
 int bvg_forecast_draws(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,

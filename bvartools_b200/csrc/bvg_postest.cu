@@ -160,13 +160,17 @@ cudaError_t launch_irf_draws(const double* coef, long long coef_stride, const do
 // mse_i = sum_{l<=i} phi_l Sigma phi_l',  result_i[c] = numerator_i[c] / sigmajj / mse_i  (sigmajj = sqrt(Sigma_rr) for gir,
 // 1 for oir -- exactly as the reference normalises).  fevd.bvar returns the MEAN over the draws of the (h + 1) x k table:
 // a thread per draw, warp-shuffle sums, per-warp slots in shared memory, per-CTA partials reduced in a fixed order.
+// Structural types (vardecomp.cpp:32-36,41-45): sir P = A0^-1, Sigma_mse = A0^-1 A0^-T; sgir P = A0^-1 Sigma, Sigma_mse =
+// A0^-1 Sigma A0^-T -- with w = phi A0^-1 these are the oir-free / gir formulas applied to w instead of phi.
 struct FevdDims {
-  long long n_draws, coef_stride, sigma_stride;
-  int k, p, h, type, response;                    // type 1 oir, 2 gir
+  long long n_draws, coef_stride, sigma_stride, a0_stride;
+  int k, p, h, type, response;                    // type 1 oir, 2 gir, 3 sir, 4 sgir
+  int a0_mode;                                    // 1 full k x k, 2 compact strict lower triangle by column (unit diagonal)
 };
 
 __global__ void __launch_bounds__(128) fevd_draws_kernel(const __grid_constant__ FevdDims d, const double* __restrict__ coef,
-                                                         const double* __restrict__ sigma, double* __restrict__ partial) {
+                                                         const double* __restrict__ sigma, const double* __restrict__ a0,
+                                                         double* __restrict__ partial) {
   extern __shared__ double sm[];
   const int k = d.k, p = d.p, h = d.h, nout = (h + 1) * k;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -194,8 +198,31 @@ __global__ void __launch_bounds__(128) fevd_draws_kernel(const __grid_constant__
           for (int m = 0; m < c; ++m) s = fma(-Lc[(i * (i + 1)) / 2 + m], Lc[(c * (c + 1)) / 2 + m], s);
           Lc[(i * (i + 1)) / 2 + c] = (i == c) ? sqrt(s) : s / Lc[(c * (c + 1)) / 2 + c];
         }
-    } else {
+    } else if (d.type != 3) {
       sigmajj = sqrt(S[d.response + k * d.response]);
+    }
+    const double* A0 = (d.type >= 3) ? a0 + (live ? dr : 0) * d.a0_stride : nullptr;
+    double Ainv[IRF_A0_KMAX * IRF_A0_KMAX];
+    if (d.type >= 3 && d.a0_mode == 1) {
+      // full A0: Gauss-Jordan inverse with partial pivoting, once per draw
+      double W[IRF_A0_KMAX * IRF_A0_KMAX];
+      for (int e = 0; e < k * k; ++e) { W[e] = A0[e]; Ainv[e] = (e % k == e / k) ? 1.0 : 0.0; }
+      for (int c = 0; c < k; ++c) {
+        int pv = c;
+        for (int i = c + 1; i < k; ++i) if (fabs(W[i + k * c]) > fabs(W[pv + k * c])) pv = i;
+        if (pv != c)
+          for (int e = 0; e < k; ++e) {
+            double tw = W[c + k * e]; W[c + k * e] = W[pv + k * e]; W[pv + k * e] = tw;
+            tw = Ainv[c + k * e]; Ainv[c + k * e] = Ainv[pv + k * e]; Ainv[pv + k * e] = tw;
+          }
+        const double piv = 1.0 / W[c + k * c];
+        for (int e = 0; e < k; ++e) { W[c + k * e] *= piv; Ainv[c + k * e] *= piv; }
+        for (int i = 0; i < k; ++i) {
+          if (i == c) continue;
+          const double f = W[i + k * c];
+          for (int e = 0; e < k; ++e) { W[i + k * e] = fma(-f, W[c + k * e], W[i + k * e]); Ainv[i + k * e] = fma(-f, Ainv[c + k * e], Ainv[i + k * e]); }
+        }
+      }
     }
     for (int b = 0; b < k; ++b) num[b] = 0.0;
     double mse = 0.0;
@@ -217,17 +244,38 @@ __global__ void __launch_bounds__(128) fevd_draws_kernel(const __grid_constant__
         }
       }
       if (p > 0) for (int b = 0; b < k; ++b) ring[(i % p) * k + b] = ph[b];
+      if (d.type >= 3) {
+        // ph <- w = phi A0^-1 (the ring keeps phi itself)
+        if (d.a0_mode == 2) {
+          // w A0 = phi with A0 unit lower: w_c = phi_c - sum_{i > c} A0[i][c] w_i, from the last column to the first
+          for (int c = k - 2; c >= 0; --c) {
+            double sv = ph[c];
+            for (int i2 = c + 1; i2 < k; ++i2) sv = fma(-A0[c * (k - 1) - (c * (c - 1)) / 2 + (i2 - c - 1)], ph[i2], sv);
+            ph[c] = sv;
+          }
+        } else {
+          double pw[IRF_A0_KMAX];
+          for (int c = 0; c < k; ++c) {
+            double sv = 0.0;
+            for (int a = 0; a < k; ++a) sv = fma(ph[a], Ainv[a + k * c], sv);
+            pw[c] = sv;
+          }
+          for (int c = 0; c < k; ++c) ph[c] = pw[c];
+        }
+      }
       // v = phi P ;  mse += phi Sigma phi'
       for (int c = 0; c < k; ++c) {
         double s = 0.0;
         if (d.type == 1) { for (int a = c; a < k; ++a) s = fma(ph[a], Lc[(a * (a + 1)) / 2 + c], s); }
+        else if (d.type == 3) s = ph[c];
         else { for (int a = 0; a < k; ++a) s = fma(ph[a], S[a + k * c], s); }
         v[c] = s;
       }
       double q = 0.0;
       for (int c = 0; c < k; ++c) {
         double s = 0.0;
-        for (int a = 0; a < k; ++a) s = fma(ph[a], S[a + k * c], s);
+        if (d.type == 3) s = ph[c];
+        else for (int a = 0; a < k; ++a) s = fma(ph[a], S[a + k * c], s);
         q = fma(s, ph[c], q);
       }
       mse += q;
@@ -259,11 +307,13 @@ __global__ void fevd_reduce_kernel(const double* __restrict__ partial, int n_par
 // d_out: (h + 1) x k row-major = result[i][c], the mean over the draws
 cudaError_t launch_fevd_draws(const double* coef, long long coef_stride, const double* sigma, long long sigma_stride,
                               long long n_draws, int k, int p, int h, int type, int response, double* d_out,
-                              cudaStream_t stream) {
-  if (k < 1 || k > IRF_KMAX || p < 0 || h < 0 || (type != 1 && type != 2) || response < 0 || response >= k || n_draws < 1)
+                              cudaStream_t stream, const double* a0, long long a0_stride, int a0_mode) {
+  if (k < 1 || k > IRF_KMAX || p < 0 || h < 0 || type < 1 || type > 4 || response < 0 || response >= k || n_draws < 1)
     return cudaErrorInvalidValue;
+  if (type >= 3 && (a0 == nullptr || a0_mode < 1 || a0_mode > 2 || (a0_mode == 1 && k > IRF_A0_KMAX))) return cudaErrorInvalidValue;
   FevdDims d;
   d.n_draws = n_draws; d.coef_stride = coef_stride; d.sigma_stride = sigma_stride;
+  d.a0_stride = a0_stride; d.a0_mode = (type >= 3) ? a0_mode : 0;
   d.k = k; d.p = p; d.h = h; d.type = type; d.response = response;
   const int nout = (h + 1) * k;
   int threads = 128;
@@ -279,7 +329,7 @@ cudaError_t launch_fevd_draws(const double* coef, long long coef_stride, const d
   int grid = (int)((want < (long long)sms * 4) ? want : (long long)sms * 4);
   double* partial = nullptr;
   if ((e = cudaMallocAsync((void**)&partial, (size_t)grid * nout * 8, stream)) != cudaSuccess) return e;
-  fevd_draws_kernel<<<grid, threads, bytes(threads), stream>>>(d, coef, sigma, partial);
+  fevd_draws_kernel<<<grid, threads, bytes(threads), stream>>>(d, coef, sigma, a0, partial);
   fevd_reduce_kernel<<<(nout + 127) / 128, 128, 0, stream>>>(partial, grid, nout, 1.0 / (double)n_draws, d_out);
   e = cudaGetLastError();
   cudaFreeAsync(partial, stream);

@@ -300,20 +300,29 @@ def irf(obj, impulse, response, n_ahead=5, ci=0.95, shock=1, type="feir", cumula
 
 def fevd(obj, response, n_ahead=5, type="oir", normalise_gir=False, period=None):
     """fevd.bvar (R/fevd.bvar.R:72-186) for a host `bvar` object: (n_ahead + 1) x k table, mean over the draws."""
-    types = {"oir": 1, "gir": 2}
+    import torch
+    types = {"oir": 1, "gir": 2, "sir": 3, "sgir": 4}
     if type not in types:
-        if type in ("sir", "sgir"):
-            raise ValueError("Structural FEVD requires that draws of 'A0' are contained in the 'bvar' object.")
         raise ValueError("The specified type of the used impulse response is not known.")
+    structural = type in ("sir", "sgir")
+    if structural and obj.get("A0") is None:
+        raise ValueError("Structural FEVD requires that draws of 'A0' are contained in the 'bvar' object.")
     k, p, draws, dA, dS = _device_draws(obj, period)
-    if p == 0:
+    if p == 0 and not structural:                                  # R/fevd.bvar.R:93-95
         raise ValueError("Variance decompositions only supported for models with p > 0, i.e. argument 'object' must "
                          "contain element 'A', or structural models.")
     out = np.empty((n_ahead + 1, k))
     vp = C.c_void_p
-    check(lib().bvg_fevd_draws(vp(dA.data_ptr()), dA.shape[1], vp(dS.data_ptr()), k * k, draws, k, p, int(n_ahead),
-                               types[type], int(response), int(bool(normalise_gir)),
-                               out.ctypes.data_as(C.POINTER(C.c_double)), None))
+    d0 = None
+    if structural:
+        A0 = obj["A0"]
+        if isinstance(A0, list):
+            A0 = A0[np.asarray(obj["y"]).shape[0] - 1 if period is None else period]
+        d0 = torch.from_numpy(np.ascontiguousarray(A0, dtype=np.float64)).cuda()
+    check(lib().bvg_fevd_draws_a0(None if dA is None else vp(dA.data_ptr()), 0 if dA is None else dA.shape[1],
+                                  vp(dS.data_ptr()), k * k, None if d0 is None else vp(d0.data_ptr()), k * k, 0, draws, k, p,
+                                  int(n_ahead), types[type], int(response), int(bool(normalise_gir)),
+                                  out.ctypes.data_as(C.POINTER(C.c_double)), None))
     return out
 
 

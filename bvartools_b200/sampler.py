@@ -187,12 +187,13 @@ class ChainSampler:
 
     def fevd(self, response, n_ahead=5, type="oir", normalise_gir=False, period=None, p=None, stream=0):
         """Forecast error variance decomposition averaged over ALL retained draws resident on the device (fevd.bvar,
-        R/fevd.bvar.R:72-186): the (n_ahead + 1) x k table for the 0-based `response` variable; type "oir" or "gir"."""
-        types = {"oir": 1, "gir": 2}
+        R/fevd.bvar.R:72-186): the (n_ahead + 1) x k table for the 0-based `response` variable; type "oir" / "gir", and
+        "sir" / "sgir" for structural models."""
+        types = {"oir": 1, "gir": 2, "sir": 3, "sgir": 4}
         if type not in types:
-            if type in ("sir", "sgir"):
-                raise ValueError("Structural FEVD requires that draws of 'A0' are contained in the 'bvar' object.")
             raise ValueError("The specified type of the used impulse response is not known.")
+        if type in ("sir", "sgir") and not self.spec.c.structural:
+            raise ValueError("Structural FEVD requires that draws of 'A0' are contained in the 'bvar' object.")
         k = int(self.spec.c.k)
         out = np.empty((n_ahead + 1, k))
         check(lib().bvg_sampler_fevd(self.handle, int(self.lags if p is None else p), int(n_ahead), types[type],

@@ -285,11 +285,16 @@ int bvg_sampler_irf(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, in
 /* ---- forecast error variance decomposition per draw -----------------------------------------------
  * Replaces the per-draw loop of fevd.bvar (R/fevd.bvar.R:128-165) around .vardecomp (src/vardecomp.cpp:4-87) and its
  * rowMeans over the draws: host_out is the (n_ahead + 1) x k table (row i = horizon, column c = shock variable; row-major),
- * the MEAN over all draws.  type: 1 oir, 2 gir (sir / sgir need A0 draws); response 0-based; normalise_gir as :167-171.
+ * the MEAN over all draws.  type: 1 oir, 2 gir (sir / sgir: bvg_fevd_draws_a0); response 0-based; normalise_gir as :166-170.
  * Buffer layouts as in bvg_irf_draws. */
 int bvg_fevd_draws(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
                    int64_t n_draws, int32_t k, int32_t p, int32_t n_ahead, int32_t type, int32_t response,
                    int32_t normalise_gir, double* host_out, void* cuda_stream);
+/* the same with the structural types (src/vardecomp.cpp:32-36,41-45): type 3 sir, 4 sgir; dev_a0 as in bvg_irf_draws_a0 */
+int bvg_fevd_draws_a0(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
+                      const double* dev_a0, int64_t a0_stride, int32_t a0_compact, int64_t n_draws, int32_t k, int32_t p,
+                      int32_t n_ahead, int32_t type, int32_t response, int32_t normalise_gir, double* host_out,
+                      void* cuda_stream);
 int bvg_sampler_fevd(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, int32_t response, int32_t normalise_gir,
                      int32_t period, double* host_out, void* cuda_stream);
 

@@ -402,7 +402,7 @@ def irf_bvar(A_draws, Sigma_draws, k, impulse, response, n_ahead=5, ci=0.95, sho
     return np.quantile(result, [lo, 0.5, 1 - lo], axis=0).T
 
 
-def vardecomp(A, Sigma, h, type, response):
+def vardecomp(A, Sigma, h, type, response, A0=None):
     """src/vardecomp.cpp:4-87, literally; response 1-based.  Returns the (h + 1) x k table of one draw."""
     a = np.asarray(A, dtype=float)
     sigma = np.asarray(Sigma, dtype=float)
@@ -415,9 +415,17 @@ def vardecomp(A, Sigma, h, type, response):
     elif type == "gir":
         P = sigma
         sigma_mse = sigma
+    elif type == "sir":                                                  # :32-36
+        a0i = np.linalg.solve(np.asarray(A0, dtype=float), np.eye(k))
+        P = a0i
+        sigma_mse = a0i @ a0i.T
+    elif type == "sgir":                                                 # :41-45
+        a0i = np.linalg.solve(np.asarray(A0, dtype=float), np.eye(k))
+        P = a0i @ sigma
+        sigma_mse = a0i @ sigma @ a0i.T
     else:
         raise ValueError("type")
-    sigmajj = np.sqrt(sigma[response - 1, response - 1]) if type == "gir" else 1.0
+    sigmajj = np.sqrt(sigma[response - 1, response - 1]) if type in ("gir", "sgir") else 1.0
     A_temp = np.zeros((k, h * k))
     A_temp[:, :p_cols] = a[:, :p_cols]
     result = np.zeros((h + 1, k))
@@ -442,14 +450,15 @@ def vardecomp(A, Sigma, h, type, response):
     return result
 
 
-def fevd_bvar(A_draws, Sigma_draws, k, response, n_ahead=5, type="oir", normalise_gir=False):
+def fevd_bvar(A_draws, Sigma_draws, k, response, n_ahead=5, type="oir", normalise_gir=False, A0_draws=None):
     """R/fevd.bvar.R:128-175 for a constant-parameter `bvar`: the mean over the draws of .vardecomp."""
     acc = np.zeros((n_ahead + 1, k))
     for i in range(A_draws.shape[0]):
         A = A_draws[i].reshape(k, -1, order="F") if A_draws.shape[1] else np.zeros((k, k))
-        acc += vardecomp(A, Sigma_draws[i].reshape(k, k, order="F"), n_ahead, type, response)
+        A0 = None if A0_draws is None else A0_draws[i].reshape(k, k, order="F")
+        acc += vardecomp(A, Sigma_draws[i].reshape(k, k, order="F"), n_ahead, type, response, A0)
     result = acc / A_draws.shape[0]
-    if type == "gir" and normalise_gir:
+    if type in ("gir", "sgir") and normalise_gir:
         result = result / result.sum(axis=1, keepdims=True)
     return result
 

@@ -154,3 +154,28 @@ def test_structural_impulse_responses(gpu, type):
     np.testing.assert_allclose(bt.irf(fit, 1, 2, n_ahead=5, type=type, ci=0.9), wantf, rtol=1e-10, atol=1e-14)
     with pytest.raises(ValueError, match="A0"):
         bt.irf({k_: v for k_, v in fit.items() if k_ != "A0"}, 1, 2, type=type)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("type", ["sir", "sgir"])
+def test_structural_variance_decomposition(gpu, type):
+    """sir / sgir of .vardecomp (src/vardecomp.cpp:32-36,41-45): resident draws (compact a0 rows) and the host object."""
+    import bvartools_b200 as bt
+    from bvartools_b200 import ChainSampler, _abi
+    obj = helpers.model_structural(K=3, p=2, nobs=60, iterations=30, burnin=10)
+    k = 3
+    s = ChainSampler(obj, n_chains=2, seed=8)
+    s.run(0)
+    host = _abi.OutBuffers(s.spec)
+    s.fetch(host)
+    coef = host.arrays["coef"].reshape(-1, host.arrays["coef"].shape[-1])
+    sig = host.arrays["sigma"].reshape(coef.shape[0], -1)
+    A0 = np.tile(np.eye(k).reshape(-1, order="F"), (coef.shape[0], 1))
+    A0[:, [i + k * j for j in range(k) for i in range(k) if i > j]] = coef[:, -3:]
+    want = ob.fevd_bvar(coef[:, :k * k * 2], sig, k, 2, n_ahead=6, type=type, normalise_gir=True, A0_draws=A0)
+    assert helpers.relerr(s.fevd(1, n_ahead=6, type=type, normalise_gir=True), want) < TOL
+    s.close()
+    fit = bt.draw_posterior(obj, seed=8)
+    wantf = ob.fevd_bvar(np.asarray(fit["A"]), np.asarray(fit["Sigma"]), k, 3, n_ahead=4, type=type,
+                         A0_draws=np.asarray(fit["A0"]))
+    assert helpers.relerr(bt.fevd(fit, 2, n_ahead=4, type=type), wantf) < TOL
