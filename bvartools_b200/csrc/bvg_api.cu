@@ -911,6 +911,15 @@ int bvg_sampler_fevd(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, i
 int bvg_forecast_draws(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
                        int64_t n_draws, int32_t k, int32_t p, int32_t tot, int32_t n_ahead, const double* pred,
                        const double* dev_eps, uint64_t seed, double* dev_out, void* cuda_stream) {
+  return bvg_forecast_draws_a0(dev_coef, coef_stride, dev_sigma, sigma_stride, nullptr, 0, 0, n_draws, k, p, tot, n_ahead, pred,
+                               dev_eps, seed, dev_out, cuda_stream);
+}
+
+int bvg_forecast_draws_a0(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
+                          const double* dev_a0, int64_t a0_stride, int32_t a0_compact, int64_t n_draws, int32_t k, int32_t p,
+                          int32_t tot, int32_t n_ahead, const double* pred, const double* dev_eps, uint64_t seed,
+                          double* dev_out, void* cuda_stream) {
+  if (dev_a0 && !a0_compact && k > 16) return fail(-2, "forecasts from full A0 matrices need k <= 16");
   if (!dev_sigma || !pred || !dev_out || n_draws < 1) return fail(-1, "invalid arguments to bvg_forecast_draws");
   if (k < 1 || k > 32 || p < 0 || n_ahead < 1 || tot < k || (p > 0 && tot < k * p))
     return fail(-2, "bvg_forecast_draws: need 1 <= k <= 32, n_ahead >= 1, tot >= k max(p, 1)");
@@ -925,7 +934,7 @@ int bvg_forecast_draws(const double* dev_coef, int64_t coef_stride, const double
   cudaError_t e = cudaMemcpyAsync(d_pred, pred, pb, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess)
     e = launch_forecast_draws(dev_coef, coef_stride, dev_sigma, sigma_stride, n_draws, k, p, tot, n_ahead, use_a, d_pred,
-                              dev_eps, seed, dev_out, st);
+                              dev_eps, seed, dev_out, st, dev_a0, a0_stride, a0_compact ? 2 : 1);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(d_pred);
   if (e != cudaSuccess) return cuda_fail(e, "forecast kernel");
@@ -953,8 +962,9 @@ int bvg_sampler_forecast(bvg_sampler* s, int32_t p, int32_t tot, int32_t n_ahead
     if (e != cudaSuccess) rc = cuda_fail(e, "forecast eps upload");
   }
   if (rc == 0)
-    rc = bvg_forecast_draws(coef, s->rows_coef, sig, s->rows_sigma, nd, k, p, tot, n_ahead, pred, d_eps, seed, d_out,
-                            cuda_stream);
+    rc = bvg_forecast_draws_a0(coef, s->rows_coef, sig, s->rows_sigma,
+                               s->P.structural ? s->d_coef + s->P.a0_from : nullptr, s->rows_coef, 1, nd, k, p, tot, n_ahead,
+                               pred, d_eps, seed, d_out, cuda_stream);    // structural: y = A0^-1 (A x + u), predict.bvar.R:200-209
   if (rc == 0 && (n_probs > 0 || mean))
     rc = bvg_summary_draws(d_out, nd, (int64_t)n_ahead * k, probs, n_probs, mean, nullptr, quantiles, cuda_stream);
   if (rc == 0 && host_draws) {

@@ -64,7 +64,8 @@ cudaError_t launch_fevd_draws(const double* coef, long long coef_stride, const d
                               int a0_mode = 0);
 cudaError_t launch_forecast_draws(const double* coef, long long coef_stride, const double* sigma, long long sigma_stride,
                                   long long n_draws, int k, int p, int tot, int h, int use_a, const double* d_pred,
-                                  const double* d_eps, unsigned long long seed, double* d_out, cudaStream_t stream);
+                                  const double* d_eps, unsigned long long seed, double* d_out, cudaStream_t stream,
+                                  const double* a0 = nullptr, long long a0_stride = 0, int a0_mode = 0);
 cudaError_t launch_moments(const double* draws, long long chains, long long iters, long long rows, double* sums,
                            double* sumsq, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* tflops, cudaStream_t stream);

@@ -343,15 +343,50 @@ cudaError_t launch_fevd_draws(const double* coef, long long coef_stride, const d
 // deterministic; column 0 = data at T, later columns = the future exogenous / deterministic values), shared by all draws.
 // One thread per draw, its matrices in a private slice of shared memory.  eps: injected [draw][n_ahead][k] or Philox.
 struct FcstDims {
-  long long n_draws, coef_stride, sigma_stride;
+  long long n_draws, coef_stride, sigma_stride, a0_stride;
   int k, p, tot, h, use_a;
+  int a0_mode;                                    // 0 none; 1 full k x k; 2 compact strict lower triangle (unit diagonal)
   unsigned long long seed;
 };
+
+// x <- A0^-1 x: forward substitution on the compact unit-lower rows, Gaussian elimination with partial pivoting otherwise
+__device__ void a0_solve(const double* A0, int mode, int k, double* x) {
+  if (mode == 2) {
+    for (int i = 1; i < k; ++i) {
+      double sv = x[i];
+      for (int c = 0; c < i; ++c) sv = fma(-A0[c * (k - 1) - (c * (c - 1)) / 2 + (i - c - 1)], x[c], sv);
+      x[i] = sv;
+    }
+    return;
+  }
+  double W[IRF_A0_KMAX * IRF_A0_KMAX];
+  for (int e = 0; e < k * k; ++e) W[e] = A0[e];
+  for (int c = 0; c < k; ++c) {
+    int pv = c;
+    for (int i = c + 1; i < k; ++i) if (fabs(W[i + k * c]) > fabs(W[pv + k * c])) pv = i;
+    if (pv != c) {
+      for (int e = 0; e < k; ++e) { const double tw = W[c + k * e]; W[c + k * e] = W[pv + k * e]; W[pv + k * e] = tw; }
+      const double tb = x[c]; x[c] = x[pv]; x[pv] = tb;
+    }
+    const double piv = W[c + k * c];
+    for (int i = c + 1; i < k; ++i) {
+      const double f = W[i + k * c] / piv;
+      for (int e = c + 1; e < k; ++e) W[i + k * e] = fma(-f, W[c + k * e], W[i + k * e]);
+      x[i] = fma(-f, x[c], x[i]);
+    }
+  }
+  for (int i = k - 1; i >= 0; --i) {
+    double sv = x[i];
+    for (int e = i + 1; e < k; ++e) sv = fma(-W[i + k * e], x[e], sv);
+    x[i] = sv / W[i + k * i];
+  }
+}
 static constexpr int VB_FORECAST = 40;            // variate block id of the forecast errors (site = draw, period, variable)
 
 __global__ void __launch_bounds__(128) forecast_draws_kernel(const __grid_constant__ FcstDims d, const double* __restrict__ coef,
                                                              const double* __restrict__ sigma, const double* __restrict__ pred0,
-                                                             const double* __restrict__ eps, double* __restrict__ out) {
+                                                             const double* __restrict__ eps, const double* __restrict__ a0,
+                                                             double* __restrict__ out) {
   extern __shared__ double sm[];
   const int k = d.k, p = d.p, tot = d.tot, h = d.h, kk = k * k;
   const int per_thread = 3 * kk + tot + k;
@@ -381,13 +416,15 @@ __global__ void __launch_bounds__(128) forecast_draws_kernel(const __grid_consta
         }
         u[i] = s;
       }
-      // y_next = A x + u   (x = whole column, or its rows k.. when p = 0; plain random walk without coefficients)
+      // y_next = A0^-1 (A x + u)   (x = whole column, or its rows k.. when p = 0); without coefficients a random walk
+      // y + A0^-1 u (draw_forecast.cpp:33-41; A0 = I for non-structural models)
       for (int i = 0; i < k; ++i) {
         double s = u[i];
         if (d.use_a) { for (int c = 0; c < na; ++c) s = fma(A[i + k * c], col[(p == 0 ? k : 0) + c], s); }
-        else s += col[i];
-        o[(size_t)j * k + i] = s;
+        u[i] = s;
       }
+      if (d.a0_mode != 0) a0_solve(a0 + dr * d.a0_stride, d.a0_mode, k, u);
+      for (int i = 0; i < k; ++i) o[(size_t)j * k + i] = d.use_a ? u[i] : u[i] + col[i];
       // next column: new y on top, lags shifted down, exogenous / deterministic rows from pred
       for (int l = p - 1; l >= 1; --l)
         for (int i = 0; i < k; ++i) col[l * k + i] = col[(l - 1) * k + i];
@@ -400,10 +437,13 @@ __global__ void __launch_bounds__(128) forecast_draws_kernel(const __grid_consta
 
 cudaError_t launch_forecast_draws(const double* coef, long long coef_stride, const double* sigma, long long sigma_stride,
                                   long long n_draws, int k, int p, int tot, int h, int use_a, const double* d_pred,
-                                  const double* d_eps, unsigned long long seed, double* d_out, cudaStream_t stream) {
+                                  const double* d_eps, unsigned long long seed, double* d_out, cudaStream_t stream,
+                                  const double* a0, long long a0_stride, int a0_mode) {
   if (k < 1 || k > IRF_KMAX || p < 0 || h < 1 || tot < k || n_draws < 1 || ((p > 0) && tot < k * p)) return cudaErrorInvalidValue;
+  if (a0 != nullptr && (a0_mode < 1 || a0_mode > 2 || (a0_mode == 1 && k > IRF_A0_KMAX))) return cudaErrorInvalidValue;
   FcstDims d;
   d.n_draws = n_draws; d.coef_stride = coef_stride; d.sigma_stride = sigma_stride;
+  d.a0_stride = a0_stride; d.a0_mode = (a0 != nullptr) ? a0_mode : 0;
   d.k = k; d.p = p; d.tot = tot; d.h = h; d.use_a = use_a; d.seed = seed;
   int threads = 128;
   auto bytes = [&](int t) { return (size_t)t * (3 * k * k + tot + k) * 8; };
@@ -416,7 +456,7 @@ cudaError_t launch_forecast_draws(const double* coef, long long coef_stride, con
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   long long want = (n_draws + threads - 1) / threads;
   int grid = (int)((want < (long long)sms * 8) ? want : (long long)sms * 8);
-  forecast_draws_kernel<<<grid, threads, bytes(threads), stream>>>(d, coef, sigma, d_pred, d_eps, d_out);
+  forecast_draws_kernel<<<grid, threads, bytes(threads), stream>>>(d, coef, sigma, d_pred, d_eps, a0, d_out);
   return cudaGetLastError();
 }
 

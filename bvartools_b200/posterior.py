@@ -380,9 +380,14 @@ def predict(obj, n_ahead=10, new_x=None, new_d=None, ci=0.95, seed=None, eps=Non
     dE = None if eps is None else torch.from_numpy(np.ascontiguousarray(eps, dtype=np.float64)).cuda()
     out = torch.empty((draws, n_ahead, k), dtype=torch.float64, device="cuda")
     vp, dp = C.c_void_p, C.POINTER(C.c_double)
-    check(lib().bvg_forecast_draws(vp(dA.data_ptr()), coef.shape[1], vp(dS.data_ptr()), k * k, draws, k, p, tot,
-                                   int(n_ahead), predf.ctypes.data_as(dp), None if dE is None else vp(dE.data_ptr()),
-                                   _seed(seed), vp(out.data_ptr()), None))
+    d0 = None
+    if obj.get("A0") is not None:                                  # structural: y = A0^-1 (A x + u), :200-209
+        A0 = obj["A0"]
+        d0 = torch.from_numpy(np.ascontiguousarray(pick(A0) if isinstance(A0, list) else A0, dtype=np.float64)).cuda()
+    check(lib().bvg_forecast_draws_a0(vp(dA.data_ptr()), coef.shape[1], vp(dS.data_ptr()), k * k,
+                                      None if d0 is None else vp(d0.data_ptr()), k * k, 0, draws, k, p, tot,
+                                      int(n_ahead), predf.ctypes.data_as(dp), None if dE is None else vp(dE.data_ptr()),
+                                      _seed(seed), vp(out.data_ptr()), None))
     if keep_draws:
         return out.cpu().numpy()
     lo = (1.0 - ci) / 2.0

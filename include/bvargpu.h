@@ -309,6 +309,12 @@ int bvg_sampler_fevd(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, i
 int bvg_forecast_draws(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
                        int64_t n_draws, int32_t k, int32_t p, int32_t tot, int32_t n_ahead, const double* pred,
                        const double* dev_eps, uint64_t seed, double* dev_out, void* cuda_stream);
+/* the same for structural models: y_{T+j+1} = A0^-1 (A pred_j + Sigma^{1/2} eps_j) (R/predict.bvar.R:200-209,
+ * draw_forecast.cpp:33-41); dev_a0 as in bvg_irf_draws_a0 (NULL = identity) */
+int bvg_forecast_draws_a0(const double* dev_coef, int64_t coef_stride, const double* dev_sigma, int64_t sigma_stride,
+                          const double* dev_a0, int64_t a0_stride, int32_t a0_compact, int64_t n_draws, int32_t k, int32_t p,
+                          int32_t tot, int32_t n_ahead, const double* pred, const double* dev_eps, uint64_t seed,
+                          double* dev_out, void* cuda_stream);
 /* on the retained draws of a sampler (TVP / SV: the last period) + the bands of predict.bvar (:219-221): quantiles
  * [n_probs][n_ahead * k] (entry j * k + i = horizon j + 1, variable i), mean, host_draws [draws][n_ahead][k] (may be NULL),
  * host_eps injected normals on the HOST (may be NULL) */

@@ -463,10 +463,12 @@ def fevd_bvar(A_draws, Sigma_draws, k, response, n_ahead=5, type="oir", normalis
     return result
 
 
-def draw_forecast(a, sigma, pred, k, p, eps):
-    """src/draw_forecast.cpp:6-51 for one draw, literally (non-structural: a0_i = I): a = k x n_tot coefficient matrix or
-    None, sigma k x k, pred tot x (n_ahead + 1), eps (n_ahead x k) the injected arma::randn(k) of each period."""
+def draw_forecast(a, sigma, pred, k, p, eps, a0_i=None):
+    """src/draw_forecast.cpp:6-51 for one draw, literally: a = k x n_tot coefficient matrix or None, sigma k x k,
+    pred tot x (n_ahead + 1), eps (n_ahead x k) the injected arma::randn(k) of each period, a0_i = solve(A0) for
+    structural models (R/predict.bvar.R:200-209), identity otherwise."""
     pred = np.array(pred, dtype=float)
+    a0_i = np.eye(k) if a0_i is None else np.asarray(a0_i, dtype=float)
     n_ahead = pred.shape[1] - 1
     use_a = a is not None
     n_tot = a.shape[1] if use_a else 0
@@ -475,11 +477,11 @@ def draw_forecast(a, sigma, pred, k, p, eps):
         u = eigvec @ np.diag(np.sqrt(eigval)) @ eigvec.T @ eps[j]
         if use_a:
             if p == 0:
-                pred[:k, j + 1] = a @ pred[k:k + n_tot, j] + u
+                pred[:k, j + 1] = a0_i @ a @ pred[k:k + n_tot, j] + a0_i @ u
             else:
-                pred[:k, j + 1] = a @ pred[:, j] + u
+                pred[:k, j + 1] = a0_i @ a @ pred[:, j] + a0_i @ u
         else:
-            pred[:k, j + 1] = pred[:, j] + u
+            pred[:k, j + 1] = pred[:, j] + a0_i @ u
         if p > 1:
             for l in range(p - 1):
                 pred[(l + 1) * k:(l + 2) * k, j + 1] = pred[l * k:(l + 1) * k, j]

@@ -90,3 +90,42 @@ def test_predict_of_a_host_bvar_object(gpu):
     bands = bt.predict(fit, n_ahead=h, new_d=new_d, eps=eps, ci=0.9)
     for i in range(k):
         np.testing.assert_allclose(bands[i], np.quantile(want[:, :, i], [0.05, 0.5, 0.95], axis=0).T, rtol=1e-10, atol=1e-13)
+
+
+def test_structural_forecasts(gpu):
+    """Structural model: y_{T+j+1} = A0^-1 (A pred_j + u_j) (R/predict.bvar.R:200-209, draw_forecast.cpp:33-41) from the
+    resident draws (compact a0 rows) and from the host `bvar` object (full A0 matrices)."""
+    import bvartools_b200 as bt
+    from bvartools_b200 import ChainSampler, _abi
+    obj = helpers.model_structural(K=3, p=2, nobs=60, iterations=20, burnin=5)
+    k, h = 3, 4
+    s = ChainSampler(obj, n_chains=2, seed=3)
+    s.run(0)
+    host = _abi.OutBuffers(s.spec)
+    s.fetch(host)
+    coef = host.arrays["coef"].reshape(-1, host.arrays["coef"].shape[-1])
+    sig = host.arrays["sigma"].reshape(coef.shape[0], -1)
+    lower = [i + k * j for j in range(k) for i in range(k) if i > j]
+    A0 = np.tile(np.eye(k).reshape(-1, order="F"), (coef.shape[0], 1))
+    A0[:, lower] = coef[:, -3:]
+    eps = np.random.default_rng(2).standard_normal((coef.shape[0], h, k))
+    new_d = np.ones(h)
+    pred = _pred_matrix(obj, s.lags, h, new_d)
+    n_abc = coef.shape[1] - 3
+    want = np.empty((coef.shape[0], h, k))
+    for d in range(coef.shape[0]):
+        a0_i = np.linalg.inv(A0[d].reshape(k, k, order="F"))
+        want[d] = ob.draw_forecast(coef[d, :n_abc].reshape(k, -1, order="F"), sig[d].reshape(k, k, order="F"), pred, k,
+                                   s.lags, eps[d], a0_i)[:k, 1:].T
+    got = s.predict(n_ahead=h, new_d=new_d, eps=eps, keep_draws=True)
+    assert helpers.relerr(got, want) < TOL
+    s.close()
+    fit = bt.draw_posterior(obj, seed=3)
+    cf = np.concatenate([np.asarray(fit[n]) for n in ("A", "B", "C") if fit.get(n) is not None], axis=1)
+    eps1 = eps[: cf.shape[0]]
+    wantf = np.empty((cf.shape[0], h, k))
+    for d in range(cf.shape[0]):
+        a0_i = np.linalg.inv(np.asarray(fit["A0"])[d].reshape(k, k, order="F"))
+        wantf[d] = ob.draw_forecast(cf[d].reshape(k, -1, order="F"), np.asarray(fit["Sigma"])[d].reshape(k, k, order="F"),
+                                    pred, k, 2, eps1[d], a0_i)[:k, 1:].T
+    assert helpers.relerr(bt.predict(fit, n_ahead=h, new_d=new_d, eps=eps1, keep_draws=True), wantf) < TOL
