@@ -121,20 +121,26 @@ def draw_posterior(obj, FUN=None, mc_cores=None, seed=None, **kw):
     return out[0] if only_one else out
 
 
-def summary(obj, ci=(0.025, 0.5, 0.975), n_chains=1):
+def summary(obj, ci=(0.025, 0.5, 0.975), n_chains=1, period=None):
     """Posterior means, SDs, naive and time-series SEs and quantiles of a `bvar` object (R/summary.bvar.R:121-140,
     185-203, i.e. coda::summary.mcmc per draw matrix).  The draw matrices are uploaded once and reduced on the device
     (bvg_summary_draws: exact type-7 quantiles; bvg_tsse_draws: spectrum0.ar).  n_chains: the draws are `n_chains`
-    equally long chains stacked chain-major (1 = a single chain, as in the reference)."""
+    equally long chains stacked chain-major (1 = a single chain, as in the reference).  period: 0-based period for TVP /
+    SV entries (lists over t); default the last one (:33-38)."""
     import torch
     require_device()
     dp = C.POINTER(C.c_double)
     probs = np.ascontiguousarray(ci, dtype=np.float64)
     res = {}
+    tt = np.asarray(obj["y"]).shape[0]
+    if period is not None and not 0 <= int(period) < tt:
+        raise ValueError("Implausible specification of argument 'period'.")
     for name in ("A0", "A", "B", "C", "Sigma"):
         d = obj.get(name)
-        if d is None or isinstance(d, list):
+        if d is None:
             continue
+        if isinstance(d, list):
+            d = d[tt - 1 if period is None else int(period)]
         d = np.ascontiguousarray(d, dtype=np.float64)
         n, rows = d.shape
         dev = torch.from_numpy(d).cuda()

@@ -125,3 +125,19 @@ def test_summary_of_a_host_bvar_object(gpu):
         np.testing.assert_allclose(res[name]["mean"], x.mean(axis=0), rtol=1e-12, atol=1e-14)
         np.testing.assert_allclose(res[name]["quantiles"], np.quantile(x, (0.05, 0.5, 0.95), axis=0), rtol=1e-12, atol=1e-14)
         np.testing.assert_allclose(res[name]["ts_se"], ob.time_series_se(x, 1), rtol=1e-8, atol=1e-300)
+
+
+def test_summary_of_a_tvp_object_picks_a_period(gpu):
+    """TVP / SV entries of a `bvar` object are lists over the periods: summary() takes the last one unless told
+    otherwise (R/summary.bvar.R:33-38,125,187)."""
+    import bvartools_b200 as bt
+    fit = bt.draw_posterior(helpers.model_sv(tvp=True, nobs=30, iterations=40, burnin=5), seed=4)
+    T = np.asarray(fit["y"]).shape[0]
+    last = bt.summary(fit)
+    np.testing.assert_allclose(last["A"]["mean"], np.asarray(fit["A"][T - 1]).mean(axis=0), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(last["Sigma"]["sd"], np.asarray(fit["Sigma"][T - 1]).std(axis=0, ddof=1), rtol=1e-10, atol=1e-14)
+    first = bt.summary(fit, period=0)
+    np.testing.assert_allclose(first["A"]["quantiles"], np.quantile(np.asarray(fit["A"][0]), (0.025, 0.5, 0.975), axis=0),
+                               rtol=1e-12, atol=1e-14)
+    with pytest.raises(ValueError, match="period"):
+        bt.summary(fit, period=T)
