@@ -18,7 +18,7 @@ import ctypes as C
 from . import sampler
 from ._lib import check, lib, require_device
 
-__all__ = ["draw_posterior", "bvarpost", "bvar", "summary", "summary_bvarlist", "information_criteria", "thin", "irf",
+__all__ = ["draw_posterior", "bvarpost", "bvar", "summary", "summary_bvarlist", "information_criteria", "thin", "thin_bvarlist", "irf",
            "fevd", "predict"]
 
 
@@ -176,6 +176,11 @@ def thin(obj, thin=10):
                 continue
             out[name] = [np.asarray(x)[pos] for x in d] if isinstance(d, list) else np.asarray(d)[pos]
     return out
+
+
+def thin_bvarlist(objects, thin=10):
+    """thin.bvarlist (R/thin.bvarlist.R): thin every `bvar` object of a list (error objects pass through)."""
+    return [o if o.get("error") else globals()["thin"](o, thin) for o in objects]
 
 
 def information_criteria(ll, tot_pars, tt):

@@ -196,6 +196,43 @@ def test_invalid_specs_are_rejected(emu):
     assert b"SSVS with stochastic volatility" in emu.emu_last_error()
 
 
+def test_unsupported_combinations_of_the_new_branches_are_rejected(emu):
+    """Error behaviour of the structural / TVP-psi branches: what the reference forbids, or what is not built, is an
+    error code with the reference's message where there is one -- never a silent fallback."""
+    # structural + Wishart (R/add_priors.bvarmodel.R: "Structural models may not use a Wishart prior.")
+    spec = helpers._abi.spec_from_model(helpers.model_structural(), n_chains=1)
+    spec.c.sigma_type = 0
+    out = helpers._abi.OutBuffers(spec)
+    assert emu.emu_bvaralg(C.byref(spec.c), C.byref(out.c)) == -7
+    assert b"Wishart" in emu.emu_last_error()
+    # structural + SSVS: not built
+    spec = helpers._abi.spec_from_model(helpers.model_structural(), n_chains=1)
+    spec.c.varsel = helpers._abi.VARSEL_SSVS
+    assert emu.emu_bvaralg(C.byref(spec.c), C.byref(out.c)) == -5
+    # structural flag on a TVP spec: not built
+    spec = helpers._abi.spec_from_model(helpers.model_sv(tvp=True, nobs=30), n_chains=1)
+    spec.c.structural = 1
+    out = helpers._abi.OutBuffers(spec)
+    assert emu.emu_bvartvpalg(C.byref(spec.c), C.byref(out.c)) == -5
+    # TVP psi block without its state-variance prior / initial draw
+    spec = helpers._abi.spec_from_model(helpers.model_tvp_covar(), n_chains=1)
+    spec.c.psi_rate = None
+    out = helpers._abi.OutBuffers(spec)
+    assert emu.emu_bvartvpalg(C.byref(spec.c), C.byref(out.c)) == -4
+    # SSVS on the covariances of a TVP-SV model: rejected like SSVS + SV (src/bvaralg.cpp:173-175)
+    spec = helpers._abi.spec_from_model(helpers.model_tvp_covar(), n_chains=1)
+    spec.c.psi_varsel = helpers._abi.VARSEL_SSVS
+    assert emu.emu_bvartvpalg(C.byref(spec.c), C.byref(out.c)) == -11
+    assert b"SSVS" in emu.emu_last_error()
+    # covariance block together with structural coefficients (R/add_priors.bvarmodel.R)
+    cov = helpers._abi.spec_from_model(helpers.model_covar_gamma(), n_chains=1)
+    spec = helpers._abi.spec_from_model(helpers.model_structural(nobs=70), n_chains=1)
+    spec.c.psi_mu, spec.c.psi_vi = cov.c.psi_mu, cov.c.psi_vi
+    out = helpers._abi.OutBuffers(spec)
+    assert emu.emu_bvaralg(C.byref(spec.c), C.byref(out.c)) == -7
+    assert b"cannot be estimated at the same time" in emu.emu_last_error()
+
+
 def test_non_spd_prior_flags_chain_status(emu):
     obj = helpers.model_c1(iterations=5, burnin=1, coef=dict(v_i=1, v_i_det=0.1))
     obj["priors"]["coefficients"]["v_i"] = -1e6 * np.eye(21)
