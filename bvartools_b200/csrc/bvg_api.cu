@@ -78,8 +78,9 @@ static void rows_of(const Prepared& P, long long* coef, long long* sigma, long l
   *sigma = tv_sigma_of(P) ? k * k * T : k * k;
   *lambda = ((P.varsel != BVG_VARSEL_NONE) ? n : 0) + ((P.psi_varsel != BVG_VARSEL_NONE) ? k * (k - 1) / 2 : 0);
   if (P.structural) {                       // stored rows: [a | b | c | a0]; the mask itself is not an output
-    *coef = P.n_user;
+    *coef = P.tvp ? (long long)P.n_user * T : P.n_user;
     *lambda = (P.varsel_user != BVG_VARSEL_NONE) ? P.n_user : 0;
+    *sv = P.tvp ? P.n_user : 0;
   }
   *sh = svm ? k : 0;
   *sv = P.tvp ? n : 0;
@@ -822,14 +823,14 @@ int bvg_sampler_irf(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, in
     if (period >= T) return fail(-11, "Implausible specification of argument 'period'.");
   }
   const long long nd = (long long)s->n_chains * s->P.iterations;
-  const double* coef = s->d_coef + (tv_coef ? (size_t)period * s->P.n : 0);
+  const double* coef = s->d_coef + (tv_coef ? (size_t)period * (s->P.structural ? s->P.n_user : s->P.n) : 0);
   const double* sig = s->d_sigma + (tv_sig ? (size_t)period * k * k : 0);
   double* d_out = nullptr;
   CK(cudaMalloc((void**)&d_out, (size_t)nd * (n_ahead + 1) * sizeof(double)));
   const double* a0 = nullptr;                     // structural sampler: compact a0 rows at the end of every coefficient draw
   if (type >= 3) {
     if (!s->P.structural) { cudaFree(d_out); return fail(-12, "Structural IR requires that draws of 'A0' are contained in the 'bvar' x."); }
-    a0 = s->d_coef + s->P.a0_from;
+    a0 = coef + s->P.a0_from;                    // (period offset included for TVP draws)
   }
   int rc = bvg_irf_draws_a0(coef, s->rows_coef, sig, s->rows_sigma, a0, s->rows_coef, 1, nd, k, p, n_ahead, type, impulse,
                             response, shock_kind, shock, cumulative, d_out, cuda_stream);
@@ -897,12 +898,12 @@ int bvg_sampler_fevd(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, i
     if (period < 0) period = T - 1;
     if (period >= T) return fail(-11, "Implausible specification of argument 'period'.");
   }
-  const double* coef = s->d_coef + (tv_coef ? (size_t)period * s->P.n : 0);
+  const double* coef = s->d_coef + (tv_coef ? (size_t)period * (s->P.structural ? s->P.n_user : s->P.n) : 0);
   const double* sig = s->d_sigma + (tv_sig ? (size_t)period * k * k : 0);
   const double* a0 = nullptr;
   if (type == 3 || type == 4) {
     if (!s->P.structural) return fail(-12, "Structural FEVD requires that draws of 'A0' are contained in the 'bvar' object.");
-    a0 = s->d_coef + s->P.a0_from;
+    a0 = coef + s->P.a0_from;                    // (period offset included for TVP draws)
   }
   return bvg_fevd_draws_a0(coef, s->rows_coef, sig, s->rows_sigma, a0, s->rows_coef, 1, (int64_t)s->n_chains * s->P.iterations,
                            k, p, n_ahead, type, response, normalise_gir, host_out, cuda_stream);
@@ -949,7 +950,7 @@ int bvg_sampler_forecast(bvg_sampler* s, int32_t p, int32_t tot, int32_t n_ahead
   const int k = s->P.k, T = s->P.T;
   const bool tv_coef = s->P.tvp != 0, tv_sig = tv_sigma_of(s->P);
   const long long nd = (long long)s->n_chains * s->P.iterations;
-  const double* coef = s->d_coef + (tv_coef ? (size_t)(T - 1) * s->P.n : 0);      // last period (R/predict.bvar.R:73,85,146)
+  const double* coef = s->d_coef + (tv_coef ? (size_t)(T - 1) * (s->P.structural ? s->P.n_user : s->P.n) : 0);      // last period (R/predict.bvar.R:73,85,146)
   const double* sig = s->d_sigma + (tv_sig ? (size_t)(T - 1) * k * k : 0);
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const size_t ob = (size_t)nd * n_ahead * k * sizeof(double);
@@ -963,7 +964,7 @@ int bvg_sampler_forecast(bvg_sampler* s, int32_t p, int32_t tot, int32_t n_ahead
   }
   if (rc == 0)
     rc = bvg_forecast_draws_a0(coef, s->rows_coef, sig, s->rows_sigma,
-                               s->P.structural ? s->d_coef + s->P.a0_from : nullptr, s->rows_coef, 1, nd, k, p, tot, n_ahead,
+                               s->P.structural ? coef + s->P.a0_from : nullptr, s->rows_coef, 1, nd, k, p, tot, n_ahead,
                                pred, d_eps, seed, d_out, cuda_stream);    // structural: y = A0^-1 (A x + u), predict.bvar.R:200-209
   if (rc == 0 && (n_probs > 0 || mean))
     rc = bvg_summary_draws(d_out, nd, (int64_t)n_ahead * k, probs, n_probs, mean, nullptr, quantiles, cuda_stream);

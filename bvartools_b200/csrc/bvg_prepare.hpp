@@ -103,7 +103,7 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
   const int k = s->k, T = s->T, Mu = s->M;
   if (k < 2) BVG_FAIL(-7, "Model must contain at least two endogenous variables for structural analysis.");
   if (k > 64 || T < 2 || Mu < 0 || !s->Y || (Mu > 0 && !s->X)) BVG_FAIL(-3, "invalid dimensions or missing data");
-  if (s->tvp) BVG_FAIL(-5, "structural TVP models are not supported");
+  if (s->tvp && (!s->tvp_shape || !s->tvp_rate || !s->a_init)) BVG_FAIL(-4, "TVP prior shape / rate or initial draw missing");
   if (s->varsel == BVG_VARSEL_SSVS) BVG_FAIL(-5, "SSVS on a structural model is not supported");
   if (s->sigma_type == BVG_SIGMA_WISHART) BVG_FAIL(-7, "Structural models may not use a Wishart prior.");
   if (s->psi_mu || s->psi_vi) BVG_FAIL(-7, "Error covariances and structural coefficients cannot be estimated at the same time.");
@@ -135,8 +135,14 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
       include.push_back(pos[s->include[e]]);
     }
   }
+  std::vector<double> tshape, trate, ainit;
+  if (s->tvp) {                                  // state-variance priors and initial draw (masked positions: any valid value)
+    tshape.assign((size_t)na, 1.0); trate.assign((size_t)na, 1.0); ainit.assign((size_t)na, 0.0);
+    for (int r = 0; r < nu; ++r) { tshape[pos[r]] = s->tvp_shape[r]; trate[pos[r]] = s->tvp_rate[r]; ainit[pos[r]] = s->a_init[r]; }
+  }
   bvg_spec eff = *s;
   eff.structural = 0;
+  if (s->tvp) { eff.tvp_shape = tshape.data(); eff.tvp_rate = trate.data(); eff.a_init = ainit.data(); }
   eff.M = Ma; eff.X = X.data(); eff.mu = mu.data(); eff.Vi = Vi.data(); eff.vi_dense = 1;
   eff.varsel = BVG_VARSEL_BVS; eff.inprior = inprior.data();
   eff.include = include.empty() ? nullptr : include.data(); eff.n_include = (int32_t)include.size();
@@ -144,10 +150,12 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
   const int rc = prepare_impl(&eff, P);
   if (rc) return rc;
   P.structural = 1; P.n_user = nu; P.varsel_user = s->varsel; P.a0_from = k * Mu;
-  // lambda = 0 on the masked positions (state: Sigma^-1 (k k) | prior diagonal (n) | lambda (n) | ...)
+  // lambda = 0 on the masked positions (state: Sigma^-1 (k k) | prior diagonal (n) | lambda (n) | ...;
+  // TVP state: Sigma^-1 | state precisions (n) | initial state (n) | lambda (n) | ...)
   std::vector<unsigned char> kept((size_t)na, 0);
   for (int r = 0; r < nu; ++r) kept[pos[r]] = 1;
-  for (int r = 0; r < na; ++r) if (!kept[r]) P.state0[(size_t)k * k + na + r] = 0.0;
+  const size_t lam_off = (size_t)k * k + (size_t)(s->tvp ? 2 : 1) * na;
+  for (int r = 0; r < na; ++r) if (!kept[r]) P.state0[lam_off + r] = 0.0;
   return 0;
 }
 

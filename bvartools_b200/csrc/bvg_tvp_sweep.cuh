@@ -617,7 +617,25 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
 
     BVG_TVPC_TICK(12);
     // ================= store (:502-551) =================
-    if (keep) {
+    if (keep && m.a0_from >= 0) {
+      // structural model: only the kept rows [a | b | c | a0 (variable j, equation i > j)] of the masked augmented system
+      const int a0 = m.a0_from, n_out = a0 + (k * (k - 1)) / 2;
+      double* oc = out.coef + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n_out * (size_t)T;
+      double* ov = out.sigma_v + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n_out;
+      double* ol = (out.lambda != nullptr) ? out.lambda + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n_out
+                                           : nullptr;
+      for (int r = tid; r < n; r += G) {
+        int o = r;
+        if (r >= a0) {
+          const int j = (r - a0) / k, i = (r - a0) % k;
+          if (i <= j) continue;
+          o = a0 + j * (k - 1) - (j * (j - 1)) / 2 + (i - j - 1);
+        }
+        for (int t = 0; t < T; ++t) oc[(size_t)t * n_out + o] = apath[(size_t)t * n + r];
+        ov[o] = 1.0 / q[r];
+        if (ol != nullptr) ol[o] = lam[r];
+      }
+    } else if (keep) {
       double* oc = out.coef + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n * (size_t)T;
       for (int e = tid; e < n * T; e += G) oc[e] = apath[e];
       double* ov = out.sigma_v + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n;

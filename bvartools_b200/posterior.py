@@ -94,9 +94,19 @@ def bvarpost(obj, seed=None, **kw):
         lower = [i + k * j for j in range(k) for i in range(k) if i > j]
         a0 = post["a0"]
         draws = np.asarray(a0["coeffs"]).shape[1]
-        coeffs = np.tile(np.eye(k).reshape(-1, 1, order="F"), (1, draws))
-        coeffs[lower] = a0["coeffs"]
+        if obj["model"].get("tvp"):                                 # k^2 T rows, period-major (:84-87)
+            tt = np.asarray(obj["data"]["Y"]).shape[0]
+            coeffs = np.tile(np.eye(k).reshape(-1, 1, order="F"), (tt, draws))
+            rows = [t * k * k + r for t in range(tt) for r in lower]
+            coeffs[rows] = a0["coeffs"]
+        else:
+            coeffs = np.tile(np.eye(k).reshape(-1, 1, order="F"), (1, draws))
+            coeffs[lower] = a0["coeffs"]
         A0 = {"coeffs": coeffs}
+        if "sigma" in a0:                                           # :93-96
+            sg = np.zeros((k * k, draws))
+            sg[lower] = a0["sigma"]
+            A0["sigma"] = sg
         if "lambda" in a0:
             lam = np.full((k * k, draws), np.nan)
             lam[lower] = a0["lambda"]

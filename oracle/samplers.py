@@ -7,8 +7,8 @@
 the (nT) x (nT) TVP system) and runs the same LAPACK-level operations; `literal=False` evaluates the identical
 formulas through their Kronecker / banded structure (used for long tier-2 runs; proven equal to the literal
 path to <= 1e-10 in tests/test_oracle.py).  The covariance (psi) block of the constant-parameter sampler
-(bvaralg.cpp:373-455, gamma / SV errors) is restated literally; its SSVS / BVS twins, the TVP psi block and
-structural TVP models are outside the accelerated path and raise.  Random variates come from a VariateSource (injected arrays
+(bvaralg.cpp:373-455, gamma / SV errors) with its SSVS / BVS twins, the TVP psi block (bvartvpalg.cpp:339-407) and
+structural models (general z from data$SUR) are restated literally.  Random variates come from a VariateSource (injected arrays
 or a NumPy Generator) in the site order of oracle/variates.py.
 """
 from __future__ import annotations
@@ -47,8 +47,6 @@ def _unpack_common(obj):
     if "exogen" in model:
         n_b = k * len(model["exogen"]["variables"]) * (int(model["exogen"]["lags"]) + 1)
     n_c = k * len(model.get("deterministic", []))
-    if model.get("structural") and model.get("tvp"):
-        raise NotImplementedError("structural TVP models are outside the accelerated path (SURVEY.md 8f-4)")
     return data, model, priors, initial, y, k, tt, z, n_tot, n_a, n_b, n_c
 
 
@@ -642,6 +640,12 @@ def bvartvpalg(obj, variates: VariateSource | None = None, literal=True, table="
 
     posteriors = {"a0": None, "a": None, "b": None, "c": None, "sigma": None}
     _split_rows(posteriors, draws_coef, draws_lambda, n_a, n_b, n_c, tvp_T=tt, sig=draws_sigma_v)
+    if model.get("structural") and k > 1:                                                 # :513-516,590-603
+        a0_from = n_a + n_b + n_c
+        cube = draws_coef.reshape(tt, n, -1)
+        posteriors["a0"] = {"coeffs": cube[:, a0_from:, :].reshape(tt * (n - a0_from), -1), "sigma": draws_sigma_v[a0_from:]}
+        if draws_lambda is not None:
+            posteriors["a0"]["lambda"] = draws_lambda[a0_from:]
     posteriors["sigma"] = {"coeffs": draws_sigma_u}
     if sv:
         posteriors["sigma"]["sigma"] = draws_sigma_sigma

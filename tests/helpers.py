@@ -113,14 +113,14 @@ def model_tvp_covar(K=3, p=1, nobs=24, iterations=8, burnin=3, seed=41, sv=True,
                       bvs=dict(inprior=0.5, exclude_det=True, covar=psi_bvs) if (bvs or psi_bvs) else None)
 
 
-def model_structural(K=3, p=1, nobs=50, iterations=12, burnin=4, seed=9, sv=False, bvs=False):
+def model_structural(K=3, p=1, nobs=50, iterations=12, burnin=4, seed=9, sv=False, bvs=False, tvp=False):
     """Structural VAR (A0 coefficients: equation i contains -y_j, j < i) with inverse-gamma or SV error variances."""
     y = synth_var(K, p, nobs, seed)
-    m = gen_var(y, p=p, deterministic="const", iterations=iterations, burnin=burnin, structural=True, sv=sv)
+    m = gen_var(y, p=p, deterministic="const", iterations=iterations, burnin=burnin, structural=True, sv=sv, tvp=tvp)
     sigma = dict(shape=3, rate=1e-3)
     if sv:
         sigma.update(mu=0, v_i=0.01, sigma_h=0.05, constant=1e-4)
-    return add_priors(m, coef=dict(v_i=1, v_i_det=0.1), sigma=sigma,
+    return add_priors(m, coef=dict(v_i=1, v_i_det=0.1, shape=3, rate=1e-4, rate_det=0.01), sigma=sigma,
                       bvs=dict(inprior=0.5, exclude_det=True) if bvs else None)
 
 
@@ -195,11 +195,18 @@ def make_variates(obj, n_chains, seed):
         # (variable j, equation i <= j) masked: coefficient-level injected arrays are indexed by the internal position
         Mu = obj["data"]["Z"].shape[1]
         pos = list(range(k * Mu)) + [k * (Mu + j) + i for j in range(k) for i in range(j + 1, k)]
-        for kname in ("coef_normal", "bvs_u1", "bvs_u2"):
+        na = k * (Mu + k)
+        for kname in ("coef_normal", "bvs_u1", "bvs_u2", "sigma_v_gamma", "a_init_normal"):
             if kname in stacked:
-                full = np.full(stacked[kname].shape[:2] + (k * (Mu + k),), 0.5)
+                full = np.full(stacked[kname].shape[:2] + (na,), 0.5)
                 full[:, :, pos] = stacked[kname]
                 stacked[kname] = full
+        if "state_normal" in stacked:                         # [chain][sweep][T * n], period-major
+            sn = stacked["state_normal"]
+            src = sn.reshape(sn.shape[0], sn.shape[1], T, -1)
+            full = np.full(sn.shape[:2] + (T, na), 0.5)
+            full[:, :, :, pos] = src
+            stacked["state_normal"] = full.reshape(sn.shape[0], sn.shape[1], T * na)
     return per_chain, stacked
 
 

@@ -89,9 +89,21 @@ CASES["exogen_ssvs"] = (lambda: _exogen(ssvs=True), {})
 CASES["exogen_sv_covar"] = (lambda: _exogen(sv=True), {})
 
 
-@pytest.mark.parametrize("name", sorted(CASES))
+# Structural TVP models (A0_t random walks): added after the round's GPU budget was spent -- verified on the host
+# emulation of the kernel logic only, hence not part of CASES (which tests/test_gpu_parity.py runs on the device).
+CPU_ONLY_CASES = {
+    "structural_tvp_gamma": (lambda: helpers.model_structural(tvp=True, nobs=24, iterations=6, burnin=2), {}),
+    "structural_tvp_sv": (lambda: helpers.model_structural(tvp=True, sv=True, nobs=24, iterations=6, burnin=2), {}),
+    "structural_tvp_gamma_bvs": (lambda: helpers.model_structural(tvp=True, bvs=True, nobs=24, iterations=8, burnin=2), {}),
+    "structural_tvp_sv_bvs_k4": (lambda: helpers.model_structural(tvp=True, K=4, p=1, sv=True, bvs=True, nobs=20,
+                                                                  iterations=6, burnin=2), {}),
+}
+ALL_CASES = dict(CASES, **CPU_ONLY_CASES)
+
+
+@pytest.mark.parametrize("name", sorted(ALL_CASES))
 def test_kernel_logic_matches_oracle(emu, name):
-    builder, kw = CASES[name]
+    builder, kw = ALL_CASES[name]
     obj = builder()
     table = kw.get("mixture", "ksc1998")
     per, stacked = helpers.make_variates(obj, 2, seed=11)
@@ -109,11 +121,12 @@ def test_kernel_logic_matches_oracle(emu, name):
 
 @pytest.mark.parametrize("G", [4, 32])
 @pytest.mark.parametrize("name", ["kron_c1", "kron_grid_p4", "kron_k2", "c1_wishart_moment", "c1_informative_prior", "ssvs_moment", "bvs_direct", "gamma",
-                                  "sv_bvs", "tvp_sv_bvs", "tvp_wishart", "tvp_covar_sv", "tvp_covar_gamma"])
+                                  "sv_bvs", "tvp_sv_bvs", "tvp_wishart", "tvp_covar_sv", "tvp_covar_gamma",
+                                  "structural_gamma_bvs", "structural_tvp_sv"])
 def test_kernel_logic_spmd_lanes_match_oracle(emu, name, G):
     """Same check with the chain owned by G real threads (barriers + emulated shuffles): exercises the
     one-row-per-lane Cholesky / back substitution, the register Wishart block and the work distribution."""
-    builder, kw = CASES[name]
+    builder, kw = ALL_CASES[name]
     obj = builder()
     per, stacked = helpers.make_variates(obj, 1, seed=13)
     fn = emu.emu_bvartvpalg if obj["model"].get("tvp") else emu.emu_bvaralg
@@ -209,11 +222,12 @@ def test_unsupported_combinations_of_the_new_branches_are_rejected(emu):
     spec = helpers._abi.spec_from_model(helpers.model_structural(), n_chains=1)
     spec.c.varsel = helpers._abi.VARSEL_SSVS
     assert emu.emu_bvaralg(C.byref(spec.c), C.byref(out.c)) == -5
-    # structural flag on a TVP spec: not built
-    spec = helpers._abi.spec_from_model(helpers.model_sv(tvp=True, nobs=30), n_chains=1)
-    spec.c.structural = 1
+    # structural TVP model together with the covariance block
+    cov = helpers._abi.spec_from_model(helpers.model_tvp_covar(), n_chains=1)
+    spec = helpers._abi.spec_from_model(helpers.model_structural(tvp=True, sv=True, nobs=24), n_chains=1)
+    spec.c.psi_mu, spec.c.psi_vi = cov.c.psi_mu, cov.c.psi_vi
     out = helpers._abi.OutBuffers(spec)
-    assert emu.emu_bvartvpalg(C.byref(spec.c), C.byref(out.c)) == -5
+    assert emu.emu_bvartvpalg(C.byref(spec.c), C.byref(out.c)) == -7
     # TVP psi block without its state-variance prior / initial draw
     spec = helpers._abi.spec_from_model(helpers.model_tvp_covar(), n_chains=1)
     spec.c.psi_rate = None
