@@ -337,7 +337,7 @@ int bvg_stochvol(int64_t B, int T, int k, const double* y, const double* h, cons
   if (eps) inject(rp, VB_SV_N, de.as<double>(), (int)kt);
   BvarModel proto;
   memset(&proto, 0, sizeof(proto));
-  proto.k = k; proto.T = T; proto.n_mix = J; proto.sigma_type = SIG_SV;
+  proto.k = k; proto.T = T; proto.n_mix = J; proto.sigma_type = SIG_SV; proto.a0_from = -1;
   proto.mix_p = dtab.as<double>(); proto.mix_mu = dtab.as<double>() + 10; proto.mix_s2 = dtab.as<double>() + 20;
   const size_t smem = (4 * kt + BVG_BLOCK_SCRATCH) * 8;
   if ((rc = prep_smem(stochvol_kernel, smem))) return rc;

@@ -278,7 +278,7 @@ extern "C" int emu_stochvol(int64_t B, int T, int k, const double* y, const doub
   if (eps) block_inject(rp, VB_SV_N, eps, (int)kt);
   BvarModel m;
   memset(&m, 0, sizeof(m));
-  m.k = k; m.T = T; m.n_mix = J; m.sigma_type = SIG_SV;
+  m.k = k; m.T = T; m.n_mix = J; m.sigma_type = SIG_SV; m.a0_from = -1;
   m.mix_p = tab.data(); m.mix_mu = tab.data() + 10; m.mix_s2 = tab.data() + 20;
   std::vector<double> U(kt), hh(kt), pr(kt), rh(kt);
   std::vector<int> sidx(kt);
