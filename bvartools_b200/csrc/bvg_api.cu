@@ -77,13 +77,13 @@ static void rows_of(const Prepared& P, long long* coef, long long* sigma, long l
   *coef = P.tvp ? n * T : n;
   *sigma = tv_sigma_of(P) ? k * k * T : k * k;
   *lambda = ((P.varsel != BVG_VARSEL_NONE) ? n : 0) + ((P.psi_varsel != BVG_VARSEL_NONE) ? k * (k - 1) / 2 : 0);
+  *sh = svm ? k : 0;
+  *sv = P.tvp ? n : 0;
   if (P.structural) {                       // stored rows: [a | b | c | a0]; the mask itself is not an output
     *coef = P.tvp ? (long long)P.n_user * T : P.n_user;
     *lambda = (P.varsel_user != BVG_VARSEL_NONE) ? P.n_user : 0;
     *sv = P.tvp ? P.n_user : 0;
   }
-  *sh = svm ? k : 0;
-  *sv = P.tvp ? n : 0;
 }
 
 extern "C" {
@@ -109,10 +109,17 @@ void bvg_set_interrupt_poll(int (*poll)(void)) { g_poll = poll; }
 int bvg_out_rows(const bvg_spec* spec, int64_t* coef_rows, int64_t* sigma_rows, int64_t* lambda_rows,
                  int64_t* sigma_h_rows, int64_t* sigma_v_rows) {
   if (!spec) return fail(-1, "spec is NULL");
-  Prepared P;
+  Prepared P;                              // the fields rows_of() reads, derived as prepare() derives them
   P.k = spec->k; P.T = spec->T; P.M = spec->M; P.n = spec->k * spec->M; P.tvp = spec->tvp ? 1 : 0;
   P.sigma_type = spec->sigma_type; P.varsel = spec->varsel;
+  P.n_psi = (spec->psi_mu != nullptr) ? spec->k * (spec->k - 1) / 2 : 0;
   P.psi_varsel = (spec->psi_mu != nullptr) ? spec->psi_varsel : BVG_VARSEL_NONE;
+  if (spec->structural) {                  // masked BVS model on [x; -y]; the kept rows [a | b | c | a0] are stored
+    P.structural = 1;
+    P.n_user = spec->k * spec->M + spec->k * (spec->k - 1) / 2;
+    P.varsel_user = spec->varsel;
+    P.M = spec->M + spec->k; P.n = spec->k * P.M; P.varsel = BVG_VARSEL_BVS;
+  }
   long long a, b, c, d, e;
   rows_of(P, &a, &b, &c, &d, &e);
   if (coef_rows) *coef_rows = a;

@@ -43,7 +43,20 @@ def test_out_rows():
     L = lib()
     for obj, want in ((helpers.model_c1(), (21, 9, 0, 0, 0)),
                       (helpers.model_c3(K=3, p=2, nobs=60), (21, 9, 21, 0, 0)),
-                      (helpers.model_sv(nobs=40, tvp=True), (21 * 38, 9 * 38, 0, 3, 21))):
+                      (helpers.model_sv(nobs=40, tvp=True), (21 * 38, 9 * 38, 0, 3, 21)),
+                      # structural: k M + k (k - 1) / 2 stored rows (constant and TVP), BVS indicators on the same rows
+                      (helpers.model_structural(K=3, p=1, nobs=30), (15, 9, 0, 0, 0)),
+                      (helpers.model_structural(K=3, p=1, nobs=30, bvs=True), (15, 9, 15, 0, 0)),
+                      (helpers.model_structural(K=3, p=1, nobs=30, tvp=True), (15 * 29, 9, 0, 0, 15)),
+                      (helpers.model_structural(K=3, p=1, nobs=30, tvp=True, sv=True, bvs=True),
+                       (15 * 29, 9 * 29, 15, 3, 15)),
+                      # covariance (psi) block: Sigma_t per period for TVP models even with gamma variances; psi
+                      # inclusion draws appended to lambda
+                      (helpers.model_tvp_covar(K=3, p=1, nobs=24, sv=False), (12 * 23, 9 * 23, 0, 0, 12)),
+                      (helpers.model_tvp_covar(K=3, p=1, nobs=24, sv=True, bvs=True, psi_bvs=True),
+                       (12 * 23, 9 * 23, 12 + 3, 3, 12)),
+                      (helpers.model_covar_gamma(K=3, p=2, nobs=40, psi_sel="ssvs"), (21, 9, 24, 0, 0)),
+                      (helpers.model_covar_gamma(K=3, p=2, nobs=40, bvs=True, psi_sel="bvs"), (21, 9, 24, 0, 0))):
         spec = _abi.spec_from_model(obj)
         vals = [C.c_int64() for _ in range(5)]
         assert L.bvg_out_rows(C.byref(spec.c), *[C.byref(v) for v in vals]) == 0

@@ -64,6 +64,20 @@ def test_c4_shape_tvp_sv_injected(gpu):
         assert helpers.relerr(out.arrays[key], want[key]) < 1e-8, key      # state dim nT = 1260
 
 
+def test_c4_full_size_tvp_sv_injected(gpu):
+    """Config c4 at BASELINE size (T = 200, n = 21, state dimension nT = 4200; bvartvpalg.cpp:290-297): 2 chains x 3
+    sweeps against the structured oracle (== the literal dense path at this size: test_oracle.py
+    ::test_literal_equals_structured_c4_full_size)."""
+    obj = helpers.model_sv(tvp=True, nobs=202, iterations=2, burnin=1)
+    per, stacked = helpers.make_variates(obj, 2, seed=8)
+    out = _run(gpu, obj, 2, stacked)
+    want = helpers.oracle_stack(obj, per, literal=False)
+    assert out.arrays["coef"].shape == (2, 2, 4200)
+    for key in want:
+        assert helpers.relerr(out.arrays[key], want[key]) < 1e-8, key
+    assert not out.status.any()
+
+
 @pytest.mark.parametrize("case", ["n21", "n150", "n189"])
 def test_large_path_small_models_injected(gpu, case):
     """The large-VAR path (per-chain matrices in HBM, blocked DMMA Cholesky) forced on models that also fit on chip
@@ -383,3 +397,45 @@ def test_structural_model_through_the_mirror(gpu):
     got_m, ref_m = A0[:, lower].mean(axis=0), ref.mean(axis=1)
     se = np.sqrt(A0[:, lower].var(axis=0, ddof=1) / 400 + ref.var(axis=1, ddof=1) / 400)
     assert np.all(np.abs(got_m - ref_m) < 6.0 * se), (got_m, ref_m, se)
+
+
+def test_structural_tvp_guard_padded_buffers(gpu):
+    """Structural TVP models store k M + k (k - 1) / 2 rows of sigma_v / lambda per draw, not the k (M + k) rows of the
+    augmented model the kernels run on: bvg_bvartvpalg must fill exactly the buffers bvg_out_rows announces (guard words
+    behind every output stay intact) and run_to_host == fetch == the oracle."""
+    from bvartools_b200 import _abi
+    obj = helpers.model_structural(tvp=True, sv=True, bvs=True, nobs=24, iterations=6, burnin=2)
+    per, stacked = helpers.make_variates(obj, 3, seed=17)
+    spec = _abi.spec_from_model(obj, n_chains=3, seed=0, inject=stacked)
+    vals = [C.c_int64() for _ in range(5)]
+    assert gpu.bvg_out_rows(C.byref(spec.c), *[C.byref(v) for v in vals]) == 0
+    rows = spec.out_rows()
+    assert [v.value for v in vals] == [rows[nm] for nm in ("coef", "sigma", "lambda", "sigma_h", "sigma_v")]
+    GUARD = 64
+    sentinel = -7.25e300
+
+    def alloc(shape):
+        flat = np.full(int(np.prod(shape)) + GUARD, sentinel)
+        alloc.raw.append(flat)
+        return flat[:-GUARD].reshape(shape)
+    alloc.raw = []
+    out = _abi.OutBuffers(spec, alloc=alloc)
+    assert gpu.bvg_bvartvpalg(C.byref(spec.c), C.byref(out.c)) == 0, gpu.bvg_last_error()
+    for flat in alloc.raw:
+        assert np.all(flat[-GUARD:] == sentinel)
+        assert not np.any(flat[:-GUARD] == sentinel)
+    want = helpers.oracle_stack(obj, per)
+    assert set(want) == set(out.arrays)
+    for key in want:
+        assert helpers.relerr(out.arrays[key], want[key]) < TOL, key
+    assert np.array_equal(out.arrays["lambda"], want["lambda"])
+    # handle API: fetch() and the on-device summary of sigma_v use the same row count
+    from bvartools_b200 import ChainSampler
+    s = ChainSampler(obj, n_chains=3, seed=0, inject=stacked)
+    s.run()
+    got = s.fetch()
+    for key in want:
+        assert np.array_equal(got.arrays[key], out.arrays[key]), key
+    sm = s.summary("sigma_v", ts_se=False)
+    np.testing.assert_allclose(sm["mean"], out.arrays["sigma_v"].reshape(-1, rows["sigma_v"]).mean(axis=0), rtol=1e-12)
+    s.close()

@@ -89,16 +89,13 @@ CASES["exogen_ssvs"] = (lambda: _exogen(ssvs=True), {})
 CASES["exogen_sv_covar"] = (lambda: _exogen(sv=True), {})
 
 
-# Structural TVP models (A0_t random walks): added after the round's GPU budget was spent -- verified on the host
-# emulation of the kernel logic only, hence not part of CASES (which tests/test_gpu_parity.py runs on the device).
-CPU_ONLY_CASES = {
-    "structural_tvp_gamma": (lambda: helpers.model_structural(tvp=True, nobs=24, iterations=6, burnin=2), {}),
-    "structural_tvp_sv": (lambda: helpers.model_structural(tvp=True, sv=True, nobs=24, iterations=6, burnin=2), {}),
-    "structural_tvp_gamma_bvs": (lambda: helpers.model_structural(tvp=True, bvs=True, nobs=24, iterations=8, burnin=2), {}),
-    "structural_tvp_sv_bvs_k4": (lambda: helpers.model_structural(tvp=True, K=4, p=1, sv=True, bvs=True, nobs=20,
-                                                                  iterations=6, burnin=2), {}),
-}
-ALL_CASES = dict(CASES, **CPU_ONLY_CASES)
+# Structural TVP models (A0_t random walks; bvartvpalg.cpp:44-47,544,594)
+CASES["structural_tvp_gamma"] = (lambda: helpers.model_structural(tvp=True, nobs=24, iterations=6, burnin=2), {})
+CASES["structural_tvp_sv"] = (lambda: helpers.model_structural(tvp=True, sv=True, nobs=24, iterations=6, burnin=2), {})
+CASES["structural_tvp_gamma_bvs"] = (lambda: helpers.model_structural(tvp=True, bvs=True, nobs=24, iterations=8, burnin=2), {})
+CASES["structural_tvp_sv_bvs_k4"] = (lambda: helpers.model_structural(tvp=True, K=4, p=1, sv=True, bvs=True, nobs=20,
+                                                                      iterations=6, burnin=2), {})
+ALL_CASES = CASES
 
 
 @pytest.mark.parametrize("name", sorted(ALL_CASES))

@@ -98,6 +98,18 @@ def test_literal_equals_structured(builder):
         assert np.array_equal(lit["lambda"], stru["lambda"])
 
 
+def test_literal_equals_structured_c4_full_size():
+    """Config c4 at BASELINE size (T = 200, state dimension nT = 4200): the dense (nT)^2 LU + Cholesky path of
+    bvartvpalg.cpp:290-297 against the block-bidiagonal restatement the device tests use as their checker."""
+    obj = helpers.model_sv(tvp=True, nobs=202, iterations=1, burnin=1)
+    per, _ = helpers.make_variates(obj, 1, seed=3)
+    lit = helpers.oracle_stack(obj, per, literal=True)
+    stru = helpers.oracle_stack(obj, per, literal=False)
+    assert lit["coef"].shape == (1, 1, 4200)
+    for name in lit:
+        assert helpers.relerr(stru[name], lit[name]) < 1e-9, name
+
+
 @pytest.mark.parametrize("builder", [
     lambda: helpers.model_c1(iterations=25, burnin=5),
     lambda: helpers.model_c3(K=3, p=2, nobs=80, iterations=20, burnin=5),
