@@ -211,9 +211,9 @@ int bvg_sampler_create(const bvg_spec* spec, bvg_sampler** out) {
   CKS(cudaMalloc(&s->d_state, (size_t)s->n_chains * P.state_len * sizeof(double)));
   CKS(cudaMalloc(&s->d_status, (size_t)s->n_chains * sizeof(int)));
   if (P.tvp) {
-    s->scratch_per_chain = tvp_scratch_len(P.T, P.n);
-    CKS(cudaMalloc(&s->d_scratch, (size_t)s->n_chains * (size_t)s->scratch_per_chain * sizeof(double)));
     bind_tvp(P, s->d_blob, s->d_include, &s->tm);
+    s->scratch_per_chain = tvp_scratch_len(P.T, P.k, P.M, P.n, P.n_psi, s->tm.b.diag_sigma);
+    CKS(cudaMalloc(&s->d_scratch, (size_t)s->n_chains * (size_t)s->scratch_per_chain * sizeof(double)));
   } else {
     bind_bvar(P, s->d_blob, s->d_include, &s->bm);
   }

@@ -60,6 +60,8 @@ struct BvarModel {
   const double* mix_p; const double* mix_mu; const double* mix_s2;   // n_mix each
   const double* omega_off;         // k x k off-diagonal part of the initial Sigma^-1 (gamma prior), zero diagonal
   // covariance (psi) block (bvaralg.cpp:373-455); n_psi = 0: none
+  int diag_sigma;                  // TVP: the measurement precision stays diagonal (SV, or gamma variances with a diagonal
+                                   // initial value, no covariance block): equation-decoupled state draw (bvg_tvp_eq8.cuh)
   int a0_from;                     // structural models: first internal row of the -y block (k M_user); -1 otherwise
   int n_psi;                       // k (k - 1) / 2
   const double* psi_vi;            // n_psi x n_psi prior precision (col-major); its diagonal lives in the chain state
@@ -423,6 +425,131 @@ BVG_HD void sv_step(const Grp& g, const ChainRng& rng, int sweep, const BvarMode
 }
 
 #if defined(__CUDACC__)
+// The same step for a chain owned by one full warp (device only).  Differences to the group-generic version above, all
+// about latency -- with ~200 KB of shared memory per SM the L1 is a few KB, so local-memory arrays and global tables miss
+// to L2 on every touch:
+//   * the mixture tables live in registers (J is a template parameter: the component loops unroll, no local arrays) and,
+//     for the data-dependent look-up of the selected component, in 2 J doubles of shared memory (`tab`);
+//   * divisions by per-component constants are multiplications by their reciprocals and the J normalisations q_j / sum
+//     are one reciprocal (differences of an ulp in the cumulative probabilities: an indicator changes only if the uniform
+//     falls within ~1e-16 of a boundary);
+//   * the log-volatility normals are drawn as Box-Muller pairs (same sites, half the Philox / log calls);
+//   * the power-of-two rescale of the continued fraction works on the exponent bits (same values as frexp / ldexp).
+template <int J>
+static __device__ __noinline__ void sv_step_w32_j(const ChainRng& rng, int sweep, const int k, const int T,
+                                                  const double* __restrict__ mix_p, const double* __restrict__ mix_mu,
+                                                  const double* __restrict__ mix_s2, const double* __restrict__ sv_const,
+                                                  double* U, double* h, const double* sigma_h, const double* h_init,
+                                                  double* pr, double* rh, double* tab) {
+  const int lane = threadIdx.x & 31;
+  double c_mu[J], c_isd[J], c_pd[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const double sd = sqrt(mix_s2[j]);
+    c_isd[j] = 1.0 / sd;
+    c_pd[j] = mix_p[j] / (sd * 2.5066282746310002);
+    c_mu[j] = mix_mu[j];
+  }
+  if (lane < J) { tab[lane] = 1.0 / mix_s2[lane]; tab[J + lane] = mix_mu[lane]; }
+  __syncwarp();
+  const bool inj_u = rng.injected(VB_SV_U);
+  for (int e = lane; e < k * T; e += 32) {
+    const int t = e / k, i = e - t * k;
+    const double u = U[e];
+    const double ys = log(fma(u, u, sv_const[i]));                                 // :91
+    const double ht = h[t + T * i];
+    double q[J];
+    double qs = 0.0;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const double z = (ys - (ht + c_mu[j])) * c_isd[j];
+      q[j] = c_pd[j] * exp(-0.5 * (z * z));                                        // :94 (arma::normpdf)
+      qs += q[j];
+    }
+    const double uu = inj_u ? rng.inj_at(VB_SV_U, sweep, i * T + t) : philox_uniform(rng.seed, rng.chain, VB_SV_U, sweep, i * T + t, 0);
+    const double rq = 1.0 / qs;
+    double cum = 0.0;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      cum = fma(q[j], rq, cum);                                                    // :95-96
+      cnt += (uu < cum) ? 1 : 0;
+    }
+    int s = J - cnt;
+    if (s > J - 1) s = J - 1;                                                      // reference: out of bounds
+    const double p = tab[s];                                                       // :101
+    pr[i * T + t] = p;
+    rh[i * T + t] = p * (ys - tab[J + s]);                                         // :103 sigs * (y - mu_s)
+  }
+  __syncwarp();
+  // eps: the residual array U is free now and takes the normals, site (series, t) -> U[i T + t]
+  {
+    const int nsite = k * T, npair = (nsite + 1) >> 1;
+    for (int p = lane; p < npair; p += 32) {
+      const Normal2 nn = rng.normal_pair(VB_SV_N, sweep, p, nsite);
+      U[2 * p] = nn.a;
+      if (2 * p + 1 < nsite) U[2 * p + 1] = nn.b;
+    }
+  }
+  if (lane < k) {                                                                  // (a): pr <- N_t, h <- D_t
+    const int i = lane;
+    const double si = 1.0 / sigma_h[i], si2 = si * si;                             // hh / sigma(i), :99
+    double* p = pr + i * T;
+    double* hd = h + T * i;
+    double N = ((0 < T - 1) ? 2.0 : 1.0) * si + p[0], D = 1.0;
+    p[0] = N; hd[0] = D;
+#pragma unroll 4
+    for (int t = 1; t < T; ++t) {
+      const double dg = ((t < T - 1) ? 2.0 : 1.0) * si + p[t];
+      const double Nn = fma(dg, N, -si2 * D);
+      D = N; N = Nn;
+      if ((t & 3) == 3) {                                                          // joint power-of-two rescale: ratio exact
+        int f = 2045 - ((__double2hiint(N) >> 20) & 0x7ff);                        // N 2^(f - 1023) lies in [0.5, 1)
+        f = f < 1 ? 1 : (f > 2046 ? 2046 : f);
+        const double sc = __hiloint2double(f << 20, 0);
+        N *= sc; D *= sc;
+      }
+      p[t] = N; hd[t] = D;
+    }
+  }
+  __syncwarp();
+  for (int e = lane; e < k * T; e += 32) {                                         // pr <- 1 / l_t ; non-positive pivot -> NaN
+    const double c = pr[e] / h[e];
+    pr[e] = 1.0 / sqrt(c);
+  }
+  __syncwarp();
+  if (lane < k) {                                                                  // (b) and (c)
+    const int i = lane;
+    const double si = 1.0 / sigma_h[i];
+    const double* rl = pr + i * T;
+    double* r = rh + i * T;
+    const double* ep = U + i * T;
+    double w = (r[0] + si * h_init[i]) * rl[0];                                    // hh * 1 * h_init = e_1 h_init
+    r[0] = w + ep[0];
+#pragma unroll 4
+    for (int t = 1; t < T; ++t) {
+      w = fma(si * rl[t - 1] * rl[t], w, r[t] * rl[t]);
+      r[t] = w + ep[t];                                                            // z_t = w_t + eps_t
+    }
+    double hn = r[T - 1] * rl[T - 1];
+    h[T - 1 + T * i] = hn;
+#pragma unroll 4
+    for (int t = T - 2; t >= 0; --t) {
+      hn = fma(si * rl[t] * rl[t], hn, r[t] * rl[t]);
+      h[t + T * i] = hn;
+    }
+  }
+  __syncwarp();
+}
+
+// tab: 20 doubles of shared memory
+static __device__ __forceinline__ void sv_step_w32(const ChainRng& rng, int sweep, const BvarModel& m, double* U, double* h,
+                                                   const double* sigma_h, const double* h_init, double* pr, double* rh,
+                                                   double* tab) {
+  if (m.n_mix == 7) sv_step_w32_j<7>(rng, sweep, m.k, m.T, m.mix_p, m.mix_mu, m.mix_s2, m.sv_const, U, h, sigma_h, h_init, pr, rh, tab);
+  else sv_step_w32_j<10>(rng, sweep, m.k, m.T, m.mix_p, m.mix_mu, m.mix_s2, m.sv_const, U, h, sigma_h, h_init, pr, rh, tab);
+}
+
 // Tile-packed precision matrix for the CTA-per-chain kernels (bvg_tiled.cuh): P = V^-1 + Lambda (z'Dz) Lambda written
 // half tile by half tile (a warp stores 32 consecutive doubles: no bank conflicts, no per-row imbalance), identity
 // padding rows included.  GW != nullptr: SV form (block-diagonal weights), else XX' (x) Sigma^-1.   (bvaralg.cpp:303-305)

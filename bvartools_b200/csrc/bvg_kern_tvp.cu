@@ -11,7 +11,7 @@
 namespace bvg {
 
 #if BVG_G == 32
-#define BVG_TVP_BOUNDS __launch_bounds__(128, 2)   // shared memory allows ~7 warps per SM anyway: registers are free
+#define BVG_TVP_BOUNDS __launch_bounds__(256, 1)   // shared memory allows ~7 warps per SM anyway: registers are free
 #else
 #define BVG_TVP_BOUNDS __launch_bounds__(128, 6)
 #endif
@@ -28,8 +28,16 @@ __global__ void BVG_TVP_BOUNDS BVG_CAT(tvp_tile_kernel_g, BVG_G)(
   if (chain >= n_chains) return;
   TileGroup<G> g;
   const ChainRng rng(&rp, chain);
+#if defined(BVG_TVP_PROF) && BVG_G == 32
+  if (threadIdx.x < 16) s_tvp_prof[threadIdx.x] = 0;
+  __syncthreads();
+#endif
   tvp_chain(g, m, rng, state + (size_t)chain * state_len, scratch + (size_t)chain * scratch_per_chain,
             smem + (size_t)cib * smem_per_chain, out, chain, s0, s1, burnin);
+#if defined(BVG_TVP_PROF) && BVG_G == 32
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x < 16) g_tvp_prof[threadIdx.x] += s_tvp_prof[threadIdx.x];
+#endif
 }
 #else
 __global__ void BVG_CAT(tvp_tile_kernel_g, BVG_G)(

@@ -1,5 +1,6 @@
 // bvg_kern_util.cu -- launch planning, posterior-moment reduction, FP64 peak probe.
 #include "bvg_kernels.cuh"
+#include <stdlib.h>
 
 namespace bvg {
 
@@ -50,21 +51,24 @@ cudaError_t plan_bvar(const BvarModel& m, long long n_chains, int requested_tpc,
 
 cudaError_t plan_tvp(const TvpModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan) {
   plan->kron = 0;
-  int per = tvp_smem_len(m.b.k, m.b.T, m.b.n, m.b.sigma_type, false, m.b.n_psi);
+  int per = tvp_smem_len(m.b.k, m.b.T, m.b.n, m.b.sigma_type, TVP_GENERIC, m.b.n_psi);
   int tpc = requested_tpc;
   if (tpc <= 0) {
-    if ((size_t)per * 8 > 48 * 1024 || m.b.n > 64) tpc = (m.b.n > 96) ? 256 : 128;
+    if (tvp_eq8_ok(m.b.k, m.b.M, m.b.n_psi, m.b.diag_sigma)) tpc = 32;      // equation-decoupled path: one warp per chain
+    else if ((size_t)per * 8 > 48 * 1024 || m.b.n > 64) tpc = (m.b.n > 96) ? 256 : 128;
     else tpc = pick_tile(m.b.n);
   }
-  const bool tiled = (tpc == 32) && tvp_tiled_ok(m.b.n, m.b.n_psi);      // warp per chain, DMMA tile path
-  if (tiled) per = tvp_smem_len(m.b.k, m.b.T, m.b.n, m.b.sigma_type, true);
+  const int mode = tvp_mode(tpc, m.b.k, m.b.M, m.b.n, m.b.n_psi, m.b.diag_sigma);
+  if (mode != TVP_GENERIC) per = tvp_smem_len(m.b.k, m.b.T, m.b.n, m.b.sigma_type, mode, m.b.n_psi);
   cudaError_t e = finish_plan(plan, per, n_chains, tpc);
-  if (e == cudaSuccess && tiled) {
+  if (e == cudaSuccess && mode != TVP_GENERIC) {
     // one chain per CTA: the chains (each a latency-bound sequential recursion) spread evenly over the SMs
-    plan->block_threads = 32;
-    plan->chains_per_block = 1;
-    plan->smem_bytes = (size_t)per * 8;
-    plan->grid = (int)n_chains;
+    int cpb = 1;
+    if (const char* ev = getenv("BVG_TVP_CPB")) cpb = atoi(ev) > 0 ? atoi(ev) : 1;   // experiment: warps (chains) per CTA
+    plan->block_threads = 32 * cpb;
+    plan->chains_per_block = cpb;
+    plan->smem_bytes = (size_t)per * 8 * cpb;
+    plan->grid = (int)((n_chains + cpb - 1) / cpb);
   }
   return e;
 }

@@ -34,6 +34,7 @@ struct Prepared {
   // of the -y block permanently masked; n_user = k M_user + k (k - 1) / 2 rows are stored, varsel_user is what the
   // caller asked for (the mask itself rides on the BVS machinery), a0_from = k M_user (first row of the A0 block)
   int structural = 0, n_user = 0, varsel_user = 0, a0_from = -1;
+  int diag_sigma = 0;   // Sigma_t^-1 stays diagonal over the whole run (SV / gamma variances, diagonal start, no psi block)
   int psi_varsel = 0;
   long psi_mu = -1, psi_vi = -1, psi_vmu = -1, psi_tau0 = -1, psi_tau1 = -1, psi_inprior = -1;
   std::vector<unsigned char> psi_include;
@@ -237,6 +238,7 @@ static inline int prepare_impl(const bvg_spec* s, Prepared& P) {
     if (!s->sv_mu || !s->sv_vi || !s->sigma_shape || !s->sigma_rate || !s->sv_sigma_h || !s->sv_constant || !s->sv_h)
       BVG_FAIL(-4, "Missing prior specifications for stochastic volatility prior.");
     P.n_mix = (s->sv_mixture == BVG_MIX_OCSN2007) ? 10 : 7;
+    P.diag_sigma = 1;
     std::vector<double> gs(k);
     for (int i = 0; i < k; ++i) gs[i] = s->sigma_shape[i] + 0.5 * T;               // bvaralg.cpp:223
     P.gshape = P.push(gs);
@@ -268,6 +270,8 @@ static inline int prepare_impl(const bvg_spec* s, Prepared& P) {
       P.grate = P.push(s->sigma_rate, k);
       for (int e = 0; e < kk; ++e) omega_off[e] = (e % k == e / k) ? 0.0 : s->sigma_i[e];
       P.omega_off = P.push(omega_off);
+      P.diag_sigma = 1;
+      for (int e = 0; e < kk; ++e) if (omega_off[e] != 0.0) P.diag_sigma = 0;
     }
   }
 
@@ -478,6 +482,7 @@ static inline const double* at(const double* base, long off) { return off < 0 ? 
 static inline void bind_bvar(const Prepared& P, const double* base, const unsigned char* inc, BvarModel* m) {
   m->k = P.k; m->T = P.T; m->M = P.M; m->n = P.n;
   m->a0_from = P.a0_from;
+  m->diag_sigma = (P.diag_sigma && P.n_psi == 0) ? 1 : 0;
   m->sigma_type = P.sigma_type; m->varsel = P.varsel; m->resid_mode = P.resid_mode; m->n_mix = P.n_mix;
   m->Y = at(base, P.Y); m->X = at(base, P.X); m->XX = at(base, P.XX); m->YX = at(base, P.YX);
   m->Aols = at(base, P.Aols); m->SSE = at(base, P.SSE); m->mu = at(base, P.mu);

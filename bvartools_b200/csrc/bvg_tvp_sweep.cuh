@@ -13,6 +13,7 @@
 #pragma once
 #include "bvg_bvar_sweep.cuh"
 #include "bvg_tvp_tiled.cuh"
+#include "bvg_tvp_eq8.cuh"
 
 namespace bvg {
 
@@ -53,14 +54,35 @@ BVG_HD int tvp_state_len(int k, int T, int n, int sigma_type, int n_psi = 0) {
 // global scratch per chain: T*tri(n) (M_t) + T*n (w_t + eps_t) + T*n (a path)
 // (the warp-per-chain tile path streams full 8 x 8 tiles: tiled_len(n) >= tri(n) doubles per period)
 // (models with the psi block run the generic recursion: their Sigma_t^-1 is a full matrix per period)
+// (diagonal Sigma_t^-1, warp per chain: the equation-decoupled path streams 44 k doubles per period, bvg_tvp_eq8.cuh)
+enum TvpMode : int { TVP_GENERIC = 0, TVP_TILED = 1, TVP_EQ8 = 2 };
 BVG_HD bool tvp_tiled_ok(int n, int n_psi = 0) { return n <= 32 && n_psi == 0; }
-BVG_HD long long tvp_scratch_len(int T, int n) { return (long long)T * ((tvp_tiled_ok(n) ? tiled_len(n) : tri(n)) + 2 * n); }
+// the path a chain owned by `lanes` lanes takes (lanes = 32: one warp per chain)
+BVG_HD int tvp_mode(int lanes, int k, int M, int n, int n_psi, int diag_sigma) {
+  if (lanes != 32) return TVP_GENERIC;
+  if (tvp_eq8_ok(k, M, n_psi, diag_sigma)) return TVP_EQ8;
+  return tvp_tiled_ok(n, n_psi) ? TVP_TILED : TVP_GENERIC;
+}
+BVG_HD int tvp_stream_len(int mode, int k, int n) {
+  return mode == TVP_EQ8 ? tvp_eq8_stream(k) : (mode == TVP_TILED ? tiled_len(n) : tri(n));
+}
+// large enough for whichever path the launch plan picks (even, so that chains stay 16-byte aligned)
+BVG_HD long long tvp_scratch_len(int T, int k, int M, int n, int n_psi, int diag_sigma) {
+  int st = tri(n);
+  if (tvp_tiled_ok(n, n_psi) && tiled_len(n) > st) st = tiled_len(n);
+  if (tvp_eq8_ok(k, M, n_psi, diag_sigma)) st = (tvp_eq8_stream(k) > tri(n)) ? tvp_eq8_stream(k) : tri(n);
+  const long long len = (long long)T * (st + 2 * n);
+  return len + (len & 1);
+}
 
-BVG_HD int tvp_smem_len(int k, int T, int n, int sigma_type, bool tiled = false, int n_psi = 0) {
-  int len = (tiled ? 2 * tiled_len(n) + 10 * (n + 8) : 3 * tri(n) + 9 * n) + 6 * k * k + 2 * k + k * T;
-  if (sigma_type == SIG_SV) len += 3 * k * T + 2 * k;
+BVG_HD int tvp_smem_len(int k, int T, int n, int sigma_type, int mode = TVP_GENERIC, int n_psi = 0) {
+  int len = 6 * k * k + 2 * k + k * T;
+  if (mode == TVP_TILED) len += 2 * tiled_len(n) + 10 * (n + 8);
+  else if (mode == TVP_EQ8) len += tvp_eq8_smem(k) + tri(n) + 9 * n;
+  else len += 3 * tri(n) + 9 * n;
+  if (sigma_type == SIG_SV) len += 3 * k * T + 2 * k + 20;                   // h, ew, work, sigma_h, h_init, mixture look-up
   if (n_psi > 0) len += T * k * k + T * n_psi + 4 * n_psi;
-  return len;
+  return len + (len & 1);
 }
 
 template <class Grp>
@@ -172,14 +194,18 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
   const int n_psi = m.n_psi;
   const bool covar = n_psi > 0;
 #if defined(__CUDA_ARCH__)
-  const bool tiled = Grp::kWarp32 && tvp_tiled_ok(n, n_psi);   // warp per chain, n <= 32: DMMA tile path (bvg_tvp_tiled.cuh)
+  const int mode = tvp_mode(Grp::kWarp32 ? 32 : 0, k, M, n, n_psi, m.diag_sigma);
 #else
-  const bool tiled = false;
+  const int mode = TVP_GENERIC;
 #endif
+  const bool tiled = mode == TVP_TILED;                 // warp per chain, n <= 32: DMMA tile path (bvg_tvp_tiled.cuh)
+  const bool eq8 = mode == TVP_EQ8;                     // warp per chain, diagonal Sigma_t^-1: bvg_tvp_eq8.cuh
+  const bool fused = eq8 && !bvs && m.a0_from < 0;      // its backward pass also stores the path and forms the residuals
   const int nv = tiled ? n + 8 : n;                     // vectors are zero padded to whole tiles
+  double* xs = sm;      sm += eq8 ? tvp_eq8_smem(k) : 0;   // first: 16-byte aligned exchange area of the eq8 path
   double* Dt = sm;      sm += tiled ? tiled_len(n) : tn;
-  double* Mi = sm;      sm += tiled ? 0 : tn;
-  double* Cq = sm;      sm += tiled ? tiled_len(n) : tn;
+  double* Mi = sm;      sm += (tiled || eq8) ? 0 : tn;
+  double* Cq = sm;      sm += tiled ? tiled_len(n) : (eq8 ? 0 : tn);
   double* wv = sm;      sm += nv;     // rhs_t -> w_t
   double* cvec = sm;    sm += nv;     // Q M_t' w_t (carry into t+1)
   double* dinv = sm;    sm += nv;
@@ -200,7 +226,8 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
   double* kv = sm;      sm += k;
   double* U = sm;       sm += k * T;
   double* h = nullptr; double* ew = nullptr; double* svw = nullptr; double* sigma_h = nullptr; double* h_init = nullptr;
-  if (sv) { h = sm; sm += k * T; ew = sm; sm += k * T; svw = sm; sm += k * T; sigma_h = sm; sm += k; h_init = sm; sm += k; }
+  double* svtab = nullptr;
+  if (sv) { h = sm; sm += k * T; ew = sm; sm += k * T; svw = sm; sm += k * T; sigma_h = sm; sm += k; h_init = sm; sm += k; svtab = sm; sm += 20; }
   double* sigt = nullptr; double* psip = nullptr; double* pq = nullptr; double* pinit = nullptr;
   double* plam = nullptr; double* pnew = nullptr;
   const bool psi_bvs = covar && m.psi_varsel == VS_BVS;
@@ -209,8 +236,8 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
     plam = sm; sm += n_psi; pnew = sm; sm += n_psi;
   }
   const int lam_rows = (bvs ? n : 0) + (psi_bvs ? n_psi : 0);
-  double* Mpath = scratch;                         // [T][tn]  (tiled: [T][tiled_len(n)])
-  double* wpath = scratch + (size_t)T * (tiled ? tiled_len(n) : tn);   // [T][n]
+  double* Mpath = scratch;                         // [T][tn]  (tiled: [T][tiled_len(n)], eq8: [T][44 k])
+  double* wpath = scratch + (size_t)T * tvp_stream_len(mode, k, n);   // [T][n]
   double* apath = wpath + (size_t)T * n;           // [T][n]
   int fail = 0;
 
@@ -235,8 +262,9 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
   for (int sweep = sweep_begin; sweep < sweep_end; ++sweep) {
     const bool keep = sweep >= burnin;
     const long long pos = (long long)sweep - burnin;
-    if (sv) {
+    if (sv && (sweep == sweep_begin || !Grp::kWarp32)) {
       // bvartvpalg.cpp:446; the very first sweep uses h.row(0) for every period (:224-225,230)
+      // (warp per chain: later sweeps take exp(-h) from the end of the previous sweep's SV block, one exp pass per sweep)
       for (int e = tid; e < k * T; e += G) ew[e] = 1.0 / exp(sweep == 0 ? h[T * (e / T)] : h[e]);
       g.sync();
     }
@@ -250,7 +278,14 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
     }
     const bool svd = sv && !covar;                      // diagonal Sigma_t^-1 read from ew; covar: full matrix per period
 #if defined(__CUDA_ARCH__)
-    if (tiled) {
+    if (eq8) {
+      // without BVS (and without the row selection of structural models) the backward pass stores the retained path and
+      // forms the residuals itself; the scratch copy of the path is not needed then
+      double* oc = (fused && keep) ? out.coef + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n * (size_t)T : nullptr;
+      if constexpr (Grp::kWarp32)
+        tvp_state_draw_eq8(m, rng, sweep, sv, xs, q, a_init, bvs ? lam : nullptr, sig, ew, Mpath, wpath,
+                           fused ? nullptr : apath, oc, fused ? U : nullptr, tmp2, fail);
+    } else if (tiled) {
       if constexpr (Grp::kWarp32)
         tvp_state_draw_tiled(m, rng, sweep, sv, Dt, Cq, wv, cvec, xl, anext, tmp, q, a_init, bvs ? lam : nullptr, sig,
                              ew, kv, Mpath, wpath, apath, fail);
@@ -346,7 +381,7 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
 
     // ================= BVS (bvartvpalg.cpp:300-330) and residuals (:332-336) =================
     BVG_TVPC_TICK0
-    tvp_residuals(g, m, apath, lam, bvs, U);
+    if (!fused) tvp_residuals(g, m, apath, lam, bvs, U);
     BVG_TVPC_TICK(8);
     if (bvs) {
       for (int r = tid; r < n; r += G) {
@@ -451,6 +486,10 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
     double* out_sig = nullptr;
     if (keep) out_sig = out.sigma + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)((sv || covar) ? kk * T : kk);
     if (sv) {
+#if defined(__CUDA_ARCH__)
+      if constexpr (Grp::kWarp32) sv_step_w32(rng, sweep, m, U, h, sigma_h, h_init, ew, svw, svtab);
+      else
+#endif
       sv_step(g, rng, sweep, m, U, h, sigma_h, h_init, ew, svw);                       // :414
       BVG_TVPC_TICK(9);
       for (int i = tid; i < k; i += G) {
@@ -480,12 +519,22 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
       for (int i = tid; i < k; i += G) W4[i] += rng.normal(VB_HINIT_N, sweep, i);
       g.sync();
       back_solve_lt_generic(g, W1, kd, W4, h_init, k);                                         // :429
-      if (keep) {
-        if (!covar)
+      if (Grp::kWarp32 && !covar) {
+        // exp(-h) once per sweep: the measurement precisions of the next sweep (:446) and, inverted, the stored Sigma_t
+        for (int e = tid; e < k * T; e += G) { const double w = 1.0 / exp(h[e]); ew[e] = w; svw[e] = 1.0 / w; }
+        g.sync();
+        if (keep)
           for (int e = tid; e < kk * T; e += G) {
-            const int t = e / kk, f = e % kk, i = f % k, j = f / k;
-            out_sig[e] = (i == j) ? 1.0 / (1.0 / exp(h[t + T * i])) : 0.0;             // :507-509
+            const int t = e / kk, f = e - t * kk, j = f / k, i = f - j * k;
+            out_sig[e] = (i == j) ? svw[t + T * i] : 0.0;                              // :507-509
           }
+      } else if (keep && !covar) {
+        for (int e = tid; e < kk * T; e += G) {
+          const int t = e / kk, f = e % kk, i = f % k, j = f / k;
+          out_sig[e] = (i == j) ? 1.0 / (1.0 / exp(h[t + T * i])) : 0.0;               // :507-509
+        }
+      }
+      if (keep) {
         double* osh = out.sigma_h + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)k;
         for (int i = tid; i < k; i += G) osh[i] = kv[i];
       }
@@ -590,7 +639,9 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
     // ================= state variances (:469-477) and initial state (:480-482) =================
     for (int r = tid; r < n; r += G) {
       double ss = 0.0, prev = a_init[r];
-      for (int t = 0; t < T; ++t) { const double v = apath[(size_t)t * n + r]; const double d = v - prev; ss = fma(d, d, ss); prev = v; }
+      if (eq8 && !bvs) ss = tmp2[r];                  // accumulated by the backward pass of the state draw
+      else
+        for (int t = 0; t < T; ++t) { const double v = apath[(size_t)t * n + r]; const double d = v - prev; ss = fma(d, d, ss); prev = v; }
       const double scale = 1.0 / (tm.v_rate[r] + ss * 0.5);
       tmp[r] = rng.gamma(VB_SIGV_G, sweep, r, tm.v_shape_post[r]) * scale;             // :476
     }
@@ -598,6 +649,17 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
     BVG_TVPC_TICK(11);
     for (int r = tid; r < n; r += G) q[r] = tmp[r];
     g.sync();
+    if (eq8 && m.vi_off == nullptr) {
+      // diagonal prior precision: the n x n system of :480-482 is diagonal, L = sqrt(d), a_init = (b / L + eps) / L
+      for (int r = tid; r < n; r += G) {
+        const double a0 = fused ? xs[68 * k + 8 * (r % k) + r / k] : apath[r];          // a_0 (Eq8Smem::AN after the backward pass)
+        const double v0 = m.vdiag0[r], d = v0 + q[r];
+        if (!(d > 0.0)) fail = 1;
+        const double rs = bvg_rsqrt(d);
+        a_init[r] = (fma(v0, m.mu[r], q[r] * a0) * rs + rng.normal(VB_AINIT_N, sweep, r)) * rs;
+      }
+      g.sync();
+    } else {
     for (int r = tid; r < n; r += G) {
       double* Dr = Dt + tri(r);
       for (int c = 0; c <= r; ++c) {
@@ -605,7 +667,7 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
         if (c == r) v += m.vdiag0[r] + q[r];
         Dr[c] = v;
       }
-      double b = m.vdiag0[r] * m.mu[r] + q[r] * apath[r];
+      double b = m.vdiag0[r] * m.mu[r] + q[r] * (fused ? xs[68 * k + 8 * (r % k) + r / k] : apath[r]);
       if (m.vmu_off != nullptr) b += m.vmu_off[r];
       wv[r] = b;
     }
@@ -614,6 +676,7 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
     for (int r = tid; r < n; r += G) wv[r] += rng.normal(VB_AINIT_N, sweep, r);
     g.sync();
     back_solve_lt(g, Dt, dinv, wv, a_init, n);
+    }
 
     BVG_TVPC_TICK(12);
     // ================= store (:502-551) =================
@@ -637,7 +700,8 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
       }
     } else if (keep) {
       double* oc = out.coef + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n * (size_t)T;
-      for (int e = tid; e < n * T; e += G) oc[e] = apath[e];
+      if (!fused)
+        for (int e = tid; e < n * T; e += G) oc[e] = apath[e];
       double* ov = out.sigma_v + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n;
       for (int r = tid; r < n; r += G) ov[r] = 1.0 / q[r];                             // :525
       if (out.lambda != nullptr && lam_rows > 0) {

@@ -18,8 +18,11 @@ namespace bvg {
 
 #if defined(__CUDACC__)
 #ifdef BVG_TVP_PROF   // cycles per phase of the state draw, accumulated by lane 0 of chain 0 (tools/micro, never in the product build)
+// accumulated in shared memory (an LDS / STS pair per tick; a global read-modify-write would stall the in-order warp for an
+// L2 round trip at every tick) and flushed to g_tvp_prof at the end of the kernel (bvg_kern_tvp.cu)
 static __device__ long long g_tvp_prof[16];
-#define BVG_TVP_TICK(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now_ = clock64(); g_tvp_prof[slot] += now_ - tick_; tick_ = now_; } } while (0)
+__shared__ long long s_tvp_prof[16];
+#define BVG_TVP_TICK(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now_ = clock64(); s_tvp_prof[slot] += now_ - tick_; tick_ = now_; } } while (0)
 #define BVG_TVP_TICK0 long long tick_ = clock64();
 #else
 #define BVG_TVP_TICK(slot) do { } while (0)

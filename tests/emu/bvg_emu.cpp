@@ -146,8 +146,8 @@ extern "C" int emu_bvartvpalg(const bvg_spec* s, const bvg_out* o) {
   std::vector<int> status(s->n_chains, 0);
   out.status = status.data();
   out.iters = s->iterations;
-  std::vector<double> sm(tvp_smem_len(P.k, P.T, P.n, P.sigma_type, false, P.n_psi) + 16);
-  std::vector<double> scratch((size_t)tvp_scratch_len(P.T, P.n));
+  std::vector<double> sm(tvp_smem_len(P.k, P.T, P.n, P.sigma_type, TVP_GENERIC, P.n_psi) + 16);
+  std::vector<double> scratch((size_t)tvp_scratch_len(P.T, P.k, P.M, P.n, P.n_psi, m.b.diag_sigma));
   SerialGroup g;
   const int sweeps = s->iterations + s->burnin;
   const int chunk = s->sweeps_per_launch > 0 ? s->sweeps_per_launch : sweeps;

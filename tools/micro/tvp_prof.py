@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
-"""Cycles per phase of the tiled TVP state draw (chain 0, lane 0).  Needs a measurement build of the library:
-    make -C bvartools_b200/csrc clean && make -C bvartools_b200/csrc -j16 EXTRA=-DBVG_TVP_PROF
-(rebuild without EXTRA afterwards: the product library carries no instrumentation)."""
+"""Cycles per phase of the warp-per-chain TVP sweep (chain 0, lane 0).  Needs a measurement build of the library
+(tools/build_prof_lib.sh -> build_alt/libbvargpu_prof.so; the product library carries no instrumentation):
+    BVG_LIB=build_alt/libbvargpu_prof.so python tools/micro/tvp_prof.py"""
 import ctypes as C
 import pathlib
 import sys
@@ -23,7 +23,7 @@ torch.cuda.synchronize()
 out = (C.c_longlong * 16)()
 rc = lib().bvg_debug_tvp_prof(out)
 T = 200
-names = ["build", "factor", "inverse", "w=M b + stream", "carry (M.M, cvec)", "(unused)", "backward (whole pass)", "normals prologue", "residuals", "sv_step", "sigma_h / h_init / Sigma out", "state variances", "a_init draw", "store", "factor_invert only"]
+names = ["build", "factor", "inverse / columns", "publish + stream", "carry (tiled path)", "(unused)", "backward (whole pass)", "normals prologue", "residuals", "sv_step", "sigma_h / h_init / Sigma out", "state variances", "a_init draw", "store", "factor_invert only (tiled path)"]
 tot = sum(out[:15])
 print("rc", rc, "kernel ms", s.last_kernel_ms)
 for i, nm in enumerate(names):
