@@ -1,6 +1,5 @@
 // bvg_kern_util.cu -- launch planning, posterior-moment reduction, FP64 peak probe.
 #include "bvg_kernels.cuh"
-#include <stdlib.h>
 
 namespace bvg {
 
@@ -63,12 +62,10 @@ cudaError_t plan_tvp(const TvpModel& m, long long n_chains, int requested_tpc, L
   cudaError_t e = finish_plan(plan, per, n_chains, tpc);
   if (e == cudaSuccess && mode != TVP_GENERIC) {
     // one chain per CTA: the chains (each a latency-bound sequential recursion) spread evenly over the SMs
-    int cpb = 1;
-    if (const char* ev = getenv("BVG_TVP_CPB")) cpb = atoi(ev) > 0 ? atoi(ev) : 1;   // experiment: warps (chains) per CTA
-    plan->block_threads = 32 * cpb;
-    plan->chains_per_block = cpb;
-    plan->smem_bytes = (size_t)per * 8 * cpb;
-    plan->grid = (int)((n_chains + cpb - 1) / cpb);
+    plan->block_threads = 32;
+    plan->chains_per_block = 1;
+    plan->smem_bytes = (size_t)per * 8;
+    plan->grid = (int)n_chains;
   }
   return e;
 }

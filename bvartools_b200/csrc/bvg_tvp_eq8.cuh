@@ -28,12 +28,11 @@ namespace bvg {
 
 // 1 = this path applies (host and device agree on it: scratch / shared-memory sizes depend on it)
 BVG_HD bool tvp_eq8_ok(int k, int M, int n_psi, int diag_sigma) { return diag_sigma != 0 && n_psi == 0 && k <= 4 && M >= 1 && M <= 8; }
-BVG_HD int tvp_eq8_smem(int k) { return 44 * k + 4 * 8 * k + 4; }                    // CQ|g, cvec, x, eps, a_next, y
-BVG_HD int tvp_eq8_stream(int k) { return 44 * k; }                                  // doubles per period in HBM
+BVG_HD int tvp_eq8_smem(int k) { return (44 * k + 12) + 4 * 8 * k + 4; }             // block (CQ|g, x, y), cvec, x, eps, a_next, y
+BVG_HD int tvp_eq8_stream(int k) { return 44 * k + 12; }                             // doubles per period in HBM
 
 #if defined(__CUDACC__)
 #define BVG_EQ8_OFF(c) (8 * (c) - (((c) * ((c) - 1)) >> 1))      // first slot of packed column c (rows c..7)
-#define BVG_EQ8_RING 4                                            // periods of the backward stream in flight (registers)
 
 // 1 / sqrt(d) for the pivots: the hardware seed (MUFU.RSQ64H, ~20 bits) and one third-order step,
 // y = y0 + y0 e (1/2 + 3/8 e), e = 1 - d y0^2 -- the fast path of the library's rsqrt() without its range check, call and
@@ -51,15 +50,41 @@ __device__ __forceinline__ double eq8_rsqrt(double d) {
 // lives in local memory, and with ~200 KB of shared memory per SM the L1 that would cache it is a few KB: a miss is an L2
 // round trip on the critical path).  Forward and backward passes are separate functions so that each gets its own register
 // allocation (the backward ring is 96 registers that the forward loop needs for the factor).
+// Values that must live in registers across the period loops.  Kernel parameters and function arguments are otherwise
+// re-materialised by ptxas from the constant bank / the stack at the top of every period (an L2 round trip when the small
+// caches miss); the result of a shuffle is opaque to it.  (The lane reads its own value: identity.)
+// Pointers keep their address space: global ones through __builtin_assume(__isGlobal), shared ones as an (opaque) offset
+// into the dynamic shared-memory array -- a pointer rebuilt from two shuffled halves would be generic, and every access
+// through it a generic load with 64-bit address arithmetic.
+extern __shared__ double eq8_dyn_smem[];
+__device__ __forceinline__ int eq8_pin(int v) { return __shfl_sync(0xffffffffu, v, threadIdx.x & 31); }
+template <class P>
+__device__ __forceinline__ P* eq8_pin(P* p) {            // global memory
+  const unsigned long long a = (unsigned long long)p;
+  const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)a, threadIdx.x & 31);
+  const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(a >> 32), threadIdx.x & 31);
+  P* r = (P*)(((unsigned long long)hi << 32) | lo);
+  __builtin_assume(__isGlobal(r));
+  return r;
+}
+__device__ __forceinline__ double* eq8_pin_smem(const double* p) {   // dynamic shared memory
+  const int off = (int)(((unsigned)__cvta_generic_to_shared(p) - (unsigned)__cvta_generic_to_shared(eq8_dyn_smem)) >> 3);
+  return eq8_dyn_smem + eq8_pin(off);
+}
+
 struct Eq8Smem {
-  double* CQ;   // [k][44]: packed lower columns of Cq (36) | g (8)   -> Gpath
+  // CQ | BX | BY are one contiguous block per period -> Gpath
+  double* CQ;   // [k][44]: packed lower columns of Cq (36) | g (8)
+  double* BX;   // [8]      x_t (unmasked)
+  double* BY;   // [4]      y_t
   double* CV;   // [k][8]   cvec
   double* XE;   // [k][8]   x_t, BVS-masked per equation
   double* EP;   // [k][8]   eps_t
   double* AN;   // [k][8]   a_{t+1} (backward pass)
   double* YS;   // [4]      y_t of the equations
   __device__ __forceinline__ Eq8Smem(double* xs, int k)
-      : CQ(xs), CV(xs + 44 * k), XE(xs + 52 * k), EP(xs + 60 * k), AN(xs + 68 * k), YS(xs + 76 * k) {}
+      : CQ(xs), BX(xs + 44 * k), BY(xs + 44 * k + 8), CV(xs + 44 * k + 12), XE(xs + 52 * k + 12), EP(xs + 60 * k + 12),
+        AN(xs + 68 * k + 12), YS(xs + 76 * k + 12) {}
 };
 
 // all state normals of the sweep in one throughput-bound pass (site = t n + r, Box-Muller pairs): eps -> wpath
@@ -87,9 +112,12 @@ static __device__ __noinline__ void tvp_eq8_normals(const ChainRng& rng, int swe
 // Forward recursion.  om: the lane's measurement precisions omega_{i,t} at om[oms * t] (shared memory).
 template <int MB>
 static __device__ __noinline__ bool tvp_eq8_forward(const double* __restrict__ X, const double* __restrict__ Y,
-                                                    const int k, const int T, const int n, double* xs, const double* q,
+                                                    const int k_, const int T_, const int n_, double* xs, const double* q,
                                                     const double* a_init, const double* lam, const double* om_base,
-                                                    const int oms, double* Gpath, const double* wpath) {
+                                                    const int oms_, double* Gpath, const double* wpath) {
+  const int k = eq8_pin(k_), T = eq8_pin(T_), n = eq8_pin(n_), oms = eq8_pin(oms_);
+  xs = eq8_pin_smem(xs);
+  Gpath = eq8_pin(Gpath);
   const int lane = threadIdx.x & 31, gi = lane >> 3, c = lane & 7;
   const bool act = gi < k, own = act && c < MB;
   const int ie = act ? gi : 0;
@@ -99,7 +127,7 @@ static __device__ __noinline__ bool tvp_eq8_forward(const double* __restrict__ X
   const double* xe = S.XE + 8 * ie;
   const double* ep = S.EP + 8 * ie;
   const int offc = BVG_EQ8_OFF(c);
-  const int ST = 44 * k;                 // stream doubles per period
+  const int ST = 44 * k + 12;            // stream doubles per period
   const int rown = c * k + ie;           // the lane's own coefficient (regressor c, equation ie)
   BVG_TVP_TICK0
 
@@ -120,7 +148,7 @@ static __device__ __noinline__ bool tvp_eq8_forward(const double* __restrict__ X
   const double* Xp = X + c;
   const double* Yp = Y + ie;
   const double* Wp = wpath + rown;
-  asm volatile("" : "+l"(Xp), "+l"(Yp), "+l"(Wp));
+  Xp = eq8_pin(Xp); Yp = eq8_pin(Yp); Wp = eq8_pin(Wp);
   double* YS = S.YS;
   const bool ylane = act && c == 0;
   if (act) {
@@ -134,7 +162,8 @@ static __device__ __noinline__ bool tvp_eq8_forward(const double* __restrict__ X
     if (ylane) pfy = Yp[k];
   }
   Xp += 2 * MB; Wp += 2 * (size_t)n; Yp += 2 * k;       // period t + 2 relative to the loop counter
-  const double* om_p = om_base;
+  const double* om_p = eq8_pin_smem(om_base);
+  for (int e = lane; e < 12; e += 32) S.BX[e] = 0.0;
   __syncwarp();
 
   bool bad = false;
@@ -144,6 +173,7 @@ static __device__ __noinline__ bool tvp_eq8_forward(const double* __restrict__ X
     const double om = *om_p;
     om_p += oms;
     const double yv = YS[ie];
+    const double xown = S.XE[c];                    // x_{c,t} (equation 0's copy; unmasked whenever the block's copy is used)
     const double ct = (t < T - 1) ? 2.0 : 1.0;
 #pragma unroll
     for (int j = 0; j < MB; ++j) x[j] = xe[j];
@@ -205,6 +235,8 @@ static __device__ __noinline__ bool tvp_eq8_forward(const double* __restrict__ X
       cv[c] = qc * (u0 + u1);
       cq[36 + c] = g0 + g1;
     }
+    if (lane < 8) S.BX[lane] = xown;                // x_t, y_t travel with the block: the backward pass forms the residuals
+    if (ylane) S.BY[gi] = yv;
     if (act) { S.XE[lane] = pfx * lamc; S.EP[lane] = pfe; }
     if (ylane) YS[gi] = pfy;
     __syncwarp();
@@ -212,7 +244,7 @@ static __device__ __noinline__ bool tvp_eq8_forward(const double* __restrict__ X
     {
       double2* dst = reinterpret_cast<double2*>(Gpath + (size_t)t * ST);
       const double2* src = reinterpret_cast<const double2*>(S.CQ);
-      for (int u = lane; u < 22 * k; u += 32) dst[u] = src[u];
+      for (int u = lane; u < 22 * k + 6; u += 32) dst[u] = src[u];
     }
     if (t + 2 < T) {
       if (own) { pfx = *Xp; pfe = *Wp; }
@@ -225,112 +257,118 @@ static __device__ __noinline__ bool tvp_eq8_forward(const double* __restrict__ X
 }
 
 // Backward recursion:  a_{T-1} = g_{T-1};  a_t = g_t + (1 / q) (Cq_t a_{t+1}):  lane c gathers row c of the symmetric Cq_t
-// from the packed columns.  The stream comes back through a register ring BVG_EQ8_RING periods deep: a period is ~100
-// cycles of work, an L2 / HBM round trip ~1000.  ss_out[r] (shared, n) receives sum_t (a_t - a_{t-1})^2 with
-// a_{-1} = a_init, the input of the state-variance draw (bvartvpalg.cpp:471-477).
-// Optional fused outputs (models without BVS): coef_out != nullptr stores a_t straight into the retained-draw buffer
-// ([T][n], bvartvpalg.cpp:521-524); U != nullptr forms the residuals u_t = y_t - Z_t a_t (:332-336) from the x_t / y_t
-// that travel through the same ring -- the path then never goes through the scratch array apath (nullptr).
-template <int MB>
-static __device__ __noinline__ void tvp_eq8_backward(const double* __restrict__ X, const double* __restrict__ Y,
-                                                     const int k, const int T, const int n, double* xs, const double* q,
+// from the packed columns.  A period is ~100 cycles of work, an L2 / HBM round trip ~1000: the blocks come back through a
+// ring of D periods in shared memory filled by cp.async (LDGSTS, 16 bytes per lane and word) -- the loop stays rolled (an
+// unrolled register ring of the same depth is 30 KB of code per instantiation, and the instruction cache, not the data
+// path, became the limit).  `ring`: 16-byte aligned shared memory free during the pass (the SV work arrays), `ring_len`
+// doubles; D = 8 or 4 periods as it fits, otherwise the blocks are loaded synchronously.  ss_out[r] (shared, n) receives
+// sum_t (a_t - a_{t-1})^2 with a_{-1} = a_init, the input of the state-variance draw (bvartvpalg.cpp:471-477).
+// FUSED (models without BVS): a_t goes straight into the retained-draw buffer when coef_out != nullptr ([T][n],
+// bvartvpalg.cpp:521-524) and the residuals u_t = y_t - Z_t a_t (:332-336) are formed from the x_t / y_t that travel
+// with the block; the scratch copy of the path (apath) is not written then.
+__device__ __forceinline__ void eq8_cp16(double* dst_shared, const double* src_global) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global) : "memory");
+}
+__device__ __forceinline__ void eq8_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void eq8_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int MB, bool FUSED>
+static __device__ __noinline__ void tvp_eq8_backward(const int k_, const int T_, const int n_, double* xs, const double* q,
                                                      const double* a_init, const double* Gpath, double* apath,
-                                                     double* coef_out, double* U, double* ss_out) {
+                                                     double* coef_out, double* U, double* ss_out, double* ring,
+                                                     int ring_len) {
+  const int k = eq8_pin(k_), T = eq8_pin(T_), n = eq8_pin(n_);
+  xs = eq8_pin_smem(xs);
+  Gpath = eq8_pin(Gpath);
+  if (ring != nullptr) ring = eq8_pin_smem(ring);
+  if (FUSED) { U = eq8_pin_smem(U); if (coef_out != nullptr) coef_out = eq8_pin(coef_out); }
+  else apath = eq8_pin(apath);
   const int lane = threadIdx.x & 31, gi = lane >> 3, c = lane & 7;
   const bool act = gi < k, own = act && c < MB;
   const int ie = act ? gi : 0;
   const Eq8Smem S(xs, k);
-  const double* cq = S.CQ + 44 * ie;
   double* an = S.AN + 8 * ie;
   const int offc = BVG_EQ8_OFF(c);
-  const int ST = 44 * k;
+  const int ST = 44 * k + 12;
   const int rown = c * k + ie;
   BVG_TVP_TICK0
   int gidx[MB];
 #pragma unroll
-  for (int j = 0; j < MB; ++j) gidx[j] = (j <= c) ? (BVG_EQ8_OFF(j) + c - j) : (offc + j - c);
+  for (int j = 0; j < MB; ++j) gidx[j] = 44 * ie + ((j <= c) ? (BVG_EQ8_OFF(j) + c - j) : (offc + j - c));
+  const int gslot = 44 * ie + 36 + (own ? c : 0);   // g_c
+  const int xslot = 44 * k + (own ? c : 0), yslot = 44 * k + 8 + ie;
   const double invq = own ? 1.0 / q[rown] : 0.0;
   const double a0c = own ? a_init[rown] : 0.0;
   const bool ylane = act && c == 0;
-  const double* Xp = X + c;
-  const double* Yp = Y + ie;
-  asm volatile("" : "+l"(Gpath), "+l"(apath), "+l"(coef_out), "+l"(Xp), "+l"(Yp));   // stream pointers stay in registers (see the forward pass)
-  const int nw = 22 * k;                            // double2 words per period (<= 88: three per lane)
-  // word w of a period for this lane and slot v; out-of-range slots re-read the last word (unconditional loads keep the
-  // ring in registers; only the shared-memory stores are predicated)
-  int wv[3];
-#pragma unroll
-  for (int v = 0; v < 3; ++v) wv[v] = (lane + 32 * v < nw) ? lane + 32 * v : nw - 1;
+  const int nw = 22 * k + 6;                        // 16-byte words per period (<= 94: three per lane)
   double aprev = 0.0, ss = 0.0;
-  double2* stage = reinterpret_cast<double2*>(S.CQ);
-  // one period: the words of [Cq_t | g_t] are in w0..w2
-#define BVG_EQ8_BACK_STEP(t_, w0_, w1_, w2_, xr_, yr_)                                                        \
+  // one period from the block at blk_ (shared memory)
+#define BVG_EQ8_BACK_STEP(t_, blk_)                                                                   \
   do {                                                                                                \
-    stage[wv[0]] = (w0_);                                                                             \
-    if (lane + 32 < nw) stage[wv[1]] = (w1_);                                                         \
-    if (lane + 64 < nw) stage[wv[2]] = (w2_);                                                         \
-    __syncwarp();                               /* Cq_t, g_t and a_{t+1} visible */                   \
-    double a_ = cq[36 + (own ? c : 0)];                                                               \
+    double a_ = (blk_)[gslot];                                                                        \
     if ((t_) < T - 1) {                                                                               \
       double s0_ = 0.0, s1_ = 0.0;                                                                    \
       _Pragma("unroll") for (int j = 0; j < MB; ++j) {                                                \
-        if (j & 1) s1_ = fma(cq[gidx[j]], an[j], s1_); else s0_ = fma(cq[gidx[j]], an[j], s0_);       \
+        if (j & 1) s1_ = fma((blk_)[gidx[j]], an[j], s1_); else s0_ = fma((blk_)[gidx[j]], an[j], s0_); \
       }                                                                                               \
       a_ = fma(s0_ + s1_, invq, a_);                                                                  \
       const double dd_ = aprev - a_;                                                                  \
       ss = fma(dd_, dd_, ss);                                                                         \
     }                                                                                                 \
     aprev = a_;                                                                                       \
-    if (U != nullptr) {                         /* residual of the group's equation */               \
-      double pr_ = own ? (xr_) * a_ : 0.0;                                                            \
+    if (FUSED) {                                /* residual of the group's equation */               \
+      double pr_ = own ? (blk_)[xslot] * a_ : 0.0;                                                    \
+      const double yr_ = (blk_)[yslot];                                                               \
       pr_ += __shfl_xor_sync(0xffffffffu, pr_, 1);                                                    \
       pr_ += __shfl_xor_sync(0xffffffffu, pr_, 2);                                                    \
       pr_ += __shfl_xor_sync(0xffffffffu, pr_, 4);                                                    \
-      if (ylane) U[gi + k * (t_)] = (yr_) - pr_;                                                      \
+      if (ylane) U[gi + k * (t_)] = yr_ - pr_;                                                        \
     }                                                                                                 \
-    __syncwarp();                               /* all reads of a_{t+1} and Cq_t done */              \
+    __syncwarp();                               /* all reads of a_{t+1} and of the block done */      \
     if (own) {                                                                                        \
       an[c] = a_;                                                                                     \
-      if (apath != nullptr) apath[(size_t)(t_) * n + rown] = a_;                                      \
-      if (coef_out != nullptr) coef_out[(size_t)(t_) * n + rown] = a_;                                \
+      if (!FUSED) apath[(size_t)(t_) * n + rown] = a_;                                                \
+      else if (coef_out != nullptr) coef_out[(size_t)(t_) * n + rown] = a_;                           \
     }                                                                                                 \
   } while (0)
-  int t = T - 1;
-  for (int h = T % BVG_EQ8_RING; h > 0; --h, --t) {   // head: the periods that do not fill a ring, unpipelined
-    const double2* src = reinterpret_cast<const double2*>(Gpath + (size_t)t * ST);
-    const double2 w0 = src[wv[0]], w1 = src[wv[1]], w2 = src[wv[2]];
-    const double xr = (U != nullptr && own) ? Xp[(size_t)MB * t] : 0.0;
-    const double yr = (U != nullptr && ylane) ? Yp[(size_t)k * t] : 0.0;
-    BVG_EQ8_BACK_STEP(t, w0, w1, w2, xr, yr);
-  }
-  if (t >= 0) {                                     // (t + 1) is a multiple of the ring depth
-    double2 ring[BVG_EQ8_RING][3];
-    double xring[BVG_EQ8_RING], yring[BVG_EQ8_RING];
-    const bool ldx = U != nullptr && own, ldy = U != nullptr && ylane;
-#pragma unroll
-    for (int u = 0; u < BVG_EQ8_RING; ++u) {
-      const double2* src = reinterpret_cast<const double2*>(Gpath + (size_t)(t - u) * ST);
-#pragma unroll
-      for (int v = 0; v < 3; ++v) ring[u][v] = src[wv[v]];
-      xring[u] = ldx ? Xp[(size_t)MB * (t - u)] : 0.0;
-      yring[u] = ldy ? Yp[(size_t)k * (t - u)] : 0.0;
+  // the lane's words of period p into slot s_ (an empty group is committed for p < 0 so that the group count stays in step)
+#define BVG_EQ8_FETCH(p_, s_)                                                                         \
+  do {                                                                                                \
+    if ((p_) >= 0) {                                                                                  \
+      const double* src_ = Gpath + (size_t)(p_) * ST;                                                 \
+      double* dst_ = ring + (s_) * ST;                                                                \
+      for (int w_ = lane; w_ < nw; w_ += 32) eq8_cp16(dst_ + 2 * w_, src_ + 2 * w_);                  \
+    }                                                                                                 \
+    eq8_cp_commit();                                                                                  \
+  } while (0)
+#define BVG_EQ8_BACK_LOOP(D_)                                                                         \
+  do {                                                                                                \
+    for (int u_ = 0; u_ < (D_); ++u_) BVG_EQ8_FETCH(T - 1 - u_, u_);                                  \
+    int s_ = 0;                                                                                       \
+    for (int t = T - 1; t >= 0; --t) {                                                                \
+      eq8_cp_wait<(D_) - 1>();                  /* the oldest group in flight (period t) has landed */ \
+      __syncwarp();                             /* ... for every lane; a_{t+1} visible */             \
+      const double* blk = ring + s_ * ST;                                                             \
+      BVG_EQ8_BACK_STEP(t, blk);                                                                      \
+      BVG_EQ8_FETCH(t - (D_), s_);              /* the slot is free again (barrier inside the step) */ \
+      s_ = (s_ + 1 == (D_)) ? 0 : s_ + 1;                                                             \
+    }                                                                                                 \
+  } while (0)
+  if (ring != nullptr && ring_len >= 8 * ST) BVG_EQ8_BACK_LOOP(8);
+  else if (ring != nullptr && ring_len >= 4 * ST) BVG_EQ8_BACK_LOOP(4);
+  else {                                            // synchronous: stage the block in the (idle) carry area
+    double2* stage = reinterpret_cast<double2*>(S.CQ);
+    for (int t = T - 1; t >= 0; --t) {
+      const double2* src = reinterpret_cast<const double2*>(Gpath + (size_t)t * ST);
+      for (int w = lane; w < nw; w += 32) stage[w] = src[w];
+      __syncwarp();
+      const double* blk = S.CQ;
+      BVG_EQ8_BACK_STEP(t, blk);
     }
-    for (; t >= 0; t -= BVG_EQ8_RING) {
-#pragma unroll
-      for (int u = 0; u < BVG_EQ8_RING; ++u) {
-        const double2 w0 = ring[u][0], w1 = ring[u][1], w2 = ring[u][2];
-        const double xr = xring[u], yr = yring[u];
-        const int tn = t - u - BVG_EQ8_RING;        // refill the slot (the last ring re-reads period 0: harmless)
-        const int tc = tn > 0 ? tn : 0;
-        const double2* src = reinterpret_cast<const double2*>(Gpath + (size_t)tc * ST);
-#pragma unroll
-        for (int v = 0; v < 3; ++v) ring[u][v] = src[wv[v]];
-        if (ldx) xring[u] = Xp[(size_t)MB * tc];
-        if (ldy) yring[u] = Yp[(size_t)k * tc];
-        BVG_EQ8_BACK_STEP(t - u, w0, w1, w2, xr, yr);
-      }
-    }
   }
+#undef BVG_EQ8_BACK_LOOP
+#undef BVG_EQ8_FETCH
 #undef BVG_EQ8_BACK_STEP
   if (own) {
     const double dd = aprev - a0c;                  // a_0 - a_init
@@ -344,14 +382,16 @@ template <int MB>
 static __device__ __forceinline__ void tvp_eq8_mb(const BvarModel& m, bool sv, double* xs, const double* q,
                                                   const double* a_init, const double* lam, const double* sig,
                                                   const double* ew, double* Gpath, double* wpath, double* apath,
-                                                  double* coef_out, double* U, double* ss_out, int& fail) {
+                                                  double* coef_out, double* U, double* ss_out, double* ring, int ring_len,
+                                                  int& fail) {
   const int k = m.k, T = m.T, lane = threadIdx.x & 31;
   const int ie = ((lane >> 3) < k) ? (lane >> 3) : 0;
   const bool bad = tvp_eq8_forward<MB>(m.X, m.Y, k, T, m.n, xs, q, a_init, lam, sv ? ew + (size_t)T * ie : sig + ie + k * ie,
                                        sv ? 1 : 0, Gpath, wpath);
   if (__any_sync(0xffffffffu, bad)) fail = 1;
   __syncwarp();                                     // the last periods' stores are ordered before the loads of the backward pass
-  tvp_eq8_backward<MB>(m.X, m.Y, k, T, m.n, xs, q, a_init, Gpath, apath, coef_out, U, ss_out);
+  if (U != nullptr) tvp_eq8_backward<MB, true>(k, T, m.n, xs, q, a_init, Gpath, apath, coef_out, U, ss_out, ring, ring_len);
+  else tvp_eq8_backward<MB, false>(k, T, m.n, xs, q, a_init, Gpath, apath, coef_out, U, ss_out, ring, ring_len);
 }
 
 // state normals, then dispatch on the regressors per equation
@@ -359,11 +399,11 @@ static __device__ __forceinline__ void tvp_state_draw_eq8(const BvarModel& m, co
                                                           double* xs, const double* q, const double* a_init,
                                                           const double* lam, const double* sig, const double* ew,
                                                           double* Gpath, double* wpath, double* apath, double* coef_out,
-                                                          double* U, double* ss_out, int& fail) {
+                                                          double* U, double* ss_out, double* ring, int ring_len, int& fail) {
   BVG_TVP_TICK0
   tvp_eq8_normals(rng, sweep, m.n * m.T, wpath);
   BVG_TVP_TICK(7);
-#define BVG_EQ8_ARGS m, sv, xs, q, a_init, lam, sig, ew, Gpath, wpath, apath, coef_out, U, ss_out, fail
+#define BVG_EQ8_ARGS m, sv, xs, q, a_init, lam, sig, ew, Gpath, wpath, apath, coef_out, U, ss_out, ring, ring_len, fail
   switch (m.M) {
     case 1: tvp_eq8_mb<1>(BVG_EQ8_ARGS); break;
     case 2: tvp_eq8_mb<2>(BVG_EQ8_ARGS); break;

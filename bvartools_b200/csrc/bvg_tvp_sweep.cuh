@@ -283,8 +283,19 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
       // forms the residuals itself; the scratch copy of the path is not needed then
       double* oc = (fused && keep) ? out.coef + ((size_t)chain_local * (size_t)out.iters + (size_t)pos) * (size_t)n * (size_t)T : nullptr;
       if constexpr (Grp::kWarp32)
+      {
+        // backward-stream ring: the SV work arrays ew | svw are idle during the backward pass (ew is consumed by the forward
+        // pass and refreshed at the end of the SV block), 16-byte aligned inside them
+        double* ring = nullptr;
+        int ring_len = 0;
+        if (sv) {                                       // (the BVS step still reads ew: only svw is free then)
+          double* r0 = bvs ? svw : ew;
+          ring = r0 + (((unsigned long long)r0 >> 3) & 1);
+          ring_len = (bvs ? 1 : 2) * k * T - (int)(ring - r0);
+        }
         tvp_state_draw_eq8(m, rng, sweep, sv, xs, q, a_init, bvs ? lam : nullptr, sig, ew, Mpath, wpath,
-                           fused ? nullptr : apath, oc, fused ? U : nullptr, tmp2, fail);
+                           fused ? nullptr : apath, oc, fused ? U : nullptr, tmp2, ring, ring_len, fail);
+      }
     } else if (tiled) {
       if constexpr (Grp::kWarp32)
         tvp_state_draw_tiled(m, rng, sweep, sv, Dt, Cq, wv, cvec, xl, anext, tmp, q, a_init, bvs ? lam : nullptr, sig,
@@ -652,7 +663,7 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
     if (eq8 && m.vi_off == nullptr) {
       // diagonal prior precision: the n x n system of :480-482 is diagonal, L = sqrt(d), a_init = (b / L + eps) / L
       for (int r = tid; r < n; r += G) {
-        const double a0 = fused ? xs[68 * k + 8 * (r % k) + r / k] : apath[r];          // a_0 (Eq8Smem::AN after the backward pass)
+        const double a0 = fused ? xs[68 * k + 12 + 8 * (r % k) + r / k] : apath[r];          // a_0 (Eq8Smem::AN after the backward pass)
         const double v0 = m.vdiag0[r], d = v0 + q[r];
         if (!(d > 0.0)) fail = 1;
         const double rs = bvg_rsqrt(d);
@@ -667,7 +678,7 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
         if (c == r) v += m.vdiag0[r] + q[r];
         Dr[c] = v;
       }
-      double b = m.vdiag0[r] * m.mu[r] + q[r] * (fused ? xs[68 * k + 8 * (r % k) + r / k] : apath[r]);
+      double b = m.vdiag0[r] * m.mu[r] + q[r] * (fused ? xs[68 * k + 12 + 8 * (r % k) + r / k] : apath[r]);
       if (m.vmu_off != nullptr) b += m.vmu_off[r];
       wv[r] = b;
     }
