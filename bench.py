@@ -2,13 +2,17 @@
 """bench.py -- retained Gibbs draws/sec (chains x iterations, whole box) of the B200 sampler, next to the
 reference-faithful CPU restatement timed on the same box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2a|c2b|c3|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload all|c2a|c2b|c3|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 A step = one pass of the hot path over one batch: `chains` independent chains x (iterations + burnin) sweeps of the
-named model (default: BASELINE.json configs[1], e1 VAR(2) normal-Wishart, 4096 chains, 5000 / 1000).  Chains are
-sharded over ranks by global chain id with no data-path collective (weak scaling: `chains` PER GPU); the only
-collective is the NCCL all-reduce of on-device posterior moments at the end of each step.
+named model.  The headline (top-level keys of the JSON line) is BASELINE.json configs[1] part A: e1 VAR(2) normal-Wishart,
+4096 chains, 5000 / 1000.  The default run (--workload all) also measures the other BASELINE configs at their full
+iteration counts -- c2-B (p = 0:4 model grid + model-comparison table), c3 (SSVS, K = 6), c4 (TVP + SV, T = 200),
+c5 (K = 20, n = 1620) -- and reports them under `workloads`, each with its own roofline / e2e / cpu_baseline, plus the
+strong-scaling point of the north star (4096 chains IN TOTAL over the N GPUs) under `strong`.
+Chains are sharded over ranks by global chain id with no data-path collective (weak scaling: `chains` PER GPU); the
+only collective is the NCCL all-reduce of on-device posterior moments / log-likelihood sums at the end of each step.
 """
 from __future__ import annotations
 
@@ -26,35 +30,14 @@ import numpy as np
 
 ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, str(ROOT / "tests"))
 
 METRIC = "retained_gibbs_draws_per_sec"
 UNIT = "draws/s"
+CHAINS = {"c2a": 4096, "c2b": 1024, "c3": 1024, "c4": 1024, "c5": 256}     # per GPU (c2b: per model and GPU)
+SEED = 20240113
 
 
-def build_workload(name, iterations=None, burnin=None):
-    import helpers
-    if name == "c2a":
-        it, bi = iterations or 5000, 1000 if burnin is None else burnin
-        obj = helpers.model_c1(iterations=it, burnin=bi)
-        label = "c2-A: e1 VAR(2)+const, independent normal-Wishart (v_i=0, df=1, scale=1e-4), %d iter / %d burn-in" % (it, bi)
-    elif name == "c3":
-        it, bi = iterations or 5000, 1000 if burnin is None else burnin
-        obj = helpers.model_c3(iterations=it, burnin=bi)
-        label = "c3: synthetic VAR(4) K=6 T=191 SSVS (semiautomatic 0.01/10), %d iter / %d burn-in" % (it, bi)
-    elif name == "c4":
-        it, bi = iterations or 500, 500 if burnin is None else burnin
-        obj = helpers.model_sv(K=3, p=2, nobs=202, iterations=it, burnin=bi, tvp=True)
-        label = "c4: synthetic TVP-VAR(2) K=3 T=200 + KSC-1998 SV, %d iter / %d burn-in" % (it, bi)
-    elif name == "c5":
-        it, bi = iterations or 200, 50 if burnin is None else burnin
-        obj = helpers.model_c5(iterations=it, burnin=bi)
-        label = "c5: synthetic large BVAR K=20 p=4 T=200 (n=1620), Minnesota prior, %d iter / %d burn-in" % (it, bi)
-    else:
-        raise SystemExit(f"unknown workload {name}")
-    return obj, label
-
-
+# ------------------------------------------------------------------------------------------------ flop / byte models
 def flops_per_sweep(obj, resid_moment):
     """Algorithmic FP64 flops of one sweep of one chain as EXECUTED ('Roofline accounting').
     Constant-parameter path: precision build + rhs + Cholesky + two triangular solves + residual cross product
@@ -63,9 +46,10 @@ def flops_per_sweep(obj, resid_moment):
     M = obj["data"]["Z"].shape[1]
     n = k * M
     if obj["model"].get("tvp"):
-        # per period: Cholesky n^3/3, triangular inverse n^3/3, M'M n^3/3, block build + mat-vecs ~ 6 n^2;
-        # plus residuals, J pdf evaluations per (series, t) and the tridiagonal solves of the SV step
-        return T * (n ** 3 + 6 * n * n) + 2 * k * M * T + T * k * 7 * 30 + 12 * T * k
+        # equation-decoupled state draw (diagonal Sigma_t^-1): per period and equation Cholesky M^3/3, two column
+        # solves M^2 per lane-column (M^3 in total), build + carry ~ 4 M^2; plus residuals, J pdf evaluations per
+        # (series, t) and the tridiagonal solves of the SV step
+        return T * k * (4.0 * M ** 3 / 3.0 + 4 * M * M) + 2 * k * M * T + T * k * 7 * 30 + 12 * T * k
     base = n * (n + 1) / 2 + 2 * k * k * M + n + n ** 3 / 3 + 2 * n * n + 5 * k ** 3
     if resid_moment:
         return base + 2 * k * M * M + 2 * k * k * M
@@ -90,7 +74,7 @@ def survey_flops_per_sweep(obj):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks + throttle reasons during the timed region (B200_PROFILING.md recipe), NVML in-process every ~2 ms."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -100,7 +84,6 @@ class ClockSampler(threading.Thread):
         self.device, self.rows, self.stop_flag = device, [], threading.Event()
 
     def _run_nvml(self):
-        """NVML in-process: a sample every ~2 ms, so that even a 50 ms timed region is covered by tens of samples."""
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(int(self.device))
@@ -157,203 +140,566 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def _numpy_oracle_chain(args):
-    obj, seed = args
-    from oracle import samplers
-    from oracle.variates import VariateSource
-    fn = samplers.bvartvpalg if obj["model"].get("tvp") else samplers.bvaralg
-    fn(obj, VariateSource(rng=np.random.default_rng(seed)), literal=True)
+# ------------------------------------------------------------------------------------------------------ CPU baselines
+def _numpy_worker_init():
+    """Worker start-up outside the timed region: imports, and one BLAS thread per chain (like one R process per core)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1)
+    except Exception:
+        pass
+    from oracle import samplers  # noqa: F401
     return 0
 
 
-def cpu_reference_run(obj, label, steps, warmup, sample_sweeps, as_line, n_gpus=1):
-    """The reference's own algorithm (dense restatement: oracle/bvar_dense_ref.c, or the NumPy oracle for SV / TVP /
-    BVS) on all host cores: one chain per core like parallel::mclapply(mc.cores = ncores)."""
+def _numpy_oracle_chain(args):
+    obj, seed, literal = args
+    from oracle import samplers
+    from oracle.variates import VariateSource
+    fn = samplers.bvartvpalg if obj["model"].get("tvp") else samplers.bvaralg
+    fn(obj, VariateSource(rng=np.random.default_rng(seed)), literal=literal)
+    return 0
+
+
+def _c_port_ok(obj):
+    pc = obj["priors"].get("coefficients", {})
+    return not (obj["model"].get("tvp") or obj["model"].get("sv") or "bvs" in pc or "df" not in obj["priors"]["sigma"]) \
+        and obj["data"]["SUR"].shape[1] <= 600
+
+
+def cpu_timed(obj, variant, sweeps, steps=1, warmup=0, max_procs=0):
+    """One CPU arm on all host cores, one chain per core like parallel::mclapply(mc.cores = ncores)
+    (R/draw_posterior.bvarmodel.R:57-58).  Variants:
+      port_dense        oracle/bvar_dense_ref.c: the reference's dense algorithm (kron(I_T, Sigma^-1), GEMM, LU solve,
+                        chol) with plain loops standing in for BLAS (Wishart prior +- SSVS)
+      port_structured   the same C port using the Kronecker / cross-moment identities (structure-exploiting CPU version)
+      numpy_dense       oracle/samplers.py literal=True: the same dense matrices through NumPy / SciPy (OpenBLAS, LAPACK),
+                        one BLAS thread per chain
+      numpy_structured  oracle/samplers.py literal=False: banded / Kronecker forms (band-detecting for SV / TVP)
+    max_procs: use at most that many cores (the dense (nT)^2 / (kT)^2 arms of c4 / c5 are memory-bound: all cores at once
+    would take a minute for one sweep each).  Returns draws/s (all sweeps counted) and the description of the sample."""
     cores = os.cpu_count() or 1
-    is_c = not (obj["model"].get("tvp") or obj["model"].get("sv") or "bvs" in obj["priors"].get("coefficients", {}))
-    if obj["data"]["SUR"].shape[1] > 600:
-        is_c = False            # c5: the dense products go through LAPACK/OpenBLAS (NumPy oracle), as Armadillo would
+    if max_procs:
+        cores = min(cores, max_procs)
     times = []
-    if is_c:
+    if variant.startswith("port_"):
         from oracle.dense_ref import bvar_dense
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            bvar_dense(obj, n_chains=cores, seed=1 + i, n_threads=cores, dense_gemm=True, iterations=sample_sweeps,
-                       burnin=0)
-            dt = time.perf_counter() - t0
+            bvar_dense(obj, n_chains=cores, seed=1 + i, n_threads=cores, dense_gemm=(variant == "port_dense"),
+                       iterations=sweeps, burnin=0)
             if i >= warmup:
-                times.append(dt)
-        kind_note = "oracle/bvar_dense_ref.c (dense kron(I_T,Sigma^-1) + GEMM + LU solve + chol, plain loops as reference BLAS)"
+                times.append(time.perf_counter() - t0)
+        note = "oracle/bvar_dense_ref.c " + ("(dense kron(I_T,Sigma^-1) + GEMM + LU solve + chol, plain loops as reference BLAS)"
+                                             if variant == "port_dense" else "(Kronecker / cross-moment identities, n x n Cholesky)")
     else:
         import copy
         from concurrent.futures import ProcessPoolExecutor
         small = copy.deepcopy(obj)
-        small["model"]["iterations"], small["model"]["burnin"] = sample_sweeps, 0
-        with ProcessPoolExecutor(max_workers=cores) as ex:
+        small["model"]["iterations"], small["model"]["burnin"] = sweeps, 0
+        lit = variant == "numpy_dense"
+        with ProcessPoolExecutor(max_workers=cores, initializer=_numpy_worker_init) as ex:
+            list(ex.map(abs, range(4 * cores)))            # spin the workers up before the clock starts
             for i in range(warmup + steps):
                 t0 = time.perf_counter()
-                list(ex.map(_numpy_oracle_chain, [(small, 100 * i + c) for c in range(cores)]))
-                dt = time.perf_counter() - t0
+                list(ex.map(_numpy_oracle_chain, [(small, 100 * i + c, lit) for c in range(cores)]))
                 if i >= warmup:
-                    times.append(dt)
-        kind_note = "oracle/samplers.py literal dense path (NumPy/SciPy LAPACK), one chain per process"
+                    times.append(time.perf_counter() - t0)
+        note = "oracle/samplers.py " + ("literal dense path (NumPy / SciPy: OpenBLAS + LAPACK, one BLAS thread per chain)"
+                                        if lit else "structured path (Kronecker / banded forms, NumPy / SciPy)") + \
+               ", one chain per process"
     t = float(np.mean(times))
-    value = cores * sample_sweeps / t
-    base = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{cores} chains x {sample_sweeps} sweeps per step; {kind_note}"}
-    if not as_line:
-        return base
-    return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
-            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "e1 data set (shipped fixture) / synthetic", "impl": "reference", "config": {"workload": label},
-            "cpu_baseline": base,
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+    return {"value": cores * sweeps / t, "unit": UNIT, "cores": cores, "kind": "port", "variant": variant,
+            "ms_per_step": t * 1e3, "sample": f"{cores} chains x {sweeps} sweeps per step; {note}"}
 
 
-def run_grid(args, rank, world, local_rank):
-    """Workload c2-B: the p = 0:4 model grid (vignettes/model-comparison.Rmd:44-60), `chains` chains per model and GPU,
-    followed by the model-comparison table (summary.bvarlist) from the draws resident in HBM."""
-    import torch
-    import torch.distributed as dist
-    import helpers
-    from bvartools_b200 import ChainSampler, _abi, pinned_empty
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        from bvartools_b200.distributed import bind_to_gpu_numa
-        bind_to_gpu_numa(local_rank)
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    it = args.iterations or 5000
-    bi = 1000 if args.burnin < 0 else args.burnin
-    models = helpers.model_grid_c2b(iterations=it, burnin=bi)
-    chains = args.chains or 1024
-    stream = torch.cuda.current_stream()
-    seed = 20240113
-    samplers = [ChainSampler(m, n_chains=chains, seed=seed + 1000 * i, chain_offset=rank * chains, device=local_rank)
-                for i, m in enumerate(models)]
-    rows = [s.spec.out_rows() for s in samplers]
+CPU_SWEEPS = {      # bounded samples: a few seconds of CPU work per variant
+    "c2a": {"port_dense": 1500, "port_structured": 20000, "numpy_dense": 1500, "numpy_structured": 3000},
+    "c2b": {"port_dense": 1500, "port_structured": 20000},
+    "c3": {"port_dense": 8, "port_structured": 300, "numpy_dense": 3, "numpy_structured": 40},
+    "c4": {"numpy_dense": 1, "numpy_structured": 4},
+    "c5": {"numpy_dense": 1, "numpy_structured": 1},
+}
 
-    def fence():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    def table():
-        # one log-likelihood sum and draw count per model; a single all-reduce for the whole grid
-        from bvartools_b200.posterior import information_criteria
-        acc = torch.zeros(2 * len(samplers), dtype=torch.float64)
-        for i, s in enumerate(samplers):
-            tot, nd = s.loglik_total(stream.cuda_stream)
-            acc[2 * i], acc[2 * i + 1] = tot, float(nd)
-        if world > 1:
-            acc = acc.to(dev)
-            dist.all_reduce(acc)
-            acc = acc.cpu()
-        out = []
-        for i, m in enumerate(models):
-            T_, M_ = m["data"]["Z"].shape
-            out.append(information_criteria(float(acc[2 * i] / acc[2 * i + 1]), M_, T_))
-        return out
+def cpu_baselines(name, obj, args):
+    """The `cpu_baseline` object of one workload: the reference-faithful dense arm first (C port where it covers the
+    model, NumPy / OpenBLAS otherwise), the other variants under `variants` (dense with OpenBLAS,
+    band-detecting, structure-exploiting) so that algorithmic and hardware gains can be separated."""
+    table = dict(CPU_SWEEPS[name])
+    if args.cpu_sweeps:
+        table = {k: args.cpu_sweeps for k in table}
+    primary = "port_dense" if ("port_dense" in table and _c_port_ok(obj)) else "numpy_dense"
+    mp = 4 if name in ("c4", "c5") else 0
+    out = cpu_timed(obj, primary, table[primary], max_procs=mp)
+    variants = {}
+    if not args.cpu_primary_only:
+        for v, sw in table.items():
+            if v == primary or (v.startswith("port_") and not _c_port_ok(obj)):
+                continue
+            try:
+                variants[v] = cpu_timed(obj, v, sw, max_procs=mp)
+            except Exception as exc:
+                variants[v] = {"error": str(exc)}
+    out["variants"] = variants
+    return out
 
-    def step():
-        for s in samplers:           # back to back on one stream: each launch already fills the SMs evenly (running the
-            s.reset()                # models on separate streams measured no faster: 35.8 vs 36.3 ms per step)
-            s.run(stream.cuda_stream)
-        return table()
 
-    for _ in range(max(args.warmup, 1)):
+# ------------------------------------------------------------------------------------------------------- GPU workloads
+class Ctx:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            from bvartools_b200.distributed import bind_to_gpu_numa
+            bind_to_gpu_numa(self.local_rank)      # pinned output buffers on the GPU's own NUMA node
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.current_stream()
+        from bvartools_b200._lib import lib
+        self.L = lib()
+        self.peaks = {}
+        try:
+            self.peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        self.hbm_peak = self.peaks.get("hbm_gbs") or 6650.0
+        self.hbm_src = "MEASURED_PEAKS.json hbm_gbs" if self.peaks.get("hbm_gbs") else "B200_PROFILING.md fallback"
+        self.traffic = {}
+        for f in sorted((ROOT / "profiles").glob("r0*_traffic.json")):
+            try:
+                self.traffic.update(json.loads(f.read_text()))
+            except Exception:
+                pass
+        self._fp64 = None
+
+    def fence(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def fp64_peaks(self):
+        if self._fp64 is None:
+            from bvartools_b200._lib import check
+            a, b = C.c_double(0.0), C.c_double(0.0)
+            check(self.L.bvg_fp64_peak(C.byref(a), None))
+            check(self.L.bvg_dmma_peak(C.byref(b), None))
+            self._fp64 = (a.value, b.value)
+        return self._fp64
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def timed_steps(ctx, step, steps, warmup, clocks=None):
+    """W untimed + K timed steps bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks."""
+    torch = ctx.torch
+    for _ in range(max(warmup, 1)):
         step()
-    fence()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
+    ctx.fence()
+    if clocks is not None and ctx.rank == 0:
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fence()
-    e0.record(stream)
-    for _ in range(args.steps):
-        tab = step()
-    e1.record(stream)
-    fence()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
-    if rank == 0:
+    ctx.fence()
+    e0.record(ctx.stream)
+    for _ in range(steps):
+        step()
+    e1.record(ctx.stream)
+    ctx.fence()
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    if clocks is not None and ctx.rank == 0:
         clocks.stop_flag.set()
         clocks.join(timeout=3)
+    return ms / steps
+
+
+def roofline_of(ctx, name, obj, sampler_info, chains, it, bi, rows, ms_per_step):
+    """Roofline record of the dominant (sweep) kernel: algorithmic bytes or flops per step / sweep-kernel time measured
+    with CUDA events on the launching stream (bvg_sampler_last_kernel_ms)."""
+    kernel_name, last_sweep_ms, n_launches = sampler_info
+    sweep_s = last_sweep_ms * 1e-3
+    peak64, dmma = ctx.fp64_peaks()
+    T, k = obj["data"]["Y"].shape
+    M = obj["data"]["Z"].shape[1]
+    n = k * M
+    out_bytes = 8.0 * chains * it * sum(rows.values())
+    moment = not (obj["model"].get("tvp") or obj["model"].get("sv")) and T > M
+    fl = kron_flops_per_sweep(obj) if kernel_name.startswith("kron") else flops_per_sweep(obj, moment)
+    if kernel_name.startswith("large"):
+        fl = survey_flops_per_sweep(obj)            # direct residuals, full n^3/3 Cholesky: 1.4246 Gflop for c5
+    tflops = fl * chains * (it + bi) / sweep_s / 1e12
+    tr = ctx.traffic.get(f"{name}:{chains}:{it}:{bi}:{kernel_name}") or ctx.traffic.get(f"{name}:{kernel_name}")
+    traffic = traffic_note = None
+    if tr and "chains" in tr:
+        # captures are per launch of a stated number of sweeps: scaled to the launches of this run
+        per_sweep_chain = tr["dram_bytes_per_launch"] / (tr["chains"] * tr["sweeps_per_launch"])
+        traffic = per_sweep_chain * chains * (it + bi) / max(n_launches, 1)
+        traffic_note = tr["note"]
+    elif tr:
+        traffic, traffic_note = tr["dram_bytes_per_launch"], tr.get("note")
+    fp64 = {"achieved_tflops": tflops, "peak_tflops": peak64, "frac": tflops / peak64 if peak64 > 0 else None,
+            "peak_source": "FP64 FMA probe kernel run live by bench.py (bvg_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+            "fp64_dmma_peak_tflops": dmma, "flops_per_sweep_executed": fl, "flops_per_sweep_survey": survey_flops_per_sweep(obj)}
+    common = {"traffic": traffic, "traffic_note": traffic_note, "kernel": kernel_name,
+              "sweep_kernel_ms_per_step": last_sweep_ms, "sweep_launches_per_step": n_launches,
+              "sweep_share_of_step": last_sweep_ms / ms_per_step, "hbm_write_GBps": out_bytes / sweep_s / 1e9,
+              "hbm_peak_GBps": ctx.hbm_peak}
+    if kernel_name.startswith("kron"):
+        # flat-prior Kronecker kernel: ~550 flop and 240 B of output per chain-sweep; of the two stated rooflines the
+        # applicable one is HBM (SURVEY.md 8d: algorithmic bytes = retained draws, 8 (n + k^2) per chain and iteration).
+        # Neither binds: the kernel is instruction-issue bound (variate generation), see `issue`.
+        gbps = out_bytes / sweep_s / 1e9
+        r = {"bound": "hbm", "achieved": gbps, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": gbps / ctx.hbm_peak,
+             "algorithmic_bytes_per_launch": out_bytes / max(n_launches, 1), "peak_source": ctx.hbm_src, "fp64": fp64}
+        if tr and tr.get("warp_inst_per_chain_sweep"):
+            return dict(r, **common), tr["warp_inst_per_chain_sweep"]
+        return dict(r, **common), None
+    if kernel_name.startswith("tvp"):
+        # TVP sweep, HBM view.  Algorithmic bytes per chain-sweep of the algorithm that runs (equation-decoupled state
+        # draw): the carry stream written forward / read backward, 2 * 8 * T * k (tri(M) + M), + the retained draws.
+        # `round1_definition`: the same time against the bytes of the un-decoupled block recursion the round-1 kernel
+        # streamed (2 * 8 * T * tri(n) + draws), kept for continuity with BENCH_r01 / VERDICT.
+        diag = bool(obj["model"].get("sv")) and "psi" not in obj["priors"]
+        per = 2.0 * 8.0 * T * (k * (M * (M + 1) / 2 + M) if diag else n * (n + 1) / 2)
+        stream_bytes = per * chains * (it + bi)
+        gbps = (stream_bytes + out_bytes) / sweep_s / 1e9
+        old = (2.0 * 8.0 * T * (n * (n + 1) / 2) * chains * (it + bi) + out_bytes) / sweep_s / 1e9
+        r = {"bound": "hbm", "achieved": gbps, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": gbps / ctx.hbm_peak,
+             "algorithmic_bytes_per_launch": (stream_bytes + out_bytes) / max(n_launches, 1),
+             "round1_definition": {"achieved": old, "frac": old / ctx.hbm_peak,
+                                   "what": "2*8*T*tri(n) + draws per chain-sweep (block recursion on n x n blocks)"},
+             "peak_source": ctx.hbm_src, "fp64": fp64}
+        return dict(r, **common), None
+    tensor = kernel_name.startswith("large") or kernel_name.startswith("bvar_g0")
+    tpeak = max(peak64, dmma) if tensor else peak64
+    r = {"bound": "tensor" if tensor else "fp64", "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s",
+         "frac": tflops / tpeak if tpeak > 0 else None,
+         "peak_source": ("FP64 DMMA (mma.sync m8n8k4) probe kernel run live by bench.py (bvg_dmma_peak)"
+                         if tensor and dmma >= peak64 else fp64["peak_source"]),
+         "fp64_dmma_peak_tflops": dmma, "flops_per_sweep_executed": fl, "flops_per_sweep_survey": survey_flops_per_sweep(obj)}
+    return dict(r, **common), None
+
+
+def run_sampler_workload(ctx, args, name, steps, warmup, chains=None, headline=False, with_cpu=True, with_e2e=True,
+                         iterations=None, burnin=None):
+    """One single-model workload (c2a, c3, c4, c5): device-timed steps, roofline, e2e through the public API, CPU arm."""
+    torch, dist = ctx.torch, ctx.dist
+    from bvartools_b200 import ChainSampler, _abi, pinned_empty
+    from bvartools_b200._lib import check
+    from bvartools_b200.workloads import baseline_workload
+    obj, label = baseline_workload(name, iterations, burnin)
+    chains = chains or CHAINS[name]
+    it, bi = obj["model"]["iterations"], obj["model"]["burnin"]
+    sampler = ChainSampler(obj, n_chains=chains, seed=SEED, chain_offset=ctx.rank * chains, device=ctx.local_rank,
+                           threads_per_chain=args.threads_per_chain if headline else 0)
+    rows = sampler.spec.out_rows()
+    dout = sampler.device_out()
+    n_out = rows["coef"]
+    sums = torch.zeros(n_out, dtype=torch.float64, device=ctx.dev)
+    sumsq = torch.zeros(n_out, dtype=torch.float64, device=ctx.dev)
+
+    def step():
+        sampler.reset()
+        sampler.run(ctx.stream.cuda_stream)
+        check(ctx.L.bvg_moments(C.cast(dout.coef, C.c_void_p), chains, it, n_out, C.c_void_p(sums.data_ptr()),
+                                C.c_void_p(sumsq.data_ptr()), C.c_void_p(ctx.stream.cuda_stream)))
+        if ctx.world > 1:
+            dist.all_reduce(sums)
+            dist.all_reduce(sumsq)
+
+    clocks = ClockSampler(ctx.local_rank)
+    ms_per_step = timed_steps(ctx, step, steps, warmup, clocks)
+    info = (sampler.kernel_name, sampler.last_kernel_ms, max(int(sampler.launch_count), 1))
+    launches_per_step = int(sampler.launch_count) + 1          # + the moments kernel
+    total_draws = ctx.world * chains * it
+    value = total_draws / (ms_per_step * 1e-3)
+    post_mean = (sums / (ctx.world * chains * it)).cpu().numpy()
+    out_bytes = 8.0 * chains * it * sum(rows.values())
+    extras = {}
+    if headline and not args.no_loglik:
+        extras = headline_extras(ctx, sampler, obj, chains, it, rows, args)
+
+    e2e = None
+    if with_e2e:
+        # pinned host memory per rank is bounded (8 ranks share one host): when the retained draws of the workload exceed
+        # the budget the end-to-end run uses fewer chains and says so (`chains_per_gpu`)
+        budget = (32 << 30) if ctx.world == 1 else (6 << 30)
+        ce = chains
+        while ce > 148 and 8.0 * ce * it * sum(rows.values()) > budget:
+            ce //= 2
+        sampler.close()
+        spec_e = _abi.spec_from_model(obj, n_chains=ce, seed=SEED, chain_offset=ctx.rank * ce, device=ctx.local_rank)
+        host = _abi.OutBuffers(spec_e, alloc=pinned_empty)
+        d2h = sum(a.nbytes for a in host.arrays.values()) + host.status.nbytes
+        times, h2d, checksum = [], 0, 0.0
+        n_warm = 1 if not headline else 2
+        chains_full, chains = chains, ce
+        for i in range(n_warm + steps):
+            ctx.fence()
+            t0 = time.perf_counter()
+            s = ChainSampler(obj, n_chains=chains, seed=SEED, chain_offset=ctx.rank * chains, device=ctx.local_rank,
+                             threads_per_chain=args.threads_per_chain if headline else 0)   # validates + uploads the inputs
+            s.run_to_host(host, ctx.stream.cuda_stream)                         # sweeps, D2H overlapped
+            checksum = float(host.arrays["coef"][0, -1, 0])                     # host read of the result
+            ctx.fence()
+            dt = time.perf_counter() - t0
+            h2d = sum(v.nbytes for v in s.spec.keep.values())
+            s.close()
+            if i >= n_warm:
+                times.append(dt)
+        te = ctx.max_over_ranks(float(np.mean(times)))
+        e2e = {"value": ctx.world * chains * it / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * ctx.world,
+               "d2h_bytes_per_step": int(d2h) * ctx.world, "ms_per_step": te * 1e3,
+               "d2h_GBps_per_gpu": d2h / te / 1e9, "chains_per_gpu": chains,
+               "api": "ChainSampler(model).run_to_host(pinned out) = bvg_sampler_create + bvg_sampler_run_to_host",
+               "checksum": checksum}
+        chains = chains_full
+        del host
+    else:
+        sampler.close()
+    if ctx.rank != 0:
+        return None
+    roofline, winst = roofline_of(ctx, name, obj, info, chains, it, bi, rows, ms_per_step)
+    clk = clocks.summary()
+    if winst and clk.get("sm_mhz"):
+        # issue-slot roofline: executed warp instructions per chain-sweep (ncu capture of this launch shape, profiles/)
+        # x chain-sweeps / sweep-kernel time against 4 schedulers x SMs x the SM clock seen during the run
+        sms = torch.cuda.get_device_properties(ctx.dev).multi_processor_count
+        rate = winst * chains * (it + bi) / (info[1] * 1e-3)
+        peak = 4.0 * sms * clk["sm_mhz"] * 1e6
+        roofline["issue"] = {"bound": "issue", "achieved": rate / 1e12, "peak": peak / 1e12, "unit": "T warp-inst/s",
+                             "frac": rate / peak, "warp_inst_per_chain_sweep": winst,
+                             "what": "executed warp instructions (ncu smsp__inst_executed.sum of this launch shape) / "
+                                     "(4 issue slots x SMs x SM clock under load)"}
+    cpu = cpu_baselines(name, obj, args) if (with_cpu and ctx.world == 1 and not args.no_cpu) else None
+    par = "1 GPU" if ctx.world == 1 else (f"chains sharded over {ctx.world} GPUs by global chain id, no data-path "
+                                          "collective; NCCL all-reduce of posterior moments per step")
+    rec = {"value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
+           "config": {"workload": label, "chains_per_gpu": chains, "chains_total": chains * ctx.world, "parallelism": par,
+                      "l2": f"retained draws {out_bytes / 1e9:.2f} GB per step per GPU >> 126 MB L2 (no flush needed)",
+                      "threads_per_chain": sampler.spec.c.threads_per_chain or "auto"},
+           "clocks": clk, "e2e": e2e, "gpu_launches": launches_per_step * steps, "roofline": roofline,
+           "cpu_baseline": cpu, "posterior_mean_first3": [float(v) for v in post_mean[:3]]}
+    rec.update(extras)
+    return rec
+
+
+def headline_extras(ctx, sampler, obj, chains, it, rows, args):
+    """Next-row kernels on the draws resident in HBM: model-comparison log-likelihood and
+    summary.bvar statistics, timed end to end per call."""
+    out = {}
+    try:
+        ll_ms = []
+        for i in range(4):
+            ctx.fence()
+            t0 = time.perf_counter()
+            ll_tot, n_dr = sampler.loglik_total(ctx.stream.cuda_stream)
+            if i > 0:
+                ll_ms.append((time.perf_counter() - t0) * 1e3)
+        rd_bytes = 8.0 * chains * it * (rows["coef"] + rows["sigma"])
+        ms = float(np.median(ll_ms))
+        mc = {"what": "bvg_sampler_loglik_total: log-likelihood of summary.bvarlist over all resident draws "
+                      "(R/summary.bvarlist.R:160-186), incl. the result D2H; bound: HBM (draws read once)", "ms": ms,
+              "draws_per_s": n_dr / (ms * 1e-3), "read_GBps": rd_bytes / (ms * 1e-3) / 1e9, "LL": float(ll_tot / n_dr)}
+        mc["hbm_frac"] = mc["read_GBps"] / ctx.hbm_peak
+        if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu:
+            from oracle import blocks as ob          # the reference's per-draw loop on a bounded sample (checker as baseline)
+            rng = np.random.default_rng(0)
+            Yh, Zh = obj["data"]["Y"], obj["data"]["Z"]
+            nd = 2000
+            ols = np.linalg.lstsq(Zh, Yh, rcond=None)[0].T
+            pars = np.stack([(ols + 0.01 * rng.standard_normal(ols.shape)).reshape(-1, order="F") for _ in range(nd)])
+            sg = np.stack([np.cov((Yh - Zh @ ols.T).T).reshape(-1, order="F") for _ in range(nd)])
+            t0 = time.perf_counter()
+            ob.summary_bvarlist_row(Yh, Zh, pars, sg)
+            mc["cpu_baseline"] = {"draws_per_s": nd / (time.perf_counter() - t0), "cores": 1, "kind": "port",
+                                  "sample": f"{nd} draws, oracle/blocks.py summary_bvarlist_row (per-draw loop)"}
+        out["model_comparison"] = mc
+    except Exception as exc:                     # never let the auxiliary measurement break the bench line
+        out["model_comparison"] = {"error": str(exc)}
+    try:
+        sm_ms, ts_ms = [], []
+        for i in range(3):
+            ctx.fence()
+            t0 = time.perf_counter()
+            sm = sampler.summary("coef", ts_se=False)
+            if i > 0:
+                sm_ms.append((time.perf_counter() - t0) * 1e3)
+        for i in range(3):
+            ctx.fence()
+            t0 = time.perf_counter()
+            ts = sampler.time_series_se("coef")
+            if i > 0:
+                ts_ms.append((time.perf_counter() - t0) * 1e3)
+        nbytes = 8.0 * chains * it * rows["coef"]
+        ms = float(np.median(sm_ms))
+        out["posterior_summary"] = {
+            "what": "bvg_sampler_summary(coef): moments + 8-pass radix select + neighbour pass over all resident draws "
+                    "(R/summary.bvar.R:121-140)", "ms": ms, "values": chains * it * rows["coef"], "passes": 11,
+            "stream_GBps": 11 * nbytes / (ms * 1e-3) / 1e9, "median_first3": [float(v) for v in sm["quantiles"][1][:3]],
+            "time_series_se": {"what": "bvg_sampler_tsse(coef): coda spectrum0.ar per chain and row, pooled over chains",
+                               "ms": float(np.median(ts_ms)), "first3": [float(v) for v in ts[:3]],
+                               "naive_se_first3": [float(v) for v in (sm["sd"] / np.sqrt(chains * it))[:3]]}}
+    except Exception as exc:
+        out["posterior_summary"] = {"error": str(exc)}
+    return out
+
+
+def run_summary_e2e(ctx, args, steps):
+    """Second end-to-end record of the headline workload: host inputs -> sweeps -> posterior summary ON THE DEVICE (moments,
+    exact quantiles, time-series SE, log-likelihood) -> only the tables cross PCIe (what summary() of the fitted object needs)."""
+    from bvartools_b200 import ChainSampler
+    from bvartools_b200.workloads import baseline_workload
+    obj, _ = baseline_workload("c2a")
+    chains, it = CHAINS["c2a"], obj["model"]["iterations"]
+    times, d2h, chk = [], 0, 0.0
+    for i in range(1 + steps):
+        ctx.fence()
+        t0 = time.perf_counter()
+        s = ChainSampler(obj, n_chains=chains, seed=SEED, chain_offset=ctx.rank * chains, device=ctx.local_rank)
+        s.run(ctx.stream.cuda_stream)
+        sc = s.summary("coef", ts_se=True)
+        ss = s.summary("sigma", ts_se=True)
+        ll, _n = s.loglik_total(ctx.stream.cuda_stream)
+        chk = float(sc["mean"][0])
+        ctx.fence()
+        dt = time.perf_counter() - t0
+        d2h = sum(np.asarray(v).nbytes for d in (sc, ss) for v in d.values()) + 8
+        h2d = sum(v.nbytes for v in s.spec.keep.values())
+        s.close()
+        if i >= 1:
+            times.append(dt)
+    te = ctx.max_over_ranks(float(np.mean(times)))
+    return {"value": ctx.world * chains * it / te, "unit": UNIT, "ms_per_step": te * 1e3,
+            "h2d_bytes_per_step": int(h2d) * ctx.world, "d2h_bytes_per_step": int(d2h) * ctx.world,
+            "api": "ChainSampler(model).run() + summary(coef) + summary(sigma) + loglik_total: draws stay in HBM, tables to host",
+            "checksum": chk}
+
+
+def run_grid(ctx, args, steps, warmup, with_cpu=True, with_e2e=True):
+    """Workload c2-B: the p = 0:4 model grid (vignettes/model-comparison.Rmd:44-60), `chains` chains per model and GPU,
+    followed by the model-comparison table (summary.bvarlist) from the draws resident in HBM.  The log-likelihood sums
+    stay on the device and are all-reduced once per step (one host read of 2 x models doubles)."""
+    torch, dist = ctx.torch, ctx.dist
+    from bvartools_b200 import ChainSampler, _abi, pinned_empty
+    from bvartools_b200.posterior import information_criteria
+    from bvartools_b200.workloads import model_grid_c2b
+    it = 5000
+    bi = 1000
+    models = model_grid_c2b(iterations=it, burnin=bi)
+    chains = CHAINS["c2b"]
+    stream = ctx.stream
+    samplers = [ChainSampler(m, n_chains=chains, seed=SEED + 1000 * i, chain_offset=ctx.rank * chains, device=ctx.local_rank)
+                for i, m in enumerate(models)]
+    rows = [s.spec.out_rows() for s in samplers]
+    acc = torch.zeros(2 * len(samplers), dtype=torch.float64, device=ctx.dev)
+    cnt = torch.tensor([float(chains * it)] * len(samplers), dtype=torch.float64, device=ctx.dev)
+    tab_holder = {}
+
+    def step():
+        for s in samplers:           # back to back on one stream: each launch already fills the SMs evenly
+            s.reset()
+            s.run(stream.cuda_stream)
+        for i, s in enumerate(samplers):
+            s.loglik_total_device(acc.data_ptr() + 16 * i, stream.cuda_stream)
+        acc[1::2] = cnt
+        if ctx.world > 1:
+            dist.all_reduce(acc)
+        tab_holder["acc"] = acc.cpu()              # the one host read of the step
+
+    clocks = ClockSampler(ctx.local_rank)
+    ms_per_step = timed_steps(ctx, step, steps, warmup, clocks)
+    a = tab_holder["acc"]
+    tab = []
+    for i, m in enumerate(models):
+        T_, M_ = m["data"]["Z"].shape
+        tab.append(information_criteria(float(a[2 * i] / a[2 * i + 1]), M_, T_))
     sweep_ms = sum(s.last_kernel_ms for s in samplers)
     launches = sum(int(s.launch_count) for s in samplers) + 2 * len(samplers)       # + total-loglik + reduce kernels
     kernels = [s.kernel_name for s in samplers]
-    total_draws = world * chains * it * len(models)
+    total_draws = ctx.world * chains * it * len(models)
     out_bytes = sum(8.0 * chains * it * sum(r.values()) for r in rows)
-    # ---- end to end: host inputs -> sweeps -> all draws to pinned host memory -> table
     e2e = None
-    if not args.no_e2e:
+    if with_e2e:
         hosts = [_abi.OutBuffers(s.spec, alloc=pinned_empty) for s in samplers]
-        d2h = sum(sum(a.nbytes for a in h.arrays.values()) + h.status.nbytes for h in hosts)
+        d2h = sum(sum(a_.nbytes for a_ in h.arrays.values()) + h.status.nbytes for h in hosts)
         for s in samplers:
             s.close()
-        times, h2d = [], 0
-        for i in range(1 + args.steps):
-            fence()
+        times, h2d, tab_e = [], 0, []
+        for i in range(1 + steps):
+            ctx.fence()
             t0 = time.perf_counter()
             tab_e = []
             for j, m in enumerate(models):
-                s = ChainSampler(m, n_chains=chains, seed=seed + 1000 * j, chain_offset=rank * chains, device=local_rank)
+                s = ChainSampler(m, n_chains=chains, seed=SEED + 1000 * j, chain_offset=ctx.rank * chains, device=ctx.local_rank)
                 s.run_to_host(hosts[j], stream.cuda_stream)
                 tot, nd = s.loglik_total(stream.cuda_stream)
                 tab_e.append(tot / nd)
                 h2d += sum(v.nbytes for v in s.spec.keep.values()) if i == 0 else 0
                 s.close()
-            fence()
+            ctx.fence()
             if i >= 1:
                 times.append(time.perf_counter() - t0)
-        te = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": total_draws / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
-               "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": float(te.item()) * 1e3,
+        te = ctx.max_over_ranks(float(np.mean(times)))
+        e2e = {"value": total_draws / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * ctx.world,
+               "d2h_bytes_per_step": int(d2h) * ctx.world, "ms_per_step": te * 1e3,
                "api": "per model: ChainSampler(model).run_to_host(pinned out) + loglik_total", "checksum": float(tab_e[2])}
+        del hosts
     else:
         for s in samplers:
             s.close()
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-    peaks = {}
-    try:
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-    except Exception:
-        pass
-    hbm_peak = peaks.get("hbm_gbs") or 6530.6
+    if ctx.rank != 0:
+        return None
     gbps = out_bytes / (sweep_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak,
-                "traffic": None, "kernel": ",".join(sorted(set(kernels))),
-                "algorithmic_bytes_per_step": out_bytes, "sweep_kernel_ms_per_step": sweep_ms,
-                "sweep_share_of_step": sweep_ms / ms_per_step,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "B200_PROFILING.md fallback"}
-    cpu = None
-    if not args.no_cpu:
-        cpu = cpu_reference_run(models[2], "c2-B, p = 2 member of the grid", 1, 0, args.cpu_sweeps or 1500, False)
-    par = "1 GPU" if world == 1 else f"every model's chains sharded over {world} GPUs by global chain id; NCCL all-reduce of one log-likelihood sum per model"
-    line = {"metric": METRIC, "value": total_draws / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "e1 data set (shipped fixture)",
+    roofline = {"bound": "hbm", "achieved": gbps, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": gbps / ctx.hbm_peak,
+                "traffic": None, "kernel": ",".join(sorted(set(kernels))), "algorithmic_bytes_per_step": out_bytes,
+                "sweep_kernel_ms_per_step": sweep_ms, "sweep_share_of_step": sweep_ms / ms_per_step,
+                "peak_source": ctx.hbm_src}
+    cpu = cpu_baselines("c2b", models[2], args) if (with_cpu and ctx.world == 1 and not args.no_cpu) else None
+    par = "1 GPU" if ctx.world == 1 else (f"every model's chains sharded over {ctx.world} GPUs by global chain id; one NCCL "
+                                          "all-reduce of the log-likelihood sums of the whole grid per step")
+    return {"value": total_draws / (ms_per_step * 1e-3), "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps,
+            "warmup": warmup,
             "config": {"workload": "c2-B: e1 VAR(p)+const grid p = 0:4 on the common sample (T = 71), v_i = 0, df = k, "
                                    "scale = 1e-4, %d iter / %d burn-in, + summary.bvarlist table" % (it, bi),
-                       "chains_per_model_per_gpu": chains, "chains_total": chains * world * len(models),
-                       "parallelism": par,
+                       "chains_per_model_per_gpu": chains, "chains_total": chains * ctx.world * len(models), "parallelism": par,
                        "l2": f"retained draws {out_bytes / 1e9:.2f} GB per step per GPU >> 126 MB L2 (no flush needed)"},
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches * args.steps, "roofline": roofline,
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches * steps, "roofline": roofline,
             "cpu_baseline": cpu,
-            "model_comparison": [{"p": i, **{k: float(v) for k, v in r.items()}} for i, r in enumerate(tab)]}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+            "model_comparison": [{"p": i, **{k_: float(v) for k_, v in r.items()}} for i, r in enumerate(tab)]}
+
+
+def reference_line(args):
+    """--impl reference: the reference's own algorithm for the headline config on the host cores (the dense C port:
+    oracle/bvar_dense_ref.c -- the reference itself cannot be built here), same warm-up and steps."""
+    from bvartools_b200.workloads import baseline_workload
+    name = "c2a" if args.workload in ("all", "c2b") else args.workload
+    obj, label = baseline_workload(name, args.iterations or None, None if args.burnin < 0 else args.burnin)
+    table = CPU_SWEEPS[name]
+    variant = "port_dense" if ("port_dense" in table and _c_port_ok(obj)) else "numpy_dense"
+    sweeps = args.cpu_sweeps or table[variant]
+    r = cpu_timed(obj, variant, sweeps, steps=args.steps, warmup=args.warmup)
+    cores = r["cores"]
+    return {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "e1 data set (shipped fixture) / synthetic", "impl": "reference",
+            "config": {"workload": label, "sample": f"{cores} chains x {sweeps} sweeps per step (bounded sample of the workload)"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "variant", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
 
 
 def main():
@@ -362,305 +708,72 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2a")
-    ap.add_argument("--chains", type=int, default=0, help="chains PER GPU (default: 4096 for c2a, 1024 otherwise)")
+    ap.add_argument("--workload", default="all", help="all (headline c2a + the other BASELINE configs) or one of c2a c2b c3 c4 c5")
+    ap.add_argument("--chains", type=int, default=0, help="chains PER GPU of a single-workload run")
     ap.add_argument("--iterations", type=int, default=0)
     ap.add_argument("--burnin", type=int, default=-1)
     ap.add_argument("--threads-per-chain", type=int, default=0)
-    ap.add_argument("--cpu-sweeps", type=int, default=0, help="sweeps per chain of the CPU sample")
+    ap.add_argument("--cpu-sweeps", type=int, default=0, help="sweeps per chain of the CPU samples")
+    ap.add_argument("--cpu-primary-only", action="store_true", help="skip the extra CPU variants")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-loglik", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.workload == "c2b" and args.impl != "reference":
-        return run_grid(args, rank, world, local_rank)
-    obj, label = build_workload("c2a" if args.workload == "c2b" else args.workload, args.iterations or None,
-                                None if args.burnin < 0 else args.burnin)
-    cpu_sweeps = args.cpu_sweeps or {"c2a": 1500, "c3": 8, "c4": 2, "c5": 1}.get(args.workload, 50)
-
     if args.impl == "reference":
         if rank == 0:
-            line = cpu_reference_run(obj, label, args.steps, min(args.warmup, 1), cpu_sweeps, True, n_gpus=args.gpus)
-            print(json.dumps(line), flush=True)
+            print(json.dumps(reference_line(args)), flush=True)
         return 0
 
-    import torch
-    import torch.distributed as dist
-    from bvartools_b200 import ChainSampler, _abi, pinned_empty
-    from bvartools_b200._lib import check, lib
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        from bvartools_b200.distributed import bind_to_gpu_numa
-        bind_to_gpu_numa(local_rank)          # pinned output buffers on the GPU's own NUMA node
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    L = lib()
-    chains = args.chains or {"c2a": 4096, "c5": 256}.get(args.workload, 1024)
-    it, bi = obj["model"]["iterations"], obj["model"]["burnin"]
-    seed = 20240113
-    stream = torch.cuda.current_stream()
-
-    sampler = ChainSampler(obj, n_chains=chains, seed=seed, chain_offset=rank * chains, device=local_rank,
-                           threads_per_chain=args.threads_per_chain)
-    rows = sampler.spec.out_rows()
-    dout = sampler.device_out()
-    n_out = rows["coef"]
-    sums = torch.zeros(n_out, dtype=torch.float64, device=dev)
-    sumsq = torch.zeros(n_out, dtype=torch.float64, device=dev)
-
-    def step():
-        sampler.reset()
-        sampler.run(stream.cuda_stream)
-        check(L.bvg_moments(C.cast(dout.coef, C.c_void_p), chains, it, n_out, C.c_void_p(sums.data_ptr()),
-                            C.c_void_p(sumsq.data_ptr()), C.c_void_p(stream.cuda_stream)))
-        if world > 1:
-            dist.all_reduce(sums)
-            dist.all_reduce(sumsq)
-
-    def fence():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 1)):
-        step()
-    fence()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sweep_ms = []
-    fence()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    fence()
-    elapsed_ms = e0.elapsed_time(e1)
-    # duration of the sweep kernels of the last step, from the library's CUDA events on the launching stream
-    last_sweep_ms = sampler.last_kernel_ms
-    kernel_name = sampler.kernel_name
-    launches_per_step = int(sampler.launch_count) + 1          # + the moments kernel
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    if rank == 0:
-        clocks.stop_flag.set()
-        clocks.join(timeout=3)
-    ms_per_step = elapsed_ms / args.steps
-    total_draws = world * chains * it
-    value = total_draws / (ms_per_step * 1e-3)
-    post_mean = (sums / (world * chains * it)).cpu().numpy()
-    tpc_used = sampler.spec.c.threads_per_chain
-
-    # ---- next-row kernel: summary.bvarlist log-likelihood over the draws resident in HBM
-    model_cmp = None
-    if not args.no_loglik:
-        try:
-            ll_ms = []
-            for i in range(4):
-                fence()
-                t0 = time.perf_counter()
-                ll_tot, n_dr = sampler.loglik_total(stream.cuda_stream)
-                dt = time.perf_counter() - t0
-                if i > 0:
-                    ll_ms.append(dt * 1e3)
-            rd_bytes = 8.0 * chains * it * (rows["coef"] + rows["sigma"])
-            ms = float(np.median(ll_ms))
-            model_cmp = {"what": "bvg_sampler_loglik_total: log-likelihood of summary.bvarlist over all resident draws "
-                                 "(R/summary.bvarlist.R:160-186), incl. the result D2H; bound: HBM (draws read once)", "ms": ms,
-                         "draws_per_s": n_dr / (ms * 1e-3), "read_GBps": rd_bytes / (ms * 1e-3) / 1e9,
-                         "LL": float(ll_tot / n_dr)}
-        except Exception as exc:       # never let the auxiliary measurement break the bench line
-            model_cmp = {"error": str(exc)}
-
-    # ---- next-row kernel: summary.bvar statistics (mean, SD, exact 2.5 / 50 / 97.5 % quantiles) of
-    #      the coefficient draws resident in HBM
-    post_summary = None
-    if not args.no_loglik:
-        try:
-            sm_ms = []
-            for i in range(3):
-                fence()
-                t0 = time.perf_counter()
-                sm = sampler.summary("coef", ts_se=False)
-                dt = time.perf_counter() - t0
-                if i > 0:
-                    sm_ms.append(dt * 1e3)
-            ms = float(np.median(sm_ms))
-            ts_ms = []
-            for i in range(3):
-                fence()
-                t0 = time.perf_counter()
-                ts = sampler.time_series_se("coef")
-                dt = time.perf_counter() - t0
-                if i > 0:
-                    ts_ms.append(dt * 1e3)
-            nbytes = 8.0 * chains * it * rows["coef"]
-            post_summary = {"what": "bvg_sampler_summary(coef): moments + 8-pass radix select + neighbour pass over all "
-                                    "resident draws (R/summary.bvar.R:121-140)", "ms": ms, "values": chains * it * rows["coef"],
-                            "passes": 11, "stream_GBps": 11 * nbytes / (ms * 1e-3) / 1e9,
-                            "median_first3": [float(v) for v in sm["quantiles"][1][:3]],
-                            "time_series_se": {"what": "bvg_sampler_tsse(coef): coda spectrum0.ar per chain and row "
-                                                       "(means, autocovariances to lag floor(10 log10 iter), "
-                                                       "Levinson-Durbin + AIC), pooled over chains",
-                                               "ms": float(np.median(ts_ms)),
-                                               "first3": [float(v) for v in ts[:3]],
-                                               "naive_se_first3": [float(v) for v in
-                                                                   (sm["sd"] / np.sqrt(chains * it))[:3]]}}
-        except Exception as exc:
-            post_summary = {"error": str(exc)}
-
-    # ---- end to end through the public API: host inputs -> H2D -> sweeps -> D2H into pinned host memory
-    e2e = None
-    if not args.no_e2e:
-        host = _abi.OutBuffers(sampler.spec, alloc=pinned_empty)
-        d2h = sum(a.nbytes for a in host.arrays.values()) + host.status.nbytes
-        sampler.close()
-        e2e_times, h2d, checksum = [], 0, 0.0
-        n_warm = 2
-        for i in range(n_warm + args.steps):
-            fence()
-            t0 = time.perf_counter()
-            s = ChainSampler(obj, n_chains=chains, seed=seed, chain_offset=rank * chains, device=local_rank,
-                             threads_per_chain=args.threads_per_chain)          # validates + uploads the inputs
-            s.run_to_host(host, stream.cuda_stream)                             # sweeps, D2H overlapped
-            checksum = float(host.arrays["coef"][0, -1, 0])                     # host read of the result
-            fence()
-            dt = time.perf_counter() - t0
-            h2d = sum(v.nbytes for v in s.spec.keep.values())
-            s.close()
-            if i >= n_warm:
-                e2e_times.append(dt)
-        te = torch.tensor([float(np.mean(e2e_times))], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": total_draws / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
-               "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": float(te.item()) * 1e3,
-               "api": "ChainSampler(model).run_to_host(pinned out) = bvg_sampler_create + bvg_sampler_run_to_host",
-               "checksum": checksum}
+    ctx = Ctx(args)
+    single = args.workload != "all"
+    head_name = args.workload if single and args.workload != "c2b" else "c2a"
+    it = args.iterations or None
+    bi = None if args.burnin < 0 else args.burnin
+    if single and args.workload == "c2b":
+        head = run_grid(ctx, args, args.steps, args.warmup, with_e2e=not args.no_e2e)
     else:
-        sampler.close()
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
-    # ---- roofline of the dominant kernel (the sweep kernel): executed algorithmic FP64 flops / launch time
-    moment = not (obj["model"].get("tvp") or obj["model"].get("sv")) and \
-        obj["data"]["Y"].shape[0] > obj["data"]["Z"].shape[1]
-    fl_sweep = kron_flops_per_sweep(obj) if kernel_name.startswith("kron") else flops_per_sweep(obj, moment)
-    if kernel_name.startswith("large"):
-        fl_sweep = survey_flops_per_sweep(obj)          # direct residuals, full n^3/3 Cholesky: 1.4246 Gflop for c5
-    peak = C.c_double(0.0)
-    check(L.bvg_fp64_peak(C.byref(peak), None))
-    dmma_peak = C.c_double(0.0)
-    check(L.bvg_dmma_peak(C.byref(dmma_peak), None))
-    peak_source = ("FP64 FMA probe kernel run live by bench.py (bvg_fp64_peak); MEASURED_PEAKS.json has no FP64 entry")
-    if kernel_name.startswith("large") and dmma_peak.value > peak.value:
-        peak = dmma_peak
-        peak_source = "FP64 DMMA (mma.sync m8n8k4) probe kernel run live by bench.py (bvg_dmma_peak)"
-    sweep_kernel_s = last_sweep_ms * 1e-3
-    achieved = fl_sweep * chains * (it + bi) / sweep_kernel_s / 1e12
-    peaks = {}
-    try:
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-    except Exception:
-        pass
-    out_bytes = 8.0 * chains * it * sum(rows.values())
-    hbm_peak = peaks.get("hbm_gbs") or 6530.6
-    # ncu-measured DRAM bytes per launch of this kernel in this launch shape (profiles/r01_traffic.json, written from
-    # `ncu --set full` captures of this very command); null when there is no capture of this shape
-    traffic, traffic_note = None, None
-    try:
-        tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
-        key = f"{args.workload}:{chains}:{it}:{bi}:{kernel_name}"
-        if key in tj:
-            traffic, traffic_note = tj[key]["dram_bytes_per_launch"], tj[key]["note"]
-    except Exception:
-        pass
-    n_sweep_launches = max(int(launches_per_step) - 1, 1)
-    fp64 = {"achieved_tflops": achieved, "peak_tflops": peak.value,
-            "frac": achieved / peak.value if peak.value > 0 else None, "peak_source": peak_source,
-            "fp64_dmma_peak_tflops": dmma_peak.value, "flops_per_sweep_executed": fl_sweep,
-            "flops_per_sweep_survey": survey_flops_per_sweep(obj)}
-    if kernel_name.startswith("kron"):
-        # flat-prior Kronecker kernel: ~550 flop and 240 B of output per chain-sweep; the applicable roofline of the
-        # two is HBM (algorithmic bytes = retained draws only, 8 (n + k^2) per chain and iteration)
-        gbps = out_bytes / sweep_kernel_s / 1e9
-        roofline = {"bound": "hbm", "achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak,
-                    "traffic": traffic, "traffic_note": traffic_note, "kernel": kernel_name,
-                    "algorithmic_bytes_per_launch": out_bytes / n_sweep_launches,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "B200_PROFILING.md fallback",
-                    "fp64": fp64}
-    elif kernel_name.startswith("tvp"):
-        # TVP sweep: the block-bidiagonal factor does not fit on chip and is streamed through HBM (written forward, read
-        # backward); SURVEY.md 8d algorithmic bytes = 2 * 8 * T * tri(n) per chain-sweep + the retained draws
-        T_, k_ = obj["data"]["Y"].shape
-        n_ = k_ * obj["data"]["Z"].shape[1]
-        stream_bytes = 2.0 * 8.0 * T_ * (n_ * (n_ + 1) / 2) * chains * (it + bi)
-        gbps = (stream_bytes + out_bytes) / sweep_kernel_s / 1e9
-        roofline = {"bound": "hbm", "achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak,
-                    "traffic": traffic, "traffic_note": traffic_note, "kernel": kernel_name,
-                    "algorithmic_bytes_per_launch": (stream_bytes + out_bytes) / n_sweep_launches,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "B200_PROFILING.md fallback",
-                    "fp64": fp64}
-    else:
-        tensor = kernel_name.startswith("large") or kernel_name.startswith("bvar_g0")
-        tpeak = max(peak.value, dmma_peak.value) if tensor else peak.value
-        roofline = {"bound": "tensor" if tensor else "fp64", "achieved": achieved, "peak": tpeak, "unit": "TFLOP/s",
-                    "frac": achieved / tpeak if tpeak > 0 else None, "traffic": traffic, "traffic_note": traffic_note,
-                    "kernel": kernel_name,
-                    "peak_source": ("FP64 DMMA (mma.sync m8n8k4) probe kernel run live by bench.py (bvg_dmma_peak)"
-                                    if tensor and dmma_peak.value >= peak.value else peak_source),
-                    "fp64_dmma_peak_tflops": dmma_peak.value, "flops_per_sweep_executed": fl_sweep,
-                    "flops_per_sweep_survey": survey_flops_per_sweep(obj)}
-    roofline.update({"sweep_kernel_ms_per_step": last_sweep_ms, "sweep_launches_per_step": n_sweep_launches,
-                     "sweep_share_of_step": last_sweep_ms / ms_per_step,
-                     "hbm_write_GBps": out_bytes / sweep_kernel_s / 1e9, "hbm_peak_GBps": hbm_peak})
-    if model_cmp and "read_GBps" in model_cmp:
-        model_cmp["hbm_frac"] = model_cmp["read_GBps"] / hbm_peak
-        if not args.no_cpu and not obj["model"].get("tvp") and not obj["model"].get("sv"):
-            # the reference's per-draw loop (oracle restatement of R/summary.bvarlist.R:160-180) on a bounded sample
-            from oracle import blocks as ob
-            rng = np.random.default_rng(0)
-            Yh, Zh = obj["data"]["Y"], obj["data"]["Z"]
-            kk_ = Yh.shape[1]
-            nd = 2000
-            ols = np.linalg.lstsq(Zh, Yh, rcond=None)[0].T
-            pars = np.stack([(ols + 0.01 * rng.standard_normal(ols.shape)).reshape(-1, order="F") for _ in range(nd)])
-            sg = np.stack([np.cov((Yh - Zh @ ols.T).T).reshape(-1, order="F") for _ in range(nd)])
-            t0 = time.perf_counter()
-            ob.summary_bvarlist_row(Yh, Zh, pars, sg)
-            dtc = time.perf_counter() - t0
-            model_cmp["cpu_baseline"] = {"draws_per_s": nd / dtc, "cores": 1, "kind": "port",
-                                         "sample": f"{nd} draws, oracle/blocks.py summary_bvarlist_row (per-draw loop)"}
-    cpu = None
-    if not args.no_cpu:
-        cpu = cpu_reference_run(obj, label, 1, 0, cpu_sweeps, False)
-    par = "1 GPU" if world == 1 else (f"chains sharded over {world} GPUs by global chain id, no data-path "
-                                      "collective; NCCL all-reduce of posterior moments per step")
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64",
-            "data": "e1 data set (shipped fixture)" if args.workload == "c2a" else "synthetic",
-            "config": {"workload": label, "chains_per_gpu": chains, "chains_total": chains * world,
-                       "parallelism": par,
-                       "l2": f"retained draws {out_bytes / 1e9:.2f} GB per step per GPU >> 126 MB L2 (no flush needed)",
-                       "threads_per_chain": tpc_used or "auto"},
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "model_comparison": model_cmp, "posterior_summary": post_summary,
-            "posterior_mean_first3": [float(v) for v in post_mean[:3]]}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        head = run_sampler_workload(ctx, args, head_name, args.steps, args.warmup, chains=args.chains or None,
+                                    headline=True, with_e2e=not args.no_e2e, iterations=it, burnin=bi)
+    workloads, strong, summary_e2e = {}, None, None
+    if not single:
+        sub_steps, sub_warm = min(args.steps, 2), 1
+        workloads["c2b"] = run_grid(ctx, args, sub_steps, sub_warm, with_e2e=not args.no_e2e)
+        for nm in ("c3", "c4", "c5"):
+            workloads[nm] = run_sampler_workload(ctx, args, nm, sub_steps, sub_warm, with_e2e=not args.no_e2e)
+        # strong scaling point of the north star: 4096 chains IN TOTAL over the N GPUs (512 per GPU at N = 8)
+        if ctx.world > 1:
+            per = max(CHAINS["c2a"] // ctx.world, 1)
+            strong = run_sampler_workload(ctx, args, "c2a", min(args.steps, 5), 2, chains=per, with_cpu=False,
+                                          with_e2e=not args.no_e2e)
+            if strong is not None:
+                strong = {k_: strong[k_] for k_ in ("value", "unit", "ms_per_step", "config", "e2e", "roofline")}
+                strong["scaling"] = "strong"
+        if not args.no_e2e:
+            try:
+                summary_e2e = run_summary_e2e(ctx, args, min(args.steps, 3))
+            except Exception as exc:
+                summary_e2e = {"error": str(exc)}
+    if ctx.rank == 0:
+        if strong is None and not single:
+            strong = {"scaling": "strong", "value": head["value"], "ms_per_step": head["ms_per_step"],
+                      "note": "N = 1: the strong-scaling point (4096 chains in total) is the headline run"}
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64",
+                "data": "e1 data set (shipped fixture)" if head_name == "c2a" else "synthetic"}
+        for k_ in ("config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "model_comparison",
+                   "posterior_summary", "posterior_mean_first3"):
+            if k_ in head:
+                line[k_] = head[k_]
+        if not single:
+            line["workloads"] = workloads
+            line["strong"] = strong
+            line["e2e_summary_mode"] = summary_e2e
+            line["gpu_launches"] = head["gpu_launches"] + sum((w or {}).get("gpu_launches", 0) for w in workloads.values())
+        print(json.dumps(line), flush=True)
+    ctx.close()
     return 0
 
 

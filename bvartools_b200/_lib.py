@@ -62,6 +62,7 @@ def lib():
     L.bvg_loglik_draws.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp]
     L.bvg_sampler_loglik.argtypes = [vp, dp, vp]
     L.bvg_sampler_loglik_total.argtypes = [vp, dp, vp]
+    L.bvg_sampler_loglik_total_device.argtypes = [vp, vp, vp]
     L.bvg_loglik_total_host.argtypes = [dp, dp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, dp, dp, dp]
     L.bvg_loglik_draws_host.argtypes = [dp, dp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, dp, dp, dp]
     L.bvg_loglik_normal.argtypes = [dp, dp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, dp]
@@ -107,5 +108,5 @@ EXPORTED = ["bvg_version", "bvg_last_error", "bvg_device_count", "bvg_host_alloc
             "bvg_bvaralg", "bvg_bvartvpalg", "bvg_sampler_create", "bvg_sampler_reset", "bvg_sampler_run",
             "bvg_sampler_run_to_host", "bvg_sampler_fetch", "bvg_sampler_device_out", "bvg_sampler_sync",
             "bvg_sampler_last_kernel_ms", "bvg_sampler_launch_count", "bvg_sampler_kernel_name", "bvg_sampler_destroy",
-            "bvg_set_interrupt_poll", "bvg_moments", "bvg_loglik_draws", "bvg_loglik_draws_host", "bvg_sampler_loglik", "bvg_sampler_loglik_total", "bvg_loglik_total_host", "bvg_loglik_normal", "bvg_summary_draws", "bvg_sampler_summary", "bvg_tsse_draws", "bvg_sampler_tsse", "bvg_irf_draws", "bvg_irf_draws_a0", "bvg_sampler_irf", "bvg_fevd_draws", "bvg_fevd_draws_a0", "bvg_sampler_fevd", "bvg_forecast_draws", "bvg_forecast_draws_a0", "bvg_sampler_forecast", "bvg_fp64_peak", "bvg_dmma_peak", "bvg_post_normal", "bvg_post_normal_sur",
+            "bvg_set_interrupt_poll", "bvg_moments", "bvg_loglik_draws", "bvg_loglik_draws_host", "bvg_sampler_loglik", "bvg_sampler_loglik_total", "bvg_sampler_loglik_total_device", "bvg_loglik_total_host", "bvg_loglik_normal", "bvg_summary_draws", "bvg_sampler_summary", "bvg_tsse_draws", "bvg_sampler_tsse", "bvg_irf_draws", "bvg_irf_draws_a0", "bvg_sampler_irf", "bvg_fevd_draws", "bvg_fevd_draws_a0", "bvg_sampler_fevd", "bvg_forecast_draws", "bvg_forecast_draws_a0", "bvg_sampler_forecast", "bvg_fp64_peak", "bvg_dmma_peak", "bvg_post_normal", "bvg_post_normal_sur",
             "bvg_ssvs", "bvg_bvs", "bvg_stochvol", "bvg_kalman_dk"]

@@ -613,6 +613,18 @@ int bvg_sampler_loglik_total(bvg_sampler* s, double* total, void* cuda_stream) {
   return 0;
 }
 
+int bvg_sampler_loglik_total_device(bvg_sampler* s, double* dev_total, void* cuda_stream) {
+  if (!s || !dev_total) return fail(-1, "sampler / output is NULL");
+  if (s->P.structural) return fail(-6, "the log-likelihood kernels do not cover structural models");
+  CK(cudaSetDevice(s->device));
+  const bool fast = !s->P.tvp && !tv_sigma_of(s->P) && s->P.M > 0 && s->bm.XX && s->bm.Aols && s->bm.SSE && s->P.k <= 32;
+  if (!fast) return fail(-6, "bvg_sampler_loglik_total_device covers constant-parameter models with T > M (cross-moment kernel)");
+  cudaError_t e = launch_loglik_total(s->P.k, s->P.M, s->P.T, (long long)s->n_chains * s->P.iterations, s->bm.XX,
+                                      s->bm.Aols, s->bm.SSE, s->d_coef, s->d_sigma, dev_total, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "total log-likelihood kernel");
+  return 0;
+}
+
 int bvg_loglik_total_host(const double* coef, const double* sigma, int64_t n_draws, int32_t k, int32_t M, int32_t T,
                           const double* Y, const double* X, double* total) {
   if (!coef || !sigma || !Y || !X || !total || n_draws < 1 || M < 1)

@@ -118,6 +118,12 @@ class ChainSampler:
         check(lib().bvg_sampler_loglik_total(self.handle, C.byref(tot), C.c_void_p(stream or 0)))
         return tot.value, int(self.spec.c.n_chains) * int(self.spec.c.iterations)
 
+    def loglik_total_device(self, dev_ptr, stream=0):
+        """The same sum written asynchronously to one double of DEVICE memory (`dev_ptr`: integer address): no host
+        synchronisation, e.g. for one all-reduce over a whole model grid."""
+        check(lib().bvg_sampler_loglik_total_device(self.handle, C.c_void_p(int(dev_ptr)), C.c_void_p(stream or 0)))
+        return int(self.spec.c.n_chains) * int(self.spec.c.iterations)
+
     _WHICH = {"coef": 0, "sigma": 1, "lambda": 2, "sigma_h": 3, "sigma_v": 4}
 
     def summary(self, which="coef", ci=0.95, probs=None, stream=0, ts_se=True):

@@ -228,6 +228,10 @@ int bvg_sampler_loglik(bvg_sampler* s, double* host_ll_t, void* cuda_stream);
  * S = SSE_ols + (A - A_ols) XX' (A - A_ols)', an HBM-bound pass over the draws; other models (and a rank-deficient X)
  * fall back to the per-period kernel.  *total on the host. */
 int bvg_sampler_loglik_total(bvg_sampler* s, double* total, void* cuda_stream);
+/* Same sum written to DEVICE memory (dev_total: one double), asynchronously on cuda_stream: no host synchronisation, so
+ * the sums of a whole model grid can be all-reduced in one collective (constant-parameter models with T > M only: -6
+ * otherwise). */
+int bvg_sampler_loglik_total_device(bvg_sampler* s, double* dev_total, void* cuda_stream);
 int bvg_loglik_total_host(const double* coef, const double* sigma, int64_t n_draws, int32_t k, int32_t M, int32_t T,
                           const double* Y, const double* X, double* total);
 /* stand-alone block, host buffers: loglik_normal(u, sigma) of src/loglik_normal.cpp:37-58 for n_batch problems.
