@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 SIGMA_WISHART, SIGMA_GAMMA, SIGMA_SV = 0, 1, 2
 VARSEL_NONE, VARSEL_SSVS, VARSEL_BVS = 0, 1, 2
 RESID_AUTO, RESID_DIRECT, RESID_MOMENT = 0, 1, 2
@@ -46,6 +46,7 @@ class BvgSpec(C.Structure):
         ("psi_n_include", C.c_int32), ("psi_shape", _dp), ("psi_rate", _dp), ("psi_init", _dp),
         ("structural", C.c_int32),
         ("resid_mode", C.c_int32), ("threads_per_chain", C.c_int32), ("sweeps_per_launch", C.c_int32),
+        ("n_gpus", C.c_int32),
         ("inject", C.POINTER(BvgInject)),
     ]
 
@@ -103,7 +104,7 @@ class Spec:
 
 
 def spec_from_model(obj, n_chains=1, seed=0, chain_offset=0, device=-1, resid_mode=RESID_AUTO,
-                    threads_per_chain=0, sweeps_per_launch=0, mixture="ksc1998", inject=None) -> Spec:
+                    threads_per_chain=0, sweeps_per_launch=0, mixture="ksc1998", inject=None, n_gpus=0) -> Spec:
     """bvarmodel list -> bvg_spec (the unpacking of src/bvaralg.cpp:9-249 / src/bvartvpalg.cpp:11-279)."""
     data, model, priors, initial = obj["data"], obj["model"], obj["priors"], obj["initial"]
     structural = bool(model.get("structural"))
@@ -200,6 +201,7 @@ def spec_from_model(obj, n_chains=1, seed=0, chain_offset=0, device=-1, resid_mo
             sp.set("psi_include", pinc)
             c.psi_n_include = pinc.shape[0]
     c.resid_mode, c.threads_per_chain, c.sweeps_per_launch = resid_mode, threads_per_chain, sweeps_per_launch
+    c.n_gpus = int(n_gpus)
     if inject:
         st = BvgInject()
         for name in INJECT_FIELDS:

@@ -9,8 +9,12 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <future>
 #include <string>
+#include <thread>
 #include <vector>
 #include "bvg_kernels.cuh"
 #include "bvg_prepare.hpp"
@@ -19,6 +23,11 @@ using namespace bvg;
 
 static thread_local std::string g_last_error;
 static int (*g_poll)(void) = nullptr;
+// multi-GPU one-shot calls: the shards run on worker threads, which never call the interrupt callback themselves (it may
+// touch the R API: calling thread only); the calling thread polls it and raises g_abort, which the workers check
+// between kernel batches
+static thread_local bool t_worker = false;
+static std::atomic<int> g_abort{0};
 
 static int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -170,6 +179,8 @@ int bvg_sampler_reset(bvg_sampler* s) {
 int bvg_sampler_create(const bvg_spec* spec, bvg_sampler** out) {
   if (!out) return fail(-1, "sampler output pointer is NULL");
   *out = nullptr;
+  if (spec && spec->n_gpus > 1)
+    return fail(-54, "the handle API drives one device: n_gpus > 1 is served by bvg_bvaralg / bvg_bvartvpalg");
   bvg_sampler* s = new bvg_sampler();
   int rc = prepare(spec, s->P);
   if (rc != 0) { std::string m = s->P.error; delete s; return fail(rc, m); }
@@ -340,7 +351,8 @@ int bvg_sampler_run(bvg_sampler* s, void* cuda_stream) {
     const int s1 = (s0 + chunk < s->sweeps) ? s0 + chunk : s->sweeps;
     int rc = launch_chunk(s, s0, s1, st);
     if (rc) return rc;
-    if (g_poll) {   // the callback is only meaningful between finished batches
+    if (t_worker) { if (g_abort.load()) return fail(-100, "interrupted"); }
+    else if (g_poll) {   // the callback is only meaningful between finished batches
       CK(cudaStreamSynchronize(st));
       if (g_poll()) return fail(-100, "interrupted");
     }
@@ -390,7 +402,8 @@ int bvg_sampler_run_to_host(bvg_sampler* s, const bvg_out* h, void* cuda_stream)
       if ((rc = copy_rows(h->sigma_h, s->d_sigma_h, s->n_chains, P.iterations, s->rows_sigma_h, it0, it1, s->copy_stream))) return rc;
       if ((rc = copy_rows(h->sigma_v, s->d_sigma_v, s->n_chains, P.iterations, s->rows_sigma_v, it0, it1, s->copy_stream))) return rc;
     }
-    if (g_poll) {
+    if (t_worker) { if (g_abort.load()) { cudaDeviceSynchronize(); return fail(-100, "interrupted"); } }
+    else if (g_poll) {
       CK(cudaStreamSynchronize(st));
       if (g_poll()) { cudaDeviceSynchronize(); return fail(-100, "interrupted"); }
     }
@@ -443,10 +456,87 @@ double bvg_sampler_last_kernel_ms(bvg_sampler* s) {
 int64_t bvg_sampler_launch_count(bvg_sampler* s) { return s ? s->launches : 0; }
 const char* bvg_sampler_kernel_name(bvg_sampler* s) { return s ? s->kernel_name : ""; }
 
+static int one_shot_single(const bvg_spec* spec, const bvg_out* out);
+
+// n_gpus > 1: contiguous blocks of global chain ids, one host thread per shard, results straight into the caller's buffers
+static int one_shot_sharded(const bvg_spec* spec, const bvg_out* out, int shards) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(-50, "no CUDA device available: libbvargpu has no CPU fallback");
+  }
+  int64_t rc_[5] = {0, 0, 0, 0, 0};
+  int rc = bvg_out_rows(spec, &rc_[0], &rc_[1], &rc_[2], &rc_[3], &rc_[4]);
+  if (rc) return rc;
+  const int64_t n = spec->n_chains, iters = spec->iterations, sweeps = (int64_t)spec->iterations + spec->burnin;
+  const int base = spec->device >= 0 ? spec->device : 0;
+  const int k = spec->k, T = spec->T, nint = spec->structural ? k * (spec->M + k) : k * spec->M, np = k * (k - 1) / 2;
+  // per-chain strides of the injected arrays ([chain][sweep][count], counts as in bvg_sampler_create)
+  const int64_t icnt[19] = {nint, nint, nint, nint, (int64_t)k * T, (int64_t)k * T, k, k, k, k, np, (int64_t)nint * T, nint, nint,
+                            spec->tvp ? (int64_t)np * T : np, np, np, np, np};
+  struct Shard { bvg_spec sp; bvg_out o; bvg_inject inj; int rc; std::string msg; };
+  std::vector<Shard> sh((size_t)shards);
+  for (int g = 0; g < shards; ++g) {
+    const int64_t c0 = n * g / shards, c1 = n * (g + 1) / shards;
+    Shard& S = sh[(size_t)g];
+    S.sp = *spec;
+    S.sp.n_gpus = 1;
+    S.sp.device = (base + g) % ndev;
+    S.sp.n_chains = c1 - c0;
+    S.sp.chain_offset = spec->chain_offset + c0;
+    S.o = *out;
+    const int64_t per = c0 * iters;
+    if (out->coef) S.o.coef = out->coef + per * rc_[0];
+    if (out->sigma) S.o.sigma = out->sigma + per * rc_[1];
+    if (out->lambda) S.o.lambda = out->lambda + per * rc_[2];
+    if (out->sigma_h) S.o.sigma_h = out->sigma_h + per * rc_[3];
+    if (out->sigma_v) S.o.sigma_v = out->sigma_v + per * rc_[4];
+    if (out->status) S.o.status = out->status + c0;
+    if (spec->inject) {
+      S.inj = *spec->inject;
+      const double** f = reinterpret_cast<const double**>(&S.inj);
+      for (int b = 0; b < 19; ++b)
+        if (f[b]) f[b] += c0 * sweeps * icnt[b];
+      S.sp.inject = &S.inj;
+    }
+    S.rc = 0;
+  }
+  g_abort.store(0);
+  std::vector<std::future<void>> fut;
+  for (int g = 0; g < shards; ++g)
+    fut.push_back(std::async(std::launch::async, [&sh, g]() {
+      t_worker = true;
+      Shard& S = sh[(size_t)g];
+      S.rc = (S.sp.n_chains > 0) ? one_shot_single(&S.sp, &S.o) : 0;
+      if (S.rc) S.msg = g_last_error;
+    }));
+  bool interrupted = false;
+  for (auto& f : fut) {
+    while (f.wait_for(std::chrono::milliseconds(20)) != std::future_status::ready)
+      if (g_poll && !interrupted && g_poll()) { interrupted = true; g_abort.store(1); }
+  }
+  g_abort.store(0);
+  if (interrupted) return fail(-100, "interrupted");
+  for (int g = 0; g < shards; ++g)
+    if (sh[(size_t)g].rc) return fail(sh[(size_t)g].rc, "GPU shard " + std::to_string(g) + ": " + sh[(size_t)g].msg);
+  return 0;
+}
+
 static int one_shot(const bvg_spec* spec, const bvg_out* out, int want_tvp) {
   if (!spec || !out) return fail(-1, "spec / out is NULL");
   if ((spec->tvp ? 1 : 0) != want_tvp)
     return fail(-10, want_tvp ? "bvg_bvartvpalg needs spec.tvp = 1" : "bvg_bvaralg needs spec.tvp = 0");
+  if (spec->abi_version != BVG_ABI_VERSION) return fail(-2, "bvg_spec.abi_version does not match this library");
+  int shards = spec->n_gpus;
+  if (shards < 0) shards = bvg_device_count();
+  if (shards > 1 && spec->n_chains > 1) {
+    if ((int64_t)shards > spec->n_chains) shards = (int)spec->n_chains;
+    return one_shot_sharded(spec, out, shards);
+  }
+  return one_shot_single(spec, out);
+}
+
+static int one_shot_single(const bvg_spec* spec, const bvg_out* out) {
   bvg_sampler* s = nullptr;
   int rc = bvg_sampler_create(spec, &s);
   if (rc) return rc;

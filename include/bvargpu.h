@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BVG_ABI_VERSION 1
+#define BVG_ABI_VERSION 2
 
 /* error-variance prior (priors$sigma, R/add_priors.bvarmodel.R:521-569) */
 #define BVG_SIGMA_WISHART 0
@@ -151,6 +151,13 @@ typedef struct bvg_spec {
   int32_t resid_mode;       /* BVG_RESID_*                                 */
   int32_t threads_per_chain; /* 0 = auto; 1,2,4,8,16,32 (sub-warp tiles) or a multiple of 32 (CTA per chain) */
   int32_t sweeps_per_launch; /* 0 = auto: kernel launches are chunked so that D2H copies overlap compute */
+  /* bvg_bvaralg / bvg_bvartvpalg only: shard the n_chains chains over this many GPUs of the box (0, 1 = one device;
+   * -1 = all devices).  Contiguous blocks of GLOBAL chain ids, one host thread per shard, shard i on device
+   * (device + i) mod device count, results straight into the caller's buffers: bit-identical to n_gpus = 1 (the RNG is
+   * keyed by the global chain id).  The interrupt callback is polled from the CALLING thread only.  What
+   * parallel::mclapply(mc.cores) is to the reference (R/draw_posterior.bvarmodel.R:57-58), without forking a CUDA
+   * context.  The handle API drives one device (-54 otherwise). */
+  int32_t n_gpus;
   const bvg_inject* inject;  /* NULL = Philox                              */
 } bvg_spec;
 

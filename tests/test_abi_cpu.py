@@ -28,14 +28,14 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header(tmp_path):
     """sizeof/offsetof of the ctypes mirror == what the C compiler sees."""
     src = tmp_path / "lay.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "bvargpu.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "bvargpu.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(bvg_spec),sizeof(bvg_out),sizeof(bvg_inject),offsetof(bvg_spec,seed),offsetof(bvg_spec,sigma_i),'
-                   'offsetof(bvg_spec,inject),offsetof(bvg_out,status));return 0;}\n')
+                   'offsetof(bvg_spec,inject),offsetof(bvg_out,status),offsetof(bvg_spec,n_gpus));return 0;}\n')
     exe = tmp_path / "lay"
     subprocess.check_call(["/usr/bin/gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(_abi.BvgSpec), C.sizeof(_abi.BvgOut), C.sizeof(_abi.BvgInject), _abi.BvgSpec.seed.offset,
-            _abi.BvgSpec.sigma_i.offset, _abi.BvgSpec.inject.offset, _abi.BvgOut.status.offset]
+            _abi.BvgSpec.sigma_i.offset, _abi.BvgSpec.inject.offset, _abi.BvgOut.status.offset, _abi.BvgSpec.n_gpus.offset]
     assert got == want
 
 

@@ -439,3 +439,58 @@ def test_structural_tvp_guard_padded_buffers(gpu):
     sm = s.summary("sigma_v", ts_se=False)
     np.testing.assert_allclose(sm["mean"], out.arrays["sigma_v"].reshape(-1, rows["sigma_v"]).mean(axis=0), rtol=1e-12)
     s.close()
+
+
+@pytest.mark.parametrize("case", ["kron", "ssvs_injected", "tvp_sv"])
+def test_library_internal_sharding_is_bit_identical(gpu, case):
+    """bvg_spec.n_gpus: the one-shot entry points shard the chains over host threads / devices themselves (shard i on
+    device (device + i) mod count -- on a one-GPU box all shards share the device, which exercises the same slicing of
+    outputs, injected variates and global chain ids); results equal the single-device call bit for bit."""
+    if case == "kron":
+        obj, n, kw = helpers.model_c1(iterations=60, burnin=20), 37, {}
+        stacked = None
+    elif case == "ssvs_injected":
+        obj, n, kw = helpers.model_c3(K=3, p=2, nobs=80, iterations=12, burnin=4), 7, {}
+        _, stacked = helpers.make_variates(obj, n, seed=3)
+    else:
+        obj, n, kw = helpers.model_sv(tvp=True, nobs=30, iterations=6, burnin=2), 5, {}
+        stacked = None
+    one = _run(gpu, obj, n, stacked, seed=99, **kw)
+    for g in (2, 3, -1):
+        many = _run(gpu, obj, n, stacked, seed=99, n_gpus=g, **kw)
+        for key in one.arrays:
+            assert np.array_equal(one.arrays[key], many.arrays[key]), (case, g, key)
+        assert np.array_equal(one.status, many.status)
+    # more shards than chains, and an offset shard of a larger job
+    few = _run(gpu, obj, 2, None if stacked is None else {k_: v[:2] for k_, v in stacked.items()}, seed=99, n_gpus=8, **kw)
+    for key in one.arrays:
+        assert np.array_equal(one.arrays[key][:2], few.arrays[key]), key
+
+
+def test_interrupt_poll_aborts_the_run(gpu):
+    """bvg_set_interrupt_poll (Rcpp::checkUserInterrupt analogue, bvaralg.cpp:294-296): a non-zero return of the callback
+    aborts the call with -100, on the single-device path and -- polled from the calling thread -- on the sharded one."""
+    from bvartools_b200 import _abi
+    obj = helpers.model_c3(iterations=3000, burnin=0)         # ~0.5 s of sweeps: the calling thread polls every 20 ms
+    calls = {"n": 0}
+    CB = C.CFUNCTYPE(C.c_int)
+
+    def poll():
+        calls["n"] += 1
+        return 1 if calls["n"] >= 2 else 0
+    cb = CB(poll)
+    gpu.bvg_set_interrupt_poll.argtypes = [CB]
+    gpu.bvg_set_interrupt_poll(cb)
+    try:
+        for ng in (0, 2):
+            calls["n"] = 0
+            spec = _abi.spec_from_model(obj, n_chains=296, seed=1, sweeps_per_launch=50, n_gpus=ng)
+            out = _abi.OutBuffers(spec)
+            rc = gpu.bvg_bvaralg(C.byref(spec.c), C.byref(out.c))
+            assert rc == -100, (ng, rc, gpu.bvg_last_error())
+            assert b"interrupted" in gpu.bvg_last_error()
+            assert calls["n"] >= 2
+    finally:
+        gpu.bvg_set_interrupt_poll(CB(0))
+    ok = _run(gpu, helpers.model_c1(iterations=20, burnin=5), 4, seed=1)
+    assert not ok.status.any()
