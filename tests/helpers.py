@@ -152,3 +152,32 @@ def oracle_stack(obj, per_chain, literal=True, table="ksc1998"):
 def relerr(a, b):
     a, b = np.asarray(a), np.asarray(b)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300 + 1e-3 * np.max(np.abs(b)))))
+
+
+# ---------------------------------------------------------------- oracle runs spread over the host cores (large tests)
+def _oracle_chain_job(args):
+    obj, inj, seed, literal, table = args
+    src = VariateSource(injected=inj) if inj is not None else VariateSource(rng=np.random.default_rng(seed))
+    if inj is not None:
+        return oracle_stack(obj, [inj], literal=literal, table=table)
+    fn = osamp.bvartvpalg if obj["model"].get("tvp") else osamp.bvaralg
+    return fn(obj, src, literal=literal, table=table)["posteriors"]
+
+
+def oracle_stack_parallel(obj, per_chain, literal=False, table="ksc1998", workers=None):
+    """oracle_stack with one process per chain (the oracle is single-threaded NumPy); same result, chain order kept."""
+    import os
+    from concurrent.futures import ProcessPoolExecutor
+    workers = workers or min(len(per_chain), os.cpu_count() or 1)
+    with ProcessPoolExecutor(max_workers=workers) as ex:
+        parts = list(ex.map(_oracle_chain_job, [(obj, inj, 0, literal, table) for inj in per_chain]))
+    return {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
+
+
+def oracle_sampler_parallel(obj, seeds, literal=False, table="ksc1998", workers=None):
+    """The oracle SAMPLER (its own NumPy generator) for a list of seeds, one process per chain; list of `posteriors`."""
+    import os
+    from concurrent.futures import ProcessPoolExecutor
+    workers = workers or min(len(seeds), os.cpu_count() or 1)
+    with ProcessPoolExecutor(max_workers=workers) as ex:
+        return list(ex.map(_oracle_chain_job, [(obj, None, s, literal, table) for s in seeds]))

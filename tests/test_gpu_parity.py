@@ -184,8 +184,8 @@ def _mcse(x, nb=20):
 
 def test_tier2_c1_posterior_vs_analytic_and_readme(gpu):
     """Tier 2, config c1/c2-A: full GPU sampler (Philox).  Posterior mean of a = OLS and E[Sigma] = SSE/63 within
-    4 MCSE; README table (README.md:240-299) means within 4 combined MCSE, SD ratio within 5 %; KS-consistent
-    marginals between two disjoint sets of chains."""
+    4 MCSE; README table (README.md:240-299) means within 4 combined MCSE, SD ratio within 5 %, quantiles within 4 MCSE
+    of a sample quantile."""
     from scipy import stats
     obj = helpers.model_c1(iterations=5000, burnin=1000)
     out = _run(gpu, obj, 64, seed=1234567)
@@ -211,11 +211,14 @@ def test_tier2_c1_posterior_vs_analytic_and_readme(gpu):
             col = j * 3 + i
             assert abs(flat[:, col].mean() - row["Mean"]) < 4.0 * np.hypot(mc[col], row["TSSD"])
             assert abs(flat[:, col].std(ddof=1) / row["SD"] - 1.0) < 0.05
+            # README quantiles: 4 Monte-Carlo standard errors of a sample quantile of the README's own run (asymptotic
+            # sqrt(p (1 - p)) / phi(z_p) = 1.25 / 2.67 times the SE of the mean, = the table's time-series SD) plus the
+            # table's 4-significant-digit rounding; the GPU side (64 x 5000 draws) contributes nothing visible
             for qn, qv in (("q2.5", 0.025), ("q50", 0.5), ("q97.5", 0.975)):
-                assert abs(np.quantile(flat[:, col], qv) - row[qn]) < 8.0 * row["TSSD"] * (1.0 if qv == 0.5 else 2.5)
-    a, b = coef[:32, ::10].reshape(-1, 21), coef[32:, ::10].reshape(-1, 21)
-    pvals = [stats.ks_2samp(a[:, c], b[:, c]).pvalue for c in range(21)]
-    assert min(pvals) > 1e-3 / 21
+                tol = 4.0 * row["TSSD"] * (1.25 if qv == 0.5 else 2.67) * 1.1 + 5e-4 * abs(row[qn])
+                assert abs(np.quantile(flat[:, col], qv) - row[qn]) < tol, (var, reg, qn)
+    # (KS of the marginals: against the analytic matrix-t posterior and the oracle's own sampler, see
+    #  test_tier2_c1_marginals_vs_analytic_matrix_t)
 
 
 def test_tier2_ssvs_vs_oracle_sampler(gpu):
@@ -494,3 +497,121 @@ def test_interrupt_poll_aborts_the_run(gpu):
         gpu.bvg_set_interrupt_poll(CB(0))
     ok = _run(gpu, helpers.model_c1(iterations=20, burnin=5), 4, seed=1)
     assert not ok.status.any()
+
+
+# ------------------------------------------------------------------------------------------- tier 2 at BASELINE shapes
+def _across_chain_check(dev_means, ref_means, z=4.5, what=""):
+    """|mean_dev - mean_ref| < z * SE, SE from the spread of the per-chain means of both samplers (independent chains)."""
+    d, o = np.asarray(dev_means), np.asarray(ref_means)
+    se = np.hypot(d.std(axis=0, ddof=1) / np.sqrt(d.shape[0]), o.std(axis=0, ddof=1) / np.sqrt(o.shape[0]))
+    bad = np.abs(d.mean(axis=0) - o.mean(axis=0)) > z * se + 1e-12
+    assert not bad.any(), (what, int(bad.sum()), np.abs(d.mean(axis=0) - o.mean(axis=0))[bad][:5], se[bad][:5])
+
+
+def test_tier2_c1_marginals_vs_analytic_matrix_t(gpu):
+    """Config c1 / c2-A against the ANALYTIC posterior.  Flat coefficient prior + Wishart prior: integrating a out of the joint
+    posterior gives Sigma^-1 ~ W((S0 + SSE)^-1, T + df - M) and A | y matrix-t, i.e. every coefficient is Student-t with
+    nu = T + df - M - k + 1 = 65 degrees of freedom, location OLS and scale^2 = (S0 + SSE)_ii (X X')^-1_jj / nu.
+    One-sample KS of the (thinned) GPU draws against that t distribution for all 21 coefficients, Bonferroni 1e-3; plus a
+    two-sample KS against the draws of the oracle's C restatement run with its own generator."""
+    import os
+    from scipy import stats
+    from oracle.dense_ref import bvar_dense
+    obj = helpers.model_c1(iterations=5000, burnin=1000)
+    out = _run(gpu, obj, 64, seed=424242)
+    coef = out.arrays["coef"][:, ::10, :].reshape(-1, 21)         # thinned: the chain mixes in a few sweeps
+    Y, Z = obj["data"]["Y"], obj["data"]["Z"]
+    T, k = Y.shape
+    M = Z.shape[1]
+    B = np.linalg.lstsq(Z, Y, rcond=None)[0]                      # M x k
+    S = (Y - Z @ B).T @ (Y - Z @ B) + 1e-4 * np.eye(k)
+    XXi = np.linalg.inv(Z.T @ Z)
+    nu = T + 1.0 - M - k + 1.0
+    pvals = []
+    for j in range(M):
+        for i in range(k):
+            scale = np.sqrt(S[i, i] * XXi[j, j] / nu)
+            pvals.append(stats.kstest(coef[:, j * k + i], stats.t(df=nu, loc=B[j, i], scale=scale).cdf).pvalue)
+    assert min(pvals) > 1e-3 / 21, sorted(pvals)[:3]
+    assert np.median(pvals) > 0.05
+    ref = bvar_dense(obj, n_chains=16, seed=777, n_threads=os.cpu_count() or 1, dense_gemm=False)
+    rc = ref["coef"][:, ::10, :].reshape(-1, 21)
+    rs = ref["sigma"][:, ::10, :].reshape(-1, 9)
+    ds = out.arrays["sigma"][:, ::10, :].reshape(-1, 9)
+    p2 = [stats.ks_2samp(coef[:, c], rc[:, c]).pvalue for c in range(21)] + \
+         [stats.ks_2samp(ds[:, c], rs[:, c]).pvalue for c in (0, 1, 2, 4, 5, 8)]
+    assert min(p2) > 1e-3 / len(p2), sorted(p2)[:3]
+
+
+def test_tier2_c3_full_size_ssvs_vs_c_port(gpu):
+    """Tier 2 at the c3 shape (K = 6, p = 4, n = 150, T = 191, SSVS): GPU sampler (Philox) against the structure-exploiting C
+    restatement with its own generator; posterior means of all 150 coefficients, their inclusion frequencies and Sigma
+    within 4.5 standard errors of the across-chain means."""
+    import os
+    from oracle.dense_ref import bvar_dense
+    obj = helpers.model_c3(iterations=500, burnin=300)
+    dev = _run(gpu, obj, 64, seed=31)
+    ref = bvar_dense(obj, n_chains=12, seed=5, n_threads=os.cpu_count() or 1, dense_gemm=False)
+    assert not dev.status.any()
+    assert 0.02 < dev.arrays["lambda"][:, :, :144].mean() < 0.98
+    for name in ("coef", "lambda", "sigma"):
+        _across_chain_check(dev.arrays[name].mean(axis=1), ref[name].mean(axis=1), what=name)
+
+
+def test_tier2_c4_full_size_tvp_sv_vs_oracle_sampler(gpu):
+    """Tier 2 at the c4 shape (T = 200, n = 21, KSC SV): posterior means of the whole state path (4200 marginals), of the
+    state variances and of log Sigma_t of the GPU sampler against the oracle sampler (own NumPy generator, structured path
+    == literal dense path: test_oracle.py), 8 oracle chains."""
+    obj = helpers.model_sv(tvp=True, nobs=202, iterations=200, burnin=200)
+    dev = _run(gpu, obj, 32, seed=77)
+    assert not dev.status.any()
+    posts = helpers.oracle_sampler_parallel(obj, [900 + c for c in range(8)], literal=False)
+    T = obj["data"]["Y"].shape[0]
+    o_coef, o_sv, o_sig = [], [], []
+    for r in posts:
+        parts = [r[nm] for nm in ("a", "c")]
+        it = parts[0]["coeffs"].shape[1]
+        cube = np.concatenate([p["coeffs"].reshape(T, -1, it) for p in parts], axis=1).reshape(-1, it)
+        o_coef.append(cube.mean(axis=1))
+        o_sv.append(np.log(np.concatenate([p["sigma"] for p in parts])).mean(axis=1))
+        o_sig.append(np.log(r["sigma"]["coeffs"].reshape(T, 9, it)[:, [0, 4, 8], :]).mean(axis=2).reshape(-1))
+    d_coef = dev.arrays["coef"].mean(axis=1)
+    d_sv = np.log(dev.arrays["sigma_v"]).mean(axis=1)
+    d_sig = np.log(dev.arrays["sigma"].reshape(32, -1, T, 9)[:, :, :, [0, 4, 8]]).mean(axis=1).reshape(32, -1)
+    _across_chain_check(d_coef, o_coef, z=5.0, what="state path")          # 4200 comparisons
+    _across_chain_check(d_sv, o_sv, what="log state variances")
+    _across_chain_check(d_sig, o_sig, z=5.0, what="log Sigma_t")
+
+
+def test_tier2_large_path_vs_c_port(gpu):
+    """Tier 2 for the large-VAR path (config c5's kernels: blocked DMMA Cholesky in HBM) at K = 6, p = 4 (n = 150, three
+    block columns, Minnesota prior) -- the c5 shape itself is beyond what the CPU restatement samples in test time (one
+    dense sweep at n = 1620 takes seconds); c5 at full size is covered by tier 1 (test_c5_full_size_large_var_injected)."""
+    import os
+    from oracle.dense_ref import bvar_dense
+    y = helpers.synth_var(6, 4, 150, 77)
+    m = helpers.gen_var(y, p=4, deterministic="const", iterations=400, burnin=200)
+    obj = helpers.add_priors(m, coef=dict(minnesota=dict(kappa0=2, kappa1=0.5, kappa3=5)), sigma=dict(df="k", scale=1))
+    dev = _run(gpu, obj, 48, seed=13, threads_per_chain=-1)
+    ref = bvar_dense(obj, n_chains=12, seed=6, n_threads=os.cpu_count() or 1, dense_gemm=False)
+    assert not dev.status.any()
+    for name in ("coef", "sigma"):
+        _across_chain_check(dev.arrays[name].mean(axis=1), ref[name].mean(axis=1), what=name)
+
+
+def test_bvs_decisions_match_over_a_million_sites(gpu):
+    """the BVS inclusion decisions of the CUDA path (rank-1 likelihood ratio, stale A_G) against the
+    reference-ordered evaluation of the oracle on the same injected uniforms / normals: 64 chains x 900 sweeps x 18 positions
+    = 1.04e6 decisions, zero mismatches allowed; continuous draws <= 1e-10."""
+    obj = helpers.model_c3(K=3, p=2, nobs=80, iterations=900, burnin=0, bvs=True)
+    n_chains = 64
+    per, stacked = helpers.make_variates(obj, n_chains, seed=2024)
+    out = _run(gpu, obj, n_chains, stacked)
+    want = helpers.oracle_stack_parallel(obj, per, literal=False)
+    n_inc = int(np.asarray(obj["priors"]["coefficients"]["bvs"]["include"]).size)
+    assert n_chains * 900 * n_inc >= 1_000_000
+    mism = int((out.arrays["lambda"] != want["lambda"]).sum())
+    assert mism == 0, mism
+    assert 0.05 < want["lambda"][:, :, :n_inc].mean() < 0.95          # the decisions are not trivial
+    for key in ("coef", "sigma"):
+        assert helpers.relerr(out.arrays[key], want[key]) < TOL, key
