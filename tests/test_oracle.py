@@ -190,3 +190,93 @@ def test_kalman_dk_posterior_mean_matches_precision_form():
     sig_t = np.tile(np.linalg.inv(su)[None], (T, 1, 1))
     mean = samplers._tvp_state_banded(Zt, sig_t, q, a0, y, np.ones(n), np.zeros(n * T)).reshape(n, T, order="F")
     np.testing.assert_allclose(sm[:, :T], mean, rtol=1e-8, atol=1e-10)
+
+
+# ---- second, independent restatement (plain C, dense) of the blocks only one restatement covered ---------------------
+
+@pytest.mark.parametrize("table", ["ksc1998", "ocsn2007"])
+def test_c_stochvol_equals_numpy_oracle(table):
+    """src/stochvol_ksc1998.cpp:60-108 / stochvol_ocsn2007.cpp:60-114 read twice: NumPy (oracle/blocks.py) and plain C
+    (oracle/blocks_ref.c) on the same injected uniforms / normals; indicators exact, h to 1e-12."""
+    from oracle import blocks_ref
+    rng = np.random.default_rng(5)
+    T, k = 73, 3
+    y = rng.standard_normal((T, k)) * np.array([0.3, 1.0, 2.5])
+    h0 = np.log(np.tile(y.var(axis=0), (T, 1))) + 0.1 * rng.standard_normal((T, k))
+    sigma, const = np.array([0.02, 0.05, 0.4]), np.array([1e-4, 1e-3, 1e-5])
+    u, eps = rng.random((k, T)), rng.standard_normal((k, T))
+    want_h, want_s = blocks.stochvol_mixture(y, h0, sigma, h0[0], const, u, eps, table=table, return_s=True)
+    got_h, got_s = blocks_ref.stochvol(y, h0, sigma, h0[0], const, u, eps, table=table)
+    assert np.array_equal(got_s, want_s)
+    assert helpers.relerr(got_h, want_h) < 1e-12
+
+
+@pytest.mark.parametrize("tvp,tv_sigma", [(False, False), (True, False), (False, True), (True, True)])
+def test_c_bvs_equals_numpy_oracle(tvp, tv_sigma):
+    """src/bvs.cpp:73-159 read twice; constant / time-varying a, constant / per-period Sigma^-1, include subset.  The
+    decisions must agree exactly over many calls (each call visits up to n sites)."""
+    from oracle import blocks_ref
+    rng = np.random.default_rng(11 + 2 * tvp + tv_sigma)
+    k, T, n = 3, 40, 12
+    mismatches = sites = 0
+    for rep in range(40):
+        z = rng.standard_normal((k * T, n))
+        a = rng.standard_normal((n, T)) * 0.3 if tvp else rng.standard_normal(n) * 0.3
+        lam = np.diag((rng.random(n) < 0.6).astype(np.float64))
+        th = (np.diag(lam)[:, None] * a) if tvp else np.diag(lam) * a
+        mean = np.stack([z[t * k:(t + 1) * k] @ (th[:, t] if tvp else th) for t in range(T)], axis=1)
+        y = mean + 0.5 * rng.standard_normal((k, T))
+        if tv_sigma:
+            blocks_t = []
+            for t in range(T):
+                w = rng.standard_normal((k, k + 2))
+                blocks_t.append(np.linalg.inv(w @ w.T / (k + 2)))
+            sig = np.vstack(blocks_t)
+        else:
+            w = rng.standard_normal((k, k + 2))
+            sig = np.linalg.inv(w @ w.T / (k + 2))
+        prior = rng.uniform(0.2, 0.8, n)
+        u1, u2 = rng.random(n), rng.random(n)
+        include = None if rep % 2 == 0 else np.sort(rng.choice(n, size=7, replace=False)) + 1
+        want = np.diag(blocks.bvs(y, z, a, lam, sig, prior, u1, u2, include=include))
+        got = np.diag(blocks_ref.bvs(y, z, a, lam, sig, prior, u1, u2, include=include))
+        mismatches += int((want != got).sum())
+        sites += n if include is None else len(include)
+    assert sites > 300 and mismatches == 0
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_c_tvp_state_equals_numpy_oracle(masked):
+    """src/bvartvpalg.cpp:290-297 read three ways: the literal dense NumPy form (H, kron, block_diag as written), the
+    banded structured form of oracle/samplers.py and the plain-C dense form of oracle/blocks_ref.c."""
+    import scipy.linalg as sla
+    from oracle import blocks_ref
+    rng = np.random.default_rng(21 + masked)
+    k, T, M = 3, 25, 4
+    n = k * M
+    x = rng.standard_normal((M, T))
+    Zt = [np.kron(x[:, t][None, :], np.eye(k)) for t in range(T)]                  # k x n
+    lam = (rng.random(n) < 0.7).astype(np.float64) if masked else np.ones(n)
+    sig_t = []
+    for t in range(T):
+        w = rng.standard_normal((k, k + 3))
+        sig_t.append(np.linalg.inv(w @ w.T / (k + 3)))
+    sig_t = np.array(sig_t)
+    y = rng.standard_normal((k, T))
+    sv_i = rng.uniform(5.0, 200.0, n)
+    a_init = rng.standard_normal(n) * 0.2
+    eps = rng.standard_normal(n * T)
+    # literal dense form, as the reference writes it
+    H = np.eye(n * T)
+    idx = np.arange(n * (T - 1))
+    H[idx + n, idx] = -1.0
+    zz = sla.block_diag(*Zt) * np.tile(lam, T)[None, :]
+    zzss = zz.T @ sla.block_diag(*sig_t)
+    hsh = H.T @ np.kron(np.eye(T), np.diag(sv_i)) @ H
+    post_v = hsh + zzss @ zz
+    post_mu = sla.solve(post_v, hsh @ np.tile(a_init, T) + zzss @ y.reshape(-1, order="F"))
+    lit = post_mu + sla.solve_triangular(sla.cholesky(post_v, lower=False), eps, lower=False)
+    band = samplers._tvp_state_banded(Zt, sig_t, sv_i, a_init, y, lam, eps)
+    got = blocks_ref.tvp_state(y, np.vstack(Zt) * lam[None, :], np.vstack(list(sig_t)), sv_i, a_init, eps)
+    assert helpers.relerr(got, lit) < 1e-11
+    assert helpers.relerr(got, band) < 1e-11
