@@ -262,9 +262,10 @@ BVG_HD void tvp_chain(const Grp& g, const TvpModel& tm, const ChainRng& rng, dou
   for (int sweep = sweep_begin; sweep < sweep_end; ++sweep) {
     const bool keep = sweep >= burnin;
     const long long pos = (long long)sweep - burnin;
-    if (sv && (sweep == sweep_begin || !Grp::kWarp32)) {
+    if (sv && (sweep == sweep_begin || !Grp::kWarp32 || covar)) {
       // bvartvpalg.cpp:446; the very first sweep uses h.row(0) for every period (:224-225,230)
-      // (warp per chain: later sweeps take exp(-h) from the end of the previous sweep's SV block, one exp pass per sweep)
+      // (warp per chain without the psi block: later sweeps take exp(-h) from the end of the previous sweep's SV block,
+      //  one exp pass per sweep; with the psi block that pass does not run and ew is a work array of the SV step)
       for (int e = tid; e < k * T; e += G) ew[e] = 1.0 / exp(sweep == 0 ? h[T * (e / T)] : h[e]);
       g.sync();
     }
