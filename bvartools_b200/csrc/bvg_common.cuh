@@ -7,6 +7,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define BVG_HD __host__ __device__ __forceinline__
@@ -103,40 +104,149 @@ BVG_HD void bvg_sincospi(double x, double* s, double* c) {
 #endif
 }
 
-// cos(2 pi u), sin(2 pi u) for u in (0, 1): the Box-Muller angle.  The general-purpose cospi / sinpi pair was 45 % of
-// the executed instructions of the flat-prior kernel (profiles/r01_c2a_final_*): each carries its own argument
-// reduction and special-case handling.  Here the range is known: t = 4 u, q = rint(t) in {0..4}, phi = (pi / 2)(t - q)
-// in [-pi/4, pi/4]; sin(phi) and cos(phi) by their Taylor polynomials in phi^2 (truncation < 1e-16 at pi/4), then a
-// rotation by q quarter turns.  Same code on host (tests/emu) and device.
+// ---- FP64 transforms of the variate generators --------------------------------------------------------------------
+// The generators are instruction-issue bound (profiles/r02_c2a_*): what counts is the number of issued instructions per
+// variate, not FP64 flops.  Three things are done about that here:
+//  * polynomial coefficients live in __constant__ tables: sm_100a DFMA takes no immediate / constant-bank operand, a
+//    literal double costs two UMOV (or IMAD.MOV) per use (17 % of the executed instructions of the round-1 kernel); from
+//    a table one LDCU.128 brings two coefficients into uniform registers;
+//  * log / sqrt / sincos are written for the ranges the generators produce (positive normal arguments, the angle in
+//    (0, 1) turns): no special-case handling, no slow-path calls, MUFU seed + Newton steps spelled out;
+//  * the same source is the host build of tests/emu (plain division / sqrt there: results agree to ~1e-16 relative).
+#if defined(__CUDACC__)
+#define BVG_TABLE(name, n, ...)                                             \
+  static __constant__ double name##_d[n] __attribute__((unused)) = {__VA_ARGS__}; \
+  static const double name##_h[n] __attribute__((unused)) = {__VA_ARGS__};
+#else
+#define BVG_TABLE(name, n, ...) static const double name##_h[n] __attribute__((unused)) = {__VA_ARGS__};
+#endif
+#if defined(__CUDA_ARCH__)
+#define BVG_TAB(name) name##_d
+#else
+#define BVG_TAB(name) name##_h
+#endif
+
+// sin(x) / x and cos(x) in z = x^2 on |x| <= pi/4 (Taylor; truncation < 1e-18 / 2e-18)
+BVG_TABLE(kSinTab, 9, 1.0, -0.16666666666666666, 0.008333333333333333, -0.0001984126984126984, 2.7557319223985893e-06,
+          -2.505210838544172e-08, 1.6059043836821613e-10, -7.647163731819816e-13, 2.8114572543455206e-15)
+BVG_TABLE(kCosTab, 10, 1.0, -0.5, 0.041666666666666664, -0.001388888888888889, 2.48015873015873e-05,
+          -2.755731922398589e-07, 2.08767569878681e-09, -1.1470745597729725e-11, 4.779477332387385e-14,
+          -1.5619206968586225e-16)
+// 2 atanh(f) = 2 f + f z P(z), z = f^2 <= 0.02944: P(z) = sum_k 2 / (2 k + 3) z^k, k = 0..8 (next term < 3e-17 relative)
+BVG_TABLE(kLogTab, 10, 0.6666666666666666, 0.4, 0.2857142857142857, 0.2222222222222222, 0.18181818181818182,
+          0.15384615384615385, 0.13333333333333333, 0.11764705882352941, 0.10526315789473684, 0.6931471805599453)
+
+// log(x) for a positive NORMAL double (no zero / denormal / inf / nan handling): x = m 2^e with m in [2^-1/2, 2^1/2),
+// log m = 2 atanh((m - 1) / (m + 1)).  ~2 ulp.
+BVG_HD double bvg_logpos(double x) {
+#if defined(__CUDA_ARCH__)
+  int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+#else
+  uint64_t bits;
+  memcpy(&bits, &x, 8);
+  int hi = (int)(bits >> 32);
+  const int lo = (int)(uint32_t)bits;
+#endif
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;
+  if (hi >= 0x3ff6a09f) { hi -= 0x00100000; e += 1; }
+#if defined(__CUDA_ARCH__)
+  const double m = __hiloint2double(hi, lo);
+#else
+  double m;
+  bits = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+  memcpy(&m, &bits, 8);
+#endif
+  const double num = m - 1.0, den = m + 1.0;
+  double f;
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));      // MUFU.RCP64H, then two Newton steps and a residual fix
+  double t = fma(-den, r, 1.0);
+  r = fma(r, t, r);
+  t = fma(-den, r, 1.0);
+  r = fma(r, t, r);
+  f = num * r;
+  f = fma(fma(-den, f, num), r, f);
+#else
+  f = num / den;
+#endif
+  const double z = f * f;
+  const double* c = BVG_TAB(kLogTab);
+  double p = c[8];
+  p = fma(p, z, c[7]);
+  p = fma(p, z, c[6]);
+  p = fma(p, z, c[5]);
+  p = fma(p, z, c[4]);
+  p = fma(p, z, c[3]);
+  p = fma(p, z, c[2]);
+  p = fma(p, z, c[1]);
+  p = fma(p, z, c[0]);
+  const double lm = fma(f * z, p, f + f);
+  return fma((double)e, c[9], lm);
+}
+
+// sqrt(x) for a positive NORMAL double: MUFU.RSQ64H seed, two coupled (Goldschmidt) steps, residual fix.  ~1 ulp.
+BVG_HD double bvg_sqrtpos(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double g = x * r, h = 0.5 * r;
+  double e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  return fma(fma(-g, g, x), h, g);
+#else
+  return sqrt(x);
+#endif
+}
+
+// cos(2 pi u), sin(2 pi u) for u in (0, 1): the Box-Muller angle.  t = 4 u, q = rint(t) in {0..4}, phi = (pi / 2)(t - q)
+// in [-pi/4, pi/4]; sin(phi) and cos(phi) by their Taylor polynomials in phi^2, then a rotation by q quarter turns.
 BVG_HD void bvg_sincos2pi(double u, double* sn, double* cs) {
   const double t = 4.0 * u;
   const double qd = rint(t);
   const int q = (int)qd;
   const double x = (t - qd) * 1.5707963267948966;
   const double z = x * x;
-  double ps = 2.8114572543455206e-15;
-  ps = fma(ps, z, -7.647163731819816e-13);
-  ps = fma(ps, z, 1.6059043836821613e-10);
-  ps = fma(ps, z, -2.505210838544172e-08);
-  ps = fma(ps, z, 2.7557319223985893e-06);
-  ps = fma(ps, z, -0.0001984126984126984);
-  ps = fma(ps, z, 0.008333333333333333);
-  ps = fma(ps, z, -0.16666666666666666);
-  ps = fma(ps, z, 1.0);
-  double pc = -1.5619206968586225e-16;
-  pc = fma(pc, z, 4.779477332387385e-14);
-  pc = fma(pc, z, -1.1470745597729725e-11);
-  pc = fma(pc, z, 2.08767569878681e-09);
-  pc = fma(pc, z, -2.755731922398589e-07);
-  pc = fma(pc, z, 2.48015873015873e-05);
-  pc = fma(pc, z, -0.001388888888888889);
-  pc = fma(pc, z, 0.041666666666666664);
-  pc = fma(pc, z, -0.5);
-  pc = fma(pc, z, 1.0);
+  const double* ts = BVG_TAB(kSinTab);
+  const double* tc = BVG_TAB(kCosTab);
+  double ps = ts[8];
+  double pc = tc[9];
+  pc = fma(pc, z, tc[8]);
+  ps = fma(ps, z, ts[7]);
+  pc = fma(pc, z, tc[7]);
+  ps = fma(ps, z, ts[6]);
+  pc = fma(pc, z, tc[6]);
+  ps = fma(ps, z, ts[5]);
+  pc = fma(pc, z, tc[5]);
+  ps = fma(ps, z, ts[4]);
+  pc = fma(pc, z, tc[4]);
+  ps = fma(ps, z, ts[3]);
+  pc = fma(pc, z, tc[3]);
+  ps = fma(ps, z, ts[2]);
+  pc = fma(pc, z, tc[2]);
+  ps = fma(ps, z, ts[1]);
+  pc = fma(pc, z, tc[1]);
+  ps = fma(ps, z, ts[0]);
+  pc = fma(pc, z, tc[0]);
   const double s = x * ps, c = pc;
   const double a = (q & 1) ? s : c, b = (q & 1) ? c : s;           // |cos|, |sin| before the quadrant signs
   *cs = (((q + 1) >> 1) & 1) ? -a : a;                              // q = 0: c  1: -s  2: -c  3: s  4: c
   *sn = ((q >> 1) & 1) ? -b : b;                                    // q = 0: s  1: c   2: -s  3: -c 4: s
+}
+
+// Box-Muller: (u1, u2) in (0, 1)^2 -> two independent N(0, 1)
+BVG_HD void bvg_box_muller(double u1, double u2, double* a, double* b) {
+  const double r = bvg_sqrtpos(-2.0 * bvg_logpos(u1));
+  double sn, cs;
+  bvg_sincos2pi(u2, &sn, &cs);
+  *a = r * cs;
+  *b = r * sn;
 }
 
 // ---- random source of one chain ----------------------------------------------------------------------------
@@ -169,13 +279,8 @@ BVG_HD_NOINLINE double philox_uniform(uint64_t seed, uint64_t chain, int block, 
 // (counter index p).
 BVG_HD_NOINLINE Normal2 philox_normal_pair(uint64_t seed, uint64_t chain, int block, int sweep, int pair, int attempt) {
   const Philox4 p = philox_site(seed, chain, block, sweep, pair, attempt);
-  const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
-  const double r = sqrt(-2.0 * log(u1));
   Normal2 o;
-  double sn, cs;
-  bvg_sincos2pi(u2, &sn, &cs);
-  o.a = r * cs;
-  o.b = r * sn;
+  bvg_box_muller(u53(p.x, p.y), u53(p.z, p.w), &o.a, &o.b);
   return o;
 }
 // Two independent pairs at once (two chains / two sites): the two Philox + log + sincospi dependency chains are
@@ -185,27 +290,16 @@ BVG_HD_NOINLINE Normal4 philox_normal_pair_x2(uint64_t seed, uint64_t chain_a, i
                                               uint64_t chain_b, int block_b, int sweep_b, int pair_b) {
   const Philox4 pa = philox_site(seed, chain_a, block_a, sweep_a, pair_a, 0);
   const Philox4 pb = philox_site(seed, chain_b, block_b, sweep_b, pair_b, 0);
-  const double ua1 = u53(pa.x, pa.y), ua2 = u53(pa.z, pa.w);
-  const double ub1 = u53(pb.x, pb.y), ub2 = u53(pb.z, pb.w);
-  const double la = log(ua1), lb = log(ub1);
-  const double ra = sqrt(-2.0 * la), rb = sqrt(-2.0 * lb);
   Normal4 o;
-  double sa, ca, sb, cb;
-  bvg_sincos2pi(ua2, &sa, &ca);
-  bvg_sincos2pi(ub2, &sb, &cb);
-  o.p.a = ra * ca;
-  o.q.a = rb * cb;
-  o.p.b = ra * sa;
-  o.q.b = rb * sb;
+  bvg_box_muller(u53(pa.x, pa.y), u53(pa.z, pa.w), &o.p.a, &o.p.b);
+  bvg_box_muller(u53(pb.x, pb.y), u53(pb.z, pb.w), &o.q.a, &o.q.b);
   return o;
 }
 BVG_HD_NOINLINE double philox_normal(uint64_t seed, uint64_t chain, int block, int sweep, int idx, int attempt) {
   const Philox4 p = philox_site(seed, chain, block, sweep, idx >> 1, attempt);
-  const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
-  const double r = sqrt(-2.0 * log(u1));
-  double sn, cs;
-  bvg_sincos2pi(u2, &sn, &cs);
-  return (idx & 1) ? r * sn : r * cs;
+  double a, b;
+  bvg_box_muller(u53(p.x, p.y), u53(p.z, p.w), &a, &b);
+  return (idx & 1) ? b : a;
 }
 // Gamma(shape, 1), Marsaglia-Tsang 2000 (shape < 1 boosted); attempts are separate sites.  `x0` is the N(0,1) of
 // attempt 0, i.e. philox_normal(.., idx, 0): callers may draw it earlier together with other normals so that all
@@ -223,10 +317,8 @@ BVG_HD_NOINLINE double philox_gamma_from_x0(uint64_t seed, uint64_t chain, int b
   for (int attempt = 0; attempt < 100; ++attempt) {
     if (attempt > 0) {
       const Philox4 p = philox_site(seed, chain, block, sweep, idx, attempt);
-      const double u1 = u53(p.x, p.y), u2 = u53(p.z, p.w);
-      double sn, cs;
-      bvg_sincos2pi(u2, &sn, &cs);
-      x = sqrt(-2.0 * log(u1)) * cs;
+      double xb;
+      bvg_box_muller(u53(p.x, p.y), u53(p.z, p.w), &x, &xb);
     }
     double v = 1.0 + c * x;
     if (v <= 0.0) continue;
@@ -235,7 +327,7 @@ BVG_HD_NOINLINE double philox_gamma_from_x0(uint64_t seed, uint64_t chain, int b
     const double u = u53(q.x, q.y);
     const double x2 = x * x;
     if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * v;       // squeeze: sufficient for the test below, no logs
-    if (log(u) < 0.5 * x2 + d - d * v + d * log(v)) return boost * d * v;
+    if (bvg_logpos(u) < 0.5 * x2 + d - d * v + d * bvg_logpos(v)) return boost * d * v;
   }
   return boost * d;   // unreachable in practice (acceptance > 95 %)
 }
