@@ -304,6 +304,35 @@ class Ctx:
             self.dist.destroy_process_group()
 
 
+def d2h_ceiling(ctx, nbytes):
+    """Bare device -> pinned-host copy rate of this box: one cudaMemcpyAsync per copy on the bench stream, every rank at
+    the same time (max over ranks), nothing else running.  The end-to-end arm cannot beat it; `frac_of_ceiling` in the
+    e2e record says how close it gets."""
+    torch = ctx.torch
+    size = int(min(max(nbytes, 1 << 26), 2 << 30))
+    try:
+        host = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+        dev = torch.empty(size, dtype=torch.uint8, device=ctx.dev)
+    except Exception as exc:
+        return {"error": str(exc)}
+    dev.zero_()
+    with torch.cuda.stream(ctx.stream):
+        host.copy_(dev, non_blocking=True)
+    ctx.fence()
+    reps = 4
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ctx.stream)
+    with torch.cuda.stream(ctx.stream):
+        for _ in range(reps):
+            host.copy_(dev, non_blocking=True)
+    e1.record(ctx.stream)
+    ctx.fence()
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / reps
+    del host, dev
+    return {"GBps_per_gpu": size / ms / 1e6, "GBps_all_gpus": ctx.world * size / ms / 1e6, "bytes_per_copy": size,
+            "what": "plain cudaMemcpyAsync device -> pinned host, one copy at a time per rank, all ranks concurrently"}
+
+
 def timed_steps(ctx, step, steps, warmup, clocks=None):
     """W untimed + K timed steps bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks."""
     torch = ctx.torch
@@ -468,6 +497,11 @@ def run_sampler_workload(ctx, args, name, steps, warmup, chains=None, headline=F
                "checksum": checksum}
         chains = chains_full
         del host
+        if headline:
+            ceil = d2h_ceiling(ctx, d2h)
+            e2e["d2h_ceiling"] = ceil
+            if ceil.get("GBps_per_gpu"):
+                e2e["frac_of_ceiling"] = e2e["d2h_GBps_per_gpu"] / ceil["GBps_per_gpu"]
     else:
         sampler.close()
     if ctx.rank != 0:

@@ -1,25 +1,28 @@
 // bvg_kern_kron.cu -- sm_100a kernel of the flat-prior Kronecker sweep (bvg_kron_sweep.cuh): configs c1 / c2.
 //
 // Everything random in this sweep is independent of the chain state, and the state recursion is a handful of
-// k x k products.  A CTA owns CH chains and works in rounds of NB sweeps; one round q does
-//   1  (threads < CH, one THREAD per chain, W in registers) the state recursion W <- U(S0 + SSE + W E E' W') A_B^-1 of
-//      the sweeps of round q: latency-bound, ~150 dependent instructions per sweep; W before / after the step are left
-//      in the record of the sweep (over the G / A_B^-1 slots it has just consumed);
-//   G  (all warps; the recursion warp joins when it is done) the variates of round q + 1, as warp-sized work units
-//      handed out through a shared-memory counter.  A unit is (two variate SLOTS) x (32 records): the slot -- Philox
-//      counter word, variate block, the two destinations of a Box-Muller pair inside the record -- is warp-uniform and
-//      comes from a small descriptor table, so that a lane runs nothing but Philox4x32-10 with constant-bank round keys,
-//      the FP64 transforms of bvg_common.cuh (two independent dependency chains per lane) and four STS.  Chi-square units
-//      (one lane per record) draw the Bartlett diagonal: Marsaglia-Tsang with the constants d, c of each diagonal
-//      position precomputed, the attempt-0 acceptance test inline, the rare rejection through the generic generator;
-//   -- barrier --
-//   2  one thread per record: state-independent products of round q + 1 (G = E E', A_B^-1, T = E L_X^-1 in place;
-//      E in registers when M is one of the compile-time shapes) and the retained draws of round q
-//      (a = vec(A_ols + W T), Sigma = W W') written DENSE per chain into a staging buffer;
-//   -- barrier --
-//   3  thread c hands the staged draws of chain c to the copy engine: two cp.async.bulk (shared -> global) per chain
-//      and round, nk n and nk k^2 consecutive doubles (16-byte alignment permitting; a plain coalesced copy otherwise).
-// Variates live in shared memory (double-buffered records), HBM sees only the draws.
+// k x k products.  A CTA owns CH chains and works in rounds of NB sweeps; the CH x NB records of a round (one record =
+// the variates / products of one sweep of one chain, in shared memory) are split into CHUNKS of 32 records (32 / NB
+// chains x NB sweeps), and the warps have fixed roles:
+//   warp 0     the state recursion W <- U(S0 + SSE + W E E' W') A_B^-1, one LANE per chain with W in registers:
+//              latency-bound (~150 dependent instructions per sweep, three rsqrt chains), so nothing else runs on it; the
+//              W a sweep starts from and ends with are left in its record (over the G / A_B^-1 slots just consumed);
+//   warp 1     one round behind: the retained draws a = vec(A_ols + W T), Sigma = W W', one lane per chain, written
+//              straight to the [chain][iter][row] output (consecutive sweeps of a chain are consecutive in memory; the
+//              partial sectors of neighbouring stores merge in L2 -- profiles/r02_c2a_*: DRAM bytes = algorithmic bytes).
+//              Staging the draws in shared memory for cp.async.bulk copies was measured and dropped: one bulk copy per
+//              chain and array is ~30 instructions of address set-up + R2UR per 0.7 KB, slower than the stores;
+//   warps 2 + 2 j, 3 + 2 j   the variates of chunk j, one lane per record, FIXED for the whole launch: chain id, Philox
+//              counter words and record address are computed once; a round is a uniform loop over variate SLOTS (Philox
+//              counter word, block, the two destinations of a Box-Muller pair), four slots in flight per lane:
+//              Philox4x32-10 with constant-bank round keys + the FP64 transforms of bvg_common.cuh.  The A warp draws
+//              the first SA slots; the B warp the rest and, after a 64-thread named barrier with A, the Bartlett
+//              diagonal (Marsaglia-Tsang, constants precomputed, the attempt-0 test inline, rejections through the
+//              generic generator) and the state-independent products of the chunk (G = E E', A_B^-1, T = E L_X^-1).
+// Rounds are pipelined over three record generations: the generators run up to two rounds ahead of the recursion.  All
+// cross-role hand-offs are mbarriers in shared memory (arrive = release, try_wait = acquire, waiting warps are parked by
+// the hardware); there is no CTA-wide barrier after the set-up.  HBM sees only the draws.
+#include <type_traits>
 #include "bvg_kernels.cuh"
 #include "bvg_kron_sweep.cuh"
 
@@ -33,17 +36,8 @@ struct KronPlanDims {
   int NB;      // sweeps per round
   int VL;      // doubles per record (odd)
   int CS;      // record stride between chains (odd): record (c, sw) at c CS + sw VL
-  int SC, SG;  // staging strides per chain (even): coefficients, Sigma
-  int skip0;   // 1: the warps 4, 8, 12 (scheduler of the recursion warp) do not work
+  int SA;      // variate slots drawn by the A warp of a chunk
   uint32_t rk[20];   // Philox round keys: (k0 + r W0, k1 + r W1), r = 0..9
-};
-
-// x / d for x * d < 2^32 by one multiply-high
-struct FastDiv {
-  unsigned d, mg;
-  __host__ __device__ explicit FastDiv(unsigned dd) : d(dd), mg(dd > 1 ? 0xFFFFFFFFu / dd + 1u : 0u) {}   // ceil(2^32 / d)
-  __device__ __forceinline__ unsigned div(unsigned x) const { return d == 1 ? x : __umulhi(x, mg); }
-  __device__ __forceinline__ void divmod(unsigned x, unsigned& q, unsigned& r) const { q = div(x); r = x - q * d; }
 };
 
 // Philox4x32-10 with the round keys as constant-bank operands of the xor (no key schedule in the instruction stream)
@@ -134,10 +128,26 @@ __device__ __forceinline__ void kron_coef_to(const double* Wp, const double* tv,
   }
 }
 
-__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
-               : "memory");
+// mbarrier hand-offs (shared memory, CTA scope): arrive = release, wait = acquire; waiting warps are parked by the hardware
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+#ifdef BVG_KRON_HINT
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 2000;\n\t"
+#else
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+#endif
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+      : "memory");
 }
 
 template <int K>
@@ -146,19 +156,20 @@ __global__ void __launch_bounds__(512, BVG_KRON_MINB) bvar_kron_batch_kernel(
     const __grid_constant__ BvarOut out, long long n_chains, int s0, int s1, int burnin,
     const __grid_constant__ KronPlanDims pd) {
   extern __shared__ __align__(16) double smem[];
-  __shared__ int work_ctr[1];
-  __shared__ int flags[2];      // [0] rounds prepared, [1] rounds through the recursion (monotone; polled)
+  // hand-offs, one pair per record generation: prep_bar[g] completes when every chunk of a round in generation g is
+  // prepared (one arrival per B warp), rec_bar[g] when the recursion is through it, out_bar[g] when its draws are written
+  // and the records may be overwritten (one arrival each)
+  __shared__ uint64_t prep_bar[3], rec_bar[3], out_bar[3];
   constexpr int KU = (K * (K + 1)) / 2, NW = (K * (K - 1)) / 2, KK = K * K;
   constexpr int PW = (NW + 1) / 2, PX = (K + 1) / 2;
   const int M = m.M, n = K * M, CH = pd.CH, NB = pd.NB, VL = pd.VL, CS = pd.CS;
   const int PC = (n + 1) >> 1;
-  const int NT = blockDim.x, tid = threadIdx.x, lane = tid & 31;
-  // ---- record layout: eps (2 PC) | Bartlett normals (2 PW) | G (KU) | A_B^-1 (KU); the chi-square slots overlay G
-  const int o_wn = 2 * PC, o_G = o_wn + 2 * PW, o_Ai = o_G + KU, o_chi = o_G;
-  // ---- shared memory: staging (coef [CH][SC], Sigma [CH][SG]) | records [3][CH CS] | constants | MT constants
-  double* st_coef = smem;
-  double* st_sig = st_coef + (size_t)CH * pd.SC;
-  double* var = st_sig + (size_t)CH * pd.SG;
+  const int NT = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- record layout: eps (2 PC) | G (KU) | A_B^-1 (KU) [| pad]; until the chunk is prepared the tail holds the
+  //      Bartlett normals (2 PW, at o_wn) and the attempt-0 normals of the Bartlett diagonal (2 PX, at o_x0)
+  const int o_G = 2 * PC, o_Ai = o_G + KU, o_wn = o_G, o_x0 = o_G + 2 * PW;
+  // ---- shared memory: records [3][CH CS] | constants | MT constants
+  double* var = smem;
   double* p = var + 3 * (size_t)CH * CS;
   KronConsts cs;
   {
@@ -176,150 +187,32 @@ __global__ void __launch_bounds__(512, BVG_KRON_MINB) bvar_kron_batch_kernel(
     mt[2 * tid] = d;
     mt[2 * tid + 1] = 1.0 / sqrt(9.0 * d);
   }
-  // slot descriptor: x = Philox counter word 0 (pair index), y = block << 24, z / w = destinations of the pair members
-  const int NSL = PC + PW;                    // Box-Muller slots of the pair units
-  const int NSLP = (NSL + 1) >> 1;            // slot pairs (the last one may repeat its first member)
-  auto slot_of = [&](int s) {
-    int4 d;
-    if (s < PC) { d.x = s; d.y = VB_COEF_N << 24; d.z = 2 * s; d.w = 2 * s + 1; }
-    else { d.x = s - PC; d.y = VB_WISH_N << 24; d.z = o_wn + 2 * (s - PC); d.w = d.z + 1; }
-    return d;
-  };
-  const FastDiv dNB((unsigned)NB);
-  auto div_of = [&](int x) { return (x == NB) ? dNB : FastDiv((unsigned)(x > 0 ? x : 1)); };
   const long long chain0 = (long long)blockIdx.x * CH;
   const int CHv = (int)((n_chains - chain0 < CH) ? (n_chains - chain0) : CH);   // valid chains of this CTA
-  const uint64_t chain_g0 = rp.chain_offset + (uint64_t)chain0;
-  const bool inj_coef = rp.inj[VB_COEF_N] != nullptr, inj_wn = rp.inj[VB_WISH_N] != nullptr;
-  const bool inj_chi = rp.inj[VB_WISH_C] != nullptr;
-
-  // records r = c nb + sw of a round of nb sweeps
-  // ---- G: variates of the sweeps [b0, b0 + nb) into record buffer `buf`
-  auto gen_variates = [&](int b0, int nb, int buf) {
-    const int R = CHv * nb, RW = (R + 31) >> 5;
-    const int n_units = RW * (1 + NSLP);                       // chi-square units first (they hold the divergent code)
-    const FastDiv dnb = div_of(nb), dRW((unsigned)RW);
-    double* vb = var + (size_t)buf * CH * CS;
-    for (;;) {
-      int unit = 0;
-      if (lane == 0) unit = atomicAdd(&work_ctr[0], 1);
-      unit = __shfl_sync(0xffffffffu, unit, 0);
-      if (unit >= n_units) break;
-      unsigned uq, ur;
-      dRW.divmod((unsigned)unit, uq, ur);
-      const int sp = (int)uq - 1;                              // -1: chi-square unit; else slot pair
-      int r = (int)ur * 32 + lane;
-      if (r >= R) r = R - 1;                                   // (idle lanes repeat the last record)
-      unsigned c, sw;
-      dnb.divmod((unsigned)r, c, sw);
-      double* rec = vb + c * (unsigned)CS + sw * (unsigned)VL;
-      const int sweep = b0 + (int)sw;
-      const uint64_t chain = chain_g0 + c;
-      const uint32_t c2 = (uint32_t)chain, c3 = (uint32_t)(chain >> 32);
-      if (sp < 0) {
-        // ---- Bartlett diagonal: sqrt(chi2(df - i)), i < K
-        if (inj_chi) {
-#pragma unroll
-          for (int i = 0; i < K; ++i)
-            rec[o_chi + i] = sqrt(rp.inj[VB_WISH_C][(size_t)(chain0 + c) * (size_t)rp.inj_chain_stride[VB_WISH_C] +
-                                                    (size_t)sweep * (size_t)rp.inj_stride[VB_WISH_C] + i]);
-          continue;
-        }
-        double x0[2 * PX];
-#pragma unroll
-        for (int q = 0; q < PX; ++q) {                          // attempt-0 normals: pairs q of block VB_WISH_C
-          const Philox4 ph = philox_rk((uint32_t)q, (uint32_t)sweep, c2, c3 ^ ((uint32_t)VB_WISH_C << 24), pd.rk);
-          bvg_box_muller(u53(ph.x, ph.y), u53(ph.z, ph.w), &x0[2 * q], &x0[2 * q + 1]);
-        }
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-          const double d = mt[2 * i], cc = mt[2 * i + 1], x = x0[i];
-          const Philox4 ph = philox_rk((uint32_t)i | (100u << 24), (uint32_t)sweep, c2, c3 ^ ((uint32_t)VB_WISH_C << 24), pd.rk);
-          const double u = u53(ph.x, ph.y);
-          const double v1 = fma(cc, x, 1.0), v = v1 * v1 * v1, x2 = x * x;
-          bool ok = false;
-          if (v1 > 0.0 && d > 2.0 / 3.0) {                      // (shape >= 1: no boost step)
-            ok = u < 1.0 - 0.0331 * x2 * x2;
-            if (!ok) ok = bvg_logpos(u) < 0.5 * x2 + d - d * v + d * bvg_logpos(v);
-          }
-          double g = d * v;
-          if (!ok) g = philox_gamma_from_x0(rp.seed, chain, VB_WISH_C, sweep, i, 0.5 * (m.wish_df_post - (double)i), x);
-          rec[o_chi + i] = bvg_sqrtpos(2.0 * g);
-        }
-        continue;
-      }
-      // ---- two Box-Muller slots of the record
-      const int sa = 2 * sp, sb = (2 * sp + 1 < NSL) ? 2 * sp + 1 : 2 * sp;
-      const int4 da = slot_of(sa), db = slot_of(sb);
-      if (inj_coef || inj_wn) {
-        auto one = [&](const int4& d) {
-          const int blk = d.y >> 24, cnt = (blk == VB_COEF_N) ? n : NW;
-          if (rp.inj[blk] != nullptr) {
-            const double* src = rp.inj[blk] + (size_t)(chain0 + c) * (size_t)rp.inj_chain_stride[blk] +
-                                (size_t)sweep * (size_t)rp.inj_stride[blk];
-            rec[d.z] = src[2 * d.x];
-            rec[d.w] = (2 * d.x + 1 < cnt) ? src[2 * d.x + 1] : 0.0;
-          } else {
-            const Philox4 ph = philox_rk((uint32_t)d.x, (uint32_t)sweep, c2, c3 ^ (uint32_t)d.y, pd.rk);
-            bvg_box_muller(u53(ph.x, ph.y), u53(ph.z, ph.w), &rec[d.z], &rec[d.w]);
-          }
-        };
-        one(da);
-        one(db);
-        continue;
-      }
-      const Philox4 pa = philox_rk((uint32_t)da.x, (uint32_t)sweep, c2, c3 ^ (uint32_t)da.y, pd.rk);
-      const Philox4 pb = philox_rk((uint32_t)db.x, (uint32_t)sweep, c2, c3 ^ (uint32_t)db.y, pd.rk);
-      double a0, a1, b0v, b1v;
-      bvg_box_muller(u53(pa.x, pa.y), u53(pa.z, pa.w), &a0, &a1);
-      bvg_box_muller(u53(pb.x, pb.y), u53(pb.z, pb.w), &b0v, &b1v);
-      rec[da.z] = a0;
-      rec[da.w] = a1;
-      rec[db.z] = b0v;
-      rec[db.w] = b1v;
+  const int CPC = 32 / NB;                                                      // chains per chunk
+  const int NCHv = (CHv + CPC - 1) / CPC;                                       // valid chunks
+  if (tid == 0) {
+    for (int g = 0; g < 3; ++g) {
+      mbar_init(&prep_bar[g], (unsigned)NCHv);
+      mbar_init(&rec_bar[g], 1u);
+      mbar_init(&out_bar[g], 1u);
     }
-  };
-  // ---- 2a: state-independent products of record `it` of buffer `buf` (round of nb sweeps)
-  auto prep = [&](int it, const FastDiv& dnb, int buf) {
-    unsigned c, sw;
-    dnb.divmod((unsigned)it, c, sw);
-    double* v = var + (size_t)buf * CH * CS + c * (unsigned)CS + sw * (unsigned)VL;
-    double chi[K], wn[NW > 0 ? NW : 1];
-#pragma unroll
-    for (int i = 0; i < K; ++i) chi[i] = v[o_chi + i];
-#pragma unroll
-    for (int i = 0; i < NW; ++i) wn[i] = v[o_wn + i];
-    if (K * M <= 40 && M == 2 * K + 1) kron_prep_regs<K, 2 * K + 1>(v, wn, chi, cs.Linv, v + o_G, v + o_Ai);
-    else if (K * M <= 40 && M == K + 1) kron_prep_regs<K, K + 1>(v, wn, chi, cs.Linv, v + o_G, v + o_Ai);
-    else if (K * M <= 40 && M == 4 * K + 1) kron_prep_regs<K, (K * (4 * K + 1) <= 40) ? 4 * K + 1 : 1>(v, wn, chi, cs.Linv, v + o_G, v + o_Ai);
-    else if (K * M <= 40 && M == 3 * K + 1) kron_prep_regs<K, (K * (3 * K + 1) <= 40) ? 3 * K + 1 : 1>(v, wn, chi, cs.Linv, v + o_G, v + o_Ai);
-    else {
-      kron_prep<K>(v, wn, chi, M, v + o_G, v + o_Ai);
-      kron_t_inplace<K>(v, cs.Linv, M);
-    }
-  };
-
-  if (tid == 0) { work_ctr[0] = 0; flags[0] = 0; flags[1] = 0; }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
-  // ---- roles: warp 0 runs the state recursion; the workers generate, prepare and write; with pd.skip0 the other warps of
-  //      warp 0's scheduler (warp id % 4 == 0) stay out of it, so that the latency-bound recursion has its issue slots
-  const int warp = tid >> 5, n_warps = NT >> 5;
-  const int n_workers = (n_warps - 1) - (pd.skip0 ? (n_warps - 1) / 4 : 0);
-  const int wi = warp - 1 - (pd.skip0 ? warp / 4 : 0);        // worker rank of this warp
-  const int WT = n_workers * 32, wt = wi * 32 + lane;
   const int n_rounds = (s1 - s0 + NB - 1) / NB;
-  auto round_b0 = [&](int q) { return s0 + q * NB; };
-  auto round_nb = [&](int q) { return (q < 0 || q >= n_rounds) ? 0 : ((s1 - round_b0(q) < NB) ? (s1 - round_b0(q)) : NB); };
+  auto round_nb = [&](int q) { return (s1 - (s0 + q * NB) < NB) ? (s1 - (s0 + q * NB)) : NB; };
 
   if (warp == 0) {
-    // ================= state recursion: round q as soon as its records are prepared =================
+    // ================= state recursion =================
     double W[K][K], SSu[K][K];
     int fail = 0;
 #pragma unroll
     for (int i = 0; i < K; ++i)
 #pragma unroll
       for (int j = 0; j < K; ++j) SSu[i][j] = m.kron_SS[i + K * j];
-    if (tid < CHv) {
+    const bool act = tid < CHv;
+    if (act) {
       const double* st = state + (size_t)(chain0 + tid) * state_len;
 #pragma unroll
       for (int i = 0; i < K; ++i)
@@ -327,12 +220,9 @@ __global__ void __launch_bounds__(512, BVG_KRON_MINB) bvar_kron_batch_kernel(
         for (int j = 0; j < K; ++j) W[i][j] = (i <= j) ? st[i + K * j] : 0.0;
     }
     for (int q = 0; q < n_rounds; ++q) {
-      if (lane == 0)
-        while (*(volatile int*)&flags[0] < q + 1) __nanosleep(20);
-      __syncwarp();
-      __threadfence_block();
+      mbar_wait(&prep_bar[q % 3], (unsigned)((q / 3) & 1));
       const int nb = round_nb(q);
-      if (tid < CHv) {
+      if (act) {
         double* rec = var + (size_t)(q % 3) * CH * CS + tid * CS;
         double Gp[KU], Aip[KU];
 #pragma unroll
@@ -341,25 +231,24 @@ __global__ void __launch_bounds__(512, BVG_KRON_MINB) bvar_kron_batch_kernel(
 #pragma unroll
           for (int j = 0; j < K; ++j)
 #pragma unroll
-            for (int i = 0; i <= j; ++i) rec[o_Ai + tri(j) + i] = W[i][j];          // W used by this sweep
-          double Gn[KU], Ain[KU];                                                 // next sweep's inputs: loads in flight
-          const double* nx = rec + ((sw + 1 < nb) ? VL : 0);                      //   during this sweep's dependent chain
+            for (int i = 0; i <= j; ++i) rec[o_Ai + tri(j) + i] = W[i][j];        // W this sweep starts from
+          double Gn[KU], Ain[KU];                              // next sweep's inputs: loads in flight during this
+          const double* nx = rec + ((sw + 1 < nb) ? VL : 0);   //   sweep's dependent chain
 #pragma unroll
           for (int e = 0; e < KU; ++e) { Gn[e] = nx[o_G + e]; Ain[e] = nx[o_Ai + e]; }
           kron_step_core<K>(W, Gp, Aip, SSu, fail);
 #pragma unroll
           for (int j = 0; j < K; ++j)
 #pragma unroll
-            for (int i = 0; i <= j; ++i) rec[o_G + tri(j) + i] = W[i][j];           // W after this sweep
+            for (int i = 0; i <= j; ++i) rec[o_G + tri(j) + i] = W[i][j];         // W after this sweep
 #pragma unroll
           for (int e = 0; e < KU; ++e) { Gp[e] = Gn[e]; Aip[e] = Ain[e]; }
         }
       }
-      __threadfence_block();
       __syncwarp();
-      if (lane == 0) *(volatile int*)&flags[1] = q + 1;
+      if (lane == 0) mbar_arrive(&rec_bar[q % 3]);
     }
-    if (tid < CHv) {
+    if (act) {
       double* st = state + (size_t)(chain0 + tid) * state_len;
 #pragma unroll
       for (int i = 0; i < K; ++i)
@@ -369,83 +258,155 @@ __global__ void __launch_bounds__(512, BVG_KRON_MINB) bvar_kron_batch_kernel(
     }
     return;
   }
-  if (wi < 0 || (pd.skip0 && (warp & 3) == 0)) return;         // (idle warps of the recursion warp's scheduler)
 
-  // ================= workers: iteration q generates and prepares round q + 2 and writes round q =================
-  bool bulk_pending = false, bulk_any = false;
-  for (int q = -2; q < n_rounds; ++q) {
-    const int r2 = q + 2, nb2 = round_nb(r2);
-    if (nb2 > 0) gen_variates(round_b0(r2), nb2, r2 % 3);
-    if (bulk_pending) {                                        // the staging buffer is rewritten after the barrier
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      bulk_pending = false;
-    }
-    asm volatile("bar.sync 1, %0;" ::"r"(WT) : "memory");
-    if (wt == 0) work_ctr[0] = 0;
-    // ---- 2a: state-independent products of round q + 2
-    {
-      const int n_prep = CHv * nb2;
-      const FastDiv d2 = div_of(nb2);
-      for (int it = wt; it < n_prep; it += WT) prep(it, d2, r2 % 3);
-    }
-    // ---- 2b: draws of round q (its recursion has to be through -- also before round q + 3 may overwrite the records)
-    const int b0 = round_b0(q), nb = round_nb(q), b1 = b0 + nb;
-    const int k0 = (b0 > burnin) ? b0 : burnin;                // first retained sweep of the round
-    const int nk = (q >= 0 && b1 > k0) ? b1 - k0 : 0, sw0 = k0 - b0;
-    if (q >= 0) {
-      if (lane == 0)
-        while (*(volatile int*)&flags[1] < q + 1) __nanosleep(64);
-      __syncwarp();
-      __threadfence_block();
-    }
-    if (nk > 0) {
-      const int n_out = CHv * nk;
-      const FastDiv dnk = div_of(nk);
-      const double* vb = var + (size_t)(q % 3) * CH * CS;
-      for (int it = wt; it < n_out; it += WT) {
-        unsigned c, swu;
-        dnk.divmod((unsigned)it, c, swu);
-        const double* v = vb + c * (unsigned)CS + (sw0 + swu) * (unsigned)VL;
-        double* dc = st_coef + c * (unsigned)pd.SC + swu * (unsigned)n;
-        if (M == 2 * K + 1) kron_coef_to<K, 2 * K + 1>(v + o_Ai, v, cs.Aols, M, dc);
-        else if (M == K + 1) kron_coef_to<K, K + 1>(v + o_Ai, v, cs.Aols, M, dc);
-        else kron_coef_to<K, 0>(v + o_Ai, v, cs.Aols, M, dc);
-        kron_sigma<K>(v + o_G, st_sig + c * (unsigned)pd.SG + swu * (unsigned)KK);
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged draws -> visible to the copy engine
-    }
-    asm volatile("bar.sync 1, %0;" ::"r"(WT) : "memory");
-    if (wt == 0 && nb2 > 0) {
-      __threadfence_block();
-      *(volatile int*)&flags[0] = r2 + 1;                      // rounds <= q + 2 are prepared
-    }
-    // ---- 3: staged draws to the [chain][iter][row] output
-    if (nk > 0) {
-      const long long pos0 = (long long)k0 - burnin;
-      // 16-byte alignment of every chain's destination and size (chains differ by iters * n doubles)
-      const bool al_c = (((size_t)out.iters * (size_t)n) % 2 == 0 || CHv == 1) && ((nk * n) % 2 == 0) &&
-                        ((reinterpret_cast<uintptr_t>(out.coef + ((size_t)chain0 * (size_t)out.iters + (size_t)pos0) * (size_t)n)) % 16 == 0);
-      const bool al_s = (((size_t)out.iters * (size_t)KK) % 2 == 0 || CHv == 1) && ((nk * KK) % 2 == 0) &&
-                        ((reinterpret_cast<uintptr_t>(out.sigma + ((size_t)chain0 * (size_t)out.iters + (size_t)pos0) * (size_t)KK)) % 16 == 0);
-      for (int c = wi; c < CHv; c += n_workers) {              // one warp per chain: uniform addresses for the bulk copies
-        double* dstc = out.coef + ((size_t)(chain0 + c) * (size_t)out.iters + (size_t)pos0) * (size_t)n;
-        double* dsts = out.sigma + ((size_t)(chain0 + c) * (size_t)out.iters + (size_t)pos0) * (size_t)KK;
-        const double* srcc = st_coef + c * pd.SC;
-        const double* srcs = st_sig + c * pd.SG;
-        if (lane == 0 && (al_c || al_s)) {
-          if (al_c) bulk_store(dstc, srcc, (unsigned)(nk * n * 8));
-          if (al_s) bulk_store(dsts, srcs, (unsigned)(nk * KK * 8));
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          bulk_pending = bulk_any = true;
+  if (warp == 1) {
+    // ================= retained draws, one round behind the recursion: lane = chain =================
+    const bool act = tid - 32 < CHv;
+    const int c = act ? tid - 32 : 0;
+    const long long first_keep = (s0 > burnin) ? (long long)s0 - burnin : 0;   // output position of this launch's first draw
+    double* oc = out.coef + ((size_t)(chain0 + c) * (size_t)out.iters + (size_t)first_keep) * (size_t)n;
+    double* os = out.sigma + ((size_t)(chain0 + c) * (size_t)out.iters + (size_t)first_keep) * (size_t)KK;
+    for (int q = 0; q < n_rounds; ++q) {
+      mbar_wait(&rec_bar[q % 3], (unsigned)((q / 3) & 1));
+      const int nb = round_nb(q), b0 = s0 + q * NB;
+      if (act) {
+        const double* rec = var + (size_t)(q % 3) * CH * CS + c * CS;
+        for (int sw = 0; sw < nb; ++sw, rec += VL) {
+          if (b0 + sw < burnin) continue;
+          if (M == 2 * K + 1) kron_coef_to<K, 2 * K + 1>(rec + o_Ai, rec, cs.Aols, M, oc);   // a = vec(A_ols + W T)
+          else if (M == K + 1) kron_coef_to<K, K + 1>(rec + o_Ai, rec, cs.Aols, M, oc);
+          else kron_coef_to<K, 0>(rec + o_Ai, rec, cs.Aols, M, oc);
+          kron_sigma<K>(rec + o_G, os);                                                      // Sigma = W W', W after the sweep
+          oc += n;
+          os += KK;
         }
-        if (!al_c)
-          for (int e = lane; e < nk * n; e += 32) dstc[e] = srcc[e];
-        if (!al_s)
-          for (int e = lane; e < nk * KK; e += 32) dsts[e] = srcs[e];
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&out_bar[q % 3]);
+    }
+    return;
+  }
+
+  // ================= variates and state-independent products of chunk j: lane = record =================
+  const int j = (warp - 2) >> 1;
+  const bool isB = (warp & 1) != 0;
+  if (j * CPC >= CHv) return;                                  // (both warps of an empty chunk)
+  int c = j * CPC + lane / NB;
+  const int sw_l = lane & (NB - 1);
+  const bool dup_c = c >= CHv;                                 // lanes past the last chain repeat its records
+  if (dup_c) c = CHv - 1;
+  const uint64_t chain = rp.chain_offset + (uint64_t)(chain0 + c);
+  const uint32_t c2 = (uint32_t)chain, c3 = (uint32_t)(chain >> 32);
+  const bool inj_coef = rp.inj[VB_COEF_N] != nullptr, inj_wn = rp.inj[VB_WISH_N] != nullptr;
+  const bool inj_chi = rp.inj[VB_WISH_C] != nullptr;
+  const int NSL = PC + PW + PX;                                // Box-Muller slots: coefficient normals, Bartlett normals,
+                                                               //   attempt-0 normals of the Bartlett diagonal
+  const int SA = pd.SA < NSL ? pd.SA : NSL;                    // slots [0, SA) on the A warp, the rest on B
+  // slot: x = Philox counter word 0 (pair index), y = block << 24, z / w = destinations of the pair members
+  auto slot_of = [&](int s) {
+    int4 d;
+    if (s < PC) { d.x = s; d.y = VB_COEF_N << 24; d.z = 2 * s; d.w = 2 * s + 1; }
+    else if (s < PC + PW) { d.x = s - PC; d.y = VB_WISH_N << 24; d.z = o_wn + 2 * (s - PC); d.w = d.z + 1; }
+    else { d.x = s - PC - PW; d.y = VB_WISH_C << 24; d.z = o_x0 + 2 * (s - PC - PW); d.w = d.z + 1; }  // x0 of chi i at o_x0 + i
+    return d;
+  };
+  for (int q = 0; q < n_rounds; ++q) {
+    if (q >= 3) mbar_wait(&out_bar[q % 3], (unsigned)((q / 3 - 1) & 1));      // round q - 3 (same generation) is written out
+    const int nb = round_nb(q);
+    const bool dup = dup_c || sw_l >= nb;                      // (tail round: lanes past its last sweep repeat it)
+    const int sw = (sw_l < nb) ? sw_l : nb - 1;
+    const int sweep = s0 + q * NB + sw;
+    double* rec = var + (size_t)(q % 3) * CH * CS + c * CS + sw * VL;
+    const int sb = isB ? SA : 0, se = isB ? NSL : SA;
+    if (inj_coef || inj_wn || inj_chi) {
+      for (int s = sb; s < se; ++s) {
+        const int4 d = slot_of(s);
+        const int blk = d.y >> 24, cnt = (blk == VB_COEF_N) ? n : NW;
+        if (rp.inj[blk] != nullptr) {
+          if (blk == VB_WISH_C) continue;                      // (injected chi-squares are read below)
+          const double* src = rp.inj[blk] + (size_t)(chain0 + c) * (size_t)rp.inj_chain_stride[blk] +
+                              (size_t)sweep * (size_t)rp.inj_stride[blk];
+          rec[d.z] = src[2 * d.x];
+          rec[d.w] = (2 * d.x + 1 < cnt) ? src[2 * d.x + 1] : 0.0;
+        } else {
+          const Philox4 ph = philox_rk((uint32_t)d.x, (uint32_t)sweep, c2, c3 ^ (uint32_t)d.y, pd.rk);
+          bvg_box_muller(u53(ph.x, ph.y), u53(ph.z, ph.w), &rec[d.z], &rec[d.w]);
+        }
+      }
+    } else {
+      // NG slots in flight per lane: NG independent Philox / log / sincos dependency chains
+      auto group = [&](auto ng_tag, int s) {
+        constexpr int NG = decltype(ng_tag)::value;
+        int4 d[NG];
+        Philox4 ph[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+          d[i] = slot_of(s + i);
+          ph[i] = philox_rk((uint32_t)d[i].x, (uint32_t)sweep, c2, c3 ^ (uint32_t)d[i].y, pd.rk);
+        }
+        double za[NG], zb[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) bvg_box_muller(u53(ph[i].x, ph[i].y), u53(ph[i].z, ph[i].w), &za[i], &zb[i]);
+#pragma unroll
+        for (int i = 0; i < NG; ++i) { rec[d[i].z] = za[i]; rec[d[i].w] = zb[i]; }
+      };
+      int s = sb;
+      for (; s + 4 <= se; s += 4) group(std::integral_constant<int, 4>(), s);
+      if (s + 2 <= se) { group(std::integral_constant<int, 2>(), s); s += 2; }
+      if (s < se) group(std::integral_constant<int, 1>(), s);
+    }
+    __threadfence_block();
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + j) : "memory");  // the chunk's normals are complete (A and B)
+    if (isB) {
+      // ---- Bartlett diagonal: sqrt(chi2(df - i)), i < K
+      double chi[K];
+      if (inj_chi) {
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+          chi[i] = sqrt(rp.inj[VB_WISH_C][(size_t)(chain0 + c) * (size_t)rp.inj_chain_stride[VB_WISH_C] +
+                                          (size_t)sweep * (size_t)rp.inj_stride[VB_WISH_C] + i]);
+      } else {
+        Philox4 pu[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+          pu[i] = philox_rk((uint32_t)i | (100u << 24), (uint32_t)sweep, c2, c3 ^ ((uint32_t)VB_WISH_C << 24), pd.rk);
+        double g[K], x0[K];
+        bool ok[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) {                           // acceptance test of attempt 0, branch-free
+          const double d = mt[2 * i], cc = mt[2 * i + 1], x = rec[o_x0 + i];
+          const double u = u53(pu[i].x, pu[i].y);
+          const double v1 = fma(cc, x, 1.0), v = v1 * v1 * v1, x2 = x * x;
+          const double vs = (v1 > 0.0) ? v : 1.0;
+          ok[i] = (v1 > 0.0) && (d > 2.0 / 3.0) &&
+                  ((u < 1.0 - 0.0331 * x2 * x2) || (bvg_logpos(u) < 0.5 * x2 + d - d * v + d * bvg_logpos(vs)));
+          g[i] = d * v;
+          x0[i] = x;
+        }
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          if (!ok[i]) g[i] = philox_gamma_from_x0(rp.seed, chain, VB_WISH_C, sweep, i, 0.5 * (m.wish_df_post - (double)i), x0[i]);
+          chi[i] = bvg_sqrtpos(2.0 * g[i]);
+        }
+      }
+      __syncwarp();                                            // (lanes repeating a record have read its x0 too)
+      if (!dup) {
+        double wn[NW > 0 ? NW : 1];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) wn[i] = rec[o_wn + i];
+        if (K * M <= 40 && M == 2 * K + 1) kron_prep_regs<K, 2 * K + 1>(rec, wn, chi, cs.Linv, rec + o_G, rec + o_Ai);
+        else if (K * M <= 40 && M == K + 1) kron_prep_regs<K, K + 1>(rec, wn, chi, cs.Linv, rec + o_G, rec + o_Ai);
+        else if (K * M <= 40 && M == 4 * K + 1) kron_prep_regs<K, (K * (4 * K + 1) <= 40) ? 4 * K + 1 : 1>(rec, wn, chi, cs.Linv, rec + o_G, rec + o_Ai);
+        else if (K * M <= 40 && M == 3 * K + 1) kron_prep_regs<K, (K * (3 * K + 1) <= 40) ? 3 * K + 1 : 1>(rec, wn, chi, cs.Linv, rec + o_G, rec + o_Ai);
+        else {
+          kron_prep<K>(rec, wn, chi, M, rec + o_G, rec + o_Ai);
+          kron_t_inplace<K>(rec, cs.Linv, M);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&prep_bar[q % 3]);
     }
   }
-  if (bulk_any) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 template <int K>
@@ -462,23 +423,27 @@ static cudaError_t launch_k(const KronPlanDims& pd, BVG_BVAR_ARGS_NAMED) {
 // record and staging geometry shared by the planner and the launcher
 static void kron_dims(int k, int M, int CH, int NB, KronPlanDims* pd) {
   const int n = k * M, NW = (k * (k - 1)) / 2, KU = (k * (k + 1)) / 2;
-  const int len = 2 * ((n + 1) / 2) + 2 * ((NW + 1) / 2) + 2 * KU;
+  const int tail_raw = 2 * ((NW + 1) / 2) + 2 * ((k + 1) / 2), tail = tail_raw > 2 * KU ? tail_raw : 2 * KU;
+  const int len = 2 * ((n + 1) / 2) + tail;
   pd->CH = CH;
   pd->NB = NB;
-  pd->skip0 = 0;
   pd->VL = len | 1;                         // odd strides: the lanes of a warp (consecutive records / chains) hit
   pd->CS = (NB * pd->VL) | 1;               //   different banks
-  pd->SC = (NB * n + 1) & ~1;               // even: 16-byte aligned bulk-copy sources
-  pd->SG = (NB * k * k + 1) & ~1;
+  // split of the Box-Muller slots between the two warps of a chunk: B also draws the Bartlett diagonal (about five
+  // slots' worth of instructions) and prepares the chunk (about two)
+  const int nsl = (n + 1) / 2 + (NW + 1) / 2 + (k + 1) / 2;
+  int sa = (nsl + 7 + 1) / 2;               // B: its slots + ~7 slots' worth of extra work (measured: c2-A, SA = 10..14)
+  if (sa > nsl) sa = nsl;
+  pd->SA = sa;
 }
 static size_t kron_smem_bytes(int k, int M, const KronPlanDims& pd) {
-  return ((size_t)pd.CH * (pd.SC + pd.SG) + 3 * (size_t)pd.CH * pd.CS + (size_t)kron_consts_len(k, M) + 2 * k) * 8;
+  return (3 * (size_t)pd.CH * pd.CS + (size_t)kron_consts_len(k, M) + 2 * k) * 8;
 }
 
 cudaError_t launch_bvar_kron(BVG_BVAR_ARGS_NAMED) {
   KronPlanDims pd;
-  kron_dims(m.k, m.M, plan.chains_per_block, plan.kron_nb & 0xffff, &pd);
-  pd.skip0 = (plan.kron_nb >> 16) & 1;
+  kron_dims(m.k, m.M, plan.chains_per_block, plan.kron_nb, &pd);
+  if (plan.kron_sa > 0) pd.SA = plan.kron_sa;
   const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
   uint32_t k0 = (uint32_t)rp.seed, k1 = (uint32_t)(rp.seed >> 32);
   for (int r = 0; r < 10; ++r) { pd.rk[2 * r] = k0; pd.rk[2 * r + 1] = k1; k0 += W0; k1 += W1; }
@@ -491,57 +456,50 @@ cudaError_t launch_bvar_kron(BVG_BVAR_ARGS_NAMED) {
   }
 }
 
-// Launch geometry.  The kernel runs for the whole launch with a fixed set of CTAs, so what matters is (i) an even
-// fill of the SMs -- r CTAs on every SM, CH = ceil(chains / (SMs r)) <= 32 chains each -- and (ii) enough warps per SM
-// that the variate phase hides the latency of the state recursion.  threads_per_chain (tuning knob) = CTA threads per
-// chain, 0 = auto.
+// Launch geometry.  A CTA holds NCH <= 7 chunks of 32 records (32 / NB chains x NB sweeps) and runs 2 + 2 NCH warps; one
+// CTA per SM (shared memory).  Chains per SM decide the chunk shape: the fewer chains, the more sweeps per round, so that
+// a round always offers 32 NCH records to the generators.  threads_per_chain (tuning knob): >= 1000 is an explicit
+// geometry 1000 NB + NCH (e.g. 8007); other values are ignored (the kernel has one layout).
 cudaError_t plan_bvar_kron(const BvarModel& m, long long n_chains, int requested_tpc, LaunchPlan* plan) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int CH = 32, NT = 512, NB = 0, skip0 = 0;
-  if (requested_tpc > 0) {
-    // tuning / tests: 4..15 -> 128-thread CTAs, 16..128 -> 512-thread CTAs; >= 1000: explicit geometry
-    // 10000000 * skip0 + 100000 * NB + 1000 * (NT / 128) + CH, e.g. 604028 = 6 sweeps per round, 512 threads, 28 chains
-    int tpc = requested_tpc < 4 ? 4 : requested_tpc;
-    if (tpc >= 1000) {
-      skip0 = tpc / 10000000; tpc %= 10000000;
-      NB = tpc / 100000; tpc %= 100000;
-      NT = 128 * (tpc / 1000); CH = tpc % 1000;
-      if (NT > 512) NT = 512;
-      if (NT < 64) NT = 64;
-    }
-    else { if (tpc > 128) tpc = 128; NT = (tpc >= 16) ? 512 : 128; CH = NT / tpc; }
-    if (CH > 32) CH = 32;
-    if (CH < 1) CH = 1;
-  } else {
-    int r = 1;                                   // CTAs per SM
-    while (r < 4 && (n_chains + (long long)sms * r - 1) / ((long long)sms * r) > 32) ++r;
-    long long ch = (n_chains + (long long)sms * r - 1) / ((long long)sms * r);
-    CH = (int)(ch > 32 ? 32 : (ch < 1 ? 1 : ch));
-    NT = 512 / r;
-    if (NT < 128) NT = 128;
-  }
-  if (skip0 && NT < 256) skip0 = 0;
   const int k = m.k, M = m.M;
+  int NB = 0, NCH = 0;
+  int sa_override = 0;
+  if (requested_tpc >= 1000) {
+    sa_override = requested_tpc / 100000;                      // 100000 SA + 1000 NB + NCH
+    requested_tpc %= 100000;
+    NB = requested_tpc / 1000;
+    NCH = requested_tpc % 1000;
+    if (NB < 1 || NB > 32 || (NB & (NB - 1)) != 0) return cudaErrorInvalidConfiguration;
+    if (NCH < 1) NCH = 1;
+    if (NCH > 7) NCH = 7;
+  } else {
+    long long cps = (n_chains + sms - 1) / sms;              // chains per SM
+    if (cps > 28) cps = 28;
+    if (cps < 1) cps = 1;
+    int CPC = 1;
+    while ((cps + CPC - 1) / CPC > 7) CPC <<= 1;
+    NB = 32 / CPC;
+    NCH = (int)((cps + CPC - 1) / CPC);
+  }
   KronPlanDims pd;
-  auto bytes = [&](int nb) {
-    kron_dims(k, M, CH, nb, &pd);
+  auto bytes = [&](int nch) {
+    kron_dims(k, M, nch * (32 / NB), NB, &pd);
     return kron_smem_bytes(k, M, pd);
   };
-  if (NB <= 0) {
-    NB = 8;
-    while (NB < 64 && CH * NB < 224) NB <<= 1;    // few chains per CTA: longer rounds keep >= 224 records per round
-    while (NB > 1 && bytes(NB) > (size_t)216 * 1024 / (512 / NT)) --NB;
-  }
-  if (bytes(NB) > 227 * 1024 - 64) return cudaErrorInvalidConfiguration;
+  while (NCH > 1 && bytes(NCH) > 227 * 1024 - 256) --NCH;
+  if (bytes(NCH) > 227 * 1024 - 256) return cudaErrorInvalidConfiguration;
+  const int CH = NCH * (32 / NB);
   plan->kron = 1;
-  plan->kron_nb = NB | (skip0 << 16);
-  plan->threads_per_chain = NT / CH;
+  plan->kron_nb = NB;
+  plan->block_threads = 64 + 64 * NCH;
+  plan->threads_per_chain = plan->block_threads / CH;
+  plan->kron_sa = sa_override;
   plan->smem_per_chain = pd.VL;
-  plan->block_threads = NT;
   plan->chains_per_block = CH;
-  plan->smem_bytes = bytes(NB);
+  plan->smem_bytes = bytes(NCH);
   plan->grid = (int)((n_chains + CH - 1) / CH);
   return cudaSuccess;
 }

@@ -15,6 +15,7 @@ struct LaunchPlan {
   int grid;
   int kron;                // 1 = flat-prior Kronecker sweep kernel (bvg_kern_kron.cu)
   int kron_nb;             // its sweeps per round
+  int kron_sa;             // tuning: variate slots on the A warp of a chunk (0 = planner's choice)
 };
 
 #define BVG_BLOCK_SCRATCH 40   // doubles reserved in front of the chain's shared memory for BlockGroup
