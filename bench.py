@@ -333,6 +333,95 @@ def d2h_ceiling(ctx, nbytes):
             "what": "plain cudaMemcpyAsync device -> pinned host, one copy at a time per rank, all ranks concurrently"}
 
 
+def blocks_throughput(ctx, args):
+    """Stand-alone building blocks through their C-ABI entry points, batched: host arrays in,
+    host arrays out (the reference's calling convention), so the timed region holds H2D + kernel + D2H.  The bound of each
+    call is the PCIe transfer of its arguments / results (bytes listed); `cpu_baseline` is the oracle restatement of the
+    same block on a bounded sample, one core."""
+    import bvartools_b200.blocks as bb
+    rng = np.random.default_rng(7)
+    out = {}
+
+    def timed(fn, reps=3):
+        fn()
+        ts = []
+        for _ in range(reps):
+            ctx.fence()
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts))
+
+    def cpu(fn, n):
+        if args.no_cpu:
+            return None
+        t0 = time.perf_counter()
+        for i in range(n):
+            fn(i)
+        return {"problems_per_s": n / (time.perf_counter() - t0), "cores": 1, "kind": "port",
+                "sample": f"{n} problems, oracle/blocks.py"}
+
+    try:
+        from oracle import blocks as ob
+        k, M, T = 3, 7, 73
+        n = k * M
+        x = rng.standard_normal((M, T))
+        y = rng.standard_normal((k, T))
+        # ---- post_normal (src/post_normal.cpp:61-93): B posterior draws of the coefficients, c1 shape
+        B = 65536
+        w = rng.standard_normal((B, k, k + 2))
+        sig = np.linalg.inv(np.einsum("bij,bkj->bik", w, w) / (k + 2))
+        eps = rng.standard_normal((B, n))
+        a0, v0 = np.zeros(n), np.eye(n) * 0.1
+        t = timed(lambda: bb.post_normal(y, x, sig, a0, v0, eps=eps, method="chol"))
+        moved = 8.0 * B * (k * k + n + n)
+        out["post_normal"] = {"what": f"bvg_post_normal, k={k} M={M} T={T}, batch {B}", "problems_per_s": B / t, "ms": t * 1e3,
+                              "pcie_bytes": moved, "pcie_GBps": moved / t / 1e9,
+                              "cpu_baseline": cpu(lambda i: ob.post_normal(y, x, sig[i], a0[:, None], v0, eps[i]), 300)}
+        # ---- bvs (src/bvs.cpp:73-159)
+        B = 16384
+        z = np.kron(x.T, np.eye(k))
+        a = rng.standard_normal((B, n)) * 0.3
+        lam = (rng.random((B, n)) < 0.6).astype(np.float64)
+        prior = np.full(n, 0.5)
+        u1, u2 = rng.random((B, n)), rng.random((B, n))
+        t = timed(lambda: bb.bvs(y, z, a, lam, sig[:B], prior, u1=u1, u2=u2))
+        moved = 8.0 * B * (n + n + k * k + 2 * n + n)
+        out["bvs"] = {"what": f"bvg_bvs, k={k} T={T} n={n}, batch {B}", "problems_per_s": B / t, "ms": t * 1e3,
+                      "pcie_bytes": moved, "pcie_GBps": moved / t / 1e9,
+                      "cpu_baseline": cpu(lambda i: ob.bvs(y, z, a[i], np.diag(lam[i]), sig[i], prior, u1[i], u2[i]), 40)}
+        # ---- stochvol (src/stochvol_ksc1998.cpp:60-108), c4 shape
+        B, T2 = 8192, 200
+        ysv = rng.standard_normal((B, T2, k)) * 0.5
+        h0 = np.log(np.broadcast_to(ysv.var(axis=1, keepdims=True), ysv.shape)).copy()
+        u, e = rng.random((B, k, T2)), rng.standard_normal((B, k, T2))
+        sg_h, cst = np.full(k, 0.05), np.full(k, 1e-4)
+        t = timed(lambda: bb.stochvol_ksc1998(ysv, h0, sg_h, h0[:, 0, :], cst, u=u, eps=e))
+        moved = 8.0 * B * (5 * k * T2)
+        out["stochvol"] = {"what": f"bvg_stochvol (KSC 1998), T={T2} k={k}, batch {B}", "problems_per_s": B / t, "ms": t * 1e3,
+                           "pcie_bytes": moved, "pcie_GBps": moved / t / 1e9,
+                           "cpu_baseline": cpu(lambda i: ob.stochvol_mixture(ysv[i], h0[i], sg_h, h0[i, 0], cst, u[i], e[i]), 20)}
+        # ---- kalman_dk (src/kalman_dk.cpp:91-184): TVP state path of a k = 3, p = 2 VAR, T = 200
+        B = 2048
+        xk = rng.standard_normal((M, T2))
+        zk = np.vstack([np.kron(xk[:, tt][None, :], np.eye(k)) for tt in range(T2)])
+        yk = rng.standard_normal((k, T2))
+        su = np.linalg.inv(sig[:B])
+        sv = np.broadcast_to(np.eye(n) * 0.01, (B, n, n)).copy()
+        Bm = np.eye(n)
+        ai, Pi = np.zeros((B, n)), np.broadcast_to(np.eye(n), (B, n, n)).copy()
+        ek = rng.standard_normal((B, n + T2 * (k + n)))
+        t = timed(lambda: bb.kalman_dk(yk, zk, su, sv, Bm, ai, Pi, eps=ek), reps=2)
+        moved = 8.0 * B * (k * k + 2 * n * n + n + ek.shape[1] + n * (T2 + 1))
+        sm = lambda i: ob.kalman_dk(yk, zk, su[i], sv[i], Bm, ai[i], Pi[i], ek[i, :n], ek[i, n:].reshape(T2, k + n)[:, :k],
+                                    ek[i, n:].reshape(T2, k + n)[:, k:])
+        out["kalman_dk"] = {"what": f"bvg_kalman_dk, k={k} n={n} T={T2}, batch {B}", "problems_per_s": B / t, "ms": t * 1e3,
+                            "pcie_bytes": moved, "pcie_GBps": moved / t / 1e9, "cpu_baseline": cpu(sm, 30)}
+    except Exception as exc:                     # auxiliary measurement: never break the bench line
+        out["error"] = f"{type(exc).__name__}: {exc}"
+    return out
+
+
 def timed_steps(ctx, step, steps, warmup, clocks=None):
     """W untimed + K timed steps bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks."""
     torch = ctx.torch
@@ -770,7 +859,7 @@ def main():
     else:
         head = run_sampler_workload(ctx, args, head_name, args.steps, args.warmup, chains=args.chains or None,
                                     headline=True, with_e2e=not args.no_e2e, iterations=it, burnin=bi)
-    workloads, strong, summary_e2e = {}, None, None
+    workloads, strong, summary_e2e, blocks_rec = {}, None, None, None
     if not single:
         sub_steps, sub_warm = min(args.steps, 2), 1
         workloads["c2b"] = run_grid(ctx, args, sub_steps, sub_warm, with_e2e=not args.no_e2e)
@@ -784,6 +873,8 @@ def main():
             if strong is not None:
                 strong = {k_: strong[k_] for k_ in ("value", "unit", "ms_per_step", "config", "e2e", "roofline")}
                 strong["scaling"] = "strong"
+        if ctx.rank == 0 and not args.no_e2e:
+            blocks_rec = blocks_throughput(ctx, args)
         if not args.no_e2e:
             try:
                 summary_e2e = run_summary_e2e(ctx, args, min(args.steps, 3))
@@ -805,6 +896,7 @@ def main():
             line["workloads"] = workloads
             line["strong"] = strong
             line["e2e_summary_mode"] = summary_e2e
+            line["blocks"] = blocks_rec
             line["gpu_launches"] = head["gpu_launches"] + sum((w or {}).get("gpu_launches", 0) for w in workloads.values())
         print(json.dumps(line), flush=True)
     ctx.close()

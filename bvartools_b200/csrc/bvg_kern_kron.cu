@@ -7,9 +7,10 @@
 //   warp 0     the state recursion W <- U(S0 + SSE + W E E' W') A_B^-1, one LANE per chain with W in registers:
 //              latency-bound (~150 dependent instructions per sweep, three rsqrt chains), so nothing else runs on it; the
 //              W a sweep starts from and ends with are left in its record (over the G / A_B^-1 slots just consumed);
-//   warp 1     one round behind: the retained draws a = vec(A_ols + W T), Sigma = W W', one lane per chain, written
-//              straight to the [chain][iter][row] output (consecutive sweeps of a chain are consecutive in memory; the
-//              partial sectors of neighbouring stores merge in L2 -- profiles/r02_c2a_*: DRAM bytes = algorithmic bytes).
+//   warp 1     one round behind: the retained draws a = vec(A_ols + W T), Sigma = W W', one lane per record, written
+//              straight to the [chain][iter][row] output (consecutive lanes = consecutive sweeps of a chain = consecutive
+//              n-vectors in memory; the partial sectors of neighbouring stores merge in L2 -- profiles/r02_c2a_*: DRAM
+//              bytes = algorithmic bytes).
 //              Staging the draws in shared memory for cp.async.bulk copies was measured and dropped: one bulk copy per
 //              chain and array is ~30 instructions of address set-up + R2UR per 0.7 KB, slower than the stores;
 //   warps 2 + 2 j, 3 + 2 j   the variates of chunk j, one lane per record, FIXED for the whole launch: chain id, Philox
@@ -135,19 +136,22 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, unsigned parity) {
+  unsigned ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-#ifdef BVG_KRON_HINT
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 2000;\n\t"
-#else
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-#endif
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+// try_wait parks the warp only for a short, implementation-defined time: the role warps that mostly wait (recursion,
+// output) would otherwise spend a third of the SM's issued instructions on re-polls (profiles/r02_c2a_final_*)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity, unsigned sleep_ns = 0) {
+  while (!mbar_try(bar, parity))
+    if (sleep_ns) __nanosleep(sleep_ns);
 }
 
 template <int K>
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(512, BVG_KRON_MINB) bvar_kron_batch_kernel(
         for (int j = 0; j < K; ++j) W[i][j] = (i <= j) ? st[i + K * j] : 0.0;
     }
     for (int q = 0; q < n_rounds; ++q) {
-      mbar_wait(&prep_bar[q % 3], (unsigned)((q / 3) & 1));
+      mbar_wait(&prep_bar[q % 3], (unsigned)((q / 3) & 1), 40);
       const int nb = round_nb(q);
       if (act) {
         double* rec = var + (size_t)(q % 3) * CH * CS + tid * CS;
@@ -260,25 +264,28 @@ __global__ void __launch_bounds__(512, BVG_KRON_MINB) bvar_kron_batch_kernel(
   }
 
   if (warp == 1) {
-    // ================= retained draws, one round behind the recursion: lane = chain =================
-    const bool act = tid - 32 < CHv;
-    const int c = act ? tid - 32 : 0;
-    const long long first_keep = (s0 > burnin) ? (long long)s0 - burnin : 0;   // output position of this launch's first draw
-    double* oc = out.coef + ((size_t)(chain0 + c) * (size_t)out.iters + (size_t)first_keep) * (size_t)n;
-    double* os = out.sigma + ((size_t)(chain0 + c) * (size_t)out.iters + (size_t)first_keep) * (size_t)KK;
+    // ================= retained draws, one round behind the recursion: lane = record =================
+    // (records c NB + sw in passes of 32: full lanes whatever the number of chains of the CTA; consecutive lanes are
+    //  consecutive sweeps of a chain, i.e. consecutive n-vectors of the output)
+    const int lnb = 31 - __clz(NB);
     for (int q = 0; q < n_rounds; ++q) {
-      mbar_wait(&rec_bar[q % 3], (unsigned)((q / 3) & 1));
+      mbar_wait(&rec_bar[q % 3], (unsigned)((q / 3) & 1), 200);
       const int nb = round_nb(q), b0 = s0 + q * NB;
-      if (act) {
-        const double* rec = var + (size_t)(q % 3) * CH * CS + c * CS;
-        for (int sw = 0; sw < nb; ++sw, rec += VL) {
-          if (b0 + sw < burnin) continue;
+      if (b0 + nb > burnin) {
+        const double* vb = var + (size_t)(q % 3) * CH * CS;
+        for (int r = lane; r < CHv * NB; r += 32) {
+          const int c = r >> lnb, sw = r & (NB - 1);
+          const long long pos = (long long)b0 + sw - burnin;
+          if (sw >= nb || pos < 0) continue;
+          const double* rec = vb + c * CS + sw * VL;
+          double* oc = out.coef + ((size_t)(chain0 + c) * (size_t)out.iters + (size_t)pos) * (size_t)n;
+          double* os = out.sigma + ((size_t)(chain0 + c) * (size_t)out.iters + (size_t)pos) * (size_t)KK;
           if (M == 2 * K + 1) kron_coef_to<K, 2 * K + 1>(rec + o_Ai, rec, cs.Aols, M, oc);   // a = vec(A_ols + W T)
           else if (M == K + 1) kron_coef_to<K, K + 1>(rec + o_Ai, rec, cs.Aols, M, oc);
+          else if (M == 3 * K + 1) kron_coef_to<K, 3 * K + 1>(rec + o_Ai, rec, cs.Aols, M, oc);
+          else if (M == 4 * K + 1) kron_coef_to<K, 4 * K + 1>(rec + o_Ai, rec, cs.Aols, M, oc);
           else kron_coef_to<K, 0>(rec + o_Ai, rec, cs.Aols, M, oc);
           kron_sigma<K>(rec + o_G, os);                                                      // Sigma = W W', W after the sweep
-          oc += n;
-          os += KK;
         }
       }
       __syncwarp();
