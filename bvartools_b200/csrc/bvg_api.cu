@@ -43,6 +43,17 @@ static int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call);     \
   } while (0)
 
+// device allocations of one entry point: released on every exit path
+struct DevGuard {
+  std::vector<void*> ptrs;
+  ~DevGuard() { for (void* q : ptrs) cudaFree(q); }
+  cudaError_t alloc(void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) ptrs.push_back(*p);
+    return e;
+  }
+};
+
 struct bvg_sampler {
   Prepared P;
   int device = 0;
@@ -571,10 +582,17 @@ int bvg_loglik_draws(const double* dev_coef, const double* dev_sigma, int64_t n_
   return 0;
 }
 
+// Post-estimation calls may be given another stream than the run: order them after its last launch.
+static inline cudaError_t after_run(bvg_sampler* s, void* cuda_stream) {
+  if (s == nullptr || !s->timed) return cudaSuccess;
+  return cudaStreamWaitEvent((cudaStream_t)cuda_stream, s->ev1, 0);
+}
+
 int bvg_sampler_loglik(bvg_sampler* s, double* host_ll_t, void* cuda_stream) {
   if (!s || !host_ll_t) return fail(-1, "sampler / output is NULL");
   if (s->P.structural) return fail(-6, "the log-likelihood kernels do not cover structural models");
   CK(cudaSetDevice(s->device));
+  CK(after_run(s, cuda_stream));
   const int T = s->P.T;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   double* d_ll = nullptr;
@@ -680,6 +698,7 @@ int bvg_sampler_loglik_total(bvg_sampler* s, double* total, void* cuda_stream) {
   if (!s || !total) return fail(-1, "sampler / output is NULL");
   if (s->P.structural) return fail(-6, "the log-likelihood kernels do not cover structural models");
   CK(cudaSetDevice(s->device));
+  CK(after_run(s, cuda_stream));
   const bool fast = !s->P.tvp && !tv_sigma_of(s->P) && s->P.M > 0 && s->bm.XX && s->bm.Aols && s->bm.SSE &&
                     s->P.k <= 32;
   if (!fast) {                           // time-varying coefficients / variances: per-period kernel, summed on the host
@@ -707,6 +726,7 @@ int bvg_sampler_loglik_total_device(bvg_sampler* s, double* dev_total, void* cud
   if (!s || !dev_total) return fail(-1, "sampler / output is NULL");
   if (s->P.structural) return fail(-6, "the log-likelihood kernels do not cover structural models");
   CK(cudaSetDevice(s->device));
+  CK(after_run(s, cuda_stream));
   const bool fast = !s->P.tvp && !tv_sigma_of(s->P) && s->P.M > 0 && s->bm.XX && s->bm.Aols && s->bm.SSE && s->P.k <= 32;
   if (!fast) return fail(-6, "bvg_sampler_loglik_total_device covers constant-parameter models with T > M (cross-moment kernel)");
   cudaError_t e = launch_loglik_total(s->P.k, s->P.M, s->P.T, (long long)s->n_chains * s->P.iterations, s->bm.XX,
@@ -784,9 +804,10 @@ int bvg_loglik_normal(const double* u, const double* sigma, int32_t k, int32_t T
           for (int r = 0; r < k; ++r) dst[(size_t)t * k * k + r + (size_t)k * c] = src[(size_t)t * k + r + (size_t)sigma_rows * c];
   }
   double *d_u = nullptr, *d_sg = nullptr, *d_out = nullptr;
-  CK(cudaMalloc((void**)&d_u, (size_t)n_batch * k * T * sizeof(double)));
-  CK(cudaMalloc((void**)&d_sg, sg.size() * sizeof(double)));
-  CK(cudaMalloc((void**)&d_out, (size_t)n_batch * T * sizeof(double)));
+  DevGuard mem;
+  CK(mem.alloc((void**)&d_u, (size_t)n_batch * k * T * sizeof(double)));
+  CK(mem.alloc((void**)&d_sg, sg.size() * sizeof(double)));
+  CK(mem.alloc((void**)&d_out, (size_t)n_batch * T * sizeof(double)));
   CK(cudaMemcpy(d_u, u, (size_t)n_batch * k * T * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_sg, sg.data(), sg.size() * sizeof(double), cudaMemcpyHostToDevice));
   int rc = 0;
@@ -797,7 +818,6 @@ int bvg_loglik_normal(const double* u, const double* sigma, int32_t k, int32_t T
     cudaError_t e = cudaMemcpy(out, d_out, (size_t)n_batch * T * sizeof(double), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = cuda_fail(e, "log-likelihood copy");
   }
-  cudaFree(d_u); cudaFree(d_sg); cudaFree(d_out);
   return rc;
 }
 
@@ -841,6 +861,7 @@ int bvg_sampler_summary(bvg_sampler* s, int32_t which, const double* probs, int3
                         double* quantiles, void* cuda_stream) {
   if (!s) return fail(-1, "sampler is NULL");
   CK(cudaSetDevice(s->device));
+  CK(after_run(s, cuda_stream));
   const double* buf = nullptr;
   long long rows = 0;
   switch (which) {
@@ -875,6 +896,7 @@ int bvg_tsse_draws(const double* dev_draws, int64_t n_chains, int64_t iters, int
 int bvg_sampler_tsse(bvg_sampler* s, int32_t which, double* tsse, void* cuda_stream) {
   if (!s) return fail(-1, "sampler is NULL");
   CK(cudaSetDevice(s->device));
+  CK(after_run(s, cuda_stream));
   const double* buf = nullptr;
   long long rows = 0;
   switch (which) {
@@ -924,6 +946,7 @@ int bvg_sampler_irf(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, in
                     int32_t n_probs, double* quantiles, double* mean, double* host_draws, void* cuda_stream) {
   if (!s) return fail(-1, "sampler is NULL");
   CK(cudaSetDevice(s->device));
+  CK(after_run(s, cuda_stream));
   const int k = s->P.k, T = s->P.T;
   if (p < 0 || (long long)k * k * p > (long long)s->P.n) return fail(-2, "p lags do not fit the coefficient vector");
   const bool tv_coef = s->P.tvp != 0, tv_sig = tv_sigma_of(s->P);
@@ -1000,6 +1023,7 @@ int bvg_sampler_fevd(bvg_sampler* s, int32_t p, int32_t n_ahead, int32_t type, i
                      int32_t period, double* host_out, void* cuda_stream) {
   if (!s) return fail(-1, "sampler is NULL");
   CK(cudaSetDevice(s->device));
+  CK(after_run(s, cuda_stream));
   const int k = s->P.k, T = s->P.T;
   if (p < 0 || (long long)k * k * p > (long long)s->P.n) return fail(-2, "p lags do not fit the coefficient vector");
   const bool tv_coef = s->P.tvp != 0, tv_sig = tv_sigma_of(s->P);
@@ -1056,6 +1080,7 @@ int bvg_sampler_forecast(bvg_sampler* s, int32_t p, int32_t tot, int32_t n_ahead
                          double* host_draws, void* cuda_stream) {
   if (!s) return fail(-1, "sampler is NULL");
   CK(cudaSetDevice(s->device));
+  CK(after_run(s, cuda_stream));
   const int k = s->P.k, T = s->P.T;
   const bool tv_coef = s->P.tvp != 0, tv_sig = tv_sigma_of(s->P);
   const long long nd = (long long)s->n_chains * s->P.iterations;

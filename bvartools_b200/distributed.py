@@ -95,16 +95,21 @@ def allreduce_moments(draws, device=None):
         raise ValueError("allreduce_moments needs the number of rows even for an empty shard; pass a (0, 0, rows) array")
     rows = draws.shape[-1]
     flat = np.asarray(draws, dtype=np.float64).reshape(-1, rows)
-    acc = torch.empty(2 * rows + 1, dtype=torch.float64, device=device or "cpu")
+    # two all-reduces: (sums, count) first, then the sums of squares CENTRED at the global mean -- the one-pass form
+    # sum x^2 - n mean^2 cancels for coefficients with |mean| >> sd (intercepts, trends), cf. DESIGN.md section 3.5b
+    acc = torch.empty(rows + 1, dtype=torch.float64, device=device or "cpu")
     acc[:rows] = torch.from_numpy(flat.sum(axis=0))
-    acc[rows:2 * rows] = torch.from_numpy((flat * flat).sum(axis=0))
-    acc[2 * rows] = float(flat.shape[0])
+    acc[rows] = float(flat.shape[0])
     if dist is not None and world > 1:
         dist.all_reduce(acc)
-    acc = acc.cpu().numpy()
-    cnt = acc[2 * rows]
-    mean = acc[:rows] / cnt
-    var = (acc[rows:2 * rows] - cnt * mean * mean) / max(cnt - 1.0, 1.0)
+    acc_h = acc.cpu().numpy()
+    cnt = acc_h[rows]
+    mean = acc_h[:rows] / max(cnt, 1.0)
+    dev = flat - mean[None, :]
+    ss = torch.from_numpy((dev * dev).sum(axis=0)).to(device or "cpu")
+    if dist is not None and world > 1:
+        dist.all_reduce(ss)
+    var = ss.cpu().numpy() / max(cnt - 1.0, 1.0)
     return mean, var, int(cnt)
 
 
@@ -150,14 +155,16 @@ def gather_draws(local, n_chains_total, dst=0):
         return np.asarray(local)
     local = np.ascontiguousarray(local, dtype=np.float64)
     shapes = [(shard(n_chains_total, r, world)[1],) + local.shape[1:] for r in range(world)]
-    t = torch.from_numpy(local)
+    # NCCL moves device tensors only: stage through this rank's GPU then (gloo takes the host tensors as they are)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(local).to(dev)
     if rank == dst:
-        bufs = [torch.empty(s, dtype=torch.float64) for s in shapes]
+        bufs = [torch.empty(s, dtype=torch.float64, device=dev) for s in shapes]
         bufs[dst] = t
         reqs = [dist.irecv(bufs[r], src=r) for r in range(world) if r != dst and shapes[r][0] > 0]
         for q in reqs:
             q.wait()
-        return np.concatenate([b.numpy() for b in bufs], axis=0)
+        return np.concatenate([b.cpu().numpy() for b in bufs], axis=0)
     if local.shape[0] > 0:
         dist.send(t, dst=dst)
     return None
