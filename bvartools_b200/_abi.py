@@ -108,8 +108,6 @@ def spec_from_model(obj, n_chains=1, seed=0, chain_offset=0, device=-1, resid_mo
     """bvarmodel list -> bvg_spec (the unpacking of src/bvaralg.cpp:9-249 / src/bvartvpalg.cpp:11-279)."""
     data, model, priors, initial = obj["data"], obj["model"], obj["priors"], obj["initial"]
     structural = bool(model.get("structural"))
-    if structural and "ssvs" in priors.get("coefficients", {}):
-        raise NotImplementedError("SSVS on a structural model is not on the accelerated path (SURVEY.md section 8f-4)")
     Y = np.asarray(data["Y"], dtype=np.float64)          # T x k
     T, k = Y.shape
     Z = data.get("Z")

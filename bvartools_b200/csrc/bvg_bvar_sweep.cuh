@@ -63,6 +63,8 @@ struct BvarModel {
   int diag_sigma;                  // TVP: the measurement precision stays diagonal (SV, or gamma variances with a diagonal
                                    // initial value, no covariance block): equation-decoupled state draw (bvg_tvp_eq8.cuh)
   int a0_from;                     // structural models: first internal row of the -y block (k M_user); -1 otherwise
+  const double* maskd;             // structural models with SSVS: n doubles, 1 = kept position, 0 = masked; nullptr otherwise
+                                   // (without selection / with BVS the mask rides on lambda)
   int n_psi;                       // k (k - 1) / 2
   const double* psi_vi;            // n_psi x n_psi prior precision (col-major); its diagonal lives in the chain state
   const double* psi_vmu;           // n_psi  OFF-diagonal part of (prior precision times prior mean)
@@ -724,18 +726,20 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
           w[r] = s;
         }
       }
-      const bool bvs = varsel == VS_BVS;
+      // regressor mask of the coefficient draw: lambda (BVS), or the static mask of a structural model under SSVS
+      const double* zmask = (varsel == VS_BVS) ? lam : (((FEAT & F_VARSEL) && varsel == VS_SSVS) ? m.maskd : nullptr);
+      const bool bvs = zmask != nullptr;
 #if defined(__CUDA_ARCH__)
       if constexpr (TILED) {
         for (int r = tid; r < tiled_nt(n) * 8; r += G) {
           double b = 0.0;                                          // zero padding of the rhs
           if (r < n) {
-            b = w[r] * (bvs ? lam[r] : 1.0) + vdiag[r] * cs.mu[r];
+            b = w[r] * (bvs ? zmask[r] : 1.0) + vdiag[r] * cs.mu[r];
             if (vmu_off != nullptr) b += vmu_off[r];
           }
           w[r] = b;
         }
-        tiled_build_precision(L, n, k, M, cs.XX, sig, sv ? GW : nullptr, vdiag, bvs ? lam : nullptr, vi_off, (sv && covar) ? PsiM : nullptr);
+        tiled_build_precision(L, n, k, M, cs.XX, sig, sv ? GW : nullptr, vdiag, zmask, vi_off, (sv && covar) ? PsiM : nullptr);
       } else
 #endif
       {
@@ -743,7 +747,7 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
           const int j = r / k, i = r % k;
           double* Lr = L + tri(r);
 #define BVG_LSET(c, v) Lr[c] = (v)
-          const double lr = bvs ? lam[r] : 1.0;
+          const double lr = bvs ? zmask[r] : 1.0;
           if (sv) {
             int j2 = 0, i2 = 0;
             for (int c = 0; c <= r; ++c) {
@@ -751,7 +755,7 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
               if (covar) {   // sum_q GW_q[j, j2] Psi_qi Psi_qi2
                 for (int q = (i > i2 ? i : i2); q < k; ++q) gv = fma(GW[q * tri(M) + tri(j) + j2], PsiM[q + k * i] * PsiM[q + k * i2], gv);
               } else if (i == i2) gv = GW[i * tri(M) + tri(j) + j2];
-              if (bvs) gv *= lr * lam[c];
+              if (bvs) gv *= lr * zmask[c];
               if (vi_off != nullptr) gv += vi_off[tri(r) + c];
               if (c == r) gv += vdiag[r];
               BVG_LSET(c, gv);
@@ -766,7 +770,7 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
               const int i2max = (j2 < j) ? k - 1 : i;
               for (int i2 = 0; i2 <= i2max; ++i2, ++c) {
                 double gv = xv * sigrow[k * i2];
-                if (bvs) gv *= lr * lam[c];
+                if (bvs) gv *= lr * zmask[c];
                 if (vi_off != nullptr) gv += vi_off[tri(r) + c];
                 if (c == r) gv += vdiag[r];
                 BVG_LSET(c, gv);
@@ -798,6 +802,10 @@ BVG_HD void bvar_chain(const Grp& g, const BvarModel& m, const BvarConsts& cs, c
 
       // ---- SSVS (bvaralg.cpp:314-331)
       if (varsel == VS_SSVS) {
+        if (zmask != nullptr) {                                    // structural model: masked positions are not coefficients
+          for (int r = tid; r < n; r += G) a[r] *= zmask[r];
+          g.sync();
+        }
         for (int r = tid; r < n; r += G) {
           if (!m.include[r]) continue;
           const double t0 = m.tau0[r], t1 = m.tau1[r], pi = m.inprior[r];

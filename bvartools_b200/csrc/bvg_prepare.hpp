@@ -27,7 +27,7 @@ struct Prepared {
   long Y = -1, X = -1, XX = -1, YX = -1, Aols = -1, SSE = -1, mu = -1, vi_off = -1, vmu_off = -1, vdiag0 = -1,
        tau0 = -1, tau1 = -1, inprior = -1, S0 = -1, gshape = -1, grate = -1, svmu = -1, svvi = -1, svconst = -1,
        mixp = -1, mixmu = -1, mixs2 = -1, omega_off = -1, vshape = -1, vrate = -1, kLinv = -1, kSS = -1,
-       psi_vshape = -1, psi_vrate = -1;
+       psi_vshape = -1, psi_vrate = -1, maskd = -1;
   int kron = 0;   // 1 = flat-prior Kronecker sweep (bvg_kron_sweep.cuh)
   int n_psi = 0;  // k (k - 1) / 2 when the covariance (psi) block is active, else 0
   // structural models (A0): the sampler runs on the regressors [x; -y] with the positions (variable j, equation i <= j)
@@ -105,7 +105,7 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
   if (k < 2) BVG_FAIL(-7, "Model must contain at least two endogenous variables for structural analysis.");
   if (k > 64 || T < 2 || Mu < 0 || !s->Y || (Mu > 0 && !s->X)) BVG_FAIL(-3, "invalid dimensions or missing data");
   if (s->tvp && (!s->tvp_shape || !s->tvp_rate || !s->a_init)) BVG_FAIL(-4, "TVP prior shape / rate or initial draw missing");
-  if (s->varsel == BVG_VARSEL_SSVS) BVG_FAIL(-5, "SSVS on a structural model is not supported");
+  if (s->varsel == BVG_VARSEL_SSVS && s->tvp) BVG_FAIL(-7, "SSVS is not defined for TVP models");
   if (s->sigma_type == BVG_SIGMA_WISHART) BVG_FAIL(-7, "Structural models may not use a Wishart prior.");
   if (s->psi_mu || s->psi_vi) BVG_FAIL(-7, "Error covariances and structural coefficients cannot be estimated at the same time.");
   if (!s->mu || !s->Vi) BVG_FAIL(-4, "priors$coefficients$mu / v_i missing");
@@ -128,6 +128,19 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
     }
   }
   std::vector<int32_t> include;
+  std::vector<double> tau0, tau1;
+  if (s->varsel == BVG_VARSEL_SSVS) {
+    // SSVS on the kept positions (bvaralg.cpp:107-135 with the structural z): the static mask cannot ride on lambda (SSVS
+    // records its indicators there and never masks the regressors), it travels as BvarModel::maskd instead
+    if (!s->inprior || !s->tau0 || !s->tau1 || s->n_include < 0 || (s->n_include > 0 && !s->include))
+      BVG_FAIL(-4, "SSVS prior (tau0 / tau1 / inprior / include) missing");
+    tau0.assign((size_t)na, 1.0); tau1.assign((size_t)na, 1.0);
+    for (int r = 0; r < nu; ++r) { inprior[pos[r]] = s->inprior[r]; tau0[pos[r]] = s->tau0[r]; tau1[pos[r]] = s->tau1[r]; }
+    for (int e = 0; e < s->n_include; ++e) {
+      if (s->include[e] < 0 || s->include[e] >= nu) BVG_FAIL(-8, "include index out of range");
+      include.push_back(pos[s->include[e]]);
+    }
+  }
   if (s->varsel == BVG_VARSEL_BVS) {
     if (!s->inprior || s->n_include < 0 || (s->n_include > 0 && !s->include)) BVG_FAIL(-4, "inclusion prior / include index missing");
     for (int r = 0; r < nu; ++r) inprior[pos[r]] = s->inprior[r];
@@ -145,12 +158,19 @@ static inline int prepare(const bvg_spec* s, Prepared& P) {
   eff.structural = 0;
   if (s->tvp) { eff.tvp_shape = tshape.data(); eff.tvp_rate = trate.data(); eff.a_init = ainit.data(); }
   eff.M = Ma; eff.X = X.data(); eff.mu = mu.data(); eff.Vi = Vi.data(); eff.vi_dense = 1;
-  eff.varsel = BVG_VARSEL_BVS; eff.inprior = inprior.data();
+  const bool ssvs = s->varsel == BVG_VARSEL_SSVS;
+  eff.varsel = ssvs ? BVG_VARSEL_SSVS : BVG_VARSEL_BVS; eff.inprior = inprior.data();
+  if (ssvs) { eff.tau0 = tau0.data(); eff.tau1 = tau1.data(); }
   eff.include = include.empty() ? nullptr : include.data(); eff.n_include = (int32_t)include.size();
   eff.resid_mode = BVG_RESID_DIRECT;                                          // [x; -y] fits y exactly: no OLS moments
   const int rc = prepare_impl(&eff, P);
   if (rc) return rc;
   P.structural = 1; P.n_user = nu; P.varsel_user = s->varsel; P.a0_from = k * Mu;
+  if (ssvs) {
+    std::vector<double> mk((size_t)na, 0.0);
+    for (int r = 0; r < nu; ++r) mk[pos[r]] = 1.0;
+    P.maskd = P.push(mk);
+  }
   // lambda = 0 on the masked positions (state: Sigma^-1 (k k) | prior diagonal (n) | lambda (n) | ...;
   // TVP state: Sigma^-1 | state precisions (n) | initial state (n) | lambda (n) | ...)
   std::vector<unsigned char> kept((size_t)na, 0);
@@ -482,6 +502,7 @@ static inline const double* at(const double* base, long off) { return off < 0 ? 
 static inline void bind_bvar(const Prepared& P, const double* base, const unsigned char* inc, BvarModel* m) {
   m->k = P.k; m->T = P.T; m->M = P.M; m->n = P.n;
   m->a0_from = P.a0_from;
+  m->maskd = at(base, P.maskd);
   m->diag_sigma = (P.diag_sigma && P.n_psi == 0) ? 1 : 0;
   m->sigma_type = P.sigma_type; m->varsel = P.varsel; m->resid_mode = P.resid_mode; m->n_mix = P.n_mix;
   m->Y = at(base, P.Y); m->X = at(base, P.X); m->XX = at(base, P.XX); m->YX = at(base, P.YX);

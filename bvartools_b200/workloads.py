@@ -83,7 +83,7 @@ def model_tvp_covar(K=3, p=1, nobs=24, iterations=8, burnin=3, seed=41, sv=True,
                       bvs=dict(inprior=0.5, exclude_det=True, covar=psi_bvs) if (bvs or psi_bvs) else None)
 
 
-def model_structural(K=3, p=1, nobs=50, iterations=12, burnin=4, seed=9, sv=False, bvs=False, tvp=False):
+def model_structural(K=3, p=1, nobs=50, iterations=12, burnin=4, seed=9, sv=False, bvs=False, tvp=False, ssvs=False):
     """Structural VAR (A0 coefficients: equation i contains -y_j, j < i) with inverse-gamma or SV error variances."""
     y = synth_var(K, p, nobs, seed)
     m = gen_var(y, p=p, deterministic="const", iterations=iterations, burnin=burnin, structural=True, sv=sv, tvp=tvp)
@@ -91,7 +91,8 @@ def model_structural(K=3, p=1, nobs=50, iterations=12, burnin=4, seed=9, sv=Fals
     if sv:
         sigma.update(mu=0, v_i=0.01, sigma_h=0.05, constant=1e-4)
     return add_priors(m, coef=dict(v_i=1, v_i_det=0.1, shape=3, rate=1e-4, rate_det=0.01), sigma=sigma,
-                      bvs=dict(inprior=0.5, exclude_det=True) if bvs else None)
+                      bvs=dict(inprior=0.5, exclude_det=True) if bvs else None,
+                      ssvs=dict(inprior=0.5, semiautomatic=(0.1, 10), exclude_det=True) if ssvs else None)
 
 
 def model_c5(K=20, p=4, nobs=204, iterations=200, burnin=50, seed=2042004):

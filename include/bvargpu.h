@@ -143,7 +143,8 @@ typedef struct bvg_spec {
    * structural = 1 every per-coefficient array (mu, Vi, inprior, include; the coef / lambda outputs; injected coef_normal
    * excepted, see below) has k M + k(k-1)/2 entries in the reference's order [a | b | c | a0], a0 by variable j then
    * equation i > j.  X stays the M x T regressor matrix WITHOUT the -y block (the library appends it).  Needs a gamma or SV
-   * error prior (R/add_priors.bvarmodel.R); SSVS and the covariance block are not available with it (-5 / -7).  TVP models:
+   * error prior (R/add_priors.bvarmodel.R); the covariance block is not available with it (-7); SSVS works on the kept
+   * positions (tau0 / tau1 / inprior / include in the same [a | b | c | a0] order).  TVP models:
    * tvp_shape / tvp_rate / a_init and the sigma_v output follow the same order and length.
    * Injected coefficient-level variates (tests) are indexed by the INTERNAL position i + k m over the M + k regressors. */
   int32_t structural;

@@ -100,7 +100,7 @@ def make_variates(obj, n_chains, seed):
         Mu = obj["data"]["Z"].shape[1]
         pos = list(range(k * Mu)) + [k * (Mu + j) + i for j in range(k) for i in range(j + 1, k)]
         na = k * (Mu + k)
-        for kname in ("coef_normal", "bvs_u1", "bvs_u2", "sigma_v_gamma", "a_init_normal"):
+        for kname in ("coef_normal", "ssvs_u", "bvs_u1", "bvs_u2", "sigma_v_gamma", "a_init_normal"):
             if kname in stacked:
                 full = np.full(stacked[kname].shape[:2] + (na,), 0.5)
                 full[:, :, pos] = stacked[kname]

@@ -47,6 +47,7 @@ def test_out_rows():
                       # structural: k M + k (k - 1) / 2 stored rows (constant and TVP), BVS indicators on the same rows
                       (helpers.model_structural(K=3, p=1, nobs=30), (15, 9, 0, 0, 0)),
                       (helpers.model_structural(K=3, p=1, nobs=30, bvs=True), (15, 9, 15, 0, 0)),
+                      (helpers.model_structural(K=3, p=1, nobs=30, ssvs=True), (15, 9, 15, 0, 0)),
                       (helpers.model_structural(K=3, p=1, nobs=30, tvp=True), (15 * 29, 9, 0, 0, 15)),
                       (helpers.model_structural(K=3, p=1, nobs=30, tvp=True, sv=True, bvs=True),
                        (15 * 29, 9 * 29, 15, 3, 15)),

@@ -69,6 +69,9 @@ CASES["structural_gamma_k4_p2"] = (lambda: helpers.model_structural(K=4, p=2, no
 CASES["structural_sv"] = (lambda: helpers.model_structural(sv=True), {})
 CASES["structural_gamma_bvs"] = (lambda: helpers.model_structural(bvs=True), {})
 CASES["structural_sv_bvs_k2"] = (lambda: helpers.model_structural(K=2, p=2, sv=True, bvs=True), {})
+# SSVS on a structural model (bvaralg.cpp:107-135 with the structural z): the static mask travels beside lambda
+CASES["structural_gamma_ssvs"] = (lambda: helpers.model_structural(ssvs=True, iterations=16, burnin=4), {})
+CASES["structural_gamma_ssvs_k4_p2"] = (lambda: helpers.model_structural(K=4, p=2, nobs=60, ssvs=True), {})
 CASES["tvp_covar_gamma_bvs"] = (lambda: helpers.model_tvp_covar(sv=False, bvs=True), {})
 
 
@@ -215,10 +218,10 @@ def test_unsupported_combinations_of_the_new_branches_are_rejected(emu):
     out = helpers._abi.OutBuffers(spec)
     assert emu.emu_bvaralg(C.byref(spec.c), C.byref(out.c)) == -7
     assert b"Wishart" in emu.emu_last_error()
-    # structural + SSVS: not built
+    # structural + SSVS without its prior arrays
     spec = helpers._abi.spec_from_model(helpers.model_structural(), n_chains=1)
     spec.c.varsel = helpers._abi.VARSEL_SSVS
-    assert emu.emu_bvaralg(C.byref(spec.c), C.byref(out.c)) == -5
+    assert emu.emu_bvaralg(C.byref(spec.c), C.byref(out.c)) == -4
     # structural TVP model together with the covariance block
     cov = helpers._abi.spec_from_model(helpers.model_tvp_covar(), n_chains=1)
     spec = helpers._abi.spec_from_model(helpers.model_structural(tvp=True, sv=True, nobs=24), n_chains=1)
