@@ -108,6 +108,57 @@ BVG_UNROLL
     for (int j = 0; j <= i; ++j) { Gp[tri(i) + j] = Gm[i][j]; Aip[tri(i) + j] = Ai[j][i]; }
 }
 
+// S = U U' with U upper (the Cholesky factorisation taken from the last column to the first); only the upper triangle of S
+// is read.  fail is set on a non-positive pivot.
+template <int K>
+BVG_HD void kron_upper_factor(const double (&S)[K][K], double (&U)[K][K], int& fail) {
+BVG_UNROLL
+  for (int j = K - 1; j >= 0; --j) {
+    double d = S[j][j];
+BVG_UNROLL
+    for (int c = j + 1; c < K; ++c) d = fma(-U[j][c], U[j][c], d);
+    if (!(d > 0.0)) fail = 1;
+    const double rs = bvg_rsqrt_fast(d);
+    U[j][j] = d * rs;
+BVG_UNROLL
+    for (int i = j - 1; i >= 0; --i) {
+      double v = S[i][j];
+BVG_UNROLL
+      for (int c = j + 1; c < K; ++c) v = fma(-U[i][c], U[j][c], v);
+      U[i][j] = v * rs;
+    }
+  }
+}
+// k = 3 and k = 2: the pivots of the sequential factorisation are ratios of trailing minors, t_11 = n11 / s22,
+// t_00 = det / n11, so the reciprocal square roots do not have to wait for one another: r22 = s22^-1/2, q11 = n11^-1/2,
+// q00 = det^-1/2 start together and U follows by products.  The state recursion is the sequential part of the sweep: its
+// latency, not its flop count, bounds launches with few chains per SM (c2-B, strong scaling).  The minors are formed with
+// the same cancellation as the Cholesky pivots themselves (s11 - s12^2 / s22 against (s11 s22 - s12^2) / s22): same
+// conditioning, results equal to rounding.
+BVG_HD void kron_upper_factor(const double (&S)[3][3], double (&U)[3][3], int& fail) {
+  const double s00 = S[0][0], s01 = S[0][1], s02 = S[0][2], s11 = S[1][1], s12 = S[1][2], s22 = S[2][2];
+  const double n11 = fma(s11, s22, -(s12 * s12));
+  const double c01 = fma(s01, s22, -(s02 * s12));
+  const double c02 = fma(s01, s12, -(s02 * s11));
+  const double det = fma(s02, c02, fma(s00, n11, -(s01 * c01)));
+  if (!(s22 > 0.0) || !(n11 > 0.0) || !(det > 0.0)) fail = 1;
+  const double r22 = bvg_rsqrt_fast(s22), q11 = bvg_rsqrt_fast(n11), q00 = bvg_rsqrt_fast(det);
+  U[2][2] = s22 * r22; U[1][2] = s12 * r22; U[0][2] = s02 * r22;
+  U[1][1] = (n11 * q11) * r22;
+  U[0][1] = c01 * (q11 * r22);
+  U[0][0] = (det * q00) * q11;
+  U[1][0] = 0.0; U[2][0] = 0.0; U[2][1] = 0.0;
+}
+BVG_HD void kron_upper_factor(const double (&S)[2][2], double (&U)[2][2], int& fail) {
+  const double s00 = S[0][0], s01 = S[0][1], s11 = S[1][1];
+  const double n00 = fma(s00, s11, -(s01 * s01));
+  if (!(s11 > 0.0) || !(n00 > 0.0)) fail = 1;
+  const double r11 = bvg_rsqrt_fast(s11), q00 = bvg_rsqrt_fast(n00);
+  U[1][1] = s11 * r11; U[0][1] = s01 * r11;
+  U[0][0] = (n00 * q00) * r11;
+  U[1][0] = 0.0;
+}
+
 // One step of the state recursion (the only state-dependent part of the sweep, a few dozen dependent FP64
 // operations): W (upper, registers) <- U(SS + W G W') Ai, with S = U U', U upper.  SSu: upper triangle of S0 + SSE.
 // fail is set on a non-positive pivot.
@@ -139,24 +190,9 @@ BVG_UNROLL
       for (int c = j; c < K; ++c) v = fma(H[i][c], W[j][c], v);
       S[i][j] = v;
     }
-  // S = U U', U upper: from the last column to the first
+  // S = U U', U upper
   double U[K][K];
-BVG_UNROLL
-  for (int j = K - 1; j >= 0; --j) {
-    double d = S[j][j];
-BVG_UNROLL
-    for (int c = j + 1; c < K; ++c) d = fma(-U[j][c], U[j][c], d);
-    if (!(d > 0.0)) fail = 1;
-    const double rs = bvg_rsqrt(d);
-    U[j][j] = d * rs;
-BVG_UNROLL
-    for (int i = j - 1; i >= 0; --i) {
-      double v = S[i][j];
-BVG_UNROLL
-      for (int c = j + 1; c < K; ++c) v = fma(-U[i][c], U[j][c], v);
-      U[i][j] = v * rs;
-    }
-  }
+  kron_upper_factor(S, U, fail);
   // W = U A_B^-1
 BVG_UNROLL
   for (int i = 0; i < K; ++i)

@@ -64,6 +64,23 @@ BVG_HD double bvg_rsqrt(double d) {
 #endif
 }
 
+// 1 / sqrt(d) for a positive NORMAL double, branch-free: the hardware seed (MUFU.RSQ64H, ~20 bits) and one third-order
+// step, y = y0 + y0 e (1/2 + 3/8 e), e = 1 - d y0^2 (error ~ e^3).  The library rsqrt() carries a range check and a
+// slow-path call behind a reconvergence barrier: independent calls do not overlap, and on the latency-bound state
+// recursion of the Kronecker sweep it was where the recursion warp spent its time (profiles/r02_c2a_512_*).  Zero /
+// negative / NaN arguments give inf / NaN; callers flag non-positive pivots themselves.
+BVG_HD double bvg_rsqrt_fast(double d) {
+#if defined(__CUDA_ARCH__)
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+  const double e = fma(-d, y0 * y0, 1.0);
+  const double p = fma(e, 0.375, 0.5);
+  return fma(p, y0 * e, y0);
+#else
+  return 1.0 / sqrt(d);
+#endif
+}
+
 // Same factorisation for n + 1 <= G <= 32: ONE row per lane (lane r owns row r, lane n owns the rhs row).  The
 // pivot is broadcast by shuffle instead of a shared-memory round trip, so a column costs one barrier.  The dot
 // product over the j already-final columns enters a 31-deep unrolled chain at depth j (switch with fall-through,
