@@ -185,6 +185,17 @@ extern "C" void emu_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
   out[0] = p.x; out[1] = p.y; out[2] = p.z; out[3] = p.w;
 }
 
+// FP64 transforms of the variate generators (host build of the same source): log, sqrt, sin / cos of 2 pi u, and the
+// uniform built from two Philox words
+extern "C" void emu_transforms(int n, const double* x, double* logx, double* sqrtx, double* s2pi, double* c2pi) {
+  for (int i = 0; i < n; ++i) {
+    logx[i] = bvg_logpos(x[i]);
+    sqrtx[i] = bvg_sqrtpos(x[i]);
+    bvg_sincos2pi(x[i], &s2pi[i], &c2pi[i]);
+  }
+}
+extern "C" double emu_u53(uint32_t hi, uint32_t lo) { return u53(hi, lo); }
+
 // ---- stand-alone building blocks: the same *_problem templates the CUDA kernels of bvg_blocks.cu instantiate,
 //      one problem at a time on the host (single-thread group), same argument lists as the bvg_* entry points
 static RngParams block_rp(uint64_t seed) {

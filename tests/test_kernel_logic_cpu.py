@@ -172,6 +172,51 @@ def test_philox_known_answer(emu):
     assert list(out) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
 
 
+def test_variate_transform_arithmetic(emu):
+    """Range-specific log / sin-cos polynomials of bvg_common.cuh against libm (host build: the device replaces the
+    division / sqrt by MUFU seeds + Newton steps, covered by the device-vs-emulator test), the uniform construction, and
+    the committed coefficient tables against tools/fit_variate_polys.py."""
+    rng = np.random.default_rng(3)
+    u = np.concatenate([rng.random(200000), np.ldexp(rng.random(2000), -rng.integers(1, 52, 2000)),
+                        1.0 - np.ldexp(rng.random(2000), -rng.integers(1, 50, 2000))])
+    u = u[(u > 0) & (u < 1)]
+    n = u.shape[0]
+    outs = [np.empty(n) for _ in range(4)]
+    dp = C.POINTER(C.c_double)
+    emu.emu_transforms.argtypes = [C.c_int] + [dp] * 5
+    emu.emu_transforms(n, u.ctypes.data_as(dp), *[o.ctypes.data_as(dp) for o in outs])
+    lg, sq, sn, cs = outs
+    assert np.max(np.abs(lg - np.log(u)) / np.abs(np.log(u))) < 4.5e-16
+    assert np.max(np.abs(sq - np.sqrt(u)) / np.sqrt(u)) < 2.3e-16
+    assert np.max(np.abs(sn - np.sin(2 * np.pi * u))) < 1.5e-15 and np.max(np.abs(cs - np.cos(2 * np.pi * u))) < 1.5e-15
+    assert np.max(np.abs(sn * sn + cs * cs - 1.0)) < 5e-16
+    big = np.array([3.0, 75.0, 1e-30, 5e10])
+    outs = [np.empty(4) for _ in range(4)]
+    emu.emu_transforms(4, big.ctypes.data_as(dp), *[o.ctypes.data_as(dp) for o in outs])
+    assert np.max(np.abs(outs[0] - np.log(big)) / np.abs(np.log(big))) < 4.5e-16
+    emu.emu_u53.restype = C.c_double
+    emu.emu_u53.argtypes = [C.c_uint32, C.c_uint32]
+    assert emu.emu_u53(0, 0) == 2.0 ** -53 and emu.emu_u53(0xffffffff, 0xffffffff) == 1.0 - 2.0 ** -53
+    assert emu.emu_u53(0x80000000, 0) == 0.5 + 2.0 ** -53
+    # tables in the header == the fit script (first 12 significant digits: the fit is deterministic, the header is a paste)
+    import importlib.util
+    import pathlib
+    import re
+    root = pathlib.Path(__file__).resolve().parents[1]
+    hdr = (root / "bvartools_b200" / "csrc" / "bvg_common.cuh").read_text()
+    spec = importlib.util.spec_from_file_location("fit_variate_polys", root / "tools" / "fit_variate_polys.py")
+    fit = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fit)
+    mp = fit.mp
+    zmax = (mp.pi / 4) ** 2
+    want = {"kSinTab": fit.cheb_fit(lambda z: mp.sin(mp.sqrt(z)) / mp.sqrt(z) if z > 0 else mp.mpf(1), mp.mpf(0), zmax, 6),
+            "kCosTab": fit.cheb_fit(lambda z: mp.cos(mp.sqrt(z)), mp.mpf(0), zmax, 7)}
+    for name, coef in want.items():
+        m = re.search(r"BVG_TABLE\(" + name + r",\s*\d+,([^)]*)\)", hdr)
+        got = [float(v) for v in m.group(1).replace("\n", " ").split(",")]
+        np.testing.assert_allclose(got[:len(coef)], [float(c) for c in coef], rtol=1e-12)
+
+
 def test_variate_transforms_are_distributionally_right(emu):
     """Box-Muller normals, uniforms, Marsaglia-Tsang gammas / chi-squares from the Philox stream: KS tests."""
     from scipy import stats
