@@ -15,15 +15,14 @@
 //              chain and array is ~30 instructions of address set-up + R2UR per 0.7 KB, slower than the stores;
 //   warps 2 + 2 j, 3 + 2 j   the variates of chunk j, one lane per record, FIXED for the whole launch: chain id, Philox
 //              counter words and record address are computed once; a round is a uniform loop over variate SLOTS (Philox
-//              counter word, block, the two destinations of a Box-Muller pair), four slots in flight per lane:
+//              counter word, block, the two destinations of a Box-Muller pair), three slots in flight per lane:
 //              Philox4x32-10 with constant-bank round keys + the FP64 transforms of bvg_common.cuh.  The A warp draws
 //              the first SA slots; the B warp the rest and, after a 64-thread named barrier with A, the Bartlett
 //              diagonal (Marsaglia-Tsang, constants precomputed, the attempt-0 test inline, rejections through the
-//              generic generator) and the state-independent products of the chunk (G = E E', A_B^-1, T = E L_X^-1).
+//              generic generator; a rolled loop: code size counts, the generators stall on instruction fetch) and the state-independent products of the chunk (G = E E', A_B^-1, T = E L_X^-1).
 // Rounds are pipelined over three record generations: the generators run up to two rounds ahead of the recursion.  All
 // cross-role hand-offs are mbarriers in shared memory (arrive = release, try_wait = acquire, waiting warps are parked by
 // the hardware); there is no CTA-wide barrier after the set-up.  HBM sees only the draws.
-#include <type_traits>
 #include "bvg_kernels.cuh"
 #include "bvg_kron_sweep.cuh"
 
@@ -31,6 +30,9 @@ namespace bvg {
 
 #ifndef BVG_KRON_MINB
 #define BVG_KRON_MINB 1
+#endif
+#ifndef BVG_KRON_NG
+#define BVG_KRON_NG 3      // Box-Muller slots in flight per generator lane (measured 1, 2, 3, 4, 6: see the generator loop)
 #endif
 struct KronPlanDims {
   int CH;      // chains per CTA
@@ -296,7 +298,9 @@ __global__ void __launch_bounds__(512, BVG_KRON_MINB) bvar_kron_batch_kernel(
 
   // ================= variates and state-independent products of chunk j: lane = record =================
   const int j = (warp - 2) >> 1;
-  const bool isB = (warp & 1) != 0;
+  // A (11 slots of pure Box-Muller) is the FP64-heavier role: alternate which warp of the pair takes it so that every
+  // scheduler (warp id mod 4) hosts as many A as B warps
+  const bool isB = (((warp & 1) != 0) != (((j >> 1) & 1) != 0));
   if (j * CPC >= CHv) return;                                  // (both warps of an empty chunk)
   int c = j * CPC + lane / NB;
   const int sw_l = lane & (NB - 1);
@@ -341,14 +345,18 @@ __global__ void __launch_bounds__(512, BVG_KRON_MINB) bvar_kron_batch_kernel(
         }
       }
     } else {
-      // NG slots in flight per lane: NG independent Philox / log / sincos dependency chains
-      auto group = [&](auto ng_tag, int s) {
-        constexpr int NG = decltype(ng_tag)::value;
+      // NG slots in flight per lane: NG independent Philox / log / sincos dependency chains.  One group size only (the
+      // last group of a warp repeats its last slot): the 4 / 2 / 1 ladder that avoided the repeat tripled the code of the
+      // loop and cost more in instruction-cache misses (12 % of the generators' stall samples) than the repeat does.
+      // Measured on c2-A (ms per step): NG = 1: 5.49, 2: 5.45, 3: 5.41, 4: 5.58, 6: 6.78; an out-of-line slot function
+      // (smallest code, pointers through the generic address space): 7.0
+      constexpr int NG = BVG_KRON_NG;
+      for (int s = sb; s < se; s += NG) {
         int4 d[NG];
         Philox4 ph[NG];
 #pragma unroll
         for (int i = 0; i < NG; ++i) {
-          d[i] = slot_of(s + i);
+          d[i] = slot_of((s + i < se) ? s + i : se - 1);
           ph[i] = philox_rk((uint32_t)d[i].x, (uint32_t)sweep, c2, c3 ^ (uint32_t)d[i].y, pd.rk);
         }
         double za[NG], zb[NG];
@@ -356,48 +364,38 @@ __global__ void __launch_bounds__(512, BVG_KRON_MINB) bvar_kron_batch_kernel(
         for (int i = 0; i < NG; ++i) bvg_box_muller(u53(ph[i].x, ph[i].y), u53(ph[i].z, ph[i].w), &za[i], &zb[i]);
 #pragma unroll
         for (int i = 0; i < NG; ++i) { rec[d[i].z] = za[i]; rec[d[i].w] = zb[i]; }
-      };
-      int s = sb;
-      for (; s + 4 <= se; s += 4) group(std::integral_constant<int, 4>(), s);
-      if (s + 2 <= se) { group(std::integral_constant<int, 2>(), s); s += 2; }
-      if (s < se) group(std::integral_constant<int, 1>(), s);
+      }
     }
     __threadfence_block();
     asm volatile("bar.sync %0, 64;" ::"r"(1 + j) : "memory");  // the chunk's normals are complete (A and B)
     if (isB) {
-      // ---- Bartlett diagonal: sqrt(chi2(df - i)), i < K
-      double chi[K];
-      if (inj_chi) {
-#pragma unroll
-        for (int i = 0; i < K; ++i)
-          chi[i] = sqrt(rp.inj[VB_WISH_C][(size_t)(chain0 + c) * (size_t)rp.inj_chain_stride[VB_WISH_C] +
-                                          (size_t)sweep * (size_t)rp.inj_stride[VB_WISH_C] + i]);
-      } else {
-        Philox4 pu[K];
-#pragma unroll
-        for (int i = 0; i < K; ++i)
-          pu[i] = philox_rk((uint32_t)i | (100u << 24), (uint32_t)sweep, c2, c3 ^ ((uint32_t)VB_WISH_C << 24), pd.rk);
-        double g[K], x0[K];
-        bool ok[K];
-#pragma unroll
-        for (int i = 0; i < K; ++i) {                           // acceptance test of attempt 0, branch-free
-          const double d = mt[2 * i], cc = mt[2 * i + 1], x = rec[o_x0 + i];
-          const double u = u53(pu[i].x, pu[i].y);
-          const double v1 = fma(cc, x, 1.0), v = v1 * v1 * v1, x2 = x * x;
-          const double vs = (v1 > 0.0) ? v : 1.0;
-          ok[i] = (v1 > 0.0) && (d > 2.0 / 3.0) &&
-                  ((u < 1.0 - 0.0331 * x2 * x2) || (bvg_logpos(u) < 0.5 * x2 + d - d * v + d * bvg_logpos(vs)));
-          g[i] = d * v;
-          x0[i] = x;
-        }
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-          if (!ok[i]) g[i] = philox_gamma_from_x0(rp.seed, chain, VB_WISH_C, sweep, i, 0.5 * (m.wish_df_post - (double)i), x0[i]);
-          chi[i] = bvg_sqrtpos(2.0 * g[i]);
-        }
-      }
-      __syncwarp();                                            // (lanes repeating a record have read its x0 too)
+      // ---- Bartlett diagonal: sqrt(chi2(df - i)), i < K, in place over the attempt-0 normals.  Rolled loop: the body
+      //      (Philox, two logs, the rare rejection call) is ~300 instructions, and instruction fetch is what the generator
+      //      warps stall on next to the FP64 pipe (lanes that repeat a record skip the whole block)
       if (!dup) {
+#pragma unroll 1
+        for (int i = 0; i < K; ++i) {
+          double ch;
+          if (inj_chi) {
+            ch = sqrt(rp.inj[VB_WISH_C][(size_t)(chain0 + c) * (size_t)rp.inj_chain_stride[VB_WISH_C] +
+                                        (size_t)sweep * (size_t)rp.inj_stride[VB_WISH_C] + i]);
+          } else {
+            const Philox4 pu = philox_rk((uint32_t)i | (100u << 24), (uint32_t)sweep, c2, c3 ^ ((uint32_t)VB_WISH_C << 24), pd.rk);
+            const double d = mt[2 * i], cc = mt[2 * i + 1], x = rec[o_x0 + i];
+            const double u = u53(pu.x, pu.y);
+            const double v1 = fma(cc, x, 1.0), v = v1 * v1 * v1, x2 = x * x;
+            const double vs = (v1 > 0.0) ? v : 1.0;
+            const bool ok = (v1 > 0.0) && (d > 2.0 / 3.0) &&
+                            ((u < 1.0 - 0.0331 * x2 * x2) || (bvg_logpos(u) < 0.5 * x2 + d - d * v + d * bvg_logpos(vs)));
+            double g = d * v;
+            if (!ok) g = philox_gamma_from_x0(rp.seed, chain, VB_WISH_C, sweep, i, 0.5 * (m.wish_df_post - (double)i), x);
+            ch = bvg_sqrtpos(2.0 * g);
+          }
+          rec[o_x0 + i] = ch;
+        }
+        double chi[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) chi[i] = rec[o_x0 + i];
         double wn[NW > 0 ? NW : 1];
 #pragma unroll
         for (int i = 0; i < NW; ++i) wn[i] = rec[o_wn + i];
@@ -440,6 +438,7 @@ static void kron_dims(int k, int M, int CH, int NB, KronPlanDims* pd) {
   // slots' worth of instructions) and prepares the chunk (about two)
   const int nsl = (n + 1) / 2 + (NW + 1) / 2 + (k + 1) / 2;
   int sa = (nsl + 7 + 1) / 2;               // B: its slots + ~7 slots' worth of extra work (measured: c2-A, SA = 10..14)
+  sa = ((sa + BVG_KRON_NG - 1) / BVG_KRON_NG) * BVG_KRON_NG;   // whole groups on A (a partial group repeats a slot)
   if (sa > nsl) sa = nsl;
   pd->SA = sa;
 }
