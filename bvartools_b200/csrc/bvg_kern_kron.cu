@@ -5,7 +5,8 @@
 // the variates / products of one sweep of one chain, in shared memory) are split into CHUNKS of 32 records (32 / NB
 // chains x NB sweeps), and the warps have fixed roles:
 //   warp 0     the state recursion W <- U(S0 + SSE + W E E' W') A_B^-1, one LANE per chain with W in registers:
-//              latency-bound (~150 dependent instructions per sweep, three rsqrt chains), so nothing else runs on it; the
+//              latency-bound (~150 instructions per sweep; k <= 3: the reciprocal square roots of the k x k factor start
+//              together, branch-free), so nothing else runs on it; the
 //              W a sweep starts from and ends with are left in its record (over the G / A_B^-1 slots just consumed);
 //   warp 1     one round behind: the retained draws a = vec(A_ols + W T), Sigma = W W', one lane per record, written
 //              straight to the [chain][iter][row] output (consecutive lanes = consecutive sweeps of a chain = consecutive
@@ -19,7 +20,9 @@
 //              Philox4x32-10 with constant-bank round keys + the FP64 transforms of bvg_common.cuh.  The A warp draws
 //              the first SA slots; the B warp the rest and, after a 64-thread named barrier with A, the Bartlett
 //              diagonal (Marsaglia-Tsang, constants precomputed, the attempt-0 test inline, rejections through the
-//              generic generator; a rolled loop: code size counts, the generators stall on instruction fetch) and the state-independent products of the chunk (G = E E', A_B^-1, T = E L_X^-1).
+//              generic generator; a rolled loop: code size counts, the generators stall on instruction fetch) and the
+//              state-independent products of the chunk (G = E E', A_B^-1, T = E L_X^-1).  Which warp of a pair is A
+//              alternates so that every scheduler hosts as many A as B warps.
 // Rounds are pipelined over three record generations: the generators run up to two rounds ahead of the recursion.  All
 // cross-role hand-offs are mbarriers in shared memory (arrive = release, try_wait = acquire, waiting warps are parked by
 // the hardware); there is no CTA-wide barrier after the set-up.  HBM sees only the draws.
