@@ -55,21 +55,14 @@ BVG_HD void chol_crout_generic(const Grp& g, double* L, double* dinv, double* b,
   }
 }
 
-// 1/sqrt(d): the device uses the FP64 rsqrt sequence (a few ulp, far inside the 1e-10 parity bar)
+// 1 / sqrt(d) for the pivots of the Cholesky factorisations, branch-free: the hardware seed (MUFU.RSQ64H, ~20 bits) and
+// one third-order step, y = y0 + y0 e (1/2 + 3/8 e), e = 1 - d y0^2 (error ~ e^3: a few ulp, far inside the 1e-10 parity
+// bar).  The library rsqrt() carries a range check and a slow-path call behind a reconvergence barrier: ~74 cycles of
+// dependent latency against ~50 here, on every pivot of every chain, and independent calls do not overlap (on the
+// latency-bound state recursion of the Kronecker sweep it was where the recursion warp spent its time,
+// profiles/r02_c2a_512_*).  Pivots of an SPD matrix are positive normal numbers; zero / negative / NaN arguments give
+// inf / NaN, and every caller flags non-positive pivots itself.
 BVG_HD double bvg_rsqrt(double d) {
-#if defined(__CUDA_ARCH__)
-  return rsqrt(d);
-#else
-  return 1.0 / sqrt(d);
-#endif
-}
-
-// 1 / sqrt(d) for a positive NORMAL double, branch-free: the hardware seed (MUFU.RSQ64H, ~20 bits) and one third-order
-// step, y = y0 + y0 e (1/2 + 3/8 e), e = 1 - d y0^2 (error ~ e^3).  The library rsqrt() carries a range check and a
-// slow-path call behind a reconvergence barrier: independent calls do not overlap, and on the latency-bound state
-// recursion of the Kronecker sweep it was where the recursion warp spent its time (profiles/r02_c2a_512_*).  Zero /
-// negative / NaN arguments give inf / NaN; callers flag non-positive pivots themselves.
-BVG_HD double bvg_rsqrt_fast(double d) {
 #if defined(__CUDA_ARCH__)
   double y0;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
@@ -80,6 +73,7 @@ BVG_HD double bvg_rsqrt_fast(double d) {
   return 1.0 / sqrt(d);
 #endif
 }
+BVG_HD double bvg_rsqrt_fast(double d) { return bvg_rsqrt(d); }
 
 // Same factorisation for n + 1 <= G <= 32: ONE row per lane (lane r owns row r, lane n owns the rhs row).  The
 // pivot is broadcast by shuffle instead of a shared-memory round trip, so a column costs one barrier.  The dot

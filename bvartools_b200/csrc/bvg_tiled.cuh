@@ -17,6 +17,7 @@
 // Reference call sites: arma::chol + arma::solve in bvaralg.cpp:306-307.
 #pragma once
 #include "bvg_group.cuh"
+#include "bvg_linalg.cuh"
 
 namespace bvg {
 
@@ -61,7 +62,7 @@ __device__ __forceinline__ void tiled_factor_invert(double* D, int& fail) {
   for (int j = 0; j < 8; ++j) {
     const double d = L[j][j];
     bad = bad || !(d > 0.0);
-    const double rs = rsqrt(d);
+    const double rs = bvg_rsqrt(d);
     rsv[j] = rs;
 #pragma unroll
     for (int i = j + 1; i < 8; ++i) L[i][j] *= rs;
