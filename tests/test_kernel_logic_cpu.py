@@ -51,6 +51,17 @@ CASES["kron_k2"] = (lambda: _grid_model(2, K=2), {})
 CASES["kron_k1"] = (lambda: _grid_model(3, K=1), {})
 
 
+def _kron_k4(p):
+    """Four variables (synthetic): the generic k x k factor of the state recursion, and the M = 2 k + 1 / run-time-M paths."""
+    y = helpers.synth_var(4, 2, 90, 31)
+    m = helpers.gen_var(y, p=p, deterministic="const", iterations=20, burnin=5)
+    return helpers.add_priors(m, coef=dict(v_i=0, v_i_det=0), sigma=dict(df="k", scale=1e-3))
+
+
+CASES["kron_k4_p2"] = (lambda: _kron_k4(2), {})
+CASES["kron_k4_p5"] = (lambda: _kron_k4(5), {})
+
+
 def _tvp_wishart():
     y = helpers.synth_var(2, 1, 28, 11)
     m = helpers.gen_var(y, p=1, deterministic="const", iterations=8, burnin=3, tvp=True)
