@@ -108,7 +108,7 @@ static void rows_of(const Prepared& P, long long* coef, long long* sigma, long l
 
 extern "C" {
 
-const char* bvg_version(void) { return "bvargpu 0.1.0 (sm_100a, abi 1)"; }
+const char* bvg_version(void) { return "bvargpu 0.2.0 (sm_100a, abi 2)"; }
 const char* bvg_last_error(void) { return g_last_error.c_str(); }
 
 int bvg_device_count(void) {
