@@ -135,6 +135,20 @@ def test_chunking_and_layout_invariance_philox(gpu):
         assert np.array_equal(ref.arrays[key], exact.arrays[key]), key
 
 
+@pytest.mark.parametrize("chains", [5, 37, 300])
+def test_kronecker_kernel_chunking_is_bit_identical(gpu, chains):
+    """Flat-prior Kronecker kernel (fixed warp roles, three record generations): launches of 7, 33 and all sweeps give the
+    same draws bit for bit -- rounds restart at every launch (tail rounds, chunks with repeated lanes), the chain state
+    W crosses launches, the Philox sites are sweep-addressed.  300 chains = 3 chains per CTA on a 148-SM part."""
+    obj = helpers.model_c1(iterations=70, burnin=21)
+    ref = _run(gpu, obj, chains, seed=7)
+    for spl in (7, 33):
+        other = _run(gpu, obj, chains, seed=7, sweeps_per_launch=spl)
+        for key in ref.arrays:
+            assert np.array_equal(ref.arrays[key], other.arrays[key]), (chains, spl, key)
+    assert not ref.status.any()
+
+
 @pytest.mark.parametrize("case", ["c3_cta_tiled", "tvp_warp_tiled", "large"])
 def test_run_to_run_determinism_of_the_tile_kernels(gpu, case):
     """Same seed, same launch shape => bit-identical draws on repeated runs (compute-sanitizer is not available on the
